@@ -1,0 +1,336 @@
+"""arborx_b200 -- host-side mirror of the ArborX interface for the hot path
+(BoundingVolumeHierarchy, query with intersects/nearest predicates, dbscan) over
+the C ABI of libabx.so (include/abx.h).  torch is used only for device memory and
+streams.  Spellings follow the reference:
+
+    bvh = BoundingVolumeHierarchy(space, points)            # ArborX_LinearBVH.hpp:68-73
+    indices, offsets = bvh.query(space, make_intersects(q, r))   # :90-110
+    indices, offsets = bvh.query(space, make_nearest(q, k))
+    labels = dbscan(space, points, eps, minpts, DBSCANParameters())  # ArborX_DBSCAN.hpp:219-223
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import SearchException, lib
+
+POINT, BOX, TRIANGLE = 0, 1, 2            # primitive kinds (ABX_PRIM_*)
+SPHERE_PRED, BOX_PRED, POINT_PRED = 0, 1, 2  # predicate geometries (ABX_PRED_*)
+_PRIM_STRIDE = {POINT: 3, BOX: 6, TRIANGLE: 9}
+_PRED_STRIDE = {SPHERE_PRED: 4, BOX_PRED: 6, POINT_PRED: 3}
+
+__all__ = ["ExecutionSpace", "BoundingVolumeHierarchy", "BVH", "TraversalPolicy", "intersects", "nearest",
+           "make_intersects", "make_nearest", "query", "dbscan", "DBSCANParameters", "SearchException",
+           "POINT", "BOX", "TRIANGLE", "launch_count"]
+
+
+class ExecutionSpace:
+    """Execution space instance = a CUDA stream; every kernel of a call is enqueued on it
+    (reference: the `space` argument of every API, tstKokkosToolsExecutionSpaceInstances.cpp:80-153)."""
+
+    def __init__(self, stream=None, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("arborx_b200 needs a CUDA device (no CPU fallback)")
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.stream = stream if stream is not None else torch.cuda.current_stream(self.device)
+
+    @property
+    def handle(self):
+        return C.c_void_p(self.stream.cuda_stream)
+
+    def fence(self):
+        self.stream.synchronize()
+
+
+class TraversalPolicy:
+    """Experimental::TraversalPolicy (detail/ArborX_TraversalPolicy.hpp:19-48)."""
+
+    def __init__(self, buffer_size=0, sort_predicates=True):
+        self._buffer_size = buffer_size
+        self._sort_predicates = sort_predicates
+
+    def setBufferSize(self, b):
+        self._buffer_size = b
+        return self
+
+    def setPredicateSorting(self, s):
+        self._sort_predicates = s
+        return self
+
+    def _c(self):
+        return _lib.AbxPolicy(int(self._buffer_size), int(bool(self._sort_predicates)))
+
+
+class Predicates:
+    def __init__(self, tag, kind, data, k=None):
+        self.tag = tag      # "spatial" | "nearest"
+        self.kind = kind
+        self.data = data    # float32 [q, stride], device or host tensor
+        self.k = k
+
+    def size(self):
+        return self.data.shape[0]
+
+
+def _as_f32(t, stride):
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(t, dtype=torch.float32)
+    t = t.to(torch.float32).reshape(-1, stride).contiguous()
+    return t
+
+
+def intersects(geometry, kind=None):
+    """intersects(Sphere|Box|Point) for a batch (detail/ArborX_Predicates.hpp:130-147):
+    [q,4] spheres (centre, radius), [q,6] boxes or [q,3] points."""
+    if not isinstance(geometry, torch.Tensor):
+        geometry = torch.as_tensor(geometry, dtype=torch.float32)
+    if kind is None:
+        kind = {4: SPHERE_PRED, 6: BOX_PRED, 3: POINT_PRED}[geometry.shape[-1]]
+    return Predicates("spatial", kind, _as_f32(geometry, _PRED_STRIDE[kind]))
+
+
+def nearest(points, k=1):
+    """nearest(Point, k) for a batch (Predicates.hpp:221-238); k may be a tensor of per-query k."""
+    return Predicates("nearest", POINT_PRED, _as_f32(points, 3), k)
+
+
+def make_intersects(points, r):
+    """Experimental::make_intersects(points, r): spheres of radius r (detail/ArborX_PredicateHelpers.hpp:93-105)."""
+    p = _as_f32(points, 3)
+    rr = torch.full((p.shape[0], 1), float(r), dtype=torch.float32, device=p.device)
+    return Predicates("spatial", SPHERE_PRED, torch.cat([p, rr], 1).contiguous())
+
+
+def make_nearest(points, k):
+    """Experimental::make_nearest(points, k) (PredicateHelpers.hpp:107-119)."""
+    return nearest(points, k)
+
+
+class _Allocator:
+    """abx_alloc_fn backed by torch tensors (the library 'resizes the caller's views')."""
+    _DT = {0: torch.int32, 1: torch.int32, 2: torch.float32}
+
+    def __init__(self, device, pinned_host=False):
+        self.device = device
+        self.pinned_host = pinned_host
+        self.out = {}
+        self.fn = _lib.ALLOC_FN(self._alloc)
+
+    def _alloc(self, user, which, nbytes):
+        n = nbytes // 4
+        if self.pinned_host:
+            t = torch.empty(n, dtype=self._DT[which], pin_memory=True)
+        else:
+            t = torch.empty(n, dtype=self._DT[which], device=self.device)
+        self.out[which] = t
+        return t.data_ptr() if n else None
+
+
+class BoundingVolumeHierarchy:
+    """ArborX::BoundingVolumeHierarchy (spatial/ArborX_LinearBVH.hpp:50-142): leaf value = index of the primitive."""
+
+    def __init__(self, space, values, kind=None):
+        if not isinstance(values, torch.Tensor):
+            values = torch.as_tensor(values, dtype=torch.float32)
+        if kind is None:
+            kind = {3: POINT, 6: BOX, 9: TRIANGLE}[values.shape[-1]] if values.dim() == 2 else POINT
+        self.kind = kind
+        self._space = space
+        v = _as_f32(values, _PRIM_STRIDE[kind])
+        h = C.c_void_p()
+        with torch.cuda.stream(space.stream):
+            if v.is_cuda:
+                _lib.check(lib().abx_bvh_build(space.handle, kind, C.c_void_p(v.data_ptr()), v.shape[0], C.byref(h)))
+            else:
+                _lib.check(lib().abx_bvh_build_host(space.handle, kind, C.c_void_p(v.data_ptr()), v.shape[0],
+                                                    C.byref(h)))
+        self._values = v  # keep the input alive until the build has been enqueued and run
+        self._h = h
+
+    @classmethod
+    def _from_sorted_codes(cls, space, values, codes, kind):
+        self = cls.__new__(cls)
+        self.kind = kind
+        self._space = space
+        v = _as_f32(values, _PRIM_STRIDE[kind]).to(space.device)
+        c = codes.to(space.device).contiguous()
+        h = C.c_void_p()
+        with torch.cuda.stream(space.stream):
+            _lib.check(lib().abx_bvh_build_from_sorted_codes(space.handle, kind, C.c_void_p(v.data_ptr()),
+                                                             C.c_void_p(c.data_ptr()), v.shape[0], C.byref(h)))
+        space.fence()
+        self._values = v
+        self._h = h
+        return self
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                lib().abx_bvh_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def size(self):
+        return lib().abx_bvh_size(self._h)
+
+    def empty(self):
+        return bool(lib().abx_bvh_empty(self._h))
+
+    def bounds(self):
+        out = (C.c_float * 6)()
+        _lib.check(lib().abx_bvh_bounds(self._h, out))
+        return torch.tensor(list(out), dtype=torch.float32)
+
+    def memory_bytes(self):
+        return lib().abx_bvh_memory_bytes(self._h)
+
+    def query(self, space, predicates, policy=None, return_distances=False):
+        """query(space, predicates, indices, offsets[, policy]) -> (indices, offsets[, distances]).
+        Device predicates give device results; host (CPU tensor) predicates run the host-buffer
+        entry points and give pinned host results (the end-to-end path)."""
+        pol = (policy or TraversalPolicy())._c()
+        d = predicates.data
+        q = d.shape[0]
+        host = not d.is_cuda
+        alloc = _Allocator(space.device, pinned_host=host)
+        off, idx, dist = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        nnz = C.c_int64()
+        L = lib()
+        with torch.cuda.stream(space.stream):
+            if predicates.tag == "spatial":
+                fn = L.abx_query_spatial_crs_host if host else L.abx_query_spatial_crs
+                _lib.check(fn(self._h, space.handle, predicates.kind, C.c_void_p(d.data_ptr()), q, C.byref(pol),
+                              alloc.fn, None, C.byref(off), C.byref(idx), C.byref(nnz)))
+            else:
+                k = predicates.k
+                want_d = C.byref(dist) if return_distances else None
+                if isinstance(k, torch.Tensor):
+                    if host:
+                        raise ValueError("per-query k needs device predicates")
+                    kk = k.to(device=space.device, dtype=torch.int32).contiguous()
+                    _lib.check(L.abx_query_nearest_crs(self._h, space.handle, C.c_void_p(d.data_ptr()), q, 0,
+                                                       C.c_void_p(kk.data_ptr()), C.byref(pol), alloc.fn, None,
+                                                       C.byref(off), C.byref(idx), want_d, C.byref(nnz)))
+                elif host:
+                    _lib.check(L.abx_query_nearest_crs_host(self._h, space.handle, C.c_void_p(d.data_ptr()), q, int(k),
+                                                            C.byref(pol), alloc.fn, None, C.byref(off), C.byref(idx),
+                                                            want_d, C.byref(nnz)))
+                else:
+                    _lib.check(L.abx_query_nearest_crs(self._h, space.handle, C.c_void_p(d.data_ptr()), q, int(k),
+                                                       None, C.byref(pol), alloc.fn, None, C.byref(off), C.byref(idx),
+                                                       want_d, C.byref(nnz)))
+        dev = "cpu" if host else space.device
+        indices = alloc.out.get(1, torch.empty(0, dtype=torch.int32, device=dev))
+        offsets = alloc.out[0]
+        if return_distances:
+            return indices, offsets, alloc.out.get(2, torch.empty(0, dtype=torch.float32, device=dev))
+        return indices, offsets
+
+    def count(self, space, predicates, limit=0, sort_predicates=True):
+        """query(space, predicates, callback) with a counting callback (optionally CountUpToN)."""
+        d = predicates.data.to(space.device)
+        counts = torch.empty(d.shape[0], dtype=torch.int32, device=space.device)
+        with torch.cuda.stream(space.stream):
+            _lib.check(lib().abx_query_spatial_count(self._h, space.handle, predicates.kind, C.c_void_p(d.data_ptr()),
+                                                     d.shape[0], int(sort_predicates), int(limit),
+                                                     C.c_void_p(counts.data_ptr())))
+        return counts
+
+    def export_reference_layout(self, space):
+        n = self.size()
+        m = max(n - 1, 0)
+        dev = space.device
+        out = dict(leaf_rope=torch.empty(n, dtype=torch.int32, device=dev),
+                   leaf_index=torch.empty(n, dtype=torch.int32, device=dev),
+                   left_child=torch.empty(m, dtype=torch.int32, device=dev),
+                   rope=torch.empty(m, dtype=torch.int32, device=dev),
+                   boxes=torch.empty((m, 6), dtype=torch.float32, device=dev),
+                   codes=torch.empty(n, dtype=torch.int64, device=dev))
+        with torch.cuda.stream(space.stream):
+            _lib.check(lib().abx_bvh_export_reference_layout(
+                self._h, space.handle, *[C.c_void_p(out[k].data_ptr()) for k in
+                                         ("leaf_rope", "leaf_index", "left_child", "rope", "boxes", "codes")]))
+        space.fence()
+        return out
+
+    def half_traversal_pairs(self, space, r):
+        cnt = C.c_int64()
+        with torch.cuda.stream(space.stream):
+            _lib.check(lib().abx_half_traversal_pairs(self._h, space.handle, float(r), None, 0, C.byref(cnt)))
+            pairs = torch.empty((cnt.value, 2), dtype=torch.int32, device=space.device)
+            _lib.check(lib().abx_half_traversal_pairs(self._h, space.handle, float(r), C.c_void_p(pairs.data_ptr()),
+                                                      cnt.value, C.byref(cnt)))
+        return pairs
+
+
+BVH = BoundingVolumeHierarchy
+
+
+def query(tree, space, predicates, policy=None, **kw):
+    """ArborX::query free function (spatial/ArborX_CrsGraphWrapper.hpp:22-35)."""
+    return tree.query(space, predicates, policy, **kw)
+
+
+class DBSCANParameters:
+    """DBSCAN::Parameters (cluster/ArborX_DBSCAN.hpp:192-216); default implementation FDBSCAN_DenseBox."""
+    FDBSCAN, FDBSCAN_DenseBox = 0, 1
+    DBSCAN, DBSCAN_STAR = 0, 1
+
+    def __init__(self, implementation=1, algorithm=0, verbose=False):
+        self._implementation = implementation
+        self._algorithm = algorithm
+        self._verbose = verbose
+
+    def setImplementation(self, impl):
+        self._implementation = impl
+        return self
+
+    def setAlgorithm(self, algo):
+        self._algorithm = algo
+        return self
+
+    def setVerbosity(self, v):
+        self._verbose = v
+        return self
+
+
+def dbscan(space, primitives, eps, core_min_size, parameters=None):
+    """ArborX::dbscan(space, primitives, eps, core_min_size, labels, parameters) -> labels (int32)."""
+    p = parameters or DBSCANParameters()
+    x = _as_f32(primitives, 3)
+    n = x.shape[0]
+    L = lib()
+    with torch.cuda.stream(space.stream):
+        if x.is_cuda:
+            labels = torch.empty(n, dtype=torch.int32, device=space.device)
+            _lib.check(L.abx_dbscan(space.handle, C.c_void_p(x.data_ptr()), n, float(eps), int(core_min_size),
+                                    p._implementation, p._algorithm, C.c_void_p(labels.data_ptr())))
+        else:
+            labels = torch.empty(n, dtype=torch.int32, pin_memory=n > 0)
+            _lib.check(L.abx_dbscan_host(space.handle, C.c_void_p(x.data_ptr()), n, float(eps), int(core_min_size),
+                                         p._implementation, p._algorithm, C.c_void_p(labels.data_ptr())))
+    return labels
+
+
+def launch_count():
+    return lib().abx_launch_count()
+
+
+def profile_enable(on=True):
+    """Start/stop per-kernel CUDA-event timing inside the library."""
+    _lib.check(lib().abx_profile_enable(int(bool(on))))
+
+
+def profile_report():
+    """-> list of (kernel name, launches, total_ms), most expensive first."""
+    need = lib().abx_profile_report(None, 0)
+    buf = C.create_string_buffer(int(need) + 16)
+    lib().abx_profile_report(buf, len(buf))
+    rows = []
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.rsplit("\t", 2)
+        rows.append((name, int(cnt), float(ms)))
+    return rows

@@ -1,0 +1,89 @@
+"""ctypes binding of libabx.so (include/abx.h).  No CPU fallback: if the shared
+library is missing the import fails, and every compute entry point fails with
+ABX_ERR_CUDA when there is no CUDA device."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libabx.so")
+
+ABX_OK, ABX_ERR_SEARCH, ABX_ERR_CUDA, ABX_ERR_PRECISION, ABX_ERR_ARG = 0, 1, 2, 3, 4
+
+
+class SearchException(Exception):
+    """Mirror of ArborX::SearchException (misc/ArborX_Exception.hpp:19-38)."""
+
+
+class AbxPolicy(C.Structure):
+    _fields_ = [("buffer_size", C.c_int32), ("sort_predicates", C.c_int32)]
+
+
+ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_int, C.c_size_t)
+
+_vp, _i32, _i64, _f = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+_pp = C.POINTER(C.c_void_p)
+_pol = C.POINTER(AbxPolicy)
+_pi64 = C.POINTER(C.c_int64)
+
+SIGNATURES = {
+    "abx_last_error": (C.c_char_p, []),
+    "abx_version": (C.c_int, []),
+    "abx_launch_count": (_i64, []),
+    "abx_free": (C.c_int, [_vp, _vp]),
+    "abx_profile_enable": (C.c_int, [C.c_int]),
+    "abx_profile_report": (_i64, [C.c_char_p, _i64]),
+    "abx_bvh_build": (C.c_int, [_vp, C.c_int, _vp, _i64, _pp]),
+    "abx_bvh_build_host": (C.c_int, [_vp, C.c_int, _vp, _i64, _pp]),
+    "abx_bvh_build_from_sorted_codes": (C.c_int, [_vp, C.c_int, _vp, _vp, _i64, _pp]),
+    "abx_bvh_destroy": (C.c_int, [_vp]),
+    "abx_bvh_size": (_i64, [_vp]),
+    "abx_bvh_empty": (C.c_int, [_vp]),
+    "abx_bvh_bounds": (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    "abx_bvh_memory_bytes": (_i64, [_vp]),
+    "abx_bvh_export_reference_layout": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "abx_query_spatial_crs": (C.c_int, [_vp, _vp, C.c_int, _vp, _i64, _pol, ALLOC_FN, _vp, _pp, _pp, _pi64]),
+    "abx_query_spatial_count": (C.c_int, [_vp, _vp, C.c_int, _vp, _i64, C.c_int, _i32, _vp]),
+    "abx_query_nearest_crs": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _pol, ALLOC_FN, _vp, _pp, _pp, _pp, _pi64]),
+    "abx_query_spatial_crs_host": (C.c_int, [_vp, _vp, C.c_int, _vp, _i64, _pol, ALLOC_FN, _vp, _pp, _pp, _pi64]),
+    "abx_query_nearest_crs_host": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _pol, ALLOC_FN, _vp, _pp, _pp, _pp, _pi64]),
+    "abx_half_traversal_pairs": (C.c_int, [_vp, _vp, _f, _vp, _i64, _pi64]),
+    "abx_dbscan": (C.c_int, [_vp, _vp, _i64, _f, _i32, C.c_int, C.c_int, _vp]),
+    "abx_dbscan_host": (C.c_int, [_vp, _vp, _i64, _f, _i32, C.c_int, C.c_int, _vp]),
+    "abx_scene_bounds": (C.c_int, [_vp, C.c_int, _vp, _i64, _vp]),
+    "abx_morton64": (C.c_int, [_vp, C.c_int, _vp, _i64, _vp, _vp]),
+    "abx_morton32": (C.c_int, [_vp, C.c_int, _vp, _i64, _vp, _vp]),
+    "abx_sort_u64": (C.c_int, [_vp, _vp, _vp, _i64]),
+    "abx_sort_u32": (C.c_int, [_vp, _vp, _vp, _i64]),
+    "abx_exclusive_scan_i32": (C.c_int, [_vp, _vp, _vp, _i64]),
+}
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "arborx_b200: %s not found -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(make -C arborx_b200/csrc).  There is no CPU fallback." % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            f = getattr(L, name)  # AttributeError here = missing export
+            f.restype = res
+            f.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(status):
+    if status == ABX_OK:
+        return
+    msg = lib().abx_last_error().decode("utf-8", "replace")
+    if status == ABX_ERR_SEARCH:
+        raise SearchException(msg)
+    if status == ABX_ERR_PRECISION:
+        raise RuntimeError(msg)
+    if status == ABX_ERR_ARG:
+        raise ValueError(msg)
+    raise RuntimeError("libabx: CUDA failure: " + msg)

@@ -1,0 +1,683 @@
+// abx_capi.cu -- the C ABI (include/abx.h): argument checking, orchestration of
+// the kernels in abx_{sort,build,query,dbscan}.cu, output allocation.
+#include "abx_common.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+namespace abx
+{
+
+static thread_local std::string t_last_error;
+int64_t g_launch_count = 0;
+
+void setError(std::string const &msg) { t_last_error = msg; }
+
+// ---- per-kernel timing -------------------------------------------------------------
+bool g_profile = false;
+namespace
+{
+struct ProfileRecord
+{
+  char const *name;
+  cudaEvent_t start, stop;
+};
+std::vector<ProfileRecord> g_records;
+std::vector<cudaEvent_t> g_event_pool;
+cudaEvent_t takeEvent()
+{
+  if (!g_event_pool.empty())
+  {
+    cudaEvent_t e = g_event_pool.back();
+    g_event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+} // namespace
+void profileBegin(char const *name, cudaStream_t s)
+{
+  ProfileRecord r{name, takeEvent(), takeEvent()};
+  cudaEventRecord(r.start, s);
+  g_records.push_back(r);
+}
+void profileEnd(cudaStream_t s) { cudaEventRecord(g_records.back().stop, s); }
+
+static abx_status ensureDevice()
+{
+  static std::once_flag once;
+  static cudaError_t init_err = cudaSuccess;
+  std::call_once(once, [] {
+    int count = 0;
+    init_err = cudaGetDeviceCount(&count);
+    if (init_err == cudaSuccess && count == 0)
+      init_err = cudaErrorNoDevice;
+    if (init_err != cudaSuccess)
+      return;
+    // keep freed blocks in the stream-ordered pool: temporaries are re-used
+    // across calls instead of going back to the driver
+    for (int d = 0; d < count; ++d)
+    {
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, d) == cudaSuccess)
+      {
+        unsigned long long threshold = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+      }
+    }
+  });
+  if (init_err != cudaSuccess)
+  {
+    setError(std::string("no usable CUDA device (libabx has no CPU fallback): ") + cudaGetErrorString(init_err));
+    return ABX_ERR_CUDA;
+  }
+  return ABX_OK;
+}
+
+abx_status deviceAlloc(void **p, size_t bytes, cudaStream_t s)
+{
+  *p = nullptr;
+  if (bytes == 0)
+    bytes = 16;
+  ABX_CUDA_TRY(cudaMallocAsync(p, bytes, s));
+  return ABX_OK;
+}
+
+void deviceFree(void *p, cudaStream_t s)
+{
+  if (p)
+    cudaFreeAsync(p, s);
+}
+
+static abx_policy defaultPolicy()
+{
+  abx_policy p;
+  p.buffer_size = 0;
+  p.sort_predicates = 1;
+  return p;
+}
+
+static int predStride(int kind) { return kind == ABX_PRED_SPHERE3F ? 4 : kind == ABX_PRED_BOX3F ? 6 : 3; }
+static int primStride(int kind) { return kind == ABX_PRIM_POINT3F ? 3 : kind == ABX_PRIM_BOX3F ? 6 : 9; }
+
+// output buffer from the caller's allocator or from the stream-ordered pool
+static abx_status allocOut(abx_alloc_fn alloc, void *user, int which, size_t bytes, cudaStream_t s, void **out)
+{
+  if (alloc)
+  {
+    *out = alloc(user, which, bytes);
+    if (!*out && bytes)
+    {
+      setError("output allocator returned NULL");
+      return ABX_ERR_ARG;
+    }
+    return ABX_OK;
+  }
+  return deviceAlloc(out, bytes, s);
+}
+
+__global__ void fillStrideKernel(int32_t *offsets, int64_t q_plus_1, int stride)
+{
+  int64_t const i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < q_plus_1)
+    offsets[i] = (int32_t)(i * stride);
+}
+
+// overflow[0] = 1 if any count exceeds |buffer|
+__global__ void overflowKernel(int32_t const *__restrict__ counts, int64_t q, int buffer, int *overflow)
+{
+  int64_t const i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < q && counts[i] > buffer)
+    *overflow = 1;
+}
+
+static abx_status checkPredPointer(int pred_kind, void const *preds, int64_t q)
+{
+  if (q > 0 && !preds)
+  {
+    setError("null predicates");
+    return ABX_ERR_ARG;
+  }
+  if (pred_kind == ABX_PRED_SPHERE3F && (reinterpret_cast<uintptr_t>(preds) & 15u))
+  {
+    setError("sphere predicates must be 16-byte aligned");
+    return ABX_ERR_ARG;
+  }
+  return ABX_OK;
+}
+
+// spatial CRS: CrsGraphWrapperImpl.hpp:148-446.  The reference counts, scans and
+// traverses again to fill; buffer_size only changes how the first pass stores
+// results, never the result, so the policy is honoured for its error contract
+// (hard preallocation overflow throws, :263-268) and the count/fill scheme is used
+// for every value.
+static abx_status spatialCrs(abx_bvh *bvh, cudaStream_t s, int pred_kind, void const *preds, int64_t q,
+                             abx_policy const &policy, abx_alloc_fn alloc, void *user, int32_t **offsets_out,
+                             uint32_t **indices_out, int64_t *nnz_out)
+{
+  ABX_TRY(checkPredPointer(pred_kind, preds, q));
+  if (q < 0 || q >= (int64_t)1 << 30)
+  {
+    setError("number of predicates must be in [0, 2^30)");
+    return ABX_ERR_ARG;
+  }
+  void *offsets_v = nullptr;
+  ABX_TRY(allocOut(alloc, user, 0, sizeof(int32_t) * (size_t)(q + 1), s, &offsets_v));
+  int32_t *offsets = (int32_t *)offsets_v;
+  *offsets_out = offsets;
+  *indices_out = nullptr;
+  *nnz_out = 0;
+  if (q == 0 || bvh->n == 0)
+  {
+    ABX_CUDA_TRY(cudaMemsetAsync(offsets, 0, sizeof(int32_t) * (size_t)(q + 1), s));
+    void *idx = nullptr;
+    ABX_TRY(allocOut(alloc, user, 1, 0, s, &idx));
+    *indices_out = (uint32_t *)idx;
+    return ABX_OK;
+  }
+  TempBuffer<uint32_t> qperm;
+  if (policy.sort_predicates && bvh->n > 1)
+    ABX_TRY(predicatePermutation(s, bvh, pred_kind, preds, q, qperm));
+  // first pass: counts land in offsets[0..q) in ORIGINAL query order
+  ABX_TRY(spatialCount(s, bvh, pred_kind, preds, q, qperm.ptr, 0, offsets));
+  TempBuffer<int> overflow;
+  int h_overflow = 0;
+  if (policy.buffer_size < 0)
+  {
+    ABX_TRY(overflow.alloc(1, s));
+    ABX_CUDA_TRY(cudaMemsetAsync(overflow.ptr, 0, sizeof(int), s));
+    ABX_LAUNCH(overflowKernel, divUp(q, 256), 256, 0, s, offsets, q, -policy.buffer_size, overflow.ptr);
+    ABX_CUDA_TRY(cudaMemcpyAsync(&h_overflow, overflow.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
+  }
+  ABX_TRY(exclusiveScanI32(s, offsets, offsets, q + 1));
+  int32_t total = 0;
+  ABX_CUDA_TRY(cudaMemcpyAsync(&total, offsets + q, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  ABX_CUDA_TRY(cudaStreamSynchronize(s)); // the reference blocks here too (lastElement, :248)
+  *nnz_out = total;
+  void *idx = nullptr;
+  if (total == 0)
+  {
+    ABX_TRY(allocOut(alloc, user, 1, 0, s, &idx));
+    *indices_out = (uint32_t *)idx;
+    return ABX_OK; // :252-261
+  }
+  if (h_overflow)
+  {
+    setError("SearchException: hard preallocation buffer_size is too small for the results");
+    return ABX_ERR_SEARCH;
+  }
+  ABX_TRY(allocOut(alloc, user, 1, sizeof(uint32_t) * (size_t)total, s, &idx));
+  *indices_out = (uint32_t *)idx;
+  ABX_TRY(spatialFill(s, bvh, pred_kind, preds, q, qperm.ptr, offsets, *indices_out));
+  return ABX_OK;
+}
+
+static abx_status nearestCrs(abx_bvh *bvh, cudaStream_t s, void const *pts, int64_t q, int32_t k,
+                             int32_t const *k_per_query, abx_policy const &policy, abx_alloc_fn alloc, void *user,
+                             int32_t **offsets_out, uint32_t **indices_out, float **distances_out, int64_t *nnz_out)
+{
+  if (q > 0 && !pts)
+  {
+    setError("null query points");
+    return ABX_ERR_ARG;
+  }
+  if (q < 0 || q >= (int64_t)1 << 30)
+  {
+    setError("number of predicates must be in [0, 2^30)");
+    return ABX_ERR_ARG;
+  }
+  void *offsets_v = nullptr;
+  ABX_TRY(allocOut(alloc, user, 0, sizeof(int32_t) * (size_t)(q + 1), s, &offsets_v));
+  int32_t *offsets = (int32_t *)offsets_v;
+  *offsets_out = offsets;
+  *indices_out = nullptr;
+  if (distances_out)
+    *distances_out = nullptr;
+  *nnz_out = 0;
+  int const n = (int)bvh->n;
+  int64_t total = 0;
+  bool const uniform = (k_per_query == nullptr);
+  if (uniform)
+  {
+    // allocateAndInitializeStorage(Nearest) (CrsGraphWrapperImpl.hpp:353-374) with
+    // rows already compacted to min(k, n)
+    int const row = std::max(0, std::min(k, n));
+    total = (int64_t)row * q;
+    if (total >= (int64_t)1 << 31)
+    {
+      setError("nearest query: more than 2^31 results");
+      return ABX_ERR_ARG;
+    }
+    ABX_LAUNCH(fillStrideKernel, divUp(q + 1, 256), 256, 0, s, offsets, q + 1, row);
+  }
+  else
+  {
+    ABX_TRY(clipK(s, k_per_query, k, n, q, offsets));
+    ABX_TRY(exclusiveScanI32(s, offsets, offsets, q + 1));
+    int32_t t32 = 0;
+    ABX_CUDA_TRY(cudaMemcpyAsync(&t32, offsets + q, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    ABX_CUDA_TRY(cudaStreamSynchronize(s));
+    total = t32;
+  }
+  *nnz_out = total;
+  void *idx = nullptr, *dist = nullptr;
+  ABX_TRY(allocOut(alloc, user, 1, sizeof(uint32_t) * (size_t)total, s, &idx));
+  *indices_out = (uint32_t *)idx;
+  if (distances_out)
+  {
+    ABX_TRY(allocOut(alloc, user, 2, sizeof(float) * (size_t)total, s, &dist));
+    *distances_out = (float *)dist;
+  }
+  if (total == 0)
+    return ABX_OK;
+  TempBuffer<uint32_t> qperm;
+  if (policy.sort_predicates && n > 1)
+    ABX_TRY(predicatePermutation(s, bvh, ABX_PRED_POINT3F, pts, q, qperm));
+  ABX_TRY(nearestQuery(s, bvh, (float const *)pts, q, k, k_per_query, qperm.ptr, uniform ? nullptr : offsets, total,
+                       nullptr, *indices_out, (float *)dist));
+  return ABX_OK;
+}
+
+} // namespace abx
+
+using namespace abx;
+
+extern "C"
+{
+
+const char *abx_last_error(void) { return t_last_error.c_str(); }
+int abx_version(void) { return ABX_VERSION; }
+int64_t abx_launch_count(void) { return g_launch_count; }
+
+abx_status abx_profile_enable(int on)
+{
+  ABX_TRY(ensureDevice());
+  cudaDeviceSynchronize();
+  for (auto &r : g_records)
+  {
+    g_event_pool.push_back(r.start);
+    g_event_pool.push_back(r.stop);
+  }
+  g_records.clear();
+  g_profile = on != 0;
+  return ABX_OK;
+}
+
+// "name\tlaunches\ttotal_ms\n" per kernel, most expensive first; returns the number
+// of bytes needed (including the terminating NUL)
+int64_t abx_profile_report(char *buf, int64_t capacity)
+{
+  cudaDeviceSynchronize();
+  struct Agg
+  {
+    std::string name;
+    int64_t count = 0;
+    double ms = 0;
+  };
+  std::vector<Agg> aggs;
+  for (auto &r : g_records)
+  {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, r.start, r.stop) != cudaSuccess)
+      continue;
+    std::string name(r.name);
+    auto it = std::find_if(aggs.begin(), aggs.end(), [&](Agg const &a) { return a.name == name; });
+    if (it == aggs.end())
+    {
+      aggs.push_back(Agg{name, 0, 0});
+      it = aggs.end() - 1;
+    }
+    it->count++;
+    it->ms += ms;
+  }
+  std::sort(aggs.begin(), aggs.end(), [](Agg const &a, Agg const &b) { return a.ms > b.ms; });
+  std::string out;
+  for (auto &a : aggs)
+  {
+    char line[512];
+    snprintf(line, sizeof line, "%s\t%lld\t%.6f\n", a.name.c_str(), (long long)a.count, a.ms);
+    out += line;
+  }
+  if (buf && capacity > 0)
+  {
+    size_t const c = std::min<size_t>(out.size(), (size_t)capacity - 1);
+    memcpy(buf, out.data(), c);
+    buf[c] = 0;
+  }
+  return (int64_t)out.size() + 1;
+}
+
+abx_status abx_free(void *stream, void *ptr_dev)
+{
+  ABX_TRY(ensureDevice());
+  deviceFree(ptr_dev, (cudaStream_t)stream);
+  return ABX_OK;
+}
+
+abx_status abx_bvh_build(void *stream, int prim_kind, const void *prims_dev, int64_t n, abx_bvh **out)
+{
+  if (!out)
+  {
+    setError("null output handle");
+    return ABX_ERR_ARG;
+  }
+  *out = nullptr;
+  ABX_TRY(ensureDevice());
+  return buildTree((cudaStream_t)stream, prim_kind, prims_dev, n, nullptr, out);
+}
+
+abx_status abx_bvh_build_host(void *stream, int prim_kind, const void *prims_host, int64_t n, abx_bvh **out)
+{
+  if (!out)
+  {
+    setError("null output handle");
+    return ABX_ERR_ARG;
+  }
+  *out = nullptr;
+  ABX_TRY(ensureDevice());
+  if (prim_kind < 0 || prim_kind > ABX_PRIM_TRI3F || n < 0)
+  {
+    setError("bad primitive kind or count");
+    return ABX_ERR_ARG;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  TempBuffer<float> dev;
+  ABX_TRY(dev.alloc((size_t)primStride(prim_kind) * (size_t)std::max<int64_t>(n, 1), s));
+  if (n > 0)
+    ABX_CUDA_TRY(cudaMemcpyAsync(dev.ptr, prims_host, sizeof(float) * primStride(prim_kind) * (size_t)n,
+                                 cudaMemcpyHostToDevice, s));
+  return buildTree(s, prim_kind, dev.ptr, n, nullptr, out);
+}
+
+abx_status abx_bvh_build_from_sorted_codes(void *stream, int prim_kind, const void *prims_dev,
+                                           const uint64_t *sorted_codes_dev, int64_t n, abx_bvh **out)
+{
+  if (!out || (n > 0 && !sorted_codes_dev))
+  {
+    setError("null argument");
+    return ABX_ERR_ARG;
+  }
+  *out = nullptr;
+  ABX_TRY(ensureDevice());
+  return buildTree((cudaStream_t)stream, prim_kind, prims_dev, n, sorted_codes_dev, out);
+}
+
+int64_t abx_bvh_size(const abx_bvh *bvh) { return bvh ? bvh->n : 0; }
+int abx_bvh_empty(const abx_bvh *bvh) { return !bvh || bvh->n == 0; }
+int64_t abx_bvh_memory_bytes(const abx_bvh *bvh) { return bvh ? bvh->bytes : 0; }
+
+abx_status abx_bvh_bounds(abx_bvh *bvh, float out6[6])
+{
+  if (!bvh || !out6)
+  {
+    setError("null argument");
+    return ABX_ERR_ARG;
+  }
+  if (!bvh->bounds_host_valid)
+  {
+    ABX_CUDA_TRY(cudaMemcpyAsync(bvh->bounds_host, bvh->bounds_dev, 6 * sizeof(float), cudaMemcpyDeviceToHost,
+                                 bvh->stream));
+    ABX_CUDA_TRY(cudaStreamSynchronize(bvh->stream));
+    bvh->bounds_host_valid = true;
+  }
+  for (int d = 0; d < 6; ++d)
+    out6[d] = bvh->bounds_host[d];
+  return ABX_OK;
+}
+
+abx_status abx_bvh_export_reference_layout(abx_bvh *bvh, void *stream, int32_t *leaf_rope, uint32_t *leaf_index,
+                                           int32_t *left_child, int32_t *rope, float *boxes6, uint64_t *sorted_codes)
+{
+  if (!bvh)
+  {
+    setError("null tree");
+    return ABX_ERR_ARG;
+  }
+  return exportReference((cudaStream_t)stream, bvh, leaf_rope, leaf_index, left_child, rope, boxes6, sorted_codes);
+}
+
+abx_status abx_query_spatial_crs(abx_bvh *bvh, void *stream, int pred_kind, const void *preds_dev, int64_t q,
+                                 const abx_policy *policy, abx_alloc_fn alloc, void *user, int32_t **offsets_dev,
+                                 uint32_t **indices_dev, int64_t *nnz)
+{
+  if (!bvh || !offsets_dev || !indices_dev || !nnz)
+  {
+    setError("null argument");
+    return ABX_ERR_ARG;
+  }
+  abx_policy const p = policy ? *policy : defaultPolicy();
+  return spatialCrs(bvh, (cudaStream_t)stream, pred_kind, preds_dev, q, p, alloc, user, offsets_dev, indices_dev, nnz);
+}
+
+abx_status abx_query_spatial_count(abx_bvh *bvh, void *stream, int pred_kind, const void *preds_dev, int64_t q,
+                                   int sort_predicates, int32_t limit, int32_t *counts_dev)
+{
+  if (!bvh || (q > 0 && !counts_dev))
+  {
+    setError("null argument");
+    return ABX_ERR_ARG;
+  }
+  ABX_TRY(checkPredPointer(pred_kind, preds_dev, q));
+  cudaStream_t s = (cudaStream_t)stream;
+  TempBuffer<uint32_t> qperm;
+  if (sort_predicates && bvh->n > 1 && q > 0)
+    ABX_TRY(predicatePermutation(s, bvh, pred_kind, preds_dev, q, qperm));
+  return spatialCount(s, bvh, pred_kind, preds_dev, q, qperm.ptr, limit, counts_dev);
+}
+
+abx_status abx_query_nearest_crs(abx_bvh *bvh, void *stream, const void *points_dev, int64_t q, int32_t k,
+                                 const int32_t *k_per_query_dev, const abx_policy *policy, abx_alloc_fn alloc,
+                                 void *user, int32_t **offsets_dev, uint32_t **indices_dev, float **distances_dev,
+                                 int64_t *nnz)
+{
+  if (!bvh || !offsets_dev || !indices_dev || !nnz)
+  {
+    setError("null argument");
+    return ABX_ERR_ARG;
+  }
+  abx_policy const p = policy ? *policy : defaultPolicy();
+  return nearestCrs(bvh, (cudaStream_t)stream, points_dev, q, k, k_per_query_dev, p, alloc, user, offsets_dev,
+                    indices_dev, distances_dev, nnz);
+}
+
+// ---- host-buffer variants: H2D of the predicates and D2H of the CRS arrays are
+// part of the call (the end-to-end path timed by bench.py) -------------------------
+abx_status abx_query_spatial_crs_host(abx_bvh *bvh, void *stream, int pred_kind, const void *preds_host, int64_t q,
+                                      const abx_policy *policy, abx_alloc_fn alloc_host, void *user,
+                                      int32_t **offsets_host, uint32_t **indices_host, int64_t *nnz)
+{
+  if (!bvh || !offsets_host || !indices_host || !nnz || !alloc_host)
+  {
+    setError("null argument");
+    return ABX_ERR_ARG;
+  }
+  if (pred_kind < 0 || pred_kind > ABX_PRED_POINT3F || q < 0)
+  {
+    setError("bad predicate kind or count");
+    return ABX_ERR_ARG;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  abx_policy const p = policy ? *policy : defaultPolicy();
+  TempBuffer<float> preds;
+  ABX_TRY(preds.alloc((size_t)predStride(pred_kind) * (size_t)std::max<int64_t>(q, 1), s));
+  if (q > 0)
+    ABX_CUDA_TRY(cudaMemcpyAsync(preds.ptr, preds_host, sizeof(float) * predStride(pred_kind) * (size_t)q,
+                                 cudaMemcpyHostToDevice, s));
+  int32_t *off_dev = nullptr;
+  uint32_t *idx_dev = nullptr;
+  abx_status st = spatialCrs(bvh, s, pred_kind, preds.ptr, q, p, nullptr, nullptr, &off_dev, &idx_dev, nnz);
+  if (st == ABX_OK)
+  {
+    *offsets_host = (int32_t *)alloc_host(user, 0, sizeof(int32_t) * (size_t)(q + 1));
+    *indices_host = (uint32_t *)alloc_host(user, 1, sizeof(uint32_t) * (size_t)*nnz);
+    cudaError_t e = cudaMemcpyAsync(*offsets_host, off_dev, sizeof(int32_t) * (size_t)(q + 1), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && *nnz > 0)
+      e = cudaMemcpyAsync(*indices_host, idx_dev, sizeof(uint32_t) * (size_t)*nnz, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess)
+      e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess)
+    {
+      setError(std::string("result copy: ") + cudaGetErrorString(e));
+      st = ABX_ERR_CUDA;
+    }
+  }
+  deviceFree(off_dev, s);
+  deviceFree(idx_dev, s);
+  return st;
+}
+
+abx_status abx_query_nearest_crs_host(abx_bvh *bvh, void *stream, const void *points_host, int64_t q, int32_t k,
+                                      const abx_policy *policy, abx_alloc_fn alloc_host, void *user,
+                                      int32_t **offsets_host, uint32_t **indices_host, float **distances_host,
+                                      int64_t *nnz)
+{
+  if (!bvh || !offsets_host || !indices_host || !nnz || !alloc_host || q < 0)
+  {
+    setError("null argument");
+    return ABX_ERR_ARG;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  abx_policy const p = policy ? *policy : defaultPolicy();
+  TempBuffer<float> pts;
+  ABX_TRY(pts.alloc(3 * (size_t)std::max<int64_t>(q, 1), s));
+  if (q > 0)
+    ABX_CUDA_TRY(cudaMemcpyAsync(pts.ptr, points_host, sizeof(float) * 3 * (size_t)q, cudaMemcpyHostToDevice, s));
+  int32_t *off_dev = nullptr;
+  uint32_t *idx_dev = nullptr;
+  float *dist_dev = nullptr;
+  abx_status st = nearestCrs(bvh, s, pts.ptr, q, k, nullptr, p, nullptr, nullptr, &off_dev, &idx_dev,
+                             distances_host ? &dist_dev : nullptr, nnz);
+  if (st == ABX_OK)
+  {
+    *offsets_host = (int32_t *)alloc_host(user, 0, sizeof(int32_t) * (size_t)(q + 1));
+    *indices_host = (uint32_t *)alloc_host(user, 1, sizeof(uint32_t) * (size_t)*nnz);
+    cudaError_t e = cudaMemcpyAsync(*offsets_host, off_dev, sizeof(int32_t) * (size_t)(q + 1), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && *nnz > 0)
+      e = cudaMemcpyAsync(*indices_host, idx_dev, sizeof(uint32_t) * (size_t)*nnz, cudaMemcpyDeviceToHost, s);
+    if (distances_host)
+    {
+      *distances_host = (float *)alloc_host(user, 2, sizeof(float) * (size_t)*nnz);
+      if (e == cudaSuccess && *nnz > 0)
+        e = cudaMemcpyAsync(*distances_host, dist_dev, sizeof(float) * (size_t)*nnz, cudaMemcpyDeviceToHost, s);
+    }
+    if (e == cudaSuccess)
+      e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess)
+    {
+      setError(std::string("result copy: ") + cudaGetErrorString(e));
+      st = ABX_ERR_CUDA;
+    }
+  }
+  deviceFree(off_dev, s);
+  deviceFree(idx_dev, s);
+  deviceFree(dist_dev, s);
+  return st;
+}
+
+abx_status abx_half_traversal_pairs(abx_bvh *bvh, void *stream, float r, uint32_t *pairs_dev, int64_t capacity,
+                                    int64_t *count)
+{
+  if (!bvh || !count)
+  {
+    setError("null argument");
+    return ABX_ERR_ARG;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  TempBuffer<unsigned long long> cnt;
+  ABX_TRY(cnt.alloc(1, s));
+  ABX_TRY(halfTraversalPairs(s, bvh, r, pairs_dev, capacity, cnt.ptr));
+  unsigned long long h = 0;
+  ABX_CUDA_TRY(cudaMemcpyAsync(&h, cnt.ptr, sizeof(h), cudaMemcpyDeviceToHost, s));
+  ABX_CUDA_TRY(cudaStreamSynchronize(s));
+  *count = (int64_t)h;
+  return ABX_OK;
+}
+
+abx_status abx_dbscan(void *stream, const float *xyz_dev, int64_t n, float eps, int32_t minpts, int implementation,
+                      int algorithm, int32_t *labels_dev)
+{
+  ABX_TRY(ensureDevice());
+  if (n > 0 && (!xyz_dev || !labels_dev))
+  {
+    setError("null argument");
+    return ABX_ERR_ARG;
+  }
+  return dbscan((cudaStream_t)stream, xyz_dev, n, eps, minpts, implementation, algorithm, labels_dev);
+}
+
+abx_status abx_dbscan_host(void *stream, const float *xyz_host, int64_t n, float eps, int32_t minpts,
+                           int implementation, int algorithm, int32_t *labels_host)
+{
+  ABX_TRY(ensureDevice());
+  if (n > 0 && (!xyz_host || !labels_host))
+  {
+    setError("null argument");
+    return ABX_ERR_ARG;
+  }
+  if (n < 0)
+  {
+    setError("negative point count");
+    return ABX_ERR_ARG;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  TempBuffer<float> xyz;
+  TempBuffer<int32_t> labels;
+  ABX_TRY(xyz.alloc(3 * (size_t)std::max<int64_t>(n, 1), s));
+  ABX_TRY(labels.alloc((size_t)std::max<int64_t>(n, 1), s));
+  if (n > 0)
+    ABX_CUDA_TRY(cudaMemcpyAsync(xyz.ptr, xyz_host, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, s));
+  ABX_TRY(dbscan(s, xyz.ptr, n, eps, minpts, implementation, algorithm, labels.ptr));
+  if (n > 0)
+    ABX_CUDA_TRY(cudaMemcpyAsync(labels_host, labels.ptr, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, s));
+  ABX_CUDA_TRY(cudaStreamSynchronize(s));
+  return ABX_OK;
+}
+
+// ---- stage-level entry points -------------------------------------------------------
+abx_status abx_scene_bounds(void *stream, int prim_kind, const void *prims_dev, int64_t n, float *bounds6_dev)
+{
+  ABX_TRY(ensureDevice());
+  cudaStream_t s = (cudaStream_t)stream;
+  TempBuffer<unsigned> enc;
+  ABX_TRY(enc.alloc(6, s));
+  ABX_TRY(sceneBounds(s, prim_kind, prims_dev, n, enc.ptr));
+  return decodeBounds(s, enc.ptr, bounds6_dev);
+}
+
+abx_status abx_morton64(void *stream, int prim_kind, const void *prims_dev, int64_t n, const float *bounds6_dev,
+                        uint64_t *codes_dev)
+{
+  ABX_TRY(ensureDevice());
+  return morton64((cudaStream_t)stream, prim_kind, prims_dev, n, bounds6_dev, codes_dev);
+}
+
+abx_status abx_morton32(void *stream, int pred_kind, const void *preds_dev, int64_t q, const float *bounds6_dev,
+                        uint32_t *codes_dev)
+{
+  ABX_TRY(ensureDevice());
+  return morton32((cudaStream_t)stream, pred_kind, preds_dev, q, bounds6_dev, codes_dev);
+}
+
+abx_status abx_sort_u64(void *stream, uint64_t *keys_dev, uint32_t *perm_dev, int64_t n)
+{
+  ABX_TRY(ensureDevice());
+  return sortPairsU64((cudaStream_t)stream, keys_dev, perm_dev, n, true);
+}
+
+abx_status abx_sort_u32(void *stream, uint32_t *keys_dev, uint32_t *perm_dev, int64_t n)
+{
+  ABX_TRY(ensureDevice());
+  return sortPairsU32((cudaStream_t)stream, keys_dev, perm_dev, n, true);
+}
+
+abx_status abx_exclusive_scan_i32(void *stream, const int32_t *in_dev, int32_t *out_dev, int64_t n_plus_1)
+{
+  ABX_TRY(ensureDevice());
+  return exclusiveScanI32((cudaStream_t)stream, in_dev, out_dev, n_plus_1);
+}
+
+} // extern "C"

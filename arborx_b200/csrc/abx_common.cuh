@@ -1,0 +1,299 @@
+// abx_common.cuh -- shared device/host helpers for libabx (sm_100a only).
+//
+// Float arithmetic that feeds a comparison uses the __f*_rn intrinsics so that it
+// is never contracted into FMAs: results must be bit-identical to the reference's
+// unfused float chains (geometry/algorithms/ArborX_Distance.hpp:54-70,
+// ArborX_Intersects.hpp:84-114).
+#pragma once
+
+#include <cfloat>
+#include <climits>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include <cuda_runtime.h>
+
+#include "../../include/abx.h"
+
+namespace abx
+{
+
+// ---------------------------------------------------------------- errors ----
+void setError(std::string const &msg);
+extern int64_t g_launch_count;
+
+#define ABX_CUDA_TRY(expr)                                                                                            \
+  do                                                                                                                   \
+  {                                                                                                                    \
+    cudaError_t _e = (expr);                                                                                           \
+    if (_e != cudaSuccess)                                                                                             \
+    {                                                                                                                  \
+      ::abx::setError(std::string(#expr) + ": " + cudaGetErrorString(_e));                                            \
+      return ABX_ERR_CUDA;                                                                                             \
+    }                                                                                                                  \
+  } while (0)
+
+#define ABX_TRY(expr)                                                                                                 \
+  do                                                                                                                   \
+  {                                                                                                                    \
+    abx_status _s = (expr);                                                                                            \
+    if (_s != ABX_OK)                                                                                                  \
+      return _s;                                                                                                       \
+  } while (0)
+
+// per-kernel device timing (abx_profile_enable / abx_profile_report): CUDA events on
+// the launching stream around every launch, aggregated by kernel name
+extern bool g_profile;
+void profileBegin(char const *name, cudaStream_t s);
+void profileEnd(cudaStream_t s);
+
+// every kernel launch goes through this so that launches are counted, checked and
+// (optionally) timed
+#define ABX_LAUNCH_TAGGED(tag, kernel, grid, block, smem, stream, ...)                                                \
+  do                                                                                                                   \
+  {                                                                                                                    \
+    if (::abx::g_profile)                                                                                              \
+      ::abx::profileBegin(tag, stream);                                                                                \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                                                       \
+    if (::abx::g_profile)                                                                                              \
+      ::abx::profileEnd(stream);                                                                                       \
+    ++::abx::g_launch_count;                                                                                           \
+    ABX_CUDA_TRY(cudaGetLastError());                                                                                  \
+  } while (0)
+#define ABX_LAUNCH(kernel, grid, block, smem, stream, ...)                                                            \
+  ABX_LAUNCH_TAGGED(#kernel, kernel, grid, block, smem, stream, __VA_ARGS__)
+
+constexpr int kNumSMs = 148; // B200
+
+static inline int divUp(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// stream-ordered temporary buffer (cudaMallocAsync pool, release threshold maxed)
+abx_status deviceAlloc(void **p, size_t bytes, cudaStream_t s);
+void deviceFree(void *p, cudaStream_t s);
+
+template <class T>
+struct TempBuffer
+{
+  T *ptr = nullptr;
+  cudaStream_t stream = nullptr;
+  TempBuffer() = default;
+  TempBuffer(TempBuffer const &) = delete;
+  TempBuffer &operator=(TempBuffer const &) = delete;
+  abx_status alloc(size_t count, cudaStream_t s)
+  {
+    release();
+    stream = s;
+    return deviceAlloc((void **)&ptr, count * sizeof(T), s);
+  }
+  void release()
+  {
+    if (ptr)
+      deviceFree(ptr, stream);
+    ptr = nullptr;
+  }
+  T *take()
+  {
+    T *p = ptr;
+    ptr = nullptr;
+    return p;
+  }
+  ~TempBuffer() { release(); }
+};
+
+// ------------------------------------------------------------- geometry ----
+struct Box
+{
+  float lo[3];
+  float hi[3];
+};
+
+__host__ __device__ inline Box emptyBox()
+{
+  // ArborX_Box.hpp:35-44
+  Box b;
+  for (int d = 0; d < 3; ++d)
+  {
+    b.lo[d] = FLT_MAX;
+    b.hi[d] = -FLT_MAX;
+  }
+  return b;
+}
+
+__device__ __forceinline__ void boxUnion(Box &a, Box const &b)
+{
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+  {
+    a.lo[d] = fminf(a.lo[d], b.lo[d]);
+    a.hi[d] = fmaxf(a.hi[d], b.hi[d]);
+  }
+}
+
+// distance^2 from point c to box [lo,hi], reference operation order:
+// closestPoint (ClosestPoint.hpp:49-66) then sum of squares in index order
+// (Distance.hpp:54-70).  tmp = projected - point.
+__device__ __forceinline__ float pointBoxDist2(float cx, float cy, float cz, float lx, float ly, float lz, float hx,
+                                               float hy, float hz)
+{
+  float px = cx < lx ? lx : (cx > hx ? hx : cx);
+  float py = cy < ly ? ly : (cy > hy ? hy : cy);
+  float pz = cz < lz ? lz : (cz > hz ? hz : cz);
+  float tx = __fsub_rn(px, cx), ty = __fsub_rn(py, cy), tz = __fsub_rn(pz, cz);
+  float d2 = __fmul_rn(tx, tx);
+  d2 = __fadd_rn(d2, __fmul_rn(ty, ty));
+  d2 = __fadd_rn(d2, __fmul_rn(tz, tz));
+  return d2;
+}
+
+// Largest float t with sqrtf(t) <= r, so that (sqrtf(d2) <= r) == (d2 <= t) for
+// every non-negative float d2 (sqrtf is correctly rounded and monotone).  Lets the
+// traversal loops skip the square root without changing a single result.
+__host__ __device__ inline float sqrtThreshold(float r)
+{
+  if (!(r >= 0.f))
+    return -1.f; // sqrt(d2) <= r is false for every d2 >= 0 (also NaN radius)
+  if (r > FLT_MAX)
+    return r; // +inf radius: every non-NaN d2 qualifies
+#ifdef __CUDA_ARCH__
+  float t = __fmul_rn(r, r);
+  if (t > FLT_MAX)
+    t = FLT_MAX;
+  // walk to the boundary (a couple of ulps at most)
+  while (__fsqrt_rn(t) > r)
+    t = __uint_as_float(__float_as_uint(t) - 1u);
+  for (;;)
+  {
+    float u = __uint_as_float(__float_as_uint(t) + 1u);
+    if (u <= FLT_MAX && __fsqrt_rn(u) <= r)
+      t = u;
+    else
+      break;
+  }
+  return t;
+#else
+  return r * r;
+#endif
+}
+
+// ------------------------------------------------------------ tree node ----
+// Node64: one 64-byte record per internal node k (Karras index, root = 0), holding
+// BOTH children's boxes so that one aligned 64-byte load decides both branches:
+//   f[0] = (L.lo.xyz, bits(left_ref))   f[1] = (L.hi.xyz, bits(right_ref))
+//   f[2] = (R.lo.xyz, bits(range_lo))   f[3] = (R.hi.xyz, bits(range_hi))
+// ref >= 0: internal node index; ref < 0: leaf, original index = ~ref.
+// [range_lo, range_hi] is the node's range of sorted leaf positions; a leaf left
+// child sits at position range_lo, a leaf right child at range_hi.
+// The reference layout ({left_child, rope, box}, detail/ArborX_Node.hpp:24-44) is
+// derivable from it (abx_bvh_export_reference_layout).
+struct Node64
+{
+  float4 f[4];
+};
+static_assert(sizeof(Node64) == 64, "Node64 must be 64 bytes");
+
+__device__ __forceinline__ int refLeaf(unsigned orig) { return ~(int)orig; }
+__device__ __forceinline__ bool refIsLeaf(int ref) { return ref < 0; }
+__device__ __forceinline__ unsigned refOrig(int ref) { return (unsigned)(~ref); }
+
+// ------------------------------------------------------------ Morton ----
+// spatial/detail/ArborX_MortonCode.hpp:187-197
+__host__ __device__ inline unsigned long long expandBits2_64(unsigned long long x)
+{
+  x &= 0x1fffffllu;
+  x = (x | x << 32) & 0x1f00000000ffffllu;
+  x = (x | x << 16) & 0x1f0000ff0000ffllu;
+  x = (x | x << 8) & 0x100f00f00f00f00fllu;
+  x = (x | x << 4) & 0x10c30c30c30c30c3llu;
+  x = (x | x << 2) & 0x1249249249249249llu;
+  return x;
+}
+// :63-73
+__host__ __device__ inline unsigned expandBits2_32(unsigned x)
+{
+  x &= 0x000003ffu;
+  x = (x ^ (x << 16)) & 0xff0000ffu;
+  x = (x ^ (x << 8)) & 0x0300f00fu;
+  x = (x ^ (x << 4)) & 0x030c30c3u;
+  x = (x ^ (x << 2)) & 0x09249249u;
+  return x;
+}
+
+// ordered-uint encoding of floats for atomicMin/atomicMax
+__host__ __device__ inline unsigned floatToOrdered(float f)
+{
+#ifdef __CUDA_ARCH__
+  unsigned u = __float_as_uint(f);
+#else
+  unsigned u;
+  memcpy(&u, &f, 4);
+#endif
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ inline float orderedToFloat(unsigned u)
+{
+  u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+#endif
+}
+
+__device__ __forceinline__ float4 ldcg4(float4 const *p) { return __ldcg(p); }
+
+} // namespace abx
+
+// ------------------------------------------------------- internal C++ API ----
+struct abx_bvh
+{
+  int kind = 0;
+  int64_t n = 0;
+  int device = 0;
+  cudaStream_t stream = nullptr; // stream the tree was built on
+  abx::Node64 *nodes = nullptr;  // n-1 records
+  float4 *leaf_box = nullptr;    // sorted leaves: points 1 float4 (xyz, bits(orig)); others 2 float4 (lo,orig)(hi,0)
+  float4 *leaf_tri = nullptr;    // triangles only: 3 float4 per sorted leaf (a, b, c)
+  uint32_t *perm = nullptr;      // sorted position -> original index
+  uint64_t *codes = nullptr;     // sorted Morton64 codes
+  float *bounds_dev = nullptr;   // 6 floats, root box (scene bounds)
+  float bounds_host[6];
+  bool bounds_host_valid = false;
+  int64_t bytes = 0;
+};
+
+namespace abx
+{
+// sort.cu
+abx_status sortPairsU64(cudaStream_t s, uint64_t *keys, uint32_t *vals, int64_t n, bool iota_vals);
+abx_status sortPairsU32(cudaStream_t s, uint32_t *keys, uint32_t *vals, int64_t n, bool iota_vals);
+abx_status exclusiveScanI32(cudaStream_t s, int32_t const *in, int32_t *out, int64_t n_plus_1);
+// build.cu
+abx_status sceneBounds(cudaStream_t s, int kind, void const *prims, int64_t n, unsigned *bounds_enc6);
+abx_status decodeBounds(cudaStream_t s, unsigned const *bounds_enc6, float *bounds6);
+abx_status morton64(cudaStream_t s, int kind, void const *prims, int64_t n, float const *bounds6, uint64_t *codes);
+abx_status morton32(cudaStream_t s, int pred_kind, void const *preds, int64_t q, float const *bounds6, uint32_t *codes);
+abx_status buildHierarchy(cudaStream_t s, abx_bvh *bvh, void const *prims);
+abx_status buildTree(cudaStream_t s, int kind, void const *prims, int64_t n, uint64_t const *sorted_codes_or_null,
+                     abx_bvh **out);
+abx_status exportReference(cudaStream_t s, abx_bvh *bvh, int32_t *leaf_rope, uint32_t *leaf_index, int32_t *left_child,
+                           int32_t *rope, float *boxes6, uint64_t *codes);
+// query.cu
+abx_status predicatePermutation(cudaStream_t s, abx_bvh *bvh, int pred_kind, void const *preds, int64_t q,
+                                TempBuffer<uint32_t> &perm);
+abx_status spatialCount(cudaStream_t s, abx_bvh *bvh, int pred_kind, void const *preds, int64_t q,
+                        uint32_t const *qperm, int32_t limit, int32_t *counts);
+abx_status spatialFill(cudaStream_t s, abx_bvh *bvh, int pred_kind, void const *preds, int64_t q,
+                       uint32_t const *qperm, int32_t const *offsets, uint32_t *indices);
+abx_status nearestQuery(cudaStream_t s, abx_bvh *bvh, float const *pts, int64_t q, int32_t k,
+                        int32_t const *k_per_query, uint32_t const *qperm, int32_t const *offsets, int64_t total_rows,
+                        int32_t *counts, uint32_t *indices, float *distances);
+abx_status clipK(cudaStream_t s, int32_t const *k_per_query, int k, int n, int64_t q, int32_t *out);
+abx_status halfTraversalPairs(cudaStream_t s, abx_bvh *bvh, float r, uint32_t *pairs, int64_t capacity,
+                              unsigned long long *count_dev);
+// dbscan.cu
+abx_status dbscan(cudaStream_t s, float const *xyz, int64_t n, float eps, int32_t minpts, int impl, int algo,
+                  int32_t *labels);
+} // namespace abx

@@ -1,0 +1,646 @@
+// abx_dbscan.cu -- ArborX::dbscan: FDBSCAN and FDBSCAN-DenseBox.
+//
+// Behavioural contract: cluster/ArborX_DBSCAN.hpp:219-522,
+// cluster/detail/ArborX_FDBSCAN.hpp:31-110, ArborX_FDBSCANDenseBox.hpp:32-307,
+// ArborX_UnionFind.hpp:74-181 (ECL-CC), ArborX_CartesianGrid.hpp:27-142.
+#include "abx_traverse.cuh"
+
+namespace abx
+{
+
+namespace
+{
+
+// ---- lock-free union-find (UnionFind.hpp:113-181) ---------------------------------
+// Stale reads are benign (every value ever stored in labels[x] is an ancestor of x
+// in the final forest); only the root link needs an atomic CAS.
+__device__ __forceinline__ int ufLoad(int const *labels, int i) { return __ldcg(labels + i); }
+
+__device__ __forceinline__ int ufRepresentative(int *labels, int i)
+{
+  int curr = ufLoad(labels, i);
+  if (curr != i)
+  {
+    int next, prev = i;
+    while (curr > (next = ufLoad(labels, curr)))
+    {
+      __stcg(labels + prev, next); // path halving
+      prev = curr;
+      curr = next;
+    }
+  }
+  return curr;
+}
+
+__device__ __forceinline__ void ufMergeInto(int *labels, int i, int j) { __stcg(labels + i, ufRepresentative(labels, j)); }
+
+__device__ __forceinline__ void ufMerge(int *labels, int i, int j)
+{
+  int vstat = ufRepresentative(labels, i);
+  int ostat = ufRepresentative(labels, j);
+  while (vstat != ostat)
+  {
+    if (vstat < ostat)
+      ostat = atomicCAS(labels + ostat, ostat, vstat);
+    else
+      vstat = atomicCAS(labels + vstat, vstat, ostat);
+  }
+}
+
+__global__ void iotaLabelsKernel(int *labels, int n)
+{
+  int const i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    labels[i] = i;
+}
+
+// ---- FDBSCAN: core-point counting (CountUpToN, FDBSCAN.hpp:31-46) ----------------
+// one thread per sorted leaf: queries are the tree's own points, already in
+// Morton order, so neighbouring threads walk neighbouring subtrees
+__global__ void __launch_bounds__(kThreads)
+    countCoreKernel(Node64 const *__restrict__ nodes, float4 const *__restrict__ leaf_box, int n, float eps,
+                    int minpts, int *__restrict__ num_neigh)
+{
+  int const t = blockIdx.x * kThreads + threadIdx.x;
+  if (t >= n)
+    return;
+  float4 const p = __ldg(leaf_box + t);
+  Pred<ABX_PRED_SPHERE3F> pred;
+  pred.cx = p.x, pred.cy = p.y, pred.cz = p.z, pred.r = eps;
+  pred.t = sqrtThreshold(eps);
+  int count = 0;
+  traverseSpatial(nodes, pred, [&](int, int) { return ++count >= minpts; });
+  num_neigh[__float_as_uint(p.w)] = count;
+}
+
+// ---- FDBSCAN: half traversal + FDBSCANCallback (FDBSCAN.hpp:49-110) ---------------
+template <bool SPECIAL /*minpts == 2*/, bool STAR>
+__global__ void __launch_bounds__(kThreads)
+    fdbscanMainKernel(Node64 const *__restrict__ nodes, float4 const *__restrict__ leaf_box, int n, float eps,
+                      int minpts, int const *__restrict__ num_neigh, int *labels)
+{
+  int const t = blockIdx.x * kThreads + threadIdx.x;
+  if (t >= n)
+    return;
+  float4 const p = __ldg(leaf_box + t);
+  Pred<ABX_PRED_SPHERE3F> pred;
+  pred.cx = p.x, pred.cy = p.y, pred.cz = p.z, pred.r = eps;
+  pred.t = sqrtThreshold(eps);
+  int const i = (int)__float_as_uint(p.w);
+  bool const i_core = SPECIAL ? true : (num_neigh[i] >= minpts);
+  if (STAR && !i_core)
+    return; // border points do not take part in DBSCAN* (callback would return at once)
+  traverseHalf(nodes, t, pred, [&](int ref, int) {
+    int const j = (int)refOrig(ref);
+    bool const j_core = SPECIAL ? true : (num_neigh[j] >= minpts);
+    if (STAR)
+    {
+      if (j_core)
+        ufMerge(labels, i, j);
+      return;
+    }
+    if (!i_core)
+    {
+      if (j_core)
+        ufMergeInto(labels, i, j); // never merge(): a border point must not bridge clusters
+    }
+    else
+    {
+      if (j_core)
+        ufMerge(labels, i, j);
+      else
+        ufMergeInto(labels, j, i);
+    }
+  });
+}
+
+// ---- finalize_labels (:489-506) and mark_noise (:512-518) -------------------------
+__global__ void finalizeLabelsKernel(int *labels, int *cluster_sizes, int n)
+{
+  int const i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  int next;
+  int vstat = ufLoad(labels, i);
+  int const old = vstat;
+  while (vstat > (next = ufLoad(labels, vstat)))
+    vstat = next;
+  if (vstat != old)
+    __stcg(labels + i, vstat);
+  atomicAdd(cluster_sizes + vstat, 1);
+}
+
+__global__ void markNoiseKernel(int *labels, int const *__restrict__ cluster_sizes, int const *__restrict__ num_neigh,
+                                int minpts, int n)
+{
+  int const i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  bool const special = (minpts == 2);
+  int const l = labels[i];
+  if (cluster_sizes[l] == 1 && (special || !(num_neigh[i] >= minpts)))
+    labels[i] = -1;
+}
+
+// ---- FDBSCAN-DenseBox --------------------------------------------------------------
+struct Grid
+{
+  float lo[3];
+  float h;
+  unsigned long long n[3];
+};
+
+// CartesianGrid::cellIndex (CartesianGrid.hpp:51-63)
+__device__ __forceinline__ unsigned long long cellIndex(Grid const &g, float x, float y, float z)
+{
+  float const p[3] = {x, y, z};
+  unsigned long long s = 0;
+#pragma unroll
+  for (int d = 2; d >= 0; --d)
+  {
+    int const i = (int)floorf(__fdiv_rn(__fsub_rn(p[d], g.lo[d]), g.h));
+    s = s * g.n[d] + (unsigned long long)(long long)i;
+  }
+  return s;
+}
+
+__global__ void cellIndicesKernel(float const *__restrict__ xyz, int n, Grid g, unsigned long long *__restrict__ cells)
+{
+  int const i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    cells[i] = cellIndex(g, xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2]);
+}
+
+// flags[i] = 1 when sorted position i starts a new cell (computeOffsetsInOrderedView,
+// misc/ArborX_Utils.hpp:25-51); flags has n+1 slots, the last one is scratch
+__global__ void cellStartFlagsKernel(unsigned long long const *__restrict__ cells, int n, int *__restrict__ flags)
+{
+  int const i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    flags[i] = (i == 0 || cells[i] != cells[i - 1]) ? 1 : 0;
+}
+
+// cell_offsets[rank[i]] = i for every cell start, cell_offsets[num_cells] = n
+__global__ void cellOffsetsKernel(int const *__restrict__ flags, int const *__restrict__ rank, int n,
+                                  int *__restrict__ cell_offsets)
+{
+  int const i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+  {
+    if (flags[i])
+      cell_offsets[rank[i]] = i;
+  }
+  else if (i == n)
+    cell_offsets[rank[n]] = n;
+}
+
+// per cell: dense size (>= minpts ? size : 0) and sparse size, scanned separately so
+// that dense cells come first and cells keep their sorted order inside each class
+// (reorderDenseAndSparseCells, FDBSCANDenseBox.hpp:215-283; the reference's order of
+// cells inside a class is arbitrary)
+__global__ void cellClassSizesKernel(int const *__restrict__ cell_offsets, int num_cells, int minpts,
+                                     int *__restrict__ dense_size, int *__restrict__ sparse_size,
+                                     int *__restrict__ dense_flag)
+{
+  int const c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= num_cells)
+    return;
+  int const sz = cell_offsets[c + 1] - cell_offsets[c];
+  bool const dense = sz >= minpts;
+  dense_size[c] = dense ? sz : 0;
+  sparse_size[c] = dense ? 0 : sz;
+  dense_flag[c] = dense ? 1 : 0;
+}
+
+// scatter points to their reordered position; records for each dense cell its
+// start in the reordered arrays (dense_cell_offsets) and its grid cell
+__global__ void reorderCellsKernel(int const *__restrict__ flags_rank /*cell id per sorted position*/,
+                                   int const *__restrict__ cell_offsets, int const *__restrict__ dense_off,
+                                   int const *__restrict__ sparse_off, int const *__restrict__ dense_flag,
+                                   int const *__restrict__ dense_rank, int num_points_dense,
+                                   unsigned const *__restrict__ perm_in, unsigned long long const *__restrict__ cells_in,
+                                   int n, unsigned *__restrict__ perm_out, int *__restrict__ dense_cell_offsets,
+                                   unsigned long long *__restrict__ dense_cell_ids)
+{
+  int const i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  int const c = flags_rank[i];
+  int const within = i - cell_offsets[c];
+  bool const dense = dense_flag[c] != 0;
+  int const dst = dense ? dense_off[c] + within : num_points_dense + sparse_off[c] + within;
+  perm_out[dst] = perm_in[i];
+  if (dense && within == 0)
+  {
+    dense_cell_offsets[dense_rank[c]] = dst;
+    dense_cell_ids[dense_rank[c]] = cells_in[i];
+  }
+}
+
+// cell id of every sorted position = (inclusive scan of start flags) - 1
+__global__ void cellIdKernel(int const *__restrict__ flags, int const *__restrict__ rank, int n, int *__restrict__ id)
+{
+  int const i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    id[i] = rank[i] + flags[i] - 1;
+}
+
+// unionFindWithinEachDenseCell (FDBSCANDenseBox.hpp:286-307): points of a dense cell
+// are mutually within eps, link neighbours in the reordered order
+__global__ void denseCellUnionKernel(int const *__restrict__ dense_cell_offsets, int num_dense,
+                                     unsigned const *__restrict__ perm, int num_points_dense, int *labels)
+{
+  int const i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 1 || i >= num_points_dense)
+    return;
+  // i and i-1 are in the same dense cell unless i starts a cell: binary search
+  int lo = 0, hi = num_dense;
+  while (hi - lo > 1)
+  {
+    int const mid = (lo + hi) / 2;
+    if (dense_cell_offsets[mid] <= i)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  if (dense_cell_offsets[lo] != i)
+    ufMerge(labels, (int)perm[i], (int)perm[i - 1]);
+}
+
+// MixedBoxPrimitives (ArborX_DBSCAN.hpp:73-175): dense-cell boxes (CartesianGrid::cellBox,
+// CartesianGrid.hpp:66-82) followed by degenerate boxes of the sparse points
+__global__ void mixedPrimitivesKernel(float const *__restrict__ xyz, unsigned const *__restrict__ perm, Grid g,
+                                      unsigned long long const *__restrict__ dense_cell_ids, int num_dense,
+                                      int num_points_dense, int n_prims, float *__restrict__ boxes6)
+{
+  int const i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_prims)
+    return;
+  float lo[3], hi[3];
+  if (i < num_dense)
+  {
+    unsigned long long cell = dense_cell_ids[i];
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+    {
+      unsigned long long const k = cell % g.n[d];
+      cell /= g.n[d];
+      // max = min + (i+1)*h ; min += i*h   (size_t -> float conversions as in the reference)
+      hi[d] = __fadd_rn(g.lo[d], __fmul_rn((float)(k + 1), g.h));
+      lo[d] = __fadd_rn(g.lo[d], __fmul_rn((float)k, g.h));
+    }
+  }
+  else
+  {
+    unsigned const o = perm[num_points_dense + (i - num_dense)];
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+      lo[d] = hi[d] = xyz[3 * (size_t)o + d];
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+  {
+    boxes6[6 * (size_t)i + d] = lo[d];
+    boxes6[6 * (size_t)i + 3 + d] = hi[d];
+  }
+}
+
+__global__ void markDenseCoreKernel(unsigned const *__restrict__ perm, int num_points_dense, int *num_neigh)
+{
+  int const i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < num_points_dense)
+    num_neigh[perm[i]] = INT_MAX; // ArborX_DBSCAN.hpp:438-441
+}
+
+__device__ __forceinline__ bool withinEps(float const *__restrict__ xyz, float px, float py, float pz, int j, float t)
+{
+  // distance(query_point, point_j) <= eps with the reference's operand order
+  float tx = __fsub_rn(xyz[3 * (size_t)j], px), ty = __fsub_rn(xyz[3 * (size_t)j + 1], py),
+        tz = __fsub_rn(xyz[3 * (size_t)j + 2], pz);
+  float d2 = __fmul_rn(tx, tx);
+  d2 = __fadd_rn(d2, __fmul_rn(ty, ty));
+  d2 = __fadd_rn(d2, __fmul_rn(tz, tz));
+  return d2 <= t;
+}
+
+// CountUpToN_DenseBox (FDBSCANDenseBox.hpp:32-96) for the points of sparse cells
+__global__ void __launch_bounds__(kThreads)
+    denseCountKernel(Node64 const *__restrict__ nodes, int n_prims, float const *__restrict__ xyz,
+                     unsigned const *__restrict__ perm, int const *__restrict__ dense_cell_offsets, int num_dense,
+                     int num_points_dense, int n, float eps, int minpts, int *__restrict__ num_neigh)
+{
+  int const s = blockIdx.x * kThreads + threadIdx.x;
+  if (s >= n - num_points_dense)
+    return;
+  int const i = (int)perm[num_points_dense + s];
+  float const px = xyz[3 * (size_t)i], py = xyz[3 * (size_t)i + 1], pz = xyz[3 * (size_t)i + 2];
+  Pred<ABX_PRED_SPHERE3F> pred;
+  pred.cx = px, pred.cy = py, pred.cz = pz, pred.r = eps;
+  pred.t = sqrtThreshold(eps);
+  int count = 0;
+  if (n_prims >= 2)
+    traverseSpatial(nodes, pred, [&](int ref, int) {
+      int const k = (int)refOrig(ref);
+      if (k < num_dense)
+      {
+        int const ce = dense_cell_offsets[k + 1];
+        for (int jj = dense_cell_offsets[k]; jj < ce; ++jj)
+          if (withinEps(xyz, px, py, pz, (int)perm[jj], pred.t))
+            if (++count >= minpts)
+              return true;
+        return false;
+      }
+      return ++count >= minpts;
+    });
+  else
+    count = 1; // a single primitive: the point itself
+  num_neigh[i] = count;
+}
+
+// FDBSCANDenseBoxCallback (FDBSCANDenseBox.hpp:98-205): full traversal per point
+template <bool SPECIAL, bool STAR>
+__global__ void __launch_bounds__(kThreads)
+    denseMainKernel(Node64 const *__restrict__ nodes, int n_prims, float const *__restrict__ xyz,
+                    unsigned const *__restrict__ perm, int const *__restrict__ dense_cell_offsets, int num_dense,
+                    int num_points_dense, int n, float eps, int minpts, int const *__restrict__ num_neigh,
+                    int *labels)
+{
+  int const t = blockIdx.x * kThreads + threadIdx.x;
+  if (t >= n)
+    return;
+  // walk the points in the reordered (cell-sorted) order for coherence
+  int const i = (int)perm[t];
+  bool const i_core = SPECIAL ? true : (num_neigh[i] >= minpts);
+  if (!i_core)
+    return; // border points exit at the first callback (:130-132)
+  float const px = xyz[3 * (size_t)i], py = xyz[3 * (size_t)i + 1], pz = xyz[3 * (size_t)i + 2];
+  Pred<ABX_PRED_SPHERE3F> pred;
+  pred.cx = px, pred.cy = py, pred.cz = pz, pred.r = eps;
+  pred.t = sqrtThreshold(eps);
+  if (n_prims < 2)
+    return;
+  traverseSpatial(nodes, pred, [&](int ref, int) {
+    int const k = (int)refOrig(ref);
+    if (k < num_dense)
+    {
+      int const cs = dense_cell_offsets[k], ce = dense_cell_offsets[k + 1];
+      if (ufRepresentative(labels, i) == ufRepresentative(labels, (int)perm[cs]))
+        return false;
+      for (int jj = cs; jj < ce; ++jj)
+      {
+        int const j = (int)perm[jj];
+        if (ufRepresentative(labels, i) == ufRepresentative(labels, j))
+          break;
+        if (withinEps(xyz, px, py, pz, j, pred.t))
+        {
+          ufMerge(labels, i, j);
+          break;
+        }
+      }
+    }
+    else
+    {
+      int const j = (int)perm[num_points_dense + (k - num_dense)];
+      bool const j_core = SPECIAL ? true : (num_neigh[j] >= minpts);
+      if (j_core && i > j)
+        ufMerge(labels, i, j);
+      else if (!STAR && !j_core)
+        ufMergeInto(labels, j, i);
+    }
+    return false;
+  });
+}
+
+abx_status readInt(cudaStream_t s, int const *dev, int &out)
+{
+  ABX_CUDA_TRY(cudaMemcpyAsync(&out, dev, sizeof(int), cudaMemcpyDeviceToHost, s));
+  ABX_CUDA_TRY(cudaStreamSynchronize(s));
+  return ABX_OK;
+}
+
+abx_status finalize(cudaStream_t s, int n, int minpts, int const *num_neigh, int *labels)
+{
+  TempBuffer<int> cluster_sizes;
+  ABX_TRY(cluster_sizes.alloc(n, s));
+  ABX_CUDA_TRY(cudaMemsetAsync(cluster_sizes.ptr, 0, sizeof(int) * (size_t)n, s));
+  ABX_LAUNCH(finalizeLabelsKernel, divUp(n, 256), 256, 0, s, labels, cluster_sizes.ptr, n);
+  ABX_LAUNCH(markNoiseKernel, divUp(n, 256), 256, 0, s, labels, cluster_sizes.ptr, num_neigh, minpts, n);
+  return ABX_OK;
+}
+
+struct TreeGuard
+{
+  abx_bvh *t = nullptr;
+  ~TreeGuard()
+  {
+    if (t)
+      abx_bvh_destroy(t);
+  }
+};
+
+abx_status fdbscan(cudaStream_t s, float const *xyz, int n, float eps, int minpts, int algo, int *labels)
+{
+  TreeGuard tree;
+  ABX_TRY(buildTree(s, ABX_PRIM_POINT3F, xyz, n, nullptr, &tree.t));
+  abx_bvh *t = tree.t;
+  ABX_LAUNCH(iotaLabelsKernel, divUp(n, 256), 256, 0, s, labels, n);
+  bool const special = (minpts == 2);
+  bool const star = (algo == ABX_DBSCAN_DBSCAN_STAR);
+  TempBuffer<int> num_neigh;
+  int const grid = divUp(n, kThreads);
+  if (!special)
+  {
+    ABX_TRY(num_neigh.alloc(n, s));
+    if (n >= 2)
+      ABX_LAUNCH(countCoreKernel, grid, kThreads, 0, s, t->nodes, t->leaf_box, n, eps, minpts, num_neigh.ptr);
+    else
+      ABX_CUDA_TRY(cudaMemsetAsync(num_neigh.ptr, 0, sizeof(int) * (size_t)n, s)); // 1 point: count 1 < minpts
+  }
+  if (n >= 2)
+  {
+    if (special)
+      ABX_LAUNCH((fdbscanMainKernel<true, false>), grid, kThreads, 0, s, t->nodes, t->leaf_box, n, eps, minpts,
+                 (int const *)nullptr, labels);
+    else if (star)
+      ABX_LAUNCH((fdbscanMainKernel<false, true>), grid, kThreads, 0, s, t->nodes, t->leaf_box, n, eps, minpts,
+                 (int const *)num_neigh.ptr, labels);
+    else
+      ABX_LAUNCH((fdbscanMainKernel<false, false>), grid, kThreads, 0, s, t->nodes, t->leaf_box, n, eps, minpts,
+                 (int const *)num_neigh.ptr, labels);
+  }
+  return finalize(s, n, minpts, num_neigh.ptr, labels);
+}
+
+abx_status denseBox(cudaStream_t s, float const *xyz, int n, float eps, int minpts, int algo, int *labels)
+{
+  bool const special = (minpts == 2);
+  bool const star = (algo == ABX_DBSCAN_DBSCAN_STAR);
+  // scene bounds -> grid (ArborX_DBSCAN.hpp:333-342); the grid lives on the host,
+  // like the reference's CartesianGrid
+  TempBuffer<unsigned> enc;
+  TempBuffer<float> bounds_dev;
+  ABX_TRY(enc.alloc(6, s));
+  ABX_TRY(bounds_dev.alloc(6, s));
+  ABX_TRY(sceneBounds(s, ABX_PRIM_POINT3F, xyz, n, enc.ptr));
+  ABX_TRY(decodeBounds(s, enc.ptr, bounds_dev.ptr));
+  float b[6];
+  ABX_CUDA_TRY(cudaMemcpyAsync(b, bounds_dev.ptr, sizeof(b), cudaMemcpyDeviceToHost, s));
+  ABX_CUDA_TRY(cudaStreamSynchronize(s));
+  Grid g;
+  g.h = eps / sqrtf(3.f); // ArborX_DBSCAN.hpp:341
+  for (int d = 0; d < 3; ++d)
+  {
+    g.lo[d] = b[d];
+    float const delta = b[3 + d] - b[d];
+    g.n[d] = delta != 0 ? (unsigned long long)std::ceil(delta / g.h) : 1ull; // CartesianGrid.hpp:92-108
+  }
+  {
+    // overflow guard (:110-119) and loss-of-precision guard (:121-136)
+    unsigned long long m = ~0ull;
+    for (int d = 1; d < 3; ++d)
+    {
+      m /= g.n[d - 1];
+      if (!(g.n[d] < m))
+      {
+        setError("DenseBox grid cell index would overflow");
+        return ABX_ERR_SEARCH;
+      }
+    }
+    float const tol = 5 * FLT_EPSILON;
+    for (int d = 0; d < 3; ++d)
+      if (std::fabs(g.h / g.lo[d]) < tol)
+      {
+        setError("ArborX exception: FDBSCAN-DenseBox algorithm will experience loss of precision, undetectably "
+                 "producing wrong results. Please switch to using FDBSCAN.");
+        return ABX_ERR_PRECISION;
+      }
+  }
+  int const grid_n = divUp(n, 256);
+  TempBuffer<unsigned long long> cells;
+  TempBuffer<unsigned> perm, perm2;
+  ABX_TRY(cells.alloc(n, s));
+  ABX_TRY(perm.alloc(n, s));
+  ABX_TRY(perm2.alloc(n, s));
+  ABX_LAUNCH(cellIndicesKernel, grid_n, 256, 0, s, xyz, n, g, cells.ptr);
+  ABX_TRY(sortPairsU64(s, (uint64_t *)cells.ptr, perm.ptr, n, true));
+
+  // distinct cells
+  TempBuffer<int> flags, rank, cell_id, cell_offsets;
+  ABX_TRY(flags.alloc((size_t)n + 1, s));
+  ABX_TRY(rank.alloc((size_t)n + 1, s));
+  ABX_TRY(cell_id.alloc(n, s));
+  ABX_LAUNCH(cellStartFlagsKernel, grid_n, 256, 0, s, cells.ptr, n, flags.ptr);
+  ABX_TRY(exclusiveScanI32(s, flags.ptr, rank.ptr, (int64_t)n + 1));
+  int num_cells = 0;
+  ABX_TRY(readInt(s, rank.ptr + n, num_cells));
+  ABX_TRY(cell_offsets.alloc((size_t)num_cells + 1, s));
+  ABX_LAUNCH(cellOffsetsKernel, divUp((int64_t)n + 1, 256), 256, 0, s, flags.ptr, rank.ptr, n, cell_offsets.ptr);
+  ABX_LAUNCH(cellIdKernel, grid_n, 256, 0, s, flags.ptr, rank.ptr, n, cell_id.ptr);
+
+  // dense / sparse classes
+  TempBuffer<int> dense_size, sparse_size, dense_flag, dense_off, sparse_off, dense_rank;
+  size_t const nc1 = (size_t)num_cells + 1;
+  ABX_TRY(dense_size.alloc(nc1, s));
+  ABX_TRY(sparse_size.alloc(nc1, s));
+  ABX_TRY(dense_flag.alloc(nc1, s));
+  ABX_TRY(dense_off.alloc(nc1, s));
+  ABX_TRY(sparse_off.alloc(nc1, s));
+  ABX_TRY(dense_rank.alloc(nc1, s));
+  ABX_LAUNCH(cellClassSizesKernel, divUp(num_cells, 256), 256, 0, s, cell_offsets.ptr, num_cells, minpts,
+             dense_size.ptr, sparse_size.ptr, dense_flag.ptr);
+  ABX_TRY(exclusiveScanI32(s, dense_size.ptr, dense_off.ptr, (int64_t)nc1));
+  ABX_TRY(exclusiveScanI32(s, sparse_size.ptr, sparse_off.ptr, (int64_t)nc1));
+  ABX_TRY(exclusiveScanI32(s, dense_flag.ptr, dense_rank.ptr, (int64_t)nc1));
+  int num_points_dense = 0, num_dense = 0;
+  ABX_TRY(readInt(s, dense_off.ptr + num_cells, num_points_dense));
+  ABX_TRY(readInt(s, dense_rank.ptr + num_cells, num_dense));
+
+  TempBuffer<int> dense_cell_offsets;
+  TempBuffer<unsigned long long> dense_cell_ids;
+  ABX_TRY(dense_cell_offsets.alloc((size_t)num_dense + 1, s));
+  ABX_TRY(dense_cell_ids.alloc((size_t)std::max(num_dense, 1), s));
+  ABX_LAUNCH(reorderCellsKernel, grid_n, 256, 0, s, cell_id.ptr, cell_offsets.ptr, dense_off.ptr, sparse_off.ptr,
+             dense_flag.ptr, dense_rank.ptr, num_points_dense, perm.ptr, cells.ptr, n, perm2.ptr,
+             dense_cell_offsets.ptr, dense_cell_ids.ptr);
+  ABX_CUDA_TRY(cudaMemcpyAsync(dense_cell_offsets.ptr + num_dense, &num_points_dense, sizeof(int),
+                               cudaMemcpyHostToDevice, s));
+  // (the host int outlives the copy: every path below synchronises or the copy is
+  // from pageable memory, which cudaMemcpyAsync stages before returning)
+
+  ABX_LAUNCH(iotaLabelsKernel, grid_n, 256, 0, s, labels, n);
+  if (num_points_dense > 1)
+    ABX_LAUNCH(denseCellUnionKernel, divUp(num_points_dense, 256), 256, 0, s, dense_cell_offsets.ptr, num_dense,
+               perm2.ptr, num_points_dense, labels);
+
+  // BVH over the mixed primitives
+  int const n_sparse = n - num_points_dense;
+  int const n_prims = num_dense + n_sparse;
+  TempBuffer<float> boxes;
+  ABX_TRY(boxes.alloc(6 * (size_t)n_prims, s));
+  ABX_LAUNCH(mixedPrimitivesKernel, divUp(n_prims, 256), 256, 0, s, xyz, perm2.ptr, g, dense_cell_ids.ptr, num_dense,
+             num_points_dense, n_prims, boxes.ptr);
+  TreeGuard tree;
+  ABX_TRY(buildTree(s, ABX_PRIM_BOX3F, boxes.ptr, n_prims, nullptr, &tree.t));
+  abx_bvh *t = tree.t;
+
+  TempBuffer<int> num_neigh;
+  if (!special)
+  {
+    ABX_TRY(num_neigh.alloc(n, s));
+    if (num_points_dense > 0)
+      ABX_LAUNCH(markDenseCoreKernel, divUp(num_points_dense, 256), 256, 0, s, perm2.ptr, num_points_dense,
+                 num_neigh.ptr);
+    if (n_sparse > 0)
+      ABX_LAUNCH(denseCountKernel, divUp(n_sparse, kThreads), kThreads, 0, s, t->nodes, n_prims, xyz, perm2.ptr,
+                 dense_cell_offsets.ptr, num_dense, num_points_dense, n, eps, minpts, num_neigh.ptr);
+  }
+  int const grid = divUp(n, kThreads);
+  if (special)
+    ABX_LAUNCH((denseMainKernel<true, false>), grid, kThreads, 0, s, t->nodes, n_prims, xyz, perm2.ptr,
+               dense_cell_offsets.ptr, num_dense, num_points_dense, n, eps, minpts, (int const *)nullptr, labels);
+  else if (star)
+    ABX_LAUNCH((denseMainKernel<false, true>), grid, kThreads, 0, s, t->nodes, n_prims, xyz, perm2.ptr,
+               dense_cell_offsets.ptr, num_dense, num_points_dense, n, eps, minpts, (int const *)num_neigh.ptr, labels);
+  else
+    ABX_LAUNCH((denseMainKernel<false, false>), grid, kThreads, 0, s, t->nodes, n_prims, xyz, perm2.ptr,
+               dense_cell_offsets.ptr, num_dense, num_points_dense, n, eps, minpts, (int const *)num_neigh.ptr, labels);
+  return finalize(s, n, minpts, num_neigh.ptr, labels);
+}
+
+} // namespace
+
+abx_status dbscan(cudaStream_t s, float const *xyz, int64_t n, float eps, int32_t minpts, int impl, int algo,
+                  int32_t *labels)
+{
+  // ArborX_DBSCAN.hpp:240-241
+  if (!(eps > 0))
+  {
+    setError("SearchException: dbscan requires eps > 0");
+    return ABX_ERR_SEARCH;
+  }
+  if (minpts < 2)
+  {
+    setError("SearchException: dbscan requires core_min_size >= 2");
+    return ABX_ERR_SEARCH;
+  }
+  if (n < 0 || n >= (int64_t)1 << 30)
+  {
+    setError("number of points must be in [0, 2^30)");
+    return ABX_ERR_ARG;
+  }
+  if (algo != ABX_DBSCAN_DBSCAN && algo != ABX_DBSCAN_DBSCAN_STAR)
+  {
+    setError("unknown DBSCAN algorithm");
+    return ABX_ERR_ARG;
+  }
+  if (n == 0)
+    return ABX_OK;
+  if (impl == ABX_DBSCAN_FDBSCAN)
+    return fdbscan(s, xyz, (int)n, eps, minpts, algo, labels);
+  if (impl == ABX_DBSCAN_FDBSCAN_DENSEBOX)
+    return denseBox(s, xyz, (int)n, eps, minpts, algo, labels);
+  setError("unknown DBSCAN implementation");
+  return ABX_ERR_ARG;
+}
+
+} // namespace abx

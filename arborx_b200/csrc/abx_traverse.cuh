@@ -1,0 +1,282 @@
+// abx_traverse.cuh -- predicates and traversal cores shared by the query and
+// DBSCAN kernels.  See abx_query.cu for the behavioural contract.
+#pragma once
+#include "abx_common.cuh"
+
+namespace abx
+{
+
+constexpr int kThreads = 128;
+constexpr int kStackSize = 96; // >= 63 code bits + 31 index bits of tie-breaking
+
+// ---- predicates ------------------------------------------------------------------
+template <int PRED>
+struct Pred;
+
+template <>
+struct Pred<ABX_PRED_SPHERE3F>
+{
+  float cx, cy, cz, r, t; // t: largest d2 with sqrt(d2) <= r
+  __device__ __forceinline__ void load(float const *__restrict__ p, int64_t i)
+  {
+    float4 v = *reinterpret_cast<float4 const *>(p + 4 * i);
+    cx = v.x;
+    cy = v.y;
+    cz = v.z;
+    r = v.w;
+    t = sqrtThreshold(r);
+  }
+  // intersects(Sphere, Box): distance(centre, box) <= radius (Intersects.hpp:84-91)
+  __device__ __forceinline__ bool box(float4 lo, float4 hi) const
+  {
+    return pointBoxDist2(cx, cy, cz, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z) <= t;
+  }
+};
+
+template <>
+struct Pred<ABX_PRED_BOX3F>
+{
+  float lx, ly, lz, hx, hy, hz;
+  __device__ __forceinline__ void load(float const *__restrict__ p, int64_t i)
+  {
+    lx = p[6 * i];
+    ly = p[6 * i + 1];
+    lz = p[6 * i + 2];
+    hx = p[6 * i + 3];
+    hy = p[6 * i + 4];
+    hz = p[6 * i + 5];
+  }
+  // intersects(Box, Box): Intersects.hpp:53-65
+  __device__ __forceinline__ bool box(float4 lo, float4 hi) const
+  {
+    return !(lx > hi.x || hx < lo.x || ly > hi.y || hy < lo.y || lz > hi.z || hz < lo.z);
+  }
+};
+
+template <>
+struct Pred<ABX_PRED_POINT3F>
+{
+  float x, y, z;
+  __device__ __forceinline__ void load(float const *__restrict__ p, int64_t i)
+  {
+    x = p[3 * i];
+    y = p[3 * i + 1];
+    z = p[3 * i + 2];
+  }
+  // intersects(Point, Box): Intersects.hpp:69-80
+  __device__ __forceinline__ bool box(float4 lo, float4 hi) const
+  {
+    return !(x > hi.x || x < lo.x || y > hi.y || y < lo.y || z > hi.z || z < lo.z);
+  }
+};
+
+// ---- point-triangle distance (ClosestPoint.hpp:69-153, Distance.hpp:112-123) ----
+__device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz)
+{
+  // misc/ArborX_Vector.hpp dot(): accumulate from 0 in index order, unfused
+  float r = __fmul_rn(ax, bx);
+  r = __fadd_rn(r, __fmul_rn(ay, by));
+  r = __fadd_rn(r, __fmul_rn(az, bz));
+  return r;
+}
+
+__device__ inline float pointTriangleDist2(float px, float py, float pz, float4 A, float4 B, float4 C)
+{
+  float abx_ = __fsub_rn(B.x, A.x), aby = __fsub_rn(B.y, A.y), abz = __fsub_rn(B.z, A.z);
+  float acx = __fsub_rn(C.x, A.x), acy = __fsub_rn(C.y, A.y), acz = __fsub_rn(C.z, A.z);
+  float apx = __fsub_rn(px, A.x), apy = __fsub_rn(py, A.y), apz = __fsub_rn(pz, A.z);
+  float qx, qy, qz; // closest point
+  float const d1 = dot3(abx_, aby, abz, apx, apy, apz);
+  float const d2 = dot3(acx, acy, acz, apx, apy, apz);
+  bool done = false;
+  float u = 0, v = 0, w = 0;
+  if (d1 <= 0 && d2 <= 0)
+  {
+    qx = A.x, qy = A.y, qz = A.z;
+    done = true;
+  }
+  float d3 = 0, d4 = 0, d5 = 0, d6 = 0;
+  if (!done)
+  {
+    float bpx = __fsub_rn(px, B.x), bpy = __fsub_rn(py, B.y), bpz = __fsub_rn(pz, B.z);
+    d3 = dot3(abx_, aby, abz, bpx, bpy, bpz);
+    d4 = dot3(acx, acy, acz, bpx, bpy, bpz);
+    if (d3 >= 0 && d4 <= d3)
+    {
+      qx = B.x, qy = B.y, qz = B.z;
+      done = true;
+    }
+  }
+  if (!done)
+  {
+    float cpx = __fsub_rn(px, C.x), cpy = __fsub_rn(py, C.y), cpz = __fsub_rn(pz, C.z);
+    d5 = dot3(abx_, aby, abz, cpx, cpy, cpz);
+    d6 = dot3(acx, acy, acz, cpx, cpy, cpz);
+    if (d6 >= 0 && d5 <= d6)
+    {
+      qx = C.x, qy = C.y, qz = C.z;
+      done = true;
+    }
+  }
+  if (!done)
+  {
+    bool comb = false;
+    float const vc = __fsub_rn(__fmul_rn(d1, d4), __fmul_rn(d3, d2));
+    if (vc <= 0 && d1 >= 0 && d3 <= 0)
+    {
+      float const t = __fdiv_rn(d1, __fsub_rn(d1, d3));
+      u = __fsub_rn(1.f, t), v = t, w = 0.f;
+      comb = true;
+    }
+    float vb = 0;
+    if (!comb)
+    {
+      vb = __fsub_rn(__fmul_rn(d5, d2), __fmul_rn(d1, d6));
+      if (vb <= 0 && d2 >= 0 && d6 <= 0)
+      {
+        float const t = __fdiv_rn(d2, __fsub_rn(d2, d6));
+        u = __fsub_rn(1.f, t), v = 0.f, w = t;
+        comb = true;
+      }
+    }
+    if (!comb)
+    {
+      float const va = __fsub_rn(__fmul_rn(d3, d6), __fmul_rn(d5, d4));
+      float const e43 = __fsub_rn(d4, d3), e56 = __fsub_rn(d5, d6);
+      if (va <= 0 && e43 >= 0 && e56 >= 0)
+      {
+        float const t = __fdiv_rn(e43, __fadd_rn(e43, e56));
+        u = 0.f, v = __fsub_rn(1.f, t), w = t;
+      }
+      else
+      {
+        float const denom = __fdiv_rn(1.f, __fadd_rn(__fadd_rn(va, vb), vc));
+        float const vv = __fmul_rn(vb, denom);
+        float const ww = __fmul_rn(vc, denom);
+        u = __fsub_rn(__fsub_rn(1.f, vv), ww), v = vv, w = ww;
+      }
+    }
+    // combine(): r[d] = u*a[d] + v*b[d] + w*c[d]
+    qx = __fadd_rn(__fadd_rn(__fmul_rn(u, A.x), __fmul_rn(v, B.x)), __fmul_rn(w, C.x));
+    qy = __fadd_rn(__fadd_rn(__fmul_rn(u, A.y), __fmul_rn(v, B.y)), __fmul_rn(w, C.y));
+    qz = __fadd_rn(__fadd_rn(__fmul_rn(u, A.z), __fmul_rn(v, B.z)), __fmul_rn(w, C.z));
+  }
+  float tx = __fsub_rn(qx, px), ty = __fsub_rn(qy, py), tz = __fsub_rn(qz, pz);
+  float r2 = __fmul_rn(tx, tx);
+  r2 = __fadd_rn(r2, __fmul_rn(ty, ty));
+  r2 = __fadd_rn(r2, __fmul_rn(tz, tz));
+  return r2;
+}
+
+// ---- spatial traversal core -----------------------------------------------------
+// Calls emit(child_ref, sorted_leaf_position) for every leaf whose box satisfies
+// the predicate; emit returns true to stop the traversal (early exit).
+template <class P, class Emit>
+__device__ __forceinline__ void traverseSpatial(Node64 const *__restrict__ nodes, P const &pred, Emit &&emit)
+{
+  int stack[kStackSize];
+  int sp = 0;
+  int node = 0;
+  while (true)
+  {
+    float4 const *f = reinterpret_cast<float4 const *>(nodes + node);
+    float4 const a0 = __ldg(f), a1 = __ldg(f + 1), a2 = __ldg(f + 2), a3 = __ldg(f + 3);
+    int const lref = __float_as_int(a0.w), rref = __float_as_int(a1.w);
+    bool hit_l = pred.box(a0, a1);
+    bool hit_r = pred.box(a2, a3);
+    if (hit_l && refIsLeaf(lref))
+    {
+      if (emit(lref, __float_as_int(a2.w)))
+        return;
+      hit_l = false;
+    }
+    if (hit_r && refIsLeaf(rref))
+    {
+      if (emit(rref, __float_as_int(a3.w)))
+        return;
+      hit_r = false;
+    }
+    if (hit_l)
+    {
+      if (hit_r)
+        stack[sp++] = rref;
+      node = lref;
+    }
+    else if (hit_r)
+      node = rref;
+    else
+    {
+      if (sp == 0)
+        return;
+      node = stack[--sp];
+    }
+  }
+}
+
+// exact leaf test for triangle leaves (only sphere predicates are defined in 3-D:
+// Intersects.hpp:118-126)
+template <int PRED>
+__device__ __forceinline__ bool triangleLeafTest(Pred<PRED> const &, float4 const *, int)
+{
+  return true;
+}
+template <>
+__device__ __forceinline__ bool triangleLeafTest<ABX_PRED_SPHERE3F>(Pred<ABX_PRED_SPHERE3F> const &p,
+                                                                     float4 const *__restrict__ leaf_tri, int pos)
+{
+  float4 A = __ldg(leaf_tri + 3 * (size_t)pos), B = __ldg(leaf_tri + 3 * (size_t)pos + 1),
+         C = __ldg(leaf_tri + 3 * (size_t)pos + 2);
+  return pointTriangleDist2(p.cx, p.cy, p.cz, A, B, C) <= p.t;
+}
+
+// ---- half traversal ---------------------------------------------------------------
+// Leaf i (sorted position) pairs with every leaf j > i within r: the subtrees to
+// the right of the root-to-leaf path, which is what starting at rope(i) visits in
+// the reference (HalfTraversal.hpp:52-74).
+template <class Emit>
+__device__ __forceinline__ void traverseHalf(Node64 const *__restrict__ nodes, int i,
+                                             Pred<ABX_PRED_SPHERE3F> const &pred, Emit &&emit)
+{
+  int stack[kStackSize];
+  int sp = 0;
+  int node = 0;
+  while (true)
+  {
+    float4 const *f = reinterpret_cast<float4 const *>(nodes + node);
+    float4 const a0 = __ldg(f), a1 = __ldg(f + 1), a2 = __ldg(f + 2), a3 = __ldg(f + 3);
+    int const lref = __float_as_int(a0.w), rref = __float_as_int(a1.w);
+    int const rl = __float_as_int(a2.w), rr = __float_as_int(a3.w);
+    // left subtree covers [rl, split], split = position rl for a leaf, Karras
+    // index of the left child otherwise; it holds leaves > i iff split > i
+    int const split = refIsLeaf(lref) ? rl : lref;
+    bool hit_l = (split > i) && pred.box(a0, a1);
+    bool hit_r = (rr > i) && pred.box(a2, a3);
+    if (hit_l && refIsLeaf(lref))
+    {
+      emit(lref, rl);
+      hit_l = false;
+    }
+    if (hit_r && refIsLeaf(rref))
+    {
+      emit(rref, rr);
+      hit_r = false;
+    }
+    if (hit_l)
+    {
+      if (hit_r)
+        stack[sp++] = rref;
+      node = lref;
+    }
+    else if (hit_r)
+      node = rref;
+    else
+    {
+      if (sp == 0)
+        return;
+      node = stack[--sp];
+    }
+  }
+}
+
+
+} // namespace abx

@@ -1,0 +1,193 @@
+/*
+ * abx.h -- C ABI of the B200-native geometric-search engine (libabx.so).
+ *
+ * This is the drop-in boundary for ArborX's hot path: BVH construction,
+ * spatial / nearest queries with CRS output, DBSCAN.  The reference has no FFI
+ * (its boundary is a C++ template API), so every entry point below cites the
+ * reference interface it replaces (paths relative to the reference's src/).
+ * A header-only C++ facade with the reference's spellings sits on top of this
+ * ABI (include/ArborX_B200.hpp); INTEGRATION.md shows the bindings.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++/torch types cross the boundary;
+ *  - `stream` is a cudaStream_t passed as void* (the reference's execution
+ *    space instance, e.g. spatial/ArborX_LinearBVH.hpp:68-73): every kernel of a
+ *    call is enqueued on it;
+ *  - `*_dev` pointers are device memory, `*_host` pointers host memory;
+ *  - all functions return an abx_status; abx_last_error() gives the message of
+ *    the last failure on the calling thread.  ABX_ERR_SEARCH corresponds to the
+ *    reference throwing ArborX::SearchException (misc/ArborX_Exception.hpp:19-38);
+ *  - there is no CPU fallback: without a CUDA device every compute entry point
+ *    fails with ABX_ERR_CUDA.
+ */
+#ifndef ABX_H
+#define ABX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ABX_VERSION 100
+#if defined(__GNUC__)
+#define ABX_API __attribute__((visibility("default")))
+#else
+#define ABX_API
+#endif
+
+typedef int abx_status;
+enum
+{
+  ABX_OK = 0,
+  ABX_ERR_SEARCH = 1,    /* precondition failure == ArborX::SearchException */
+  ABX_ERR_CUDA = 2,      /* CUDA runtime error / no device */
+  ABX_ERR_PRECISION = 3, /* FDBSCAN-DenseBox loss-of-precision guard (cluster/detail/ArborX_CartesianGrid.hpp:121-136) */
+  ABX_ERR_ARG = 4        /* malformed argument (null pointer, unknown enum) */
+};
+
+/* Primitive (indexable) layouts: geometry/ArborX_Point.hpp:24-38, ArborX_Box.hpp:32-67,
+ * ArborX_Triangle.hpp:21-26 -- tightly packed float arrays. */
+enum
+{
+  ABX_PRIM_POINT3F = 0, /* 3 floats: x y z */
+  ABX_PRIM_BOX3F = 1,   /* 6 floats: min xyz, max xyz */
+  ABX_PRIM_TRI3F = 2    /* 9 floats: a, b, c */
+};
+/* Predicate geometries: spatial/detail/ArborX_Predicates.hpp:83-101,130-147 */
+enum
+{
+  ABX_PRED_SPHERE3F = 0, /* intersects(Sphere): 4 floats centre xyz, radius (geometry/ArborX_Sphere.hpp:25-47) */
+  ABX_PRED_BOX3F = 1,    /* intersects(Box):    6 floats */
+  ABX_PRED_POINT3F = 2   /* intersects(Point) / nearest(Point, k): 3 floats */
+};
+
+/* Experimental::TraversalPolicy (spatial/detail/ArborX_TraversalPolicy.hpp:19-48) */
+typedef struct abx_policy
+{
+  int32_t buffer_size;     /* 0: two-pass; +b: soft preallocation; -b: hard (overflow -> ABX_ERR_SEARCH) */
+  int32_t sort_predicates; /* non-zero: Morton32-sort predicates (default in the reference) */
+} abx_policy;
+
+/* Output allocation.  The reference re-allocates the caller's Views
+ * (spatial/detail/ArborX_CrsGraphWrapperImpl.hpp:257,286,337,349); across a C ABI
+ * the caller supplies the allocator instead.  `which`: 0 offsets, 1 indices,
+ * 2 distances.  Must return device memory of at least `bytes` (may return NULL
+ * for bytes == 0).  Passing a NULL allocator makes the library allocate with
+ * cudaMallocAsync on `stream`; release those with abx_free(). */
+typedef void *(*abx_alloc_fn)(void *user, int which, size_t bytes);
+
+typedef struct abx_bvh abx_bvh;
+
+ABX_API const char *abx_last_error(void);
+ABX_API int abx_version(void);
+/* number of kernel launches issued by this library on the calling process so far
+ * (bench.py reports the delta over the timed region as gpu_launches) */
+ABX_API int64_t abx_launch_count(void);
+ABX_API abx_status abx_free(void *stream, void *ptr_dev);
+/* Per-kernel device timing (the analogue of the reference's Kokkos-Tools regions,
+ * SURVEY.md section 5): CUDA events on the launching stream around every launch.
+ * enable(1) clears and starts recording, enable(0) stops.  report() synchronises
+ * and writes "name\tlaunches\ttotal_ms\n" lines, most expensive first; it
+ * returns the bytes needed including the NUL. */
+ABX_API abx_status abx_profile_enable(int on);
+ABX_API int64_t abx_profile_report(char *buf, int64_t capacity);
+
+/* ---- BoundingVolumeHierarchy (spatial/ArborX_LinearBVH.hpp:50-142,171-256) ---- */
+/* ctor BVH(space, values): builds over n primitives; leaf value = original index */
+ABX_API abx_status abx_bvh_build(void *stream, int prim_kind, const void *prims_dev, int64_t n, abx_bvh **out);
+/* same with primitives in host memory: H2D copy is part of the call */
+ABX_API abx_status abx_bvh_build_host(void *stream, int prim_kind, const void *prims_host, int64_t n, abx_bvh **out);
+ABX_API abx_status abx_bvh_destroy(abx_bvh *bvh);
+ABX_API int64_t abx_bvh_size(const abx_bvh *bvh);               /* size()  :75-76 */
+ABX_API int abx_bvh_empty(const abx_bvh *bvh);                  /* empty() :78-79 */
+ABX_API abx_status abx_bvh_bounds(abx_bvh *bvh, float out6[6]); /* bounds() :81-82; blocks like the ctor's root-box copy
+                                                           (spatial/detail/ArborX_TreeConstruction.hpp:108-113) */
+/* bytes of device memory held by the tree */
+ABX_API int64_t abx_bvh_memory_bytes(const abx_bvh *bvh);
+
+/* Structural parity hook (tests): writes the tree in the reference's node layout
+ * (spatial/detail/ArborX_Node.hpp:24-44, ArborX_HappyTreeFriends.hpp:26-85).  All
+ * pointers are device memory and may be NULL: leaf_rope[n], leaf_index[n],
+ * left_child[n-1], rope[n-1], boxes6[6(n-1)], sorted_codes[n]. */
+ABX_API abx_status abx_bvh_export_reference_layout(abx_bvh *bvh, void *stream, int32_t *leaf_rope, uint32_t *leaf_index,
+                                           int32_t *left_child, int32_t *rope, float *boxes6, uint64_t *sorted_codes);
+
+/* ---- query(space, predicates, indices, offsets, policy)  (ArborX_LinearBVH.hpp:90-110,
+ *      ArborX_CrsGraphWrapper.hpp:22-35, detail/ArborX_CrsGraphWrapperImpl.hpp:148-446) ---- */
+/* Spatial predicates -> CRS.  offsets has q+1 ints, row i = ORIGINAL query i. */
+ABX_API abx_status abx_query_spatial_crs(abx_bvh *bvh, void *stream, int pred_kind, const void *preds_dev, int64_t q,
+                                 const abx_policy *policy, abx_alloc_fn alloc, void *user, int32_t **offsets_dev,
+                                 uint32_t **indices_dev, int64_t *nnz);
+/* query(space, predicates, callback) with a counting callback: counts_dev[i] =
+ * number of matches of query i; limit > 0 stops each query at `limit` matches
+ * (CountUpToN early exit, cluster/detail/ArborX_FDBSCAN.hpp:31-46;
+ * CallbackTreeTraversalControl, detail/ArborX_Callbacks.hpp:24-28). */
+ABX_API abx_status abx_query_spatial_count(abx_bvh *bvh, void *stream, int pred_kind, const void *preds_dev, int64_t q,
+                                   int sort_predicates, int32_t limit, int32_t *counts_dev);
+/* nearest(Point, k) -> CRS, rows ascending by distance (detail/ArborX_TreeTraversal.hpp:180-335).
+ * k_per_query_dev may be NULL (uniform k).  distances_dev may be NULL. */
+ABX_API abx_status abx_query_nearest_crs(abx_bvh *bvh, void *stream, const void *points_dev, int64_t q, int32_t k,
+                                 const int32_t *k_per_query_dev, const abx_policy *policy, abx_alloc_fn alloc,
+                                 void *user, int32_t **offsets_dev, uint32_t **indices_dev, float **distances_dev,
+                                 int64_t *nnz);
+/* Host-buffer variants (end-to-end path): predicates in host memory, results
+ * copied into host arrays obtained from `alloc_host` (which: as above). */
+ABX_API abx_status abx_query_spatial_crs_host(abx_bvh *bvh, void *stream, int pred_kind, const void *preds_host, int64_t q,
+                                      const abx_policy *policy, abx_alloc_fn alloc_host, void *user,
+                                      int32_t **offsets_host, uint32_t **indices_host, int64_t *nnz);
+ABX_API abx_status abx_query_nearest_crs_host(abx_bvh *bvh, void *stream, const void *points_host, int64_t q, int32_t k,
+                                      const abx_policy *policy, abx_alloc_fn alloc_host, void *user,
+                                      int32_t **offsets_host, uint32_t **indices_host, float **distances_host,
+                                      int64_t *nnz);
+
+/* Experimental::HalfTraversal over point leaves with WithinRadiusGetter
+ * (detail/ArborX_HalfTraversal.hpp:24-75, cluster/ArborX_DBSCAN.hpp:55-70): every
+ * unordered pair of leaves within r exactly once, as (original index, original
+ * index).  pairs_dev may be NULL (count only); at most `capacity` pairs are stored. */
+ABX_API abx_status abx_half_traversal_pairs(abx_bvh *bvh, void *stream, float r, uint32_t *pairs_dev, int64_t capacity,
+                                    int64_t *count);
+
+/* ---- ArborX::dbscan(space, points, eps, minpts, labels, params) (cluster/ArborX_DBSCAN.hpp:180-223) ---- */
+enum
+{
+  ABX_DBSCAN_FDBSCAN = 0,
+  ABX_DBSCAN_FDBSCAN_DENSEBOX = 1
+};
+enum
+{
+  ABX_DBSCAN_DBSCAN = 0,
+  ABX_DBSCAN_DBSCAN_STAR = 1
+};
+/* labels_dev[n]: cluster id (smallest original index among the cluster's core
+ * points) or -1 for noise.  eps <= 0 or minpts < 2 -> ABX_ERR_SEARCH (:240-241). */
+ABX_API abx_status abx_dbscan(void *stream, const float *xyz_dev, int64_t n, float eps, int32_t minpts, int implementation,
+                      int algorithm, int32_t *labels_dev);
+ABX_API abx_status abx_dbscan_host(void *stream, const float *xyz_host, int64_t n, float eps, int32_t minpts,
+                           int implementation, int algorithm, int32_t *labels_host);
+
+/* ---- stage-level entry points (tests localise mismatches with these) ---- */
+/* TreeConstruction::calculateBoundingBoxOfTheScene (detail/ArborX_TreeConstruction.hpp:27-39) */
+ABX_API abx_status abx_scene_bounds(void *stream, int prim_kind, const void *prims_dev, int64_t n, float *bounds6_dev);
+/* projectOntoSpaceFillingCurve with Morton64 (detail/ArborX_SpaceFillingCurves.hpp:45-57,67-84) */
+ABX_API abx_status abx_morton64(void *stream, int prim_kind, const void *prims_dev, int64_t n, const float *bounds6_dev,
+                        uint64_t *codes_dev);
+/* Morton32 of predicate centroids (ArborX_LinearBVH.hpp:287-298) */
+ABX_API abx_status abx_morton32(void *stream, int pred_kind, const void *preds_dev, int64_t q, const float *bounds6_dev,
+                        uint32_t *codes_dev);
+/* sortObjects (misc/ArborX_SortUtils.hpp:28-43): sorts keys in place (stable) and
+ * writes the permutation */
+ABX_API abx_status abx_sort_u64(void *stream, uint64_t *keys_dev, uint32_t *perm_dev, int64_t n);
+ABX_API abx_status abx_sort_u32(void *stream, uint32_t *keys_dev, uint32_t *perm_dev, int64_t n);
+/* generateHierarchy on caller-sorted codes, primitives taken in the given order
+ * (test/tstDetailsTreeConstruction.cpp:152-175) */
+ABX_API abx_status abx_bvh_build_from_sorted_codes(void *stream, int prim_kind, const void *prims_dev,
+                                           const uint64_t *sorted_codes_dev, int64_t n, abx_bvh **out);
+/* exclusive scan used by the CRS path (kokkos_ext/ArborX_KokkosExtStdAlgorithms.hpp) */
+ABX_API abx_status abx_exclusive_scan_i32(void *stream, const int32_t *in_dev, int32_t *out_dev, int64_t n_plus_1);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ABX_H */
