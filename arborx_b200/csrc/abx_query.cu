@@ -432,6 +432,7 @@ abx_status spatialLaunch(cudaStream_t s, abx_bvh *t, int pred_kind, void const *
     return ABX_OK;
   int const grid = divUp(q, kThreads);
   int const n = (int)t->n;
+  char const *tag = MODE == MODE_COUNT ? "spatialKernel<count>" : "spatialKernel<fill>";
   if (t->kind == ABX_PRIM_TRI3F && pred_kind != ABX_PRED_SPHERE3F)
   {
     setError("only intersects(Sphere) is defined for triangle primitives");
@@ -451,13 +452,13 @@ abx_status spatialLaunch(cudaStream_t s, abx_bvh *t, int pred_kind, void const *
   }
   if (t->kind == ABX_PRIM_TRI3F)
   {
-    ABX_DISPATCH_PRED(pred_kind, ABX_LAUNCH((spatialKernel<P, MODE, true>), grid, kThreads, 0, s, t->nodes,
+    ABX_DISPATCH_PRED(pred_kind, ABX_LAUNCH_TAGGED(tag, (spatialKernel<P, MODE, true>), grid, kThreads, 0, s, t->nodes,
                                             t->leaf_box, t->leaf_tri, n, (float const *)preds, q, qperm, limit, counts,
                                             offsets, indices));
   }
   else
   {
-    ABX_DISPATCH_PRED(pred_kind, ABX_LAUNCH((spatialKernel<P, MODE, false>), grid, kThreads, 0, s, t->nodes,
+    ABX_DISPATCH_PRED(pred_kind, ABX_LAUNCH_TAGGED(tag, (spatialKernel<P, MODE, false>), grid, kThreads, 0, s, t->nodes,
                                             t->leaf_box, t->leaf_tri, n, (float const *)preds, q, qperm, limit, counts,
                                             offsets, indices));
   }
@@ -513,10 +514,10 @@ abx_status nearestQuery(cudaStream_t s, abx_bvh *t, float const *pts, int64_t q,
   do                                                                                                                   \
   {                                                                                                                    \
     if (tri)                                                                                                           \
-      ABX_LAUNCH((nearestKernel<KCAP, true>), grid, kThreads, 0, s, t->nodes, t->leaf_box, t->leaf_tri, n, t->kind,    \
+      ABX_LAUNCH_TAGGED("nearestKernel<" #KCAP ",tri>", (nearestKernel<KCAP, true>), grid, kThreads, 0, s, t->nodes, t->leaf_box, t->leaf_tri, n, t->kind,    \
                  pts, q, qperm, k, row_stride, k_per_query, offsets, counts, indices, distances, SCRATCH);                         \
     else                                                                                                               \
-      ABX_LAUNCH((nearestKernel<KCAP, false>), grid, kThreads, 0, s, t->nodes, t->leaf_box, t->leaf_tri, n, t->kind,   \
+      ABX_LAUNCH_TAGGED("nearestKernel<" #KCAP ">", (nearestKernel<KCAP, false>), grid, kThreads, 0, s, t->nodes, t->leaf_box, t->leaf_tri, n, t->kind,   \
                  pts, q, qperm, k, row_stride, k_per_query, offsets, counts, indices, distances, SCRATCH);                         \
   } while (0)
   if (kmax <= 1)

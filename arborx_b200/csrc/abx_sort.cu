@@ -343,7 +343,8 @@ abx_status sortPairsImpl(cudaStream_t s, KeyT *keys, unsigned *vals, int64_t n, 
   unsigned *states = counters + PASSES;
 
   int const hist_grid = (int)std::min<int64_t>(divUp(n, kSortThreads * 8), kNumSMs * 8);
-  ABX_LAUNCH((radixHistogramKernel<KeyT, BITS, PASSES>), hist_grid, kSortThreads, 0, s, keys, n, hist);
+  ABX_LAUNCH_TAGGED(sizeof(KeyT) == 8 ? "radixHistogramKernel<u64>" : "radixHistogramKernel<u32>",
+                    (radixHistogramKernel<KeyT, BITS, PASSES>), hist_grid, kSortThreads, 0, s, keys, n, hist);
   ABX_LAUNCH((radixScanHistKernel<BITS>), PASSES, kSortThreads, 0, s, hist);
 
   auto kernel = onesweepPassKernel<KeyT, BITS>;

@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""bench.py -- the bvh_driver workload of BASELINE.json (configs[1]) on B200.
+
+One "step" = one pass of the hot path over one batch of synthetic input:
+    BVH build over n points  +  intersects(sphere) CRS query with q spheres
+    +  nearest(k=10) CRS query with q points
+with n = q = 10M filled-box points, r = cbrt(10*6/pi), predicates Morton-sorted,
+buffer_size = 0 (benchmarks/bvh_driver/benchmark_registration.hpp:129-205).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+prints ONE JSON line (see the task contract).  `value` is the aggregate item rate
+(n + 2q items per step) with inputs resident in HBM; `components` holds the three
+rates BASELINE.json names (build Mprims/s, radius Mqueries/s, kNN Mqueries/s) and
+their HBM-roofline fractions; `e2e` is the same step through the host-buffer C-ABI
+entry points (pinned host inputs, results copied back to the host).
+
+--impl reference times the CPU restatement of the reference (oracle/, OpenMP, all
+host threads) -- the real reference cannot be built here (Kokkos absent).
+Multi-GPU (--gpus N under torchrun): the single-tree path does not shard ("replicas
+only"): every rank runs the same step on its own tree, weak scaling.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "BVH build Mprims/s; radius & kNN(k=10) Mqueries/s at 10M pts; % HBM roofline"
+UNIT = "Mitems/s (n prims + q radius queries + q kNN queries per step second)"
+K_NEIGHBORS = 10
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", d
+    return 6650.0, "fallback (B200_PROFILING.md)", {}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, power, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_inputs(n, q):
+    from tests import clouds
+    values = clouds.filled_box(0x5EED0001, n)
+    queries = clouds.filled_box(0x5EED0002, q)
+    r = clouds.bvh_driver_radius(K_NEIGHBORS)
+    spheres = np.concatenate([queries, np.full((q, 1), r, np.float32)], 1).astype(np.float32)
+    return values, queries, spheres, float(r)
+
+
+# ------------------------------------------------------------------ CPU arm ----
+def cpu_run(values, queries, spheres, q_sample, build_n=None):
+    """Times the oracle (restated reference, OpenMP) on a bounded sample: full build,
+    q_sample of the queries.  Returns rates, the per-query traversal counters used for
+    the algorithmic-byte figures, and the wall time."""
+    import oracle
+    n = len(values) if build_n is None else build_n
+    t0 = time.time()
+    tree = oracle.Tree(values[:n])
+    t_build = time.time() - t0
+    sp = spheres[:q_sample]
+    t0 = time.time()
+    off, idx = tree.spatial_crs(sp, oracle.PRED_SPHERE, True, 0)
+    t_radius = time.time() - t0
+    t0 = time.time()
+    koff, kidx, kd = tree.nearest_crs(queries[:q_sample], K_NEIGHBORS, True)
+    t_knn = time.time() - t0
+    _, c_sp = tree.spatial_count(sp, counters=True)
+    _, _, _, c_nn = tree.nearest_crs(queries[:q_sample], K_NEIGHBORS, True, counters=True)
+    return dict(n=n, q_sample=q_sample, t_build=t_build, t_radius=t_radius, t_knn=t_knn,
+                nnz_per_query=float(off[-1]) / q_sample,
+                spatial_I=float(c_sp[0]) / q_sample, spatial_L=float(c_sp[1]) / q_sample,
+                nearest_I=float(c_nn[0]) / q_sample, nearest_L=float(c_nn[1]) / q_sample,
+                cores=oracle.num_threads())
+
+
+def combined_rate(n, q, t_build, t_radius, t_knn):
+    return (n + 2 * q) / (t_build + t_radius + t_knn) / 1e6
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n, q = args.n, args.q
+    values, queries, spheres, r = make_inputs(n, q)
+    qs = min(q, args.cpu_sample)
+    times = []
+    res = None
+    for it in range(args.warmup + args.steps):
+        res = cpu_run(values, queries, spheres, qs)
+        scale = q / qs
+        step = res["t_build"] + (res["t_radius"] + res["t_knn"]) * scale
+        if it >= args.warmup:
+            times.append((step, res["t_build"], res["t_radius"] * scale, res["t_knn"] * scale))
+    t = np.mean(np.array(times), 0)
+    value = (n + 2 * q) / t[0] / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t[0] * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(n, q, r),
+        "components": {"build_Mprims_s": n / t[1] / 1e6, "radius_Mqueries_s": q / t[2] / 1e6,
+                       "knn_Mqueries_s": q / t[3] / 1e6},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": res["cores"], "kind": "port",
+                         "sample": "per step: full build of n=%d points, radius+kNN on the first %d of %d queries "
+                                   "(query time scaled by q/sample); oracle/arborx_oracle.cpp, OpenMP" % (n, qs, q)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(n, q, r):
+    return {"workload": "bvh_driver filled_box: build + intersects(sphere) CRS + nearest(k=10) CRS "
+                        "(BASELINE.json configs[1])",
+            "n_values": n, "n_queries": q, "k": K_NEIGHBORS, "radius": r, "sort_predicates": True, "buffer_size": 0,
+            "cloud": "uniform in [-cbrt(n), cbrt(n)]^3, counter-based RNG (tests/clouds.py)",
+            "cache": "inputs and tree (%.0f MB nodes) larger than the 126 MB L2; no explicit flush" % (64e-6 * n)}
+
+
+# ------------------------------------------------------------------ GPU arm ----
+def algorithmic_bytes(cpu, n, q, nnz):
+    """Per-launch algorithmic bytes of each kernel:
+    traversals are defined on the reference-layout tree from the oracle's counters
+    (32 B per internal-node test, 20 B per leaf test)."""
+    sp = 32.0 * cpu["spatial_I"] + 20.0 * cpu["spatial_L"]
+    nn = 32.0 * cpu["nearest_I"] + 20.0 * cpu["nearest_L"]
+    return {
+        "spatialKernel<count>": q * (sp + 16 + 4),
+        "spatialKernel<fill>": q * (sp + 16 + 4) + 4.0 * nnz,
+        "nearestKernel": q * (nn + 12 + 4 * K_NEIGHBORS),
+        "onesweepPassKernel<u64>": 24.0 * n,
+        "onesweepPassKernel<u32>": 16.0 * q,
+        "hierarchyKernel": 64.0 * n,
+        "radixHistogramKernel<u64>": 8.0 * n,
+        "morton64Kernel": 20.0 * n,
+        "sceneBoundsKernel": 12.0 * n,
+    }
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import arborx_b200 as abx
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n, q = args.n, args.q
+    values, queries, spheres, r = make_inputs(n, q)
+    space = abx.ExecutionSpace()
+    d_values = torch.from_numpy(values).cuda()
+    d_queries = torch.from_numpy(queries).cuda()
+    d_spheres = torch.from_numpy(spheres).cuda()
+    p_spatial = abx.intersects(d_spheres)
+    p_nearest = abx.nearest(d_queries, K_NEIGHBORS)
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def step(timers=None):
+        e = [ev() for _ in range(4)] if timers is not None else None
+        if e:
+            e[0].record()
+        bvh = abx.BoundingVolumeHierarchy(space, d_values)
+        if e:
+            e[1].record()
+        idx, off = bvh.query(space, p_spatial)
+        if e:
+            e[2].record()
+        kidx, koff = bvh.query(space, p_nearest)
+        if e:
+            e[3].record()
+            timers.append(e)
+        return idx.numel()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        nnz = step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    abx.profile_enable(True)
+    launches0 = abx.launch_count()
+    timers = []
+    t_start, t_stop = ev(), ev()
+    barrier()
+    t_start.record()
+    for _ in range(args.steps):
+        nnz = step(timers)
+    t_stop.record()
+    barrier()
+    launches = abx.launch_count() - launches0
+    prof = abx.profile_report()
+    abx.profile_enable(False)
+    clocks = sampler.stop()
+    elapsed_ms = t_start.elapsed_time(t_stop)
+    parts = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(3)] for e in timers]).mean(0)  # build, radius, knn
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = world * (n + 2 * q) / (ms_per_step * 1e-3) / 1e6
+
+    # ---- end to end through the host-buffer C-ABI entry points -----------------------
+    h_values = torch.from_numpy(values).pin_memory()
+    h_spheres = torch.from_numpy(spheres).pin_memory()
+    h_queries = torch.from_numpy(queries).pin_memory()
+    hp_spatial = abx.intersects(h_spheres)
+    hp_nearest = abx.nearest(h_queries, K_NEIGHBORS)
+
+    def e2e_step():
+        bvh = abx.BoundingVolumeHierarchy(space, h_values)
+        idx, off = bvh.query(space, hp_spatial)
+        kidx, koff = bvh.query(space, hp_nearest)
+        # results are host tensors: touch them so the step really ends on the host
+        return int(off[-1]) + int(koff[-1]), idx.numel(), kidx.numel()
+
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    for _ in range(max(1, min(args.warmup, 2))):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        _, n_idx, n_kidx = e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * (n + 2 * q) / e2e_s / 1e6
+    h2d = 12 * n + 16 * q + 12 * q
+    d2h = 4 * (q + 1) + 4 * n_idx + 4 * (q + 1) + 4 * n_kidx
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline (bounded sample) + traversal counters for the roofline ---------
+    qs = min(q, args.cpu_sample)
+    cpu = cpu_run(values, queries, spheres, qs)
+    scale = q / qs
+    cpu_value = combined_rate(n, q, cpu["t_build"], cpu["t_radius"] * scale, cpu["t_knn"] * scale)
+
+    peak, peak_src, _ = peaks()
+    alg = algorithmic_bytes(cpu, n, q, nnz)
+    # kernel table from the live CUDA-event profile of the timed region
+    kernels = []
+    for name, cnt, ms in prof:
+        key = None
+        for kname in alg:  # tags are resolved names, e.g. "spatialKernel<count>", "(hierarchyKernel<K>)"
+            if kname in name or ("<" not in kname and kname in name.split("<")[0]):
+                key = kname
+        per_launch_ms = ms / cnt
+        row = {"kernel": name, "launches": cnt, "total_ms": round(ms, 4), "avg_ms": round(per_launch_ms, 5)}
+        if key:
+            row["algorithmic_bytes"] = alg[key]
+            row["achieved_gbs"] = alg[key] / (per_launch_ms * 1e-3) / 1e9
+        kernels.append(row)
+    top = kernels[0] if kernels else None
+    roofline = None
+    if top and "achieved_gbs" in top:
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(top["kernel"].split("<")[0].strip("( "))
+        roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": top["achieved_gbs"], "peak": peak,
+                    "unit": "GB/s", "frac": top["achieved_gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
+                    "share_of_step": top["total_ms"] / (ms_per_step * args.steps)}
+
+    # phase rooflines (SURVEY.md 8(d) / BASELINE.md section 2)
+    b_build = 300.0 * n
+    sp_pass = 32.0 * cpu["spatial_I"] + 20.0 * cpu["spatial_L"]
+    b_radius = q * (2 * sp_pass + 16 + 4 + 92) + 4.0 * nnz
+    b_knn = q * (32.0 * cpu["nearest_I"] + 20.0 * cpu["nearest_L"] + 16 + 4 + 4 * K_NEIGHBORS + 92)
+    comp = {
+        "build_Mprims_s": n / parts[0] / 1e3, "radius_Mqueries_s": q / parts[1] / 1e3,
+        "knn_Mqueries_s": q / parts[2] / 1e3,
+        "build_ms": parts[0], "radius_ms": parts[1], "knn_ms": parts[2],
+        "build_roofline_frac": b_build / (parts[0] * 1e-3) / 1e9 / peak,
+        "radius_roofline_frac": b_radius / (parts[1] * 1e-3) / 1e9 / peak,
+        "knn_roofline_frac": b_knn / (parts[2] * 1e-3) / 1e9 / peak,
+        "algorithmic_bytes": {"build": b_build, "radius": b_radius, "knn": b_knn},
+        "results_per_radius_query": nnz / q,
+    }
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(n, q, r),
+        "components": comp,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+                "api": "abx_bvh_build_host + abx_query_spatial_crs_host + abx_query_nearest_crs_host"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "kernels": kernels[:12],
+        "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cpu["cores"], "kind": "port",
+                         "sample": "full build of n=%d points; radius+kNN on the first %d of %d queries, query time "
+                                   "scaled by q/sample; oracle/arborx_oracle.cpp (OpenMP)" % (n, qs, q),
+                         "build_Mprims_s": n / cpu["t_build"] / 1e6,
+                         "radius_Mqueries_s": qs / cpu["t_radius"] / 1e6, "knn_Mqueries_s": qs / cpu["t_knn"] / 1e6,
+                         "counters_per_query": {k: cpu[k] for k in ("spatial_I", "spatial_L", "nearest_I",
+                                                                    "nearest_L", "nnz_per_query")}},
+    }
+    if world > 1:
+        line["config"]["parallelism"] = "replicas only: %d independent trees (single-tree path does not shard)" % world
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=10_000_000)
+    ap.add_argument("--q", type=int, default=None)
+    ap.add_argument("--cpu-sample", type=int, default=500_000, help="queries timed on the CPU baseline")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    args = ap.parse_args()
+    if args.q is None:
+        args.q = args.n
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
