@@ -108,19 +108,28 @@ def make_nearest(points, k):
 
 
 class _Allocator:
-    """abx_alloc_fn backed by torch tensors (the library 'resizes the caller's views')."""
+    """abx_alloc_fn backed by torch tensors (the library 'resizes the caller's views').  Host results
+    come from a small pool of pinned buffers that is reused across calls: cudaHostAlloc of a few hundred
+    MB per query would otherwise dominate the end-to-end time."""
     _DT = {0: torch.int32, 1: torch.int32, 2: torch.float32}
+    _pinned_pool = {}
 
-    def __init__(self, device, pinned_host=False):
+    def __init__(self, device, pinned_host=False, pool_key=None):
         self.device = device
         self.pinned_host = pinned_host
+        self.pool_key = pool_key
         self.out = {}
         self.fn = _lib.ALLOC_FN(self._alloc)
 
     def _alloc(self, user, which, nbytes):
         n = nbytes // 4
         if self.pinned_host:
-            t = torch.empty(n, dtype=self._DT[which], pin_memory=True)
+            key = (self.pool_key, which)
+            buf = _Allocator._pinned_pool.get(key)
+            if buf is None or buf.numel() < n:
+                buf = torch.empty(max(n, 1), dtype=self._DT[which], pin_memory=True)
+                _Allocator._pinned_pool[key] = buf
+            t = buf[:n]
         else:
             t = torch.empty(n, dtype=self._DT[which], device=self.device)
         self.out[which] = t
@@ -195,7 +204,8 @@ class BoundingVolumeHierarchy:
         d = predicates.data
         q = d.shape[0]
         host = not d.is_cuda
-        alloc = _Allocator(space.device, pinned_host=host)
+        # host results alias a per-(tree kind, predicate tag) pinned pool: valid until the next host query
+        alloc = _Allocator(space.device, pinned_host=host, pool_key=predicates.tag)
         off, idx, dist = C.c_void_p(), C.c_void_p(), C.c_void_p()
         nnz = C.c_int64()
         L = lib()
@@ -223,10 +233,14 @@ class BoundingVolumeHierarchy:
                                                        None, C.byref(pol), alloc.fn, None, C.byref(off), C.byref(idx),
                                                        want_d, C.byref(nnz)))
         dev = "cpu" if host else space.device
-        indices = alloc.out.get(1, torch.empty(0, dtype=torch.int32, device=dev))
-        offsets = alloc.out[0]
+        out = alloc.out
+        # break the allocator <-> ctypes-callback reference cycle now: otherwise the result
+        # tensors stay alive until the cyclic GC runs and device memory keeps growing
+        alloc.out, alloc.fn = {}, None
+        indices = out.get(1, torch.empty(0, dtype=torch.int32, device=dev))
+        offsets = out[0]
         if return_distances:
-            return indices, offsets, alloc.out.get(2, torch.empty(0, dtype=torch.float32, device=dev))
+            return indices, offsets, out.get(2, torch.empty(0, dtype=torch.float32, device=dev))
         return indices, offsets
 
     def count(self, space, predicates, limit=0, sort_predicates=True):

@@ -259,84 +259,240 @@ __device__ __forceinline__ void loadNodeBox(Node64 const *nodes, int k, Box &b)
   b.hi[2] = fmaxf(a1.z, a3.z);
 }
 
+// ---- hierarchy kernel ----------------------------------------------------------------
 // One thread per sorted leaf walks toward the root; the first thread to reach an
-// internal node stops (atomic flag in `ranges`), the second finishes the node.
+// internal node stops (atomic flag), the second finishes the node (Apetrei).
+//
+// B200 shape: a block owns a chunk of kHierThreads consecutive sorted leaves.  The
+// LBVH is the Cartesian tree of the delta array (key = (delta, index), larger key =
+// closer to the root), so a node p lies entirely inside the chunk [a, b] iff a
+// larger key exists on both sides of p inside [a-1, b]:
+//     max(delta[a-1 .. p-1]) > delta(p)   and   max(delta[p+1 .. b]) >= delta(p).
+// Such "local" nodes (> 95 % of all nodes) are built with shared-memory flags, boxes
+// and deltas: no global atomics, no device-scope fences, ~30-cycle hops.  Only nodes
+// that straddle a chunk boundary use the global CAS + __threadfence protocol.
+constexpr int kHierThreads = 512;
+constexpr int kHierWarps = kHierThreads / 32;
+
 template <int KIND>
-__global__ void __launch_bounds__(kThreads)
+struct LeafFloats
+{
+  static constexpr int value = (KIND == ABX_PRIM_POINT3F) ? 3 : 6;
+};
+
+__device__ __forceinline__ long long shflUp64(long long v, int o)
+{
+  return __shfl_up_sync(0xffffffffu, v, o);
+}
+__device__ __forceinline__ long long shflDown64(long long v, int o)
+{
+  return __shfl_down_sync(0xffffffffu, v, o);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kHierThreads)
     hierarchyKernel(int n, unsigned long long const *__restrict__ codes, unsigned const *__restrict__ perm,
                     float const *__restrict__ prims, Node64 *nodes, float4 *leaf_box, float4 *leaf_tri, int *ranges,
                     float *bounds6)
 {
-  int const i = blockIdx.x * kThreads + threadIdx.x;
-  if (i >= n)
-    return;
+  constexpr int LF = LeafFloats<KIND>::value;
+  __shared__ long long sdelta[kHierThreads + 1]; // sdelta[j] = delta(a - 1 + j)
+  __shared__ int sflag[kHierThreads];            // per local parent p-a: -1 untouched, -2 not local, else range end
+  __shared__ float snode[kHierThreads][6];       // box of finished local node (by Karras index - a)
+  __shared__ float sleaf[kHierThreads][LF];      // leaf boxes of the chunk
+  __shared__ unsigned sperm[kHierThreads];
+  __shared__ long long swarp[2][kHierWarps];
+
+  int const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int const a = blockIdx.x * kHierThreads;
+  int const cn = min(kHierThreads, n - a); // leaves in this chunk
   int const n_int = n - 1;
-  unsigned const orig = perm[i];
-  Box box = primBox<KIND>(prims, orig);
-  if (KIND == ABX_PRIM_POINT3F)
-    leaf_box[i] = make_float4(box.lo[0], box.lo[1], box.lo[2], __uint_as_float(orig));
+  int const i = a + tid;
+  bool const active = tid < cn;
+
+  unsigned orig = 0;
+  Box box = emptyBox();
+  if (active)
+  {
+    orig = perm[i];
+    box = primBox<KIND>(prims, orig);
+    if (KIND == ABX_PRIM_POINT3F)
+      leaf_box[i] = make_float4(box.lo[0], box.lo[1], box.lo[2], __uint_as_float(orig));
+    else
+    {
+      leaf_box[2 * (size_t)i] = make_float4(box.lo[0], box.lo[1], box.lo[2], __uint_as_float(orig));
+      leaf_box[2 * (size_t)i + 1] = make_float4(box.hi[0], box.hi[1], box.hi[2], 0.f);
+    }
+    if (KIND == ABX_PRIM_TRI3F)
+    {
+      float const *t = prims + 9 * (size_t)orig;
+      leaf_tri[3 * (size_t)i] = make_float4(t[0], t[1], t[2], 0.f);
+      leaf_tri[3 * (size_t)i + 1] = make_float4(t[3], t[4], t[5], 0.f);
+      leaf_tri[3 * (size_t)i + 2] = make_float4(t[6], t[7], t[8], 0.f);
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+      sleaf[tid][d] = box.lo[d];
+    if (LF == 6)
+    {
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+        sleaf[tid][3 + (LF == 6 ? d : 0)] = box.hi[d];
+    }
+    sperm[tid] = orig;
+    sdelta[tid + 1] = deltaOf(codes, i, n_int);
+  }
   else
+    sdelta[tid + 1] = LLONG_MAX;
+  if (tid == 0)
+    sdelta[0] = deltaOf(codes, a - 1, n_int);
+  __syncthreads();
+
+  // locality of parent p = a + tid (needs leaves p and p+1 in the chunk)
   {
-    leaf_box[2 * (size_t)i] = make_float4(box.lo[0], box.lo[1], box.lo[2], __uint_as_float(orig));
-    leaf_box[2 * (size_t)i + 1] = make_float4(box.hi[0], box.hi[1], box.hi[2], 0.f);
+    long long const mine = sdelta[tid + 1];
+    // inclusive prefix max of sdelta[0..tid]
+    long long pre = sdelta[tid];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+      long long t = shflUp64(pre, o);
+      if (lane >= o)
+        pre = max(pre, t);
+    }
+    // inclusive suffix max of w[t'] = sdelta[t'+2] (t'+2 <= cn), t' >= tid
+    long long suf = (tid + 2 <= cn) ? sdelta[tid + 2] : LLONG_MIN;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+      long long t = shflDown64(suf, o);
+      if (lane + o < 32)
+        suf = max(suf, t);
+    }
+    if (lane == 31)
+      swarp[0][warp] = pre;
+    if (lane == 0)
+      swarp[1][warp] = suf;
+    __syncthreads();
+    for (int w = 0; w < warp; ++w)
+      pre = max(pre, swarp[0][w]);
+    for (int w = warp + 1; w < kHierWarps; ++w)
+      suf = max(suf, swarp[1][w]);
+    bool const in_chunk = tid + 1 < cn;
+    bool const local = in_chunk && (pre > mine) && (suf >= mine);
+    sflag[tid] = local ? -1 : -2;
   }
-  if (KIND == ABX_PRIM_TRI3F)
-  {
-    float const *t = prims + 9 * (size_t)orig;
-    leaf_tri[3 * (size_t)i] = make_float4(t[0], t[1], t[2], 0.f);
-    leaf_tri[3 * (size_t)i + 1] = make_float4(t[3], t[4], t[5], 0.f);
-    leaf_tri[3 * (size_t)i + 2] = make_float4(t[6], t[7], t[8], 0.f);
-  }
+  __syncthreads();
+  if (!active)
+    return;
 
   int range_left = i, range_right = i;
-  long long delta_left = deltaOf(codes, i - 1, n_int);
-  long long delta_right = deltaOf(codes, i, n_int);
+  long long delta_left = sdelta[tid];      // delta(i - 1)
+  long long delta_right = sdelta[tid + 1]; // delta(i)
   int cur_ref = refLeaf(orig);
-
-  // publish the leaf record before signalling the parent
-  __threadfence();
+  bool global_mode = false;
 
   while (true)
   {
     bool const is_left_child = delta_right < delta_left;
+    int const apetrei_parent = is_left_child ? range_right : range_left - 1;
     Box sib;
     int sib_ref;
-    if (is_left_child)
+    if (!global_mode)
     {
-      int const apetrei_parent = range_right;
-      int const old = atomicCAS(&ranges[apetrei_parent], -1, range_left);
-      if (old == -1)
-        return; // first to arrive: the sibling's thread finishes this node
-      range_right = old;
-      int const right_child = apetrei_parent + 1;
-      bool const right_is_leaf = (right_child == range_right);
-      delta_right = deltaOf(codes, range_right, n_int);
-      __threadfence(); // acquire: the sibling published its record before its CAS
-      if (right_is_leaf)
-        loadLeafBox<KIND>(leaf_box, right_child, sib, sib_ref);
+      int const lp = apetrei_parent - a;
+      if (lp >= 0 && lp < cn - 1 && sflag[lp] != -2)
+      {
+        // ---- shared-memory protocol ------------------------------------------------
+        __threadfence_block(); // my record (sleaf / snode) before the flag
+        int const old = atomicCAS(&sflag[lp], -1, is_left_child ? range_left : range_right);
+        if (old == -1)
+          return;
+        __threadfence_block();
+        int sib_pos; // sorted position (leaf) or Karras index (internal) of the sibling
+        bool sib_is_leaf;
+        if (is_left_child)
+        {
+          range_right = old;
+          sib_pos = apetrei_parent + 1;
+          sib_is_leaf = (sib_pos == range_right);
+          delta_right = sdelta[range_right - a + 1];
+        }
+        else
+        {
+          range_left = old;
+          sib_pos = apetrei_parent;
+          sib_is_leaf = (sib_pos == range_left);
+          delta_left = sdelta[range_left - a];
+        }
+        int const sl = sib_pos - a;
+        if (sib_is_leaf)
+        {
+          volatile float *lf = sleaf[sl];
+#pragma unroll
+          for (int d = 0; d < 3; ++d)
+          {
+            sib.lo[d] = lf[d];
+            sib.hi[d] = LF == 6 ? lf[LF == 6 ? 3 + d : d] : lf[d];
+          }
+          sib_ref = refLeaf(sperm[sl]);
+        }
+        else
+        {
+          volatile float *nb = snode[sl];
+#pragma unroll
+          for (int d = 0; d < 3; ++d)
+          {
+            sib.lo[d] = nb[d];
+            sib.hi[d] = nb[3 + d];
+          }
+          sib_ref = sib_pos;
+        }
+      }
       else
       {
-        loadNodeBox(nodes, right_child, sib);
-        sib_ref = right_child;
+        global_mode = true;
+        __threadfence(); // publish my global record (leaf_box / Node64) device-wide
       }
     }
-    else
+    if (global_mode)
     {
-      int const apetrei_parent = range_left - 1;
-      int const old = atomicCAS(&ranges[apetrei_parent], -1, range_right);
-      if (old == -1)
-        return;
-      range_left = old;
-      int const left_child = apetrei_parent;
-      bool const left_is_leaf = (left_child == range_left);
-      delta_left = deltaOf(codes, range_left - 1, n_int);
-      __threadfence();
-      if (left_is_leaf)
-        loadLeafBox<KIND>(leaf_box, left_child, sib, sib_ref);
+      // ---- global protocol (nodes straddling a chunk boundary) ----------------------
+      if (is_left_child)
+      {
+        int const old = atomicCAS(&ranges[apetrei_parent], -1, range_left);
+        if (old == -1)
+          return; // first to arrive: the sibling's thread finishes this node
+        range_right = old;
+        int const right_child = apetrei_parent + 1;
+        bool const right_is_leaf = (right_child == range_right);
+        delta_right = deltaOf(codes, range_right, n_int);
+        __threadfence(); // acquire: the sibling published its record before its CAS
+        if (right_is_leaf)
+          loadLeafBox<KIND>(leaf_box, right_child, sib, sib_ref);
+        else
+        {
+          loadNodeBox(nodes, right_child, sib);
+          sib_ref = right_child;
+        }
+      }
       else
       {
-        loadNodeBox(nodes, left_child, sib);
-        sib_ref = left_child;
+        int const old = atomicCAS(&ranges[apetrei_parent], -1, range_right);
+        if (old == -1)
+          return;
+        range_left = old;
+        int const left_child = apetrei_parent;
+        bool const left_is_leaf = (left_child == range_left);
+        delta_left = deltaOf(codes, range_left - 1, n_int);
+        __threadfence();
+        if (left_is_leaf)
+          loadLeafBox<KIND>(leaf_box, left_child, sib, sib_ref);
+        else
+        {
+          loadNodeBox(nodes, left_child, sib);
+          sib_ref = left_child;
+        }
       }
     }
     int const karras_parent = delta_right < delta_left ? range_right : range_left;
@@ -364,7 +520,19 @@ __global__ void __launch_bounds__(kThreads)
       }
       return;
     }
-    __threadfence(); // release the finished node before signalling its parent
+    if (!global_mode)
+    {
+      // a local node's Karras index is an end of its range, inside the chunk
+      volatile float *nb = snode[karras_parent - a];
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+      {
+        nb[d] = box.lo[d];
+        nb[3 + d] = box.hi[d];
+      }
+    }
+    else
+      __threadfence(); // release the finished node before signalling its parent
   }
 }
 
@@ -555,7 +723,7 @@ abx_status buildHierarchy(cudaStream_t s, abx_bvh *t, void const *prims)
   TempBuffer<int> ranges;
   ABX_TRY(ranges.alloc(n - 1, s));
   ABX_CUDA_TRY(cudaMemsetAsync(ranges.ptr, 0xff, sizeof(int) * (size_t)(n - 1), s));
-  ABX_DISPATCH_PRIM(t->kind, ABX_LAUNCH((hierarchyKernel<K>), divUp(n, kThreads), kThreads, 0, s, n,
+  ABX_DISPATCH_PRIM(t->kind, ABX_LAUNCH((hierarchyKernel<K>), divUp(n, kHierThreads), kHierThreads, 0, s, n,
                                         (unsigned long long const *)t->codes, t->perm, (float const *)prims, t->nodes,
                                         t->leaf_box, t->leaf_tri, ranges.ptr, t->bounds_dev));
   return ABX_OK;

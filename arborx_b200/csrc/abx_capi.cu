@@ -151,10 +151,12 @@ static abx_status checkPredPointer(int pred_kind, void const *preds, int64_t q)
 }
 
 // spatial CRS: CrsGraphWrapperImpl.hpp:148-446.  The reference counts, scans and
-// traverses again to fill; buffer_size only changes how the first pass stores
-// results, never the result, so the policy is honoured for its error contract
-// (hard preallocation overflow throws, :263-268) and the count/fill scheme is used
-// for every value.
+// traverses again to fill (buffer_size = 0), or stores into per-query buffers in the
+// first pass and compacts.  Here ONE traversal counts and stages the first kStage
+// results of every query in a slot-major buffer; after the scan a compaction kernel
+// writes the CRS rows and re-traverses only queries with more than kStage results.
+// buffer_size never changes the result, so the policy is honoured for its error
+// contract only (hard preallocation overflow throws, :263-268).
 static abx_status spatialCrs(abx_bvh *bvh, cudaStream_t s, int pred_kind, void const *preds, int64_t q,
                              abx_policy const &policy, abx_alloc_fn alloc, void *user, int32_t **offsets_out,
                              uint32_t **indices_out, int64_t *nnz_out)
@@ -182,8 +184,16 @@ static abx_status spatialCrs(abx_bvh *bvh, cudaStream_t s, int pred_kind, void c
   TempBuffer<uint32_t> qperm;
   if (policy.sort_predicates && bvh->n > 1)
     ABX_TRY(predicatePermutation(s, bvh, pred_kind, preds, q, qperm));
-  // first pass: counts land in offsets[0..q) in ORIGINAL query order
-  ABX_TRY(spatialCount(s, bvh, pred_kind, preds, q, qperm.ptr, 0, offsets));
+  // the traversal: counts land in offsets[0..q) in ORIGINAL query order
+  TempBuffer<uint32_t> staging;
+  bool const staged = bvh->n > 1;
+  if (staged)
+  {
+    ABX_TRY(staging.alloc((size_t)spatialStageSlots() * (size_t)q, s));
+    ABX_TRY(spatialStage(s, bvh, pred_kind, preds, q, qperm.ptr, offsets, staging.ptr));
+  }
+  else
+    ABX_TRY(spatialCount(s, bvh, pred_kind, preds, q, qperm.ptr, 0, offsets));
   TempBuffer<int> overflow;
   int h_overflow = 0;
   if (policy.buffer_size < 0)
@@ -212,7 +222,10 @@ static abx_status spatialCrs(abx_bvh *bvh, cudaStream_t s, int pred_kind, void c
   }
   ABX_TRY(allocOut(alloc, user, 1, sizeof(uint32_t) * (size_t)total, s, &idx));
   *indices_out = (uint32_t *)idx;
-  ABX_TRY(spatialFill(s, bvh, pred_kind, preds, q, qperm.ptr, offsets, *indices_out));
+  if (staged)
+    ABX_TRY(spatialCompact(s, bvh, pred_kind, preds, q, qperm.ptr, offsets, *indices_out, staging.ptr));
+  else
+    ABX_TRY(spatialFill(s, bvh, pred_kind, preds, q, qperm.ptr, offsets, *indices_out));
   return ABX_OK;
 }
 

@@ -287,6 +287,11 @@ abx_status spatialCount(cudaStream_t s, abx_bvh *bvh, int pred_kind, void const 
                         uint32_t const *qperm, int32_t limit, int32_t *counts);
 abx_status spatialFill(cudaStream_t s, abx_bvh *bvh, int pred_kind, void const *preds, int64_t q,
                        uint32_t const *qperm, int32_t const *offsets, uint32_t *indices);
+int spatialStageSlots();
+abx_status spatialStage(cudaStream_t s, abx_bvh *bvh, int pred_kind, void const *preds, int64_t q,
+                        uint32_t const *qperm, int32_t *counts, uint32_t *staging);
+abx_status spatialCompact(cudaStream_t s, abx_bvh *bvh, int pred_kind, void const *preds, int64_t q,
+                          uint32_t const *qperm, int32_t const *offsets, uint32_t *indices, uint32_t const *staging);
 abx_status nearestQuery(cudaStream_t s, abx_bvh *bvh, float const *pts, int64_t q, int32_t k,
                         int32_t const *k_per_query, uint32_t const *qperm, int32_t const *offsets, int64_t total_rows,
                         int32_t *counts, uint32_t *indices, float *distances);

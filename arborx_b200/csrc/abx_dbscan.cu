@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(kThreads)
   pred.cx = p.x, pred.cy = p.y, pred.cz = p.z, pred.r = eps;
   pred.t = sqrtThreshold(eps);
   int count = 0;
-  traverseSpatial(nodes, pred, [&](int, int) { return ++count >= minpts; });
+  traverseSpatial<1>(nodes, leaf_box, pred, [&](unsigned, int) { return ++count >= minpts; });
   num_neigh[__float_as_uint(p.w)] = count;
 }
 
@@ -90,8 +90,8 @@ __global__ void __launch_bounds__(kThreads)
   bool const i_core = SPECIAL ? true : (num_neigh[i] >= minpts);
   if (STAR && !i_core)
     return; // border points do not take part in DBSCAN* (callback would return at once)
-  traverseHalf(nodes, t, pred, [&](int ref, int) {
-    int const j = (int)refOrig(ref);
+  traverseHalf(nodes, leaf_box, t, pred, [&](unsigned orig_j, int) {
+    int const j = (int)orig_j;
     bool const j_core = SPECIAL ? true : (num_neigh[j] >= minpts);
     if (STAR)
     {
@@ -325,7 +325,8 @@ __device__ __forceinline__ bool withinEps(float const *__restrict__ xyz, float p
 
 // CountUpToN_DenseBox (FDBSCANDenseBox.hpp:32-96) for the points of sparse cells
 __global__ void __launch_bounds__(kThreads)
-    denseCountKernel(Node64 const *__restrict__ nodes, int n_prims, float const *__restrict__ xyz,
+    denseCountKernel(Node64 const *__restrict__ nodes, float4 const *__restrict__ leaf_box, int n_prims,
+                     float const *__restrict__ xyz,
                      unsigned const *__restrict__ perm, int const *__restrict__ dense_cell_offsets, int num_dense,
                      int num_points_dense, int n, float eps, int minpts, int *__restrict__ num_neigh)
 {
@@ -339,8 +340,8 @@ __global__ void __launch_bounds__(kThreads)
   pred.t = sqrtThreshold(eps);
   int count = 0;
   if (n_prims >= 2)
-    traverseSpatial(nodes, pred, [&](int ref, int) {
-      int const k = (int)refOrig(ref);
+    traverseSpatial<2>(nodes, leaf_box, pred, [&](unsigned prim, int) {
+      int const k = (int)prim;
       if (k < num_dense)
       {
         int const ce = dense_cell_offsets[k + 1];
@@ -360,7 +361,8 @@ __global__ void __launch_bounds__(kThreads)
 // FDBSCANDenseBoxCallback (FDBSCANDenseBox.hpp:98-205): full traversal per point
 template <bool SPECIAL, bool STAR>
 __global__ void __launch_bounds__(kThreads)
-    denseMainKernel(Node64 const *__restrict__ nodes, int n_prims, float const *__restrict__ xyz,
+    denseMainKernel(Node64 const *__restrict__ nodes, float4 const *__restrict__ leaf_box, int n_prims,
+                    float const *__restrict__ xyz,
                     unsigned const *__restrict__ perm, int const *__restrict__ dense_cell_offsets, int num_dense,
                     int num_points_dense, int n, float eps, int minpts, int const *__restrict__ num_neigh,
                     int *labels)
@@ -379,8 +381,8 @@ __global__ void __launch_bounds__(kThreads)
   pred.t = sqrtThreshold(eps);
   if (n_prims < 2)
     return;
-  traverseSpatial(nodes, pred, [&](int ref, int) {
-    int const k = (int)refOrig(ref);
+  traverseSpatial<2>(nodes, leaf_box, pred, [&](unsigned prim, int) {
+    int const k = (int)prim;
     if (k < num_dense)
     {
       int const cs = dense_cell_offsets[k], ce = dense_cell_offsets[k + 1];
@@ -591,18 +593,18 @@ abx_status denseBox(cudaStream_t s, float const *xyz, int n, float eps, int minp
       ABX_LAUNCH(markDenseCoreKernel, divUp(num_points_dense, 256), 256, 0, s, perm2.ptr, num_points_dense,
                  num_neigh.ptr);
     if (n_sparse > 0)
-      ABX_LAUNCH(denseCountKernel, divUp(n_sparse, kThreads), kThreads, 0, s, t->nodes, n_prims, xyz, perm2.ptr,
+      ABX_LAUNCH(denseCountKernel, divUp(n_sparse, kThreads), kThreads, 0, s, t->nodes, t->leaf_box, n_prims, xyz, perm2.ptr,
                  dense_cell_offsets.ptr, num_dense, num_points_dense, n, eps, minpts, num_neigh.ptr);
   }
   int const grid = divUp(n, kThreads);
   if (special)
-    ABX_LAUNCH((denseMainKernel<true, false>), grid, kThreads, 0, s, t->nodes, n_prims, xyz, perm2.ptr,
+    ABX_LAUNCH((denseMainKernel<true, false>), grid, kThreads, 0, s, t->nodes, t->leaf_box, n_prims, xyz, perm2.ptr,
                dense_cell_offsets.ptr, num_dense, num_points_dense, n, eps, minpts, (int const *)nullptr, labels);
   else if (star)
-    ABX_LAUNCH((denseMainKernel<false, true>), grid, kThreads, 0, s, t->nodes, n_prims, xyz, perm2.ptr,
+    ABX_LAUNCH((denseMainKernel<false, true>), grid, kThreads, 0, s, t->nodes, t->leaf_box, n_prims, xyz, perm2.ptr,
                dense_cell_offsets.ptr, num_dense, num_points_dense, n, eps, minpts, (int const *)num_neigh.ptr, labels);
   else
-    ABX_LAUNCH((denseMainKernel<false, false>), grid, kThreads, 0, s, t->nodes, n_prims, xyz, perm2.ptr,
+    ABX_LAUNCH((denseMainKernel<false, false>), grid, kThreads, 0, s, t->nodes, t->leaf_box, n_prims, xyz, perm2.ptr,
                dense_cell_offsets.ptr, num_dense, num_points_dense, n, eps, minpts, (int const *)num_neigh.ptr, labels);
   return finalize(s, n, minpts, num_neigh.ptr, labels);
 }

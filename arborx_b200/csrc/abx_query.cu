@@ -17,36 +17,54 @@ namespace
 
 enum
 {
-  MODE_COUNT = 0,
-  MODE_FILL = 1
+  MODE_COUNT = 0,   // counts only (query with a counting callback, CountUpToN)
+  MODE_FILL = 1,    // second traversal writing rows at their CRS offsets
+  MODE_STAGE = 2,   // count AND keep the first kStage results of every query in a staging buffer
+  MODE_COMPACT = 3  // staged results -> CRS rows; re-traverses only the queries that overflowed
 };
+// Staging buffer of the single-traversal CRS path: slot-major ([slot][sorted query]),
+// so a warp writes/reads slot s of 32 neighbouring queries as one coalesced row.
+constexpr int kStage = 32;
 
-template <int PRED, int MODE, bool TRI>
+template <int PRED, int MODE, int LEAF_F4, bool TRI>
 __global__ void __launch_bounds__(kThreads)
     spatialKernel(Node64 const *__restrict__ nodes, float4 const *__restrict__ leaf_box,
                   float4 const *__restrict__ leaf_tri, int n, float const *__restrict__ preds, int64_t q,
                   unsigned const *__restrict__ qperm, int limit, int32_t *__restrict__ counts,
-                  int32_t const *__restrict__ offsets, uint32_t *__restrict__ indices)
+                  int32_t const *__restrict__ offsets, uint32_t *__restrict__ indices, uint32_t *__restrict__ staging)
 {
   int64_t const t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (t >= q)
     return;
   int64_t const qi = qperm ? (int64_t)qperm[t] : t;
+  int64_t base = 0;
+  if (MODE == MODE_FILL || MODE == MODE_COMPACT)
+    base = (int64_t)offsets[qi];
+  if (MODE == MODE_COMPACT)
+  {
+    int const c = offsets[qi + 1] - (int)base;
+    if (c <= kStage)
+    {
+      for (int s = 0; s < c; ++s)
+        indices[base + s] = staging[(size_t)s * q + t];
+      return;
+    }
+    // overflowed the staging slots: fall through to a filling traversal
+  }
   Pred<PRED> pred;
   pred.load(preds, qi);
   int count = 0;
-  int64_t const base = (MODE == MODE_FILL) ? (int64_t)offsets[qi] : 0;
-  if (n == 1)
-    return; // handled by singleLeafKernel
-  traverseSpatial(nodes, pred, [&](int ref, int pos) {
+  traverseSpatial<LEAF_F4>(nodes, leaf_box, pred, [&](unsigned orig, int pos) {
     if (TRI && !triangleLeafTest<PRED>(pred, leaf_tri, pos))
       return false;
-    if (MODE == MODE_FILL)
-      indices[base + count] = refOrig(ref);
+    if (MODE == MODE_FILL || MODE == MODE_COMPACT)
+      indices[base + count] = orig;
+    if (MODE == MODE_STAGE && count < kStage)
+      staging[(size_t)count * q + t] = orig;
     ++count;
     return limit > 0 && count >= limit;
   });
-  if (MODE == MODE_COUNT)
+  if (MODE == MODE_COUNT || MODE == MODE_STAGE)
     counts[qi] = count;
 }
 
@@ -74,74 +92,60 @@ __global__ void __launch_bounds__(kThreads)
 }
 
 // ---- nearest ---------------------------------------------------------------------
-// distance(Point, Box) as a float, sqrt included (Distance.hpp:72-80): kNN reports
-// distances, so the root is taken (correctly rounded) rather than skipped.
-__device__ __forceinline__ float pointBoxDist(float px, float py, float pz, float4 lo, float4 hi)
+// The traversal works on SQUARED distances and takes the (correctly rounded) root
+// only when a row is written.  sqrtf is monotone, so the k smallest squared
+// distances give exactly the k smallest distances of the reference
+// (TreeTraversal.hpp:180-335, Distance.hpp:54-80): reported distances are
+// bit-identical; indices can differ from the reference only among candidates whose
+// reported distances are equal -- the ties the reference leaves to its heap order.
+__device__ __forceinline__ float pointBoxDist2v(float px, float py, float pz, float4 lo, float4 hi)
 {
-  return __fsqrt_rn(pointBoxDist2(px, py, pz, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z));
+  return pointBoxDist2(px, py, pz, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
 }
 
-// Bounded candidate list kept sorted ascending in registers.  Acceptance rule is
-// the reference's: a leaf enters iff distance < radius, radius = k-th distance
-// once k candidates are known (TreeTraversal.hpp:255-290).
-template <int KCAP>
+// Bounded candidate list, ascending, entirely in registers (K is a compile-time
+// constant so every index below is static).  A candidate enters iff d2 < d[K-1]
+// (strict, like the reference's `distance < radius`).
+template <int K>
 struct RegList
 {
-  float d[KCAP];
-  unsigned id[KCAP];
+  float d[K];
+  unsigned id[K];
   __device__ __forceinline__ void init()
   {
 #pragma unroll
-    for (int i = 0; i < KCAP; ++i)
+    for (int i = 0; i < K; ++i)
     {
       d[i] = __int_as_float(0x7f800000); // +inf
       id[i] = 0xffffffffu;
     }
   }
-  // insert (dist, idx) knowing dist < d[k-1]; entries beyond k-1 stay +inf
-  __device__ __forceinline__ void insert(float dist, unsigned idx, int k)
+  __device__ __forceinline__ float radius() const { return d[K - 1]; }
+  __device__ __forceinline__ void insert(float dist, unsigned idx)
   {
-    // place at slot k-1 then bubble toward the front; strict < keeps earlier
-    // arrivals ahead of later ones at equal distance
+    // replace the worst entry, then one bubble pass toward the front; strict <
+    // keeps earlier arrivals ahead of later ones at equal distance
+    d[K - 1] = dist;
+    id[K - 1] = idx;
 #pragma unroll
-    for (int i = KCAP - 1; i >= 0; --i)
+    for (int i = K - 1; i >= 1; --i)
     {
-      if (i == k - 1)
-      {
-        d[i] = dist;
-        id[i] = idx;
-      }
+      bool const sw = d[i] < d[i - 1];
+      float const lo = sw ? d[i] : d[i - 1], hi = sw ? d[i - 1] : d[i];
+      unsigned const ilo = sw ? id[i] : id[i - 1], ihi = sw ? id[i - 1] : id[i];
+      d[i - 1] = lo;
+      d[i] = hi;
+      id[i - 1] = ilo;
+      id[i] = ihi;
     }
-#pragma unroll
-    for (int i = KCAP - 1; i >= 1; --i)
-    {
-      if (i <= k - 1 && d[i] < d[i - 1])
-      {
-        float td = d[i];
-        d[i] = d[i - 1];
-        d[i - 1] = td;
-        unsigned ti = id[i];
-        id[i] = id[i - 1];
-        id[i - 1] = ti;
-      }
-    }
-  }
-  __device__ __forceinline__ float radius(int k) const
-  {
-    float r = d[0];
-#pragma unroll
-    for (int i = 1; i < KCAP; ++i)
-      if (i == k - 1)
-        r = d[i];
-    return r;
   }
 };
 
-// max-heap in global scratch for large k (reference: NearestBufferProvider.hpp:24-72,
-// misc/ArborX_Heap.hpp).  Entries are (distance, index) pairs.
+// max-heap of (squared distance, index) in global scratch for large or per-query k
+// (reference: NearestBufferProvider.hpp:24-72, misc/ArborX_Heap.hpp)
 struct GlobalHeap
 {
-  float2 *h; // x = distance, y = bits(index)
+  float2 *h; // x = squared distance, y = bits(index)
   int size;
   __device__ __forceinline__ void push(float dist, unsigned idx)
   {
@@ -200,7 +204,11 @@ struct GlobalHeap
   }
 };
 
-template <int KCAP, bool TRI>
+// K > 0: register list of exactly K candidates (the first min(k, found) are
+// reported; K >= k).  K == 0: global heap with run-time k.
+constexpr int kNearestBucket = 1; // 1 = leaves only
+
+template <int K, int LEAF_F4, bool TRI>
 __global__ void __launch_bounds__(kThreads)
     nearestKernel(Node64 const *__restrict__ nodes, float4 const *__restrict__ leaf_box,
                   float4 const *__restrict__ leaf_tri, int n, int prim_kind, float const *__restrict__ pts, int64_t q,
@@ -213,7 +221,7 @@ __global__ void __launch_bounds__(kThreads)
   if (t >= q)
     return;
   int64_t const qi = qperm ? (int64_t)qperm[t] : t;
-  int k = k_per_query ? k_per_query[qi] : k_uniform;
+  int const k = k_per_query ? k_per_query[qi] : k_uniform;
   // rows are compact: row_stride = min(k, n) for uniform k, CRS offsets otherwise
   int64_t const base = offsets ? (int64_t)offsets[qi] : qi * (int64_t)row_stride;
   if (k < 1)
@@ -229,61 +237,57 @@ __global__ void __launch_bounds__(kThreads)
     // TreeTraversal.hpp:168-178: the single value is reported unconditionally
     float4 lo = __ldg(leaf_box);
     float4 hi = prim_kind == ABX_PRIM_POINT3F ? lo : __ldg(leaf_box + 1);
-    float dist = TRI ? __fsqrt_rn(pointTriangleDist2(px, py, pz, __ldg(leaf_tri), __ldg(leaf_tri + 1), __ldg(leaf_tri + 2)))
-                     : pointBoxDist(px, py, pz, lo, hi);
+    float const d2 = TRI ? pointTriangleDist2(px, py, pz, __ldg(leaf_tri), __ldg(leaf_tri + 1), __ldg(leaf_tri + 2))
+                         : pointBoxDist2v(px, py, pz, lo, hi);
     indices[base] = 0u;
     if (distances)
-      distances[base] = dist;
+      distances[base] = __fsqrt_rn(d2);
     if (counts)
       counts[qi] = 1;
     return;
   }
 
-  constexpr bool USE_REGS = KCAP > 0;
-  RegList<USE_REGS ? KCAP : 1> list;
+  constexpr bool USE_REGS = K > 0;
+  RegList<USE_REGS ? K : 1> list;
   GlobalHeap heap;
+  heap.h = nullptr;
+  heap.size = 0;
   if (USE_REGS)
     list.init();
   else
-  {
     heap.h = scratch + base;
-    heap.size = 0;
-  }
-  float radius = __int_as_float(0x7f800000);
+  float radius2 = __int_as_float(0x7f800000);
   int found = 0;
 
-  auto offer = [&](float dist, int ref, int pos) {
-    // leaf candidate with (box) distance < radius
+  auto offer = [&](float d2, unsigned idx, int pos) {
+    // leaf whose (box) squared distance is < radius2
     if (TRI)
     {
-      dist = __fsqrt_rn(pointTriangleDist2(px, py, pz, __ldg(leaf_tri + 3 * (size_t)pos),
-                                            __ldg(leaf_tri + 3 * (size_t)pos + 1), __ldg(leaf_tri + 3 * (size_t)pos + 2)));
-      if (!(dist < radius))
+      d2 = pointTriangleDist2(px, py, pz, __ldg(leaf_tri + 3 * (size_t)pos), __ldg(leaf_tri + 3 * (size_t)pos + 1),
+                              __ldg(leaf_tri + 3 * (size_t)pos + 2));
+      if (!(d2 < radius2))
         return;
     }
-    unsigned const idx = refOrig(ref);
     if (USE_REGS)
     {
-      list.insert(dist, idx, k);
-      if (found < k)
-        ++found;
-      if (found == k)
-        radius = list.radius(k);
+      list.insert(d2, idx);
+      ++found;
+      radius2 = list.radius(); // +inf until K candidates are known
     }
     else
     {
       if (heap.size < k)
-        heap.push(dist, idx);
+        heap.push(d2, idx);
       else
-        heap.replaceTop(dist, idx);
+        heap.replaceTop(d2, idx);
       found = heap.size;
       if (found == k)
-        radius = heap.top();
+        radius2 = heap.top();
     }
   };
 
-  int stack[kStackSize];
-  float stack_d[kStackSize];
+  // stack of (squared box distance, node) for the farther child
+  unsigned long long stack[kStackSize];
   int sp = 0;
   int node = 0;
   while (true)
@@ -291,32 +295,71 @@ __global__ void __launch_bounds__(kThreads)
     float4 const *f = reinterpret_cast<float4 const *>(nodes + node);
     float4 const a0 = __ldg(f), a1 = __ldg(f + 1), a2 = __ldg(f + 2), a3 = __ldg(f + 3);
     int const lref = __float_as_int(a0.w), rref = __float_as_int(a1.w);
-    float const dl = pointBoxDist(px, py, pz, a0, a1);
-    float const dr = pointBoxDist(px, py, pz, a2, a3);
-    bool go_l = false, go_r = false;
-    if (dl < radius)
+    int const rl = __float_as_int(a2.w), rr = __float_as_int(a3.w);
+    float const dl = pointBoxDist2v(px, py, pz, a0, a1);
+    float const dr = pointBoxDist2v(px, py, pz, a2, a3);
+    int const l_hi = refIsLeaf(lref) ? rl : lref;
+    int const r_lo = refIsLeaf(rref) ? rr : rref;
+    // leaves and small subtrees (<= kBucket contiguous sorted leaves) are consumed on
+    // the spot, nearer one first; radius2 may shrink between the two
+    // (kNN prunes better by descending: sub-boxes reject most of a bucket once the list is
+    // full, so only subtrees of <= kNearestBucket leaves are scanned; measured on B200 at
+    // 10M / k = 10: bucket 8 = 13.3 ms, bucket 2 = 14.5 ms, leaves only = 11.4 ms)
+    bool const l_small = l_hi - rl < kNearestBucket, r_small = rr - r_lo < kNearestBucket;
+    auto consume = [&](bool is_leaf, float d, int ref, int lo, int hi) {
+      if (!(d < radius2))
+        return;
+      if (is_leaf)
+      {
+        offer(d, refOrig(ref), lo);
+        return;
+      }
+      for (int j = lo; j <= hi; ++j)
+      {
+        float d2;
+        unsigned orig;
+        if (LEAF_F4 == 1)
+        {
+          float4 const p = __ldg(leaf_box + j);
+          float tx = __fsub_rn(p.x, px), ty = __fsub_rn(p.y, py), tz = __fsub_rn(p.z, pz);
+          d2 = __fmul_rn(tx, tx);
+          d2 = __fadd_rn(d2, __fmul_rn(ty, ty));
+          d2 = __fadd_rn(d2, __fmul_rn(tz, tz));
+          orig = __float_as_uint(p.w);
+        }
+        else
+        {
+          float4 const l = __ldg(leaf_box + 2 * (size_t)j), h = __ldg(leaf_box + 2 * (size_t)j + 1);
+          d2 = pointBoxDist2v(px, py, pz, l, h);
+          orig = __float_as_uint(l.w);
+        }
+        if (d2 < radius2)
+          offer(d2, orig, j);
+      }
+    };
+    if (l_small && r_small && dr < dl)
     {
-      if (refIsLeaf(lref))
-        offer(dl, lref, __float_as_int(a2.w));
-      else
-        go_l = true;
+      consume(refIsLeaf(rref), dr, rref, r_lo, rr);
+      consume(refIsLeaf(lref), dl, lref, rl, l_hi);
     }
-    if (dr < radius) // radius may already have shrunk (TreeTraversal.hpp:273-274)
+    else
     {
-      if (refIsLeaf(rref))
-        offer(dr, rref, __float_as_int(a3.w));
-      else
-        go_r = true;
+      if (l_small)
+        consume(refIsLeaf(lref), dl, lref, rl, l_hi);
+      if (r_small)
+        consume(refIsLeaf(rref), dr, rref, r_lo, rr);
     }
+    bool const go_l = !l_small && dl < radius2;
+    bool const go_r = !r_small && dr < radius2;
     if (go_l || go_r)
     {
       // nearer child first; left on ties (TreeTraversal.hpp:310-313)
       bool const left_first = go_l && (dl <= dr || !go_r);
       if (go_l && go_r)
       {
-        stack[sp] = left_first ? rref : lref;
-        stack_d[sp] = left_first ? dr : dl;
-        ++sp;
+        float const fd = left_first ? dr : dl;
+        int const fn = left_first ? rref : lref;
+        stack[sp++] = ((unsigned long long)__float_as_uint(fd) << 32) | (unsigned)fn;
       }
       node = left_first ? lref : rref;
       continue;
@@ -325,10 +368,10 @@ __global__ void __launch_bounds__(kThreads)
     bool popped = false;
     while (sp > 0)
     {
-      --sp;
-      if (stack_d[sp] < radius)
+      unsigned long long const e = stack[--sp];
+      if (__uint_as_float((unsigned)(e >> 32)) < radius2)
       {
-        node = stack[sp];
+        node = (int)(unsigned)e;
         popped = true;
         break;
       }
@@ -339,14 +382,16 @@ __global__ void __launch_bounds__(kThreads)
 
   if (USE_REGS)
   {
+    int const m = min(min(found, k), USE_REGS ? K : 1);
 #pragma unroll
-    for (int i = 0; i < (USE_REGS ? KCAP : 1); ++i)
-      if (i < found)
+    for (int i = 0; i < (USE_REGS ? K : 1); ++i)
+      if (i < m)
       {
         indices[base + i] = list.id[i];
         if (distances)
-          distances[base + i] = list.d[i];
+          distances[base + i] = __fsqrt_rn(list.d[i]);
       }
+    found = m;
   }
   else
   {
@@ -356,7 +401,7 @@ __global__ void __launch_bounds__(kThreads)
       float2 e = heap.h[i];
       indices[base + i] = __float_as_uint(e.y);
       if (distances)
-        distances[base + i] = e.x;
+        distances[base + i] = __fsqrt_rn(e.x);
     }
   }
   if (counts)
@@ -375,12 +420,12 @@ __global__ void __launch_bounds__(kThreads)
   pred.cx = p.x, pred.cy = p.y, pred.cz = p.z, pred.r = r;
   pred.t = sqrtThreshold(r);
   unsigned const me = __float_as_uint(p.w);
-  traverseHalf(nodes, i, pred, [&](int ref, int) {
+  traverseHalf(nodes, leaf_box, i, pred, [&](unsigned orig, int) {
     unsigned long long slot = atomicAdd(count, 1ull);
     if (pairs && slot < capacity)
     {
       pairs[2 * slot] = me;
-      pairs[2 * slot + 1] = refOrig(ref);
+      pairs[2 * slot + 1] = orig;
     }
   });
 }
@@ -426,13 +471,16 @@ __global__ void clipKKernel(int32_t const *__restrict__ k_per_query, int k_unifo
 template <int MODE>
 abx_status spatialLaunch(cudaStream_t s, abx_bvh *t, int pred_kind, void const *preds, int64_t q,
                          uint32_t const *qperm, int32_t limit, int32_t *counts, int32_t const *offsets,
-                         uint32_t *indices)
+                         uint32_t *indices, uint32_t *staging = nullptr)
 {
   if (q <= 0)
     return ABX_OK;
   int const grid = divUp(q, kThreads);
   int const n = (int)t->n;
-  char const *tag = MODE == MODE_COUNT ? "spatialKernel<count>" : "spatialKernel<fill>";
+  char const *tag = MODE == MODE_COUNT   ? "spatialKernel<count>"
+                    : MODE == MODE_FILL  ? "spatialKernel<fill>"
+                    : MODE == MODE_STAGE ? "spatialKernel<stage>"
+                                         : "spatialKernel<compact>";
   if (t->kind == ABX_PRIM_TRI3F && pred_kind != ABX_PRED_SPHERE3F)
   {
     setError("only intersects(Sphere) is defined for triangle primitives");
@@ -440,28 +488,35 @@ abx_status spatialLaunch(cudaStream_t s, abx_bvh *t, int pred_kind, void const *
   }
   if (n == 0)
   {
-    if (MODE == MODE_COUNT)
+    if (MODE == MODE_COUNT || MODE == MODE_STAGE)
       ABX_CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(int32_t) * q, s));
     return ABX_OK;
   }
   if (n == 1)
   {
-    ABX_DISPATCH_PRED(pred_kind, ABX_LAUNCH((spatialSingleLeafKernel<P, MODE>), grid, kThreads, 0, s, t->leaf_box,
+    // one leaf: the count and fill forms are all that is needed (no staging)
+    constexpr int M1 = (MODE == MODE_COUNT || MODE == MODE_STAGE) ? MODE_COUNT : MODE_FILL;
+    ABX_DISPATCH_PRED(pred_kind, ABX_LAUNCH((spatialSingleLeafKernel<P, M1>), grid, kThreads, 0, s, t->leaf_box,
                                             t->leaf_tri, t->kind, (float const *)preds, q, counts, offsets, indices));
     return ABX_OK;
   }
+#define ABX_SPATIAL(LF4, TRIFLAG)                                                                                     \
+  ABX_DISPATCH_PRED(pred_kind, ABX_LAUNCH_TAGGED(tag, (spatialKernel<P, MODE, LF4, TRIFLAG>), grid, kThreads, 0, s,   \
+                                                 t->nodes, t->leaf_box, t->leaf_tri, n, (float const *)preds, q,      \
+                                                 qperm, limit, counts, offsets, indices, staging))
   if (t->kind == ABX_PRIM_TRI3F)
   {
-    ABX_DISPATCH_PRED(pred_kind, ABX_LAUNCH_TAGGED(tag, (spatialKernel<P, MODE, true>), grid, kThreads, 0, s, t->nodes,
-                                            t->leaf_box, t->leaf_tri, n, (float const *)preds, q, qperm, limit, counts,
-                                            offsets, indices));
+    ABX_SPATIAL(2, true);
+  }
+  else if (t->kind == ABX_PRIM_BOX3F)
+  {
+    ABX_SPATIAL(2, false);
   }
   else
   {
-    ABX_DISPATCH_PRED(pred_kind, ABX_LAUNCH_TAGGED(tag, (spatialKernel<P, MODE, false>), grid, kThreads, 0, s, t->nodes,
-                                            t->leaf_box, t->leaf_tri, n, (float const *)preds, q, qperm, limit, counts,
-                                            offsets, indices));
+    ABX_SPATIAL(1, false);
   }
+#undef ABX_SPATIAL
   return ABX_OK;
 }
 
@@ -491,6 +546,20 @@ abx_status spatialFill(cudaStream_t s, abx_bvh *t, int pred_kind, void const *pr
   return spatialLaunch<MODE_FILL>(s, t, pred_kind, preds, q, qperm, 0, nullptr, offsets, indices);
 }
 
+// single-traversal CRS: stage (count + keep first kStage results) ... scan ... compact
+int spatialStageSlots() { return kStage; }
+abx_status spatialStage(cudaStream_t s, abx_bvh *t, int pred_kind, void const *preds, int64_t q, uint32_t const *qperm,
+                        int32_t *counts, uint32_t *staging)
+{
+  return spatialLaunch<MODE_STAGE>(s, t, pred_kind, preds, q, qperm, 0, counts, nullptr, nullptr, staging);
+}
+abx_status spatialCompact(cudaStream_t s, abx_bvh *t, int pred_kind, void const *preds, int64_t q,
+                          uint32_t const *qperm, int32_t const *offsets, uint32_t *indices, uint32_t const *staging)
+{
+  return spatialLaunch<MODE_COMPACT>(s, t, pred_kind, preds, q, qperm, 0, nullptr, offsets, indices,
+                                     const_cast<uint32_t *>(staging));
+}
+
 // uniform k: offsets == nullptr and rows start at i * min(k, n); per-query k:
 // offsets = CRS offsets of min(k_i, n).  total_rows = size of indices.
 abx_status nearestQuery(cudaStream_t s, abx_bvh *t, float const *pts, int64_t q, int32_t k, int32_t const *k_per_query,
@@ -514,22 +583,43 @@ abx_status nearestQuery(cudaStream_t s, abx_bvh *t, float const *pts, int64_t q,
   do                                                                                                                   \
   {                                                                                                                    \
     if (tri)                                                                                                           \
-      ABX_LAUNCH_TAGGED("nearestKernel<" #KCAP ",tri>", (nearestKernel<KCAP, true>), grid, kThreads, 0, s, t->nodes, t->leaf_box, t->leaf_tri, n, t->kind,    \
-                 pts, q, qperm, k, row_stride, k_per_query, offsets, counts, indices, distances, SCRATCH);                         \
+      ABX_LAUNCH_TAGGED("nearestKernel<" #KCAP ",tri>", (nearestKernel<KCAP, 2, true>), grid, kThreads, 0, s,          \
+                        t->nodes, t->leaf_box, t->leaf_tri, n, t->kind, pts, q, qperm, k, row_stride, k_per_query,     \
+                        offsets, counts, indices, distances, SCRATCH);                                                 \
+    else if (t->kind == ABX_PRIM_BOX3F)                                                                                \
+      ABX_LAUNCH_TAGGED("nearestKernel<" #KCAP ",box>", (nearestKernel<KCAP, 2, false>), grid, kThreads, 0, s,         \
+                        t->nodes, t->leaf_box, t->leaf_tri, n, t->kind, pts, q, qperm, k, row_stride, k_per_query,     \
+                        offsets, counts, indices, distances, SCRATCH);                                                 \
     else                                                                                                               \
-      ABX_LAUNCH_TAGGED("nearestKernel<" #KCAP ">", (nearestKernel<KCAP, false>), grid, kThreads, 0, s, t->nodes, t->leaf_box, t->leaf_tri, n, t->kind,   \
-                 pts, q, qperm, k, row_stride, k_per_query, offsets, counts, indices, distances, SCRATCH);                         \
+      ABX_LAUNCH_TAGGED("nearestKernel<" #KCAP ">", (nearestKernel<KCAP, 1, false>), grid, kThreads, 0, s, t->nodes,   \
+                        t->leaf_box, t->leaf_tri, n, t->kind, pts, q, qperm, k, row_stride, k_per_query, offsets,      \
+                        counts, indices, distances, SCRATCH);                                                          \
   } while (0)
-  if (kmax <= 1)
-    ABX_NEAREST(1, nullptr);
-  else if (kmax <= 4)
-    ABX_NEAREST(4, nullptr);
-  else if (kmax <= 8)
-    ABX_NEAREST(8, nullptr);
-  else if (kmax <= 12)
-    ABX_NEAREST(12, nullptr);
-  else if (kmax <= 16)
-    ABX_NEAREST(16, nullptr);
+  if (kmax <= 16)
+  {
+    // exact-k register lists
+    switch (std::max(kmax, 1))
+    {
+    case 1: ABX_NEAREST(1, nullptr); break;
+    case 2: ABX_NEAREST(2, nullptr); break;
+    case 3: ABX_NEAREST(3, nullptr); break;
+    case 4: ABX_NEAREST(4, nullptr); break;
+    case 5: ABX_NEAREST(5, nullptr); break;
+    case 6: ABX_NEAREST(6, nullptr); break;
+    case 7: ABX_NEAREST(7, nullptr); break;
+    case 8: ABX_NEAREST(8, nullptr); break;
+    case 9: ABX_NEAREST(9, nullptr); break;
+    case 10: ABX_NEAREST(10, nullptr); break;
+    case 11: ABX_NEAREST(11, nullptr); break;
+    case 12: ABX_NEAREST(12, nullptr); break;
+    case 13: ABX_NEAREST(13, nullptr); break;
+    case 14: ABX_NEAREST(14, nullptr); break;
+    case 15: ABX_NEAREST(15, nullptr); break;
+    default: ABX_NEAREST(16, nullptr); break;
+    }
+  }
+  else if (kmax <= 24)
+    ABX_NEAREST(24, nullptr); // keeps the 24 nearest, reports the first k
   else if (kmax <= 32)
     ABX_NEAREST(32, nullptr);
   else

@@ -16,6 +16,8 @@
 //                             it out in coalesced runs.
 #include "abx_common.cuh"
 
+#include <cstdlib>
+
 namespace abx
 {
 
@@ -30,6 +32,8 @@ constexpr int kTile = kSortThreads * kItems; // 4096 keys per tile
 constexpr unsigned kFlagAgg = 1u << 30;
 constexpr unsigned kFlagIncl = 1u << 31;
 constexpr unsigned kValueMask = (1u << 30) - 1;
+constexpr int kDefaultConfig64 = 0; // see sortPairsImpl: tile-shape table
+constexpr int kDefaultConfig32 = 0;
 
 template <int BITS>
 struct Radix
@@ -113,6 +117,35 @@ __device__ __forceinline__ unsigned blockExclusiveScan(unsigned v, unsigned *war
   return prefix + incl - v;
 }
 
+template <int WARPS>
+__device__ __forceinline__ unsigned blockExclusiveScanT(unsigned v, unsigned *warp_sums /*[WARPS]*/, unsigned &total)
+{
+  int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1)
+  {
+    unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o)
+      incl += t;
+  }
+  if (lane == 31)
+    warp_sums[warp] = incl;
+  __syncthreads();
+  unsigned prefix = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < WARPS; ++w)
+  {
+    unsigned s = warp_sums[w];
+    if (w < warp)
+      prefix += s;
+    tot += s;
+  }
+  total = tot;
+  __syncthreads();
+  return prefix + incl - v;
+}
+
 // ---- 2. exclusive scan of each histogram -----------------------------------
 template <int BITS>
 __global__ void __launch_bounds__(kSortThreads) radixScanHistKernel(unsigned *__restrict__ hist)
@@ -140,31 +173,55 @@ __global__ void __launch_bounds__(kSortThreads) radixScanHistKernel(unsigned *__
 }
 
 // ---- 3. one onesweep digit pass ----------------------------------------------
-template <typename KeyT, int BITS>
+// Configurable tile shape: THREADS x ITEMS keys per tile, MINB resident blocks per SM
+// (register cap).  BITS = 8: thread d < 256 owns digit d in the per-digit steps.
+template <typename KeyT, int BITS, int THREADS, int ITEMS>
 struct PassSmem
 {
   static constexpr int BINS = 1 << BITS;
-  KeyT keys[kTile];
-  unsigned vals[kTile];
-  unsigned warp_hist[kSortWarps][BINS]; // per-warp digit counts, then per-warp offsets inside the digit
-  unsigned digit_excl[BINS];            // first position of digit d in the tile's sorted order
-  unsigned global_off[BINS];            // global position = global_off[d] + position in tile
-  unsigned warp_sums[kSortWarps];
+  static constexpr int WARPS = THREADS / 32;
+  static constexpr int TILE = THREADS * ITEMS;
+  KeyT keys[TILE];
+  unsigned vals[TILE];
+  unsigned warp_hist[WARPS][BINS]; // per-warp digit counts, then per-warp offsets inside the digit
+  unsigned digit_excl[BINS];       // first position of digit d in the tile's sorted order
+  unsigned global_off[BINS];       // global position = global_off[d] + position in tile
+  unsigned warp_sums[WARPS];
   unsigned tile;
 };
 
-template <typename KeyT, int BITS>
-__global__ void __launch_bounds__(kSortThreads)
+// lanes of the warp holding the same digit: either one MATCH.ANY or BITS ballots
+template <int BITS, bool BALLOT>
+__device__ __forceinline__ unsigned matchDigit(unsigned d)
+{
+  if (!BALLOT)
+    return __match_any_sync(0xffffffffu, d);
+  unsigned peers = 0xffffffffu;
+#pragma unroll
+  for (int b = 0; b < BITS; ++b)
+  {
+    bool const bit = (d >> b) & 1u;
+    unsigned const bal = __ballot_sync(0xffffffffu, bit);
+    peers &= bit ? bal : ~bal;
+  }
+  return peers;
+}
+
+template <typename KeyT, int BITS, int THREADS, int ITEMS, int MINB, bool BALLOT>
+__global__ void __launch_bounds__(THREADS, MINB)
     onesweepPassKernel(KeyT const *__restrict__ keys_in, KeyT *__restrict__ keys_out,
                        unsigned const *__restrict__ vals_in /* may be null: iota */, unsigned *__restrict__ vals_out,
                        unsigned n, int shift, unsigned const *__restrict__ bin_base /*[BINS] exclusive*/,
                        unsigned *tile_state /*[tiles][BINS], zeroed*/, unsigned *tile_counter /*zeroed*/)
 {
-  constexpr int BINS = 1 << BITS;
-  constexpr int PER = BINS / kSortThreads;
+  using Smem = PassSmem<KeyT, BITS, THREADS, ITEMS>;
+  constexpr int BINS = Smem::BINS;
+  constexpr int WARPS = Smem::WARPS;
+  constexpr int TILE = Smem::TILE;
   constexpr unsigned MASK = BINS - 1;
+  static_assert(THREADS >= BINS, "one thread per digit");
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  PassSmem<KeyT, BITS> &sm = *reinterpret_cast<PassSmem<KeyT, BITS> *>(smem_raw);
+  Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
 
   int const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -172,19 +229,19 @@ __global__ void __launch_bounds__(kSortThreads)
   // have already started (forward progress of the look-back)
   if (tid == 0)
     sm.tile = atomicAdd(tile_counter, 1u);
-  for (int i = tid; i < kSortWarps * BINS; i += kSortThreads)
+  for (int i = tid; i < WARPS * BINS; i += THREADS)
     (&sm.warp_hist[0][0])[i] = 0;
   __syncthreads();
   unsigned const tile = sm.tile;
-  unsigned const tile_base = tile * (unsigned)kTile;
-  unsigned const valid = min((unsigned)kTile, n - tile_base);
+  unsigned const tile_base = tile * (unsigned)TILE;
+  unsigned const valid = min((unsigned)TILE, n - tile_base);
 
-  // warp-striped load: element order inside the tile is warp*512 + j*32 + lane
-  KeyT key[kItems];
-  unsigned val[kItems];
-  unsigned const warp_base = warp * (32 * kItems);
+  // warp-striped load: element order inside the tile is warp*(32*ITEMS) + j*32 + lane
+  KeyT key[ITEMS];
+  unsigned val[ITEMS];
+  unsigned const warp_base = warp * (32 * ITEMS);
 #pragma unroll
-  for (int j = 0; j < kItems; ++j)
+  for (int j = 0; j < ITEMS; ++j)
   {
     unsigned const local = warp_base + j * 32 + lane;
     bool const ok = local < valid;
@@ -192,120 +249,114 @@ __global__ void __launch_bounds__(kSortThreads)
     val[j] = ok ? (vals_in ? vals_in[tile_base + local] : tile_base + local) : 0u;
   }
 
-  // rank inside (warp, digit): match-any multisplit, one step per item
-  unsigned short rank[kItems];
+  // rank inside (warp, digit).  All ITEMS match-any votes are issued back to back
+  // (independent), then the per-warp digit counters are updated in item order.
+  unsigned peers[ITEMS];
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j)
+    peers[j] = matchDigit<BITS, BALLOT>(digitOf(key[j], shift, MASK));
+  unsigned short rank[ITEMS];
   unsigned const lanemask_lt = (1u << lane) - 1u;
 #pragma unroll
-  for (int j = 0; j < kItems; ++j)
+  for (int j = 0; j < ITEMS; ++j)
   {
     unsigned const d = digitOf(key[j], shift, MASK);
-    unsigned const peers = __match_any_sync(0xffffffffu, d);
-    int const leader = __ffs(peers) - 1;
+    int const leader = __ffs(peers[j]) - 1;
     unsigned base = 0;
     if (lane == leader)
     {
       base = sm.warp_hist[warp][d];
-      sm.warp_hist[warp][d] = base + __popc(peers);
+      sm.warp_hist[warp][d] = base + __popc(peers[j]);
     }
     base = __shfl_sync(0xffffffffu, base, leader);
-    rank[j] = (unsigned short)(base + __popc(peers & lanemask_lt));
+    rank[j] = (unsigned short)(base + __popc(peers[j] & lanemask_lt));
     __syncwarp();
   }
   __syncthreads();
 
-  // per digit: offsets of each warp inside the digit, tile total, look-back
-  unsigned count[PER];
-#pragma unroll
-  for (int i = 0; i < PER; ++i)
+  // per digit (thread d): offsets of each warp inside the digit and the tile total;
+  // publish the tile's aggregate right away, look back later
+  unsigned count = 0;
+  unsigned *my_state = tile_state + (size_t)tile * BINS;
+  if (tid < BINS)
   {
-    int const d = tid * PER + i;
-    unsigned sum = 0;
 #pragma unroll
-    for (int w = 0; w < kSortWarps; ++w)
+    for (int w = 0; w < WARPS; ++w)
     {
-      unsigned c = sm.warp_hist[w][d];
-      sm.warp_hist[w][d] = sum;
-      sum += c;
+      unsigned c = sm.warp_hist[w][tid];
+      sm.warp_hist[w][tid] = count;
+      count += c;
     }
-    count[i] = sum;
-  }
-  unsigned excl_tiles[PER];
-  {
-    unsigned *my_state = tile_state + (size_t)tile * BINS;
-#pragma unroll
-    for (int i = 0; i < PER; ++i)
-    {
-      int const d = tid * PER + i;
-      if (tile == 0)
-      {
-        stVolatile(&my_state[d], count[i] | kFlagIncl);
-        excl_tiles[i] = 0;
-      }
-      else
-        stVolatile(&my_state[d], count[i] | kFlagAgg);
-    }
-    if (tile != 0)
-    {
-#pragma unroll
-      for (int i = 0; i < PER; ++i)
-      {
-        int const d = tid * PER + i;
-        unsigned excl = 0;
-        int t = (int)tile - 1;
-        while (true)
-        {
-          unsigned v = ldVolatile(&tile_state[(size_t)t * BINS + d]);
-          if (v & kFlagIncl)
-          {
-            excl += v & kValueMask;
-            break;
-          }
-          if (v & kFlagAgg)
-          {
-            excl += v & kValueMask;
-            --t;
-          }
-        }
-        excl_tiles[i] = excl;
-        stVolatile(&my_state[d], (excl + count[i]) | kFlagIncl);
-      }
-    }
+    stVolatile(&my_state[tid], count | (tile == 0 ? kFlagIncl : kFlagAgg));
   }
   // position of each digit inside the tile's sorted order
   {
-    unsigned local = 0;
-#pragma unroll
-    for (int i = 0; i < PER; ++i)
-      local += count[i];
     unsigned total;
-    unsigned excl = blockExclusiveScan(local, sm.warp_sums, total);
-#pragma unroll
-    for (int i = 0; i < PER; ++i)
-    {
-      int const d = tid * PER + i;
-      sm.digit_excl[d] = excl;
-      sm.global_off[d] = bin_base[d] + excl_tiles[i] - excl;
-      excl += count[i];
-    }
+    unsigned excl = blockExclusiveScanT<WARPS>(tid < BINS ? count : 0u, sm.warp_sums, total);
+    if (tid < BINS)
+      sm.digit_excl[tid] = excl;
   }
   __syncthreads();
 
-  // stage the tile in shared memory in sorted order
+  // stage the tile in shared memory in sorted order (overlaps the predecessors'
+  // progress: the look-back below rarely has to spin)
 #pragma unroll
-  for (int j = 0; j < kItems; ++j)
+  for (int j = 0; j < ITEMS; ++j)
   {
     unsigned const d = digitOf(key[j], shift, MASK);
     unsigned const pos = sm.digit_excl[d] + sm.warp_hist[warp][d] + rank[j];
     sm.keys[pos] = key[j];
     sm.vals[pos] = val[j];
   }
+
+  // decoupled look-back for digit d
+  if (tid < BINS)
+  {
+    unsigned excl = 0;
+    if (tile != 0)
+    {
+      // windowed look-back: kWindow predecessor states are fetched with independent
+      // loads and consumed in order, so a chain of W unresolved tiles (the first wave
+      // of every pass) costs W / kWindow L2 round trips instead of W
+      constexpr int kWindow = 8;
+      int t = (int)tile - 1;
+      bool done = false;
+      while (!done)
+      {
+        unsigned v[kWindow];
+#pragma unroll
+        for (int i = 0; i < kWindow; ++i)
+          v[i] = (t - i >= 0) ? ldVolatile(&tile_state[(size_t)(t - i) * BINS + tid]) : kFlagIncl;
+#pragma unroll
+        for (int i = 0; i < kWindow; ++i)
+        {
+          if (done)
+            break;
+          if (v[i] & kFlagIncl)
+          {
+            excl += v[i] & kValueMask;
+            done = true;
+          }
+          else if (v[i] & kFlagAgg)
+          {
+            excl += v[i] & kValueMask;
+            --t;
+          }
+          else
+            break; // not published yet: re-fetch from this tile
+        }
+      }
+      stVolatile(&my_state[tid], (excl + count) | kFlagIncl);
+    }
+    sm.global_off[tid] = bin_base[tid] + excl - sm.digit_excl[tid];
+  }
   __syncthreads();
 
   // coalesced runs out
 #pragma unroll
-  for (int j = 0; j < kItems; ++j)
+  for (int j = 0; j < ITEMS; ++j)
   {
-    unsigned const pos = j * kSortThreads + tid;
+    unsigned const pos = j * THREADS + tid;
     if (pos < valid)
     {
       KeyT const k = sm.keys[pos];
@@ -316,6 +367,34 @@ __global__ void __launch_bounds__(kSortThreads)
   }
 }
 
+template <typename KeyT, int BITS, int THREADS, int ITEMS, int MINB, bool BALLOT>
+abx_status launchPasses(cudaStream_t s, int passes, KeyT *keys, KeyT *keys_alt, unsigned *vals, unsigned *vals_alt,
+                        int64_t n, bool iota_vals, unsigned *hist, unsigned *counters, unsigned *states, int tiles)
+{
+  constexpr int BINS = 1 << BITS;
+  auto kernel = onesweepPassKernel<KeyT, BITS, THREADS, ITEMS, MINB, BALLOT>;
+  size_t const smem = sizeof(PassSmem<KeyT, BITS, THREADS, ITEMS>);
+  static bool attr_set = false;
+  if (!attr_set)
+  {
+    ABX_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ABX_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    attr_set = true;
+  }
+  KeyT *kin = keys, *kout = keys_alt;
+  unsigned *vin = vals, *vout = vals_alt;
+  for (int p = 0; p < passes; ++p)
+  {
+    ABX_LAUNCH_TAGGED(sizeof(KeyT) == 8 ? "onesweepPassKernel<u64>" : "onesweepPassKernel<u32>", kernel, tiles,
+                      THREADS, smem, s, kin, kout, (p == 0 && iota_vals) ? (unsigned const *)nullptr : vin, vout,
+                      (unsigned)n, p * BITS, hist + (size_t)p * BINS, states + (size_t)p * tiles * BINS, counters + p);
+    std::swap(kin, kout);
+    std::swap(vin, vout);
+  }
+  return ABX_OK;
+}
+
+// tile shapes: {threads, items, min blocks/SM}; ABX_SORT_CONFIG picks one (tuning aid)
 template <typename KeyT, int BITS, int PASSES>
 abx_status sortPairsImpl(cudaStream_t s, KeyT *keys, unsigned *vals, int64_t n, bool iota_vals)
 {
@@ -328,7 +407,24 @@ abx_status sortPairsImpl(cudaStream_t s, KeyT *keys, unsigned *vals, int64_t n, 
     setError("sort: n must be < 2^30");
     return ABX_ERR_ARG;
   }
-  int const tiles = divUp(n, kTile);
+  static int const config = [] {
+    char const *e = getenv("ABX_SORT_CONFIG");
+    return e ? atoi(e) : -1;
+  }();
+  int const cfg = config >= 0 ? config : (sizeof(KeyT) == 8 ? kDefaultConfig64 : kDefaultConfig32);
+  int tile_keys;
+  switch (cfg)
+  {
+  case 1: tile_keys = 256 * 8; break;
+  case 2: tile_keys = 512 * 8; break;
+  case 3: tile_keys = 384 * 12; break;
+  case 4: tile_keys = 512 * 12; break;
+  case 5: tile_keys = 256 * 16; break;
+  case 6: tile_keys = 256 * 16; break;
+  case 7: tile_keys = 384 * 12; break;
+  default: tile_keys = 256 * 16; break;
+  }
+  int const tiles = divUp(n, tile_keys);
   TempBuffer<KeyT> keys_alt;
   TempBuffer<unsigned> vals_alt;
   TempBuffer<unsigned> ctrl; // [PASSES*BINS hist][PASSES counters][PASSES * tiles * BINS states]
@@ -347,25 +443,21 @@ abx_status sortPairsImpl(cudaStream_t s, KeyT *keys, unsigned *vals, int64_t n, 
                     (radixHistogramKernel<KeyT, BITS, PASSES>), hist_grid, kSortThreads, 0, s, keys, n, hist);
   ABX_LAUNCH((radixScanHistKernel<BITS>), PASSES, kSortThreads, 0, s, hist);
 
-  auto kernel = onesweepPassKernel<KeyT, BITS>;
-  size_t const smem = sizeof(PassSmem<KeyT, BITS>);
-  static bool attr_set = false;
-  if (!attr_set)
+#define ABX_PASSES(T, I, M, B)                                                                                        \
+  return launchPasses<KeyT, BITS, T, I, M, B>(s, PASSES, keys, keys_alt.ptr, vals, vals_alt.ptr, n, iota_vals, hist,  \
+                                              counters, states, tiles)
+  switch (cfg)
   {
-    ABX_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+  case 1: ABX_PASSES(256, 8, 5, false);
+  case 2: ABX_PASSES(512, 8, 2, false);
+  case 3: ABX_PASSES(384, 12, 2, false);
+  case 4: ABX_PASSES(512, 12, 2, false);
+  case 5: ABX_PASSES(256, 16, 3, false);
+  case 6: ABX_PASSES(256, 16, 2, true);
+  case 7: ABX_PASSES(384, 12, 2, true);
+  default: ABX_PASSES(256, 16, 2, false);
   }
-  KeyT *kin = keys, *kout = keys_alt.ptr;
-  unsigned *vin = vals, *vout = vals_alt.ptr;
-  for (int p = 0; p < PASSES; ++p)
-  {
-    ABX_LAUNCH_TAGGED(sizeof(KeyT) == 8 ? "onesweepPassKernel<u64>" : "onesweepPassKernel<u32>", kernel, tiles,
-                      kSortThreads, smem, s, kin, kout, (p == 0 && iota_vals) ? (unsigned const *)nullptr : vin,
-               vout, (unsigned)n, p * BITS, hist + (size_t)p * BINS, states + (size_t)p * tiles * BINS, counters + p);
-    std::swap(kin, kout);
-    std::swap(vin, vout);
-  }
-  return ABX_OK;
+#undef ABX_PASSES
 }
 
 // ---- exclusive scan (reduce-then-scan, three small launches) ----------------

@@ -31,6 +31,16 @@ struct Pred<ABX_PRED_SPHERE3F>
   {
     return pointBoxDist2(cx, cy, cz, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z) <= t;
   }
+  // intersects(Sphere, Point): distance(centre, point) <= radius (Intersects.hpp:107-114);
+  // tmp = point - centre, the same value the box path computes for a degenerate box
+  __device__ __forceinline__ bool point(float4 p) const
+  {
+    float tx = __fsub_rn(p.x, cx), ty = __fsub_rn(p.y, cy), tz = __fsub_rn(p.z, cz);
+    float d2 = __fmul_rn(tx, tx);
+    d2 = __fadd_rn(d2, __fmul_rn(ty, ty));
+    d2 = __fadd_rn(d2, __fmul_rn(tz, tz));
+    return d2 <= t;
+  }
 };
 
 template <>
@@ -51,6 +61,7 @@ struct Pred<ABX_PRED_BOX3F>
   {
     return !(lx > hi.x || hx < lo.x || ly > hi.y || hy < lo.y || lz > hi.z || hz < lo.z);
   }
+  __device__ __forceinline__ bool point(float4 p) const { return box(p, p); }
 };
 
 template <>
@@ -68,6 +79,7 @@ struct Pred<ABX_PRED_POINT3F>
   {
     return !(x > hi.x || x < lo.x || y > hi.y || y < lo.y || z > hi.z || z < lo.z);
   }
+  __device__ __forceinline__ bool point(float4 p) const { return box(p, p); }
 };
 
 // ---- point-triangle distance (ClosestPoint.hpp:69-153, Distance.hpp:112-123) ----
@@ -169,10 +181,40 @@ __device__ inline float pointTriangleDist2(float px, float py, float pz, float4 
 }
 
 // ---- spatial traversal core -----------------------------------------------------
-// Calls emit(child_ref, sorted_leaf_position) for every leaf whose box satisfies
-// the predicate; emit returns true to stop the traversal (early exit).
-template <class P, class Emit>
-__device__ __forceinline__ void traverseSpatial(Node64 const *__restrict__ nodes, P const &pred, Emit &&emit)
+// Subtrees with at most kBucket leaves are not descended: their leaves are
+// contiguous in the sorted leaf array (a node's range [lo, hi] of sorted positions
+// is known from its parent's record), so they are scanned linearly -- independent
+// 16/32-byte loads from one or two cache lines instead of three more levels of
+// dependent 64-byte node loads.  Same result set, shorter dependent chain.
+constexpr int kBucket = 8;
+
+// LEAF_F4: float4s per sorted leaf (1: points (xyz, orig); 2: boxes (lo, orig)(hi, -))
+// emit(orig, pos) returns true to stop the whole traversal (early exit).
+template <int LEAF_F4, class P, class Emit>
+__device__ __forceinline__ bool scanLeaves(float4 const *__restrict__ leaf_box, int lo, int hi, P const &pred,
+                                           Emit &&emit)
+{
+  for (int j = lo; j <= hi; ++j)
+  {
+    if (LEAF_F4 == 1)
+    {
+      float4 const p = __ldg(leaf_box + j);
+      if (pred.point(p) && emit(__float_as_uint(p.w), j))
+        return true;
+    }
+    else
+    {
+      float4 const l = __ldg(leaf_box + 2 * (size_t)j), h = __ldg(leaf_box + 2 * (size_t)j + 1);
+      if (pred.box(l, h) && emit(__float_as_uint(l.w), j))
+        return true;
+    }
+  }
+  return false;
+}
+
+template <int LEAF_F4, class P, class Emit>
+__device__ __forceinline__ void traverseSpatial(Node64 const *__restrict__ nodes,
+                                                float4 const *__restrict__ leaf_box, P const &pred, Emit &&emit)
 {
   int stack[kStackSize];
   int sp = 0;
@@ -182,19 +224,42 @@ __device__ __forceinline__ void traverseSpatial(Node64 const *__restrict__ nodes
     float4 const *f = reinterpret_cast<float4 const *>(nodes + node);
     float4 const a0 = __ldg(f), a1 = __ldg(f + 1), a2 = __ldg(f + 2), a3 = __ldg(f + 3);
     int const lref = __float_as_int(a0.w), rref = __float_as_int(a1.w);
+    int const rl = __float_as_int(a2.w), rr = __float_as_int(a3.w);
     bool hit_l = pred.box(a0, a1);
     bool hit_r = pred.box(a2, a3);
-    if (hit_l && refIsLeaf(lref))
+    // left child covers [rl, l_hi], right child [r_lo, rr] (an internal left child's
+    // Karras index is its last leaf, an internal right child's its first)
+    int const l_hi = refIsLeaf(lref) ? rl : lref;
+    int const r_lo = refIsLeaf(rref) ? rr : rref;
+    if (hit_l)
     {
-      if (emit(lref, __float_as_int(a2.w)))
-        return;
-      hit_l = false;
+      if (refIsLeaf(lref))
+      {
+        if (emit(refOrig(lref), rl))
+          return;
+        hit_l = false;
+      }
+      else if (l_hi - rl < kBucket)
+      {
+        if (scanLeaves<LEAF_F4>(leaf_box, rl, l_hi, pred, emit))
+          return;
+        hit_l = false;
+      }
     }
-    if (hit_r && refIsLeaf(rref))
+    if (hit_r)
     {
-      if (emit(rref, __float_as_int(a3.w)))
-        return;
-      hit_r = false;
+      if (refIsLeaf(rref))
+      {
+        if (emit(refOrig(rref), rr))
+          return;
+        hit_r = false;
+      }
+      else if (rr - r_lo < kBucket)
+      {
+        if (scanLeaves<LEAF_F4>(leaf_box, r_lo, rr, pred, emit))
+          return;
+        hit_r = false;
+      }
     }
     if (hit_l)
     {
@@ -232,34 +297,54 @@ __device__ __forceinline__ bool triangleLeafTest<ABX_PRED_SPHERE3F>(Pred<ABX_PRE
 // ---- half traversal ---------------------------------------------------------------
 // Leaf i (sorted position) pairs with every leaf j > i within r: the subtrees to
 // the right of the root-to-leaf path, which is what starting at rope(i) visits in
-// the reference (HalfTraversal.hpp:52-74).
+// the reference (HalfTraversal.hpp:52-74).  Point leaves only.  emit(orig, pos).
 template <class Emit>
-__device__ __forceinline__ void traverseHalf(Node64 const *__restrict__ nodes, int i,
-                                             Pred<ABX_PRED_SPHERE3F> const &pred, Emit &&emit)
+__device__ __forceinline__ void traverseHalf(Node64 const *__restrict__ nodes, float4 const *__restrict__ leaf_box,
+                                             int i, Pred<ABX_PRED_SPHERE3F> const &pred, Emit &&emit)
 {
   int stack[kStackSize];
   int sp = 0;
   int node = 0;
+  auto emit_all = [&](unsigned orig, int pos) {
+    emit(orig, pos);
+    return false;
+  };
   while (true)
   {
     float4 const *f = reinterpret_cast<float4 const *>(nodes + node);
     float4 const a0 = __ldg(f), a1 = __ldg(f + 1), a2 = __ldg(f + 2), a3 = __ldg(f + 3);
     int const lref = __float_as_int(a0.w), rref = __float_as_int(a1.w);
     int const rl = __float_as_int(a2.w), rr = __float_as_int(a3.w);
-    // left subtree covers [rl, split], split = position rl for a leaf, Karras
-    // index of the left child otherwise; it holds leaves > i iff split > i
-    int const split = refIsLeaf(lref) ? rl : lref;
-    bool hit_l = (split > i) && pred.box(a0, a1);
+    int const l_hi = refIsLeaf(lref) ? rl : lref;
+    int const r_lo = refIsLeaf(rref) ? rr : rref;
+    // a subtree holds leaves > i iff its last position is > i
+    bool hit_l = (l_hi > i) && pred.box(a0, a1);
     bool hit_r = (rr > i) && pred.box(a2, a3);
-    if (hit_l && refIsLeaf(lref))
+    if (hit_l)
     {
-      emit(lref, rl);
-      hit_l = false;
+      if (refIsLeaf(lref))
+      {
+        emit(refOrig(lref), rl);
+        hit_l = false;
+      }
+      else if (l_hi - rl < kBucket)
+      {
+        scanLeaves<1>(leaf_box, max(rl, i + 1), l_hi, pred, emit_all);
+        hit_l = false;
+      }
     }
-    if (hit_r && refIsLeaf(rref))
+    if (hit_r)
     {
-      emit(rref, rr);
-      hit_r = false;
+      if (refIsLeaf(rref))
+      {
+        emit(refOrig(rref), rr);
+        hit_r = false;
+      }
+      else if (rr - r_lo < kBucket)
+      {
+        scanLeaves<1>(leaf_box, max(r_lo, i + 1), rr, pred, emit_all);
+        hit_r = false;
+      }
     }
     if (hit_l)
     {
@@ -277,6 +362,5 @@ __device__ __forceinline__ void traverseHalf(Node64 const *__restrict__ nodes, i
     }
   }
 }
-
 
 } // namespace abx

@@ -1,0 +1,225 @@
+"""DistributedTree -- host-side mirror of ArborX::DistributedTree for one process per GPU.
+
+Reference: distributed/ArborX_DistributedTree.hpp:33-252 (ctor: bottom tree, all-gather of rank
+boxes, replicated top tree, all-gather of sizes), detail/ArborX_DistributedTreeSpatial.hpp:31-60,
+detail/ArborX_DistributedTreeNearest.hpp:41-218 (two-phase kNN), detail/ArborX_DistributedTreeUtils.hpp
+(forwardQueries :52-115, communicateResultsBack :153-224, countResults/sort :229-263, filterResults
+:267-342).  The reference exchanges with MPI point-to-point, three messages each way
+(detail/ArborX_Distributor.hpp:276-440); here every exchange is ONE all-to-all-v of packed 32-bit
+records over torch.distributed (NCCL over NVLink on the GPUs; gloo in the CPU protocol tests), preceded
+by an all-to-all of the R counts.
+
+The tree work (top-tree queries, bottom-tree queries, kNN) runs in the hand-written CUDA kernels behind
+the C ABI; the packing between exchanges is a handful of torch tensor ops (bucket by destination, gather,
+segmented sort by query id) -- plumbing around the hot path.  The local engine is injectable so that the
+exchange protocol can be exercised on CPU with gloo (tests/ plug the oracle in; the product default is the
+CUDA engine and fails without a GPU).
+
+Values returned by queries are (index, rank) pairs (int32 [nnz, 2]): the reference returns user values or
+`{index, rank}` from a callback (examples/distributed_tree/distributed_knn.cpp:62-104).
+"""
+import torch
+import torch.distributed as dist
+
+POINT, BOX, TRIANGLE = 0, 1, 2
+SPHERE_PRED, BOX_PRED, POINT_PRED = 0, 1, 2
+
+
+class CudaEngine:
+    """Local trees on this rank's GPU through libabx.so."""
+
+    def __init__(self, space):
+        import arborx_b200 as abx
+        self.abx = abx
+        self.space = space
+
+    def build(self, values, kind):
+        return self.abx.BoundingVolumeHierarchy(self.space, values, kind)
+
+    def size(self, tree):
+        return tree.size()
+
+    def bounds(self, tree):
+        return tree.bounds()
+
+    def spatial(self, tree, pred_kind, preds):
+        idx, off = tree.query(self.space, self.abx.intersects(preds, pred_kind))
+        return idx, off
+
+    def nearest(self, tree, pts, k):
+        idx, off, d = tree.query(self.space, self.abx.nearest(pts, int(k)), return_distances=True)
+        return idx, off, d
+
+
+def _alltoallv(comm, rows, send_counts):
+    """rows [F, w] (32-bit words) ordered by destination rank, send_counts [R] (host list).
+    Returns (recv_rows [G, w], recv_counts list)."""
+    R = dist.get_world_size(comm)
+    dev = rows.device
+    sc = torch.tensor(send_counts, dtype=torch.int64, device=dev)
+    rc = torch.empty(R, dtype=torch.int64, device=dev)
+    dist.all_to_all_single(rc, sc, group=comm)
+    recv_counts = rc.tolist()
+    w = rows.shape[1]
+    out = torch.empty((sum(recv_counts), w), dtype=rows.dtype, device=dev)
+    dist.all_to_all_single(out.view(-1), rows.contiguous().view(-1), [c * w for c in recv_counts],
+                           [c * w for c in send_counts], group=comm)
+    return out, recv_counts
+
+
+class DistributedTree:
+    def __init__(self, comm, space, values, kind=None, engine=None):
+        self.comm = comm
+        self.rank = dist.get_rank(comm)
+        self.world = dist.get_world_size(comm)
+        self.space = space
+        self.engine = engine if engine is not None else CudaEngine(space)
+        if not isinstance(values, torch.Tensor):
+            values = torch.as_tensor(values, dtype=torch.float32)
+        if kind is None:
+            kind = {3: POINT, 6: BOX, 9: TRIANGLE}[values.shape[-1]]
+        self.kind = kind
+        self.device = values.device
+        # bottom tree (ArborX_DistributedTree.hpp:183-186)
+        self._bottom = self.engine.build(values, kind)
+        n_local = int(self.engine.size(self._bottom))
+        # all-gather rank boxes (:208-227) and sizes (:243-245)
+        b = self.engine.bounds(self._bottom).to(torch.float32).cpu()
+        meta = torch.cat([b, torch.tensor([float(n_local)])]).to(self.device)
+        gathered = [torch.empty_like(meta) for _ in range(self.world)]
+        dist.all_gather(gathered, meta, group=comm)
+        g = torch.stack(gathered).cpu()
+        self._rank_boxes = g[:, :6].contiguous()
+        self._sizes = g[:, 6].to(torch.int64)
+        self._size = int(self._sizes.sum())
+        # replicated top tree over the rank boxes (:227); leaf value = rank
+        self._top = self.engine.build(self._rank_boxes.to(self.device), BOX)
+
+    # ---- ArborX_DistributedTree.hpp:112-127 ----------------------------------------------
+    def size(self):
+        return self._size
+
+    def empty(self):
+        return self._size == 0
+
+    def bounds(self):
+        return self.engine.bounds(self._top)
+
+    # ---- query ------------------------------------------------------------------------
+    def query(self, space, predicates, return_distances=False):
+        """Collective.  -> (values int32 [nnz, 2] = (index, rank), offsets int32 [q + 1][, distances])."""
+        data = predicates.data
+        q = data.shape[0]
+        dev = data.device
+        if self.empty():
+            # DistributedTreeSpatial.hpp:44-50
+            out = (torch.empty((0, 2), dtype=torch.int32, device=dev), torch.zeros(q + 1, dtype=torch.int32, device=dev))
+            return out + ((torch.empty(0, dtype=torch.float32, device=dev),) if return_distances else ())
+        if predicates.tag == "spatial":
+            ranks, off = self.engine.spatial(self._top, predicates.kind, data)
+            vals, offsets, _ = self._forward_and_collect(data, ranks.long(), off.long(), ("spatial", predicates.kind))
+            return (vals, offsets) + ((torch.empty(0, dtype=torch.float32, device=dev),) if return_distances else ())
+        k = int(predicates.k)
+        vals, offsets, d = self._nearest(data, k)
+        return (vals, offsets, d) if return_distances else (vals, offsets)
+
+    # forwardQueries + bottom query + communicateResultsBack + sort by query id
+    # (DistributedTreeUtils.hpp:229-263).  ranks/off: CRS of destination ranks per local query.
+    def _forward_and_collect(self, data, ranks, off, what):
+        dev = data.device
+        q = data.shape[0]
+        R = self.world
+        counts = off[1:] - off[:-1]
+        qid = torch.repeat_interleave(torch.arange(q, device=dev), counts)
+        # bucket the export list by destination rank (Distributor::createFromSends, Distributor.hpp:132-197)
+        order = torch.argsort(ranks, stable=True)
+        send_counts = torch.bincount(ranks, minlength=R).tolist()
+        qid_s = qid[order]
+        rows = torch.cat([data[qid_s].contiguous().view(torch.int32), qid_s.to(torch.int32).unsqueeze(1)], 1)
+        fwd, recv_counts = _alltoallv(self.comm, rows, send_counts)
+        stride = data.shape[1]
+        fwd_preds = fwd[:, :stride].contiguous().view(torch.float32)
+        fwd_ids = fwd[:, stride]
+        G = fwd.shape[0]
+        # bottom-tree query on the forwarded predicates
+        if what[0] == "spatial":
+            idx, loff = self.engine.spatial(self._bottom, what[1], fwd_preds)
+            dist_bits = None
+        else:
+            idx, loff, d = self.engine.nearest(self._bottom, fwd_preds, what[1])
+            dist_bits = d.contiguous().view(torch.int32)
+        idx = idx.to(torch.int32)
+        loff = loff.long()
+        lcounts = loff[1:] - loff[:-1]
+        # results are in CRS order of the forwarded queries, which arrived grouped by source rank:
+        # already bucketed by destination
+        res_ids = torch.repeat_interleave(fwd_ids, lcounts)
+        cols = [idx.unsqueeze(1), res_ids.unsqueeze(1)]
+        if dist_bits is not None:
+            cols.append(dist_bits.unsqueeze(1))
+        back_rows = torch.cat(cols, 1) if G else torch.empty((0, len(cols)), dtype=torch.int32, device=dev)
+        seg = torch.cumsum(torch.tensor([0] + recv_counts, device=dev), 0)
+        back_counts = (loff[seg[1:]] - loff[seg[:-1]]).tolist()
+        got, got_counts = _alltoallv(self.comm, back_rows, back_counts)
+        src_rank = torch.repeat_interleave(torch.arange(R, device=dev, dtype=torch.int32),
+                                           torch.tensor(got_counts, device=dev))
+        ids = got[:, 1].long()
+        order2 = torch.argsort(ids, stable=True)
+        vals = torch.stack([got[:, 0][order2], src_rank[order2]], 1)
+        offsets = torch.zeros(q + 1, dtype=torch.int64, device=dev)
+        offsets[1:] = torch.cumsum(torch.bincount(ids, minlength=q), 0)
+        dists = got[:, 2][order2].contiguous().view(torch.float32) if dist_bits is not None else None
+        return vals, offsets.to(torch.int32), dists
+
+    # DistributedTreeNearest.hpp:41-218
+    def _nearest(self, pts, k):
+        dev = pts.device
+        q = pts.shape[0]
+        if k < 1:
+            return (torch.empty((0, 2), dtype=torch.int32, device=dev), torch.zeros(q + 1, dtype=torch.int32, device=dev),
+                    torch.empty(0, dtype=torch.float32, device=dev))
+        # phase I: nearest rank boxes, truncated once their cumulated sizes reach k (:64-101)
+        ranks, off, _ = self.engine.nearest(self._top, pts, k)
+        ranks, off = ranks.long(), off.long()
+        sizes = self._sizes.to(dev)
+        counts = off[1:] - off[:-1]
+        row = torch.repeat_interleave(torch.arange(q, device=dev), counts)
+        pos = torch.arange(ranks.shape[0], device=dev) - off[row]
+        sz = sizes[ranks]
+        csum = torch.cumsum(sz, 0)
+        before = csum - sz - (csum - sz)[off[row]]  # leaves cumulated before this entry, within the row
+        # stop at the first empty tree or once k leaves are cumulated
+        empty_before = torch.cumsum((sz == 0).long(), 0)
+        empty_before = empty_before - empty_before[off[row]] + (sz[off[row]] == 0).long()
+        keep = (before < k) & (empty_before == 0)
+        ranks1 = ranks[keep]
+        off1 = torch.zeros(q + 1, dtype=torch.int64, device=dev)
+        off1[1:] = torch.cumsum(torch.bincount(row[keep], minlength=q), 0)
+        _, offd, d1 = self._forward_and_collect(pts, ranks1, off1, ("nearest", k))
+        offd = offd.long()
+        # k-th smallest distance per query (:114-125)
+        nd = offd[1:] - offd[:-1]
+        rowd = torch.repeat_interleave(torch.arange(q, device=dev), nd)
+        # segmented sort: by (row, distance)
+        o = torch.argsort(d1, stable=True)
+        o = o[torch.argsort(rowd[o], stable=True)]
+        d_sorted = d1[o]
+        kth = torch.clamp(torch.minimum(torch.full_like(nd, k), nd) - 1, min=0)
+        farthest = torch.where(nd > 0, d_sorted[torch.clamp(offd[:-1] + kth, max=max(d_sorted.shape[0] - 1, 0))]
+                               if d_sorted.shape[0] else torch.zeros(q, device=dev), torch.zeros(q, device=dev))
+        # phase II: every rank whose box is within that distance (:131-176)
+        spheres = torch.cat([pts, farthest.unsqueeze(1).to(torch.float32)], 1).contiguous()
+        ranks2, off2 = self.engine.spatial(self._top, SPHERE_PRED, spheres)
+        vals, offv, d2 = self._forward_and_collect(pts, ranks2.long(), off2.long(), ("nearest", k))
+        offv = offv.long()
+        # filterResults (DistributedTreeUtils.hpp:267-342): keep the k smallest per query, ascending
+        nv = offv[1:] - offv[:-1]
+        rowv = torch.repeat_interleave(torch.arange(q, device=dev), nv)
+        o = torch.argsort(d2, stable=True)
+        o = o[torch.argsort(rowv[o], stable=True)]
+        rank_in_row = torch.arange(o.shape[0], device=dev) - offv[rowv[o]]
+        sel = o[rank_in_row < k]
+        out_counts = torch.minimum(nv, torch.full_like(nv, k))
+        offsets = torch.zeros(q + 1, dtype=torch.int64, device=dev)
+        offsets[1:] = torch.cumsum(out_counts, 0)
+        return vals[sel], offsets.to(torch.int32), d2[sel]
