@@ -30,6 +30,7 @@ SIGNATURES = {
     "abx_version": (C.c_int, []),
     "abx_launch_count": (_i64, []),
     "abx_free": (C.c_int, [_vp, _vp]),
+    "abx_trim": (_i64, []),
     "abx_profile_enable": (C.c_int, [C.c_int]),
     "abx_profile_report": (_i64, [C.c_char_p, _i64]),
     "abx_bvh_build": (C.c_int, [_vp, C.c_int, _vp, _i64, _pp]),

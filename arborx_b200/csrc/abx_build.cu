@@ -259,18 +259,23 @@ __device__ __forceinline__ void loadNodeBox(Node64 const *nodes, int k, Box &b)
   b.hi[2] = fmaxf(a1.z, a3.z);
 }
 
-// ---- hierarchy kernel ----------------------------------------------------------------
-// One thread per sorted leaf walks toward the root; the first thread to reach an
-// internal node stops (atomic flag), the second finishes the node (Apetrei).
+// ---- hierarchy kernels ---------------------------------------------------------------
+// Apetrei's bottom-up construction (TreeConstruction.hpp:197-311): a node is finished
+// by the second of its two children to arrive at an atomic flag.
 //
-// B200 shape: a block owns a chunk of kHierThreads consecutive sorted leaves.  The
-// LBVH is the Cartesian tree of the delta array (key = (delta, index), larger key =
-// closer to the root), so a node p lies entirely inside the chunk [a, b] iff a
-// larger key exists on both sides of p inside [a-1, b]:
+// B200 shape.  The LBVH is the Cartesian tree of the delta array (key = (delta, index),
+// larger key = closer to the root).  A block owns a chunk [a, b] of kHierThreads
+// consecutive sorted leaves; node p lies entirely inside the chunk iff a larger key
+// exists on both sides of p inside [a-1, b]:
 //     max(delta[a-1 .. p-1]) > delta(p)   and   max(delta[p+1 .. b]) >= delta(p).
-// Such "local" nodes (> 95 % of all nodes) are built with shared-memory flags, boxes
-// and deltas: no global atomics, no device-scope fences, ~30-cycle hops.  Only nodes
-// that straddle a chunk boundary use the global CAS + __threadfence protocol.
+// hierarchyLocalKernel builds these "local" nodes (> 95 % of all nodes) in ROUNDS over a
+// shared-memory work queue: round 0 holds the chunk's leaves, every finished node is
+// pushed for the next round, so all rounds run with compact, fully populated warps
+// (the plain one-thread-per-leaf walk leaves 4-8 of 32 lanes alive after two levels).
+// Flags, boxes, ranges and deltas live in shared memory; no global atomics, no
+// device-scope fences.  A subtree whose parent is not local is appended to a pending
+// list; hierarchyGlobalKernel finishes those few nodes with the global CAS +
+// __threadfence protocol.
 constexpr int kHierThreads = 512;
 constexpr int kHierWarps = kHierThreads / 32;
 
@@ -278,6 +283,13 @@ template <int KIND>
 struct LeafFloats
 {
   static constexpr int value = (KIND == ABX_PRIM_POINT3F) ? 3 : 6;
+};
+
+// a finished subtree waiting for its (non-local) parent
+struct PendingNode
+{
+  int range_left, range_right, ref;
+  float box[6];
 };
 
 __device__ __forceinline__ long long shflUp64(long long v, int o)
@@ -289,33 +301,48 @@ __device__ __forceinline__ long long shflDown64(long long v, int o)
   return __shfl_down_sync(0xffffffffu, v, o);
 }
 
+__device__ __forceinline__ void writeNode(Node64 *nodes, int k, Box const &L, int lref, Box const &R, int rref,
+                                          int range_left, int range_right)
+{
+  float4 *f = reinterpret_cast<float4 *>(nodes + k);
+  f[0] = make_float4(L.lo[0], L.lo[1], L.lo[2], __int_as_float(lref));
+  f[1] = make_float4(L.hi[0], L.hi[1], L.hi[2], __int_as_float(rref));
+  f[2] = make_float4(R.lo[0], R.lo[1], R.lo[2], __int_as_float(range_left));
+  f[3] = make_float4(R.hi[0], R.hi[1], R.hi[2], __int_as_float(range_right));
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(kHierThreads)
-    hierarchyKernel(int n, unsigned long long const *__restrict__ codes, unsigned const *__restrict__ perm,
-                    float const *__restrict__ prims, Node64 *nodes, float4 *leaf_box, float4 *leaf_tri, int *ranges,
-                    float *bounds6)
+    hierarchyLocalKernel(int n, unsigned long long const *__restrict__ codes, unsigned const *__restrict__ perm,
+                         float const *__restrict__ prims, Node64 *nodes, float4 *leaf_box, float4 *leaf_tri,
+                         PendingNode *pending, unsigned *pending_count, float *bounds6)
 {
   constexpr int LF = LeafFloats<KIND>::value;
-  __shared__ long long sdelta[kHierThreads + 1]; // sdelta[j] = delta(a - 1 + j)
-  __shared__ int sflag[kHierThreads];            // per local parent p-a: -1 untouched, -2 not local, else range end
-  __shared__ float snode[kHierThreads][6];       // box of finished local node (by Karras index - a)
-  __shared__ float sleaf[kHierThreads][LF];      // leaf boxes of the chunk
-  __shared__ unsigned sperm[kHierThreads];
+  constexpr int T = kHierThreads;
+  __shared__ long long sdelta[T + 1]; // sdelta[j] = delta(a - 1 + j)
+  __shared__ int sflag[T];            // per parent p-a: -1 untouched, -2 not local, else a range end
+  __shared__ float snode[T][6];       // box of a finished local node (by Karras index - a)
+  __shared__ short srl[T], srr[T];    // its range, relative to a
+  __shared__ float sleaf[T][LF];      // leaf boxes of the chunk
+  __shared__ unsigned sperm[T];
+  __shared__ unsigned short squeue[2][T];
+  __shared__ unsigned short spend[T]; // items handed to the global kernel
+  __shared__ int sqn[2];
+  __shared__ int spn;
+  __shared__ unsigned spbase;
   __shared__ long long swarp[2][kHierWarps];
 
   int const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  int const a = blockIdx.x * kHierThreads;
-  int const cn = min(kHierThreads, n - a); // leaves in this chunk
+  int const a = blockIdx.x * T;
+  int const cn = min(T, n - a); // leaves in this chunk
   int const n_int = n - 1;
   int const i = a + tid;
   bool const active = tid < cn;
 
-  unsigned orig = 0;
-  Box box = emptyBox();
   if (active)
   {
-    orig = perm[i];
-    box = primBox<KIND>(prims, orig);
+    unsigned const orig = perm[i];
+    Box const box = primBox<KIND>(prims, orig);
     if (KIND == ABX_PRIM_POINT3F)
       leaf_box[i] = make_float4(box.lo[0], box.lo[1], box.lo[2], __uint_as_float(orig));
     else
@@ -337,7 +364,7 @@ __global__ void __launch_bounds__(kHierThreads)
     {
 #pragma unroll
       for (int d = 0; d < 3; ++d)
-        sleaf[tid][3 + (LF == 6 ? d : 0)] = box.hi[d];
+        sleaf[tid][LF == 6 ? 3 + d : d] = box.hi[d];
     }
     sperm[tid] = orig;
     sdelta[tid + 1] = deltaOf(codes, i, n_int);
@@ -345,14 +372,18 @@ __global__ void __launch_bounds__(kHierThreads)
   else
     sdelta[tid + 1] = LLONG_MAX;
   if (tid == 0)
+  {
     sdelta[0] = deltaOf(codes, a - 1, n_int);
+    sqn[0] = 0;
+    sqn[1] = 0;
+    spn = 0;
+  }
   __syncthreads();
 
   // locality of parent p = a + tid (needs leaves p and p+1 in the chunk)
   {
     long long const mine = sdelta[tid + 1];
-    // inclusive prefix max of sdelta[0..tid]
-    long long pre = sdelta[tid];
+    long long pre = sdelta[tid]; // inclusive prefix max of sdelta[0..tid]
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1)
     {
@@ -360,8 +391,7 @@ __global__ void __launch_bounds__(kHierThreads)
       if (lane >= o)
         pre = max(pre, t);
     }
-    // inclusive suffix max of w[t'] = sdelta[t'+2] (t'+2 <= cn), t' >= tid
-    long long suf = (tid + 2 <= cn) ? sdelta[tid + 2] : LLONG_MIN;
+    long long suf = (tid + 2 <= cn) ? sdelta[tid + 2] : LLONG_MIN; // inclusive suffix max of sdelta[t+2], t >= tid
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1)
     {
@@ -383,86 +413,212 @@ __global__ void __launch_bounds__(kHierThreads)
     sflag[tid] = local ? -1 : -2;
   }
   __syncthreads();
-  if (!active)
-    return;
 
-  int range_left = i, range_right = i;
-  long long delta_left = sdelta[tid];      // delta(i - 1)
-  long long delta_right = sdelta[tid + 1]; // delta(i)
-  int cur_ref = refLeaf(orig);
-  bool global_mode = false;
-
-  while (true)
+  // rounds over the work queue; item < T: leaf (chunk position), item >= T: finished
+  // local node (Karras index - a + T)
+  int cur = 0;
+  int count = cn; // round 0: one leaf per thread
+  bool first_round = true;
+  while (count > 0)
   {
-    bool const is_left_child = delta_right < delta_left;
-    int const apetrei_parent = is_left_child ? range_right : range_left - 1;
-    Box sib;
-    int sib_ref;
-    if (!global_mode)
+    if (tid < count)
     {
-      int const lp = apetrei_parent - a;
-      if (lp >= 0 && lp < cn - 1 && sflag[lp] != -2)
+      int const item = first_round ? tid : (int)squeue[cur][tid];
+      int range_left, range_right, ref;
+      Box box;
+      if (item < T)
       {
-        // ---- shared-memory protocol ------------------------------------------------
-        __threadfence_block(); // my record (sleaf / snode) before the flag
-        int const old = atomicCAS(&sflag[lp], -1, is_left_child ? range_left : range_right);
-        if (old == -1)
-          return;
-        __threadfence_block();
-        int sib_pos; // sorted position (leaf) or Karras index (internal) of the sibling
-        bool sib_is_leaf;
-        if (is_left_child)
-        {
-          range_right = old;
-          sib_pos = apetrei_parent + 1;
-          sib_is_leaf = (sib_pos == range_right);
-          delta_right = sdelta[range_right - a + 1];
-        }
-        else
-        {
-          range_left = old;
-          sib_pos = apetrei_parent;
-          sib_is_leaf = (sib_pos == range_left);
-          delta_left = sdelta[range_left - a];
-        }
-        int const sl = sib_pos - a;
-        if (sib_is_leaf)
-        {
-          volatile float *lf = sleaf[sl];
+        range_left = range_right = a + item;
+        ref = refLeaf(sperm[item]);
 #pragma unroll
-          for (int d = 0; d < 3; ++d)
-          {
-            sib.lo[d] = lf[d];
-            sib.hi[d] = LF == 6 ? lf[LF == 6 ? 3 + d : d] : lf[d];
-          }
-          sib_ref = refLeaf(sperm[sl]);
-        }
-        else
+        for (int d = 0; d < 3; ++d)
         {
-          volatile float *nb = snode[sl];
-#pragma unroll
-          for (int d = 0; d < 3; ++d)
-          {
-            sib.lo[d] = nb[d];
-            sib.hi[d] = nb[3 + d];
-          }
-          sib_ref = sib_pos;
+          box.lo[d] = sleaf[item][d];
+          box.hi[d] = LF == 6 ? sleaf[item][LF == 6 ? 3 + d : d] : sleaf[item][d];
         }
       }
       else
       {
-        global_mode = true;
-        __threadfence(); // publish my global record (leaf_box / Node64) device-wide
+        int const kk = item - T;
+        range_left = a + srl[kk];
+        range_right = a + srr[kk];
+        ref = a + kk;
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+        {
+          box.lo[d] = snode[kk][d];
+          box.hi[d] = snode[kk][3 + d];
+        }
+      }
+      long long delta_left = sdelta[range_left - a];       // delta(range_left - 1)
+      long long delta_right = sdelta[range_right - a + 1]; // delta(range_right)
+      bool const is_left_child = delta_right < delta_left;
+      int const apetrei_parent = is_left_child ? range_right : range_left - 1;
+      int const lp = apetrei_parent - a;
+      if (lp < 0 || lp >= cn - 1 || sflag[lp] == -2)
+      {
+        // parent straddles the chunk boundary: hand the subtree to the global kernel
+        // (written out at the end, one global atomic per block)
+        spend[atomicAdd(&spn, 1)] = (unsigned short)item;
+      }
+      else
+      {
+        int const old = atomicCAS(&sflag[lp], -1, is_left_child ? range_left : range_right);
+        if (old != -1)
+        {
+          // second to arrive: the sibling's record was written in an earlier round
+          int sib_pos;
+          bool sib_is_leaf;
+          if (is_left_child)
+          {
+            range_right = old;
+            sib_pos = apetrei_parent + 1;
+            sib_is_leaf = (sib_pos == range_right);
+            delta_right = sdelta[range_right - a + 1];
+          }
+          else
+          {
+            range_left = old;
+            sib_pos = apetrei_parent;
+            sib_is_leaf = (sib_pos == range_left);
+            delta_left = sdelta[range_left - a];
+          }
+          int const sl = sib_pos - a;
+          Box sib;
+          int sib_ref;
+          if (sib_is_leaf)
+          {
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+            {
+              sib.lo[d] = sleaf[sl][d];
+              sib.hi[d] = LF == 6 ? sleaf[sl][LF == 6 ? 3 + d : d] : sleaf[sl][d];
+            }
+            sib_ref = refLeaf(sperm[sl]);
+          }
+          else
+          {
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+            {
+              sib.lo[d] = snode[sl][d];
+              sib.hi[d] = snode[sl][3 + d];
+            }
+            sib_ref = sib_pos;
+          }
+          int const karras_parent = delta_right < delta_left ? range_right : range_left;
+          if (is_left_child)
+            writeNode(nodes, karras_parent, box, ref, sib, sib_ref, range_left, range_right);
+          else
+            writeNode(nodes, karras_parent, sib, sib_ref, box, ref, range_left, range_right);
+          boxUnion(box, sib);
+          if (karras_parent == 0)
+          {
+            // root (the whole tree fits in one chunk): TreeConstruction.hpp:108-113
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+            {
+              bounds6[d] = box.lo[d];
+              bounds6[3 + d] = box.hi[d];
+            }
+          }
+          else
+          {
+            int const kk = karras_parent - a; // a local node's Karras index is an end of its range
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+            {
+              snode[kk][d] = box.lo[d];
+              snode[kk][3 + d] = box.hi[d];
+            }
+            srl[kk] = (short)(range_left - a);
+            srr[kk] = (short)(range_right - a);
+            int const slot = atomicAdd(&sqn[cur ^ 1], 1);
+            squeue[cur ^ 1][slot] = (unsigned short)(T + kk);
+          }
+        }
       }
     }
-    if (global_mode)
+    __syncthreads();
+    cur ^= 1;
+    first_round = false;
+    count = sqn[cur];
+    __syncthreads();
+    if (tid == 0)
+      sqn[cur ^ 1] = 0;
+    __syncthreads();
+  }
+
+  // append this chunk's maximal local subtrees to the pending list
+  if (tid == 0)
+    spbase = spn ? atomicAdd(pending_count, (unsigned)spn) : 0u;
+  __syncthreads();
+  if (tid < spn)
+  {
+    int const item = spend[tid];
+    PendingNode pn;
+    if (item < T)
     {
-      // ---- global protocol (nodes straddling a chunk boundary) ----------------------
+      pn.range_left = pn.range_right = a + item;
+      pn.ref = refLeaf(sperm[item]);
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+      {
+        pn.box[d] = sleaf[item][d];
+        pn.box[3 + d] = LF == 6 ? sleaf[item][LF == 6 ? 3 + d : d] : sleaf[item][d];
+      }
+    }
+    else
+    {
+      int const kk = item - T;
+      pn.range_left = a + srl[kk];
+      pn.range_right = a + srr[kk];
+      pn.ref = a + kk;
+#pragma unroll
+      for (int d = 0; d < 6; ++d)
+        pn.box[d] = snode[kk][d];
+    }
+    pending[spbase + tid] = pn;
+  }
+}
+
+// finishes the nodes that straddle chunk boundaries: global CAS flags in `ranges`,
+// records published with __threadfence before the flag, read with __ldcg after it
+// (the reference's CAS + load_fence, TreeConstruction.hpp:241-270)
+template <int KIND>
+__global__ void __launch_bounds__(256)
+    hierarchyGlobalKernel(int n, unsigned long long const *__restrict__ codes, Node64 *nodes,
+                          float4 const *leaf_box, int *ranges, PendingNode const *__restrict__ pending,
+                          unsigned const *__restrict__ pending_count, float *bounds6)
+{
+  int const n_int = n - 1;
+  unsigned const total = *pending_count;
+  for (unsigned it = blockIdx.x * blockDim.x + threadIdx.x; it < total; it += gridDim.x * blockDim.x)
+  {
+    PendingNode const pn = pending[it];
+    int range_left = pn.range_left, range_right = pn.range_right;
+    int cur_ref = pn.ref;
+    Box box;
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+    {
+      box.lo[d] = pn.box[d];
+      box.hi[d] = pn.box[3 + d];
+    }
+    long long delta_left = deltaOf(codes, range_left - 1, n_int);
+    long long delta_right = deltaOf(codes, range_right, n_int);
+    // the subtree's own record (leaf_box / Node64) was written by the local kernel: visible
+    while (true)
+    {
+      bool const is_left_child = delta_right < delta_left;
+      Box sib;
+      int sib_ref;
       if (is_left_child)
       {
+        int const apetrei_parent = range_right;
         int const old = atomicCAS(&ranges[apetrei_parent], -1, range_left);
         if (old == -1)
-          return; // first to arrive: the sibling's thread finishes this node
+          break; // first to arrive: the sibling's thread finishes this node
         range_right = old;
         int const right_child = apetrei_parent + 1;
         bool const right_is_leaf = (right_child == range_right);
@@ -478,9 +634,10 @@ __global__ void __launch_bounds__(kHierThreads)
       }
       else
       {
+        int const apetrei_parent = range_left - 1;
         int const old = atomicCAS(&ranges[apetrei_parent], -1, range_right);
         if (old == -1)
-          return;
+          break;
         range_left = old;
         int const left_child = apetrei_parent;
         bool const left_is_leaf = (left_child == range_left);
@@ -494,45 +651,25 @@ __global__ void __launch_bounds__(kHierThreads)
           sib_ref = left_child;
         }
       }
-    }
-    int const karras_parent = delta_right < delta_left ? range_right : range_left;
-
-    Box const &L = is_left_child ? box : sib;
-    Box const &R = is_left_child ? sib : box;
-    int const lref = is_left_child ? cur_ref : sib_ref;
-    int const rref = is_left_child ? sib_ref : cur_ref;
-    float4 *f = reinterpret_cast<float4 *>(nodes + karras_parent);
-    f[0] = make_float4(L.lo[0], L.lo[1], L.lo[2], __int_as_float(lref));
-    f[1] = make_float4(L.hi[0], L.hi[1], L.hi[2], __int_as_float(rref));
-    f[2] = make_float4(R.lo[0], R.lo[1], R.lo[2], __int_as_float(range_left));
-    f[3] = make_float4(R.hi[0], R.hi[1], R.hi[2], __int_as_float(range_right));
-
-    boxUnion(box, sib);
-    cur_ref = karras_parent;
-    if (karras_parent == 0)
-    {
-      // root: its box is the scene box (TreeConstruction.hpp:108-113 copies it out)
-#pragma unroll
-      for (int d = 0; d < 3; ++d)
+      int const karras_parent = delta_right < delta_left ? range_right : range_left;
+      if (is_left_child)
+        writeNode(nodes, karras_parent, box, cur_ref, sib, sib_ref, range_left, range_right);
+      else
+        writeNode(nodes, karras_parent, sib, sib_ref, box, cur_ref, range_left, range_right);
+      boxUnion(box, sib);
+      cur_ref = karras_parent;
+      if (karras_parent == 0)
       {
-        bounds6[d] = box.lo[d];
-        bounds6[3 + d] = box.hi[d];
-      }
-      return;
-    }
-    if (!global_mode)
-    {
-      // a local node's Karras index is an end of its range, inside the chunk
-      volatile float *nb = snode[karras_parent - a];
 #pragma unroll
-      for (int d = 0; d < 3; ++d)
-      {
-        nb[d] = box.lo[d];
-        nb[3 + d] = box.hi[d];
+        for (int d = 0; d < 3; ++d)
+        {
+          bounds6[d] = box.lo[d];
+          bounds6[3 + d] = box.hi[d];
+        }
+        break;
       }
-    }
-    else
       __threadfence(); // release the finished node before signalling its parent
+    }
   }
 }
 
@@ -721,11 +858,22 @@ abx_status buildHierarchy(cudaStream_t s, abx_bvh *t, void const *prims)
 {
   int const n = (int)t->n;
   TempBuffer<int> ranges;
+  TempBuffer<PendingNode> pending;
+  TempBuffer<unsigned> pending_count;
   ABX_TRY(ranges.alloc(n - 1, s));
+  ABX_TRY(pending.alloc(n, s)); // every maximal chunk-local subtree, at most one per leaf
+  ABX_TRY(pending_count.alloc(1, s));
   ABX_CUDA_TRY(cudaMemsetAsync(ranges.ptr, 0xff, sizeof(int) * (size_t)(n - 1), s));
-  ABX_DISPATCH_PRIM(t->kind, ABX_LAUNCH((hierarchyKernel<K>), divUp(n, kHierThreads), kHierThreads, 0, s, n,
+  ABX_CUDA_TRY(cudaMemsetAsync(pending_count.ptr, 0, sizeof(unsigned), s));
+  ABX_DISPATCH_PRIM(t->kind, ABX_LAUNCH((hierarchyLocalKernel<K>), divUp(n, kHierThreads), kHierThreads, 0, s, n,
                                         (unsigned long long const *)t->codes, t->perm, (float const *)prims, t->nodes,
-                                        t->leaf_box, t->leaf_tri, ranges.ptr, t->bounds_dev));
+                                        t->leaf_box, t->leaf_tri, pending.ptr, pending_count.ptr, t->bounds_dev));
+  // the local kernel's records are complete at the kernel boundary; the global kernel
+  // only orders its own writes
+  int const grid = std::min(divUp(n, 256 * 8), kNumSMs * 8);
+  ABX_DISPATCH_PRIM(t->kind, ABX_LAUNCH((hierarchyGlobalKernel<K>), std::max(grid, 1), 256, 0, s, n,
+                                        (unsigned long long const *)t->codes, t->nodes, t->leaf_box, ranges.ptr,
+                                        pending.ptr, pending_count.ptr, t->bounds_dev));
   return ABX_OK;
 }
 

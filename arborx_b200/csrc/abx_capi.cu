@@ -4,7 +4,9 @@
 
 #include <algorithm>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <unordered_map>
 #include <vector>
 
 namespace abx
@@ -58,17 +60,6 @@ static abx_status ensureDevice()
       init_err = cudaErrorNoDevice;
     if (init_err != cudaSuccess)
       return;
-    // keep freed blocks in the stream-ordered pool: temporaries are re-used
-    // across calls instead of going back to the driver
-    for (int d = 0; d < count; ++d)
-    {
-      cudaMemPool_t pool;
-      if (cudaDeviceGetDefaultMemPool(&pool, d) == cudaSuccess)
-      {
-        unsigned long long threshold = ~0ull;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
-      }
-    }
   });
   if (init_err != cudaSuccess)
   {
@@ -78,19 +69,89 @@ static abx_status ensureDevice()
   return ABX_OK;
 }
 
+// ---- device memory: a small caching allocator -------------------------------------------
+// Temporaries and tree buffers are recycled through per-(device, stream, size class) free
+// lists, like the reference's memory pools keep Views cheap: a block released on a stream
+// is handed to the next request of the same class on the SAME stream, where stream order
+// already guarantees that its previous users are done.  After the first call of a given
+// shape no driver allocation happens at all.  (cudaMallocAsync's pool was measured to keep
+// re-growing for ~10 steps under this library's mix of 4 KB ... 1.3 GB requests.)
+namespace
+{
+struct AllocKey
+{
+  int device;
+  cudaStream_t stream;
+  size_t cls;
+  bool operator<(AllocKey const &o) const
+  {
+    if (device != o.device)
+      return device < o.device;
+    if (stream != o.stream)
+      return stream < o.stream;
+    return cls < o.cls;
+  }
+};
+std::mutex g_alloc_mutex;
+std::map<AllocKey, std::vector<void *>> g_free_blocks;
+std::unordered_map<void *, std::pair<int, size_t>> g_block_info; // ptr -> (device, class)
+int64_t g_cached_bytes = 0;
+
+size_t sizeClass(size_t bytes)
+{
+  if (bytes < 512)
+    return 512;
+  // 1/8-octave classes: at most 12.5 % slack
+  int const msb = 63 - __builtin_clzll((unsigned long long)bytes);
+  size_t const step = (size_t)1 << (msb >= 3 ? msb - 3 : 0);
+  return (bytes + step - 1) / step * step;
+}
+} // namespace
+
 abx_status deviceAlloc(void **p, size_t bytes, cudaStream_t s)
 {
   *p = nullptr;
-  if (bytes == 0)
-    bytes = 16;
-  ABX_CUDA_TRY(cudaMallocAsync(p, bytes, s));
+  size_t const cls = sizeClass(bytes);
+  int dev = 0;
+  ABX_CUDA_TRY(cudaGetDevice(&dev));
+  {
+    std::lock_guard<std::mutex> lock(g_alloc_mutex);
+    auto it = g_free_blocks.find(AllocKey{dev, s, cls});
+    if (it != g_free_blocks.end() && !it->second.empty())
+    {
+      *p = it->second.back();
+      it->second.pop_back();
+      g_cached_bytes -= (int64_t)cls;
+      return ABX_OK;
+    }
+  }
+  cudaError_t e = cudaMalloc(p, cls);
+  if (e != cudaSuccess)
+  {
+    // give cached blocks back to the driver and retry once
+    abx_trim();
+    e = cudaMalloc(p, cls);
+  }
+  if (e != cudaSuccess)
+  {
+    setError(std::string("cudaMalloc(") + std::to_string(cls) + "): " + cudaGetErrorString(e));
+    return ABX_ERR_CUDA;
+  }
+  std::lock_guard<std::mutex> lock(g_alloc_mutex);
+  g_block_info[*p] = {dev, cls};
   return ABX_OK;
 }
 
 void deviceFree(void *p, cudaStream_t s)
 {
-  if (p)
-    cudaFreeAsync(p, s);
+  if (!p)
+    return;
+  std::lock_guard<std::mutex> lock(g_alloc_mutex);
+  auto it = g_block_info.find(p);
+  if (it == g_block_info.end())
+    return; // not ours
+  g_free_blocks[AllocKey{it->second.first, s, it->second.second}].push_back(p);
+  g_cached_bytes += (int64_t)it->second.second;
 }
 
 static abx_policy defaultPolicy()
@@ -362,6 +423,26 @@ int64_t abx_profile_report(char *buf, int64_t capacity)
     buf[c] = 0;
   }
   return (int64_t)out.size() + 1;
+}
+
+// releases every cached (currently unused) device block; returns the bytes released
+int64_t abx_trim(void)
+{
+  cudaDeviceSynchronize();
+  std::lock_guard<std::mutex> lock(g_alloc_mutex);
+  int64_t released = 0;
+  for (auto &kv : g_free_blocks)
+  {
+    for (void *p : kv.second)
+    {
+      cudaFree(p);
+      g_block_info.erase(p);
+      released += (int64_t)kv.first.cls;
+    }
+    kv.second.clear();
+  }
+  g_cached_bytes = 0;
+  return released;
 }
 
 abx_status abx_free(void *stream, void *ptr_dev)

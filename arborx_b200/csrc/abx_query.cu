@@ -206,7 +206,15 @@ struct GlobalHeap
 
 // K > 0: register list of exactly K candidates (the first min(k, found) are
 // reported; K >= k).  K == 0: global heap with run-time k.
+//
+// Persistent lanes: a block owns kQueriesPerBlock consecutive (Morton-sorted) queries
+// and every lane pulls its next query from a shared-memory counter as soon as its
+// current one is finished.  The kernel is ONE flat loop (refill -> visit a node -> pick
+// the next node or pop), so a lane that finishes early is not parked at a
+// reconvergence point behind the longest traversal of its warp.
 constexpr int kNearestBucket = 1; // 1 = leaves only
+constexpr int kQueriesPerBlock = kThreads * 32;
+constexpr int kNodeDone = -2;
 
 template <int K, int LEAF_F4, bool TRI>
 __global__ void __launch_bounds__(kThreads)
@@ -217,47 +225,28 @@ __global__ void __launch_bounds__(kThreads)
                   int32_t *__restrict__ counts, uint32_t *__restrict__ indices, float *__restrict__ distances,
                   float2 *__restrict__ scratch)
 {
-  int64_t const t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  if (t >= q)
-    return;
-  int64_t const qi = qperm ? (int64_t)qperm[t] : t;
-  int const k = k_per_query ? k_per_query[qi] : k_uniform;
-  // rows are compact: row_stride = min(k, n) for uniform k, CRS offsets otherwise
-  int64_t const base = offsets ? (int64_t)offsets[qi] : qi * (int64_t)row_stride;
-  if (k < 1)
-  {
-    if (counts)
-      counts[qi] = 0;
-    return;
-  }
-  float const px = pts[3 * qi], py = pts[3 * qi + 1], pz = pts[3 * qi + 2];
-
-  if (n == 1)
-  {
-    // TreeTraversal.hpp:168-178: the single value is reported unconditionally
-    float4 lo = __ldg(leaf_box);
-    float4 hi = prim_kind == ABX_PRIM_POINT3F ? lo : __ldg(leaf_box + 1);
-    float const d2 = TRI ? pointTriangleDist2(px, py, pz, __ldg(leaf_tri), __ldg(leaf_tri + 1), __ldg(leaf_tri + 2))
-                         : pointBoxDist2v(px, py, pz, lo, hi);
-    indices[base] = 0u;
-    if (distances)
-      distances[base] = __fsqrt_rn(d2);
-    if (counts)
-      counts[qi] = 1;
-    return;
-  }
+  __shared__ unsigned long long s_next;
+  int64_t const block_begin = (int64_t)blockIdx.x * kQueriesPerBlock;
+  int64_t const block_end = min(q, block_begin + (int64_t)kQueriesPerBlock);
+  if (threadIdx.x == 0)
+    s_next = (unsigned long long)(block_begin + kThreads);
+  __syncthreads();
 
   constexpr bool USE_REGS = K > 0;
   RegList<USE_REGS ? K : 1> list;
   GlobalHeap heap;
   heap.h = nullptr;
   heap.size = 0;
-  if (USE_REGS)
-    list.init();
-  else
-    heap.h = scratch + base;
   float radius2 = __int_as_float(0x7f800000);
   int found = 0;
+  int k = 0;
+  int64_t qi = 0, base = 0;
+  float px = 0.f, py = 0.f, pz = 0.f;
+  unsigned long long stack[kStackSize]; // (squared box distance, node) of the farther child
+  int sp = 0;
+  int node = kNodeDone;
+  bool have_query = false;
+  int64_t t = block_begin + threadIdx.x; // first query of this lane; later ones come from s_next
 
   auto offer = [&](float d2, unsigned idx, int pos) {
     // leaf whose (box) squared distance is < radius2
@@ -286,12 +275,88 @@ __global__ void __launch_bounds__(kThreads)
     }
   };
 
-  // stack of (squared box distance, node) for the farther child
-  unsigned long long stack[kStackSize];
-  int sp = 0;
-  int node = 0;
   while (true)
   {
+    if (node == kNodeDone)
+    {
+      // ---- finish the previous query, fetch the next one ----
+      if (have_query)
+      {
+        if (USE_REGS)
+        {
+          int const m = min(min(found, k), USE_REGS ? K : 1);
+#pragma unroll
+          for (int i = 0; i < (USE_REGS ? K : 1); ++i)
+            if (i < m)
+            {
+              indices[base + i] = list.id[i];
+              if (distances)
+                distances[base + i] = __fsqrt_rn(list.d[i]);
+            }
+          found = m;
+        }
+        else
+        {
+          heap.sortAscending();
+          for (int i = 0; i < found; ++i)
+          {
+            float2 e = heap.h[i];
+            indices[base + i] = __float_as_uint(e.y);
+            if (distances)
+              distances[base + i] = __fsqrt_rn(e.x);
+          }
+        }
+        if (counts)
+          counts[qi] = found;
+        t = (int64_t)atomicAdd(&s_next, 1ull);
+        have_query = false;
+      }
+      if (t >= block_end)
+        break;
+      qi = qperm ? (int64_t)qperm[t] : t;
+      k = k_per_query ? k_per_query[qi] : k_uniform;
+      // rows are compact: row_stride = min(k, n) for uniform k, CRS offsets otherwise
+      base = offsets ? (int64_t)offsets[qi] : qi * (int64_t)row_stride;
+      px = pts[3 * qi], py = pts[3 * qi + 1], pz = pts[3 * qi + 2];
+      have_query = true;
+      found = 0;
+      radius2 = __int_as_float(0x7f800000);
+      sp = 0;
+      if (k < 1)
+        continue; // reported as an empty row on the next refill
+      if (n == 1)
+      {
+        // TreeTraversal.hpp:168-178: the single value is reported unconditionally
+        float4 lo = __ldg(leaf_box);
+        float4 hi = prim_kind == ABX_PRIM_POINT3F ? lo : __ldg(leaf_box + 1);
+        float const d2 = TRI ? pointTriangleDist2(px, py, pz, __ldg(leaf_tri), __ldg(leaf_tri + 1), __ldg(leaf_tri + 2))
+                             : pointBoxDist2v(px, py, pz, lo, hi);
+        if (USE_REGS)
+        {
+          list.init();
+          list.insert(d2, 0u);
+          found = 1;
+        }
+        else
+        {
+          heap.h = scratch + base;
+          heap.size = 0;
+          heap.push(d2, 0u);
+          found = 1;
+        }
+        continue;
+      }
+      if (USE_REGS)
+        list.init();
+      else
+      {
+        heap.h = scratch + base;
+        heap.size = 0;
+      }
+      node = 0;
+    }
+
+    // ---- visit one internal node ----
     float4 const *f = reinterpret_cast<float4 const *>(nodes + node);
     float4 const a0 = __ldg(f), a1 = __ldg(f + 1), a2 = __ldg(f + 2), a3 = __ldg(f + 3);
     int const lref = __float_as_int(a0.w), rref = __float_as_int(a1.w);
@@ -300,11 +365,11 @@ __global__ void __launch_bounds__(kThreads)
     float const dr = pointBoxDist2v(px, py, pz, a2, a3);
     int const l_hi = refIsLeaf(lref) ? rl : lref;
     int const r_lo = refIsLeaf(rref) ? rr : rref;
-    // leaves and small subtrees (<= kBucket contiguous sorted leaves) are consumed on
+    // leaves and small subtrees (<= kNearestBucket contiguous sorted leaves) are consumed on
     // the spot, nearer one first; radius2 may shrink between the two
     // (kNN prunes better by descending: sub-boxes reject most of a bucket once the list is
-    // full, so only subtrees of <= kNearestBucket leaves are scanned; measured on B200 at
-    // 10M / k = 10: bucket 8 = 13.3 ms, bucket 2 = 14.5 ms, leaves only = 11.4 ms)
+    // full; measured on B200 at 10M / k = 10: bucket 8 = 13.3 ms, bucket 2 = 14.5 ms,
+    // leaves only = 11.4 ms)
     bool const l_small = l_hi - rl < kNearestBucket, r_small = rr - r_lo < kNearestBucket;
     auto consume = [&](bool is_leaf, float d, int ref, int lo, int hi) {
       if (!(d < radius2))
@@ -337,16 +402,22 @@ __global__ void __launch_bounds__(kThreads)
           offer(d2, orig, j);
       }
     };
-    if (l_small && r_small && dr < dl)
+    // one consume site per slot (first / second), so lanes whose only candidate is the left
+    // child and lanes whose only candidate is the right child run the insertion code together
+    bool const swap = l_small && r_small && dr < dl;
+    bool const first_is_left = l_small && !swap;
+    if (l_small || r_small)
     {
-      consume(refIsLeaf(rref), dr, rref, r_lo, rr);
-      consume(refIsLeaf(lref), dl, lref, rl, l_hi);
-    }
-    else
-    {
-      if (l_small)
+      if (first_is_left)
         consume(refIsLeaf(lref), dl, lref, rl, l_hi);
-      if (r_small)
+      else
+        consume(refIsLeaf(rref), dr, rref, r_lo, rr);
+    }
+    if (l_small && r_small)
+    {
+      if (swap)
+        consume(refIsLeaf(lref), dl, lref, rl, l_hi);
+      else
         consume(refIsLeaf(rref), dr, rref, r_lo, rr);
     }
     bool const go_l = !l_small && dl < radius2;
@@ -362,50 +433,22 @@ __global__ void __launch_bounds__(kThreads)
         stack[sp++] = ((unsigned long long)__float_as_uint(fd) << 32) | (unsigned)fn;
       }
       node = left_first ? lref : rref;
-      continue;
     }
-    // pop until a node that can still contain a closer leaf
-    bool popped = false;
-    while (sp > 0)
+    else
     {
-      unsigned long long const e = stack[--sp];
-      if (__uint_as_float((unsigned)(e >> 32)) < radius2)
+      // pop until a node that can still contain a closer leaf
+      node = kNodeDone;
+      while (sp > 0)
       {
-        node = (int)(unsigned)e;
-        popped = true;
-        break;
+        unsigned long long const e = stack[--sp];
+        if (__uint_as_float((unsigned)(e >> 32)) < radius2)
+        {
+          node = (int)(unsigned)e;
+          break;
+        }
       }
     }
-    if (!popped)
-      break;
   }
-
-  if (USE_REGS)
-  {
-    int const m = min(min(found, k), USE_REGS ? K : 1);
-#pragma unroll
-    for (int i = 0; i < (USE_REGS ? K : 1); ++i)
-      if (i < m)
-      {
-        indices[base + i] = list.id[i];
-        if (distances)
-          distances[base + i] = __fsqrt_rn(list.d[i]);
-      }
-    found = m;
-  }
-  else
-  {
-    heap.sortAscending();
-    for (int i = 0; i < found; ++i)
-    {
-      float2 e = heap.h[i];
-      indices[base + i] = __float_as_uint(e.y);
-      if (distances)
-        distances[base + i] = __fsqrt_rn(e.x);
-    }
-  }
-  if (counts)
-    counts[qi] = found;
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -575,7 +618,7 @@ abx_status nearestQuery(cudaStream_t s, abx_bvh *t, float const *pts, int64_t q,
       ABX_CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(int32_t) * q, s));
     return ABX_OK;
   }
-  int const grid = divUp(q, kThreads);
+  int const grid = divUp(q, kQueriesPerBlock);
   bool const tri = t->kind == ABX_PRIM_TRI3F;
   int const kmax = k_per_query ? INT_MAX : k; // per-query k: general path
   int const row_stride = std::max(0, std::min(k, n));

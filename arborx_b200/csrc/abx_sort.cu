@@ -32,8 +32,10 @@ constexpr int kTile = kSortThreads * kItems; // 4096 keys per tile
 constexpr unsigned kFlagAgg = 1u << 30;
 constexpr unsigned kFlagIncl = 1u << 31;
 constexpr unsigned kValueMask = (1u << 30) - 1;
-constexpr int kDefaultConfig64 = 0; // see sortPairsImpl: tile-shape table
-constexpr int kDefaultConfig32 = 0;
+// see sortPairsImpl: tile-shape table.  Measured on B200, 10M pairs (scripts/tune_sort.py):
+// MATCH.ANY ranking 1.14 ms (u64) / 0.55 ms (u32); 8 ballots per key 0.86 / 0.40 ms.
+constexpr int kDefaultConfig64 = 7;
+constexpr int kDefaultConfig32 = 7;
 
 template <int BITS>
 struct Radix
@@ -207,7 +209,10 @@ __device__ __forceinline__ unsigned matchDigit(unsigned d)
   return peers;
 }
 
-template <typename KeyT, int BITS, int THREADS, int ITEMS, int MINB, bool BALLOT>
+// DEBUG != 0 variants give WRONG results on purpose; they exist to time the kernel with one
+// phase removed (ABX_SORT_CONFIG=10..13, scripts/tune_sort.py): 1 no ranking chain, 2 no
+// look-back, 3 no output stores, 4 no staging in shared memory
+template <typename KeyT, int BITS, int THREADS, int ITEMS, int MINB, bool BALLOT, int DEBUG = 0>
 __global__ void __launch_bounds__(THREADS, MINB)
     onesweepPassKernel(KeyT const *__restrict__ keys_in, KeyT *__restrict__ keys_out,
                        unsigned const *__restrict__ vals_in /* may be null: iota */, unsigned *__restrict__ vals_out,
@@ -261,6 +266,13 @@ __global__ void __launch_bounds__(THREADS, MINB)
   for (int j = 0; j < ITEMS; ++j)
   {
     unsigned const d = digitOf(key[j], shift, MASK);
+    if (DEBUG == 1)
+    {
+      rank[j] = (unsigned short)__popc(peers[j] & lanemask_lt);
+      if (lane == 0)
+        sm.warp_hist[warp][j] = 32;
+      continue;
+    }
     int const leader = __ffs(peers[j]) - 1;
     unsigned base = 0;
     if (lane == leader)
@@ -304,7 +316,11 @@ __global__ void __launch_bounds__(THREADS, MINB)
   for (int j = 0; j < ITEMS; ++j)
   {
     unsigned const d = digitOf(key[j], shift, MASK);
-    unsigned const pos = sm.digit_excl[d] + sm.warp_hist[warp][d] + rank[j];
+    unsigned pos = sm.digit_excl[d] + sm.warp_hist[warp][d] + rank[j];
+    if (DEBUG != 0)
+      pos = min(pos, (unsigned)TILE - 1);
+    if (DEBUG == 4)
+      continue;
     sm.keys[pos] = key[j];
     sm.vals[pos] = val[j];
   }
@@ -313,7 +329,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
   if (tid < BINS)
   {
     unsigned excl = 0;
-    if (tile != 0)
+    if (tile != 0 && DEBUG != 2)
     {
       // windowed look-back: kWindow predecessor states are fetched with independent
       // loads and consumed in order, so a chain of W unresolved tiles (the first wave
@@ -360,19 +376,27 @@ __global__ void __launch_bounds__(THREADS, MINB)
     if (pos < valid)
     {
       KeyT const k = sm.keys[pos];
-      unsigned const g = sm.global_off[digitOf(k, shift, MASK)] + pos;
+      unsigned g = sm.global_off[digitOf(k, shift, MASK)] + pos;
+      if (DEBUG != 0)
+        g = tile_base + pos; // keep the (wrong) stores in bounds
+      if (DEBUG == 3)
+      {
+        if (g == 0xffffffffu)
+          keys_out[0] = k;
+        continue;
+      }
       keys_out[g] = k;
       vals_out[g] = sm.vals[pos];
     }
   }
 }
 
-template <typename KeyT, int BITS, int THREADS, int ITEMS, int MINB, bool BALLOT>
+template <typename KeyT, int BITS, int THREADS, int ITEMS, int MINB, bool BALLOT, int DEBUG = 0>
 abx_status launchPasses(cudaStream_t s, int passes, KeyT *keys, KeyT *keys_alt, unsigned *vals, unsigned *vals_alt,
                         int64_t n, bool iota_vals, unsigned *hist, unsigned *counters, unsigned *states, int tiles)
 {
   constexpr int BINS = 1 << BITS;
-  auto kernel = onesweepPassKernel<KeyT, BITS, THREADS, ITEMS, MINB, BALLOT>;
+  auto kernel = onesweepPassKernel<KeyT, BITS, THREADS, ITEMS, MINB, BALLOT, DEBUG>;
   size_t const smem = sizeof(PassSmem<KeyT, BITS, THREADS, ITEMS>);
   static bool attr_set = false;
   if (!attr_set)
@@ -421,7 +445,9 @@ abx_status sortPairsImpl(cudaStream_t s, KeyT *keys, unsigned *vals, int64_t n, 
   case 4: tile_keys = 512 * 12; break;
   case 5: tile_keys = 256 * 16; break;
   case 6: tile_keys = 256 * 16; break;
-  case 7: tile_keys = 384 * 12; break;
+  case 7: case 10: case 11: case 12: case 13: tile_keys = 384 * 12; break;
+  case 8: tile_keys = 512 * 8; break;
+  case 9: tile_keys = 256 * 8; break;
   default: tile_keys = 256 * 16; break;
   }
   int const tiles = divUp(n, tile_keys);
@@ -455,6 +481,12 @@ abx_status sortPairsImpl(cudaStream_t s, KeyT *keys, unsigned *vals, int64_t n, 
   case 5: ABX_PASSES(256, 16, 3, false);
   case 6: ABX_PASSES(256, 16, 2, true);
   case 7: ABX_PASSES(384, 12, 2, true);
+  case 8: ABX_PASSES(512, 8, 2, true);
+  case 9: ABX_PASSES(256, 8, 5, true);
+  case 10: return launchPasses<KeyT, BITS, 384, 12, 2, true, 1>(s, PASSES, keys, keys_alt.ptr, vals, vals_alt.ptr, n, iota_vals, hist, counters, states, tiles);
+  case 11: return launchPasses<KeyT, BITS, 384, 12, 2, true, 2>(s, PASSES, keys, keys_alt.ptr, vals, vals_alt.ptr, n, iota_vals, hist, counters, states, tiles);
+  case 12: return launchPasses<KeyT, BITS, 384, 12, 2, true, 3>(s, PASSES, keys, keys_alt.ptr, vals, vals_alt.ptr, n, iota_vals, hist, counters, states, tiles);
+  case 13: return launchPasses<KeyT, BITS, 384, 12, 2, true, 4>(s, PASSES, keys, keys_alt.ptr, vals, vals_alt.ptr, n, iota_vals, hist, counters, states, tiles);
   default: ABX_PASSES(256, 16, 2, false);
   }
 #undef ABX_PASSES

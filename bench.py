@@ -17,8 +17,10 @@ entry points (pinned host inputs, results copied back to the host).
 
 --impl reference times the CPU restatement of the reference (oracle/, OpenMP, all
 host threads) -- the real reference cannot be built here (Kokkos absent).
-Multi-GPU (--gpus N under torchrun): the single-tree path does not shard ("replicas
-only"): every rank runs the same step on its own tree, weak scaling.
+Multi-GPU (--gpus N under torchrun): the path shards in DistributedTree -- every rank owns
+n points / q queries of a touching block lattice (distributed_tree_driver layout), the step
+is DistributedTree build + distributed radius + distributed kNN, weak scaling, NCCL
+all-to-all-v for forwarded queries and results.
 """
 import argparse
 import json
@@ -98,10 +100,21 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def make_inputs(n, q):
+def make_inputs(n, q, rank=None, world=1):
+    """rank is None: the single-tree bvh_driver clouds.  Otherwise this rank's block of the
+    distributed_tree_driver layout (benchmarks/distributed_tree_driver/distributed_tree_driver.cpp:44-149):
+    blocks of side 2a, a = cbrt(n), on a ceil(cbrt(R))^3 lattice, shift = 1 (touching)."""
     from tests import clouds
-    values = clouds.filled_box(0x5EED0001, n)
-    queries = clouds.filled_box(0x5EED0002, q)
+    if rank is None:
+        values = clouds.filled_box(0x5EED0001, n)
+        queries = clouds.filled_box(0x5EED0002, q)
+    else:
+        nb = int(np.ceil(np.cbrt(world) - 1e-9))
+        ijk = np.array([rank % nb, (rank // nb) % nb, rank // (nb * nb)], np.float32)
+        a = np.float32(np.cbrt(float(n)))
+        off = (np.float32(2) * a * ijk).astype(np.float32)
+        values = (clouds.filled_box(0x5EED0001 + 16 * rank, n) + off).astype(np.float32)
+        queries = (clouds.filled_box(0x5EED0002 + 16 * rank, q) + off).astype(np.float32)
     r = clouds.bvh_driver_radius(K_NEIGHBORS)
     spheres = np.concatenate([queries, np.full((q, 1), r, np.float32)], 1).astype(np.float32)
     return values, queries, spheres, float(r)
@@ -188,6 +201,10 @@ def algorithmic_bytes(cpu, n, q, nnz):
     return {
         "spatialKernel<count>": q * (sp + 16 + 4),
         "spatialKernel<fill>": q * (sp + 16 + 4) + 4.0 * nnz,
+        "spatialKernel<stage>": q * (sp + 16 + 4) + 4.0 * nnz,
+        "spatialKernel<compact>": 8.0 * q + 12.0 * nnz,
+        "hierarchyLocalKernel": 64.0 * n + 36.0 * n,
+        "hierarchyGlobalKernel": 0.05 * n * (36 + 64 + 64),
         "nearestKernel": q * (nn + 12 + 4 * K_NEIGHBORS),
         "onesweepPassKernel<u64>": 24.0 * n,
         "onesweepPassKernel<u32>": 16.0 * q,
@@ -213,7 +230,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n, q = args.n, args.q
-    values, queries, spheres, r = make_inputs(n, q)
+    values, queries, spheres, r = make_inputs(n, q, rank if world > 1 else None, world)
     space = abx.ExecutionSpace()
     d_values = torch.from_numpy(values).cuda()
     d_queries = torch.from_numpy(queries).cuda()
@@ -223,11 +240,20 @@ def run_ours(args):
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
+    if world > 1:
+        from arborx_b200.distributed import DistributedTree
+        comm = dist.group.WORLD
+
+    def make_tree(vals):
+        # N > 1: the path shards in DistributedTree (primitives per GPU, replicated top tree,
+        # all-to-all-v of forwarded queries and results); N = 1: the single tree
+        return DistributedTree(comm, space, vals) if world > 1 else abx.BoundingVolumeHierarchy(space, vals)
+
     def step(timers=None):
         e = [ev() for _ in range(4)] if timers is not None else None
         if e:
             e[0].record()
-        bvh = abx.BoundingVolumeHierarchy(space, d_values)
+        bvh = make_tree(d_values)
         if e:
             e[1].record()
         idx, off = bvh.query(space, p_spatial)
@@ -237,7 +263,7 @@ def run_ours(args):
         if e:
             e[3].record()
             timers.append(e)
-        return idx.numel()
+        return idx.shape[0]
 
     def barrier():
         if world > 1:
@@ -264,7 +290,10 @@ def run_ours(args):
     abx.profile_enable(False)
     clocks = sampler.stop()
     elapsed_ms = t_start.elapsed_time(t_stop)
-    parts = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(3)] for e in timers]).mean(0)  # build, radius, knn
+    per_step = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(3)] for e in timers])
+    if os.environ.get("ABX_BENCH_DEBUG"):
+        print("per-step (build, radius, knn) ms:\n", per_step, file=sys.stderr)
+    parts = per_step.mean(0)  # build, radius, knn
     if world > 1:
         t = torch.tensor([elapsed_ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -280,6 +309,14 @@ def run_ours(args):
     hp_nearest = abx.nearest(h_queries, K_NEIGHBORS)
 
     def e2e_step():
+        if world > 1:
+            # DistributedTree takes device data: the host<->device copies are done here, inside the step
+            dv = h_values.cuda(non_blocking=True)
+            tree = make_tree(dv)
+            idx, off = tree.query(space, abx.intersects(h_spheres.cuda(non_blocking=True)))
+            kidx, koff = tree.query(space, abx.nearest(h_queries.cuda(non_blocking=True), K_NEIGHBORS))
+            idx, off, kidx, koff = idx.cpu(), off.cpu(), kidx.cpu(), koff.cpu()
+            return int(off[-1]) + int(koff[-1]), idx.numel(), kidx.numel()
         bvh = abx.BoundingVolumeHierarchy(space, h_values)
         idx, off = bvh.query(space, hp_spatial)
         kidx, koff = bvh.query(space, hp_nearest)
@@ -309,8 +346,8 @@ def run_ours(args):
         return
 
     # ---- CPU baseline (bounded sample) + traversal counters for the roofline ---------
-    qs = min(q, args.cpu_sample)
-    cpu = cpu_run(values, queries, spheres, qs)
+    qs = min(q, args.cpu_sample if world == 1 else min(args.cpu_sample, 100_000))
+    cpu = cpu_run(values, queries, spheres, qs)  # rank 0's block when N > 1 (counters for the byte model)
     scale = q / qs
     cpu_value = combined_rate(n, q, cpu["t_build"], cpu["t_radius"] * scale, cpu["t_knn"] * scale)
 
@@ -376,7 +413,9 @@ def run_ours(args):
                                                                     "nearest_L", "nnz_per_query")}},
     }
     if world > 1:
-        line["config"]["parallelism"] = "replicas only: %d independent trees (single-tree path does not shard)" % world
+        line["config"]["parallelism"] = ("DistributedTree over %d GPUs: %d points and %d queries per rank on a touching "
+                                         "block lattice; top tree + all-to-all-v forwarding (NCCL)" % (world, n, q))
+        line["config"]["workload"] += " through DistributedTree (BASELINE.json configs[3] layout, weak scaling)"
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -86,6 +86,9 @@ ABX_API int abx_version(void);
  * (bench.py reports the delta over the timed region as gpu_launches) */
 ABX_API int64_t abx_launch_count(void);
 ABX_API abx_status abx_free(void *stream, void *ptr_dev);
+/* The library recycles its device buffers through per-stream free lists; abx_trim()
+ * synchronises the device and returns all cached blocks to the driver (bytes released). */
+ABX_API int64_t abx_trim(void);
 /* Per-kernel device timing (the analogue of the reference's Kokkos-Tools regions,
  * SURVEY.md section 5): CUDA events on the launching stream around every launch.
  * enable(1) clears and starts recording, enable(0) stops.  report() synchronises
