@@ -351,8 +351,60 @@ static abx_status nearestCrs(abx_bvh *bvh, cudaStream_t s, void const *pts, int6
   TempBuffer<uint32_t> qperm;
   if (policy.sort_predicates && n > 1)
     ABX_TRY(predicatePermutation(s, bvh, ABX_PRED_POINT3F, pts, q, qperm));
+  // Rows are laid out for min(k, n) results, but a leaf at infinite (or NaN) distance is never
+  // accepted (`distance < radius` with radius = +inf, TreeTraversal.hpp:255): such rows come out
+  // short and the reference compacts them (CrsGraphWrapperImpl.hpp:296-318).  The kernel counts
+  // per row and adds up the missing entries; the compaction below only runs when there are any.
+  TempBuffer<int32_t> counts;
+  TempBuffer<unsigned long long> missing;
+  ABX_TRY(counts.alloc((size_t)q + 1, s));
+  ABX_TRY(missing.alloc(1, s));
+  ABX_CUDA_TRY(cudaMemsetAsync(missing.ptr, 0, sizeof(unsigned long long), s));
   ABX_TRY(nearestQuery(s, bvh, (float const *)pts, q, k, k_per_query, qperm.ptr, uniform ? nullptr : offsets, total,
-                       nullptr, *indices_out, (float *)dist));
+                       counts.ptr, *indices_out, (float *)dist, missing.ptr));
+  unsigned long long h_missing = 0;
+  ABX_CUDA_TRY(cudaMemcpyAsync(&h_missing, missing.ptr, sizeof(h_missing), cudaMemcpyDeviceToHost, s));
+  ABX_CUDA_TRY(cudaStreamSynchronize(s));
+  if (h_missing == 0)
+    return ABX_OK;
+  // underflow: compact into exactly sized outputs
+  int64_t const new_total = total - (int64_t)h_missing;
+  TempBuffer<int32_t> old_offsets;
+  ABX_TRY(old_offsets.alloc((size_t)q + 1, s));
+  ABX_CUDA_TRY(cudaMemcpyAsync(old_offsets.ptr, offsets, sizeof(int32_t) * (size_t)(q + 1), cudaMemcpyDeviceToDevice, s));
+  ABX_TRY(exclusiveScanI32(s, counts.ptr, offsets, q + 1));
+  uint32_t *old_idx = *indices_out;
+  float *old_dist = (float *)dist;
+  TempBuffer<uint32_t> keep_idx;   // library-allocated outputs must outlive the copy
+  TempBuffer<float> keep_dist;
+  if (alloc)
+  {
+    // the caller's allocator hands out new views; stage the old rows first
+    ABX_TRY(keep_idx.alloc((size_t)total, s));
+    ABX_CUDA_TRY(cudaMemcpyAsync(keep_idx.ptr, old_idx, sizeof(uint32_t) * (size_t)total, cudaMemcpyDeviceToDevice, s));
+    old_idx = keep_idx.ptr;
+    if (dist)
+    {
+      ABX_TRY(keep_dist.alloc((size_t)total, s));
+      ABX_CUDA_TRY(cudaMemcpyAsync(keep_dist.ptr, old_dist, sizeof(float) * (size_t)total, cudaMemcpyDeviceToDevice, s));
+      old_dist = keep_dist.ptr;
+    }
+    ABX_CUDA_TRY(cudaStreamSynchronize(s)); // the allocator may free the previous views
+  }
+  void *nidx = nullptr, *ndist = nullptr;
+  ABX_TRY(allocOut(alloc, user, 1, sizeof(uint32_t) * (size_t)new_total, s, &nidx));
+  if (distances_out)
+    ABX_TRY(allocOut(alloc, user, 2, sizeof(float) * (size_t)new_total, s, &ndist));
+  ABX_TRY(compactRows(s, q, old_offsets.ptr, offsets, old_idx, old_dist, (uint32_t *)nidx, (float *)ndist));
+  if (!alloc)
+  {
+    deviceFree(*indices_out, s);
+    deviceFree(dist, s);
+  }
+  *indices_out = (uint32_t *)nidx;
+  if (distances_out)
+    *distances_out = (float *)ndist;
+  *nnz_out = new_total;
   return ABX_OK;
 }
 
@@ -729,6 +781,43 @@ abx_status abx_dbscan_host(void *stream, const float *xyz_host, int64_t n, float
     ABX_CUDA_TRY(cudaMemcpyAsync(labels_host, labels.ptr, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, s));
   ABX_CUDA_TRY(cudaStreamSynchronize(s));
   return ABX_OK;
+}
+
+abx_status abx_dist_merge_crs(void *stream, int64_t q, const int32_t *local_offsets_dev, const int32_t *local_indices_dev,
+                              int32_t rank, const int32_t *remote_offsets_dev, const int32_t *remote_values2_dev,
+                              int32_t *out_offsets_dev, int32_t *out_values2_dev)
+{
+  ABX_TRY(ensureDevice());
+  return mergeCrs((cudaStream_t)stream, q, local_offsets_dev, local_indices_dev, rank, remote_offsets_dev,
+                  remote_values2_dev, out_offsets_dev, out_values2_dev);
+}
+
+abx_status abx_dist_route_count(void *stream, int pred_kind, const void *preds_dev, int64_t q, const float *rank_boxes6_dev,
+                                int32_t n_ranks, int32_t self_rank, uint32_t *counts_dev)
+{
+  ABX_TRY(ensureDevice());
+  cudaStream_t s = (cudaStream_t)stream;
+  ABX_CUDA_TRY(cudaMemsetAsync(counts_dev, 0, sizeof(uint32_t) * (size_t)n_ranks, s));
+  return routeLaunch(s, false, pred_kind, preds_dev, q, rank_boxes6_dev, n_ranks, self_rank, counts_dev, nullptr, nullptr,
+                     nullptr);
+}
+
+abx_status abx_dist_route_fill(void *stream, int pred_kind, const void *preds_dev, int64_t q, const float *rank_boxes6_dev,
+                               int32_t n_ranks, int32_t self_rank, const uint32_t *base_dev, uint32_t *cursors_dev,
+                               int32_t *query_ids_dev)
+{
+  ABX_TRY(ensureDevice());
+  cudaStream_t s = (cudaStream_t)stream;
+  ABX_CUDA_TRY(cudaMemsetAsync(cursors_dev, 0, sizeof(uint32_t) * (size_t)n_ranks, s));
+  return routeLaunch(s, true, pred_kind, preds_dev, q, rank_boxes6_dev, n_ranks, self_rank, nullptr, base_dev, cursors_dev,
+                     query_ids_dev);
+}
+
+abx_status abx_dist_pair_with_rank(void *stream, const int32_t *indices_dev, int64_t n, int32_t rank,
+                                   int32_t *values2_dev)
+{
+  ABX_TRY(ensureDevice());
+  return pairWithRank((cudaStream_t)stream, indices_dev, n, rank, values2_dev);
 }
 
 // ---- stage-level entry points -------------------------------------------------------

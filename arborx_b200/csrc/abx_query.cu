@@ -206,15 +206,7 @@ struct GlobalHeap
 
 // K > 0: register list of exactly K candidates (the first min(k, found) are
 // reported; K >= k).  K == 0: global heap with run-time k.
-//
-// Persistent lanes: a block owns kQueriesPerBlock consecutive (Morton-sorted) queries
-// and every lane pulls its next query from a shared-memory counter as soon as its
-// current one is finished.  The kernel is ONE flat loop (refill -> visit a node -> pick
-// the next node or pop), so a lane that finishes early is not parked at a
-// reconvergence point behind the longest traversal of its warp.
 constexpr int kNearestBucket = 1; // 1 = leaves only
-constexpr int kQueriesPerBlock = kThreads * 32;
-constexpr int kNodeDone = -2;
 
 template <int K, int LEAF_F4, bool TRI>
 __global__ void __launch_bounds__(kThreads)
@@ -223,30 +215,49 @@ __global__ void __launch_bounds__(kThreads)
                   unsigned const *__restrict__ qperm, int k_uniform, int row_stride,
                   int32_t const *__restrict__ k_per_query, int32_t const *__restrict__ offsets,
                   int32_t *__restrict__ counts, uint32_t *__restrict__ indices, float *__restrict__ distances,
-                  float2 *__restrict__ scratch)
+                  float2 *__restrict__ scratch, unsigned long long *__restrict__ missing)
 {
-  __shared__ unsigned long long s_next;
-  int64_t const block_begin = (int64_t)blockIdx.x * kQueriesPerBlock;
-  int64_t const block_end = min(q, block_begin + (int64_t)kQueriesPerBlock);
-  if (threadIdx.x == 0)
-    s_next = (unsigned long long)(block_begin + kThreads);
-  __syncthreads();
+  int64_t const t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (t >= q)
+    return;
+  int64_t const qi = qperm ? (int64_t)qperm[t] : t;
+  int const k = k_per_query ? k_per_query[qi] : k_uniform;
+  // rows are compact: row_stride = min(k, n) for uniform k, CRS offsets otherwise
+  int64_t const base = offsets ? (int64_t)offsets[qi] : qi * (int64_t)row_stride;
+  if (k < 1)
+  {
+    if (counts)
+      counts[qi] = 0;
+    return;
+  }
+  float const px = pts[3 * qi], py = pts[3 * qi + 1], pz = pts[3 * qi + 2];
+
+  if (n == 1)
+  {
+    // TreeTraversal.hpp:168-178: the single value is reported unconditionally
+    float4 lo = __ldg(leaf_box);
+    float4 hi = prim_kind == ABX_PRIM_POINT3F ? lo : __ldg(leaf_box + 1);
+    float const d2 = TRI ? pointTriangleDist2(px, py, pz, __ldg(leaf_tri), __ldg(leaf_tri + 1), __ldg(leaf_tri + 2))
+                         : pointBoxDist2v(px, py, pz, lo, hi);
+    indices[base] = 0u;
+    if (distances)
+      distances[base] = __fsqrt_rn(d2);
+    if (counts)
+      counts[qi] = 1;
+    return;
+  }
 
   constexpr bool USE_REGS = K > 0;
   RegList<USE_REGS ? K : 1> list;
   GlobalHeap heap;
   heap.h = nullptr;
   heap.size = 0;
+  if (USE_REGS)
+    list.init();
+  else
+    heap.h = scratch + base;
   float radius2 = __int_as_float(0x7f800000);
   int found = 0;
-  int k = 0;
-  int64_t qi = 0, base = 0;
-  float px = 0.f, py = 0.f, pz = 0.f;
-  unsigned long long stack[kStackSize]; // (squared box distance, node) of the farther child
-  int sp = 0;
-  int node = kNodeDone;
-  bool have_query = false;
-  int64_t t = block_begin + threadIdx.x; // first query of this lane; later ones come from s_next
 
   auto offer = [&](float d2, unsigned idx, int pos) {
     // leaf whose (box) squared distance is < radius2
@@ -275,88 +286,12 @@ __global__ void __launch_bounds__(kThreads)
     }
   };
 
+  // stack of (squared box distance, node) for the farther child
+  unsigned long long stack[kStackSize];
+  int sp = 0;
+  int node = 0;
   while (true)
   {
-    if (node == kNodeDone)
-    {
-      // ---- finish the previous query, fetch the next one ----
-      if (have_query)
-      {
-        if (USE_REGS)
-        {
-          int const m = min(min(found, k), USE_REGS ? K : 1);
-#pragma unroll
-          for (int i = 0; i < (USE_REGS ? K : 1); ++i)
-            if (i < m)
-            {
-              indices[base + i] = list.id[i];
-              if (distances)
-                distances[base + i] = __fsqrt_rn(list.d[i]);
-            }
-          found = m;
-        }
-        else
-        {
-          heap.sortAscending();
-          for (int i = 0; i < found; ++i)
-          {
-            float2 e = heap.h[i];
-            indices[base + i] = __float_as_uint(e.y);
-            if (distances)
-              distances[base + i] = __fsqrt_rn(e.x);
-          }
-        }
-        if (counts)
-          counts[qi] = found;
-        t = (int64_t)atomicAdd(&s_next, 1ull);
-        have_query = false;
-      }
-      if (t >= block_end)
-        break;
-      qi = qperm ? (int64_t)qperm[t] : t;
-      k = k_per_query ? k_per_query[qi] : k_uniform;
-      // rows are compact: row_stride = min(k, n) for uniform k, CRS offsets otherwise
-      base = offsets ? (int64_t)offsets[qi] : qi * (int64_t)row_stride;
-      px = pts[3 * qi], py = pts[3 * qi + 1], pz = pts[3 * qi + 2];
-      have_query = true;
-      found = 0;
-      radius2 = __int_as_float(0x7f800000);
-      sp = 0;
-      if (k < 1)
-        continue; // reported as an empty row on the next refill
-      if (n == 1)
-      {
-        // TreeTraversal.hpp:168-178: the single value is reported unconditionally
-        float4 lo = __ldg(leaf_box);
-        float4 hi = prim_kind == ABX_PRIM_POINT3F ? lo : __ldg(leaf_box + 1);
-        float const d2 = TRI ? pointTriangleDist2(px, py, pz, __ldg(leaf_tri), __ldg(leaf_tri + 1), __ldg(leaf_tri + 2))
-                             : pointBoxDist2v(px, py, pz, lo, hi);
-        if (USE_REGS)
-        {
-          list.init();
-          list.insert(d2, 0u);
-          found = 1;
-        }
-        else
-        {
-          heap.h = scratch + base;
-          heap.size = 0;
-          heap.push(d2, 0u);
-          found = 1;
-        }
-        continue;
-      }
-      if (USE_REGS)
-        list.init();
-      else
-      {
-        heap.h = scratch + base;
-        heap.size = 0;
-      }
-      node = 0;
-    }
-
-    // ---- visit one internal node ----
     float4 const *f = reinterpret_cast<float4 const *>(nodes + node);
     float4 const a0 = __ldg(f), a1 = __ldg(f + 1), a2 = __ldg(f + 2), a3 = __ldg(f + 3);
     int const lref = __float_as_int(a0.w), rref = __float_as_int(a1.w);
@@ -365,12 +300,13 @@ __global__ void __launch_bounds__(kThreads)
     float const dr = pointBoxDist2v(px, py, pz, a2, a3);
     int const l_hi = refIsLeaf(lref) ? rl : lref;
     int const r_lo = refIsLeaf(rref) ? rr : rref;
-    // leaves and small subtrees (<= kNearestBucket contiguous sorted leaves) are consumed on
+    // leaves and small subtrees (<= kBucket contiguous sorted leaves) are consumed on
     // the spot, nearer one first; radius2 may shrink between the two
     // (kNN prunes better by descending: sub-boxes reject most of a bucket once the list is
-    // full; measured on B200 at 10M / k = 10: bucket 8 = 13.3 ms, bucket 2 = 14.5 ms,
-    // leaves only = 11.4 ms)
-    bool const l_small = l_hi - rl < kNearestBucket, r_small = rr - r_lo < kNearestBucket;
+    // full, so only subtrees of <= kNearestBucket leaves are scanned; measured on B200 at
+    // 10M / k = 10: bucket 8 = 13.3 ms, bucket 2 = 14.5 ms, leaves only = 11.4 ms)
+    bool const l_small = kNearestBucket == 1 ? refIsLeaf(lref) : (l_hi - rl < kNearestBucket);
+    bool const r_small = kNearestBucket == 1 ? refIsLeaf(rref) : (rr - r_lo < kNearestBucket);
     auto consume = [&](bool is_leaf, float d, int ref, int lo, int hi) {
       if (!(d < radius2))
         return;
@@ -402,22 +338,16 @@ __global__ void __launch_bounds__(kThreads)
           offer(d2, orig, j);
       }
     };
-    // one consume site per slot (first / second), so lanes whose only candidate is the left
-    // child and lanes whose only candidate is the right child run the insertion code together
-    bool const swap = l_small && r_small && dr < dl;
-    bool const first_is_left = l_small && !swap;
-    if (l_small || r_small)
+    if (l_small && r_small && dr < dl)
     {
-      if (first_is_left)
-        consume(refIsLeaf(lref), dl, lref, rl, l_hi);
-      else
-        consume(refIsLeaf(rref), dr, rref, r_lo, rr);
+      consume(refIsLeaf(rref), dr, rref, r_lo, rr);
+      consume(refIsLeaf(lref), dl, lref, rl, l_hi);
     }
-    if (l_small && r_small)
+    else
     {
-      if (swap)
+      if (l_small)
         consume(refIsLeaf(lref), dl, lref, rl, l_hi);
-      else
+      if (r_small)
         consume(refIsLeaf(rref), dr, rref, r_lo, rr);
     }
     bool const go_l = !l_small && dl < radius2;
@@ -433,21 +363,73 @@ __global__ void __launch_bounds__(kThreads)
         stack[sp++] = ((unsigned long long)__float_as_uint(fd) << 32) | (unsigned)fn;
       }
       node = left_first ? lref : rref;
+      continue;
     }
-    else
+    // pop until a node that can still contain a closer leaf
+    bool popped = false;
+    while (sp > 0)
     {
-      // pop until a node that can still contain a closer leaf
-      node = kNodeDone;
-      while (sp > 0)
+      unsigned long long const e = stack[--sp];
+      if (__uint_as_float((unsigned)(e >> 32)) < radius2)
       {
-        unsigned long long const e = stack[--sp];
-        if (__uint_as_float((unsigned)(e >> 32)) < radius2)
-        {
-          node = (int)(unsigned)e;
-          break;
-        }
+        node = (int)(unsigned)e;
+        popped = true;
+        break;
       }
     }
+    if (!popped)
+      break;
+  }
+
+  if (USE_REGS)
+  {
+    int const m = min(min(found, k), USE_REGS ? K : 1);
+#pragma unroll
+    for (int i = 0; i < (USE_REGS ? K : 1); ++i)
+      if (i < m)
+      {
+        indices[base + i] = list.id[i];
+        if (distances)
+          distances[base + i] = __fsqrt_rn(list.d[i]);
+      }
+    found = m;
+  }
+  else
+  {
+    heap.sortAscending();
+    for (int i = 0; i < found; ++i)
+    {
+      float2 e = heap.h[i];
+      indices[base + i] = __float_as_uint(e.y);
+      if (distances)
+        distances[base + i] = __fsqrt_rn(e.x);
+    }
+  }
+  if (counts)
+    counts[qi] = found;
+  if (missing)
+  {
+    int const expected = offsets ? (offsets[qi + 1] - (int)base) : row_stride;
+    if (found < expected)
+      atomicAdd(missing, (unsigned long long)(expected - found));
+  }
+}
+
+// rows [old_offsets[i], +count_i) -> [new_offsets[i], +count_i), count_i = new_offsets[i+1] - new_offsets[i]
+__global__ void compactRowsKernel(int64_t q, int32_t const *__restrict__ old_offsets,
+                                  int32_t const *__restrict__ new_offsets, uint32_t const *__restrict__ old_idx,
+                                  float const *__restrict__ old_dist, uint32_t *__restrict__ new_idx,
+                                  float *__restrict__ new_dist)
+{
+  int64_t const i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= q)
+    return;
+  int const src = old_offsets[i], dst = new_offsets[i], c = new_offsets[i + 1] - dst;
+  for (int j = 0; j < c; ++j)
+  {
+    new_idx[dst + j] = old_idx[src + j];
+    if (new_dist)
+      new_dist[dst + j] = old_dist[src + j];
   }
 }
 
@@ -607,7 +589,7 @@ abx_status spatialCompact(cudaStream_t s, abx_bvh *t, int pred_kind, void const 
 // offsets = CRS offsets of min(k_i, n).  total_rows = size of indices.
 abx_status nearestQuery(cudaStream_t s, abx_bvh *t, float const *pts, int64_t q, int32_t k, int32_t const *k_per_query,
                         uint32_t const *qperm, int32_t const *offsets, int64_t total_rows, int32_t *counts,
-                        uint32_t *indices, float *distances)
+                        uint32_t *indices, float *distances, unsigned long long *missing)
 {
   if (q <= 0)
     return ABX_OK;
@@ -618,7 +600,7 @@ abx_status nearestQuery(cudaStream_t s, abx_bvh *t, float const *pts, int64_t q,
       ABX_CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(int32_t) * q, s));
     return ABX_OK;
   }
-  int const grid = divUp(q, kQueriesPerBlock);
+  int const grid = divUp(q, kThreads);
   bool const tri = t->kind == ABX_PRIM_TRI3F;
   int const kmax = k_per_query ? INT_MAX : k; // per-query k: general path
   int const row_stride = std::max(0, std::min(k, n));
@@ -628,15 +610,15 @@ abx_status nearestQuery(cudaStream_t s, abx_bvh *t, float const *pts, int64_t q,
     if (tri)                                                                                                           \
       ABX_LAUNCH_TAGGED("nearestKernel<" #KCAP ",tri>", (nearestKernel<KCAP, 2, true>), grid, kThreads, 0, s,          \
                         t->nodes, t->leaf_box, t->leaf_tri, n, t->kind, pts, q, qperm, k, row_stride, k_per_query,     \
-                        offsets, counts, indices, distances, SCRATCH);                                                 \
+                        offsets, counts, indices, distances, SCRATCH, missing);                                                 \
     else if (t->kind == ABX_PRIM_BOX3F)                                                                                \
       ABX_LAUNCH_TAGGED("nearestKernel<" #KCAP ",box>", (nearestKernel<KCAP, 2, false>), grid, kThreads, 0, s,         \
                         t->nodes, t->leaf_box, t->leaf_tri, n, t->kind, pts, q, qperm, k, row_stride, k_per_query,     \
-                        offsets, counts, indices, distances, SCRATCH);                                                 \
+                        offsets, counts, indices, distances, SCRATCH, missing);                                                 \
     else                                                                                                               \
       ABX_LAUNCH_TAGGED("nearestKernel<" #KCAP ">", (nearestKernel<KCAP, 1, false>), grid, kThreads, 0, s, t->nodes,   \
                         t->leaf_box, t->leaf_tri, n, t->kind, pts, q, qperm, k, row_stride, k_per_query, offsets,      \
-                        counts, indices, distances, SCRATCH);                                                          \
+                        counts, indices, distances, SCRATCH, missing);                                                          \
   } while (0)
   if (kmax <= 16)
   {
@@ -689,6 +671,178 @@ abx_status halfTraversalPairs(cudaStream_t s, abx_bvh *t, float r, uint32_t *pai
   }
   ABX_LAUNCH(halfPairsKernel, divUp(t->n, kThreads), kThreads, 0, s, t->nodes, t->leaf_box, (int)t->n, r, pairs,
              (unsigned long long)capacity, count_dev);
+  return ABX_OK;
+}
+
+// DistributedTree: merge the CRS rows of local results (indices) and of remote results
+// ((index, rank) pairs) into one CRS of (index, rank) pairs (countResults + sort by query id,
+// distributed/detail/ArborX_DistributedTreeUtils.hpp:229-263, without a sort: both inputs are
+// already grouped by query)
+__global__ void mergeCountsKernel(int64_t q, int32_t const *__restrict__ local_off,
+                                  int32_t const *__restrict__ remote_off, int32_t *__restrict__ counts)
+{
+  int64_t const i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < q)
+    counts[i] = (local_off[i + 1] - local_off[i]) + (remote_off[i + 1] - remote_off[i]);
+}
+__global__ void mergeRowsKernel(int64_t q, int32_t const *__restrict__ local_off, int32_t const *__restrict__ local_idx,
+                                int rank, int32_t const *__restrict__ remote_off,
+                                int2 const *__restrict__ remote_vals, int32_t const *__restrict__ out_off,
+                                int2 *__restrict__ out_vals)
+{
+  int64_t const i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= q)
+    return;
+  int dst = out_off[i];
+  for (int j = local_off[i]; j < local_off[i + 1]; ++j)
+    out_vals[dst++] = make_int2(local_idx[j], rank);
+  for (int j = remote_off[i]; j < remote_off[i + 1]; ++j)
+    out_vals[dst++] = remote_vals[j];
+}
+
+// DistributedTree routing: which OTHER ranks' boxes may satisfy each predicate.  The test is
+// conservative for spheres (a rank that receives a predicate it has nothing for returns
+// nothing), exact comparisons for boxes / points.  Two passes: per-destination counts, then the
+// query ids grouped by destination (the send buffer order of the all-to-all-v).
+template <int PRED, bool FILL>
+__global__ void __launch_bounds__(256)
+    routeKernel(float const *__restrict__ preds, int64_t q, float const *__restrict__ boxes6, int R, int self_rank,
+                unsigned *__restrict__ counts /*[R]*/, unsigned const *__restrict__ base /*[R]*/,
+                unsigned *__restrict__ cursors /*[R]*/, int32_t *__restrict__ out_qid)
+{
+  __shared__ float sbox[64 * 6];
+  __shared__ unsigned scount[64];
+  for (int i = threadIdx.x; i < R * 6; i += blockDim.x)
+    sbox[i] = boxes6[i];
+  if (threadIdx.x < 64)
+    scount[threadIdx.x] = 0;
+  __syncthreads();
+  int64_t const i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < q)
+  {
+    float c[3], r2 = 0.f, hi3[3];
+    if (PRED == ABX_PRED_SPHERE3F)
+    {
+      c[0] = preds[4 * i], c[1] = preds[4 * i + 1], c[2] = preds[4 * i + 2];
+      float const r = preds[4 * i + 3];
+      r2 = r * r * 1.0001f + 1e-30f;
+    }
+    else if (PRED == ABX_PRED_BOX3F)
+    {
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+      {
+        c[d] = preds[6 * i + d];
+        hi3[d] = preds[6 * i + 3 + d];
+      }
+    }
+    else
+      c[0] = preds[3 * i], c[1] = preds[3 * i + 1], c[2] = preds[3 * i + 2];
+    for (int rk = 0; rk < R; ++rk)
+    {
+      if (rk == self_rank)
+        continue;
+      float const *b = sbox + 6 * rk;
+      if (b[0] > b[3] || b[1] > b[4] || b[2] > b[5])
+        continue; // rank without primitives
+      bool hit;
+      if (PRED == ABX_PRED_BOX3F)
+        hit = !(c[0] > b[3] || hi3[0] < b[0] || c[1] > b[4] || hi3[1] < b[1] || c[2] > b[5] || hi3[2] < b[2]);
+      else
+      {
+        float d2 = 0.f;
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+        {
+          float const p = fminf(fmaxf(c[d], b[d]), b[3 + d]) - c[d];
+          d2 += p * p;
+        }
+        hit = PRED == ABX_PRED_SPHERE3F ? (d2 <= r2 || !(r2 < __int_as_float(0x7f800000))) : (d2 == 0.f);
+      }
+      if (hit)
+      {
+        if (FILL)
+          out_qid[base[rk] + atomicAdd(&cursors[rk], 1u)] = (int32_t)i;
+        else
+          atomicAdd(&scount[rk], 1u);
+      }
+    }
+  }
+  if (!FILL)
+  {
+    __syncthreads();
+    if (threadIdx.x < R && scount[threadIdx.x])
+      atomicAdd(&counts[threadIdx.x], scount[threadIdx.x]);
+  }
+}
+
+abx_status routeLaunch(cudaStream_t s, bool fill, int pred_kind, void const *preds, int64_t q, float const *boxes6,
+                       int R, int self_rank, unsigned *counts, unsigned const *base, unsigned *cursors, int32_t *out_qid)
+{
+  if (R > 64)
+  {
+    setError("route: at most 64 ranks");
+    return ABX_ERR_ARG;
+  }
+  if (q <= 0)
+    return ABX_OK;
+  int const grid = divUp(q, 256);
+#define ABX_ROUTE(P)                                                                                                  \
+  do                                                                                                                   \
+  {                                                                                                                    \
+    if (fill)                                                                                                          \
+      ABX_LAUNCH_TAGGED("routeKernel<fill>", (routeKernel<P, true>), grid, 256, 0, s, (float const *)preds, q,         \
+                        boxes6, R, self_rank, counts, base, cursors, out_qid);                                         \
+    else                                                                                                               \
+      ABX_LAUNCH_TAGGED("routeKernel<count>", (routeKernel<P, false>), grid, 256, 0, s, (float const *)preds, q,       \
+                        boxes6, R, self_rank, counts, base, cursors, out_qid);                                         \
+  } while (0)
+  switch (pred_kind)
+  {
+  case ABX_PRED_SPHERE3F: ABX_ROUTE(ABX_PRED_SPHERE3F); break;
+  case ABX_PRED_BOX3F: ABX_ROUTE(ABX_PRED_BOX3F); break;
+  case ABX_PRED_POINT3F: ABX_ROUTE(ABX_PRED_POINT3F); break;
+  default: setError("unknown predicate kind"); return ABX_ERR_ARG;
+  }
+#undef ABX_ROUTE
+  return ABX_OK;
+}
+
+// values2[i] = (indices[i], rank)
+__global__ void pairWithRankKernel(int32_t const *__restrict__ indices, int64_t n, int rank, int2 *__restrict__ out)
+{
+  int64_t const i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    out[i] = make_int2(indices[i], rank);
+}
+abx_status pairWithRank(cudaStream_t s, int32_t const *indices, int64_t n, int rank, int32_t *out2)
+{
+  if (n > 0)
+    ABX_LAUNCH(pairWithRankKernel, divUp(n, 256), 256, 0, s, indices, n, rank, (int2 *)out2);
+  return ABX_OK;
+}
+
+abx_status mergeCrs(cudaStream_t s, int64_t q, int32_t const *local_off, int32_t const *local_idx, int rank,
+                    int32_t const *remote_off, int32_t const *remote_vals2, int32_t *out_off, int32_t *out_vals2)
+{
+  if (q < 0)
+    return ABX_OK;
+  if (q > 0)
+    ABX_LAUNCH(mergeCountsKernel, divUp(q, 256), 256, 0, s, q, local_off, remote_off, out_off);
+  ABX_TRY(exclusiveScanI32(s, out_off, out_off, q + 1));
+  if (q > 0)
+    ABX_LAUNCH(mergeRowsKernel, divUp(q, 256), 256, 0, s, q, local_off, local_idx, rank, remote_off,
+               (int2 const *)remote_vals2, out_off, (int2 *)out_vals2);
+  return ABX_OK;
+}
+
+abx_status compactRows(cudaStream_t s, int64_t q, int32_t const *old_offsets, int32_t const *new_offsets,
+                       uint32_t const *old_idx, float const *old_dist, uint32_t *new_idx, float *new_dist)
+{
+  if (q <= 0)
+    return ABX_OK;
+  ABX_LAUNCH(compactRowsKernel, divUp(q, 256), 256, 0, s, q, old_offsets, new_offsets, old_idx, old_dist, new_idx,
+             new_dist);
   return ABX_OK;
 }
 

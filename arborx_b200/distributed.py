@@ -50,6 +50,90 @@ class CudaEngine:
         idx, off, d = tree.query(self.space, self.abx.nearest(pts, int(k)), return_distances=True)
         return idx, off, d
 
+    def route(self, kind, data, rank_boxes, rank):
+        """-> (query ids grouped by destination rank [F] int64, send_counts list[R]); self is never a destination."""
+        import ctypes as C
+        from . import _lib
+        L = _lib.lib()
+        dev = data.device
+        R = rank_boxes.shape[0]
+        q = data.shape[0]
+        boxes = rank_boxes.to(device=dev, dtype=torch.float32).contiguous()
+        counts = torch.empty(R, dtype=torch.int32, device=dev)
+        d = data.contiguous()
+        with torch.cuda.stream(self.space.stream):
+            _lib.check(L.abx_dist_route_count(self.space.handle, kind, C.c_void_p(d.data_ptr()), q,
+                                              C.c_void_p(boxes.data_ptr()), R, int(rank), C.c_void_p(counts.data_ptr())))
+            send_counts = counts.tolist()
+            total = sum(send_counts)
+            qids = torch.empty(total, dtype=torch.int32, device=dev)
+            if total:
+                base = torch.tensor([sum(send_counts[:i]) for i in range(R)], dtype=torch.int32, device=dev)
+                cursors = torch.empty(R, dtype=torch.int32, device=dev)
+                _lib.check(L.abx_dist_route_fill(self.space.handle, kind, C.c_void_p(d.data_ptr()), q,
+                                                 C.c_void_p(boxes.data_ptr()), R, int(rank), C.c_void_p(base.data_ptr()),
+                                                 C.c_void_p(cursors.data_ptr()), C.c_void_p(qids.data_ptr())))
+        return qids.long(), send_counts
+
+    def pair_with_rank(self, idx, rank):
+        import ctypes as C
+        from . import _lib
+        i32 = idx.to(torch.int32).contiguous()
+        out = torch.empty((i32.shape[0], 2), dtype=torch.int32, device=i32.device)
+        with torch.cuda.stream(self.space.stream):
+            _lib.check(_lib.lib().abx_dist_pair_with_rank(self.space.handle, C.c_void_p(i32.data_ptr()), i32.shape[0],
+                                                          int(rank), C.c_void_p(out.data_ptr())))
+        return out
+
+    def merge_rows(self, local_off, local_idx, rank, remote_off, remote_vals):
+        """CRS rows of local results (index only) + CRS rows of remote results ((index, rank) pairs)
+        -> merged (values [nnz, 2], offsets [q + 1]); one kernel pass (abx_dist_merge_crs)."""
+        import ctypes as C
+        from . import _lib
+        q = local_off.shape[0] - 1
+        dev = local_off.device
+        nnz = int(local_idx.shape[0] + remote_vals.shape[0])
+        out_off = torch.empty(q + 1, dtype=torch.int32, device=dev)
+        out_vals = torch.empty((nnz, 2), dtype=torch.int32, device=dev)
+        lo = local_off.to(torch.int32).contiguous()
+        li = local_idx.to(torch.int32).contiguous()
+        ro = remote_off.to(torch.int32).contiguous()
+        rv = remote_vals.to(torch.int32).contiguous()
+        with torch.cuda.stream(self.space.stream):
+            _lib.check(_lib.lib().abx_dist_merge_crs(self.space.handle, q, C.c_void_p(lo.data_ptr()),
+                                                     C.c_void_p(li.data_ptr()), int(rank), C.c_void_p(ro.data_ptr()),
+                                                     C.c_void_p(rv.data_ptr()), C.c_void_p(out_off.data_ptr()),
+                                                     C.c_void_p(out_vals.data_ptr())))
+        return out_vals, out_off
+
+
+def route_generic(kind, data, rank_boxes, rank):
+    """Device-agnostic tensor version of CudaEngine.route (used by the CPU protocol tests)."""
+    dev = data.device
+    boxes = rank_boxes.to(dev)
+    R = boxes.shape[0]
+    parts = []
+    if kind == BOX_PRED:
+        qlo, qhi = data[:, 0:3], data[:, 3:6]
+    else:
+        c = data[:, 0:3]
+        if kind == SPHERE_PRED:
+            r = data[:, 3]
+            r2 = r * r * (1.0 + 1e-4) + 1e-30  # conservative against rounding
+    for rk in range(R):
+        lo, hi = boxes[rk, 0:3], boxes[rk, 3:6]
+        if rk == rank or bool((lo > hi).any()):
+            parts.append(torch.empty(0, dtype=torch.int64, device=dev))
+            continue
+        if kind == BOX_PRED:
+            hit = ~(((qlo > hi) | (qhi < lo)).any(1))
+        else:
+            d = torch.minimum(torch.maximum(c, lo), hi) - c
+            d2 = (d * d).sum(1)
+            hit = ((d2 <= r2) | torch.isinf(r2)) if kind == SPHERE_PRED else (d2 == 0)
+        parts.append(torch.nonzero(hit).flatten())
+    return torch.cat(parts), [int(p.shape[0]) for p in parts]
+
 
 def _alltoallv(comm, rows, send_counts):
     """rows [F, w] (32-bit words) ordered by destination rank, send_counts [R] (host list).
@@ -80,6 +164,7 @@ class DistributedTree:
             kind = {3: POINT, 6: BOX, 9: TRIANGLE}[values.shape[-1]]
         self.kind = kind
         self.device = values.device
+        self.force_generic = False  # tests flip this to exercise the reference-shaped exchange
         # bottom tree (ArborX_DistributedTree.hpp:183-186)
         self._bottom = self.engine.build(values, kind)
         n_local = int(self.engine.size(self._bottom))
@@ -115,13 +200,119 @@ class DistributedTree:
             # DistributedTreeSpatial.hpp:44-50
             out = (torch.empty((0, 2), dtype=torch.int32, device=dev), torch.zeros(q + 1, dtype=torch.int32, device=dev))
             return out + ((torch.empty(0, dtype=torch.float32, device=dev),) if return_distances else ())
+        fast = self.world <= 62 and not self.force_generic
         if predicates.tag == "spatial":
-            ranks, off = self.engine.spatial(self._top, predicates.kind, data)
-            vals, offsets, _ = self._forward_and_collect(data, ranks.long(), off.long(), ("spatial", predicates.kind))
+            if fast:
+                vals, offsets = self._spatial_fast(predicates.kind, data)
+            else:
+                ranks, off = self.engine.spatial(self._top, predicates.kind, data)
+                vals, offsets, _ = self._forward_and_collect(data, ranks.long(), off.long(),
+                                                             ("spatial", predicates.kind))
             return (vals, offsets) + ((torch.empty(0, dtype=torch.float32, device=dev),) if return_distances else ())
         k = int(predicates.k)
-        vals, offsets, d = self._nearest(data, k)
+        if fast and k >= 1 and int(self._sizes.min()) >= k:
+            vals, offsets, d = self._nearest_fast(data, k)
+        else:
+            vals, offsets, d = self._nearest(data, k)
         return (vals, offsets, d) if return_distances else (vals, offsets)
+
+    # ---- fast paths --------------------------------------------------------------------
+    # The reference forwards every query through the exchange, including the (vast majority
+    # of) queries that only concern the rank they live on.  Here the local tree is queried
+    # directly for all local queries, only the queries that also touch OTHER ranks' boxes are
+    # packed, exchanged and merged back, so the full-size arrays are touched by the tree
+    # kernels and one merge pass only.  Routing may be conservative (a rank that gets a query
+    # it has nothing for returns nothing), so it is a plain tensor test against the R boxes.
+    def _route(self, kind, data):
+        if hasattr(self.engine, "route"):
+            return self.engine.route(kind, data, self._rank_boxes, self.rank)
+        return route_generic(kind, data, self._rank_boxes, self.rank)
+
+    def _exchange_remote(self, data, qid_s, send_counts, what):
+        """Forward the predicates qid_s (grouped by destination), query there, bring the results back.
+        -> (query ids [M] (sorted), values [M, 2] (index, rank), distances [M] or None)"""
+        dev = data.device
+        R = self.world
+        rows = torch.cat([data[qid_s].contiguous().view(torch.int32), qid_s.to(torch.int32).unsqueeze(1)], 1)
+        fwd, recv_counts = _alltoallv(self.comm, rows, send_counts)
+        stride = data.shape[1]
+        fwd_preds = fwd[:, :stride].contiguous().view(torch.float32)
+        fwd_ids = fwd[:, stride]
+        if what[0] == "spatial":
+            idx, loff = self.engine.spatial(self._bottom, what[1], fwd_preds)
+            cols = [idx.to(torch.int32).unsqueeze(1)]
+        else:
+            idx, loff, d = self.engine.nearest(self._bottom, fwd_preds, what[1])
+            cols = [idx.to(torch.int32).unsqueeze(1), d.contiguous().view(torch.int32).unsqueeze(1)]
+        loff = loff.long()
+        res_ids = torch.repeat_interleave(fwd_ids, loff[1:] - loff[:-1])
+        back_rows = torch.cat(cols + [res_ids.unsqueeze(1)], 1)
+        seg = torch.cumsum(torch.tensor([0] + recv_counts, device=dev), 0)
+        back_counts = (loff[seg[1:]] - loff[seg[:-1]]).tolist()
+        got, got_counts = _alltoallv(self.comm, back_rows, back_counts)
+        src_rank = torch.repeat_interleave(torch.arange(R, device=dev, dtype=torch.int32),
+                                           torch.tensor(got_counts, device=dev))
+        ids = got[:, -1].long()
+        order = torch.argsort(ids, stable=True)
+        vals = torch.stack([got[:, 0][order], src_rank[order]], 1)
+        dists = got[:, 1][order].contiguous().view(torch.float32) if what[0] == "nearest" else None
+        return ids[order], vals, dists
+
+    def _spatial_fast(self, kind, data):
+        dev = data.device
+        q = data.shape[0]
+        qid_s, send_counts = self._route(kind, data)
+        idx_l, off_l = self.engine.spatial(self._bottom, kind, data)
+        ids, rvals, _ = self._exchange_remote(data, qid_s, send_counts, ("spatial", kind))
+        if ids.shape[0] == 0:
+            # nothing came back from other ranks: the local CRS is the answer
+            if hasattr(self.engine, "pair_with_rank"):
+                return self.engine.pair_with_rank(idx_l, self.rank), off_l.to(torch.int32)
+            return torch.stack([idx_l.to(torch.int32), torch.full_like(idx_l, self.rank, dtype=torch.int32)], 1), \
+                off_l.to(torch.int32)
+        roff = torch.zeros(q + 1, dtype=torch.int64, device=dev)
+        roff[1:] = torch.cumsum(torch.bincount(ids, minlength=q), 0)
+        return self.engine.merge_rows(off_l, idx_l, self.rank, roff, rvals)
+
+    def _nearest_fast(self, pts, k):
+        """Every rank holds >= k primitives: the local k-th distance bounds the true one (phase I
+        without an exchange), ranks within that distance are asked for their k nearest (phase II),
+        and only the queries that received remote candidates are re-ranked."""
+        dev = pts.device
+        q = pts.shape[0]
+        idx_l, off_l, d_l = self.engine.nearest(self._bottom, pts, k)
+        if idx_l.shape[0] != q * k:
+            return self._nearest(pts, k)  # short local rows (unreachable leaves): generic path
+        bound = d_l.view(q, k)[:, k - 1]
+        spheres = torch.cat([pts, bound.unsqueeze(1)], 1)
+        qid_s, send_counts = self._route(SPHERE_PRED, spheres)
+        ids, rvals, rd = self._exchange_remote(pts, qid_s, send_counts, ("nearest", k))
+        if hasattr(self.engine, "pair_with_rank"):
+            vals = self.engine.pair_with_rank(idx_l, self.rank)
+        else:
+            vals = torch.stack([idx_l.to(torch.int32), torch.full_like(idx_l, self.rank, dtype=torch.int32)], 1)
+        out_d = d_l
+        if ids.shape[0]:
+            # queries with remote candidates: k local + m remote, keep the k smallest
+            uq, inv = torch.unique(ids, return_inverse=True)
+            cnt = torch.bincount(inv, minlength=uq.shape[0])
+            m = int(cnt.max())
+            start = torch.cumsum(cnt, 0) - cnt
+            pos = torch.arange(ids.shape[0], device=dev) - start[inv]
+            u = uq.shape[0]
+            cd = torch.full((u, k + m), float("inf"), dtype=torch.float32, device=dev)
+            cv = torch.zeros((u, k + m, 2), dtype=torch.int32, device=dev)
+            rows = (uq.unsqueeze(1) * k + torch.arange(k, device=dev)).view(-1)  # local rows of the affected queries
+            cd[:, :k] = out_d[rows].view(u, k)
+            cv[:, :k] = vals[rows].view(u, k, 2)
+            cd[inv, k + pos] = rd
+            cv[inv, k + pos] = rvals
+            sd, so = torch.sort(cd, dim=1, stable=True)
+            so = so[:, :k]
+            out_d[rows] = sd[:, :k].reshape(-1)
+            vals[rows] = torch.gather(cv, 1, so.unsqueeze(2).expand(u, k, 2)).reshape(-1, 2)
+        offsets = torch.arange(q + 1, device=dev, dtype=torch.int32) * k
+        return vals, offsets, out_d
 
     # forwardQueries + bottom query + communicateResultsBack + sort by query id
     # (DistributedTreeUtils.hpp:229-263).  ranks/off: CRS of destination ranks per local query.

@@ -34,6 +34,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout must carry exactly one JSON line: keep NCCL's version banner out of it
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 METRIC = "BVH build Mprims/s; radius & kNN(k=10) Mqueries/s at 10M pts; % HBM roofline"
 UNIT = "Mitems/s (n prims + q radius queries + q kNN queries per step second)"
@@ -421,6 +423,53 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_dbscan(args):
+    """Secondary workload (BASELINE.json configs[2]): ArborX::dbscan on a GanTao clustered cloud,
+    eps = 200, minpts in {2, 5}, FDBSCAN and FDBSCAN-DenseBox.  One JSON line; `value` = points/s of
+    the reference's default configuration (FDBSCAN-DenseBox, minpts = 5)."""
+    import torch
+
+    import arborx_b200 as abx
+    import oracle
+    from tests import clouds
+    n = args.n
+    eps = 200.0
+    pts = clouds.gan_tao(3, n)
+    space = abx.ExecutionSpace()
+    d = torch.from_numpy(pts).cuda()
+    res = {}
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    for impl, iname in ((1, "densebox"), (0, "fdbscan")):
+        for minpts in (5, 2):
+            params = abx.DBSCANParameters(impl, 0)
+            for _ in range(max(1, args.warmup)):
+                labels = abx.dbscan(space, d, eps, minpts, params)
+            torch.cuda.synchronize()
+            e0, e1 = ev(), ev()
+            e0.record()
+            for _ in range(args.steps):
+                labels = abx.dbscan(space, d, eps, minpts, params)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / args.steps
+            lab = labels.cpu().numpy()
+            res["%s_minpts%d" % (iname, minpts)] = {"ms": ms, "Mpoints_s": n / ms / 1e3,
+                                                   "clusters": int(len(np.unique(lab[lab >= 0]))),
+                                                   "noise": int((lab < 0).sum())}
+    ns = min(n, args.cpu_sample * 2)
+    t0 = time.time()
+    ref = oracle.dbscan(pts[:ns], eps, 5, 1, 0)
+    t_cpu = time.time() - t0
+    line = {"metric": "DBSCAN Mpoints/s (GanTao clustered 3-D, eps=200)", "value": res["densebox_minpts5"]["Mpoints_s"],
+            "unit": "Mpoints/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": res["densebox_minpts5"]["ms"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "dbscan GanTao n=%d eps=200 (BASELINE.json configs[2])" % n}, "components": res,
+            "cpu_baseline": {"value": ns / t_cpu / 1e6, "unit": "Mpoints/s", "cores": oracle.num_threads(),
+                             "kind": "port", "sample": "oracle FDBSCAN-DenseBox minpts=5 on the first %d points" % ns}}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -431,10 +480,14 @@ def main():
     ap.add_argument("--q", type=int, default=None)
     ap.add_argument("--cpu-sample", type=int, default=500_000, help="queries timed on the CPU baseline")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--workload", default="bvh", choices=["bvh", "dbscan"],
+                    help="bvh: the headline bvh_driver step (default); dbscan: secondary DBSCAN workload")
     args = ap.parse_args()
     if args.q is None:
         args.q = args.n
-    if args.impl == "reference":
+    if args.workload == "dbscan":
+        run_dbscan(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -170,6 +170,30 @@ ABX_API abx_status abx_dbscan(void *stream, const float *xyz_dev, int64_t n, flo
 ABX_API abx_status abx_dbscan_host(void *stream, const float *xyz_host, int64_t n, float eps, int32_t minpts,
                            int implementation, int algorithm, int32_t *labels_host);
 
+/* ---- DistributedTree building block (distributed/detail/ArborX_DistributedTreeUtils.hpp:229-263) ----
+ * Merges, per query, the CRS rows of the local tree's results (indices) with the CRS rows of the
+ * results that came back from other ranks ((index, rank) pairs, grouped by query) into one CRS
+ * of (index, rank) pairs: out_offsets[q+1], out_values2[2 * (nnz_local + nnz_remote)].  The
+ * exchange itself (all-to-all-v over NCCL) is driven by the host side, arborx_b200/distributed.py. */
+ABX_API abx_status abx_dist_merge_crs(void *stream, int64_t q, const int32_t *local_offsets_dev,
+                                      const int32_t *local_indices_dev, int32_t rank,
+                                      const int32_t *remote_offsets_dev, const int32_t *remote_values2_dev,
+                                      int32_t *out_offsets_dev, int32_t *out_values2_dev);
+
+/* Routing of forwarded predicates (the top-tree query of DistributedTreeSpatial.hpp:52-55 for R <= 64
+ * ranks, evaluated directly against the R rank boxes; conservative for spheres).  Pass 1 counts the
+ * predicates that must be forwarded to every OTHER rank; pass 2 writes their query ids grouped by
+ * destination (base = exclusive scan of the counts), i.e. the send order of the all-to-all-v. */
+ABX_API abx_status abx_dist_route_count(void *stream, int pred_kind, const void *preds_dev, int64_t q,
+                                        const float *rank_boxes6_dev, int32_t n_ranks, int32_t self_rank,
+                                        uint32_t *counts_dev);
+ABX_API abx_status abx_dist_route_fill(void *stream, int pred_kind, const void *preds_dev, int64_t q,
+                                       const float *rank_boxes6_dev, int32_t n_ranks, int32_t self_rank,
+                                       const uint32_t *base_dev, uint32_t *cursors_dev, int32_t *query_ids_dev);
+/* values2[i] = (indices[i], rank): local results in the (index, rank) form DistributedTree returns */
+ABX_API abx_status abx_dist_pair_with_rank(void *stream, const int32_t *indices_dev, int64_t n, int32_t rank,
+                                           int32_t *values2_dev);
+
 /* ---- stage-level entry points (tests localise mismatches with these) ---- */
 /* TreeConstruction::calculateBoundingBoxOfTheScene (detail/ArborX_TreeConstruction.hpp:27-39) */
 ABX_API abx_status abx_scene_bounds(void *stream, int prim_kind, const void *prims_dev, int64_t n, float *bounds6_dev);

@@ -52,3 +52,55 @@ def clustered(seed, n, n_clusters=10, domain=1.0e6, spread=100.0, noise_frac=1e-
     if n_noise:
         pts[:n_noise] = uniform01(seed, n_noise, 3) * F(domain)
     return np.clip(pts, 0, domain).astype(F)
+
+
+def _normals(seed, n, dims=3):
+    """[n, dims] standard normals (Box-Muller on the counter hash)."""
+    u1 = np.maximum(uniform01(seed, n, dims).astype(np.float64), 1e-12)
+    u2 = uniform01(seed + 7919, n, dims).astype(np.float64)
+    return np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)
+
+
+def gan_tao(seed, n, variable_density=False, num_clusters=10, c_reset=100, rho_noise=1e-4, L=1.0e6):
+    """Vectorised restatement of the GanTao seed spreader of the reference's DBSCAN benchmark
+    (benchmarks/cluster/data_timpl.hpp:253-335): a seed random-walks through [0, L]^3 (step r_shift
+    every c_reset points, restart at a random location with probability (num_clusters-1)/n per point)
+    and scatters points uniformly in the ball of radius r_vicinity around itself; a fraction rho_noise
+    of uniform noise is appended.  3-D constants: r_vicinity = 100 (x (restart % 10 + 1) with
+    variable_density), r_shift = 1.5 r_vicinity.  The reference's std::default_random_engine streams are
+    implementation-defined, so the counter-based hash of this module is used instead; parity only needs
+    identical bytes on the CPU and GPU sides."""
+    n_wo = n - int(n * rho_noise)
+    rho_restart = (num_clusters - 1) / max(n_wo, 1)
+    restart_after = uniform01(seed, n_wo, 1)[:, 0].astype(np.float64) < rho_restart
+    start = np.zeros(n_wo, bool)
+    start[0] = True
+    start[1:] = restart_after[:-1]
+    cid = np.cumsum(start) - 1
+    first = np.nonzero(start)[0]
+    j = np.arange(n_wo) - first[cid]
+    new_seg = start | (j % c_reset == 0)
+    seg = np.cumsum(new_seg) - 1
+    seg_first = np.nonzero(new_seg)[0]
+    n_seg = len(seg_first)
+    seg_cluster = cid[seg_first]
+    seg_is_cluster_first = start[seg_first]
+    dens = (seg_cluster % 10 + 1) if variable_density else np.ones(n_seg, np.int64)
+    r_vic_seg = 100.0 * dens
+    r_shift_seg = 1.5 * r_vic_seg
+    d = _normals(seed + 11, n_seg)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    shift = d * r_shift_seg[:, None]
+    shift[seg_is_cluster_first] = 0.0
+    pos = np.cumsum(shift, 0)
+    n_clu = int(cid[-1]) + 1
+    origin_c = uniform01(seed + 13, n_clu, 3).astype(np.float64) * L
+    clu_first_seg = np.nonzero(seg_is_cluster_first)[0]
+    offset_c = origin_c - pos[clu_first_seg]
+    origin_seg = pos + offset_c[seg_cluster]
+    b = _normals(seed + 17, n_wo)
+    b /= np.linalg.norm(b, axis=1, keepdims=True)
+    rad = np.cbrt(uniform01(seed + 19, n_wo, 1).astype(np.float64)) * r_vic_seg[seg][:, None]
+    pts = origin_seg[seg] + b * rad
+    noise = uniform01(seed + 23, n - n_wo, 3).astype(np.float64) * L
+    return np.concatenate([pts, noise]).astype(F)

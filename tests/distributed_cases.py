@@ -37,6 +37,22 @@ class OracleEngine:
         return torch.from_numpy(idx.astype(np.int32)), torch.from_numpy(off), torch.from_numpy(d)
 
 
+    def merge_rows(self, local_off, local_idx, rank, remote_off, remote_vals):
+        lo, li = local_off.cpu().numpy().astype(np.int64), local_idx.cpu().numpy()
+        ro, rv = remote_off.cpu().numpy().astype(np.int64), remote_vals.cpu().numpy().reshape(-1, 2)
+        q = len(lo) - 1
+        off = np.zeros(q + 1, np.int64)
+        off[1:] = np.cumsum((lo[1:] - lo[:-1]) + (ro[1:] - ro[:-1]))
+        vals = np.zeros((off[-1], 2), np.int32)
+        for i in range(q):
+            a = off[i]
+            nl = lo[i + 1] - lo[i]
+            vals[a:a + nl, 0] = li[lo[i]:lo[i + 1]]
+            vals[a:a + nl, 1] = rank
+            vals[a + nl:off[i + 1]] = rv[ro[i]:ro[i + 1]]
+        return torch.from_numpy(vals), torch.from_numpy(off.astype(np.int32))
+
+
 class _Pred:
     def __init__(self, tag, kind, data, k=None):
         self.tag, self.kind, self.data, self.k = tag, kind, data, k
@@ -49,6 +65,22 @@ def rows(vals, off):
 
 
 def run_all(make_engine, device, space=None):
+    """Runs every case twice: through the fast paths (local-first, remote-only exchange) and through the
+    reference-shaped generic exchange (every query forwarded, incl. to its own rank)."""
+    orig = D.DistributedTree.__init__
+    for generic in (False, True):
+        def patched(self, *a, **k):
+            orig(self, *a, **k)
+            self.force_generic = generic
+        D.DistributedTree.__init__ = patched
+        try:
+            _run_all(make_engine, device, space)
+        finally:
+            D.DistributedTree.__init__ = orig
+    return True
+
+
+def _run_all(make_engine, device, space=None):
     rank, size = dist.get_rank(), dist.get_world_size()
     comm = dist.group.WORLD
     T = lambda a: torch.as_tensor(np.asarray(a, F)).to(device)

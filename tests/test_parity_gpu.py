@@ -324,3 +324,22 @@ def test_host_buffer_entry_points(cuda, orc):
     check_knn_vs_oracle((off.numpy(), idx.numpy().view(np.uint32), dist.numpy()), to.nearest_crs(spheres[:, :3], 5))
     labels = abx.dbscan(space, torch.from_numpy(pts), 0.02, 4, abx.DBSCANParameters(0, 0))
     dbscan_checks.check_against_oracle(pts, 0.02, 4, labels.numpy(), 0, 0, verify=False)
+
+
+def test_nearest_short_rows_for_unreachable_leaves(cuda, orc):
+    # an "empty" box (ArborX_Box.hpp:35-44) is at infinite distance from everything: it is never
+    # accepted (distance < radius fails), so rows come out shorter than min(k, n) and are compacted
+    # (DistributedTree's top tree holds such boxes for ranks without primitives)
+    fm = np.finfo(F).max
+    boxes = np.array([[0, 0, 0, 1, 1, 1], [fm, fm, fm, -fm, -fm, -fm], [2, 2, 2, 3, 3, 3],
+                      [fm, fm, fm, -fm, -fm, -fm]], F)
+    qp = np.array([[0.5, 0.5, 0.5], [2.5, 2.5, 2.9], [9, 9, 9]], F)
+    tc, to = cuda.build(boxes, PRIM_BOX), orc.build(boxes, PRIM_BOX)
+    for k in (1, 2, 3, 4, 40):
+        oc, ic, dc = tc.nearest_crs(qp, k)
+        oo, io, do = to.nearest_crs(qp, k)
+        assert np.array_equal(oc, oo) and np.array_equal(ic, io) and np.array_equal(dc, do), k
+    ks = np.array([4, 0, 2], np.int32)
+    oc, ic, dc = tc.nearest_crs(qp, ks)
+    oo, io, do = to.nearest_crs(qp, ks)
+    assert np.array_equal(oc, oo) and np.array_equal(ic, io) and np.array_equal(dc, do)
