@@ -16,9 +16,9 @@ from . import _lib
 from ._lib import SearchException, lib
 
 POINT, BOX, TRIANGLE = 0, 1, 2            # primitive kinds (ABX_PRIM_*)
-SPHERE_PRED, BOX_PRED, POINT_PRED = 0, 1, 2  # predicate geometries (ABX_PRED_*)
+SPHERE_PRED, BOX_PRED, POINT_PRED, RAY_PRED = 0, 1, 2, 3  # predicate geometries (ABX_PRED_*)
 _PRIM_STRIDE = {POINT: 3, BOX: 6, TRIANGLE: 9}
-_PRED_STRIDE = {SPHERE_PRED: 4, BOX_PRED: 6, POINT_PRED: 3}
+_PRED_STRIDE = {SPHERE_PRED: 4, BOX_PRED: 6, POINT_PRED: 3, RAY_PRED: 6}
 
 __all__ = ["ExecutionSpace", "BoundingVolumeHierarchy", "BVH", "TraversalPolicy", "intersects", "nearest",
            "make_intersects", "make_nearest", "query", "dbscan", "DBSCANParameters", "SearchException",
@@ -81,8 +81,9 @@ def _as_f32(t, stride):
 
 
 def intersects(geometry, kind=None):
-    """intersects(Sphere|Box|Point) for a batch (detail/ArborX_Predicates.hpp:130-147):
-    [q,4] spheres (centre, radius), [q,6] boxes or [q,3] points."""
+    """intersects(Sphere|Box|Point|Ray) for a batch (detail/ArborX_Predicates.hpp:130-147):
+    [q,4] spheres (centre, radius), [q,6] boxes or [q,3] points; rays ([q,6] origin, direction,
+    geometry/ArborX_Ray.hpp) need kind=RAY_PRED."""
     if not isinstance(geometry, torch.Tensor):
         geometry = torch.as_tensor(geometry, dtype=torch.float32)
     if kind is None:

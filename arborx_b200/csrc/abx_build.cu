@@ -192,6 +192,13 @@ __global__ void __launch_bounds__(kThreads) morton32Kernel(float const *__restri
     for (int d = 0; d < 3; ++d)
       c[d] = __fdiv_rn(__fadd_rn(preds[6 * i + d], preds[6 * i + 3 + d]), 2.f);
   }
+  else if (PRED == ABX_PRED_RAY3F)
+  {
+    // returnCentroid(ray) = origin (geometry/ArborX_Ray.hpp)
+    c[0] = preds[6 * i];
+    c[1] = preds[6 * i + 1];
+    c[2] = preds[6 * i + 2];
+  }
   else
   {
     c[0] = preds[3 * i];
@@ -831,6 +838,9 @@ abx_status morton32(cudaStream_t s, int pred_kind, void const *preds, int64_t q,
     break;
   case ABX_PRED_POINT3F:
     ABX_LAUNCH((morton32Kernel<ABX_PRED_POINT3F>), grid, kThreads, 0, s, (float const *)preds, q, bounds6, codes);
+    break;
+  case ABX_PRED_RAY3F:
+    ABX_LAUNCH((morton32Kernel<ABX_PRED_RAY3F>), grid, kThreads, 0, s, (float const *)preds, q, bounds6, codes);
     break;
   default:
     setError("unknown predicate kind");

@@ -28,6 +28,7 @@ struct ProfileRecord
 };
 std::vector<ProfileRecord> g_records;
 std::vector<cudaEvent_t> g_event_pool;
+std::mutex g_profile_mutex;
 cudaEvent_t takeEvent()
 {
   if (!g_event_pool.empty())
@@ -41,13 +42,20 @@ cudaEvent_t takeEvent()
   return e;
 }
 } // namespace
-void profileBegin(char const *name, cudaStream_t s)
+int profileBegin(char const *name, cudaStream_t s)
 {
+  std::lock_guard<std::mutex> lock(g_profile_mutex);
   ProfileRecord r{name, takeEvent(), takeEvent()};
   cudaEventRecord(r.start, s);
   g_records.push_back(r);
+  return (int)g_records.size() - 1;
 }
-void profileEnd(cudaStream_t s) { cudaEventRecord(g_records.back().stop, s); }
+void profileEnd(int handle, cudaStream_t s)
+{
+  std::lock_guard<std::mutex> lock(g_profile_mutex);
+  if (handle >= 0 && handle < (int)g_records.size())
+    cudaEventRecord(g_records[handle].stop, s);
+}
 
 static abx_status ensureDevice()
 {
@@ -162,7 +170,10 @@ static abx_policy defaultPolicy()
   return p;
 }
 
-static int predStride(int kind) { return kind == ABX_PRED_SPHERE3F ? 4 : kind == ABX_PRED_BOX3F ? 6 : 3; }
+static int predStride(int kind)
+{
+  return kind == ABX_PRED_SPHERE3F ? 4 : (kind == ABX_PRED_BOX3F || kind == ABX_PRED_RAY3F) ? 6 : 3;
+}
 static int primStride(int kind) { return kind == ABX_PRIM_POINT3F ? 3 : kind == ABX_PRIM_BOX3F ? 6 : 9; }
 
 // output buffer from the caller's allocator or from the stream-ordered pool
@@ -423,6 +434,7 @@ abx_status abx_profile_enable(int on)
 {
   ABX_TRY(ensureDevice());
   cudaDeviceSynchronize();
+  std::lock_guard<std::mutex> lock(g_profile_mutex);
   for (auto &r : g_records)
   {
     g_event_pool.push_back(r.start);
@@ -438,6 +450,7 @@ abx_status abx_profile_enable(int on)
 int64_t abx_profile_report(char *buf, int64_t capacity)
 {
   cudaDeviceSynchronize();
+  std::lock_guard<std::mutex> lock(g_profile_mutex);
   struct Agg
   {
     std::string name;
@@ -641,7 +654,7 @@ abx_status abx_query_spatial_crs_host(abx_bvh *bvh, void *stream, int pred_kind,
     setError("null argument");
     return ABX_ERR_ARG;
   }
-  if (pred_kind < 0 || pred_kind > ABX_PRED_POINT3F || q < 0)
+  if (pred_kind < 0 || pred_kind > ABX_PRED_RAY3F || q < 0)
   {
     setError("bad predicate kind or count");
     return ABX_ERR_ARG;
@@ -792,25 +805,26 @@ abx_status abx_dist_merge_crs(void *stream, int64_t q, const int32_t *local_offs
                   remote_values2_dev, out_offsets_dev, out_values2_dev);
 }
 
-abx_status abx_dist_route_count(void *stream, int pred_kind, const void *preds_dev, int64_t q, const float *rank_boxes6_dev,
-                                int32_t n_ranks, int32_t self_rank, uint32_t *counts_dev)
+abx_status abx_dist_route_count(void *stream, int pred_kind, const void *preds_dev, int64_t q, const float *radius_dev,
+                                int64_t radius_stride, const float *rank_boxes6_dev, int32_t n_ranks, int32_t self_rank,
+                                uint32_t *counts_dev)
 {
   ABX_TRY(ensureDevice());
   cudaStream_t s = (cudaStream_t)stream;
   ABX_CUDA_TRY(cudaMemsetAsync(counts_dev, 0, sizeof(uint32_t) * (size_t)n_ranks, s));
-  return routeLaunch(s, false, pred_kind, preds_dev, q, rank_boxes6_dev, n_ranks, self_rank, counts_dev, nullptr, nullptr,
-                     nullptr);
+  return routeLaunch(s, false, pred_kind, preds_dev, q, radius_dev, radius_stride, rank_boxes6_dev, n_ranks, self_rank,
+                     counts_dev, nullptr, nullptr, nullptr);
 }
 
-abx_status abx_dist_route_fill(void *stream, int pred_kind, const void *preds_dev, int64_t q, const float *rank_boxes6_dev,
-                               int32_t n_ranks, int32_t self_rank, const uint32_t *base_dev, uint32_t *cursors_dev,
-                               int32_t *query_ids_dev)
+abx_status abx_dist_route_fill(void *stream, int pred_kind, const void *preds_dev, int64_t q, const float *radius_dev,
+                               int64_t radius_stride, const float *rank_boxes6_dev, int32_t n_ranks, int32_t self_rank,
+                               const uint32_t *base_dev, uint32_t *cursors_dev, int32_t *query_ids_dev)
 {
   ABX_TRY(ensureDevice());
   cudaStream_t s = (cudaStream_t)stream;
   ABX_CUDA_TRY(cudaMemsetAsync(cursors_dev, 0, sizeof(uint32_t) * (size_t)n_ranks, s));
-  return routeLaunch(s, true, pred_kind, preds_dev, q, rank_boxes6_dev, n_ranks, self_rank, nullptr, base_dev, cursors_dev,
-                     query_ids_dev);
+  return routeLaunch(s, true, pred_kind, preds_dev, q, radius_dev, radius_stride, rank_boxes6_dev, n_ranks, self_rank,
+                     nullptr, base_dev, cursors_dev, query_ids_dev);
 }
 
 abx_status abx_dist_pair_with_rank(void *stream, const int32_t *indices_dev, int64_t n, int32_t rank,

@@ -45,19 +45,18 @@ extern int64_t g_launch_count;
 // per-kernel device timing (abx_profile_enable / abx_profile_report): CUDA events on
 // the launching stream around every launch, aggregated by kernel name
 extern bool g_profile;
-void profileBegin(char const *name, cudaStream_t s);
-void profileEnd(cudaStream_t s);
+int profileBegin(char const *name, cudaStream_t s); // returns a record handle (thread-safe)
+void profileEnd(int handle, cudaStream_t s);
 
 // every kernel launch goes through this so that launches are counted, checked and
 // (optionally) timed
 #define ABX_LAUNCH_TAGGED(tag, kernel, grid, block, smem, stream, ...)                                                \
   do                                                                                                                   \
   {                                                                                                                    \
-    if (::abx::g_profile)                                                                                              \
-      ::abx::profileBegin(tag, stream);                                                                                \
+    int const _prof = ::abx::g_profile ? ::abx::profileBegin(tag, stream) : -1;                                        \
     kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                                                       \
-    if (::abx::g_profile)                                                                                              \
-      ::abx::profileEnd(stream);                                                                                       \
+    if (_prof >= 0)                                                                                                    \
+      ::abx::profileEnd(_prof, stream);                                                                                \
     ++::abx::g_launch_count;                                                                                           \
     ABX_CUDA_TRY(cudaGetLastError());                                                                                  \
   } while (0)
@@ -298,8 +297,9 @@ abx_status nearestQuery(cudaStream_t s, abx_bvh *bvh, float const *pts, int64_t 
                         unsigned long long *missing = nullptr);
 abx_status compactRows(cudaStream_t s, int64_t q, int32_t const *old_offsets, int32_t const *new_offsets,
                        uint32_t const *old_idx, float const *old_dist, uint32_t *new_idx, float *new_dist);
-abx_status routeLaunch(cudaStream_t s, bool fill, int pred_kind, void const *preds, int64_t q, float const *boxes6,
-                       int R, int self_rank, unsigned *counts, unsigned const *base, unsigned *cursors, int32_t *out_qid);
+abx_status routeLaunch(cudaStream_t s, bool fill, int pred_kind, void const *preds, int64_t q, float const *radius,
+                       int64_t radius_stride, float const *boxes6, int R, int self_rank, unsigned *counts,
+                       unsigned const *base, unsigned *cursors, int32_t *out_qid);
 abx_status pairWithRank(cudaStream_t s, int32_t const *indices, int64_t n, int rank, int32_t *out2);
 abx_status mergeCrs(cudaStream_t s, int64_t q, int32_t const *local_off, int32_t const *local_idx, int rank,
                     int32_t const *remote_off, int32_t const *remote_vals2, int32_t *out_off, int32_t *out_vals2);

@@ -488,6 +488,12 @@ __global__ void clipKKernel(int32_t const *__restrict__ k_per_query, int k_unifo
     CALL;                                                                                                              \
     break;                                                                                                             \
   }                                                                                                                    \
+  case ABX_PRED_RAY3F:                                                                                                 \
+  {                                                                                                                    \
+    constexpr int P = ABX_PRED_RAY3F;                                                                                  \
+    CALL;                                                                                                              \
+    break;                                                                                                             \
+  }                                                                                                                    \
   default:                                                                                                             \
     setError("unknown predicate kind");                                                                                \
     return ABX_ERR_ARG;                                                                                                \
@@ -506,9 +512,14 @@ abx_status spatialLaunch(cudaStream_t s, abx_bvh *t, int pred_kind, void const *
                     : MODE == MODE_FILL  ? "spatialKernel<fill>"
                     : MODE == MODE_STAGE ? "spatialKernel<stage>"
                                          : "spatialKernel<compact>";
-  if (t->kind == ABX_PRIM_TRI3F && pred_kind != ABX_PRED_SPHERE3F)
+  if (t->kind == ABX_PRIM_TRI3F && pred_kind != ABX_PRED_SPHERE3F && pred_kind != ABX_PRED_RAY3F)
   {
-    setError("only intersects(Sphere) is defined for triangle primitives");
+    setError("only intersects(Sphere) and intersects(Ray) are defined for triangle primitives");
+    return ABX_ERR_ARG;
+  }
+  if (t->kind == ABX_PRIM_POINT3F && pred_kind == ABX_PRED_RAY3F)
+  {
+    setError("intersects(Ray) is defined for box and triangle primitives");
     return ABX_ERR_ARG;
   }
   if (n == 0)
@@ -706,9 +717,10 @@ __global__ void mergeRowsKernel(int64_t q, int32_t const *__restrict__ local_off
 // query ids grouped by destination (the send buffer order of the all-to-all-v).
 template <int PRED, bool FILL>
 __global__ void __launch_bounds__(256)
-    routeKernel(float const *__restrict__ preds, int64_t q, float const *__restrict__ boxes6, int R, int self_rank,
-                unsigned *__restrict__ counts /*[R]*/, unsigned const *__restrict__ base /*[R]*/,
-                unsigned *__restrict__ cursors /*[R]*/, int32_t *__restrict__ out_qid)
+    routeKernel(float const *__restrict__ preds, int64_t q, float const *__restrict__ radius, int64_t radius_stride,
+                float const *__restrict__ boxes6, int R, int self_rank, unsigned *__restrict__ counts /*[R]*/,
+                unsigned const *__restrict__ base /*[R]*/, unsigned *__restrict__ cursors /*[R]*/,
+                int32_t *__restrict__ out_qid)
 {
   __shared__ float sbox[64 * 6];
   __shared__ unsigned scount[64];
@@ -723,8 +735,10 @@ __global__ void __launch_bounds__(256)
     float c[3], r2 = 0.f, hi3[3];
     if (PRED == ABX_PRED_SPHERE3F)
     {
-      c[0] = preds[4 * i], c[1] = preds[4 * i + 1], c[2] = preds[4 * i + 2];
-      float const r = preds[4 * i + 3];
+      // spheres either packed (centre, radius) or points + a separate (strided) radius array
+      int const st = radius ? 3 : 4;
+      c[0] = preds[st * i], c[1] = preds[st * i + 1], c[2] = preds[st * i + 2];
+      float const r = radius ? radius[i * radius_stride] : preds[4 * i + 3];
       r2 = r * r * 1.0001f + 1e-30f;
     }
     else if (PRED == ABX_PRED_BOX3F)
@@ -776,8 +790,9 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-abx_status routeLaunch(cudaStream_t s, bool fill, int pred_kind, void const *preds, int64_t q, float const *boxes6,
-                       int R, int self_rank, unsigned *counts, unsigned const *base, unsigned *cursors, int32_t *out_qid)
+abx_status routeLaunch(cudaStream_t s, bool fill, int pred_kind, void const *preds, int64_t q, float const *radius,
+                       int64_t radius_stride, float const *boxes6, int R, int self_rank, unsigned *counts,
+                       unsigned const *base, unsigned *cursors, int32_t *out_qid)
 {
   if (R > 64)
   {
@@ -791,11 +806,11 @@ abx_status routeLaunch(cudaStream_t s, bool fill, int pred_kind, void const *pre
   do                                                                                                                   \
   {                                                                                                                    \
     if (fill)                                                                                                          \
-      ABX_LAUNCH_TAGGED("routeKernel<fill>", (routeKernel<P, true>), grid, 256, 0, s, (float const *)preds, q,         \
-                        boxes6, R, self_rank, counts, base, cursors, out_qid);                                         \
+      ABX_LAUNCH_TAGGED("routeKernel<fill>", (routeKernel<P, true>), grid, 256, 0, s, (float const *)preds, q, radius, \
+                        radius_stride, boxes6, R, self_rank, counts, base, cursors, out_qid);                          \
     else                                                                                                               \
       ABX_LAUNCH_TAGGED("routeKernel<count>", (routeKernel<P, false>), grid, 256, 0, s, (float const *)preds, q,       \
-                        boxes6, R, self_rank, counts, base, cursors, out_qid);                                         \
+                        radius, radius_stride, boxes6, R, self_rank, counts, base, cursors, out_qid);                  \
   } while (0)
   switch (pred_kind)
   {

@@ -82,6 +82,62 @@ struct Pred<ABX_PRED_POINT3F>
   __device__ __forceinline__ bool point(float4 p) const { return box(p, p); }
 };
 
+// Experimental::Ray (geometry/ArborX_Ray.hpp): direction normalised in double (:47-55), slab
+// test with explicit +-inf for zero components (:107-157), intersects = hit && tmax >= 0 (:159-167)
+template <>
+struct Pred<ABX_PRED_RAY3F>
+{
+  float ox, oy, oz, dx, dy, dz;
+  __device__ __forceinline__ void load(float const *__restrict__ p, int64_t i)
+  {
+    ox = p[6 * i];
+    oy = p[6 * i + 1];
+    oz = p[6 * i + 2];
+    double const gx = p[6 * i + 3], gy = p[6 * i + 4], gz = p[6 * i + 5];
+    double const m = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(gx, gx), __dmul_rn(gy, gy)), __dmul_rn(gz, gz)));
+    dx = (float)__ddiv_rn(gx, m);
+    dy = (float)__ddiv_rn(gy, m);
+    dz = (float)__ddiv_rn(gz, m);
+  }
+  __device__ __forceinline__ void slab(float o, float d, float lo, float hi, float &tmin, float &tmax) const
+  {
+    float const inf = __int_as_float(0x7f800000);
+    float tdmin, tdmax;
+    if (d == 0.f)
+    {
+      float const min_orig = __fsub_rn(lo, o);
+      if (min_orig == 0.f)
+        return;
+      float const max_orig = __fsub_rn(hi, o);
+      tdmin = signbit(__fmul_rn(d, max_orig)) ? inf : -inf;
+      tdmax = signbit(__fmul_rn(d, min_orig)) ? inf : -inf;
+    }
+    else if (d > 0.f)
+    {
+      tdmin = __fdiv_rn(__fsub_rn(lo, o), d);
+      tdmax = __fdiv_rn(__fsub_rn(hi, o), d);
+    }
+    else
+    {
+      tdmin = __fdiv_rn(__fsub_rn(hi, o), d);
+      tdmax = __fdiv_rn(__fsub_rn(lo, o), d);
+    }
+    if (tmin < tdmin)
+      tmin = tdmin;
+    if (tmax > tdmax)
+      tmax = tdmax;
+  }
+  __device__ __forceinline__ bool box(float4 lo, float4 hi) const
+  {
+    float tmin = -__int_as_float(0x7f800000), tmax = __int_as_float(0x7f800000);
+    slab(ox, dx, lo.x, hi.x, tmin, tmax);
+    slab(oy, dy, lo.y, hi.y, tmin, tmax);
+    slab(oz, dz, lo.z, hi.z, tmin, tmax);
+    return tmin <= tmax && tmax >= 0.f;
+  }
+  __device__ __forceinline__ bool point(float4 p) const { return box(p, p); }
+};
+
 // ---- point-triangle distance (ClosestPoint.hpp:69-153, Distance.hpp:112-123) ----
 __device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz)
 {
@@ -292,6 +348,150 @@ __device__ __forceinline__ bool triangleLeafTest<ABX_PRED_SPHERE3F>(Pred<ABX_PRE
   float4 A = __ldg(leaf_tri + 3 * (size_t)pos), B = __ldg(leaf_tri + 3 * (size_t)pos + 1),
          C = __ldg(leaf_tri + 3 * (size_t)pos + 2);
   return pointTriangleDist2(p.cx, p.cy, p.cz, A, B, C) <= p.t;
+}
+
+// ray-triangle (ArborX_Ray.hpp:266-427): Woop et al. watertight test with a double-precision
+// fallback for zero barycentrics and edge hits for coplanar rays; mixed float/double expressions
+// reproduced with explicit conversions, nothing contracted
+__device__ __forceinline__ void rayRotate2D(float const p[3], float out[3])
+{
+  float const r = __fsqrt_rn(__fadd_rn(__fmul_rn(p[0], p[0]), __fmul_rn(p[1], p[1])));
+  if (p[0] != 0.f)
+    out[0] = p[0] > 0.f ? r : -r;
+  else
+    out[0] = p[1] > 0.f ? r : -r;
+  out[1] = p[2];
+  out[2] = 0.f;
+}
+__device__ __forceinline__ bool rayEdgeIntersect(float const v1[3], float const v2[3], float &t)
+{
+  float const x3 = v1[0], y3 = v1[1], x4 = v2[0], y4 = v2[1];
+  float const y2 = fabsf(y3) > fabsf(y4) ? y3 : y4;
+  float const det = __fmul_rn(y2, __fsub_rn(x3, x4));
+  if (det == 0.f)
+    return false;
+  t = __fmul_rn(__fdiv_rn(__fsub_rn(__fmul_rn(x3, y4), __fmul_rn(x4, y3)), det), y2);
+  float const u = __fdiv_rn(__fmul_rn(x3, y2), det);
+  float const epsilon = 0.00001f;
+  return (u >= __fsub_rn(0.f, epsilon) && u <= __fadd_rn(1.f, epsilon));
+}
+__device__ inline bool rayTriangleIntersects(Pred<ABX_PRED_RAY3F> const &ray, float4 TA, float4 TB, float4 TC)
+{
+  float const dir[3] = {ray.dx, ray.dy, ray.dz};
+  float const ta[3] = {TA.x, TA.y, TA.z}, tb[3] = {TB.x, TB.y, TB.z}, tc[3] = {TC.x, TC.y, TC.z};
+  float const o[3] = {ray.ox, ray.oy, ray.oz};
+  int kz = 0;
+  {
+    float mx = fabsf(dir[0]);
+    for (int i = 1; i < 3; ++i)
+    {
+      float const f = fabsf(dir[i]);
+      if (f > mx)
+      {
+        mx = f;
+        kz = i;
+      }
+    }
+  }
+  int kx = (kz + 1) % 3, ky = (kz + 2) % 3;
+  if (dir[kz] < 0.f)
+  {
+    int const tmp = kx;
+    kx = ky;
+    ky = tmp;
+  }
+  float s[3];
+  s[2] = __fdiv_rn(1.0f, dir[kz]);
+  s[0] = __fmul_rn(dir[kx], s[2]);
+  s[1] = __fmul_rn(dir[ky], s[2]);
+  float oA[3], oB[3], oC[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+  {
+    oA[d] = __fsub_rn(ta[d], o[d]);
+    oB[d] = __fsub_rn(tb[d], o[d]);
+    oC[d] = __fsub_rn(tc[d], o[d]);
+  }
+  float const mag_oA = __fsqrt_rn(dot3(oA[0], oA[1], oA[2], oA[0], oA[1], oA[2]));
+  float const mag_oB = __fsqrt_rn(dot3(oB[0], oB[1], oB[2], oB[0], oB[1], oB[2]));
+  float const mag_oC = __fsqrt_rn(dot3(oC[0], oC[1], oC[2], oC[0], oC[1], oC[2]));
+  double const mag_bar = __ddiv_rn(3.0, (double)__fadd_rn(__fadd_rn(mag_oA, mag_oB), mag_oC));
+  float A[3], B[3], C[3];
+  A[0] = (float)__dmul_rn((double)__fsub_rn(oA[kx], __fmul_rn(s[0], oA[kz])), mag_bar);
+  A[1] = (float)__dmul_rn((double)__fsub_rn(oA[ky], __fmul_rn(s[1], oA[kz])), mag_bar);
+  B[0] = (float)__dmul_rn((double)__fsub_rn(oB[kx], __fmul_rn(s[0], oB[kz])), mag_bar);
+  B[1] = (float)__dmul_rn((double)__fsub_rn(oB[ky], __fmul_rn(s[1], oB[kz])), mag_bar);
+  C[0] = (float)__dmul_rn((double)__fsub_rn(oC[kx], __fmul_rn(s[0], oC[kz])), mag_bar);
+  C[1] = (float)__dmul_rn((double)__fsub_rn(oC[ky], __fmul_rn(s[1], oC[kz])), mag_bar);
+  float u = __fsub_rn(__fmul_rn(C[0], B[1]), __fmul_rn(C[1], B[0]));
+  float v = __fsub_rn(__fmul_rn(A[0], C[1]), __fmul_rn(A[1], C[0]));
+  float w = __fsub_rn(__fmul_rn(B[0], A[1]), __fmul_rn(B[1], A[0]));
+  if (u == 0.f || v == 0.f || w == 0.f)
+  {
+    u = (float)__dsub_rn(__dmul_rn((double)C[0], (double)B[1]), __dmul_rn((double)C[1], (double)B[0]));
+    v = (float)__dsub_rn(__dmul_rn((double)A[0], (double)C[1]), __dmul_rn((double)A[1], (double)C[0]));
+    w = (float)__dsub_rn(__dmul_rn((double)B[0], (double)A[1]), __dmul_rn((double)B[1], (double)A[0]));
+  }
+  float const inf = __int_as_float(0x7f800000);
+  float tmin = inf, tmax = -inf;
+  float const epsilon = 0.0000001f;
+  if ((u < -epsilon || v < -epsilon || w < -epsilon) && (u > epsilon || v > epsilon || w > epsilon))
+    return false;
+  float const det = __fadd_rn(__fadd_rn(u, v), w);
+  A[2] = __fmul_rn(s[2], oA[kz]);
+  B[2] = __fmul_rn(s[2], oB[kz]);
+  C[2] = __fmul_rn(s[2], oC[kz]);
+  if (det < -epsilon || det > epsilon)
+  {
+    float const t = __fdiv_rn(__fadd_rn(__fadd_rn(__fmul_rn(u, A[2]), __fmul_rn(v, B[2])), __fmul_rn(w, C[2])), det);
+    return t >= 0.f; // tmax = tmin = t
+  }
+  float As[3], Bs[3], Cs[3];
+  rayRotate2D(A, As);
+  rayRotate2D(B, Bs);
+  rayRotate2D(C, Cs);
+  float t_ab = inf, t_bc = inf, t_ca = inf;
+  bool const ab = rayEdgeIntersect(As, Bs, t_ab);
+  if (ab)
+  {
+    tmin = t_ab;
+    tmax = t_ab;
+  }
+  bool const bc = rayEdgeIntersect(Bs, Cs, t_bc);
+  if (bc)
+  {
+    tmin = fminf(tmin, t_bc);
+    tmax = fmaxf(tmax, t_bc);
+  }
+  bool const ca = rayEdgeIntersect(Cs, As, t_ca);
+  if (ca)
+  {
+    tmin = fminf(tmin, t_ca);
+    tmax = fmaxf(tmax, t_ca);
+  }
+  if (ab || bc || ca)
+  {
+    if (__fmul_rn(tmin, tmax) <= 0.f)
+    {
+      tmin = 0.f;
+      tmax = 0.f;
+    }
+    else if (tmin < 0.f)
+    {
+      float const tmp = tmin;
+      tmin = tmax;
+      tmax = tmp;
+    }
+    return tmax >= 0.f;
+  }
+  return false;
+}
+template <>
+__device__ __forceinline__ bool triangleLeafTest<ABX_PRED_RAY3F>(Pred<ABX_PRED_RAY3F> const &p,
+                                                                  float4 const *__restrict__ leaf_tri, int pos)
+{
+  return rayTriangleIntersects(p, __ldg(leaf_tri + 3 * (size_t)pos), __ldg(leaf_tri + 3 * (size_t)pos + 1),
+                               __ldg(leaf_tri + 3 * (size_t)pos + 2));
 }
 
 // ---- half traversal ---------------------------------------------------------------

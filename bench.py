@@ -35,7 +35,17 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 # stdout must carry exactly one JSON line: keep NCCL's version banner out of it
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
+# stdout must carry exactly ONE JSON line.  Libraries write banners to fd 1 (NCCL prints its
+# version there), so fd 1 is pointed at stderr for the whole run and the result line is written
+# to the saved descriptor by emit().
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 
 METRIC = "BVH build Mprims/s; radius & kNN(k=10) Mqueries/s at 10M pts; % HBM roofline"
 UNIT = "Mitems/s (n prims + q radius queries + q kNN queries per step second)"
@@ -182,7 +192,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(n, q, r):
@@ -310,6 +320,8 @@ def run_ours(args):
     hp_spatial = abx.intersects(h_spheres)
     hp_nearest = abx.nearest(h_queries, K_NEIGHBORS)
 
+    pinned_out = {}
+
     def e2e_step():
         if world > 1:
             # DistributedTree takes device data: the host<->device copies are done here, inside the step
@@ -317,7 +329,17 @@ def run_ours(args):
             tree = make_tree(dv)
             idx, off = tree.query(space, abx.intersects(h_spheres.cuda(non_blocking=True)))
             kidx, koff = tree.query(space, abx.nearest(h_queries.cuda(non_blocking=True), K_NEIGHBORS))
-            idx, off, kidx, koff = idx.cpu(), off.cpu(), kidx.cpu(), koff.cpu()
+            outs = []
+            for name, t in (("idx", idx), ("off", off), ("kidx", kidx), ("koff", koff)):
+                buf = pinned_out.get(name)
+                if buf is None or buf.numel() < t.numel():
+                    buf = torch.empty(int(t.numel() * 1.1) + 16, dtype=t.dtype, pin_memory=True)
+                    pinned_out[name] = buf
+                h = buf[:t.numel()].view(t.shape)
+                h.copy_(t, non_blocking=True)
+                outs.append(h)
+            torch.cuda.synchronize()
+            idx, off, kidx, koff = outs
             return int(off[-1]) + int(koff[-1]), idx.numel(), kidx.numel()
         bvh = abx.BoundingVolumeHierarchy(space, h_values)
         idx, off = bvh.query(space, hp_spatial)
@@ -418,7 +440,7 @@ def run_ours(args):
         line["config"]["parallelism"] = ("DistributedTree over %d GPUs: %d points and %d queries per rank on a touching "
                                          "block lattice; top tree + all-to-all-v forwarding (NCCL)" % (world, n, q))
         line["config"]["workload"] += " through DistributedTree (BASELINE.json configs[3] layout, weak scaling)"
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -467,7 +489,7 @@ def run_dbscan(args):
             "config": {"workload": "dbscan GanTao n=%d eps=200 (BASELINE.json configs[2])" % n}, "components": res,
             "cpu_baseline": {"value": ns / t_cpu / 1e6, "unit": "Mpoints/s", "cores": oracle.num_threads(),
                              "kind": "port", "sample": "oracle FDBSCAN-DenseBox minpts=5 on the first %d points" % ns}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():

@@ -60,7 +60,10 @@ enum
 {
   ABX_PRED_SPHERE3F = 0, /* intersects(Sphere): 4 floats centre xyz, radius (geometry/ArborX_Sphere.hpp:25-47) */
   ABX_PRED_BOX3F = 1,    /* intersects(Box):    6 floats */
-  ABX_PRED_POINT3F = 2   /* intersects(Point) / nearest(Point, k): 3 floats */
+  ABX_PRED_POINT3F = 2,  /* intersects(Point) / nearest(Point, k): 3 floats */
+  ABX_PRED_RAY3F = 3     /* intersects(Experimental::Ray): 6 floats origin xyz, direction xyz (any non-zero
+                            vector; normalised in double like the Ray constructor, geometry/ArborX_Ray.hpp:47-55);
+                            box and triangle primitives */
 };
 
 /* Experimental::TraversalPolicy (spatial/detail/ArborX_TraversalPolicy.hpp:19-48) */
@@ -185,11 +188,16 @@ ABX_API abx_status abx_dist_merge_crs(void *stream, int64_t q, const int32_t *lo
  * predicates that must be forwarded to every OTHER rank; pass 2 writes their query ids grouped by
  * destination (base = exclusive scan of the counts), i.e. the send order of the all-to-all-v. */
 ABX_API abx_status abx_dist_route_count(void *stream, int pred_kind, const void *preds_dev, int64_t q,
+                                        const float *radius_dev, int64_t radius_stride,
                                         const float *rank_boxes6_dev, int32_t n_ranks, int32_t self_rank,
                                         uint32_t *counts_dev);
 ABX_API abx_status abx_dist_route_fill(void *stream, int pred_kind, const void *preds_dev, int64_t q,
+                                       const float *radius_dev, int64_t radius_stride,
                                        const float *rank_boxes6_dev, int32_t n_ranks, int32_t self_rank,
                                        const uint32_t *base_dev, uint32_t *cursors_dev, int32_t *query_ids_dev);
+/* radius_dev != NULL (ABX_PRED_SPHERE3F only): preds_dev holds points (3 floats) and the radius of
+ * predicate i is radius_dev[i * radius_stride] -- the k-th distances of a kNN result, phase II of
+ * distributed/detail/ArborX_DistributedTreeNearest.hpp:131-176, without building the spheres. */
 /* values2[i] = (indices[i], rank): local results in the (index, rank) form DistributedTree returns */
 ABX_API abx_status abx_dist_pair_with_rank(void *stream, const int32_t *indices_dev, int64_t n, int32_t rank,
                                            int32_t *values2_dev);

@@ -14,9 +14,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "liborc.so")
 
 PRIM_POINT, PRIM_BOX, PRIM_TRI = 0, 1, 2
-PRED_SPHERE, PRED_BOX, PRED_POINT = 0, 1, 2
+PRED_SPHERE, PRED_BOX, PRED_POINT, PRED_RAY = 0, 1, 2, 3
 PRIM_STRIDE = {PRIM_POINT: 3, PRIM_BOX: 6, PRIM_TRI: 9}
-PRED_STRIDE = {PRED_SPHERE: 4, PRED_BOX: 6, PRED_POINT: 3}
+PRED_STRIDE = {PRED_SPHERE: 4, PRED_BOX: 6, PRED_POINT: 3, PRED_RAY: 6}
 
 
 def build(force=False):

@@ -73,9 +73,10 @@ enum PredKind
 {
   PRED_SPHERE = 0, // 4 floats: centre xyz, radius       intersects(Sphere)
   PRED_BOX = 1,    // 6 floats                            intersects(Box)
-  PRED_POINT = 2   // 3 floats                            intersects(Point) / nearest(Point)
+  PRED_POINT = 2,  // 3 floats                            intersects(Point) / nearest(Point)
+  PRED_RAY = 3     // 6 floats: origin xyz, direction xyz intersects(Experimental::Ray)
 };
-static int predStride(int kind) { return kind == PRED_SPHERE ? 4 : kind == PRED_BOX ? 6 : 3; }
+static int predStride(int kind) { return kind == PRED_SPHERE ? 4 : (kind == PRED_BOX || kind == PRED_RAY) ? 6 : 3; }
 
 // geometry/algorithms/ArborX_Expand.hpp:44-107
 static inline void expand(Box3 &b, P3 const &p)
@@ -221,6 +222,195 @@ static inline bool intersects(P3 const &p, Box3 const &b)
     if (p[d] > b.hi[d] || p[d] < b.lo[d])
       return false;
   return true;
+}
+
+// ---------------------------------------------------------------------------
+// Rays: geometry/ArborX_Ray.hpp.  Unfused float arithmetic; the mixed float/double
+// expressions of the reference are reproduced with explicit conversions.
+// ---------------------------------------------------------------------------
+struct Ray3
+{
+  P3 o;
+  P3 dir; // normalised in double at construction (ArborX_Ray.hpp:47-55, misc/ArborX_Vector.hpp:77-87)
+};
+static inline Ray3 makeRay(float const *g)
+{
+  Ray3 r;
+  r.o = P3{{g[0], g[1], g[2]}};
+  double m = 0;
+  for (int d = 0; d < 3; ++d)
+    m += (double)g[3 + d] * (double)g[3 + d];
+  m = std::sqrt(m);
+  for (int d = 0; d < 3; ++d)
+    r.dir[d] = (float)((double)g[3 + d] / m);
+  return r;
+}
+// :107-157
+static inline bool rayBoxIntersection(Ray3 const &ray, Box3 const &box, float &tmin, float &tmax)
+{
+  float const inf = std::numeric_limits<float>::infinity();
+  tmin = -inf;
+  tmax = inf;
+  for (int d = 0; d < 3; ++d)
+  {
+    float tdmin, tdmax;
+    if (ray.dir[d] == 0)
+    {
+      float const min_orig = box.lo[d] - ray.o[d];
+      if (min_orig == 0)
+        continue;
+      float const max_orig = box.hi[d] - ray.o[d];
+      tdmin = std::signbit(ray.dir[d] * max_orig) ? inf : -inf;
+      tdmax = std::signbit(ray.dir[d] * min_orig) ? inf : -inf;
+    }
+    else if (ray.dir[d] > 0)
+    {
+      tdmin = (box.lo[d] - ray.o[d]) / ray.dir[d];
+      tdmax = (box.hi[d] - ray.o[d]) / ray.dir[d];
+    }
+    else
+    {
+      tdmin = (box.hi[d] - ray.o[d]) / ray.dir[d];
+      tdmax = (box.lo[d] - ray.o[d]) / ray.dir[d];
+    }
+    if (tmin < tdmin)
+      tmin = tdmin;
+    if (tmax > tdmax)
+      tmax = tdmax;
+  }
+  return tmin <= tmax;
+}
+// :159-167
+static inline bool intersects(Ray3 const &ray, Box3 const &box)
+{
+  float tmin, tmax;
+  return rayBoxIntersection(ray, box, tmin, tmax) && (tmax >= 0);
+}
+// :189-212
+static inline void rotate2D(float const p[3], float out[3])
+{
+  float r = std::sqrt(p[0] * p[0] + p[1] * p[1]);
+  if (p[0] != 0)
+    out[0] = (p[0] > 0 ? 1 : -1) * r;
+  else
+    out[0] = (p[1] > 0 ? 1 : -1) * r;
+  out[1] = p[2];
+  out[2] = 0;
+}
+// :219-249
+static inline bool rayEdgeIntersect(float const v1[3], float const v2[3], float &t)
+{
+  float x3 = v1[0], y3 = v1[1], x4 = v2[0], y4 = v2[1];
+  float y2 = std::fabs(y3) > std::fabs(y4) ? y3 : y4;
+  float det = y2 * (x3 - x4);
+  if (det == 0)
+    return false;
+  t = (x3 * y4 - x4 * y3) / det * y2;
+  float u = x3 * y2 / det;
+  float const epsilon = 0.00001f;
+  return (u >= 0 - epsilon && u <= 1 + epsilon);
+}
+// :266-417 (Woop et al. watertight test, with the coplanar case returning edge hits)
+static inline bool rayTriIntersection(Ray3 const &ray, Tri3 const &tri, float &tmin, float &tmax)
+{
+  P3 const &dir = ray.dir;
+  int kz = 0;
+  {
+    float mx = std::abs(dir[0]);
+    for (int i = 1; i < 3; ++i)
+    {
+      float f = std::fabs(dir[i]);
+      if (f > mx)
+      {
+        mx = f;
+        kz = i;
+      }
+    }
+  }
+  int kx = (kz + 1) % 3, ky = (kz + 2) % 3;
+  if (dir[kz] < 0)
+    std::swap(kx, ky);
+  float s[3];
+  s[2] = 1.0f / dir[kz];
+  s[0] = dir[kx] * s[2];
+  s[1] = dir[ky] * s[2];
+  P3 const oA = sub(tri.a, ray.o), oB = sub(tri.b, ray.o), oC = sub(tri.c, ray.o);
+  float const mag_oA = std::sqrt(dot(oA, oA)), mag_oB = std::sqrt(dot(oB, oB)), mag_oC = std::sqrt(dot(oC, oC));
+  double const mag_bar = 3.0 / (double)(mag_oA + mag_oB + mag_oC);
+  float A[3], B[3], C[3];
+  A[0] = (float)((double)(oA[kx] - s[0] * oA[kz]) * mag_bar);
+  A[1] = (float)((double)(oA[ky] - s[1] * oA[kz]) * mag_bar);
+  B[0] = (float)((double)(oB[kx] - s[0] * oB[kz]) * mag_bar);
+  B[1] = (float)((double)(oB[ky] - s[1] * oB[kz]) * mag_bar);
+  C[0] = (float)((double)(oC[kx] - s[0] * oC[kz]) * mag_bar);
+  C[1] = (float)((double)(oC[ky] - s[1] * oC[kz]) * mag_bar);
+  float u = C[0] * B[1] - C[1] * B[0];
+  float v = A[0] * C[1] - A[1] * C[0];
+  float w = B[0] * A[1] - B[1] * A[0];
+  if (u == 0 || v == 0 || w == 0)
+  {
+    u = (float)((double)C[0] * B[1] - (double)C[1] * B[0]);
+    v = (float)((double)A[0] * C[1] - (double)A[1] * C[0]);
+    w = (float)((double)B[0] * A[1] - (double)B[1] * A[0]);
+  }
+  float const inf = std::numeric_limits<float>::infinity();
+  tmin = inf;
+  tmax = -inf;
+  float const epsilon = 0.0000001f;
+  if ((u < -epsilon || v < -epsilon || w < -epsilon) && (u > epsilon || v > epsilon || w > epsilon))
+    return false;
+  float const det = u + v + w;
+  A[2] = s[2] * oA[kz];
+  B[2] = s[2] * oB[kz];
+  C[2] = s[2] * oC[kz];
+  if (det < -epsilon || det > epsilon)
+  {
+    float t = (u * A[2] + v * B[2] + w * C[2]) / det;
+    tmax = t;
+    tmin = t;
+    return true;
+  }
+  float As[3], Bs[3], Cs[3];
+  rotate2D(A, As);
+  rotate2D(B, Bs);
+  rotate2D(C, Cs);
+  float t_ab = inf, t_bc = inf, t_ca = inf;
+  bool const ab = rayEdgeIntersect(As, Bs, t_ab);
+  if (ab)
+  {
+    tmin = t_ab;
+    tmax = t_ab;
+  }
+  bool const bc = rayEdgeIntersect(Bs, Cs, t_bc);
+  if (bc)
+  {
+    tmin = std::min(tmin, t_bc);
+    tmax = std::max(tmax, t_bc);
+  }
+  bool const ca = rayEdgeIntersect(Cs, As, t_ca);
+  if (ca)
+  {
+    tmin = std::min(tmin, t_ca);
+    tmax = std::max(tmax, t_ca);
+  }
+  if (ab || bc || ca)
+  {
+    if (tmin * tmax <= 0)
+    {
+      tmin = 0;
+      tmax = 0;
+    }
+    else if (tmin < 0)
+      std::swap(tmin, tmax);
+    return true;
+  }
+  return false;
+}
+// :419-427
+static inline bool intersects(Ray3 const &ray, Tri3 const &tri)
+{
+  float tmin, tmax;
+  return rayTriIntersection(ray, tri, tmin, tmax) && (tmax >= 0);
 }
 
 // ---------------------------------------------------------------------------
@@ -557,6 +747,8 @@ struct Pred
   // Intersects<G>::operator()(Box)  (Predicates.hpp:83-101 -> Intersects.hpp)
   bool operator()(Box3 const &b) const
   {
+    if (kind == PRED_RAY)
+      return intersects(makeRay(g), b); // ArborX_Ray.hpp:159-167
     if (kind == PRED_SPHERE)
       return distance(center(), b) <= g[3]; // Intersects.hpp:84-91
     if (kind == PRED_BOX)
@@ -565,6 +757,13 @@ struct Pred
   }
   bool operator()(P3 const &p) const
   {
+    if (kind == PRED_RAY)
+    { // not defined by the reference for points; a point is the degenerate box [p, p]
+      Box3 b;
+      b.lo = p;
+      b.hi = p;
+      return intersects(makeRay(g), b);
+    }
     if (kind == PRED_SPHERE)
       return distance(center(), p) <= g[3]; // Intersects.hpp:107-114
     if (kind == PRED_BOX)
@@ -573,7 +772,9 @@ struct Pred
   }
   bool operator()(Tri3 const &t) const
   {
-    // only sphere-triangle is defined in 3-D (Intersects.hpp:118-126)
+    if (kind == PRED_RAY)
+      return intersects(makeRay(g), t); // ArborX_Ray.hpp:419-427
+    // sphere-triangle (Intersects.hpp:118-126)
     return distance(center(), t) <= g[3];
   }
   P3 centroidOf() const

@@ -29,7 +29,7 @@ class _CudaTree:
         return out
 
     def spatial_crs(self, preds, kind=PRED_SPHERE, sort_predicates=True, buffer_size=0):
-        stride = {0: 4, 1: 6, 2: 3}[kind]
+        stride = {0: 4, 1: 6, 2: 3, 3: 6}[kind]
         p = abx.intersects(_dev(np.asarray(preds, np.float32).reshape(-1, stride)), kind)
         try:
             idx, off = self.bvh.query(self.space, p, abx.TraversalPolicy(buffer_size, sort_predicates))
@@ -39,7 +39,7 @@ class _CudaTree:
         return off.cpu().numpy(), idx.cpu().numpy().view(np.uint32)
 
     def spatial_count(self, preds, kind=PRED_SPHERE, limit=0):
-        stride = {0: 4, 1: 6, 2: 3}[kind]
+        stride = {0: 4, 1: 6, 2: 3, 3: 6}[kind]
         p = abx.intersects(_dev(np.asarray(preds, np.float32).reshape(-1, stride)), kind)
         c = self.bvh.count(self.space, p, limit)
         self.space.fence()

@@ -6,7 +6,7 @@ import numpy as np
 import oracle
 
 PRIM_POINT, PRIM_BOX, PRIM_TRI = 0, 1, 2
-PRED_SPHERE, PRED_BOX, PRED_POINT = 0, 1, 2
+PRED_SPHERE, PRED_BOX, PRED_POINT, PRED_RAY = 0, 1, 2, 3
 
 
 class SearchException(Exception):
