@@ -135,9 +135,11 @@ __device__ __forceinline__ void boxUnion(Box &a, Box const &b)
 __device__ __forceinline__ float pointBoxDist2(float cx, float cy, float cz, float lx, float ly, float lz, float hx,
                                                float hy, float hz)
 {
-  float px = cx < lx ? lx : (cx > hx ? hx : cx);
-  float py = cy < ly ? ly : (cy > hy ? hy : cy);
-  float pz = cz < lz ? lz : (cz > hz ? hz : cz);
+  // min(max(c, lo), hi) equals the reference's branchy clamp for every valid box; for an "empty" box
+  // (lo = +FLT_MAX > hi) both give an infinite distance, which is all any caller compares
+  float px = fminf(fmaxf(cx, lx), hx);
+  float py = fminf(fmaxf(cy, ly), hy);
+  float pz = fminf(fmaxf(cz, lz), hz);
   float tx = __fsub_rn(px, cx), ty = __fsub_rn(py, cy), tz = __fsub_rn(pz, cz);
   float d2 = __fmul_rn(tx, tx);
   d2 = __fadd_rn(d2, __fmul_rn(ty, ty));

@@ -9,6 +9,8 @@
 // the reference does not specify either.
 #include "abx_traverse.cuh"
 
+#include <cstdlib>
+
 namespace abx
 {
 
@@ -22,11 +24,12 @@ enum
   MODE_STAGE = 2,   // count AND keep the first kStage results of every query in a staging buffer
   MODE_COMPACT = 3  // staged results -> CRS rows; re-traverses only the queries that overflowed
 };
+constexpr int kSpatialBucketDefault = 4; // measured r01: 1 and 4 tie (5.85 ms stage), 8 is 6.34 ms
 // Staging buffer of the single-traversal CRS path: slot-major ([slot][sorted query]),
 // so a warp writes/reads slot s of 32 neighbouring queries as one coalesced row.
 constexpr int kStage = 32;
 
-template <int PRED, int MODE, int LEAF_F4, bool TRI>
+template <int PRED, int MODE, int LEAF_F4, bool TRI, int BUCKET>
 __global__ void __launch_bounds__(kThreads)
     spatialKernel(Node64 const *__restrict__ nodes, float4 const *__restrict__ leaf_box,
                   float4 const *__restrict__ leaf_tri, int n, float const *__restrict__ preds, int64_t q,
@@ -54,7 +57,7 @@ __global__ void __launch_bounds__(kThreads)
   Pred<PRED> pred;
   pred.load(preds, qi);
   int count = 0;
-  traverseSpatial<LEAF_F4>(nodes, leaf_box, pred, [&](unsigned orig, int pos) {
+  traverseSpatial<LEAF_F4, BUCKET>(nodes, leaf_box, pred, [&](unsigned orig, int pos) {
     if (TRI && !triangleLeafTest<PRED>(pred, leaf_tri, pos))
       return false;
     if (MODE == MODE_FILL || MODE == MODE_COMPACT)
@@ -338,18 +341,17 @@ __global__ void __launch_bounds__(kThreads)
           offer(d2, orig, j);
       }
     };
-    if (l_small && r_small && dr < dl)
-    {
-      consume(refIsLeaf(rref), dr, rref, r_lo, rr);
-      consume(refIsLeaf(lref), dl, lref, rl, l_hi);
-    }
-    else
-    {
-      if (l_small)
-        consume(refIsLeaf(lref), dl, lref, rl, l_hi);
-      if (r_small)
-        consume(refIsLeaf(rref), dr, rref, r_lo, rr);
-    }
+    // one consume site per slot (first / second): lanes whose only candidate is the left child
+    // and lanes whose only candidate is the right child run the same insertion code together
+    // instead of four serialised inlined copies
+    bool const swap = l_small && r_small && dr < dl;
+    bool const first_is_left = l_small && !swap;
+    if (l_small || r_small)
+      consume(first_is_left ? refIsLeaf(lref) : refIsLeaf(rref), first_is_left ? dl : dr, first_is_left ? lref : rref,
+              first_is_left ? rl : r_lo, first_is_left ? l_hi : rr);
+    if (l_small && r_small)
+      consume(swap ? refIsLeaf(lref) : refIsLeaf(rref), swap ? dl : dr, swap ? lref : rref, swap ? rl : r_lo,
+              swap ? l_hi : rr);
     bool const go_l = !l_small && dl < radius2;
     bool const go_r = !r_small && dr < radius2;
     if (go_l || go_r)
@@ -536,10 +538,31 @@ abx_status spatialLaunch(cudaStream_t s, abx_bvh *t, int pred_kind, void const *
                                             t->leaf_tri, t->kind, (float const *)preds, q, counts, offsets, indices));
     return ABX_OK;
   }
-#define ABX_SPATIAL(LF4, TRIFLAG)                                                                                     \
-  ABX_DISPATCH_PRED(pred_kind, ABX_LAUNCH_TAGGED(tag, (spatialKernel<P, MODE, LF4, TRIFLAG>), grid, kThreads, 0, s,   \
-                                                 t->nodes, t->leaf_box, t->leaf_tri, n, (float const *)preds, q,      \
+  // leaf-run scans: ABX_SPATIAL_BUCKET = 1 (off), 4 or 8 (tuning aid; default below)
+  static int const bucket = [] {
+    char const *e = getenv("ABX_SPATIAL_BUCKET");
+    return e ? atoi(e) : kSpatialBucketDefault;
+  }();
+#define ABX_SPATIAL_B(LF4, TRIFLAG, B)                                                                                \
+  ABX_DISPATCH_PRED(pred_kind, ABX_LAUNCH_TAGGED(tag, (spatialKernel<P, MODE, LF4, TRIFLAG, B>), grid, kThreads, 0,   \
+                                                 s, t->nodes, t->leaf_box, t->leaf_tri, n, (float const *)preds, q,   \
                                                  qperm, limit, counts, offsets, indices, staging))
+#define ABX_SPATIAL(LF4, TRIFLAG)                                                                                     \
+  do                                                                                                                   \
+  {                                                                                                                    \
+    if (bucket <= 1)                                                                                                   \
+    {                                                                                                                  \
+      ABX_SPATIAL_B(LF4, TRIFLAG, 1);                                                                                  \
+    }                                                                                                                  \
+    else if (bucket <= 4)                                                                                              \
+    {                                                                                                                  \
+      ABX_SPATIAL_B(LF4, TRIFLAG, 4);                                                                                  \
+    }                                                                                                                  \
+    else                                                                                                               \
+    {                                                                                                                  \
+      ABX_SPATIAL_B(LF4, TRIFLAG, 8);                                                                                  \
+    }                                                                                                                  \
+  } while (0)
   if (t->kind == ABX_PRIM_TRI3F)
   {
     ABX_SPATIAL(2, true);
@@ -553,6 +576,7 @@ abx_status spatialLaunch(cudaStream_t s, abx_bvh *t, int pred_kind, void const *
     ABX_SPATIAL(1, false);
   }
 #undef ABX_SPATIAL
+#undef ABX_SPATIAL_B
   return ABX_OK;
 }
 

@@ -268,7 +268,7 @@ __device__ __forceinline__ bool scanLeaves(float4 const *__restrict__ leaf_box, 
   return false;
 }
 
-template <int LEAF_F4, class P, class Emit>
+template <int LEAF_F4, int BUCKET = kBucket, class P, class Emit>
 __device__ __forceinline__ void traverseSpatial(Node64 const *__restrict__ nodes,
                                                 float4 const *__restrict__ leaf_box, P const &pred, Emit &&emit)
 {
@@ -295,7 +295,7 @@ __device__ __forceinline__ void traverseSpatial(Node64 const *__restrict__ nodes
           return;
         hit_l = false;
       }
-      else if (l_hi - rl < kBucket)
+      else if (BUCKET > 1 && l_hi - rl < BUCKET)
       {
         if (scanLeaves<LEAF_F4>(leaf_box, rl, l_hi, pred, emit))
           return;
@@ -310,7 +310,7 @@ __device__ __forceinline__ void traverseSpatial(Node64 const *__restrict__ nodes
           return;
         hit_r = false;
       }
-      else if (rr - r_lo < kBucket)
+      else if (BUCKET > 1 && rr - r_lo < BUCKET)
       {
         if (scanLeaves<LEAF_F4>(leaf_box, r_lo, rr, pred, emit))
           return;
