@@ -964,7 +964,21 @@ abx_status buildTree(cudaStream_t s, int kind, void const *prims, int64_t n, uin
     ABX_TRY_T(sceneBounds(s, kind, prims, n, enc.ptr));
     ABX_TRY_T(decodeBounds(s, enc.ptr, t->bounds_dev));
     ABX_TRY_T(morton64(s, kind, prims, n, t->bounds_dev, t->codes));
-    ABX_TRY_T(sortPairsU64(s, t->codes, t->perm, n, /*iota_vals=*/true));
+    // Morton64 codes use 63 bits (3 x 21).  Double-buffered: the tree keeps whichever pair of
+    // buffers the sort finished in
+    TempBuffer<uint64_t> codes_alt;
+    TempBuffer<uint32_t> perm_alt;
+    ABX_TRY_T(codes_alt.alloc(n, s));
+    ABX_TRY_T(perm_alt.alloc(n, s));
+    uint64_t *kb[2] = {t->codes, codes_alt.ptr};
+    uint32_t *vb[2] = {t->perm, perm_alt.ptr};
+    int cur = 0;
+    ABX_TRY_T(sortPairsU64DB(s, kb, vb, &cur, n, /*iota_vals=*/true, 63));
+    if (cur != 0)
+    {
+      std::swap(t->codes, codes_alt.ptr);
+      std::swap(t->perm, perm_alt.ptr);
+    }
   }
   ABX_TRY_T(buildHierarchy(s, t, prims));
   *out = t;

@@ -268,8 +268,17 @@ struct abx_bvh
 namespace abx
 {
 // sort.cu
-abx_status sortPairsU64(cudaStream_t s, uint64_t *keys, uint32_t *vals, int64_t n, bool iota_vals);
-abx_status sortPairsU32(cudaStream_t s, uint32_t *keys, uint32_t *vals, int64_t n, bool iota_vals);
+// stable sort of (key, value) pairs by the low key_bits bits of the key (the rest must be zero)
+// fixup = false forces plain LSD over all key_bits (keys with long runs of equal top bits, e.g. grid cells)
+abx_status sortPairsU64(cudaStream_t s, uint64_t *keys, uint32_t *vals, int64_t n, bool iota_vals, int key_bits = 64,
+                        bool fixup = true);
+abx_status sortPairsU32(cudaStream_t s, uint32_t *keys, uint32_t *vals, int64_t n, bool iota_vals, int key_bits = 32);
+// double-buffer forms: input in keys[0]/vals[0], output in keys[*cur]/vals[*cur].  approx_top_bits > 0
+// orders by the top approx_top_bits of the key_bits only (an ordering hint, e.g. predicate sorting).
+abx_status sortPairsU64DB(cudaStream_t s, uint64_t *const keys[2], uint32_t *const vals[2], int *cur, int64_t n,
+                          bool iota_vals, int key_bits);
+abx_status sortPairsU32DB(cudaStream_t s, uint32_t *const keys[2], uint32_t *const vals[2], int *cur, int64_t n,
+                          bool iota_vals, int key_bits, int approx_top_bits);
 abx_status exclusiveScanI32(cudaStream_t s, int32_t const *in, int32_t *out, int64_t n_plus_1);
 // build.cu
 abx_status sceneBounds(cudaStream_t s, int kind, void const *prims, int64_t n, unsigned *bounds_enc6);

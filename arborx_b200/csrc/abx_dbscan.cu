@@ -524,7 +524,15 @@ abx_status denseBox(cudaStream_t s, float const *xyz, int n, float eps, int minp
   ABX_TRY(perm.alloc(n, s));
   ABX_TRY(perm2.alloc(n, s));
   ABX_LAUNCH(cellIndicesKernel, grid_n, 256, 0, s, xyz, n, g, cells.ptr);
-  ABX_TRY(sortPairsU64(s, (uint64_t *)cells.ptr, perm.ptr, n, true));
+  // cell ids are < nx*ny*nz: only the digits that can be non-zero are sorted.  Cells hold long
+  // runs of equal keys, so the plain LSD form is used
+  int cell_bits = 1;
+  {
+    long double const total = (long double)g.n[0] * (long double)g.n[1] * (long double)g.n[2];
+    while (cell_bits < 64 && (long double)((unsigned long long)1 << cell_bits) < total)
+      ++cell_bits;
+  }
+  ABX_TRY(sortPairsU64(s, (uint64_t *)cells.ptr, perm.ptr, n, true, cell_bits, /*fixup=*/false));
 
   // distinct cells
   TempBuffer<int> flags, rank, cell_id, cell_offsets;

@@ -24,6 +24,7 @@ enum
   MODE_STAGE = 2,   // count AND keep the first kStage results of every query in a staging buffer
   MODE_COMPACT = 3  // staged results -> CRS rows; re-traverses only the queries that overflowed
 };
+constexpr int kPredicateSortBits = 24;
 constexpr int kSpatialBucketDefault = 4; // measured r01: 1 and 4 tie (5.85 ms stage), 8 is 6.34 ms
 // Staging buffer of the single-traversal CRS path: slot-major ([slot][sorted query]),
 // so a warp writes/reads slot s of 32 neighbouring queries as one coalesced row.
@@ -586,11 +587,26 @@ abx_status spatialLaunch(cudaStream_t s, abx_bvh *t, int pred_kind, void const *
 abx_status predicatePermutation(cudaStream_t s, abx_bvh *t, int pred_kind, void const *preds, int64_t q,
                                 TempBuffer<uint32_t> &perm)
 {
-  TempBuffer<uint32_t> codes;
+  // The permutation only has to make neighbouring threads traverse neighbouring subtrees; the
+  // results do not depend on it.  Morton32 codes use 30 bits; ordering by the top
+  // kPredicateSortBits of them (ABX_QUERY_SORT_BITS overrides) costs one digit pass less than the
+  // reference's full sort and leaves cells far smaller than a warp's worth of queries unordered.
+  static int const sort_bits = [] {
+    char const *e = getenv("ABX_QUERY_SORT_BITS");
+    return e ? atoi(e) : kPredicateSortBits;
+  }();
+  TempBuffer<uint32_t> codes, codes_alt, perm_alt;
   ABX_TRY(codes.alloc(q, s));
+  ABX_TRY(codes_alt.alloc(q, s));
   ABX_TRY(perm.alloc(q, s));
+  ABX_TRY(perm_alt.alloc(q, s));
   ABX_TRY(morton32(s, pred_kind, preds, q, t->bounds_dev, codes.ptr));
-  ABX_TRY(sortPairsU32(s, codes.ptr, perm.ptr, q, true));
+  uint32_t *kb[2] = {codes.ptr, codes_alt.ptr};
+  uint32_t *vb[2] = {perm.ptr, perm_alt.ptr};
+  int cur = 0;
+  ABX_TRY(sortPairsU32DB(s, kb, vb, &cur, q, true, 30, sort_bits >= 30 ? 0 : sort_bits));
+  if (cur != 0)
+    std::swap(perm.ptr, perm_alt.ptr);
   return ABX_OK;
 }
 

@@ -63,13 +63,22 @@ __device__ __forceinline__ void stVolatile(unsigned *p, unsigned v)
 }
 
 // ---- 1. histograms of every digit in one read of the keys -------------------
-template <typename KeyT, int BITS, int PASSES>
+// digit p of a key is (key >> shifts.s[p]) & (2^BITS - 1); windows may overlap (an LSD pass over
+// a window that re-covers already sorted bits is harmless) which lets the driver place the
+// digits wherever the key's significant bits are
+struct SortShifts
+{
+  int s[8];
+};
+
+template <typename KeyT, int BITS, int MAXP>
 __global__ void __launch_bounds__(kSortThreads)
-    radixHistogramKernel(KeyT const *__restrict__ keys, int64_t n, unsigned *__restrict__ hist /*[PASSES][BINS]*/)
+    radixHistogramKernel(KeyT const *__restrict__ keys, int64_t n, SortShifts shifts, int npass,
+                         unsigned *__restrict__ hist /*[npass][BINS]*/)
 {
   constexpr int BINS = 1 << BITS;
-  __shared__ unsigned sh[PASSES * BINS];
-  for (int i = threadIdx.x; i < PASSES * BINS; i += kSortThreads)
+  __shared__ unsigned sh[MAXP * BINS];
+  for (int i = threadIdx.x; i < npass * BINS; i += kSortThreads)
     sh[i] = 0;
   __syncthreads();
   int64_t const stride = (int64_t)gridDim.x * kSortThreads;
@@ -77,11 +86,12 @@ __global__ void __launch_bounds__(kSortThreads)
   {
     KeyT k = keys[i];
 #pragma unroll
-    for (int p = 0; p < PASSES; ++p)
-      atomicAdd(&sh[p * BINS + digitOf(k, p * BITS, BINS - 1)], 1u);
+    for (int p = 0; p < MAXP; ++p)
+      if (p < npass)
+        atomicAdd(&sh[p * BINS + digitOf(k, shifts.s[p], BINS - 1)], 1u);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < PASSES * BINS; i += kSortThreads)
+  for (int i = threadIdx.x; i < npass * BINS; i += kSortThreads)
   {
     unsigned c = sh[i];
     if (c)
@@ -392,8 +402,9 @@ __global__ void __launch_bounds__(THREADS, MINB)
 }
 
 template <typename KeyT, int BITS, int THREADS, int ITEMS, int MINB, bool BALLOT, int DEBUG = 0>
-abx_status launchPasses(cudaStream_t s, int passes, KeyT *keys, KeyT *keys_alt, unsigned *vals, unsigned *vals_alt,
-                        int64_t n, bool iota_vals, unsigned *hist, unsigned *counters, unsigned *states, int tiles)
+abx_status launchPasses(cudaStream_t s, int passes, SortShifts const &shifts, KeyT *const keys[2],
+                        unsigned *const vals[2], int &cur, int64_t n, bool iota_vals, unsigned *hist,
+                        unsigned *counters, unsigned *states, int tiles)
 {
   constexpr int BINS = 1 << BITS;
   auto kernel = onesweepPassKernel<KeyT, BITS, THREADS, ITEMS, MINB, BALLOT, DEBUG>;
@@ -405,37 +416,39 @@ abx_status launchPasses(cudaStream_t s, int passes, KeyT *keys, KeyT *keys_alt, 
     ABX_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_set = true;
   }
-  KeyT *kin = keys, *kout = keys_alt;
-  unsigned *vin = vals, *vout = vals_alt;
   for (int p = 0; p < passes; ++p)
   {
     ABX_LAUNCH_TAGGED(sizeof(KeyT) == 8 ? "onesweepPassKernel<u64>" : "onesweepPassKernel<u32>", kernel, tiles,
-                      THREADS, smem, s, kin, kout, (p == 0 && iota_vals) ? (unsigned const *)nullptr : vin, vout,
-                      (unsigned)n, p * BITS, hist + (size_t)p * BINS, states + (size_t)p * tiles * BINS, counters + p);
-    std::swap(kin, kout);
-    std::swap(vin, vout);
+                      THREADS, smem, s, keys[cur], keys[cur ^ 1],
+                      (p == 0 && iota_vals) ? (unsigned const *)nullptr : vals[cur], vals[cur ^ 1], (unsigned)n,
+                      shifts.s[p], hist + (size_t)p * BINS, states + (size_t)p * tiles * BINS, counters + p);
+    cur ^= 1;
   }
   return ABX_OK;
 }
 
-// tile shapes: {threads, items, min blocks/SM}; ABX_SORT_CONFIG picks one (tuning aid)
-template <typename KeyT, int BITS, int PASSES>
-abx_status sortPairsImpl(cudaStream_t s, KeyT *keys, unsigned *vals, int64_t n, bool iota_vals)
+inline int sortConfig(bool wide)
 {
-  constexpr int BINS = 1 << BITS;
-  static_assert(PASSES % 2 == 0, "ping-pong must end in the caller's buffers");
-  if (n <= 0)
-    return ABX_OK;
-  if (n >= (int64_t)kValueMask)
-  {
-    setError("sort: n must be < 2^30");
-    return ABX_ERR_ARG;
-  }
   static int const config = [] {
     char const *e = getenv("ABX_SORT_CONFIG");
     return e ? atoi(e) : -1;
   }();
-  int const cfg = config >= 0 ? config : (sizeof(KeyT) == 8 ? kDefaultConfig64 : kDefaultConfig32);
+  return config >= 0 ? config : (wide ? kDefaultConfig64 : kDefaultConfig32);
+}
+
+// Stable LSD passes over the given digit windows (lowest first).  keys[cur]/vals[cur] hold the
+// input (vals ignored when iota_vals) and, on return, the output; every pass flips cur.
+// tile shapes: {threads, items, min blocks/SM}; ABX_SORT_CONFIG picks one (tuning aid)
+template <typename KeyT>
+abx_status runPasses(cudaStream_t s, KeyT *const keys[2], unsigned *const vals[2], int &cur, int64_t n,
+                     bool iota_vals, SortShifts const &shifts, int passes)
+{
+  constexpr int BITS = 8;
+  constexpr int BINS = 1 << BITS;
+  constexpr int MAXP = 8;
+  if (passes <= 0)
+    return ABX_OK;
+  int const cfg = sortConfig(sizeof(KeyT) == 8);
   int tile_keys;
   switch (cfg)
   {
@@ -451,45 +464,219 @@ abx_status sortPairsImpl(cudaStream_t s, KeyT *keys, unsigned *vals, int64_t n, 
   default: tile_keys = 256 * 16; break;
   }
   int const tiles = divUp(n, tile_keys);
-  TempBuffer<KeyT> keys_alt;
-  TempBuffer<unsigned> vals_alt;
-  TempBuffer<unsigned> ctrl; // [PASSES*BINS hist][PASSES counters][PASSES * tiles * BINS states]
-  size_t const hist_words = (size_t)PASSES * BINS;
-  size_t const ctrl_words = hist_words + PASSES + (size_t)PASSES * tiles * BINS;
-  ABX_TRY(keys_alt.alloc(n, s));
-  ABX_TRY(vals_alt.alloc(n, s));
+  TempBuffer<unsigned> ctrl; // [passes*BINS hist][passes counters][passes * tiles * BINS states]
+  size_t const hist_words = (size_t)passes * BINS;
+  size_t const ctrl_words = hist_words + passes + (size_t)passes * tiles * BINS;
   ABX_TRY(ctrl.alloc(ctrl_words, s));
   ABX_CUDA_TRY(cudaMemsetAsync(ctrl.ptr, 0, ctrl_words * sizeof(unsigned), s));
   unsigned *hist = ctrl.ptr;
   unsigned *counters = ctrl.ptr + hist_words;
-  unsigned *states = counters + PASSES;
+  unsigned *states = counters + passes;
 
   int const hist_grid = (int)std::min<int64_t>(divUp(n, kSortThreads * 8), kNumSMs * 8);
   ABX_LAUNCH_TAGGED(sizeof(KeyT) == 8 ? "radixHistogramKernel<u64>" : "radixHistogramKernel<u32>",
-                    (radixHistogramKernel<KeyT, BITS, PASSES>), hist_grid, kSortThreads, 0, s, keys, n, hist);
-  ABX_LAUNCH((radixScanHistKernel<BITS>), PASSES, kSortThreads, 0, s, hist);
+                    (radixHistogramKernel<KeyT, BITS, MAXP>), hist_grid, kSortThreads, 0, s, keys[cur], n, shifts,
+                    passes, hist);
+  ABX_LAUNCH((radixScanHistKernel<BITS>), passes, kSortThreads, 0, s, hist);
 
-#define ABX_PASSES(T, I, M, B)                                                                                        \
-  return launchPasses<KeyT, BITS, T, I, M, B>(s, PASSES, keys, keys_alt.ptr, vals, vals_alt.ptr, n, iota_vals, hist,  \
-                                              counters, states, tiles)
+#define ABX_PASSES(T, I, M, B, D)                                                                                     \
+  return launchPasses<KeyT, BITS, T, I, M, B, D>(s, passes, shifts, keys, vals, cur, n, iota_vals, hist, counters,    \
+                                                 states, tiles)
   switch (cfg)
   {
-  case 1: ABX_PASSES(256, 8, 5, false);
-  case 2: ABX_PASSES(512, 8, 2, false);
-  case 3: ABX_PASSES(384, 12, 2, false);
-  case 4: ABX_PASSES(512, 12, 2, false);
-  case 5: ABX_PASSES(256, 16, 3, false);
-  case 6: ABX_PASSES(256, 16, 2, true);
-  case 7: ABX_PASSES(384, 12, 2, true);
-  case 8: ABX_PASSES(512, 8, 2, true);
-  case 9: ABX_PASSES(256, 8, 5, true);
-  case 10: return launchPasses<KeyT, BITS, 384, 12, 2, true, 1>(s, PASSES, keys, keys_alt.ptr, vals, vals_alt.ptr, n, iota_vals, hist, counters, states, tiles);
-  case 11: return launchPasses<KeyT, BITS, 384, 12, 2, true, 2>(s, PASSES, keys, keys_alt.ptr, vals, vals_alt.ptr, n, iota_vals, hist, counters, states, tiles);
-  case 12: return launchPasses<KeyT, BITS, 384, 12, 2, true, 3>(s, PASSES, keys, keys_alt.ptr, vals, vals_alt.ptr, n, iota_vals, hist, counters, states, tiles);
-  case 13: return launchPasses<KeyT, BITS, 384, 12, 2, true, 4>(s, PASSES, keys, keys_alt.ptr, vals, vals_alt.ptr, n, iota_vals, hist, counters, states, tiles);
-  default: ABX_PASSES(256, 16, 2, false);
+  case 1: ABX_PASSES(256, 8, 5, false, 0);
+  case 2: ABX_PASSES(512, 8, 2, false, 0);
+  case 3: ABX_PASSES(384, 12, 2, false, 0);
+  case 4: ABX_PASSES(512, 12, 2, false, 0);
+  case 5: ABX_PASSES(256, 16, 3, false, 0);
+  case 6: ABX_PASSES(256, 16, 2, true, 0);
+  case 7: ABX_PASSES(384, 12, 2, true, 0);
+  case 8: ABX_PASSES(512, 8, 2, true, 0);
+  case 9: ABX_PASSES(256, 8, 5, true, 0);
+  case 10: ABX_PASSES(384, 12, 2, true, 1);
+  case 11: ABX_PASSES(384, 12, 2, true, 2);
+  case 12: ABX_PASSES(384, 12, 2, true, 3);
+  case 13: ABX_PASSES(384, 12, 2, true, 4);
+  default: ABX_PASSES(256, 16, 2, false, 0);
   }
 #undef ABX_PASSES
+}
+
+// digit windows covering bits [lo, hi) of the key, lowest first; the top window is pulled down so
+// that it ends exactly at hi (overlapping its predecessor) rather than spilling over dead bits
+inline int coverBits(int lo, int hi, SortShifts &shifts)
+{
+  int const passes = (hi - lo + 7) / 8;
+  for (int p = 0; p < passes; ++p)
+    shifts.s[p] = std::max(lo, std::min(lo + 8 * p, hi - 8));
+  if (hi - lo < 8)
+    shifts.s[0] = std::max(0, hi - 8);
+  return passes;
+}
+
+// ---- 4. segment fix-up: finishes a sort whose top bits are already in place ----
+// After LSD passes over the top bits only, keys with the same prefix (key >> prefix_shift) form
+// a contiguous run in original order.  For n keys spread over >= n/8 prefixes the runs are a
+// handful of keys long, and ranking every key inside its run finishes the sort with one more
+// read+write of the data instead of one per remaining digit (5 of the 8 digits of a Morton64
+// key at 10M points).  Block b owns the runs that START in its tile of kFixTile positions; a run
+// longer than kMaxRun raises *overflow (the driver then redoes the sort with more LSD digits),
+// so the window a block needs is its tile plus kMaxRun keys.
+constexpr int kFixThreads = 256;
+constexpr int kFixItems = 8;
+constexpr int kFixTile = kFixThreads * kFixItems;
+constexpr int kMaxRun = 256;
+static_assert(kMaxRun <= kFixThreads, "one thread per halo position");
+
+template <typename KeyT>
+__global__ void __launch_bounds__(kFixThreads)
+    segmentFixKernel(KeyT const *__restrict__ keys_in, unsigned const *__restrict__ vals_in,
+                     KeyT *__restrict__ keys_out, unsigned *__restrict__ vals_out, unsigned n, int prefix_shift,
+                     unsigned *__restrict__ overflow)
+{
+  // sk[j] holds the key at position t0 - 1 + j
+  __shared__ KeyT sk[kFixTile + kMaxRun + 1];
+  unsigned const t0 = blockIdx.x * (unsigned)kFixTile;
+  unsigned const t1 = min(n, t0 + (unsigned)kFixTile);
+  unsigned const wend = min(n, t1 + (unsigned)kMaxRun); // window is [t0 - 1, wend)
+  int const count = (int)(wend - t0) + 1;
+  for (int j = threadIdx.x; j < count; j += kFixThreads)
+  {
+    KeyT k;
+    if (j == 0 && t0 == 0)
+      k = ~keys_in[0]; // position -1: a prefix that differs from key 0's
+    else
+      k = keys_in[t0 - 1 + j];
+    sk[j] = k;
+  }
+  __syncthreads();
+  int const last = count - 1; // sk index of the last loaded key
+  bool over = false;
+  // j = sk index of the key this thread places; tile positions, then the halo
+#pragma unroll 1
+  for (int it = 0; it <= kFixItems; ++it)
+  {
+    int const j = 1 + it * kFixThreads + (int)threadIdx.x;
+    bool const halo = it == kFixItems;
+    if (j > last || (!halo && j > (int)(t1 - t0)))
+      continue;
+    KeyT const mine = sk[j];
+    KeyT const pre = mine >> prefix_shift;
+    // run start: walk back to the first key with this prefix
+    int a = j;
+    while (a > 0 && (sk[a - 1] >> prefix_shift) == pre && j - a <= kMaxRun)
+      --a;
+    if (a == 0)
+      continue; // the run began in an earlier tile: that tile's block places it
+    if (halo && a > (int)(t1 - t0))
+      continue; // starts in the next tile
+    if (!halo && j - a > kMaxRun)
+    {
+      over = true;
+      continue;
+    }
+    int b = j + 1; // run end (exclusive)
+    while (b <= last && (sk[b] >> prefix_shift) == pre && b - a <= kMaxRun)
+      ++b;
+    if (b - a > kMaxRun || (b > last && t0 - 1 + (unsigned)b < n))
+    {
+      over = true;
+      continue;
+    }
+    int rank = 0;
+    for (int i = a; i < b; ++i)
+    {
+      KeyT const o = sk[i];
+      rank += (o < mine || (o == mine && i < j)) ? 1 : 0;
+    }
+    unsigned const src = t0 - 1 + (unsigned)j;
+    unsigned const dst = t0 - 1 + (unsigned)(a + rank);
+    keys_out[dst] = mine;
+    vals_out[dst] = vals_in[src];
+  }
+  if (__syncthreads_or(over) && threadIdx.x == 0)
+    atomicExch(overflow, 1u);
+}
+
+template <typename KeyT>
+abx_status sortPairsDB(cudaStream_t s, KeyT *const keys[2], unsigned *const vals[2], int &cur, int64_t n,
+                       bool iota_vals, int key_bits, int approx_top_bits, bool fixup)
+{
+  cur = 0;
+  if (n <= 0)
+    return ABX_OK;
+  if (n >= (int64_t)kValueMask)
+  {
+    setError("sort: n must be < 2^30");
+    return ABX_ERR_ARG;
+  }
+  int const width = (int)sizeof(KeyT) * 8;
+  key_bits = std::max(1, std::min(key_bits, width));
+  SortShifts shifts;
+  if (approx_top_bits > 0)
+  {
+    // ordering hint only (predicate sorting): the top bits of the key decide
+    int const passes = coverBits(std::max(0, key_bits - approx_top_bits), key_bits, shifts);
+    return runPasses<KeyT>(s, keys, vals, cur, n, iota_vals, shifts, passes);
+  }
+  int const full = (key_bits + 7) / 8;
+  // top digits such that the runs left to the fix-up average <= 8 keys
+  int top = 1;
+  while (top < full && ((int64_t)1 << (8 * top)) < n / 8)
+    ++top;
+  static int const fix_mode = [] {
+    char const *e = getenv("ABX_SORT_FIXUP");
+    return e ? atoi(e) : 1;
+  }();
+  TempBuffer<unsigned> flag;
+  while (fixup && fix_mode && top + 1 < full)
+  {
+    int const lo = key_bits - 8 * top;
+    int const passes = coverBits(lo, key_bits, shifts);
+    ABX_TRY(runPasses<KeyT>(s, keys, vals, cur, n, iota_vals, shifts, passes));
+    iota_vals = false;
+    if (!flag.ptr)
+      ABX_TRY(flag.alloc(1, s));
+    ABX_CUDA_TRY(cudaMemsetAsync(flag.ptr, 0, sizeof(unsigned), s));
+    ABX_LAUNCH_TAGGED("segmentFixKernel", (segmentFixKernel<KeyT>), divUp(n, kFixTile), kFixThreads, 0, s, keys[cur],
+                      vals[cur], keys[cur ^ 1], vals[cur ^ 1], (unsigned)n, lo, flag.ptr);
+    unsigned over = 0;
+    ABX_CUDA_TRY(cudaMemcpyAsync(&over, flag.ptr, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    ABX_CUDA_TRY(cudaStreamSynchronize(s));
+    if (!over)
+    {
+      cur ^= 1;
+      return ABX_OK;
+    }
+    // some prefix holds more than kMaxRun keys (clustered data): the fix-up output is void,
+    // keys[cur] is still sorted by its top bits in stable order; take two more digits
+    top += 2;
+  }
+  int const passes = coverBits(0, key_bits, shifts);
+  return runPasses<KeyT>(s, keys, vals, cur, n, iota_vals, shifts, passes);
+}
+
+// caller's buffers in and out
+template <typename KeyT>
+abx_status sortPairsInPlace(cudaStream_t s, KeyT *keys, unsigned *vals, int64_t n, bool iota_vals, int key_bits,
+                            bool fixup)
+{
+  if (n <= 0)
+    return ABX_OK;
+  TempBuffer<KeyT> keys_alt;
+  TempBuffer<unsigned> vals_alt;
+  ABX_TRY(keys_alt.alloc(n, s));
+  ABX_TRY(vals_alt.alloc(n, s));
+  KeyT *k[2] = {keys, keys_alt.ptr};
+  unsigned *v[2] = {vals, vals_alt.ptr};
+  int cur = 0;
+  ABX_TRY(sortPairsDB<KeyT>(s, k, v, cur, n, iota_vals, key_bits, 0, fixup));
+  if (cur != 0)
+  {
+    ABX_CUDA_TRY(cudaMemcpyAsync(keys, keys_alt.ptr, sizeof(KeyT) * n, cudaMemcpyDeviceToDevice, s));
+    ABX_CUDA_TRY(cudaMemcpyAsync(vals, vals_alt.ptr, sizeof(unsigned) * n, cudaMemcpyDeviceToDevice, s));
+  }
+  return ABX_OK;
 }
 
 // ---- exclusive scan (reduce-then-scan, three small launches) ----------------
@@ -581,13 +768,25 @@ __global__ void __launch_bounds__(kScanThreads)
 
 } // namespace
 
-abx_status sortPairsU64(cudaStream_t s, uint64_t *keys, uint32_t *vals, int64_t n, bool iota_vals)
+abx_status sortPairsU64(cudaStream_t s, uint64_t *keys, uint32_t *vals, int64_t n, bool iota_vals, int key_bits,
+                        bool fixup)
 {
-  return sortPairsImpl<unsigned long long, 8, 8>(s, (unsigned long long *)keys, vals, n, iota_vals);
+  return sortPairsInPlace<unsigned long long>(s, (unsigned long long *)keys, vals, n, iota_vals, key_bits, fixup);
 }
-abx_status sortPairsU32(cudaStream_t s, uint32_t *keys, uint32_t *vals, int64_t n, bool iota_vals)
+abx_status sortPairsU32(cudaStream_t s, uint32_t *keys, uint32_t *vals, int64_t n, bool iota_vals, int key_bits)
 {
-  return sortPairsImpl<unsigned, 8, 4>(s, keys, vals, n, iota_vals);
+  return sortPairsInPlace<unsigned>(s, keys, vals, n, iota_vals, key_bits, true);
+}
+abx_status sortPairsU64DB(cudaStream_t s, uint64_t *const keys[2], uint32_t *const vals[2], int *cur, int64_t n,
+                          bool iota_vals, int key_bits)
+{
+  return sortPairsDB<unsigned long long>(s, (unsigned long long *const *)keys, vals, *cur, n, iota_vals, key_bits, 0,
+                                         true);
+}
+abx_status sortPairsU32DB(cudaStream_t s, uint32_t *const keys[2], uint32_t *const vals[2], int *cur, int64_t n,
+                          bool iota_vals, int key_bits, int approx_top_bits)
+{
+  return sortPairsDB<unsigned>(s, keys, vals, *cur, n, iota_vals, key_bits, approx_top_bits, true);
 }
 
 // out has n_plus_1 entries: out[i] = in[0] + ... + in[i-1]; in[n_plus_1-1] is ignored.

@@ -53,6 +53,28 @@ def test_sort_u64(cuda, n):
     assert np.array_equal(p, order.astype(np.uint32))
 
 
+@pytest.mark.parametrize("n", [2, 300, 2047, 2048, 2049, 4097, 100_003, 3_000_001])
+@pytest.mark.parametrize("run", [0, 3, 200, 256, 257, 700])
+def test_sort_u64_prefix_runs(cuda, n, run):
+    """Top-digit passes + segment fix-up (abx_sort.cu): unique-ish keys take the fix-up path; runs of
+    keys sharing their top bits up to and beyond its 256-key limit exercise the escalation steps."""
+    rng = np.random.default_rng(n * 1000 + run)
+    keys = rng.integers(0, 2 ** 63, n, dtype=np.uint64)
+    if run and n > run:
+        # runs sharing the top 24 bits (low bits random, some exact duplicates), scattered over the input,
+        # one of them planted so that it straddles a fix-up tile boundary after sorting
+        for r in range(max(1, min(40, n // (4 * run)))):
+            pos = rng.choice(n, run, replace=False)
+            pre = np.uint64(0) if r == 0 else (keys[pos[0]] >> np.uint64(39)) << np.uint64(39)
+            low = rng.integers(0, 2 ** 39, run, dtype=np.uint64)
+            low[::5] = low[0]
+            keys[pos] = pre | low
+    k, p = cuda.sort_u64(keys)
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(p, order.astype(np.uint32))
+    assert np.array_equal(k, keys[order])
+
+
 @pytest.mark.parametrize("n", [1, 5, 4096, 300_001])
 def test_sort_u32(cuda, n):
     rng = np.random.default_rng(n + 1)
