@@ -270,21 +270,27 @@ __device__ __forceinline__ void loadNodeBox(Node64 const *nodes, int k, Box &b)
 // Apetrei's bottom-up construction (TreeConstruction.hpp:197-311): a node is finished
 // by the second of its two children to arrive at an atomic flag.
 //
-// B200 shape.  The LBVH is the Cartesian tree of the delta array (key = (delta, index),
-// larger key = closer to the root).  A block owns a chunk [a, b] of kHierThreads
-// consecutive sorted leaves; node p lies entirely inside the chunk iff a larger key
-// exists on both sides of p inside [a-1, b]:
-//     max(delta[a-1 .. p-1]) > delta(p)   and   max(delta[p+1 .. b]) >= delta(p).
-// hierarchyLocalKernel builds these "local" nodes (> 95 % of all nodes) in ROUNDS over a
-// shared-memory work queue: round 0 holds the chunk's leaves, every finished node is
-// pushed for the next round, so all rounds run with compact, fully populated warps
-// (the plain one-thread-per-leaf walk leaves 4-8 of 32 lanes alive after two levels).
-// Flags, boxes, ranges and deltas live in shared memory; no global atomics, no
-// device-scope fences.  A subtree whose parent is not local is appended to a pending
-// list; hierarchyGlobalKernel finishes those few nodes with the global CAS +
-// __threadfence protocol.
-constexpr int kHierThreads = 512;
-constexpr int kHierWarps = kHierThreads / 32;
+// B200 shape.  A node whose leaf range lies inside a window of consecutive sorted leaves
+// can be built from that window alone, and both of its children arrive at its flag from
+// inside the window; a node whose range leaves the window sees at most one arrival.  So
+// windows are processed independently and whatever is left with ONE arrival (or whose
+// parent slot is outside the window) is handed to the next, wider window:
+//   stage 1  one warp per 64 leaves, rounds over a warp-private work queue in shared
+//            memory, __syncwarp only: ~87 % of the nodes
+//   stage 2  warp 0 of the block over the block's W * 64 leaves: the maximal subtrees
+//            the warps left over (~12 per warp)
+//   stage 3  hierarchyGlobalKernel over the maximal subtrees of every block, with the
+//            reference's global CAS + fence protocol: ~4 % at W = 4
+// Measured at 10M points (scripts/time_build.py): W = 2: 0.59 + 0.25 ms (local + global),
+// W = 4: 0.57 + 0.16, W = 8: 0.67 + 0.10, W = 16: 0.75 + 0.09.
+// Rounds keep the warps fully populated (round r holds the nodes of height r; the plain
+// one-thread-per-leaf walk leaves 4-8 of 32 lanes alive after two levels), flags, boxes,
+// ranges and deltas live in shared memory, and stages 1-2 need no device-scope fence and
+// only two block barriers.
+constexpr int kHierWarpLeaves = 64; // stage-1 window
+constexpr int kHierWarpsDefault = 4; // warps per block: the stage-2 window is W * 64 leaves (ABX_HIER_WARPS overrides)
+constexpr int kFlagFree = -1;                            // no child has arrived
+constexpr int kFlagDone = -3;                            // both children arrived, node written
 
 template <int KIND>
 struct LeafFloats
@@ -299,15 +305,6 @@ struct PendingNode
   float box[6];
 };
 
-__device__ __forceinline__ long long shflUp64(long long v, int o)
-{
-  return __shfl_up_sync(0xffffffffu, v, o);
-}
-__device__ __forceinline__ long long shflDown64(long long v, int o)
-{
-  return __shfl_down_sync(0xffffffffu, v, o);
-}
-
 __device__ __forceinline__ void writeNode(Node64 *nodes, int k, Box const &L, int lref, Box const &R, int rref,
                                           int range_left, int range_right)
 {
@@ -318,274 +315,330 @@ __device__ __forceinline__ void writeNode(Node64 *nodes, int k, Box const &L, in
   f[3] = make_float4(R.hi[0], R.hi[1], R.hi[2], __int_as_float(range_right));
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(kHierThreads)
+template <int KIND, int W>
+struct HierSmem
+{
+  static constexpr int LF = LeafFloats<KIND>::value;
+  static constexpr int T = W * kHierWarpLeaves;
+  long long delta[T + 1]; // delta[j] = delta(a - 1 + j)
+  int flag[T];            // per parent p - a: kFlagFree, kFlagDone, or the range end of the one child so far
+  float node[T][6];       // box of a finished local node (by Karras index - a)
+  short rl[T], rr[T];     // its range, relative to a
+  float leaf[T][LF];      // leaf boxes of the chunk
+  unsigned perm[T];
+  unsigned short wqueue[W][2][kHierWarpLeaves];
+  unsigned short bqueue[2][T];
+  unsigned short pend[T]; // items handed to the global kernel
+  int bqn;
+  int pn;
+  unsigned pbase;
+};
+
+// item < T: leaf (chunk position); item >= T: finished local node (Karras index - a + T)
+template <int KIND, int W>
+__device__ __forceinline__ void loadItem(HierSmem<KIND, W> const &sm, int a, int item, int &range_left,
+                                         int &range_right, int &ref, Box &box)
+{
+  constexpr int LF = LeafFloats<KIND>::value;
+  constexpr int T = W * kHierWarpLeaves;
+  if (item < T)
+  {
+    range_left = range_right = a + item;
+    ref = refLeaf(sm.perm[item]);
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+    {
+      box.lo[d] = sm.leaf[item][d];
+      box.hi[d] = sm.leaf[item][LF == 6 ? 3 + d : d];
+    }
+  }
+  else
+  {
+    int const kk = item - T;
+    range_left = a + sm.rl[kk];
+    range_right = a + sm.rr[kk];
+    ref = a + kk;
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+    {
+      box.lo[d] = sm.node[kk][d];
+      box.hi[d] = sm.node[kk][3 + d];
+    }
+  }
+}
+
+// One Apetrei step for `item` against the parent slots [slot_lo, slot_hi) (chunk-relative).
+// Returns 0: nothing to forward (first child to arrive, or the root was written);
+//         1: second child: the parent was written and is returned in `next` for the next round;
+//         2: the parent's slot is outside the window: the caller hands `item` to the wider window.
+template <int KIND, int W>
+__device__ __forceinline__ int apetreiStep(HierSmem<KIND, W> &sm, int a, int item, int slot_lo, int slot_hi,
+                                           Node64 *nodes, float *bounds6, int &next)
+{
+  constexpr int T = W * kHierWarpLeaves;
+  // the first child to arrive only needs its range; boxes are loaded by the second
+  int range_left, range_right;
+  if (item < T)
+    range_left = range_right = a + item;
+  else
+  {
+    range_left = a + sm.rl[item - T];
+    range_right = a + sm.rr[item - T];
+  }
+  long long delta_left = sm.delta[range_left - a];       // delta(range_left - 1)
+  long long delta_right = sm.delta[range_right - a + 1]; // delta(range_right)
+  bool const is_left_child = delta_right < delta_left;
+  int const apetrei_parent = is_left_child ? range_right : range_left - 1;
+  int const lp = apetrei_parent - a;
+  if (lp < slot_lo || lp >= slot_hi)
+    return 2;
+  int const old = atomicCAS(&sm.flag[lp], kFlagFree, is_left_child ? range_left : range_right);
+  if (old == kFlagFree)
+    return 0;
+  // second to arrive: the sibling's record was written in an earlier round
+  sm.flag[lp] = kFlagDone;
+  int sib_item;
+  if (is_left_child)
+  {
+    range_right = old;
+    int const sib_pos = apetrei_parent + 1;
+    sib_item = (sib_pos == range_right) ? sib_pos - a : T + sib_pos - a;
+    delta_right = sm.delta[range_right - a + 1];
+  }
+  else
+  {
+    range_left = old;
+    int const sib_pos = apetrei_parent;
+    sib_item = (sib_pos == range_left) ? sib_pos - a : T + sib_pos - a;
+    delta_left = sm.delta[range_left - a];
+  }
+  Box box, sib;
+  int ref, sib_ref, unused_l, unused_r;
+  loadItem<KIND, W>(sm, a, item, unused_l, unused_r, ref, box);
+  loadItem<KIND, W>(sm, a, sib_item, unused_l, unused_r, sib_ref, sib);
+  int const karras_parent = delta_right < delta_left ? range_right : range_left;
+  if (is_left_child)
+    writeNode(nodes, karras_parent, box, ref, sib, sib_ref, range_left, range_right);
+  else
+    writeNode(nodes, karras_parent, sib, sib_ref, box, ref, range_left, range_right);
+  boxUnion(box, sib);
+  if (karras_parent == 0)
+  {
+    // root (the whole tree fits in one chunk): TreeConstruction.hpp:108-113
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+    {
+      bounds6[d] = box.lo[d];
+      bounds6[3 + d] = box.hi[d];
+    }
+    return 0;
+  }
+  int const kk = karras_parent - a; // a local node's Karras index is an end of its range
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+  {
+    sm.node[kk][d] = box.lo[d];
+    sm.node[kk][3 + d] = box.hi[d];
+  }
+  sm.rl[kk] = (short)(range_left - a);
+  sm.rr[kk] = (short)(range_right - a);
+  next = T + kk;
+  return 1;
+}
+
+// the child that arrived alone at parent slot s (flag value f): its item id
+template <int W>
+__device__ __forceinline__ int loneChildItem(int a, int s, int f)
+{
+  constexpr int T = W * kHierWarpLeaves;
+  int const p = a + s;
+  if (f <= p) // left child, range [f, p]: leaf p or internal node p
+    return f == p ? s : T + s;
+  return f == p + 1 ? s + 1 : T + s + 1; // right child, range [p + 1, f]
+}
+
+// Rounds of one warp over `queue` (two buffers of `cap` items) against the slots [slot_lo, slot_hi).
+// count0 items are taken from first0 + idx in the first round (leaves) when queue_init is false.
+// Items whose parent slot is outside the window go to out[] (counter *out_n, shared by several warps).
+template <int KIND, int W>
+__device__ __forceinline__ void warpRounds(HierSmem<KIND, W> &sm, int a, unsigned short *q0, unsigned short *q1,
+                                           int count, bool leaves_first, int first0, int slot_lo, int slot_hi,
+                                           unsigned short *out, int *out_n, Node64 *nodes, float *bounds6)
+{
+  int const lane = threadIdx.x & 31;
+  unsigned const lt = (1u << lane) - 1u;
+  unsigned short *cur = q0, *nxt = q1;
+  while (count > 0)
+  {
+    int produced = 0;
+    for (int base = 0; base < count; base += 32)
+    {
+      int const idx = base + lane;
+      int r = 0, next = 0, item = 0;
+      if (idx < count)
+      {
+        item = leaves_first ? first0 + idx : (int)cur[idx];
+        r = apetreiStep<KIND, W>(sm, a, item, slot_lo, slot_hi, nodes, bounds6, next);
+      }
+      unsigned const m1 = __ballot_sync(0xffffffffu, r == 1);
+      if (r == 1)
+        nxt[produced + __popc(m1 & lt)] = (unsigned short)next;
+      produced += __popc(m1);
+      unsigned const m2 = __ballot_sync(0xffffffffu, r == 2);
+      if (m2)
+      {
+        int ob = 0;
+        if (lane == 0)
+          ob = atomicAdd(out_n, __popc(m2));
+        ob = __shfl_sync(0xffffffffu, ob, 0);
+        if (r == 2)
+          out[ob + __popc(m2 & lt)] = (unsigned short)item;
+      }
+    }
+    __syncwarp();
+    unsigned short *t = cur;
+    cur = nxt;
+    nxt = t;
+    count = produced;
+    leaves_first = false;
+  }
+}
+
+// after the rounds: slots [slot_lo, slot_hi) that saw exactly one child hand that child to out[]
+template <int KIND, int W>
+__device__ __forceinline__ void collectLoneChildren(HierSmem<KIND, W> &sm, int a, int slot_lo, int slot_hi, bool reset,
+                                                    unsigned short *out, int *out_n)
+{
+  int const lane = threadIdx.x & 31;
+  unsigned const lt = (1u << lane) - 1u;
+  for (int base = slot_lo; base < slot_hi; base += 32)
+  {
+    int const sidx = base + lane;
+    int f = kFlagFree;
+    if (sidx < slot_hi)
+      f = sm.flag[sidx];
+    bool const lone = f != kFlagFree && f != kFlagDone;
+    unsigned const m = __ballot_sync(0xffffffffu, lone);
+    if (m)
+    {
+      int ob = 0;
+      if (lane == 0)
+        ob = atomicAdd(out_n, __popc(m));
+      ob = __shfl_sync(0xffffffffu, ob, 0);
+      if (lone)
+      {
+        out[ob + __popc(m & lt)] = (unsigned short)loneChildItem<W>(a, sidx, f);
+        if (reset)
+          sm.flag[sidx] = kFlagFree;
+      }
+    }
+  }
+}
+
+template <int KIND, int W>
+__global__ void __launch_bounds__(W * 32)
     hierarchyLocalKernel(int n, unsigned long long const *__restrict__ codes, unsigned const *__restrict__ perm,
                          float const *__restrict__ prims, Node64 *nodes, float4 *leaf_box, float4 *leaf_tri,
                          PendingNode *pending, unsigned *pending_count, float *bounds6)
 {
   constexpr int LF = LeafFloats<KIND>::value;
-  constexpr int T = kHierThreads;
-  __shared__ long long sdelta[T + 1]; // sdelta[j] = delta(a - 1 + j)
-  __shared__ int sflag[T];            // per parent p-a: -1 untouched, -2 not local, else a range end
-  __shared__ float snode[T][6];       // box of a finished local node (by Karras index - a)
-  __shared__ short srl[T], srr[T];    // its range, relative to a
-  __shared__ float sleaf[T][LF];      // leaf boxes of the chunk
-  __shared__ unsigned sperm[T];
-  __shared__ unsigned short squeue[2][T];
-  __shared__ unsigned short spend[T]; // items handed to the global kernel
-  __shared__ int sqn[2];
-  __shared__ int spn;
-  __shared__ unsigned spbase;
-  __shared__ long long swarp[2][kHierWarps];
+  constexpr int T = W * kHierWarpLeaves;
+  constexpr int kHierThreads = W * 32;
+  extern __shared__ __align__(16) unsigned char hier_smem_raw[];
+  HierSmem<KIND, W> &sm = *reinterpret_cast<HierSmem<KIND, W> *>(hier_smem_raw);
 
-  int const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int const tid = threadIdx.x, warp = tid >> 5;
   int const a = blockIdx.x * T;
   int const cn = min(T, n - a); // leaves in this chunk
   int const n_int = n - 1;
-  int const i = a + tid;
-  bool const active = tid < cn;
 
-  if (active)
-  {
-    unsigned const orig = perm[i];
-    Box const box = primBox<KIND>(prims, orig);
-    if (KIND == ABX_PRIM_POINT3F)
-      leaf_box[i] = make_float4(box.lo[0], box.lo[1], box.lo[2], __uint_as_float(orig));
-    else
-    {
-      leaf_box[2 * (size_t)i] = make_float4(box.lo[0], box.lo[1], box.lo[2], __uint_as_float(orig));
-      leaf_box[2 * (size_t)i + 1] = make_float4(box.hi[0], box.hi[1], box.hi[2], 0.f);
-    }
-    if (KIND == ABX_PRIM_TRI3F)
-    {
-      float const *t = prims + 9 * (size_t)orig;
-      leaf_tri[3 * (size_t)i] = make_float4(t[0], t[1], t[2], 0.f);
-      leaf_tri[3 * (size_t)i + 1] = make_float4(t[3], t[4], t[5], 0.f);
-      leaf_tri[3 * (size_t)i + 2] = make_float4(t[6], t[7], t[8], 0.f);
-    }
+  // leaf records out, leaf boxes / permutation / deltas / flags into shared memory
 #pragma unroll
-    for (int d = 0; d < 3; ++d)
-      sleaf[tid][d] = box.lo[d];
-    if (LF == 6)
+  for (int k = 0; k < T / kHierThreads; ++k)
+  {
+    int const j = k * kHierThreads + tid;
+    int const i = a + j;
+    if (j < cn)
     {
+      unsigned const orig = perm[i];
+      Box const box = primBox<KIND>(prims, orig);
+      if (KIND == ABX_PRIM_POINT3F)
+        leaf_box[i] = make_float4(box.lo[0], box.lo[1], box.lo[2], __uint_as_float(orig));
+      else
+      {
+        leaf_box[2 * (size_t)i] = make_float4(box.lo[0], box.lo[1], box.lo[2], __uint_as_float(orig));
+        leaf_box[2 * (size_t)i + 1] = make_float4(box.hi[0], box.hi[1], box.hi[2], 0.f);
+      }
+      if (KIND == ABX_PRIM_TRI3F)
+      {
+        float const *t = prims + 9 * (size_t)orig;
+        leaf_tri[3 * (size_t)i] = make_float4(t[0], t[1], t[2], 0.f);
+        leaf_tri[3 * (size_t)i + 1] = make_float4(t[3], t[4], t[5], 0.f);
+        leaf_tri[3 * (size_t)i + 2] = make_float4(t[6], t[7], t[8], 0.f);
+      }
 #pragma unroll
       for (int d = 0; d < 3; ++d)
-        sleaf[tid][LF == 6 ? 3 + d : d] = box.hi[d];
+        sm.leaf[j][d] = box.lo[d];
+      if (LF == 6)
+      {
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+          sm.leaf[j][LF == 6 ? 3 + d : d] = box.hi[d];
+      }
+      sm.perm[j] = orig;
+      sm.delta[j + 1] = deltaOf(codes, i, n_int);
     }
-    sperm[tid] = orig;
-    sdelta[tid + 1] = deltaOf(codes, i, n_int);
+    else
+      sm.delta[j + 1] = LLONG_MAX;
+    sm.flag[j] = kFlagFree;
   }
-  else
-    sdelta[tid + 1] = LLONG_MAX;
   if (tid == 0)
   {
-    sdelta[0] = deltaOf(codes, a - 1, n_int);
-    sqn[0] = 0;
-    sqn[1] = 0;
-    spn = 0;
+    sm.delta[0] = deltaOf(codes, a - 1, n_int);
+    sm.bqn = 0;
+    sm.pn = 0;
   }
   __syncthreads();
 
-  // locality of parent p = a + tid (needs leaves p and p+1 in the chunk)
+  // stage 1: every warp builds what lies inside its 64 leaves
   {
-    long long const mine = sdelta[tid + 1];
-    long long pre = sdelta[tid]; // inclusive prefix max of sdelta[0..tid]
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1)
-    {
-      long long t = shflUp64(pre, o);
-      if (lane >= o)
-        pre = max(pre, t);
-    }
-    long long suf = (tid + 2 <= cn) ? sdelta[tid + 2] : LLONG_MIN; // inclusive suffix max of sdelta[t+2], t >= tid
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1)
-    {
-      long long t = shflDown64(suf, o);
-      if (lane + o < 32)
-        suf = max(suf, t);
-    }
-    if (lane == 31)
-      swarp[0][warp] = pre;
-    if (lane == 0)
-      swarp[1][warp] = suf;
-    __syncthreads();
-    for (int w = 0; w < warp; ++w)
-      pre = max(pre, swarp[0][w]);
-    for (int w = warp + 1; w < kHierWarps; ++w)
-      suf = max(suf, swarp[1][w]);
-    bool const in_chunk = tid + 1 < cn;
-    bool const local = in_chunk && (pre > mine) && (suf >= mine);
-    sflag[tid] = local ? -1 : -2;
+    int const w0 = warp * kHierWarpLeaves;
+    int const wcount = max(0, min(kHierWarpLeaves, cn - w0));
+    // parent slot s needs leaves s and s + 1 in the window
+    int const slot_lo = w0, slot_hi = w0 + max(wcount - 1, 0);
+    warpRounds<KIND, W>(sm, a, sm.wqueue[warp][0], sm.wqueue[warp][1], wcount, true, w0, slot_lo, slot_hi, sm.bqueue[0],
+                     &sm.bqn, nodes, bounds6);
+    collectLoneChildren<KIND, W>(sm, a, slot_lo, slot_hi, true, sm.bqueue[0], &sm.bqn);
   }
   __syncthreads();
 
-  // rounds over the work queue; item < T: leaf (chunk position), item >= T: finished
-  // local node (Karras index - a + T)
-  int cur = 0;
-  int count = cn; // round 0: one leaf per thread
-  bool first_round = true;
-  while (count > 0)
+  // stage 2: warp 0 joins the warps' leftovers inside the block's chunk
+  if (warp == 0)
   {
-    if (tid < count)
+    // the first round reads bqueue[0] and fills bqueue[1]; its out-of-chunk items go to pend[]
+    warpRounds<KIND, W>(sm, a, sm.bqueue[0], sm.bqueue[1], sm.bqn, false, 0, 0, cn - 1, sm.pend, &sm.pn, nodes,
+                     bounds6);
+    collectLoneChildren<KIND, W>(sm, a, 0, cn - 1, false, sm.pend, &sm.pn);
+    __syncwarp();
+    // stage 3 input: append this chunk's maximal subtrees to the pending list
+    int const pn_total = sm.pn;
+    unsigned pbase = 0;
+    if ((tid & 31) == 0 && pn_total)
+      pbase = atomicAdd(pending_count, (unsigned)pn_total);
+    pbase = __shfl_sync(0xffffffffu, pbase, 0);
+    for (int k = tid; k < pn_total; k += 32)
     {
-      int const item = first_round ? tid : (int)squeue[cur][tid];
-      int range_left, range_right, ref;
+      PendingNode pnode;
       Box box;
-      if (item < T)
-      {
-        range_left = range_right = a + item;
-        ref = refLeaf(sperm[item]);
-#pragma unroll
-        for (int d = 0; d < 3; ++d)
-        {
-          box.lo[d] = sleaf[item][d];
-          box.hi[d] = LF == 6 ? sleaf[item][LF == 6 ? 3 + d : d] : sleaf[item][d];
-        }
-      }
-      else
-      {
-        int const kk = item - T;
-        range_left = a + srl[kk];
-        range_right = a + srr[kk];
-        ref = a + kk;
-#pragma unroll
-        for (int d = 0; d < 3; ++d)
-        {
-          box.lo[d] = snode[kk][d];
-          box.hi[d] = snode[kk][3 + d];
-        }
-      }
-      long long delta_left = sdelta[range_left - a];       // delta(range_left - 1)
-      long long delta_right = sdelta[range_right - a + 1]; // delta(range_right)
-      bool const is_left_child = delta_right < delta_left;
-      int const apetrei_parent = is_left_child ? range_right : range_left - 1;
-      int const lp = apetrei_parent - a;
-      if (lp < 0 || lp >= cn - 1 || sflag[lp] == -2)
-      {
-        // parent straddles the chunk boundary: hand the subtree to the global kernel
-        // (written out at the end, one global atomic per block)
-        spend[atomicAdd(&spn, 1)] = (unsigned short)item;
-      }
-      else
-      {
-        int const old = atomicCAS(&sflag[lp], -1, is_left_child ? range_left : range_right);
-        if (old != -1)
-        {
-          // second to arrive: the sibling's record was written in an earlier round
-          int sib_pos;
-          bool sib_is_leaf;
-          if (is_left_child)
-          {
-            range_right = old;
-            sib_pos = apetrei_parent + 1;
-            sib_is_leaf = (sib_pos == range_right);
-            delta_right = sdelta[range_right - a + 1];
-          }
-          else
-          {
-            range_left = old;
-            sib_pos = apetrei_parent;
-            sib_is_leaf = (sib_pos == range_left);
-            delta_left = sdelta[range_left - a];
-          }
-          int const sl = sib_pos - a;
-          Box sib;
-          int sib_ref;
-          if (sib_is_leaf)
-          {
-#pragma unroll
-            for (int d = 0; d < 3; ++d)
-            {
-              sib.lo[d] = sleaf[sl][d];
-              sib.hi[d] = LF == 6 ? sleaf[sl][LF == 6 ? 3 + d : d] : sleaf[sl][d];
-            }
-            sib_ref = refLeaf(sperm[sl]);
-          }
-          else
-          {
-#pragma unroll
-            for (int d = 0; d < 3; ++d)
-            {
-              sib.lo[d] = snode[sl][d];
-              sib.hi[d] = snode[sl][3 + d];
-            }
-            sib_ref = sib_pos;
-          }
-          int const karras_parent = delta_right < delta_left ? range_right : range_left;
-          if (is_left_child)
-            writeNode(nodes, karras_parent, box, ref, sib, sib_ref, range_left, range_right);
-          else
-            writeNode(nodes, karras_parent, sib, sib_ref, box, ref, range_left, range_right);
-          boxUnion(box, sib);
-          if (karras_parent == 0)
-          {
-            // root (the whole tree fits in one chunk): TreeConstruction.hpp:108-113
-#pragma unroll
-            for (int d = 0; d < 3; ++d)
-            {
-              bounds6[d] = box.lo[d];
-              bounds6[3 + d] = box.hi[d];
-            }
-          }
-          else
-          {
-            int const kk = karras_parent - a; // a local node's Karras index is an end of its range
-#pragma unroll
-            for (int d = 0; d < 3; ++d)
-            {
-              snode[kk][d] = box.lo[d];
-              snode[kk][3 + d] = box.hi[d];
-            }
-            srl[kk] = (short)(range_left - a);
-            srr[kk] = (short)(range_right - a);
-            int const slot = atomicAdd(&sqn[cur ^ 1], 1);
-            squeue[cur ^ 1][slot] = (unsigned short)(T + kk);
-          }
-        }
-      }
-    }
-    __syncthreads();
-    cur ^= 1;
-    first_round = false;
-    count = sqn[cur];
-    __syncthreads();
-    if (tid == 0)
-      sqn[cur ^ 1] = 0;
-    __syncthreads();
-  }
-
-  // append this chunk's maximal local subtrees to the pending list
-  if (tid == 0)
-    spbase = spn ? atomicAdd(pending_count, (unsigned)spn) : 0u;
-  __syncthreads();
-  if (tid < spn)
-  {
-    int const item = spend[tid];
-    PendingNode pn;
-    if (item < T)
-    {
-      pn.range_left = pn.range_right = a + item;
-      pn.ref = refLeaf(sperm[item]);
+      loadItem<KIND, W>(sm, a, sm.pend[k], pnode.range_left, pnode.range_right, pnode.ref, box);
 #pragma unroll
       for (int d = 0; d < 3; ++d)
       {
-        pn.box[d] = sleaf[item][d];
-        pn.box[3 + d] = LF == 6 ? sleaf[item][LF == 6 ? 3 + d : d] : sleaf[item][d];
+        pnode.box[d] = box.lo[d];
+        pnode.box[3 + d] = box.hi[d];
       }
+      pending[pbase + k] = pnode;
     }
-    else
-    {
-      int const kk = item - T;
-      pn.range_left = a + srl[kk];
-      pn.range_right = a + srr[kk];
-      pn.ref = a + kk;
-#pragma unroll
-      for (int d = 0; d < 6; ++d)
-        pn.box[d] = snode[kk][d];
-    }
-    pending[spbase + tid] = pn;
   }
 }
 
@@ -863,6 +916,41 @@ static void destroyTree(abx_bvh *t)
   delete t;
 }
 
+template <int K, int W>
+abx_status launchHierarchyLocalW(cudaStream_t s, abx_bvh *t, void const *prims, PendingNode *pending,
+                                 unsigned *pending_count)
+{
+  static bool attr_set = false;
+  if (!attr_set)
+  {
+    ABX_CUDA_TRY(cudaFuncSetAttribute(hierarchyLocalKernel<K, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(HierSmem<K, W>)));
+    attr_set = true;
+  }
+  int const n = (int)t->n;
+  ABX_LAUNCH_TAGGED("hierarchyLocalKernel", (hierarchyLocalKernel<K, W>), divUp(n, W * kHierWarpLeaves), W * 32,
+                    sizeof(HierSmem<K, W>), s, n, (unsigned long long const *)t->codes, t->perm, (float const *)prims,
+                    t->nodes, t->leaf_box, t->leaf_tri, pending, pending_count, t->bounds_dev);
+  return ABX_OK;
+}
+
+template <int K>
+abx_status launchHierarchyLocal(cudaStream_t s, abx_bvh *t, void const *prims, PendingNode *pending,
+                                unsigned *pending_count)
+{
+  static int const warps = [] {
+    char const *e = getenv("ABX_HIER_WARPS");
+    return e ? atoi(e) : kHierWarpsDefault;
+  }();
+  switch (warps)
+  {
+  case 2: return launchHierarchyLocalW<K, 2>(s, t, prims, pending, pending_count);
+  case 4: return launchHierarchyLocalW<K, 4>(s, t, prims, pending, pending_count);
+  case 16: return launchHierarchyLocalW<K, 16>(s, t, prims, pending, pending_count);
+  default: return launchHierarchyLocalW<K, 8>(s, t, prims, pending, pending_count);
+  }
+}
+
 // codes (sorted) and perm must already be in bvh; fills nodes / leaf arrays / bounds
 abx_status buildHierarchy(cudaStream_t s, abx_bvh *t, void const *prims)
 {
@@ -875,9 +963,7 @@ abx_status buildHierarchy(cudaStream_t s, abx_bvh *t, void const *prims)
   ABX_TRY(pending_count.alloc(1, s));
   ABX_CUDA_TRY(cudaMemsetAsync(ranges.ptr, 0xff, sizeof(int) * (size_t)(n - 1), s));
   ABX_CUDA_TRY(cudaMemsetAsync(pending_count.ptr, 0, sizeof(unsigned), s));
-  ABX_DISPATCH_PRIM(t->kind, ABX_LAUNCH((hierarchyLocalKernel<K>), divUp(n, kHierThreads), kHierThreads, 0, s, n,
-                                        (unsigned long long const *)t->codes, t->perm, (float const *)prims, t->nodes,
-                                        t->leaf_box, t->leaf_tri, pending.ptr, pending_count.ptr, t->bounds_dev));
+  ABX_DISPATCH_PRIM(t->kind, ABX_TRY(launchHierarchyLocal<K>(s, t, prims, pending.ptr, pending_count.ptr)));
   // the local kernel's records are complete at the kernel boundary; the global kernel
   // only orders its own writes
   int const grid = std::min(divUp(n, 256 * 8), kNumSMs * 8);
