@@ -5,7 +5,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libabx.so")
+# ABX_LIBRARY: alternative build of the same library (tuning experiments), still no fallback
+LIB_PATH = os.environ.get("ABX_LIBRARY") or os.path.join(_HERE, "lib", "libabx.so")
 
 ABX_OK, ABX_ERR_SEARCH, ABX_ERR_CUDA, ABX_ERR_PRECISION, ABX_ERR_ARG = 0, 1, 2, 3, 4
 

@@ -9,6 +9,14 @@
 // the reference does not specify either.
 #include "abx_traverse.cuh"
 
+// minimum resident blocks per SM of the traversal kernels (register cap; tuning aid)
+#ifndef ABX_NEAREST_MINB
+#define ABX_NEAREST_MINB 12 // 40 registers: 10.6 ms at 10M / k = 10 (1: 48 regs 11.2 ms, 16: 32 regs 10.8 ms)
+#endif
+#ifndef ABX_SPATIAL_MINB
+#define ABX_SPATIAL_MINB 1
+#endif
+
 #include <cstdlib>
 
 namespace abx
@@ -25,40 +33,47 @@ enum
   MODE_COMPACT = 3  // staged results -> CRS rows; re-traverses only the queries that overflowed
 };
 constexpr int kPredicateSortBits = 24;
-constexpr int kSpatialBucketDefault = 4; // measured r01: 1 and 4 tie (5.85 ms stage), 8 is 6.34 ms
+constexpr int kSpatialVariantDefault = 1; // r01: immediate 5.85 ms; deferred (4,12) 4.89, (4,16) 4.99, (4,8) 4.93, (2,16) 5.75
 // Staging buffer of the single-traversal CRS path: slot-major ([slot][sorted query]),
 // so a warp writes/reads slot s of 32 neighbouring queries as one coalesced row.
 constexpr int kStage = 32;
 
-template <int PRED, int MODE, int LEAF_F4, bool TRI, int BUCKET>
-__global__ void __launch_bounds__(kThreads)
+// QCAP > 0: deferred leaf tests (traverseSpatialDeferred) with QCAP queue slots per thread
+template <int PRED, int MODE, int LEAF_F4, bool TRI, int BUCKET, int QCAP>
+__global__ void __launch_bounds__(kThreads, ABX_SPATIAL_MINB)
     spatialKernel(Node64 const *__restrict__ nodes, float4 const *__restrict__ leaf_box,
                   float4 const *__restrict__ leaf_tri, int n, float const *__restrict__ preds, int64_t q,
                   unsigned const *__restrict__ qperm, int limit, int32_t *__restrict__ counts,
                   int32_t const *__restrict__ offsets, uint32_t *__restrict__ indices, uint32_t *__restrict__ staging)
 {
+  __shared__ unsigned squeue[(QCAP > 0 ? QCAP : 1) * kThreads];
   int64_t const t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  if (t >= q)
+  bool active = t < q; // deferred form: the whole warp stays for the converged leaf phase
+  if (QCAP == 0 && !active)
     return;
-  int64_t const qi = qperm ? (int64_t)qperm[t] : t;
+  int64_t const qi = active ? (qperm ? (int64_t)qperm[t] : t) : 0;
   int64_t base = 0;
-  if (MODE == MODE_FILL || MODE == MODE_COMPACT)
+  if (active && (MODE == MODE_FILL || MODE == MODE_COMPACT))
     base = (int64_t)offsets[qi];
-  if (MODE == MODE_COMPACT)
+  if (active && MODE == MODE_COMPACT)
   {
     int const c = offsets[qi + 1] - (int)base;
     if (c <= kStage)
     {
       for (int s = 0; s < c; ++s)
         indices[base + s] = staging[(size_t)s * q + t];
-      return;
+      active = false;
+      if (QCAP == 0)
+        return;
     }
     // overflowed the staging slots: fall through to a filling traversal
   }
+  if (QCAP > 0 && MODE == MODE_COMPACT && !__any_sync(0xffffffffu, active))
+    return;
   Pred<PRED> pred;
   pred.load(preds, qi);
   int count = 0;
-  traverseSpatial<LEAF_F4, BUCKET>(nodes, leaf_box, pred, [&](unsigned orig, int pos) {
+  auto emit = [&](unsigned orig, int pos) {
     if (TRI && !triangleLeafTest<PRED>(pred, leaf_tri, pos))
       return false;
     if (MODE == MODE_FILL || MODE == MODE_COMPACT)
@@ -67,8 +82,14 @@ __global__ void __launch_bounds__(kThreads)
       staging[(size_t)count * q + t] = orig;
     ++count;
     return limit > 0 && count >= limit;
-  });
-  if (MODE == MODE_COUNT || MODE == MODE_STAGE)
+  };
+  bool const had_query = active;
+  if (QCAP > 0)
+    traverseSpatialDeferred<LEAF_F4, (BUCKET <= 4 ? BUCKET : 4), (QCAP > 0 ? QCAP : 3)>(nodes, leaf_box, pred, active,
+                                                                                        squeue, emit);
+  else
+    traverseSpatial<LEAF_F4, BUCKET>(nodes, leaf_box, pred, emit);
+  if (had_query && (MODE == MODE_COUNT || MODE == MODE_STAGE))
     counts[qi] = count;
 }
 
@@ -211,9 +232,18 @@ struct GlobalHeap
 // K > 0: register list of exactly K candidates (the first min(k, found) are
 // reported; K >= k).  K == 0: global heap with run-time k.
 constexpr int kNearestBucket = 1; // 1 = leaves only
+constexpr bool kPrefetch = false;
 
+// Candidate set of the K > 0 path: K (distance, index) slots per thread in shared memory,
+// UNSORTED, plus the position and value of the largest distance in registers.  The traversal
+// only ever needs "the k-th smallest so far" and "replace the worst": filling a slot costs two
+// stores, a replacement two stores and a K-slot rescan.  A sorted register list pays a K-step
+// compare-and-shift for every candidate, and ncu showed that code taking 40 % of the kernel's
+// issue slots with 3 of 32 lanes active.  The row is sorted once, at the end, with all lanes
+// converged.  Which of several equal largest distances is replaced is arbitrary: like the
+// reference's heap this only permutes candidates of equal distance.
 template <int K, int LEAF_F4, bool TRI>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, (K > 0 && K <= 16) ? ABX_NEAREST_MINB : 1)
     nearestKernel(Node64 const *__restrict__ nodes, float4 const *__restrict__ leaf_box,
                   float4 const *__restrict__ leaf_tri, int n, int prim_kind, float const *__restrict__ pts, int64_t q,
                   unsigned const *__restrict__ qperm, int k_uniform, int row_stride,
@@ -252,13 +282,16 @@ __global__ void __launch_bounds__(kThreads)
   }
 
   constexpr bool USE_REGS = K > 0;
-  RegList<USE_REGS ? K : 1> list;
+  constexpr int KS = USE_REGS ? K : 1;
+  __shared__ float set_d[KS * kThreads];
+  __shared__ unsigned set_i[KS * kThreads];
+  float *const my_d = set_d + threadIdx.x; // slot j at my_d[j * kThreads]: conflict-free across the warp
+  unsigned *const my_i = set_i + threadIdx.x;
+  int worst = 0; // slot holding the largest distance once the set is full
   GlobalHeap heap;
   heap.h = nullptr;
   heap.size = 0;
-  if (USE_REGS)
-    list.init();
-  else
+  if (!USE_REGS)
     heap.h = scratch + base;
   float radius2 = __int_as_float(0x7f800000);
   int found = 0;
@@ -274,9 +307,29 @@ __global__ void __launch_bounds__(kThreads)
     }
     if (USE_REGS)
     {
-      list.insert(d2, idx);
-      ++found;
-      radius2 = list.radius(); // +inf until K candidates are known
+      // d2 < radius2 here; radius2 stays +inf until K candidates are known
+      int const slot = found < KS ? found : worst;
+      my_d[slot * kThreads] = d2;
+      my_i[slot * kThreads] = idx;
+      if (found < KS)
+        ++found;
+      if (found == KS)
+      {
+        float m = my_d[0];
+        int p = 0;
+#pragma unroll
+        for (int j = 1; j < KS; ++j)
+        {
+          float const v = my_d[j * kThreads];
+          if (v > m)
+          {
+            m = v;
+            p = j;
+          }
+        }
+        radius2 = m;
+        worst = p;
+      }
     }
     else
     {
@@ -364,6 +417,8 @@ __global__ void __launch_bounds__(kThreads)
         float const fd = left_first ? dr : dl;
         int const fn = left_first ? rref : lref;
         stack[sp++] = ((unsigned long long)__float_as_uint(fd) << 32) | (unsigned)fn;
+        if (kPrefetch)
+          prefetchL2(nodes + fn);
       }
       node = left_first ? lref : rref;
       continue;
@@ -386,6 +441,12 @@ __global__ void __launch_bounds__(kThreads)
 
   if (USE_REGS)
   {
+    // sort the row: insertion into a register list, in slot order (all lanes are here together)
+    RegList<KS> list;
+    list.init();
+#pragma unroll 1
+    for (int j = 0; j < found; ++j)
+      list.insert(my_d[j * kThreads], my_i[j * kThreads]);
     int const m = min(min(found, k), USE_REGS ? K : 1);
 #pragma unroll
     for (int i = 0; i < (USE_REGS ? K : 1); ++i)
@@ -539,29 +600,25 @@ abx_status spatialLaunch(cudaStream_t s, abx_bvh *t, int pred_kind, void const *
                                             t->leaf_tri, t->kind, (float const *)preds, q, counts, offsets, indices));
     return ABX_OK;
   }
-  // leaf-run scans: ABX_SPATIAL_BUCKET = 1 (off), 4 or 8 (tuning aid; default below)
-  static int const bucket = [] {
-    char const *e = getenv("ABX_SPATIAL_BUCKET");
-    return e ? atoi(e) : kSpatialBucketDefault;
+  // tuning aid: ABX_SPATIAL_VARIANT picks (leaf-run size, deferred-queue slots); 0 slots = immediate leaf tests
+  static int const variant = [] {
+    char const *e = getenv("ABX_SPATIAL_VARIANT");
+    return e ? atoi(e) : kSpatialVariantDefault;
   }();
-#define ABX_SPATIAL_B(LF4, TRIFLAG, B)                                                                                \
-  ABX_DISPATCH_PRED(pred_kind, ABX_LAUNCH_TAGGED(tag, (spatialKernel<P, MODE, LF4, TRIFLAG, B>), grid, kThreads, 0,   \
-                                                 s, t->nodes, t->leaf_box, t->leaf_tri, n, (float const *)preds, q,   \
-                                                 qperm, limit, counts, offsets, indices, staging))
+#define ABX_SPATIAL_B(LF4, TRIFLAG, B, QC)                                                                            \
+  ABX_DISPATCH_PRED(pred_kind, ABX_LAUNCH_TAGGED(tag, (spatialKernel<P, MODE, LF4, TRIFLAG, B, QC>), grid, kThreads,  \
+                                                 0, s, t->nodes, t->leaf_box, t->leaf_tri, n, (float const *)preds,   \
+                                                 q, qperm, limit, counts, offsets, indices, staging))
 #define ABX_SPATIAL(LF4, TRIFLAG)                                                                                     \
   do                                                                                                                   \
   {                                                                                                                    \
-    if (bucket <= 1)                                                                                                   \
+    switch (variant)                                                                                                   \
     {                                                                                                                  \
-      ABX_SPATIAL_B(LF4, TRIFLAG, 1);                                                                                  \
-    }                                                                                                                  \
-    else if (bucket <= 4)                                                                                              \
-    {                                                                                                                  \
-      ABX_SPATIAL_B(LF4, TRIFLAG, 4);                                                                                  \
-    }                                                                                                                  \
-    else                                                                                                               \
-    {                                                                                                                  \
-      ABX_SPATIAL_B(LF4, TRIFLAG, 8);                                                                                  \
+    case 1: ABX_SPATIAL_B(LF4, TRIFLAG, 4, 12); break;                                                                 \
+    case 2: ABX_SPATIAL_B(LF4, TRIFLAG, 4, 16); break;                                                                 \
+    case 3: ABX_SPATIAL_B(LF4, TRIFLAG, 2, 16); break;                                                                 \
+    case 4: ABX_SPATIAL_B(LF4, TRIFLAG, 4, 8); break;                                                                  \
+    default: ABX_SPATIAL_B(LF4, TRIFLAG, 4, 0); break;                                                                 \
     }                                                                                                                  \
   } while (0)
   if (t->kind == ABX_PRIM_TRI3F)

@@ -334,6 +334,114 @@ __device__ __forceinline__ void traverseSpatial(Node64 const *__restrict__ nodes
   }
 }
 
+// ---- spatial traversal with deferred leaf tests ------------------------------------
+// ncu (profiles/r01_ncu_v2_summary.md) shows the immediate form above spending two thirds of
+// its issue slots on leaf tests and emits that run with 2-3 of 32 lanes: a lane reaches a leaf
+// at its own time and the rest of the warp waits.  Here a lane only RECORDS the sorted leaf
+// positions it has to test (a hit leaf child, or every leaf of a small subtree) in a per-thread
+// queue in shared memory and keeps walking internal nodes; when its walk ends (or the queue is
+// nearly full) the warp reconverges and all lanes test their queued leaves together, one queue
+// slot per iteration.  Same tests on the same leaves, hence the same result set; only the
+// order in which a query's results are emitted changes.
+// queue: QCAP rows of blockDim.x entries (row-major, so a warp's accesses are conflict-free).
+// Every lane of the warp must call this (active = false for lanes without a query).
+template <int LEAF_F4, int BUCKET, int QCAP, class P, class Emit>
+__device__ __forceinline__ void traverseSpatialDeferred(Node64 const *__restrict__ nodes,
+                                                        float4 const *__restrict__ leaf_box, P const &pred,
+                                                        bool active, unsigned *queue, Emit &&emit)
+{
+  // a queue entry is a run of sorted leaf positions: (first << 2) | (length - 1); n < 2^30
+  static_assert(BUCKET >= 1 && BUCKET <= 4, "run length must fit in two bits");
+  static_assert(QCAP >= 3, "one node visit (two runs) must fit");
+  int const stride = blockDim.x;
+  unsigned *const myq = queue + threadIdx.x;
+  int stack[kStackSize];
+  int sp = 0;
+  int node = 0;
+  int cnt = 0; // queued runs
+  int tot = 0; // queued leaves
+  while (true)
+  {
+    while (active && cnt + 2 <= QCAP)
+    {
+      float4 const *f = reinterpret_cast<float4 const *>(nodes + node);
+      float4 const a0 = __ldg(f), a1 = __ldg(f + 1), a2 = __ldg(f + 2), a3 = __ldg(f + 3);
+      int const lref = __float_as_int(a0.w), rref = __float_as_int(a1.w);
+      int const rl = __float_as_int(a2.w), rr = __float_as_int(a3.w);
+      bool hit_l = pred.box(a0, a1);
+      bool hit_r = pred.box(a2, a3);
+      int const l_len1 = (refIsLeaf(lref) ? rl : lref) - rl; // leaves of the left child - 1
+      int const r_len1 = rr - (refIsLeaf(rref) ? rr : rref);
+      if (hit_l && l_len1 < BUCKET)
+      {
+        myq[(cnt++) * stride] = ((unsigned)rl << 2) | (unsigned)l_len1;
+        tot += l_len1 + 1;
+        hit_l = false;
+      }
+      if (hit_r && r_len1 < BUCKET)
+      {
+        myq[(cnt++) * stride] = ((unsigned)(rr - r_len1) << 2) | (unsigned)r_len1;
+        tot += r_len1 + 1;
+        hit_r = false;
+      }
+      if (hit_l)
+      {
+        if (hit_r)
+          stack[sp++] = rref;
+        node = lref;
+      }
+      else if (hit_r)
+        node = rref;
+      else if (sp == 0)
+        active = false;
+      else
+        node = stack[--sp];
+    }
+    // the warp is converged here: every lane tests its queued leaves, one per iteration
+    int const maxt = __reduce_max_sync(0xffffffffu, tot);
+    int e = 0, o = 0;
+    unsigned cur = myq[0];
+    for (int k = 0; k < maxt; ++k)
+    {
+      if (k < tot)
+      {
+        int const j = (int)(cur >> 2) + o;
+        if (o == (int)(cur & 3u))
+        {
+          ++e;
+          o = 0;
+          cur = myq[min(e, QCAP - 1) * stride];
+        }
+        else
+          ++o;
+        bool hit;
+        unsigned orig;
+        if (LEAF_F4 == 1)
+        {
+          float4 const p = __ldg(leaf_box + j);
+          hit = pred.point(p);
+          orig = __float_as_uint(p.w);
+        }
+        else
+        {
+          float4 const l = __ldg(leaf_box + 2 * (size_t)j), h = __ldg(leaf_box + 2 * (size_t)j + 1);
+          hit = pred.box(l, h);
+          orig = __float_as_uint(l.w);
+        }
+        if (hit && emit(orig, j))
+        {
+          active = false; // early exit (CountUpToN): drop the rest of the queue
+          tot = 0;
+        }
+      }
+    }
+    cnt = 0;
+    tot = 0;
+    if (!__any_sync(0xffffffffu, active))
+      return;
+  }
+}
+
 // exact leaf test for triangle leaves (only sphere predicates are defined in 3-D:
 // Intersects.hpp:118-126)
 template <int PRED>
