@@ -13,7 +13,7 @@ namespace abx
 {
 
 static thread_local std::string t_last_error;
-int64_t g_launch_count = 0;
+std::atomic<int64_t> g_launch_count{0};
 
 void setError(std::string const &msg) { t_last_error = msg; }
 

@@ -232,7 +232,6 @@ struct GlobalHeap
 // K > 0: register list of exactly K candidates (the first min(k, found) are
 // reported; K >= k).  K == 0: global heap with run-time k.
 constexpr int kNearestBucket = 1; // 1 = leaves only
-constexpr bool kPrefetch = false;
 
 // Candidate set of the K > 0 path: K (distance, index) slots per thread in shared memory,
 // UNSORTED, plus the position and value of the largest distance in registers.  The traversal
@@ -417,8 +416,6 @@ __global__ void __launch_bounds__(kThreads, (K > 0 && K <= 16) ? ABX_NEAREST_MIN
         float const fd = left_first ? dr : dl;
         int const fn = left_first ? rref : lref;
         stack[sp++] = ((unsigned long long)__float_as_uint(fd) << 32) | (unsigned)fn;
-        if (kPrefetch)
-          prefetchL2(nodes + fn);
       }
       node = left_first ? lref : rref;
       continue;

@@ -321,6 +321,9 @@ def run_ours(args):
     hp_nearest = abx.nearest(h_queries, K_NEIGHBORS)
 
     pinned_out = {}
+    import concurrent.futures
+    e2e_pool = concurrent.futures.ThreadPoolExecutor(1)
+    space2 = abx.ExecutionSpace(torch.cuda.Stream())
 
     def e2e_step():
         if world > 1:
@@ -342,8 +345,12 @@ def run_ours(args):
             idx, off, kidx, koff = outs
             return int(off[-1]) + int(koff[-1]), idx.numel(), kidx.numel()
         bvh = abx.BoundingVolumeHierarchy(space, h_values)
+        space.fence()
+        # the two query batches are independent: issued from two host threads on two execution
+        # space instances (streams), so one batch's result copy overlaps the other's traversal
+        f_knn = e2e_pool.submit(lambda: bvh.query(space2, hp_nearest))
         idx, off = bvh.query(space, hp_spatial)
-        kidx, koff = bvh.query(space, hp_nearest)
+        kidx, koff = f_knn.result()
         # results are host tensors: touch them so the step really ends on the host
         return int(off[-1]) + int(koff[-1]), idx.numel(), kidx.numel()
 
@@ -423,7 +430,7 @@ def run_ours(args):
         "components": comp,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-                "api": "abx_bvh_build_host + abx_query_spatial_crs_host + abx_query_nearest_crs_host"},
+                "api": "abx_bvh_build_host + abx_query_spatial_crs_host + abx_query_nearest_crs_host (the two query calls from two host threads on two streams)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
