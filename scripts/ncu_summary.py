@@ -47,18 +47,24 @@ lines = ["# ncu --set full --clock-control none summary of `%s` (per-launch aver
          "| kernel | launches | time ms | DRAM rd MB | DRAM wr MB | DRAM GB/s | L2 hit % | L1 hit % | occ % | lanes/inst | "
          "warp inst M | SM % | regs | stall long_sb | short_sb | barrier | membar |",
          "|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
-traffic = {}
+tj = os.path.join(os.path.dirname(out), "traffic.json")
+traffic = json.load(open(tj)) if os.path.exists(tj) else {}  # merged: a partial profile only updates its kernels
+seen = set()
 for name, a in sorted(agg.items(), key=lambda kv: -kv[1].get("time", 0)):
     n = a["n"]
     g = lambda k: a.get(k, 0.0) / n
     t = g("time")
     bw = (g("dram_rd") + g("dram_wr")) / t / 1e9 if t else 0
-    traffic[name.split("<")[0]] = g("dram_rd") + g("dram_wr")
+    # keys: full name, and the bare kernel name for its longest-running instantiation (bench.py looks that up)
+    clean = name.replace("void ", "").replace("unnamed>::", "").strip()
+    traffic[clean] = g("dram_rd") + g("dram_wr")
+    if clean.split("<")[0] not in seen:
+        seen.add(clean.split("<")[0])
+        traffic[clean.split("<")[0]] = g("dram_rd") + g("dram_wr")
     lines.append("| %s | %d | %.4f | %.1f | %.1f | %.0f | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f | %d | %.2f | %.2f | %.2f | %.2f |"
                  % (name, n, t * 1e3, g("dram_rd") / 1e6, g("dram_wr") / 1e6, bw, g("L2hit%"), g("L1hit%"), g("occ%"),
                     g("lanes/inst"), g("warp_inst") / 1e6, g("SM%"), g("regs"), g("st_long_sb"), g("st_short_sb"),
                     g("st_barrier"), g("st_membar")))
 open(out, "w").write("\n".join(lines) + "\n")
-tj = os.path.join(os.path.dirname(out), "traffic.json")
 json.dump(traffic, open(tj, "w"), indent=1)
 print("\n".join(lines))
