@@ -118,16 +118,22 @@ __global__ void __launch_bounds__(kThreads)
 __global__ void finalizeLabelsKernel(int *labels, int *cluster_sizes, int n)
 {
   int const i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n)
-    return;
-  int next;
-  int vstat = ufLoad(labels, i);
-  int const old = vstat;
-  while (vstat > (next = ufLoad(labels, vstat)))
-    vstat = next;
-  if (vstat != old)
-    __stcg(labels + i, vstat);
-  atomicAdd(cluster_sizes + vstat, 1);
+  int vstat = -1;
+  if (i < n)
+  {
+    int next;
+    vstat = ufLoad(labels, i);
+    int const old = vstat;
+    while (vstat > (next = ufLoad(labels, vstat)))
+      vstat = next;
+    if (vstat != old)
+      __stcg(labels + i, vstat);
+  }
+  // one atomic per distinct cluster per warp: neighbouring (Morton-ordered) points mostly share
+  // their cluster, and a few giant clusters would otherwise serialise 10M atomics on a few words
+  unsigned const peers = __match_any_sync(0xffffffffu, vstat);
+  if (vstat >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1)
+    atomicAdd(cluster_sizes + vstat, __popc(peers));
 }
 
 __global__ void markNoiseKernel(int *labels, int const *__restrict__ cluster_sizes, int const *__restrict__ num_neigh,

@@ -26,8 +26,6 @@ namespace
 
 constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
-constexpr int kItems = 16;
-constexpr int kTile = kSortThreads * kItems; // 4096 keys per tile
 
 constexpr unsigned kFlagAgg = 1u << 30;
 constexpr unsigned kFlagIncl = 1u << 31;
@@ -551,6 +549,20 @@ __global__ void __launch_bounds__(kFixThreads)
   }
   __syncthreads();
   int const last = count - 1; // sk index of the last loaded key
+  // a run longer than kMaxRun that starts in this tile has two keys kMaxRun apart with the same
+  // prefix inside the window: found with one comparison per key; the block then gives up at once
+  // (the driver discards the output), instead of every key walking its run
+  {
+    bool long_run = false;
+    for (int j = 1 + (int)threadIdx.x; j + kMaxRun <= last; j += kFixThreads)
+      long_run |= (sk[j] >> prefix_shift) == (sk[j + kMaxRun] >> prefix_shift);
+    if (__syncthreads_or(long_run))
+    {
+      if (threadIdx.x == 0)
+        atomicExch(overflow, 1u);
+      return;
+    }
+  }
   bool over = false;
   // j = sk index of the key this thread places; tile positions, then the halo
 #pragma unroll 1
@@ -598,6 +610,53 @@ __global__ void __launch_bounds__(kFixThreads)
     atomicExch(overflow, 1u);
 }
 
+// Starting level of the fix-up path.  kSampleKeys keys taken at a regular stride are inserted
+// into a shared-memory hash set by their prefix (key >> shift[i]); out[i] = samples whose prefix
+// was already present.  Uniform-ish data gives ~0 at 10M keys, clustered data (most keys in few
+// prefixes: every run would overflow the fix-up) gives hundreds; a handful of long runs is
+// invisible here and is caught by the fix-up's own overflow flag.
+constexpr int kSampleKeys = 2048;
+constexpr int kSampleSlots = 4096;
+
+template <typename KeyT>
+__global__ void __launch_bounds__(1024)
+    prefixSampleKernel(KeyT const *__restrict__ keys, unsigned n, int shift0, int shift1, unsigned *__restrict__ out)
+{
+  __shared__ unsigned long long table[kSampleSlots];
+  __shared__ unsigned dup;
+  unsigned const stride = max(1u, n / (unsigned)kSampleKeys);
+  for (int level = 0; level < 2; ++level)
+  {
+    int const shift = level == 0 ? shift0 : shift1;
+    for (int i = threadIdx.x; i < kSampleSlots; i += blockDim.x)
+      table[i] = ~0ull;
+    if (threadIdx.x == 0)
+      dup = 0;
+    __syncthreads();
+    for (unsigned k = threadIdx.x; k < (unsigned)kSampleKeys && (unsigned long long)k * stride < n; k += blockDim.x)
+    {
+      unsigned long long const pre = (unsigned long long)(keys[(size_t)k * stride] >> shift);
+      unsigned slot = (unsigned)((pre * 0x9E3779B97F4A7C15ull) >> 52) & (kSampleSlots - 1);
+      while (true)
+      {
+        unsigned long long const old = atomicCAS(&table[slot], ~0ull, pre);
+        if (old == ~0ull)
+          break;
+        if (old == pre)
+        {
+          atomicAdd(&dup, 1u);
+          break;
+        }
+        slot = (slot + 1) & (kSampleSlots - 1);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+      out[level] = dup;
+    __syncthreads();
+  }
+}
+
 template <typename KeyT>
 abx_status sortPairsDB(cudaStream_t s, KeyT *const keys[2], unsigned *const vals[2], int &cur, int64_t n,
                        bool iota_vals, int key_bits, int approx_top_bits, bool fixup)
@@ -629,6 +688,27 @@ abx_status sortPairsDB(cudaStream_t s, KeyT *const keys[2], unsigned *const vals
     return e ? atoi(e) : 1;
   }();
   TempBuffer<unsigned> flag;
+  if (fixup && fix_mode && top + 1 < full && n >= 2 * kSampleKeys)
+  {
+    // pick the starting level from a sample (one small launch + one 8-byte read back)
+    ABX_TRY(flag.alloc(2, s));
+    int const lo0 = key_bits - 8 * top;
+    int const lo1 = std::max(0, key_bits - 8 * (top + 2));
+    ABX_LAUNCH_TAGGED("prefixSampleKernel", (prefixSampleKernel<KeyT>), 1, 1024, 0, s, keys[cur], (unsigned)n, lo0, lo1,
+                      flag.ptr);
+    unsigned dup[2] = {0, 0};
+    ABX_CUDA_TRY(cudaMemcpyAsync(dup, flag.ptr, sizeof(dup), cudaMemcpyDeviceToHost, s));
+    ABX_CUDA_TRY(cudaStreamSynchronize(s));
+    // two samples share a prefix with probability p => a key's run holds ~n*p keys; dup ~ m^2/2 * p.
+    // Runs of ~16 keys on average are where the 256-key limit starts to be hit on clustered clouds
+    // (GanTao at 10M: the 40-bit level sampled below 64 and still overflowed).
+    double const m = (double)std::min<int64_t>(kSampleKeys, n);
+    unsigned const limit = (unsigned)std::max(4.0, 16.0 * m * m / 2.0 / (double)n);
+    if (dup[0] > limit)
+      top += 2;
+    if (dup[0] > limit && dup[1] > limit)
+      top = full; // plain LSD
+  }
   while (fixup && fix_mode && top + 1 < full)
   {
     int const lo = key_bits - 8 * top;
@@ -636,7 +716,7 @@ abx_status sortPairsDB(cudaStream_t s, KeyT *const keys[2], unsigned *const vals
     ABX_TRY(runPasses<KeyT>(s, keys, vals, cur, n, iota_vals, shifts, passes));
     iota_vals = false;
     if (!flag.ptr)
-      ABX_TRY(flag.alloc(1, s));
+      ABX_TRY(flag.alloc(2, s));
     ABX_CUDA_TRY(cudaMemsetAsync(flag.ptr, 0, sizeof(unsigned), s));
     ABX_LAUNCH_TAGGED("segmentFixKernel", (segmentFixKernel<KeyT>), divUp(n, kFixTile), kFixThreads, 0, s, keys[cur],
                       vals[cur], keys[cur ^ 1], vals[cur ^ 1], (unsigned)n, lo, flag.ptr);

@@ -475,16 +475,21 @@ def run_dbscan(args):
                 labels = abx.dbscan(space, d, eps, minpts, params)
             torch.cuda.synchronize()
             e0, e1 = ev(), ev()
+            abx.profile_enable(True)
             e0.record()
             for _ in range(args.steps):
                 labels = abx.dbscan(space, d, eps, minpts, params)
             e1.record()
             torch.cuda.synchronize()
+            prof = abx.profile_report()
+            abx.profile_enable(False)
             ms = e0.elapsed_time(e1) / args.steps
             lab = labels.cpu().numpy()
             res["%s_minpts%d" % (iname, minpts)] = {"ms": ms, "Mpoints_s": n / ms / 1e3,
                                                    "clusters": int(len(np.unique(lab[lab >= 0]))),
-                                                   "noise": int((lab < 0).sum())}
+                                                   "noise": int((lab < 0).sum()),
+                                                   "kernels_ms_per_call": {k: round(t / args.steps, 3)
+                                                                           for k, c, t in prof[:8]}}
     ns = min(n, args.cpu_sample * 2)
     t0 = time.time()
     ref = oracle.dbscan(pts[:ns], eps, 5, 1, 0)
