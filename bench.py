@@ -452,10 +452,64 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_dbscan_distributed(args, world, rank, local_rank):
+    """`--workload dbscan --gpus N` (N > 1): the distributed DBSCAN (halo exchange + label merge) with one
+    GanTao cloud of n points per rank, rank r's cloud shifted by r * L along x (touching slabs), weak scaling."""
+    import torch
+    import torch.distributed as dist
+
+    import arborx_b200 as abx
+    from arborx_b200.distributed_dbscan import dbscan as dist_dbscan
+    from tests import clouds
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n, eps = args.n, 200.0
+    pts = clouds.gan_tao(3 + rank, n)
+    pts[:, 0] += np.float32(rank * 1.0e6)
+    space = abx.ExecutionSpace()
+    d = torch.from_numpy(pts).cuda()
+    res = {}
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    for impl, iname, minpts in ((1, "densebox", 5), (0, "fdbscan", 2)):
+        params = abx.DBSCANParameters(impl, 0)
+        for _ in range(max(1, args.warmup)):
+            labels = dist_dbscan(dist.group.WORLD, space, d, eps, minpts, params)
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = ev(), ev()
+        e0.record()
+        for _ in range(args.steps):
+            labels = dist_dbscan(dist.group.WORLD, space, d, eps, minpts, params)
+        e1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / args.steps], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        nclu = torch.unique(labels[labels >= 0])
+        sizes = [None] * world
+        dist.all_gather_object(sizes, nclu.cpu().numpy())
+        res["%s_minpts%d" % (iname, minpts)] = {"ms": ms, "Mpoints_s": world * n / ms / 1e3,
+                                               "clusters": int(len(np.unique(np.concatenate(sizes))))}
+    if rank == 0:
+        k = "densebox_minpts5"
+        emit({"metric": "DBSCAN Mpoints/s (GanTao clustered 3-D, eps=200)", "value": res[k]["Mpoints_s"],
+              "unit": "Mpoints/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+              "ms_per_step": res[k]["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+              "dtype": "f32", "data": "synthetic",
+              "config": {"workload": "distributed dbscan, GanTao n=%d per rank in touching slabs, eps=200 "
+                                     "(BASELINE.json configs[2] at N GPUs)" % n}, "components": res})
+    dist.destroy_process_group()
+
+
 def run_dbscan(args):
     """Secondary workload (BASELINE.json configs[2]): ArborX::dbscan on a GanTao clustered cloud,
     eps = 200, minpts in {2, 5}, FDBSCAN and FDBSCAN-DenseBox.  One JSON line; `value` = points/s of
     the reference's default configuration (FDBSCAN-DenseBox, minpts = 5)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        return run_dbscan_distributed(args, world, int(os.environ.get("RANK", "0")),
+                                      int(os.environ.get("LOCAL_RANK", "0")))
     import torch
 
     import arborx_b200 as abx
