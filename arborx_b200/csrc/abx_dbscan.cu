@@ -90,13 +90,23 @@ __global__ void __launch_bounds__(kThreads)
   bool const i_core = SPECIAL ? true : (num_neigh[i] >= minpts);
   if (STAR && !i_core)
     return; // border points do not take part in DBSCAN* (callback would return at once)
+  // Inside a cluster almost every pair is already in one set.  rep_i is a (possibly stale) root of
+  // i's set; sets only ever merge, so labels[j] == rep_i proves j is in i's set with one load and
+  // no chase; anything else goes through the full merge and refreshes rep_i.
+  int rep_i = i_core ? ufRepresentative(labels, i) : -1;
+  auto mergeCore = [&](int j) {
+    if (ufLoad(labels, j) == rep_i)
+      return;
+    ufMerge(labels, i, j);
+    rep_i = ufRepresentative(labels, i);
+  };
   traverseHalf(nodes, leaf_box, t, pred, [&](unsigned orig_j, int) {
     int const j = (int)orig_j;
     bool const j_core = SPECIAL ? true : (num_neigh[j] >= minpts);
     if (STAR)
     {
       if (j_core)
-        ufMerge(labels, i, j);
+        mergeCore(j);
       return;
     }
     if (!i_core)
@@ -107,7 +117,7 @@ __global__ void __launch_bounds__(kThreads)
     else
     {
       if (j_core)
-        ufMerge(labels, i, j);
+        mergeCore(j);
       else
         ufMergeInto(labels, j, i);
     }
@@ -387,12 +397,17 @@ __global__ void __launch_bounds__(kThreads)
   pred.t = sqrtThreshold(eps);
   if (n_prims < 2)
     return;
+  // rep_i: a (possibly stale) root of i's set -- see fdbscanMainKernel
+  int rep_i = ufRepresentative(labels, i);
   traverseSpatial<2>(nodes, leaf_box, pred, [&](unsigned prim, int) {
     int const k = (int)prim;
     if (k < num_dense)
     {
       int const cs = dense_cell_offsets[k], ce = dense_cell_offsets[k + 1];
-      if (ufRepresentative(labels, i) == ufRepresentative(labels, (int)perm[cs]))
+      int const first = (int)perm[cs];
+      if (ufLoad(labels, first) == rep_i)
+        return false;
+      if (ufRepresentative(labels, i) == ufRepresentative(labels, first))
         return false;
       for (int jj = cs; jj < ce; ++jj)
       {
@@ -405,13 +420,20 @@ __global__ void __launch_bounds__(kThreads)
           break;
         }
       }
+      rep_i = ufRepresentative(labels, i);
     }
     else
     {
       int const j = (int)perm[num_points_dense + (k - num_dense)];
       bool const j_core = SPECIAL ? true : (num_neigh[j] >= minpts);
       if (j_core && i > j)
-        ufMerge(labels, i, j);
+      {
+        if (ufLoad(labels, j) != rep_i)
+        {
+          ufMerge(labels, i, j);
+          rep_i = ufRepresentative(labels, i);
+        }
+      }
       else if (!STAR && !j_core)
         ufMergeInto(labels, j, i);
     }

@@ -700,10 +700,10 @@ abx_status sortPairsDB(cudaStream_t s, KeyT *const keys[2], unsigned *const vals
     ABX_CUDA_TRY(cudaMemcpyAsync(dup, flag.ptr, sizeof(dup), cudaMemcpyDeviceToHost, s));
     ABX_CUDA_TRY(cudaStreamSynchronize(s));
     // two samples share a prefix with probability p => a key's run holds ~n*p keys; dup ~ m^2/2 * p.
-    // Runs of ~16 keys on average are where the 256-key limit starts to be hit on clustered clouds
-    // (GanTao at 10M: the 40-bit level sampled below 64 and still overflowed).
+    // Runs of a few keys on average are where the 256-key limit starts to be hit on clustered clouds
+    // (GanTao at 10M: the 40-bit level sampled at ~40 keys per run and still overflowed).
     double const m = (double)std::min<int64_t>(kSampleKeys, n);
-    unsigned const limit = (unsigned)std::max(4.0, 16.0 * m * m / 2.0 / (double)n);
+    unsigned const limit = (unsigned)std::max(2.0, 4.0 * m * m / 2.0 / (double)n);
     if (dup[0] > limit)
       top += 2;
     if (dup[0] > limit && dup[1] > limit)
