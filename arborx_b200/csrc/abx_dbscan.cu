@@ -21,13 +21,20 @@ __device__ __forceinline__ int ufRepresentative(int *labels, int i)
   int curr = ufLoad(labels, i);
   if (curr != i)
   {
+    int const parent = curr;
     int next, prev = i;
     while (curr > (next = ufLoad(labels, curr)))
     {
-      __stcg(labels + prev, next); // path halving
+      __stcg(labels + prev, next); // path halving (UnionFind.hpp:113-128)
       prev = curr;
       curr = next;
     }
+    // and point the queried element at the root it found: the same elements (a dense cell's first
+    // point, a thread's own point) are asked over and over, and the one-load same-set test of the
+    // main kernels only succeeds on direct children of the root.  i is not a root here (roots are
+    // only ever changed by the CAS in ufMerge), and any ancestor is a valid parent.
+    if (curr != parent)
+      __stcg(labels + i, curr);
   }
   return curr;
 }
