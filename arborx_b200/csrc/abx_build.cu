@@ -287,6 +287,9 @@ __device__ __forceinline__ void loadNodeBox(Node64 const *nodes, int k, Box &b)
 // one-thread-per-leaf walk leaves 4-8 of 32 lanes alive after two levels), flags, boxes,
 // ranges and deltas live in shared memory, and stages 1-2 need no device-scope fence and
 // only two block barriers.
+#ifndef ABX_HIER_MINB
+#define ABX_HIER_MINB 1
+#endif
 constexpr int kHierWarpLeaves = 64; // stage-1 window
 constexpr int kHierWarpsDefault = 4; // warps per block: the stage-2 window is W * 64 leaves (ABX_HIER_WARPS overrides)
 constexpr int kFlagFree = -1;                            // no child has arrived
@@ -536,7 +539,7 @@ __device__ __forceinline__ void collectLoneChildren(HierSmem<KIND, W> &sm, int a
 }
 
 template <int KIND, int W>
-__global__ void __launch_bounds__(W * 32)
+__global__ void __launch_bounds__(W * 32, ABX_HIER_MINB)
     hierarchyLocalKernel(int n, unsigned long long const *__restrict__ codes, unsigned const *__restrict__ perm,
                          float const *__restrict__ prims, Node64 *nodes, float4 *leaf_box, float4 *leaf_tri,
                          PendingNode *pending, unsigned *pending_count, float *bounds6)
