@@ -805,6 +805,16 @@ abx_status abx_dist_merge_crs(void *stream, int64_t q, const int32_t *local_offs
                   remote_values2_dev, out_offsets_dev, out_values2_dev);
 }
 
+abx_status abx_dist_merge_sorted(void *stream, int64_t q, const int32_t *local_offsets_dev,
+                                 const int32_t *local_indices_dev, int32_t rank, int64_t n_remote,
+                                 const int64_t *remote_query_ids_dev, const int32_t *remote_values2_dev,
+                                 int32_t *out_offsets_dev, int32_t *out_values2_dev)
+{
+  ABX_TRY(ensureDevice());
+  return mergeSorted((cudaStream_t)stream, q, local_offsets_dev, local_indices_dev, rank, n_remote,
+                     remote_query_ids_dev, remote_values2_dev, out_offsets_dev, out_values2_dev);
+}
+
 abx_status abx_dist_route_count(void *stream, int pred_kind, const void *preds_dev, int64_t q, const float *radius_dev,
                                 int64_t radius_stride, const float *rank_boxes6_dev, int32_t n_ranks, int32_t self_rank,
                                 uint32_t *counts_dev)
@@ -832,6 +842,50 @@ abx_status abx_dist_pair_with_rank(void *stream, const int32_t *indices_dev, int
 {
   ABX_TRY(ensureDevice());
   return pairWithRank((cudaStream_t)stream, indices_dev, n, rank, values2_dev);
+}
+
+abx_status abx_dist_nearest_pairs(abx_bvh *bvh, void *stream, const void *points_dev, int64_t q, int32_t k,
+                                  int32_t rank, int32_t *values2_dev, float *distances_dev, int64_t *missing_out)
+{
+  ABX_TRY(ensureDevice());
+  if (!bvh || !missing_out || q < 0 || rank < 0)
+  {
+    setError("null argument");
+    return ABX_ERR_ARG;
+  }
+  *missing_out = 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  int const n = (int)bvh->n;
+  int64_t const row = std::max(0, std::min(k, n));
+  if (q == 0 || row == 0)
+    return ABX_OK;
+  if (!points_dev || !values2_dev)
+  {
+    setError("null argument");
+    return ABX_ERR_ARG;
+  }
+  TempBuffer<uint32_t> qperm;
+  if (n > 1)
+    ABX_TRY(predicatePermutation(s, bvh, ABX_PRED_POINT3F, points_dev, q, qperm));
+  TempBuffer<unsigned long long> missing;
+  ABX_TRY(missing.alloc(1, s));
+  ABX_CUDA_TRY(cudaMemsetAsync(missing.ptr, 0, sizeof(unsigned long long), s));
+  ABX_TRY(nearestQuery(s, bvh, (float const *)points_dev, q, k, nullptr, qperm.ptr, nullptr, row * q, nullptr,
+                       (uint32_t *)values2_dev, distances_dev, missing.ptr, rank));
+  unsigned long long h_missing = 0;
+  ABX_CUDA_TRY(cudaMemcpyAsync(&h_missing, missing.ptr, sizeof(h_missing), cudaMemcpyDeviceToHost, s));
+  ABX_CUDA_TRY(cudaStreamSynchronize(s));
+  *missing_out = (int64_t)h_missing;
+  return ABX_OK;
+}
+
+abx_status abx_dist_knn_merge(void *stream, int64_t n_candidates, const int64_t *query_ids_dev,
+                              const int32_t *cand_values2_dev, const float *cand_distances_dev, int32_t k,
+                              int32_t *values2_dev, float *distances_dev)
+{
+  ABX_TRY(ensureDevice());
+  return knnMerge((cudaStream_t)stream, n_candidates, query_ids_dev, cand_values2_dev, cand_distances_dev, k,
+                  values2_dev, distances_dev);
 }
 
 // ---- stage-level entry points -------------------------------------------------------

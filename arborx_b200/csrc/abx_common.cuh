@@ -311,12 +311,17 @@ abx_status spatialCompact(cudaStream_t s, abx_bvh *bvh, int pred_kind, void cons
 abx_status nearestQuery(cudaStream_t s, abx_bvh *bvh, float const *pts, int64_t q, int32_t k,
                         int32_t const *k_per_query, uint32_t const *qperm, int32_t const *offsets, int64_t total_rows,
                         int32_t *counts, uint32_t *indices, float *distances,
-                        unsigned long long *missing = nullptr);
+                        unsigned long long *missing = nullptr, int pair_rank = -1);
 abx_status compactRows(cudaStream_t s, int64_t q, int32_t const *old_offsets, int32_t const *new_offsets,
                        uint32_t const *old_idx, float const *old_dist, uint32_t *new_idx, float *new_dist);
 abx_status routeLaunch(cudaStream_t s, bool fill, int pred_kind, void const *preds, int64_t q, float const *radius,
                        int64_t radius_stride, float const *boxes6, int R, int self_rank, unsigned *counts,
                        unsigned const *base, unsigned *cursors, int32_t *out_qid);
+abx_status mergeSorted(cudaStream_t s, int64_t q, int32_t const *local_off, int32_t const *local_idx, int rank,
+                       int64_t m, int64_t const *remote_ids, int32_t const *remote_vals2, int32_t *out_off,
+                       int32_t *out_vals2);
+abx_status knnMerge(cudaStream_t s, int64_t m, int64_t const *ids, int32_t const *cand2, float const *cand_d, int k,
+                    int32_t *vals2, float *dists);
 abx_status pairWithRank(cudaStream_t s, int32_t const *indices, int64_t n, int rank, int32_t *out2);
 abx_status mergeCrs(cudaStream_t s, int64_t q, int32_t const *local_off, int32_t const *local_idx, int rank,
                     int32_t const *remote_off, int32_t const *remote_vals2, int32_t *out_off, int32_t *out_vals2);

@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(kThreads, (K > 0 && K <= 16) ? ABX_NEAREST_MIN
                   unsigned const *__restrict__ qperm, int k_uniform, int row_stride,
                   int32_t const *__restrict__ k_per_query, int32_t const *__restrict__ offsets,
                   int32_t *__restrict__ counts, uint32_t *__restrict__ indices, float *__restrict__ distances,
-                  float2 *__restrict__ scratch, unsigned long long *__restrict__ missing)
+                  float2 *__restrict__ scratch, unsigned long long *__restrict__ missing, int pair_rank)
 {
   int64_t const t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (t >= q)
@@ -272,7 +272,10 @@ __global__ void __launch_bounds__(kThreads, (K > 0 && K <= 16) ? ABX_NEAREST_MIN
     float4 hi = prim_kind == ABX_PRIM_POINT3F ? lo : __ldg(leaf_box + 1);
     float const d2 = TRI ? pointTriangleDist2(px, py, pz, __ldg(leaf_tri), __ldg(leaf_tri + 1), __ldg(leaf_tri + 2))
                          : pointBoxDist2v(px, py, pz, lo, hi);
-    indices[base] = 0u;
+    if (pair_rank >= 0)
+      reinterpret_cast<int2 *>(indices)[base] = make_int2(0, pair_rank);
+    else
+      indices[base] = 0u;
     if (distances)
       distances[base] = __fsqrt_rn(d2);
     if (counts)
@@ -449,7 +452,11 @@ __global__ void __launch_bounds__(kThreads, (K > 0 && K <= 16) ? ABX_NEAREST_MIN
     for (int i = 0; i < (USE_REGS ? K : 1); ++i)
       if (i < m)
       {
-        indices[base + i] = list.id[i];
+        // pair_rank >= 0: DistributedTree's (index, rank) values, written in place of the index
+        if (pair_rank >= 0)
+          reinterpret_cast<int2 *>(indices)[base + i] = make_int2((int)list.id[i], pair_rank);
+        else
+          indices[base + i] = list.id[i];
         if (distances)
           distances[base + i] = __fsqrt_rn(list.d[i]);
       }
@@ -461,7 +468,10 @@ __global__ void __launch_bounds__(kThreads, (K > 0 && K <= 16) ? ABX_NEAREST_MIN
     for (int i = 0; i < found; ++i)
     {
       float2 e = heap.h[i];
-      indices[base + i] = __float_as_uint(e.y);
+      if (pair_rank >= 0)
+        reinterpret_cast<int2 *>(indices)[base + i] = make_int2((int)__float_as_uint(e.y), pair_rank);
+      else
+        indices[base + i] = __float_as_uint(e.y);
       if (distances)
         distances[base + i] = __fsqrt_rn(e.x);
     }
@@ -694,7 +704,7 @@ abx_status spatialCompact(cudaStream_t s, abx_bvh *t, int pred_kind, void const 
 // offsets = CRS offsets of min(k_i, n).  total_rows = size of indices.
 abx_status nearestQuery(cudaStream_t s, abx_bvh *t, float const *pts, int64_t q, int32_t k, int32_t const *k_per_query,
                         uint32_t const *qperm, int32_t const *offsets, int64_t total_rows, int32_t *counts,
-                        uint32_t *indices, float *distances, unsigned long long *missing)
+                        uint32_t *indices, float *distances, unsigned long long *missing, int pair_rank)
 {
   if (q <= 0)
     return ABX_OK;
@@ -715,15 +725,15 @@ abx_status nearestQuery(cudaStream_t s, abx_bvh *t, float const *pts, int64_t q,
     if (tri)                                                                                                           \
       ABX_LAUNCH_TAGGED("nearestKernel<" #KCAP ",tri>", (nearestKernel<KCAP, 2, true>), grid, kThreads, 0, s,          \
                         t->nodes, t->leaf_box, t->leaf_tri, n, t->kind, pts, q, qperm, k, row_stride, k_per_query,     \
-                        offsets, counts, indices, distances, SCRATCH, missing);                                                 \
+                        offsets, counts, indices, distances, SCRATCH, missing, pair_rank);                                                 \
     else if (t->kind == ABX_PRIM_BOX3F)                                                                                \
       ABX_LAUNCH_TAGGED("nearestKernel<" #KCAP ",box>", (nearestKernel<KCAP, 2, false>), grid, kThreads, 0, s,         \
                         t->nodes, t->leaf_box, t->leaf_tri, n, t->kind, pts, q, qperm, k, row_stride, k_per_query,     \
-                        offsets, counts, indices, distances, SCRATCH, missing);                                                 \
+                        offsets, counts, indices, distances, SCRATCH, missing, pair_rank);                                                 \
     else                                                                                                               \
       ABX_LAUNCH_TAGGED("nearestKernel<" #KCAP ">", (nearestKernel<KCAP, 1, false>), grid, kThreads, 0, s, t->nodes,   \
                         t->leaf_box, t->leaf_tri, n, t->kind, pts, q, qperm, k, row_stride, k_per_query, offsets,      \
-                        counts, indices, distances, SCRATCH, missing);                                                          \
+                        counts, indices, distances, SCRATCH, missing, pair_rank);                                                          \
   } while (0)
   if (kmax <= 16)
   {
@@ -924,6 +934,47 @@ __global__ void pairWithRankKernel(int32_t const *__restrict__ indices, int64_t 
   if (i < n)
     out[i] = make_int2(indices[i], rank);
 }
+// candidates of one query are contiguous (ids ascending): the thread at the start of a segment merges
+// the segment into the query's row by insertion (k and the segment are tens of entries; a few percent
+// of the queries have any)
+__global__ void knnMergeKernel(int64_t m, long long const *__restrict__ ids, int2 const *__restrict__ cand,
+                               float const *__restrict__ cand_d, int k, int2 *vals, float *dists)
+{
+  int64_t const c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= m)
+    return;
+  long long const qid = ids[c];
+  if (c > 0 && ids[c - 1] == qid)
+    return;
+  int2 *row_v = vals + qid * k;
+  float *row_d = dists + qid * k;
+  for (int64_t e = c; e < m && ids[e] == qid; ++e)
+  {
+    float const d = cand_d[e];
+    if (!(d < row_d[k - 1]))
+      continue;
+    // strict <: a local entry stays ahead of a remote one at the same distance
+    int pos = k - 1;
+    while (pos > 0 && d < row_d[pos - 1])
+    {
+      row_d[pos] = row_d[pos - 1];
+      row_v[pos] = row_v[pos - 1];
+      --pos;
+    }
+    row_d[pos] = d;
+    row_v[pos] = cand[e];
+  }
+}
+
+abx_status knnMerge(cudaStream_t s, int64_t m, int64_t const *ids, int32_t const *cand2, float const *cand_d, int k,
+                    int32_t *vals2, float *dists)
+{
+  if (m > 0 && k > 0)
+    ABX_LAUNCH(knnMergeKernel, divUp(m, 128), 128, 0, s, m, (long long const *)ids, (int2 const *)cand2, cand_d, k,
+               (int2 *)vals2, dists);
+  return ABX_OK;
+}
+
 abx_status pairWithRank(cudaStream_t s, int32_t const *indices, int64_t n, int rank, int32_t *out2)
 {
   if (n > 0)
@@ -942,6 +993,95 @@ abx_status mergeCrs(cudaStream_t s, int64_t q, int32_t const *local_off, int32_t
   if (q > 0)
     ABX_LAUNCH(mergeRowsKernel, divUp(q, 256), 256, 0, s, q, local_off, local_idx, rank, remote_off,
                (int2 const *)remote_vals2, out_off, (int2 *)out_vals2);
+  return ABX_OK;
+}
+
+// ---- merge with the remote results given as (query id ascending, value) records -------------------
+__global__ void mergeLocalCountsKernel(int64_t q, int32_t const *__restrict__ local_off, int32_t *__restrict__ counts)
+{
+  int64_t const i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < q)
+    counts[i] = local_off[i + 1] - local_off[i];
+}
+// the thread at the start of a query's segment adds the segment length (one writer per query)
+__global__ void mergeRemoteCountsKernel(int64_t m, long long const *__restrict__ ids, int32_t *__restrict__ counts)
+{
+  int64_t const c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= m)
+    return;
+  long long const qid = ids[c];
+  if (c > 0 && ids[c - 1] == qid)
+    return;
+  int len = 1;
+  while (c + len < m && ids[c + len] == qid)
+    ++len;
+  counts[qid] += len;
+}
+// local rows -> (index, rank) pairs at their new offsets.  A warp takes 32 consecutive rows and walks
+// their concatenated elements 32 at a time (coalesced in, nearly coalesced out: rows that gained no
+// remote entries keep their relative positions); the row of an element is found by a 5-step search
+// over the 32 row starts held one per lane.
+__global__ void __launch_bounds__(256)
+    mergeLocalRowsKernel(int64_t q, int32_t const *__restrict__ local_off, int32_t const *__restrict__ local_idx,
+                         int rank, int32_t const *__restrict__ out_off, int2 *__restrict__ out_vals)
+{
+  int const lane = threadIdx.x & 31;
+  int64_t const r0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
+  if (r0 >= q)
+    return;
+  int64_t const r = min(r0 + lane, q); // lanes past the last row hold its end (empty rows)
+  int const lo = local_off[r];
+  int const shift = (r < q ? out_off[r] : 0) - lo;
+  int const begin = __shfl_sync(0xffffffffu, lo, 0);
+  int const end = local_off[min(r0 + 32, q)];
+  for (int j = begin + lane; j - lane < end; j += 32)
+  {
+    // largest lane l with lo_l <= j
+    int l = 0;
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1)
+    {
+      int const probe = __shfl_sync(0xffffffffu, lo, min(l + step, 31));
+      if (l + step < 32 && probe <= j)
+        l += step;
+    }
+    int const sh = __shfl_sync(0xffffffffu, shift, l);
+    if (j < end)
+      out_vals[j + sh] = make_int2(local_idx[j], rank);
+  }
+}
+__global__ void mergeRemoteRowsKernel(int64_t m, long long const *__restrict__ ids, int2 const *__restrict__ vals,
+                                      int32_t const *__restrict__ local_off, int32_t const *__restrict__ out_off,
+                                      int2 *__restrict__ out_vals)
+{
+  int64_t const c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= m)
+    return;
+  long long const qid = ids[c];
+  if (c > 0 && ids[c - 1] == qid)
+    return;
+  int dst = out_off[qid] + (local_off[qid + 1] - local_off[qid]);
+  for (int64_t e = c; e < m && ids[e] == qid; ++e)
+    out_vals[dst++] = vals[e];
+}
+
+abx_status mergeSorted(cudaStream_t s, int64_t q, int32_t const *local_off, int32_t const *local_idx, int rank,
+                       int64_t m, int64_t const *remote_ids, int32_t const *remote_vals2, int32_t *out_off,
+                       int32_t *out_vals2)
+{
+  if (q < 0)
+    return ABX_OK;
+  if (q > 0)
+    ABX_LAUNCH(mergeLocalCountsKernel, divUp(q, 256), 256, 0, s, q, local_off, out_off);
+  if (m > 0)
+    ABX_LAUNCH(mergeRemoteCountsKernel, divUp(m, 256), 256, 0, s, m, (long long const *)remote_ids, out_off);
+  ABX_TRY(exclusiveScanI32(s, out_off, out_off, q + 1));
+  if (q > 0)
+    ABX_LAUNCH(mergeLocalRowsKernel, divUp(divUp(q, 32) * 32, 256), 256, 0, s, q, local_off, local_idx, rank, out_off,
+               (int2 *)out_vals2);
+  if (m > 0)
+    ABX_LAUNCH(mergeRemoteRowsKernel, divUp(m, 256), 256, 0, s, m, (long long const *)remote_ids,
+               (int2 const *)remote_vals2, local_off, out_off, (int2 *)out_vals2);
   return ABX_OK;
 }
 

@@ -108,6 +108,60 @@ class CudaEngine:
                                                           int(rank), C.c_void_p(out.data_ptr())))
         return out
 
+    def nearest_pairs(self, tree, pts, k, rank):
+        """k nearest of every point as (index, rank) pairs [q * row, 2] + distances [q * row], row = min(k, size);
+        None when some row could not be filled (the caller takes the general path)."""
+        import ctypes as C
+        from . import _lib
+        q = pts.shape[0]
+        row = max(0, min(int(k), tree.size()))
+        dev = pts.device
+        vals = torch.empty((q * row, 2), dtype=torch.int32, device=dev)
+        d = torch.empty(q * row, dtype=torch.float32, device=dev)
+        missing = C.c_int64(0)
+        p = pts.contiguous()
+        with torch.cuda.stream(self.space.stream):
+            _lib.check(_lib.lib().abx_dist_nearest_pairs(tree._h, self.space.handle, C.c_void_p(p.data_ptr()), q, int(k),
+                                                         int(rank), C.c_void_p(vals.data_ptr()),
+                                                         C.c_void_p(d.data_ptr()), C.byref(missing)))
+        if missing.value:
+            return None
+        return vals, d
+
+    def knn_merge(self, ids, cand_vals, cand_d, k, vals, dists):
+        """Merge remote candidates (ids ascending) into the k-entry rows of their queries, in place."""
+        import ctypes as C
+        from . import _lib
+        i64 = ids.to(torch.int64).contiguous()
+        cv = cand_vals.to(torch.int32).contiguous()
+        cd = cand_d.to(torch.float32).contiguous()
+        with torch.cuda.stream(self.space.stream):
+            _lib.check(_lib.lib().abx_dist_knn_merge(self.space.handle, i64.shape[0], C.c_void_p(i64.data_ptr()),
+                                                     C.c_void_p(cv.data_ptr()), C.c_void_p(cd.data_ptr()), int(k),
+                                                     C.c_void_p(vals.data_ptr()), C.c_void_p(dists.data_ptr())))
+
+    def merge_sorted(self, local_off, local_idx, rank, remote_ids, remote_vals):
+        """Local CRS (index only) + remote records (query id ascending, (index, rank)) -> merged
+        (values [nnz, 2], offsets [q + 1]) (abx_dist_merge_sorted)."""
+        import ctypes as C
+        from . import _lib
+        q = local_off.shape[0] - 1
+        dev = local_off.device
+        m = int(remote_ids.shape[0])
+        nnz = int(local_idx.shape[0]) + m
+        out_off = torch.empty(q + 1, dtype=torch.int32, device=dev)
+        out_vals = torch.empty((nnz, 2), dtype=torch.int32, device=dev)
+        lo = local_off.to(torch.int32).contiguous()
+        li = local_idx.to(torch.int32).contiguous()
+        ri = remote_ids.to(torch.int64).contiguous()
+        rv = remote_vals.to(torch.int32).contiguous()
+        with torch.cuda.stream(self.space.stream):
+            _lib.check(_lib.lib().abx_dist_merge_sorted(self.space.handle, q, C.c_void_p(lo.data_ptr()),
+                                                        C.c_void_p(li.data_ptr()), int(rank), m,
+                                                        C.c_void_p(ri.data_ptr()), C.c_void_p(rv.data_ptr()),
+                                                        C.c_void_p(out_off.data_ptr()), C.c_void_p(out_vals.data_ptr())))
+        return out_vals, out_off
+
     def merge_rows(self, local_off, local_idx, rank, remote_off, remote_vals):
         """CRS rows of local results (index only) + CRS rows of remote results ((index, rank) pairs)
         -> merged (values [nnz, 2], offsets [q + 1]); one kernel pass (abx_dist_merge_crs)."""
@@ -353,10 +407,14 @@ class DistributedTree:
                 return self.engine.pair_with_rank(idx_l, self.rank), off_l.to(torch.int32)
             return torch.stack([idx_l.to(torch.int32), torch.full_like(idx_l, self.rank, dtype=torch.int32)], 1), \
                 off_l.to(torch.int32)
-        roff = torch.zeros(q + 1, dtype=torch.int64, device=dev)
-        roff[1:] = torch.cumsum(torch.bincount(ids, minlength=q), 0)
-        _mark("roff")
-        out = self.engine.merge_rows(off_l, idx_l, self.rank, roff, rvals)
+        if hasattr(self.engine, "merge_sorted"):
+            _mark("roff")
+            out = self.engine.merge_sorted(off_l, idx_l, self.rank, ids, rvals)
+        else:
+            roff = torch.zeros(q + 1, dtype=torch.int64, device=dev)
+            roff[1:] = torch.cumsum(torch.bincount(ids, minlength=q), 0)
+            _mark("roff")
+            out = self.engine.merge_rows(off_l, idx_l, self.rank, roff, rvals)
         _mark("merge")
         _report("spatial")
         return out
@@ -368,22 +426,34 @@ class DistributedTree:
         dev = pts.device
         q = pts.shape[0]
         _mark("start")
-        idx_l, off_l, d_l = self.engine.nearest(self._bottom, pts, k)
-        _mark("local")
-        if idx_l.shape[0] != q * k:
-            return self._nearest(pts, k)  # short local rows (unreachable leaves): generic path
+        vals = None
+        if hasattr(self.engine, "nearest_pairs"):
+            # local rows written directly as (index, rank) pairs
+            got = self.engine.nearest_pairs(self._bottom, pts, k, self.rank)
+            if got is None or got[0].shape[0] != q * k:
+                return self._nearest(pts, k)  # short local rows (fewer than k leaves, unreachable leaves)
+            vals, d_l = got
+            _mark("local")
+        else:
+            idx_l, off_l, d_l = self.engine.nearest(self._bottom, pts, k)
+            _mark("local")
+            if idx_l.shape[0] != q * k:
+                return self._nearest(pts, k)  # short local rows (unreachable leaves): generic path
         # phase II spheres (point, local k-th distance): routed without materialising them
         qid_s, send_counts = self._route(SPHERE_PRED, pts, d_l.view(-1)[k - 1:], k)
         _mark("route")
         ids, rvals, rd = self._exchange_remote(pts, qid_s, send_counts, ("nearest", k))
         _mark("exchange")
-        if hasattr(self.engine, "pair_with_rank"):
-            vals = self.engine.pair_with_rank(idx_l, self.rank)
-        else:
-            vals = torch.stack([idx_l.to(torch.int32), torch.full_like(idx_l, self.rank, dtype=torch.int32)], 1)
+        if vals is None:
+            if hasattr(self.engine, "pair_with_rank"):
+                vals = self.engine.pair_with_rank(idx_l, self.rank)
+            else:
+                vals = torch.stack([idx_l.to(torch.int32), torch.full_like(idx_l, self.rank, dtype=torch.int32)], 1)
         _mark("pair")
         out_d = d_l
-        if ids.shape[0]:
+        if ids.shape[0] and hasattr(self.engine, "knn_merge"):
+            self.engine.knn_merge(ids, rvals, rd, k, vals, out_d)
+        elif ids.shape[0]:
             # queries with remote candidates: k local + m remote, keep the k smallest
             uq, inv = torch.unique(ids, return_inverse=True)
             cnt = torch.bincount(inv, minlength=uq.shape[0])

@@ -183,6 +183,13 @@ ABX_API abx_status abx_dist_merge_crs(void *stream, int64_t q, const int32_t *lo
                                       const int32_t *remote_offsets_dev, const int32_t *remote_values2_dev,
                                       int32_t *out_offsets_dev, int32_t *out_values2_dev);
 
+/* Same merge with the remote results as they arrive from the exchange: n_remote records ordered by query id
+ * (remote_query_ids_dev ascending), one (index, rank) pair each; no remote CRS offsets needed. */
+ABX_API abx_status abx_dist_merge_sorted(void *stream, int64_t q, const int32_t *local_offsets_dev,
+                                         const int32_t *local_indices_dev, int32_t rank, int64_t n_remote,
+                                         const int64_t *remote_query_ids_dev, const int32_t *remote_values2_dev,
+                                         int32_t *out_offsets_dev, int32_t *out_values2_dev);
+
 /* Routing of forwarded predicates (the top-tree query of DistributedTreeSpatial.hpp:52-55 for R <= 64
  * ranks, evaluated directly against the R rank boxes; conservative for spheres).  Pass 1 counts the
  * predicates that must be forwarded to every OTHER rank; pass 2 writes their query ids grouped by
@@ -201,6 +208,20 @@ ABX_API abx_status abx_dist_route_fill(void *stream, int pred_kind, const void *
 /* values2[i] = (indices[i], rank): local results in the (index, rank) form DistributedTree returns */
 ABX_API abx_status abx_dist_pair_with_rank(void *stream, const int32_t *indices_dev, int64_t n, int32_t rank,
                                            int32_t *values2_dev);
+/* DistributedTree kNN, local phase (distributed/detail/ArborX_DistributedTreeNearest.hpp:131-176): the k
+ * nearest of every point with rows of exactly row = min(k, size) entries, written directly in the
+ * (index, rank) form: values2_dev[2 * (i * row + j)] = index, [.. + 1] = rank; distances_dev[i * row + j].
+ * *missing_out = entries that could not be filled (leaves at infinite distance); when it is not 0 the
+ * rows are not usable and the caller takes the general path (abx_query_nearest_crs). */
+ABX_API abx_status abx_dist_nearest_pairs(abx_bvh *bvh, void *stream, const void *points_dev, int64_t q, int32_t k,
+                                          int32_t rank, int32_t *values2_dev, float *distances_dev,
+                                          int64_t *missing_out);
+/* DistributedTree kNN, final ranking (same file :178-233): candidates received from other ranks
+ * (query_ids_dev ascending, one (index, rank) pair and one distance each) are merged into the rows of
+ * their queries (k entries each, ascending): the k smallest survive, local entries first among equals. */
+ABX_API abx_status abx_dist_knn_merge(void *stream, int64_t n_candidates, const int64_t *query_ids_dev,
+                                      const int32_t *cand_values2_dev, const float *cand_distances_dev, int32_t k,
+                                      int32_t *values2_dev, float *distances_dev);
 
 /* ---- stage-level entry points (tests localise mismatches with these) ---- */
 /* TreeConstruction::calculateBoundingBoxOfTheScene (detail/ArborX_TreeConstruction.hpp:27-39) */
