@@ -52,6 +52,7 @@ SIGNATURES = {
     "abx_dbscan": (C.c_int, [_vp, _vp, _i64, _f, _i32, C.c_int, C.c_int, _vp]),
     "abx_dbscan_host": (C.c_int, [_vp, _vp, _i64, _f, _i32, C.c_int, C.c_int, _vp]),
     "abx_dist_merge_crs": (C.c_int, [_vp, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "abx_bvh_device_view": (C.c_int, [_vp, _vp]),
     "abx_dist_merge_sorted": (C.c_int, [_vp, _i64, _vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp]),
     "abx_dist_route_count": (C.c_int, [_vp, C.c_int, _vp, _i64, _vp, _i64, _vp, _i32, _i32, _vp]),
     "abx_dist_route_fill": (C.c_int, [_vp, C.c_int, _vp, _i64, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp]),

@@ -805,6 +805,21 @@ abx_status abx_dist_merge_crs(void *stream, int64_t q, const int32_t *local_offs
                   remote_values2_dev, out_offsets_dev, out_values2_dev);
 }
 
+abx_status abx_bvh_device_view(const abx_bvh *bvh, abx_device_view *view)
+{
+  if (!bvh || !view)
+  {
+    setError("null argument");
+    return ABX_ERR_ARG;
+  }
+  view->nodes = bvh->nodes;
+  view->leaf_box = bvh->leaf_box;
+  view->leaf_tri = bvh->leaf_tri;
+  view->n = bvh->n;
+  view->prim_kind = bvh->kind;
+  return ABX_OK;
+}
+
 abx_status abx_dist_merge_sorted(void *stream, int64_t q, const int32_t *local_offsets_dev,
                                  const int32_t *local_indices_dev, int32_t rank, int64_t n_remote,
                                  const int64_t *remote_query_ids_dev, const int32_t *remote_values2_dev,

@@ -173,6 +173,21 @@ ABX_API abx_status abx_dbscan(void *stream, const float *xyz_dev, int64_t n, flo
 ABX_API abx_status abx_dbscan_host(void *stream, const float *xyz_host, int64_t n, float eps, int32_t minpts,
                            int implementation, int algorithm, int32_t *labels_host);
 
+/* ---- device view for user callbacks (include/ArborX_B200_Callbacks.cuh) ----
+ * The reference instantiates user callbacks inside its traversal templates
+ * (spatial/detail/ArborX_Callbacks.hpp:79-150, ArborX_TreeTraversal.hpp:97-119,180-335).  Here the tree's
+ * device arrays are exported and the same traversal cores the library kernels use are instantiated in
+ * the user's .cu through the header.  The view is valid until abx_bvh_destroy. */
+typedef struct abx_device_view
+{
+  const void *nodes;    /* Node64[n - 1], NULL when n < 2 */
+  const void *leaf_box; /* sorted leaves: float4 per point, 2 x float4 per box / triangle */
+  const void *leaf_tri; /* 3 x float4 per triangle, else NULL */
+  int64_t n;
+  int32_t prim_kind;
+} abx_device_view;
+ABX_API abx_status abx_bvh_device_view(const abx_bvh *bvh, abx_device_view *view);
+
 /* ---- DistributedTree building block (distributed/detail/ArborX_DistributedTreeUtils.hpp:229-263) ----
  * Merges, per query, the CRS rows of the local tree's results (indices) with the CRS rows of the
  * results that came back from other ranks ((index, rank) pairs, grouped by query) into one CRS

@@ -32,3 +32,32 @@ def test_facade_runs():
     assert out.returncode == 0, out.stdout + out.stderr
     assert "FACADE OK" in out.stdout
     assert "offsets: 0 1 4 8" in out.stdout
+
+
+CB_EXE = os.path.join(ROOT, "arborx_b200", "lib", "callback_example")
+
+
+def _compile_callbacks():
+    lib = os.path.join(ROOT, "arborx_b200", "lib")
+    cmd = ["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "--extended-lambda",
+           "--expt-relaxed-constexpr", "-fmad=false", "-O2", "-I" + os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "callback_example.cu"), "-o", CB_EXE, "-L" + lib, "-labx",
+           "-Xlinker", "-rpath", "-Xlinker", lib]
+    subprocess.check_call(cmd)
+
+
+def test_callbacks_header_compiles():
+    """include/ArborX_B200_Callbacks.cuh instantiates the traversal cores in a user translation unit."""
+    from arborx_b200 import _lib
+    _lib.lib()
+    _compile_callbacks()
+    assert os.path.exists(CB_EXE)
+
+
+@pytest.mark.gpu
+def test_callbacks_run():
+    if not os.path.exists(CB_EXE):
+        _compile_callbacks()
+    out = subprocess.run([CB_EXE], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "CALLBACKS OK" in out.stdout
