@@ -295,7 +295,8 @@ static abx_status spatialCrs(abx_bvh *bvh, cudaStream_t s, int pred_kind, void c
   ABX_TRY(allocOut(alloc, user, 1, sizeof(uint32_t) * (size_t)total, s, &idx));
   *indices_out = (uint32_t *)idx;
   if (staged)
-    ABX_TRY(spatialCompact(s, bvh, pred_kind, preds, q, qperm.ptr, offsets, *indices_out, staging.ptr));
+    // original query order: coalesced staging-row reads and CRS writes (see kStage in abx_query.cu)
+    ABX_TRY(spatialCompact(s, bvh, pred_kind, preds, q, nullptr, offsets, *indices_out, staging.ptr));
   else
     ABX_TRY(spatialFill(s, bvh, pred_kind, preds, q, qperm.ptr, offsets, *indices_out));
   return ABX_OK;
