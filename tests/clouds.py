@@ -31,6 +31,33 @@ def filled_box(seed, n):
     return (a * (F(2) * uniform01(seed, n) - F(1))).astype(F)
 
 
+CLOUD_KINDS = {"filled_box": 0, "hollow_box": 1, "filled_sphere": 2, "hollow_sphere": 3}
+
+
+def point_cloud(kind, seed, n):
+    """The four bvh_driver cloud kinds (benchmarks/utils/ArborXBenchmark_PointClouds.hpp:25-178), scaled by
+    a = cbrt(n) like constructPoints (benchmark_registration.hpp:129-149).  Unit shapes: filled_box uniform in
+    [-1, 1]^3; hollow_box on the faces (point i on axis (i / 2) % 3, side i % 2); filled_sphere a normal
+    direction scaled by u^(1/3); hollow_sphere a normalised normal direction."""
+    a = F(np.cbrt(float(n)))
+    if kind == "filled_box":
+        return filled_box(seed, n)
+    if kind == "hollow_box":
+        p = F(2) * uniform01(seed, n) - F(1)
+        i = np.arange(n)
+        p[i, (i // 2) % 3] = np.where(i % 2 == 0, F(-1), F(1))
+        return (a * p).astype(F)
+    g = _normals(seed + 31, n)
+    norm = np.linalg.norm(g, axis=1, keepdims=True)
+    norm[norm == 0] = 1.0
+    if kind == "filled_sphere":
+        scale = np.cbrt(uniform01(seed + 37, n, 1).astype(np.float64)) / norm
+        return (a * (g * scale)).astype(F)
+    if kind == "hollow_sphere":
+        return (a * (g / norm)).astype(F)
+    raise ValueError("unknown point cloud kind " + str(kind))
+
+
 def bvh_driver_radius(k=10):
     """r = cbrt(k * 6 / pi): about k results per query (benchmark_registration.hpp:179-183)."""
     return F(np.cbrt(k * 6.0 / np.pi))
