@@ -80,15 +80,20 @@ __global__ void __launch_bounds__(kThreads)
   num_neigh[__float_as_uint(p.w)] = count;
 }
 
+constexpr int kDbscanQueue = 16; // queued leaf runs per thread (deferred leaf tests)
+
 // ---- FDBSCAN: half traversal + FDBSCANCallback (FDBSCAN.hpp:49-110) ---------------
 template <bool SPECIAL /*minpts == 2*/, bool STAR>
 __global__ void __launch_bounds__(kThreads)
     fdbscanMainKernel(Node64 const *__restrict__ nodes, float4 const *__restrict__ leaf_box, int n, float eps,
                       int minpts, int const *__restrict__ num_neigh, int *labels)
 {
-  int const t = blockIdx.x * kThreads + threadIdx.x;
-  if (t >= n)
-    return;
+  // deferred leaf tests (abx_traverse.cuh): inside a cluster a point has hundreds of neighbours, and
+  // testing them with the warp converged matters more than anywhere else; all lanes stay
+  __shared__ unsigned squeue[kDbscanQueue * kThreads];
+  int const t0 = blockIdx.x * kThreads + threadIdx.x;
+  bool active = t0 < n;
+  int const t = active ? t0 : 0;
   float4 const p = __ldg(leaf_box + t);
   Pred<ABX_PRED_SPHERE3F> pred;
   pred.cx = p.x, pred.cy = p.y, pred.cz = p.z, pred.r = eps;
@@ -96,7 +101,7 @@ __global__ void __launch_bounds__(kThreads)
   int const i = (int)__float_as_uint(p.w);
   bool const i_core = SPECIAL ? true : (num_neigh[i] >= minpts);
   if (STAR && !i_core)
-    return; // border points do not take part in DBSCAN* (callback would return at once)
+    active = false; // border points do not take part in DBSCAN* (callback would return at once)
   // Inside a cluster almost every pair is already in one set.  rep_i is a (possibly stale) root of
   // i's set; sets only ever merge, so labels[j] == rep_i proves j is in i's set with one load and
   // no chase; anything else goes through the full merge and refreshes rep_i.
@@ -107,14 +112,14 @@ __global__ void __launch_bounds__(kThreads)
     ufMerge(labels, i, j);
     rep_i = ufRepresentative(labels, i);
   };
-  traverseHalf(nodes, leaf_box, t, pred, [&](unsigned orig_j, int) {
+  auto pair = [&](unsigned orig_j, int) {
     int const j = (int)orig_j;
     bool const j_core = SPECIAL ? true : (num_neigh[j] >= minpts);
     if (STAR)
     {
       if (j_core)
         mergeCore(j);
-      return;
+      return false;
     }
     if (!i_core)
     {
@@ -128,7 +133,9 @@ __global__ void __launch_bounds__(kThreads)
       else
         ufMergeInto(labels, j, i);
     }
-  });
+    return false;
+  };
+  traverseSpatialDeferred<1, 4, kDbscanQueue>(nodes, leaf_box, pred, active, squeue, pair, t);
 }
 
 // ---- finalize_labels (:489-506) and mark_noise (:512-518) -------------------------
@@ -390,23 +397,23 @@ __global__ void __launch_bounds__(kThreads)
                     int num_points_dense, int n, float eps, int minpts, int const *__restrict__ num_neigh,
                     int *labels)
 {
-  int const t = blockIdx.x * kThreads + threadIdx.x;
-  if (t >= n)
+  __shared__ unsigned squeue[kDbscanQueue * kThreads];
+  if (n_prims < 2)
     return;
+  int const t0 = blockIdx.x * kThreads + threadIdx.x;
+  bool active = t0 < n;
   // walk the points in the reordered (cell-sorted) order for coherence
-  int const i = (int)perm[t];
+  int const i = (int)perm[active ? t0 : 0];
   bool const i_core = SPECIAL ? true : (num_neigh[i] >= minpts);
   if (!i_core)
-    return; // border points exit at the first callback (:130-132)
+    active = false; // border points exit at the first callback (:130-132)
   float const px = xyz[3 * (size_t)i], py = xyz[3 * (size_t)i + 1], pz = xyz[3 * (size_t)i + 2];
   Pred<ABX_PRED_SPHERE3F> pred;
   pred.cx = px, pred.cy = py, pred.cz = pz, pred.r = eps;
   pred.t = sqrtThreshold(eps);
-  if (n_prims < 2)
-    return;
   // rep_i: a (possibly stale) root of i's set -- see fdbscanMainKernel
   int rep_i = ufRepresentative(labels, i);
-  traverseSpatial<2>(nodes, leaf_box, pred, [&](unsigned prim, int) {
+  traverseSpatialDeferred<2, 4, kDbscanQueue>(nodes, leaf_box, pred, active, squeue, [&](unsigned prim, int) {
     int const k = (int)prim;
     if (k < num_dense)
     {

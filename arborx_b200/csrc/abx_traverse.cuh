@@ -345,10 +345,11 @@ __device__ __forceinline__ void traverseSpatial(Node64 const *__restrict__ nodes
 // order in which a query's results are emitted changes.
 // queue: QCAP rows of blockDim.x entries (row-major, so a warp's accesses are conflict-free).
 // Every lane of the warp must call this (active = false for lanes without a query).
+// after >= 0: half traversal (HalfTraversal.hpp:52-74), only the leaves at sorted positions > after.
 template <int LEAF_F4, int BUCKET, int QCAP, class P, class Emit>
 __device__ __forceinline__ void traverseSpatialDeferred(Node64 const *__restrict__ nodes,
                                                         float4 const *__restrict__ leaf_box, P const &pred,
-                                                        bool active, unsigned *queue, Emit &&emit)
+                                                        bool active, unsigned *queue, Emit &&emit, int after = -1)
 {
   // a queue entry is a run of sorted leaf positions: (first << 2) | (length - 1); n < 2^30
   static_assert(BUCKET >= 1 && BUCKET <= 4, "run length must fit in two bits");
@@ -368,20 +369,24 @@ __device__ __forceinline__ void traverseSpatialDeferred(Node64 const *__restrict
       float4 const a0 = __ldg(f), a1 = __ldg(f + 1), a2 = __ldg(f + 2), a3 = __ldg(f + 3);
       int const lref = __float_as_int(a0.w), rref = __float_as_int(a1.w);
       int const rl = __float_as_int(a2.w), rr = __float_as_int(a3.w);
-      bool hit_l = pred.box(a0, a1);
-      bool hit_r = pred.box(a2, a3);
-      int const l_len1 = (refIsLeaf(lref) ? rl : lref) - rl; // leaves of the left child - 1
+      int const l_hi = refIsLeaf(lref) ? rl : lref;
+      // a subtree holds leaves > after iff its last position is > after
+      bool hit_l = l_hi > after && pred.box(a0, a1);
+      bool hit_r = rr > after && pred.box(a2, a3);
+      int const l_len1 = l_hi - rl; // leaves of the left child - 1
       int const r_len1 = rr - (refIsLeaf(rref) ? rr : rref);
       if (hit_l && l_len1 < BUCKET)
       {
-        myq[(cnt++) * stride] = ((unsigned)rl << 2) | (unsigned)l_len1;
-        tot += l_len1 + 1;
+        int const first = max(rl, after + 1);
+        myq[(cnt++) * stride] = ((unsigned)first << 2) | (unsigned)(l_hi - first);
+        tot += l_hi - first + 1;
         hit_l = false;
       }
       if (hit_r && r_len1 < BUCKET)
       {
-        myq[(cnt++) * stride] = ((unsigned)(rr - r_len1) << 2) | (unsigned)r_len1;
-        tot += r_len1 + 1;
+        int const first = max(rr - r_len1, after + 1);
+        myq[(cnt++) * stride] = ((unsigned)first << 2) | (unsigned)(rr - first);
+        tot += rr - first + 1;
         hit_r = false;
       }
       if (hit_l)
