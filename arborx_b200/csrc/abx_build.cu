@@ -686,7 +686,9 @@ __global__ void __launch_bounds__(256)
         int const right_child = apetrei_parent + 1;
         bool const right_is_leaf = (right_child == range_right);
         delta_right = deltaOf(codes, range_right, n_int);
-        __threadfence(); // acquire: the sibling published its record before its CAS
+        // no reader-side fence: the loads below are issued after the CAS result is known (the
+        // `old == -1` branch above is resolved first; no speculation) and go to L2 (ld.cg), where
+        // the sibling's record was made visible by its __threadfence() before its own CAS
         if (right_is_leaf)
           loadLeafBox<KIND>(leaf_box, right_child, sib, sib_ref);
         else
@@ -705,7 +707,6 @@ __global__ void __launch_bounds__(256)
         int const left_child = apetrei_parent;
         bool const left_is_leaf = (left_child == range_left);
         delta_left = deltaOf(codes, range_left - 1, n_int);
-        __threadfence();
         if (left_is_leaf)
           loadLeafBox<KIND>(leaf_box, left_child, sib, sib_ref);
         else
