@@ -793,19 +793,20 @@ __global__ void __launch_bounds__(kScanThreads)
 }
 
 // single block: exclusive scan of the tile sums in place
-__global__ void __launch_bounds__(kScanThreads) scanTileOffsetsKernel(int32_t *tile_sums, int tiles)
+constexpr int kScanOffsetThreads = 1024;
+__global__ void __launch_bounds__(kScanOffsetThreads) scanTileOffsetsKernel(int32_t *tile_sums, int tiles)
 {
-  __shared__ unsigned warp_sums[kSortWarps];
+  __shared__ unsigned warp_sums[kScanOffsetThreads / 32];
   __shared__ unsigned carry_s;
   if (threadIdx.x == 0)
     carry_s = 0;
   __syncthreads();
-  for (int base = 0; base < tiles; base += kScanThreads)
+  for (int base = 0; base < tiles; base += kScanOffsetThreads)
   {
     int const i = base + threadIdx.x;
     unsigned v = i < tiles ? (unsigned)tile_sums[i] : 0u;
     unsigned total;
-    unsigned excl = blockExclusiveScan(v, warp_sums, total);
+    unsigned excl = blockExclusiveScanT<kScanOffsetThreads / 32>(v, warp_sums, total);
     unsigned const carry = carry_s;
     if (i < tiles)
       tile_sums[i] = (int32_t)(carry + excl);
@@ -818,31 +819,53 @@ __global__ void __launch_bounds__(kScanThreads) scanTileOffsetsKernel(int32_t *t
 
 // out[i] = sum(in[0..i)) for i < n_plus_1 (the last input element is not read
 // into the total, matching KokkosExt::exclusive_scan over an offsets array whose
-// last slot is scratch: out[n] = total of in[0..n))
+// last slot is scratch: out[n] = total of in[0..n)).  A thread owns kScanItems consecutive
+// elements: two 16-byte loads and stores when the arrays are 16-byte aligned and the
+// thread's elements are all in range.
 __global__ void __launch_bounds__(kScanThreads)
     scanApplyKernel(int32_t const *__restrict__ in, int32_t *__restrict__ out, int64_t n_in, int64_t n_out,
-                    int32_t const *__restrict__ tile_offsets)
+                    int32_t const *__restrict__ tile_offsets, bool aligned16)
 {
+  static_assert(kScanItems == 8, "two int4 per thread");
   __shared__ unsigned warp_sums[kSortWarps];
   int64_t const base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
   int v[kScanItems];
+  bool const vec = aligned16 && base + kScanItems <= n_in;
+  if (vec)
+  {
+    int4 const a = *reinterpret_cast<int4 const *>(in + base), b = *reinterpret_cast<int4 const *>(in + base + 4);
+    v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+  }
+  else
+  {
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j)
+      v[j] = base + j < n_in ? in[base + j] : 0;
+  }
   unsigned local = 0;
 #pragma unroll
   for (int j = 0; j < kScanItems; ++j)
-  {
-    int64_t const i = base + j;
-    v[j] = i < n_in ? in[i] : 0;
     local += (unsigned)v[j];
-  }
   unsigned total;
   unsigned excl = blockExclusiveScan(local, warp_sums, total) + (unsigned)tile_offsets[blockIdx.x];
+  int o[kScanItems];
 #pragma unroll
   for (int j = 0; j < kScanItems; ++j)
   {
-    int64_t const i = base + j;
-    if (i < n_out)
-      out[i] = (int32_t)excl;
+    o[j] = (int)excl;
     excl += (unsigned)v[j];
+  }
+  if (vec) // base + 8 <= n_in < n_out
+  {
+    *reinterpret_cast<int4 *>(out + base) = make_int4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<int4 *>(out + base + 4) = make_int4(o[4], o[5], o[6], o[7]);
+  }
+  else
+  {
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j)
+      if (base + j < n_out)
+        out[base + j] = o[j];
   }
 }
 
@@ -879,8 +902,9 @@ abx_status exclusiveScanI32(cudaStream_t s, int32_t const *in, int32_t *out, int
   TempBuffer<int32_t> tile_sums;
   ABX_TRY(tile_sums.alloc(tiles, s));
   ABX_LAUNCH(scanTileSumsKernel, tiles, kScanThreads, 0, s, in, n_in, tile_sums.ptr);
-  ABX_LAUNCH(scanTileOffsetsKernel, 1, kScanThreads, 0, s, tile_sums.ptr, tiles);
-  ABX_LAUNCH(scanApplyKernel, tiles, kScanThreads, 0, s, in, out, n_in, n_plus_1, tile_sums.ptr);
+  ABX_LAUNCH(scanTileOffsetsKernel, 1, kScanOffsetThreads, 0, s, tile_sums.ptr, tiles);
+  bool const aligned16 = ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0);
+  ABX_LAUNCH(scanApplyKernel, tiles, kScanThreads, 0, s, in, out, n_in, n_plus_1, tile_sums.ptr, aligned16);
   return ABX_OK;
 }
 
