@@ -109,7 +109,8 @@ class Tree:
             self._h = lib().orc_bvh_from_sorted_codes(kind, _p(prims, C.c_float), _p(codes, C.c_ulonglong), self.n)
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        # at interpreter shutdown the module globals (lib) may already be gone
+        if getattr(self, "_h", None) and callable(lib):
             lib().orc_bvh_destroy(self._h)
             self._h = None
 
