@@ -349,13 +349,14 @@ class DistributedTree:
             idx, loff, d = engine.nearest(self._bottom, fwd_preds, what[1])
             cols = [idx.to(torch.int32).unsqueeze(1), d.contiguous().view(torch.int32).unsqueeze(1)]
         loff = loff.long()
-        res_ids = torch.repeat_interleave(fwd_ids, loff[1:] - loff[:-1])
+        # output_size: known from the result's shape, spares the host sync of a data-dependent size
+        res_ids = torch.repeat_interleave(fwd_ids, loff[1:] - loff[:-1], output_size=int(idx.shape[0]))
         back_rows = torch.cat(cols + [res_ids.unsqueeze(1)], 1)
         seg = torch.cumsum(torch.tensor([0] + recv_counts, device=dev), 0)
         back_counts = (loff[seg[1:]] - loff[seg[:-1]]).tolist()
         got, got_counts = _alltoallv(self.comm, back_rows, back_counts)
         src_rank = torch.repeat_interleave(torch.arange(R, device=dev, dtype=torch.int32),
-                                           torch.tensor(got_counts, device=dev))
+                                           torch.tensor(got_counts, device=dev), output_size=int(got.shape[0]))
         ids = got[:, -1].long()
         order = torch.argsort(ids, stable=True)
         vals = torch.stack([got[:, 0][order], src_rank[order]], 1)
@@ -516,7 +517,7 @@ class DistributedTree:
         back_counts = (loff[seg[1:]] - loff[seg[:-1]]).tolist()
         got, got_counts = _alltoallv(self.comm, back_rows, back_counts)
         src_rank = torch.repeat_interleave(torch.arange(R, device=dev, dtype=torch.int32),
-                                           torch.tensor(got_counts, device=dev))
+                                           torch.tensor(got_counts, device=dev), output_size=int(got.shape[0]))
         ids = got[:, 1].long()
         order2 = torch.argsort(ids, stable=True)
         vals = torch.stack([got[:, 0][order2], src_rank[order2]], 1)
