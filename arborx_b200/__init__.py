@@ -205,8 +205,9 @@ class BoundingVolumeHierarchy:
         d = predicates.data
         q = d.shape[0]
         host = not d.is_cuda
-        # host results alias a per-(tree kind, predicate tag) pinned pool: valid until the next host query
-        alloc = _Allocator(space.device, pinned_host=host, pool_key=predicates.tag)
+        # host results alias a pinned pool per (predicate tag, execution space): valid until the next host
+        # query of that kind on that space (concurrent host queries on different spaces do not share buffers)
+        alloc = _Allocator(space.device, pinned_host=host, pool_key=(predicates.tag, space.stream.cuda_stream))
         off, idx, dist = C.c_void_p(), C.c_void_p(), C.c_void_p()
         nnz = C.c_int64()
         L = lib()

@@ -322,8 +322,20 @@ def run_ours(args):
 
     pinned_out = {}
     import concurrent.futures
-    e2e_pool = concurrent.futures.ThreadPoolExecutor(1)
-    space2 = abx.ExecutionSpace(torch.cuda.Stream())
+    import threading
+    E2E_THREADS, E2E_CHUNKS = args.e2e_threads, args.e2e_chunks
+    e2e_pool = concurrent.futures.ThreadPoolExecutor(E2E_THREADS)
+    e2e_local = threading.local()
+    bounds = [q * c // E2E_CHUNKS for c in range(E2E_CHUNKS + 1)]
+    hp_spatial_parts = [abx.intersects(h_spheres[bounds[c]:bounds[c + 1]]) for c in range(E2E_CHUNKS)]
+    hp_nearest_parts = [abx.nearest(h_queries[bounds[c]:bounds[c + 1]], K_NEIGHBORS) for c in range(E2E_CHUNKS)]
+
+    def e2e_task(bvh, preds):
+        if not hasattr(e2e_local, "space"):
+            torch.cuda.set_device(local_rank)
+            e2e_local.space = abx.ExecutionSpace(torch.cuda.Stream())
+        idx, off = bvh.query(e2e_local.space, preds)
+        return int(off[-1]), idx.numel()
 
     def e2e_step():
         if world > 1:
@@ -346,13 +358,21 @@ def run_ours(args):
             return int(off[-1]) + int(koff[-1]), idx.numel(), kidx.numel()
         bvh = abx.BoundingVolumeHierarchy(space, h_values)
         space.fence()
-        # the two query batches are independent: issued from two host threads on two execution
-        # space instances (streams), so one batch's result copy overlaps the other's traversal
-        f_knn = e2e_pool.submit(lambda: bvh.query(space2, hp_nearest))
-        idx, off = bvh.query(space, hp_spatial)
-        kidx, koff = f_knn.result()
-        # results are host tensors: touch them so the step really ends on the host
-        return int(off[-1]) + int(koff[-1]), idx.numel(), kidx.numel()
+        # The query batches are independent, and so are their parts: each batch is issued as E2E_CHUNKS host
+        # calls from E2E_THREADS host threads, every thread on its own execution space instance (stream), so
+        # the result copy of one call overlaps the traversal of the next (PCIe is the long pole of this path:
+        # 0.4 GB in, 0.88 GB out per step).  kNN parts first: they are the longer ones.
+        futures = [e2e_pool.submit(e2e_task, bvh, p) for p in hp_nearest_parts + hp_spatial_parts]
+        total, n_idx, n_kidx = 0, 0, 0
+        for f, p in zip(futures, hp_nearest_parts + hp_spatial_parts):
+            last, cnt = f.result()
+            total += last
+            if p.tag == "nearest":
+                n_kidx += cnt
+            else:
+                n_idx += cnt
+        # results are host tensors: their last offsets were read on the host inside the tasks
+        return total, n_idx, n_kidx
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     for _ in range(max(1, min(args.warmup, 2))):
@@ -430,7 +450,7 @@ def run_ours(args):
         "components": comp,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-                "api": "abx_bvh_build_host + abx_query_spatial_crs_host + abx_query_nearest_crs_host (the two query calls from two host threads on two streams)"},
+                "api": "abx_bvh_build_host + abx_query_spatial_crs_host + abx_query_nearest_crs_host (each query batch as %d host calls, issued from %d host threads / streams)" % (args.e2e_chunks, args.e2e_threads)},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
@@ -568,6 +588,8 @@ def main():
     ap.add_argument("--q", type=int, default=None)
     ap.add_argument("--cpu-sample", type=int, default=500_000, help="queries timed on the CPU baseline")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-threads", type=int, default=3, help="host threads (streams) of the end-to-end path")
+    ap.add_argument("--e2e-chunks", type=int, default=4, help="host calls per query batch in the end-to-end path")
     ap.add_argument("--workload", default="bvh", choices=["bvh", "dbscan"],
                     help="bvh: the headline bvh_driver step (default); dbscan: secondary DBSCAN workload")
     args = ap.parse_args()
