@@ -75,6 +75,34 @@ def test_sort_u64_prefix_runs(cuda, n, run):
     assert np.array_equal(k, keys[order])
 
 
+@pytest.mark.parametrize("n", [2048, 2049, 16_384, 16_385, 524_288, 524_289, 4_194_305])
+def test_sort_u64_level_boundaries(cuda, n):
+    """Sizes on both sides of the points where the number of top digits of the fix-up path changes
+    (n / 8 against 2^8, 2^16, 2^24; abx_sort.cu sortPairsDB), keys over all 64 bits."""
+    rng = np.random.default_rng(n)
+    keys = rng.integers(0, 2 ** 64, n, dtype=np.uint64)
+    keys[n // 3] = keys[n // 5]
+    k, p = cuda.sort_u64(keys)
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(p, order.astype(np.uint32))
+    assert np.array_equal(k, keys[order])
+
+
+@pytest.mark.parametrize("distinct", [50, 1000, 40_000])
+def test_sort_u64_clustered_prefixes(cuda, distinct):
+    """Most keys share few 40-bit prefixes (the Morton codes of a clustered cloud): the prefix sample sends the
+    sort to the plain LSD (or the 5-digit level) instead of a fix-up that would overflow."""
+    n = 600_000
+    rng = np.random.default_rng(distinct)
+    pre = rng.integers(0, 2 ** 40, distinct, dtype=np.uint64) << np.uint64(23)
+    keys = pre[rng.integers(0, distinct, n)] | rng.integers(0, 2 ** 23, n, dtype=np.uint64)
+    keys[:1000] = rng.integers(0, 2 ** 63, 1000, dtype=np.uint64)  # a little noise that spans the range
+    k, p = cuda.sort_u64(keys)
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(p, order.astype(np.uint32))
+    assert np.array_equal(k, keys[order])
+
+
 @pytest.mark.parametrize("n", [1, 5, 4096, 300_001])
 def test_sort_u32(cuda, n):
     rng = np.random.default_rng(n + 1)
