@@ -290,7 +290,10 @@ __device__ __forceinline__ void loadNodeBox(Node64 const *nodes, int k, Box &b)
 #ifndef ABX_HIER_MINB
 #define ABX_HIER_MINB 1
 #endif
-constexpr int kHierWarpLeaves = 64; // stage-1 window
+#ifndef ABX_HIER_WARP_LEAVES
+#define ABX_HIER_WARP_LEAVES 64
+#endif
+constexpr int kHierWarpLeaves = ABX_HIER_WARP_LEAVES; // stage-1 window
 constexpr int kHierWarpsDefault = 4; // warps per block: the stage-2 window is W * 64 leaves (ABX_HIER_WARPS overrides)
 constexpr int kFlagFree = -1;                            // no child has arrived
 constexpr int kFlagDone = -3;                            // both children arrived, node written
