@@ -473,8 +473,8 @@ def run_ours(args):
 
 
 def run_dbscan_distributed(args, world, rank, local_rank):
-    """`--workload dbscan --gpus N` (N > 1): the distributed DBSCAN (halo exchange + label merge) with one
-    GanTao cloud of n points per rank, rank r's cloud shifted by r * L along x (touching slabs), weak scaling."""
+    """`--workload dbscan --gpus N` (N > 1): the distributed DBSCAN (halo exchange + label merge) with the
+    GanTao cloud of n points on every rank, rank r's copy shifted by r * L along x (touching slabs), weak scaling."""
     import torch
     import torch.distributed as dist
 
@@ -484,7 +484,9 @@ def run_dbscan_distributed(args, world, rank, local_rank):
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n, eps = args.n, 200.0
-    pts = clouds.gan_tao(3 + rank, n)
+    # the same cloud on every rank (identical work per GPU: the step time then shows the halo / merge
+    # overhead, not the luck of a seed), shifted into the rank's slab
+    pts = clouds.gan_tao(3, n)
     pts[:, 0] += np.float32(rank * 1.0e6)
     space = abx.ExecutionSpace()
     d = torch.from_numpy(pts).cuda()
