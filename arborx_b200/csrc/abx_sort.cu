@@ -6,14 +6,22 @@
 // Stable: equal keys keep their original order, so the tree
 // built on top is deterministic and bit-comparable with the oracle.
 //
-// Structure (one launch per digit + two small launches up front):
-//   1. radixHistogramKernel   reads the keys once, builds all per-digit histograms
+// Structure (one launch per digit + small launches up front):
+//   0. prefixSampleKernel     2048 sampled keys -> how clustered the top bits are (sortPairsDB)
+//   1. radixHistogramKernel   reads the keys once, builds the histograms of the digits to sort
 //   2. radixScanHistKernel    exclusive scan of each 2^BITS-bin histogram
-//   3. onesweepPassKernel     per digit: tiles rank their keys with warp match-any
-//                             multisplit, obtain their global digit offsets with a
+//   3. onesweepPassKernel     per digit: tiles rank their keys with a warp multisplit
+//                             (8 ballots per key), obtain their global digit offsets with a
 //                             decoupled look-back over per-tile digit counts, stage
 //                             the tile in shared memory in sorted order and write
 //                             it out in coalesced runs.
+//   4. segmentFixKernel       when only the top digits were sorted (keys spread over many
+//                             prefixes): ranks every key inside its short run of equal top
+//                             bits, which finishes the stable sort of the full key with one
+//                             more read + write instead of one per remaining digit.
+// sortPairsDB picks the plan: top digits + fix-up (3 + 1 launches for 10M Morton64 keys),
+// more top digits if the fix-up reports a run above its 256-key limit, or the plain LSD
+// over all digits.  Every plan produces the same stable order.
 #include "abx_common.cuh"
 
 #include <cstdlib>
