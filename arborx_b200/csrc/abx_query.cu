@@ -3,10 +3,12 @@
 // Behavioural contract: spatial/detail/ArborX_TreeTraversal.hpp:34-120 (spatial),
 // :122-336 (nearest), spatial/detail/ArborX_HalfTraversal.hpp:24-75 (half).  The
 // reference walks {left_child, rope} nodes one box test per step; here one
-// 64-byte Node64 load tests both children, leaf boxes live in the parent record
-// (a point leaf is never dereferenced), and a short per-thread stack replaces the
-// ropes.  Result sets are identical; order inside a row is traversal order, which
-// the reference does not specify either.
+// 64-byte Node64 load tests both children, leaf boxes live in the parent record, and
+// a short per-thread stack replaces the ropes.  The spatial kernels queue the leaves
+// they have to test and test them with the warp converged (traverseSpatialDeferred);
+// the nearest kernel keeps its candidates in an unsorted shared-memory set and never
+// dereferences point leaves.  Result sets are identical; order inside a row is
+// traversal order, which the reference does not specify either.
 #include "abx_traverse.cuh"
 
 // minimum resident blocks per SM of the traversal kernels (register cap; tuning aid)
