@@ -38,6 +38,26 @@ struct FirstOnly
     return abx::cb::Control::early_exit;
   }
 };
+// output form: for every match emit (value, squared distance to the sphere centre) -- a custom output type
+struct Hit
+{
+  unsigned value;
+  float d2;
+};
+struct EmitHit
+{
+  float const *spheres;
+  float const *pts;
+  template <class Out>
+  __device__ void operator()(int64_t q, unsigned value, Out &out) const
+  {
+    float const dx = pts[3 * value] - spheres[4 * q], dy = pts[3 * value + 1] - spheres[4 * q + 1],
+                dz = pts[3 * value + 2] - spheres[4 * q + 2];
+    out(Hit{value, dx * dx + dy * dy + dz * dz});
+    if (value % 7 == 0) // a callback may emit any number of results per match
+      out(Hit{value, -1.f});
+  }
+};
 struct NearestSum
 {
   float *dist_sum;
@@ -100,6 +120,12 @@ int main()
   CHECK(abx::cb::query(bvh, s, abx::cb::intersects_spheres(d_spheres, q),
                        [=] __device__(int64_t, unsigned) { atomicAdd(d_total, 1); }));
 
+  int32_t *hoff_dev = nullptr;
+  Hit *hits_dev = nullptr;
+  int64_t n_hits = 0;
+  CHECK(abx::cb::query_crs<Hit>(bvh, s, abx::cb::intersects_spheres(d_spheres, q), EmitHit{d_spheres, d_pts}, &hoff_dev,
+                                &hits_dev, &n_hits));
+
   // reference answers: CRS queries through the C ABI
   abx_policy pol = {0, 1};
   int32_t *off = nullptr, *koff = nullptr;
@@ -143,6 +169,39 @@ int main()
     bad += h_last[i] != (int)h_kidx[h_koff[i + 1] - 1];
   }
   bad += h_total != (int)nnz;
+  // output-form rows: same values as the CRS rows (as sets), plus the extra record for multiples of 7
+  {
+    std::vector<int32_t> h_hoff(q + 1);
+    std::vector<Hit> h_hits(n_hits);
+    cudaMemcpy(h_hoff.data(), hoff_dev, (q + 1) * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(h_hits.data(), hits_dev, n_hits * sizeof(Hit), cudaMemcpyDeviceToHost);
+    for (int i = 0; i < q; ++i)
+    {
+      unsigned long long sum = 0, want_sum = 0;
+      int plain = 0, extra = 0, want_extra = 0;
+      for (int j = h_hoff[i]; j < h_hoff[i + 1]; ++j)
+      {
+        if (h_hits[j].d2 < 0.f)
+          ++extra;
+        else
+        {
+          ++plain;
+          sum += h_hits[j].value;
+          float const r = spheres[4 * i + 3];
+          bad += !(h_hits[j].d2 <= r * r * 1.0001f);
+        }
+      }
+      for (int j = h_off[i]; j < h_off[i + 1]; ++j)
+      {
+        want_sum += h_idx[j];
+        want_extra += h_idx[j] % 7 == 0;
+      }
+      bad += plain != h_off[i + 1] - h_off[i];
+      bad += sum != want_sum;
+      bad += extra != want_extra;
+    }
+    std::printf("output-form results %lld\n", (long long)n_hits);
+  }
   std::printf("queries %d, matches %lld, mismatches %d\n", q, (long long)nnz, bad);
   abx_bvh_destroy(bvh);
   if (bad)

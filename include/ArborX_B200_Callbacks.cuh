@@ -16,6 +16,9 @@
  *   abx::cb::Control f(int64_t query, unsigned value)            return Control::early_exit to end that query
  *                                                                (CallbackTreeTraversalControl, :24-28)
  *   nearest: void f(int64_t query, unsigned value, float distance), called for the k nearest in ascending order
+ *   output form (Callbacks.hpp:86-110, CrsGraphWrapperImpl.hpp:86-110): f(int64_t query, unsigned value, Out &out)
+ *       with out(x) emitting zero or more results of any trivially copyable type per match; query_crs() returns
+ *       them as CRS rows in the original predicate order (count pass, scan, fill pass, like the reference's 2P path)
  * `query` is the position of the predicate in the batch (what the reference passes through attach()/getData()),
  * `value` the index of the primitive the tree was built on.  Predicates are visited one per thread in batch
  * order; pass a Morton-ordered batch (abx_morton32 + abx_sort_u32) for coherent warps. */
@@ -173,6 +176,132 @@ inline abx_status query(abx_bvh *bvh, cudaStream_t stream, NearestPredicates con
   abx_free(stream, indices);
   abx_free(stream, distances);
   return st;
+}
+
+namespace detail
+{
+// the `out` object handed to an output-form callback: counts in the first pass, stores in the second
+template <class T>
+struct OutputFunctor
+{
+  T *row;     // nullptr while counting
+  int count;
+  __device__ void operator()(T const &x)
+  {
+    if (row)
+      row[count] = x;
+    ++count;
+  }
+};
+
+template <class T, class Callback>
+struct OutputAdapter
+{
+  Callback cb;
+  int32_t *counts;          // pass 1: results per query (written at the end of the query's traversal)
+  int32_t const *offsets;   // pass 2
+  T *values;
+};
+
+template <int PRED, int LEAF_F4, bool TRI, class T, class Callback>
+__global__ void __launch_bounds__(kThreads)
+    spatialOutputKernel(Node64 const *__restrict__ nodes, float4 const *__restrict__ leaf_box,
+                        float4 const *__restrict__ leaf_tri, int64_t n, float const *__restrict__ preds, int64_t q,
+                        Callback cb, int32_t *counts, int32_t const *__restrict__ offsets, T *values)
+{
+  int64_t const qi = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (qi >= q)
+    return;
+  Pred<PRED> pred;
+  pred.load(preds, qi);
+  OutputFunctor<T> out{offsets ? values + offsets[qi] : nullptr, 0};
+  if (n == 1)
+  {
+    float4 const lo = __ldg(leaf_box);
+    float4 const hi = LEAF_F4 == 1 ? lo : __ldg(leaf_box + 1);
+    if (pred.box(lo, hi) && (!TRI || triangleLeafTest<PRED>(pred, leaf_tri, 0)))
+      cb(qi, 0u, out);
+  }
+  else
+    traverseSpatial<LEAF_F4>(nodes, leaf_box, pred, [&](unsigned orig, int pos) {
+      if (TRI && !triangleLeafTest<PRED>(pred, leaf_tri, pos))
+        return false;
+      cb(qi, orig, out);
+      return false;
+    });
+  if (!offsets)
+    counts[qi] = out.count;
+}
+
+template <int PRED, class T, class Callback>
+inline abx_status launchOutput(abx_device_view const &v, cudaStream_t s, SpatialPredicates const &p, Callback const &cb,
+                               int32_t *counts, int32_t const *offsets, T *values)
+{
+  int const grid = (int)((p.q + kThreads - 1) / kThreads);
+  auto const *nodes = (Node64 const *)v.nodes;
+  auto const *lb = (float4 const *)v.leaf_box;
+  auto const *lt = (float4 const *)v.leaf_tri;
+  if (v.prim_kind == ABX_PRIM_TRI3F)
+    spatialOutputKernel<PRED, 2, true, T><<<grid, kThreads, 0, s>>>(nodes, lb, lt, v.n, p.data, p.q, cb, counts, offsets, values);
+  else if (v.prim_kind == ABX_PRIM_BOX3F)
+    spatialOutputKernel<PRED, 2, false, T><<<grid, kThreads, 0, s>>>(nodes, lb, lt, v.n, p.data, p.q, cb, counts, offsets, values);
+  else
+    spatialOutputKernel<PRED, 1, false, T><<<grid, kThreads, 0, s>>>(nodes, lb, lt, v.n, p.data, p.q, cb, counts, offsets, values);
+  return cudaGetLastError() == cudaSuccess ? ABX_OK : ABX_ERR_CUDA;
+}
+
+template <class T, class Callback>
+inline abx_status dispatchOutput(abx_device_view const &v, cudaStream_t s, SpatialPredicates const &p, Callback const &cb,
+                                 int32_t *counts, int32_t const *offsets, T *values)
+{
+  switch (p.kind)
+  {
+  case ABX_PRED_SPHERE3F: return launchOutput<ABX_PRED_SPHERE3F, T>(v, s, p, cb, counts, offsets, values);
+  case ABX_PRED_BOX3F: return launchOutput<ABX_PRED_BOX3F, T>(v, s, p, cb, counts, offsets, values);
+  case ABX_PRED_POINT3F: return launchOutput<ABX_PRED_POINT3F, T>(v, s, p, cb, counts, offsets, values);
+  case ABX_PRED_RAY3F: return launchOutput<ABX_PRED_RAY3F, T>(v, s, p, cb, counts, offsets, values);
+  default: return ABX_ERR_ARG;
+  }
+}
+} // namespace detail
+
+/* bvh.query(space, predicates, callback, out, offsets) with an output-form callback
+ * callback(query, value, out): *offsets_dev (q + 1 ints) and *values_dev (nnz elements of T) are allocated
+ * with cudaMallocAsync on `stream` (release with cudaFreeAsync); *nnz = number of emitted values.  Two
+ * traversals (count, fill), the reference's default two-pass CRS path; blocks once for nnz. */
+template <class T, class Callback>
+inline abx_status query_crs(abx_bvh const *bvh, cudaStream_t stream, SpatialPredicates const &predicates,
+                            Callback const &callback, int32_t **offsets_dev, T **values_dev, int64_t *nnz)
+{
+  static_assert(std::is_trivially_copyable_v<T>, "output values are copied bytewise");
+  abx_device_view v;
+  abx_status st = abx_bvh_device_view(bvh, &v);
+  if (st != ABX_OK)
+    return st;
+  int64_t const q = predicates.q < 0 ? 0 : predicates.q;
+  *values_dev = nullptr;
+  *nnz = 0;
+  if (cudaMallocAsync((void **)offsets_dev, sizeof(int32_t) * (size_t)(q + 1), stream) != cudaSuccess)
+    return ABX_ERR_CUDA;
+  cudaMemsetAsync(*offsets_dev, 0, sizeof(int32_t) * (size_t)(q + 1), stream);
+  if (v.n == 0 || q == 0)
+    return ABX_OK;
+  st = detail::dispatchOutput<T>(v, stream, predicates, callback, *offsets_dev, nullptr, (T *)nullptr);
+  if (st != ABX_OK)
+    return st;
+  st = abx_exclusive_scan_i32(stream, *offsets_dev, *offsets_dev, q + 1);
+  if (st != ABX_OK)
+    return st;
+  int32_t total = 0;
+  cudaMemcpyAsync(&total, *offsets_dev + q, sizeof(int32_t), cudaMemcpyDeviceToHost, stream);
+  if (cudaStreamSynchronize(stream) != cudaSuccess)
+    return ABX_ERR_CUDA;
+  *nnz = total;
+  if (total == 0)
+    return ABX_OK;
+  if (cudaMallocAsync((void **)values_dev, sizeof(T) * (size_t)total, stream) != cudaSuccess)
+    return ABX_ERR_CUDA;
+  return detail::dispatchOutput<T>(v, stream, predicates, callback, nullptr, *offsets_dev, *values_dev);
 }
 
 } // namespace cb
