@@ -285,6 +285,43 @@ class BoundingVolumeHierarchy:
 BVH = BoundingVolumeHierarchy
 
 
+def _rows_from_pairs(keys, vals, n):
+    """CRS (offsets [n + 1] int32, indices) of vals grouped by keys (rows in ascending key order)."""
+    order = torch.argsort(keys, stable=True)
+    offsets = torch.zeros(n + 1, dtype=torch.int32, device=keys.device)
+    offsets[1:] = torch.cumsum(torch.bincount(keys, minlength=n), 0).to(torch.int32)
+    return offsets, vals[order].to(torch.int32)
+
+
+def find_half_neighbor_list(space, points, radius):
+    """Experimental::findHalfNeighborList (spatial/detail/ArborX_NeighborList.hpp:47-110): every unordered pair of
+    points within `radius` appears once; row i holds the partners j of the pairs the half traversal reports as
+    (j, i), i.e. (value1, value2) with value2 the later leaf in the tree's order.  -> (offsets, indices); the order
+    inside a row is unspecified in the reference (atomics), ascending partner order here."""
+    pts = _as_f32(points, 3)
+    n = pts.shape[0]
+    bvh = BoundingVolumeHierarchy(space, pts.to(space.device), POINT)
+    pairs = bvh.half_traversal_pairs(space, radius).long()
+    with torch.cuda.stream(space.stream):
+        # sort by (row, partner): partner order first, then a stable sort by row
+        o = torch.argsort(pairs[:, 0], stable=True)
+        return _rows_from_pairs(pairs[o, 1], pairs[o, 0], n)
+
+
+def find_full_neighbor_list(space, points, radius):
+    """Experimental::findFullNeighborList (ArborX_NeighborList.hpp:112-190): the symmetric list, every pair in both
+    rows (the half list expanded, ArborX_ExpandHalfToFull.hpp:24-72)."""
+    pts = _as_f32(points, 3)
+    n = pts.shape[0]
+    bvh = BoundingVolumeHierarchy(space, pts.to(space.device), POINT)
+    pairs = bvh.half_traversal_pairs(space, radius).long()
+    with torch.cuda.stream(space.stream):
+        a = torch.cat([pairs[:, 0], pairs[:, 1]])
+        b = torch.cat([pairs[:, 1], pairs[:, 0]])
+        o = torch.argsort(b, stable=True)
+        return _rows_from_pairs(a[o], b[o], n)
+
+
 def query(tree, space, predicates, policy=None, **kw):
     """ArborX::query free function (spatial/ArborX_CrsGraphWrapper.hpp:22-35)."""
     return tree.query(space, predicates, policy, **kw)

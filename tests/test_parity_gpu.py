@@ -393,3 +393,27 @@ def test_nearest_short_rows_for_unreachable_leaves(cuda, orc):
     oc, ic, dc = tc.nearest_crs(qp, ks)
     oo, io, do = to.nearest_crs(qp, ks)
     assert np.array_equal(oc, oo) and np.array_equal(ic, io) and np.array_equal(dc, do)
+
+
+def test_neighbor_lists(cuda):
+    """findHalfNeighborList / findFullNeighborList (ArborX_NeighborList.hpp:47-190; tstNeighborList.cpp compares the
+    full list with a radius query and the half list with its j < i filter): here against the O(n^2) matrix."""
+    import torch
+    import arborx_b200 as abx
+    n, r = 3000, 0.08
+    pts = clouds.uniform01(11, n)
+    space = abx.ExecutionSpace()
+    d = brute.dist_point_point(pts, pts) <= F(r)
+    np.fill_diagonal(d, False)
+    off, idx = abx.find_full_neighbor_list(space, torch.from_numpy(pts).cuda(), r)
+    off, idx = off.cpu().numpy(), idx.cpu().numpy()
+    for i in range(n):
+        assert np.array_equal(np.sort(idx[off[i]:off[i + 1]]), np.nonzero(d[i])[0]), i
+    hoff, hidx = abx.find_half_neighbor_list(space, torch.from_numpy(pts).cuda(), r)
+    hoff, hidx = hoff.cpu().numpy(), hidx.cpu().numpy()
+    assert hoff[-1] * 2 == off[-1]
+    seen = set()
+    for i in range(n):
+        for j in hidx[hoff[i]:hoff[i + 1]]:
+            assert d[i, j] and (j, i) not in seen and (i, j) not in seen
+            seen.add((i, int(j)))
