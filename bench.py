@@ -325,6 +325,7 @@ def run_ours(args):
     import threading
     E2E_THREADS, E2E_CHUNKS = args.e2e_threads, args.e2e_chunks
     e2e_pool = concurrent.futures.ThreadPoolExecutor(E2E_THREADS)
+    e2e_copy_stream = torch.cuda.Stream()
     e2e_local = threading.local()
     bounds = [q * c // E2E_CHUNKS for c in range(E2E_CHUNKS + 1)]
     hp_spatial_parts = [abx.intersects(h_spheres[bounds[c]:bounds[c + 1]]) for c in range(E2E_CHUNKS)]
@@ -340,19 +341,33 @@ def run_ours(args):
     def e2e_step():
         if world > 1:
             # DistributedTree takes device data: the host<->device copies are done here, inside the step
+            # all three uploads are queued up front; the radius results go back on a copy stream while the kNN
+            # query runs
             dv = h_values.cuda(non_blocking=True)
+            d_sp = h_spheres.cuda(non_blocking=True)
+            d_qq = h_queries.cuda(non_blocking=True)
             tree = make_tree(dv)
-            idx, off = tree.query(space, abx.intersects(h_spheres.cuda(non_blocking=True)))
-            kidx, koff = tree.query(space, abx.nearest(h_queries.cuda(non_blocking=True), K_NEIGHBORS))
-            outs = []
-            for name, t in (("idx", idx), ("off", off), ("kidx", kidx), ("koff", koff)):
-                buf = pinned_out.get(name)
-                if buf is None or buf.numel() < t.numel():
-                    buf = torch.empty(int(t.numel() * 1.1) + 16, dtype=t.dtype, pin_memory=True)
-                    pinned_out[name] = buf
-                h = buf[:t.numel()].view(t.shape)
-                h.copy_(t, non_blocking=True)
-                outs.append(h)
+            main = torch.cuda.current_stream()
+
+            def to_host(pairs, stream):
+                hs = []
+                with torch.cuda.stream(stream):
+                    for name, t in pairs:
+                        buf = pinned_out.get(name)
+                        if buf is None or buf.numel() < t.numel():
+                            buf = torch.empty(int(t.numel() * 1.1) + 16, dtype=t.dtype, pin_memory=True)
+                            pinned_out[name] = buf
+                        h = buf[:t.numel()].view(t.shape)
+                        h.copy_(t, non_blocking=True)
+                        t.record_stream(stream)
+                        hs.append(h)
+                return hs
+
+            idx, off = tree.query(space, abx.intersects(d_sp))
+            e2e_copy_stream.wait_stream(main)
+            outs = to_host((("idx", idx), ("off", off)), e2e_copy_stream)
+            kidx, koff = tree.query(space, abx.nearest(d_qq, K_NEIGHBORS))
+            outs += to_host((("kidx", kidx), ("koff", koff)), main)
             torch.cuda.synchronize()
             idx, off, kidx, koff = outs
             return int(off[-1]) + int(koff[-1]), idx.numel(), kidx.numel()
