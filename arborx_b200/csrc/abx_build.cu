@@ -6,6 +6,8 @@
 // reference's {left_child, rope, box} nodes.
 #include "abx_common.cuh"
 
+#include <mutex>
+
 namespace abx
 {
 
@@ -919,6 +921,7 @@ static void destroyTree(abx_bvh *t)
   deviceFree(t->leaf_tri, s);
   deviceFree(t->perm, s);
   deviceFree(t->codes, s);
+  deviceFree(t->wide, s);
   deviceFree(t->bounds_dev, s);
   delete t;
 }
@@ -977,6 +980,123 @@ abx_status buildHierarchy(cudaStream_t s, abx_bvh *t, void const *prims)
   ABX_DISPATCH_PRIM(t->kind, ABX_LAUNCH((hierarchyGlobalKernel<K>), std::max(grid, 1), 256, 0, s, n,
                                         (unsigned long long const *)t->codes, t->nodes, t->leaf_box, ranges.ptr,
                                         pending.ptr, pending_count.ptr, t->bounds_dev));
+  return ABX_OK;
+}
+
+// ---- experimental 4-wide nodes (Wide64, abx_common.cuh) ------------------------------------------------------
+// one thread per binary internal node: its children, with internal children of more than kWideRun leaves expanded
+__global__ void __launch_bounds__(256) wideConvertKernel(int n, Node64 const *__restrict__ nodes, Wide64 *__restrict__ wide,
+                                                       unsigned *__restrict__ violations)
+{
+  int const i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1)
+    return;
+  float lo[4][3], hi[4][3];
+  int ref[4];
+  int m = 0;
+  auto add = [&](float4 const &bl, float4 const &bh, int child_ref, int first, int last) {
+    int const leaves = last - first + 1;
+    lo[m][0] = bl.x, lo[m][1] = bl.y, lo[m][2] = bl.z;
+    hi[m][0] = bh.x, hi[m][1] = bh.y, hi[m][2] = bh.z;
+    ref[m] = leaves <= kWideRun ? ~((first << 2) | (leaves - 1)) : child_ref;
+    ++m;
+  };
+  auto side = [&](float4 const &bl, float4 const &bh, int child_ref, int first, int last) {
+    if (last - first + 1 <= kWideRun)
+    {
+      add(bl, bh, child_ref, first, last);
+      return;
+    }
+    // internal child with more than kWideRun leaves: its two children take its place
+    float4 const *g = reinterpret_cast<float4 const *>(nodes + child_ref);
+    float4 const c0 = ldcg4(g), c1 = ldcg4(g + 1), c2 = ldcg4(g + 2), c3 = ldcg4(g + 3);
+    int const clref = __float_as_int(c0.w), crref = __float_as_int(c1.w);
+    int const crl = __float_as_int(c2.w), crr = __float_as_int(c3.w);
+    add(c0, c1, clref, crl, refIsLeaf(clref) ? crl : clref);
+    add(c2, c3, crref, refIsLeaf(crref) ? crr : crref, crr);
+  };
+  float4 const *f = reinterpret_cast<float4 const *>(nodes + i);
+  float4 const a0 = ldcg4(f), a1 = ldcg4(f + 1), a2 = ldcg4(f + 2), a3 = ldcg4(f + 3);
+  int const lref = __float_as_int(a0.w), rref = __float_as_int(a1.w);
+  int const rl = __float_as_int(a2.w), rr = __float_as_int(a3.w);
+  side(a0, a1, lref, rl, refIsLeaf(lref) ? rl : lref);
+  side(a2, a3, rref, refIsLeaf(rref) ? rr : rref, rr);
+
+  float origin[3], scale[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+  {
+    float mn = lo[0][d], mx = hi[0][d];
+    for (int k = 1; k < m; ++k)
+    {
+      mn = fminf(mn, lo[k][d]);
+      mx = fmaxf(mx, hi[k][d]);
+    }
+    origin[d] = mn;
+    scale[d] = __fdiv_ru(__fsub_ru(mx, mn), 255.0f);
+  }
+  unsigned q[6] = {0, 0, 0, 0, 0, 0};
+  // boxes with infinite or NaN coordinates cannot be quantised: the tree then keeps the Node64 walk
+  bool bad = !(isfinite(scale[0]) && isfinite(scale[1]) && isfinite(scale[2]) && isfinite(origin[0]) &&
+               isfinite(origin[1]) && isfinite(origin[2]));
+  for (int k = 0; k < m; ++k)
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+    {
+      int ql = 0, qh = 0;
+      if (scale[d] > 0.f)
+      {
+        ql = min(255, max(0, (int)floorf(__fdiv_rd(__fsub_rd(lo[k][d], origin[d]), scale[d]))));
+        qh = min(255, max(0, (int)ceilf(__fdiv_ru(__fsub_ru(hi[k][d], origin[d]), scale[d]))));
+      }
+      // conservative by construction: checked with the decoder's own arithmetic
+      while (ql > 0 && wideLo((float)ql, scale[d], origin[d]) > lo[k][d])
+        --ql;
+      while (qh < 255 && wideHi((float)qh, scale[d], origin[d]) < hi[k][d])
+        ++qh;
+      bad |= wideLo((float)ql, scale[d], origin[d]) > lo[k][d] || wideHi((float)qh, scale[d], origin[d]) < hi[k][d];
+      int const bl = 6 * k + d, bh = 6 * k + 3 + d;
+      q[bl >> 2] |= (unsigned)ql << (8 * (bl & 3));
+      q[bh >> 2] |= (unsigned)qh << (8 * (bh & 3));
+    }
+  if (bad)
+    atomicAdd(violations, 1u);
+  for (int k = m; k < 4; ++k)
+    ref[k] = kWideEmpty;
+  uint4 *o = wide[i].w;
+  o[0] = make_uint4(__float_as_uint(origin[0]), __float_as_uint(origin[1]), __float_as_uint(origin[2]),
+                    __float_as_uint(scale[0]));
+  o[1] = make_uint4(__float_as_uint(scale[1]), __float_as_uint(scale[2]), q[0], q[1]);
+  o[2] = make_uint4(q[2], q[3], q[4], q[5]);
+  o[3] = make_uint4((unsigned)ref[0], (unsigned)ref[1], (unsigned)ref[2], (unsigned)ref[3]);
+}
+
+// built once per tree, on the first query that wants it; blocks until the records are in place
+abx_status ensureWide(cudaStream_t s, abx_bvh *t)
+{
+  static std::mutex mtx;
+  std::lock_guard<std::mutex> lock(mtx);
+  if (t->wide || t->wide_unsupported || t->n < 2)
+    return ABX_OK;
+  int const n = (int)t->n;
+  Wide64 *w = nullptr;
+  ABX_TRY(deviceAlloc((void **)&w, sizeof(Wide64) * (size_t)(n - 1), s));
+  TempBuffer<unsigned> violations;
+  ABX_TRY(violations.alloc(1, s));
+  ABX_CUDA_TRY(cudaMemsetAsync(violations.ptr, 0, sizeof(unsigned), s));
+  ABX_LAUNCH(wideConvertKernel, divUp(n - 1, 256), 256, 0, s, n, t->nodes, w, violations.ptr);
+  unsigned h = 0;
+  ABX_CUDA_TRY(cudaMemcpyAsync(&h, violations.ptr, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+  ABX_CUDA_TRY(cudaStreamSynchronize(s));
+  if (h)
+  {
+    // non-finite boxes (or an encoder bug the check caught): this tree keeps the exact Node64 walk
+    deviceFree(w, s);
+    t->wide_unsupported = true;
+    return ABX_OK;
+  }
+  t->wide = w;
+  t->bytes += sizeof(Wide64) * (size_t)(n - 1);
   return ABX_OK;
 }
 

@@ -199,6 +199,30 @@ struct Node64
 };
 static_assert(sizeof(Node64) == 64, "Node64 must be 64 bytes");
 
+// Experimental 4-wide node (ABX_WIDE=1; DESIGN.md "where the time is"): one 64-byte record per internal node of
+// the binary tree holding up to four children -- the node's grandchildren, or a child itself when that child is a
+// leaf or a subtree of <= 4 leaves (then a "leaf run" of sorted positions).  Child boxes are quantised to 8 bits
+// per coordinate against the node's own box and are CONSERVATIVE (decoded box contains the exact one: the encoder
+// checks it with the decoder's own arithmetic), so a traversal that tests every reported leaf exactly returns the
+// same result set with half the dependent node loads.
+//   w[0] = (origin.x, origin.y, origin.z, scale.x)   w[1] = (scale.y, scale.z, q[0..3], q[4..7])
+//   w[2] = (q[8..11], q[12..15], q[16..19], q[20..23])   q[6k + d] = min_d, q[6k + 3 + d] = max_d of child k
+//   w[3] = child refs: >= 0 wide node (Karras index), kWideEmpty none, else ~((first << 2) | (leaves - 1))
+struct Wide64
+{
+  uint4 w[4];
+};
+static_assert(sizeof(Wide64) == 64, "Wide64 must be 64 bytes");
+constexpr int kWideEmpty = (int)0x80000000;
+constexpr int kWideRun = 4; // leaves per leaf run (two bits)
+__device__ __forceinline__ float wideByte(unsigned word, int j)
+{
+  // exact float(byte j of word): 0x4B000000 | b is 2^23 + b
+  return __fsub_rn(__uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540 | j)), 8388608.0f);
+}
+__device__ __forceinline__ float wideLo(float q, float scale, float origin) { return __fmaf_rd(q, scale, origin); }
+__device__ __forceinline__ float wideHi(float q, float scale, float origin) { return __fmaf_ru(q, scale, origin); }
+
 __device__ __forceinline__ int refLeaf(unsigned orig) { return ~(int)orig; }
 __device__ __forceinline__ bool refIsLeaf(int ref) { return ref < 0; }
 __device__ __forceinline__ unsigned refOrig(int ref) { return (unsigned)(~ref); }
@@ -265,6 +289,8 @@ struct abx_bvh
   float4 *leaf_tri = nullptr;    // triangles only: 3 float4 per sorted leaf (a, b, c)
   uint32_t *perm = nullptr;      // sorted position -> original index
   uint64_t *codes = nullptr;     // sorted Morton64 codes
+  abx::Wide64 *wide = nullptr;   // experimental 4-wide nodes, built on first use (ABX_WIDE=1)
+  bool wide_unsupported = false; // non-finite boxes: keep the Node64 walk
   float *bounds_dev = nullptr;   // 6 floats, root box (scene bounds)
   float bounds_host[6];
   bool bounds_host_valid = false;
@@ -317,6 +343,7 @@ abx_status compactRows(cudaStream_t s, int64_t q, int32_t const *old_offsets, in
 abx_status routeLaunch(cudaStream_t s, bool fill, int pred_kind, void const *preds, int64_t q, float const *radius,
                        int64_t radius_stride, float const *boxes6, int R, int self_rank, unsigned *counts,
                        unsigned const *base, unsigned *cursors, int32_t *out_qid);
+abx_status ensureWide(cudaStream_t s, abx_bvh *t);
 abx_status mergeSorted(cudaStream_t s, int64_t q, int32_t const *local_off, int32_t const *local_idx, int rank,
                        int64_t m, int64_t const *remote_ids, int32_t const *remote_vals2, int32_t *out_off,
                        int32_t *out_vals2);

@@ -47,7 +47,8 @@ constexpr int kSpatialVariantDefault = 1; // r01: immediate 5.85 ms; deferred (4
 constexpr int kStage = 32;
 
 // QCAP > 0: deferred leaf tests (traverseSpatialDeferred) with QCAP queue slots per thread
-template <int PRED, int MODE, int LEAF_F4, bool TRI, int BUCKET, int QCAP>
+// WIDE: nodes points at the tree's Wide64 records (experimental, ABX_WIDE=1; needs QCAP > 0)
+template <int PRED, int MODE, int LEAF_F4, bool TRI, int BUCKET, int QCAP, bool WIDE = false>
 __global__ void __launch_bounds__(kThreads, ABX_SPATIAL_MINB)
     spatialKernel(Node64 const *__restrict__ nodes, float4 const *__restrict__ leaf_box,
                   float4 const *__restrict__ leaf_tri, int n, float const *__restrict__ preds, int64_t q,
@@ -92,7 +93,10 @@ __global__ void __launch_bounds__(kThreads, ABX_SPATIAL_MINB)
     return limit > 0 && count >= limit;
   };
   bool const had_query = active;
-  if (QCAP > 0)
+  if (WIDE)
+    traverseWideDeferred<LEAF_F4, (QCAP >= 5 ? QCAP : 5)>(reinterpret_cast<Wide64 const *>(nodes), leaf_box, pred, active,
+                                                          squeue, emit);
+  else if (QCAP > 0)
     traverseSpatialDeferred<LEAF_F4, (BUCKET <= 4 ? BUCKET : 4), (QCAP > 0 ? QCAP : 3)>(nodes, leaf_box, pred, active,
                                                                                         squeue, emit);
   else
@@ -620,6 +624,22 @@ abx_status spatialLaunch(cudaStream_t s, abx_bvh *t, int pred_kind, void const *
     char const *e = getenv("ABX_SPATIAL_VARIANT");
     return e ? atoi(e) : kSpatialVariantDefault;
   }();
+  // experimental 4-wide nodes: ABX_WIDE=1 (built on the tree's first query; n < 2^29 for the run encoding)
+  static int const use_wide = [] {
+    char const *e = getenv("ABX_WIDE");
+    return e ? atoi(e) : 0;
+  }();
+  bool wide = use_wide && n > 64 && n < (1 << 29);
+  if (wide)
+  {
+    ABX_TRY(ensureWide(s, t));
+    wide = t->wide != nullptr;
+  }
+#define ABX_SPATIAL_W(LF4, TRIFLAG)                                                                                   \
+  ABX_DISPATCH_PRED(pred_kind,                                                                                         \
+                    ABX_LAUNCH_TAGGED(tag, (spatialKernel<P, MODE, LF4, TRIFLAG, 4, 16, true>), grid, kThreads, 0, s,  \
+                                      reinterpret_cast<Node64 const *>(t->wide), t->leaf_box, t->leaf_tri, n,          \
+                                      (float const *)preds, q, qperm, limit, counts, offsets, indices, staging))
 #define ABX_SPATIAL_B(LF4, TRIFLAG, B, QC)                                                                            \
   ABX_DISPATCH_PRED(pred_kind, ABX_LAUNCH_TAGGED(tag, (spatialKernel<P, MODE, LF4, TRIFLAG, B, QC>), grid, kThreads,  \
                                                  0, s, t->nodes, t->leaf_box, t->leaf_tri, n, (float const *)preds,   \
@@ -627,6 +647,11 @@ abx_status spatialLaunch(cudaStream_t s, abx_bvh *t, int pred_kind, void const *
 #define ABX_SPATIAL(LF4, TRIFLAG)                                                                                     \
   do                                                                                                                   \
   {                                                                                                                    \
+    if (wide)                                                                                                          \
+    {                                                                                                                  \
+      ABX_SPATIAL_W(LF4, TRIFLAG);                                                                                     \
+      break;                                                                                                           \
+    }                                                                                                                  \
     switch (variant)                                                                                                   \
     {                                                                                                                  \
     case 1: ABX_SPATIAL_B(LF4, TRIFLAG, 4, 12); break;                                                                 \
@@ -650,6 +675,7 @@ abx_status spatialLaunch(cudaStream_t s, abx_bvh *t, int pred_kind, void const *
   }
 #undef ABX_SPATIAL
 #undef ABX_SPATIAL_B
+#undef ABX_SPATIAL_W
   return ABX_OK;
 }
 

@@ -447,6 +447,117 @@ __device__ __forceinline__ void traverseSpatialDeferred(Node64 const *__restrict
   }
 }
 
+// ---- experimental: the same deferred traversal over 4-wide nodes (Wide64, abx_common.cuh) -----------------------
+// Half the dependent node loads of the Node64 walk (scripts/wide_node_study.py).  The quantised child boxes only
+// cull; every leaf of a reported run is tested exactly from leaf_box in the converged leaf phase, so the result
+// set is the one of traverseSpatialDeferred.
+template <int LEAF_F4, int QCAP, class P, class Emit>
+__device__ __forceinline__ void traverseWideDeferred(Wide64 const *__restrict__ wide, float4 const *__restrict__ leaf_box,
+                                                     P const &pred, bool active, unsigned *queue, Emit &&emit)
+{
+  static_assert(QCAP >= 5, "one node visit (four runs) must fit");
+  int const stride = blockDim.x;
+  unsigned *const myq = queue + threadIdx.x;
+  // up to three pushes per wide level, (63 code bits + 31 index bits) / 2 wide levels
+  int stack[3 * (kStackSize / 2) + 8];
+  int sp = 0;
+  int node = 0;
+  int cnt = 0; // queued runs
+  int tot = 0; // queued leaves
+  while (true)
+  {
+    while (active && cnt + 4 <= QCAP)
+    {
+      uint4 const *w = wide[node].w;
+      uint4 const w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3);
+      float const ox = __uint_as_float(w0.x), oy = __uint_as_float(w0.y), oz = __uint_as_float(w0.z);
+      float const sx = __uint_as_float(w0.w), sy = __uint_as_float(w1.x), sz = __uint_as_float(w1.y);
+      unsigned const q[6] = {w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
+      int const ref[4] = {(int)w3.x, (int)w3.y, (int)w3.z, (int)w3.w};
+      int next = -1;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+      {
+        if (ref[k] == kWideEmpty)
+          continue;
+        // bytes 6k .. 6k + 5 of q: min x y z, max x y z
+        constexpr int kB[4] = {0, 6, 12, 18};
+        int const b = kB[k];
+        float4 lo, hi;
+        lo.x = wideLo(wideByte(q[(b + 0) >> 2], (b + 0) & 3), sx, ox);
+        lo.y = wideLo(wideByte(q[(b + 1) >> 2], (b + 1) & 3), sy, oy);
+        lo.z = wideLo(wideByte(q[(b + 2) >> 2], (b + 2) & 3), sz, oz);
+        hi.x = wideHi(wideByte(q[(b + 3) >> 2], (b + 3) & 3), sx, ox);
+        hi.y = wideHi(wideByte(q[(b + 4) >> 2], (b + 4) & 3), sy, oy);
+        hi.z = wideHi(wideByte(q[(b + 5) >> 2], (b + 5) & 3), sz, oz);
+        lo.w = hi.w = 0.f;
+        if (!pred.box(lo, hi))
+          continue;
+        if (ref[k] < 0)
+        {
+          unsigned const run = (unsigned)~ref[k]; // (first << 2) | (leaves - 1)
+          myq[(cnt++) * stride] = run;
+          tot += (int)(run & 3u) + 1;
+        }
+        else
+        {
+          if (next >= 0)
+            stack[sp++] = next;
+          next = ref[k];
+        }
+      }
+      if (next >= 0)
+        node = next;
+      else if (sp == 0)
+        active = false;
+      else
+        node = stack[--sp];
+    }
+    // the warp is converged here: every lane tests its queued leaves, one per iteration
+    int const maxt = __reduce_max_sync(0xffffffffu, tot);
+    int e = 0, o = 0;
+    unsigned cur = myq[0];
+    for (int k = 0; k < maxt; ++k)
+    {
+      if (k < tot)
+      {
+        int const j = (int)(cur >> 2) + o;
+        if (o == (int)(cur & 3u))
+        {
+          ++e;
+          o = 0;
+          cur = myq[min(e, QCAP - 1) * stride];
+        }
+        else
+          ++o;
+        bool hit;
+        unsigned orig;
+        if (LEAF_F4 == 1)
+        {
+          float4 const p = __ldg(leaf_box + j);
+          hit = pred.point(p);
+          orig = __float_as_uint(p.w);
+        }
+        else
+        {
+          float4 const l = __ldg(leaf_box + 2 * (size_t)j), h = __ldg(leaf_box + 2 * (size_t)j + 1);
+          hit = pred.box(l, h);
+          orig = __float_as_uint(l.w);
+        }
+        if (hit && emit(orig, j))
+        {
+          active = false; // early exit (CountUpToN): drop the rest of the queue
+          tot = 0;
+        }
+      }
+    }
+    cnt = 0;
+    tot = 0;
+    if (!__any_sync(0xffffffffu, active))
+      return;
+  }
+}
+
 // exact leaf test for triangle leaves (only sphere predicates are defined in 3-D:
 // Intersects.hpp:118-126)
 template <int PRED>
