@@ -253,7 +253,10 @@ constexpr int kNearestBucket = 1; // 1 = leaves only
 // issue slots with 3 of 32 lanes active.  The row is sorted once, at the end, with all lanes
 // converged.  Which of several equal largest distances is replaced is arbitrary: like the
 // reference's heap this only permutes candidates of equal distance.
-template <int K, int LEAF_F4, bool TRI>
+// WIDE (experimental, ABX_WIDE=2, NOT yet validated on the GPU): nodes points at the tree's Wide64 records;
+// quantised child boxes give lower bounds of the child distances (enough for ordering and pruning), leaves of a
+// reported run are measured exactly from leaf_box.
+template <int K, int LEAF_F4, bool TRI, bool WIDE = false>
 __global__ void __launch_bounds__(kThreads, (K > 0 && K <= 16) ? ABX_NEAREST_MINB : 1)
     nearestKernel(Node64 const *__restrict__ nodes, float4 const *__restrict__ leaf_box,
                   float4 const *__restrict__ leaf_tri, int n, int prim_kind, float const *__restrict__ pts, int64_t q,
@@ -357,12 +360,115 @@ __global__ void __launch_bounds__(kThreads, (K > 0 && K <= 16) ? ABX_NEAREST_MIN
     }
   };
 
-  // stack of (squared box distance, node) for the farther child
-  unsigned long long stack[kStackSize];
+  // stack of (squared box distance, node) for the farther child (wide: up to three per wide level)
+  unsigned long long stack[WIDE ? 3 * (kStackSize / 2) + 8 : kStackSize];
   int sp = 0;
   int node = 0;
   while (true)
   {
+    if (WIDE)
+    {
+      uint4 const *w = (reinterpret_cast<Wide64 const *>(nodes) + node)->w;
+      uint4 const w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3);
+      float const ox = __uint_as_float(w0.x), oy = __uint_as_float(w0.y), oz = __uint_as_float(w0.z);
+      float const sx = __uint_as_float(w0.w), sy = __uint_as_float(w1.x), sz = __uint_as_float(w1.y);
+      unsigned const qb[6] = {w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
+      int ref[4] = {(int)w3.x, (int)w3.y, (int)w3.z, (int)w3.w};
+      float const inf = __int_as_float(0x7f800000);
+      float dk[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+      {
+        constexpr int kB[4] = {0, 6, 12, 18};
+        int const b = kB[c];
+        float const lx = wideLo(wideByte(qb[(b + 0) >> 2], (b + 0) & 3), sx, ox);
+        float const ly = wideLo(wideByte(qb[(b + 1) >> 2], (b + 1) & 3), sy, oy);
+        float const lz = wideLo(wideByte(qb[(b + 2) >> 2], (b + 2) & 3), sz, oz);
+        float const hx = wideHi(wideByte(qb[(b + 3) >> 2], (b + 3) & 3), sx, ox);
+        float const hy = wideHi(wideByte(qb[(b + 4) >> 2], (b + 4) & 3), sy, oy);
+        float const hz = wideHi(wideByte(qb[(b + 5) >> 2], (b + 5) & 3), sz, oz);
+        dk[c] = ref[c] == kWideEmpty ? inf : pointBoxDist2(px, py, pz, lx, ly, lz, hx, hy, hz);
+      }
+      // leaf runs first: exact distances, the radius may shrink before the internal children are ranked
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+      {
+        if (ref[c] >= 0 || ref[c] == kWideEmpty)
+          continue;
+        if (dk[c] < radius2)
+        {
+          unsigned const run = (unsigned)~ref[c];
+          int const first = (int)(run >> 2), last = first + (int)(run & 3u);
+          for (int j = first; j <= last; ++j)
+          {
+            float d2;
+            unsigned orig;
+            if (LEAF_F4 == 1)
+            {
+              float4 const p = __ldg(leaf_box + j);
+              float tx = __fsub_rn(p.x, px), ty = __fsub_rn(p.y, py), tz = __fsub_rn(p.z, pz);
+              d2 = __fmul_rn(tx, tx);
+              d2 = __fadd_rn(d2, __fmul_rn(ty, ty));
+              d2 = __fadd_rn(d2, __fmul_rn(tz, tz));
+              orig = __float_as_uint(p.w);
+            }
+            else
+            {
+              float4 const l = __ldg(leaf_box + 2 * (size_t)j), h = __ldg(leaf_box + 2 * (size_t)j + 1);
+              d2 = pointBoxDist2v(px, py, pz, l, h);
+              orig = __float_as_uint(l.w);
+            }
+            if (d2 < radius2)
+              offer(d2, orig, j);
+          }
+        }
+        dk[c] = inf; // not a descent candidate
+      }
+      // internal children that may still hold a closer leaf, nearest first (ties: lower slot first)
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (!(dk[c] < radius2))
+          dk[c] = inf;
+      auto cswap = [&](int a, int b) {
+        if (dk[b] < dk[a])
+        {
+          float const td = dk[a];
+          dk[a] = dk[b];
+          dk[b] = td;
+          int const tr = ref[a];
+          ref[a] = ref[b];
+          ref[b] = tr;
+        }
+      };
+      cswap(0, 1);
+      cswap(2, 3);
+      cswap(0, 2);
+      cswap(1, 3);
+      cswap(1, 2);
+      if (dk[0] < inf)
+      {
+#pragma unroll
+        for (int c = 3; c >= 1; --c)
+          if (dk[c] < inf)
+            stack[sp++] = ((unsigned long long)__float_as_uint(dk[c]) << 32) | (unsigned)ref[c];
+        node = ref[0];
+        continue;
+      }
+      bool popped_w = false;
+      while (sp > 0)
+      {
+        unsigned long long const e = stack[--sp];
+        if (__uint_as_float((unsigned)(e >> 32)) < radius2)
+        {
+          node = (int)(unsigned)e;
+          popped_w = true;
+          break;
+        }
+      }
+      if (!popped_w)
+        break;
+      continue;
+    }
     float4 const *f = reinterpret_cast<float4 const *>(nodes + node);
     float4 const a0 = __ldg(f), a1 = __ldg(f + 1), a2 = __ldg(f + 2), a3 = __ldg(f + 3);
     int const lref = __float_as_int(a0.w), rref = __float_as_int(a1.w);
@@ -753,9 +859,37 @@ abx_status nearestQuery(cudaStream_t s, abx_bvh *t, float const *pts, int64_t q,
   bool const tri = t->kind == ABX_PRIM_TRI3F;
   int const kmax = k_per_query ? INT_MAX : k; // per-query k: general path
   int const row_stride = std::max(0, std::min(k, n));
+  // experimental 4-wide nodes for the kNN walk: ABX_WIDE=2 (not validated on the GPU yet)
+  static int const use_wide = [] {
+    char const *e = getenv("ABX_WIDE");
+    return e ? atoi(e) : 0;
+  }();
+  bool wide = use_wide >= 2 && n > 64 && n < (1 << 29);
+  if (wide)
+  {
+    ABX_TRY(ensureWide(s, t));
+    wide = t->wide != nullptr;
+  }
 #define ABX_NEAREST(KCAP, SCRATCH)                                                                                    \
   do                                                                                                                   \
   {                                                                                                                    \
+    if (wide)                                                                                                          \
+    {                                                                                                                  \
+      Node64 const *wn = reinterpret_cast<Node64 const *>(t->wide);                                                    \
+      if (tri)                                                                                                         \
+        ABX_LAUNCH_TAGGED("nearestKernel<" #KCAP ",tri,wide>", (nearestKernel<KCAP, 2, true, true>), grid, kThreads,  \
+                          0, s, wn, t->leaf_box, t->leaf_tri, n, t->kind, pts, q, qperm, k, row_stride, k_per_query,   \
+                          offsets, counts, indices, distances, SCRATCH, missing, pair_rank);                           \
+      else if (t->kind == ABX_PRIM_BOX3F)                                                                              \
+        ABX_LAUNCH_TAGGED("nearestKernel<" #KCAP ",box,wide>", (nearestKernel<KCAP, 2, false, true>), grid, kThreads, \
+                          0, s, wn, t->leaf_box, t->leaf_tri, n, t->kind, pts, q, qperm, k, row_stride, k_per_query,   \
+                          offsets, counts, indices, distances, SCRATCH, missing, pair_rank);                           \
+      else                                                                                                             \
+        ABX_LAUNCH_TAGGED("nearestKernel<" #KCAP ",wide>", (nearestKernel<KCAP, 1, false, true>), grid, kThreads, 0,  \
+                          s, wn, t->leaf_box, t->leaf_tri, n, t->kind, pts, q, qperm, k, row_stride, k_per_query,      \
+                          offsets, counts, indices, distances, SCRATCH, missing, pair_rank);                           \
+      break;                                                                                                           \
+    }                                                                                                                  \
     if (tri)                                                                                                           \
       ABX_LAUNCH_TAGGED("nearestKernel<" #KCAP ",tri>", (nearestKernel<KCAP, 2, true>), grid, kThreads, 0, s,          \
                         t->nodes, t->leaf_box, t->leaf_tri, n, t->kind, pts, q, qperm, k, row_stride, k_per_query,     \
