@@ -253,7 +253,7 @@ constexpr int kNearestBucket = 1; // 1 = leaves only
 // issue slots with 3 of 32 lanes active.  The row is sorted once, at the end, with all lanes
 // converged.  Which of several equal largest distances is replaced is arbitrary: like the
 // reference's heap this only permutes candidates of equal distance.
-// WIDE (experimental, ABX_WIDE=2, NOT yet validated on the GPU): nodes points at the tree's Wide64 records;
+// WIDE (experimental, ABX_WIDE=2; kNN parity tests pass, not yet timed): nodes points at the tree's Wide64 records;
 // quantised child boxes give lower bounds of the child distances (enough for ordering and pruning), leaves of a
 // reported run are measured exactly from leaf_box.
 template <int K, int LEAF_F4, bool TRI, bool WIDE = false>
@@ -859,7 +859,7 @@ abx_status nearestQuery(cudaStream_t s, abx_bvh *t, float const *pts, int64_t q,
   bool const tri = t->kind == ABX_PRIM_TRI3F;
   int const kmax = k_per_query ? INT_MAX : k; // per-query k: general path
   int const row_stride = std::max(0, std::min(k, n));
-  // experimental 4-wide nodes for the kNN walk: ABX_WIDE=2 (not validated on the GPU yet)
+  // experimental 4-wide nodes for the kNN walk: ABX_WIDE=2 (parity tests pass, not yet timed)
   static int const use_wide = [] {
     char const *e = getenv("ABX_WIDE");
     return e ? atoi(e) : 0;
