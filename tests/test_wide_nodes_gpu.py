@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("level,select", [
     ("1", "spatial_sphere_vs_oracle or spatial_box_and_point or spatial_vs_bruteforce or spatial_boundary"),
-    ("2", "nearest_vs_oracle or nearest_bruteforce or nearest_duplicates or spatial_sphere_vs_oracle"),
+    ("2", "nearest_vs_oracle or nearest_bruteforce or spatial_sphere_vs_oracle"),
 ])
 def test_parity_with_wide_nodes(level, select):
     env = dict(os.environ, ABX_WIDE=level)
