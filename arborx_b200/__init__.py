@@ -20,7 +20,7 @@ SPHERE_PRED, BOX_PRED, POINT_PRED, RAY_PRED = 0, 1, 2, 3  # predicate geometries
 _PRIM_STRIDE = {POINT: 3, BOX: 6, TRIANGLE: 9}
 _PRED_STRIDE = {SPHERE_PRED: 4, BOX_PRED: 6, POINT_PRED: 3, RAY_PRED: 6}
 
-__all__ = ["ExecutionSpace", "BoundingVolumeHierarchy", "BVH", "TraversalPolicy", "intersects", "nearest",
+__all__ = ["ExecutionSpace", "BoundingVolumeHierarchy", "BVH", "TraversalPolicy", "HostBufferPool", "intersects", "nearest",
            "make_intersects", "make_nearest", "query", "dbscan", "DBSCANParameters", "SearchException",
            "POINT", "BOX", "TRIANGLE", "launch_count"]
 
@@ -108,29 +108,42 @@ def make_nearest(points, k):
     return nearest(points, k)
 
 
-class _Allocator:
-    """abx_alloc_fn backed by torch tensors (the library 'resizes the caller's views').  Host results
-    come from a small pool of pinned buffers that is reused across calls: cudaHostAlloc of a few hundred
-    MB per query would otherwise dominate the end-to-end time."""
-    _DT = {0: torch.int32, 1: torch.int32, 2: torch.float32}
-    _pinned_pool = {}
+class HostBufferPool:
+    """Caller-owned pool of pinned host buffers for the results of host-predicate queries
+    (`query(..., out=pool)`).  Results of a query ALIAS the pool's buffers and stay valid until the next
+    query that is given the same pool; without a pool every host query returns freshly allocated pinned
+    tensors that the caller owns.  (cudaHostAlloc of a few hundred MB per query dominates a short
+    end-to-end step, which is why bench.py passes one pool per host thread.)"""
 
-    def __init__(self, device, pinned_host=False, pool_key=None):
+    def __init__(self):
+        self._bufs = {}
+
+    def take(self, which, n, dtype):
+        buf = self._bufs.get(which)
+        if buf is None or buf.numel() < n or buf.dtype != dtype:
+            buf = torch.empty(max(int(n * 1.05) + 16, 1), dtype=dtype, pin_memory=True)
+            self._bufs[which] = buf
+        return buf[:n]
+
+
+class _Allocator:
+    """abx_alloc_fn backed by torch tensors (the library 'resizes the caller's views')."""
+    _DT = {0: torch.int32, 1: torch.int32, 2: torch.float32, 3: torch.int32, 4: torch.int32}
+
+    def __init__(self, device, pinned_host=False, pool=None):
         self.device = device
         self.pinned_host = pinned_host
-        self.pool_key = pool_key
+        self.pool = pool
         self.out = {}
         self.fn = _lib.ALLOC_FN(self._alloc)
 
     def _alloc(self, user, which, nbytes):
         n = nbytes // 4
         if self.pinned_host:
-            key = (self.pool_key, which)
-            buf = _Allocator._pinned_pool.get(key)
-            if buf is None or buf.numel() < n:
-                buf = torch.empty(max(n, 1), dtype=self._DT[which], pin_memory=True)
-                _Allocator._pinned_pool[key] = buf
-            t = buf[:n]
+            if self.pool is not None:
+                t = self.pool.take(which, n, self._DT[which])
+            else:
+                t = torch.empty(n, dtype=self._DT[which], pin_memory=n > 0)
         else:
             t = torch.empty(n, dtype=self._DT[which], device=self.device)
         self.out[which] = t
@@ -197,17 +210,17 @@ class BoundingVolumeHierarchy:
     def memory_bytes(self):
         return lib().abx_bvh_memory_bytes(self._h)
 
-    def query(self, space, predicates, policy=None, return_distances=False):
+    def query(self, space, predicates, policy=None, return_distances=False, out=None):
         """query(space, predicates, indices, offsets[, policy]) -> (indices, offsets[, distances]).
         Device predicates give device results; host (CPU tensor) predicates run the host-buffer
-        entry points and give pinned host results (the end-to-end path)."""
+        entry points and give pinned host results (the end-to-end path).  The returned tensors are owned
+        by the caller; `out` (a HostBufferPool, host predicates only) makes them views of the pool's
+        reusable pinned buffers instead, valid until the next query given the same pool."""
         pol = (policy or TraversalPolicy())._c()
         d = predicates.data
         q = d.shape[0]
         host = not d.is_cuda
-        # host results alias a pinned pool per (predicate tag, execution space): valid until the next host
-        # query of that kind on that space (concurrent host queries on different spaces do not share buffers)
-        alloc = _Allocator(space.device, pinned_host=host, pool_key=(predicates.tag, space.stream.cuda_stream))
+        alloc = _Allocator(space.device, pinned_host=host, pool=out if host else None)
         off, idx, dist = C.c_void_p(), C.c_void_p(), C.c_void_p()
         nnz = C.c_int64()
         L = lib()

@@ -59,6 +59,25 @@ SIGNATURES = {
     "abx_dist_pair_with_rank": (C.c_int, [_vp, _vp, _i64, _i32, _vp]),
     "abx_dist_nearest_pairs": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, C.POINTER(_i64)]),
     "abx_dist_knn_merge": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "abx_comm_from_nccl": (C.c_int, [_vp, _pp]),
+    "abx_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "abx_comm_init_rank": (C.c_int, [C.c_char_p, _i32, _i32, _pp]),
+    "abx_comm_create_local": (C.c_int, [_i32, _pp]),
+    "abx_comm_destroy": (C.c_int, [_vp]),
+    "abx_comm_rank": (_i32, [_vp]),
+    "abx_comm_size": (_i32, [_vp]),
+    "abx_dist_create": (C.c_int, [_vp, _vp, C.c_int, _vp, _i64, _pp]),
+    "abx_dist_create_host": (C.c_int, [_vp, _vp, C.c_int, _vp, _i64, _pp]),
+    "abx_dist_destroy": (C.c_int, [_vp]),
+    "abx_dist_size": (_i64, [_vp]),
+    "abx_dist_empty": (C.c_int, [_vp]),
+    "abx_dist_bounds": (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    "abx_dist_query_spatial_crs": (C.c_int, [_vp, _vp, C.c_int, _vp, _i64, ALLOC_FN, _vp, _pp, _pp, _pi64]),
+    "abx_dist_query_nearest_crs": (C.c_int, [_vp, _vp, _vp, _i64, _i32, ALLOC_FN, _vp, _pp, _pp, _pp, _pi64]),
+    "abx_dist_query_spatial_crs_host": (C.c_int, [_vp, _vp, C.c_int, _vp, _i64, ALLOC_FN, _vp, _pp, _pp, _pi64, _pp,
+                                                  _pp, _pi64]),
+    "abx_dist_query_nearest_crs_host": (C.c_int, [_vp, _vp, _vp, _i64, _i32, ALLOC_FN, _vp, _pp, _pp, _pp, _pi64, _pp,
+                                                  _pp, _pi64]),
     "abx_scene_bounds": (C.c_int, [_vp, C.c_int, _vp, _i64, _vp]),
     "abx_morton64": (C.c_int, [_vp, C.c_int, _vp, _i64, _vp, _vp]),
     "abx_morton32": (C.c_int, [_vp, C.c_int, _vp, _i64, _vp, _vp]),

@@ -650,9 +650,21 @@ __global__ void __launch_bounds__(W * 32, ABX_HIER_MINB)
   }
 }
 
-// finishes the nodes that straddle chunk boundaries: global CAS flags in `ranges`,
-// records published with __threadfence before the flag, read with __ldcg after it
-// (the reference's CAS + load_fence, TreeConstruction.hpp:241-270)
+// finishes the nodes that straddle chunk boundaries: global acquire-release CAS flags in `ranges`,
+// sibling records read with __ldcg after it (the reference's CAS + load_fence,
+// TreeConstruction.hpp:241-270)
+// acquire-release CAS at device scope: the first child to arrive releases its finished record with
+// it, the second acquires the sibling's record with it (TreeConstruction.hpp:241-270: CAS + load_fence)
+__device__ __forceinline__ int casAcqRel(int *addr, int compare, int value)
+{
+  int old;
+  asm volatile("atom.acq_rel.gpu.global.cas.b32 %0, [%1], %2, %3;"
+               : "=r"(old)
+               : "l"(addr), "r"(compare), "r"(value)
+               : "memory");
+  return old;
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(256)
     hierarchyGlobalKernel(int n, unsigned long long const *__restrict__ codes, Node64 *nodes,
@@ -684,16 +696,15 @@ __global__ void __launch_bounds__(256)
       if (is_left_child)
       {
         int const apetrei_parent = range_right;
-        int const old = atomicCAS(&ranges[apetrei_parent], -1, range_left);
+        int const old = casAcqRel(&ranges[apetrei_parent], -1, range_left);
         if (old == -1)
           break; // first to arrive: the sibling's thread finishes this node
         range_right = old;
         int const right_child = apetrei_parent + 1;
         bool const right_is_leaf = (right_child == range_right);
         delta_right = deltaOf(codes, range_right, n_int);
-        // no reader-side fence: the loads below are issued after the CAS result is known (the
-        // `old == -1` branch above is resolved first; no speculation) and go to L2 (ld.cg), where
-        // the sibling's record was made visible by its __threadfence() before its own CAS
+        // the acquire half of the CAS orders the loads below after it; they go to L2 (ld.cg), where
+        // the sibling's record was released by its own CAS
         if (right_is_leaf)
           loadLeafBox<KIND>(leaf_box, right_child, sib, sib_ref);
         else
@@ -705,7 +716,7 @@ __global__ void __launch_bounds__(256)
       else
       {
         int const apetrei_parent = range_left - 1;
-        int const old = atomicCAS(&ranges[apetrei_parent], -1, range_right);
+        int const old = casAcqRel(&ranges[apetrei_parent], -1, range_right);
         if (old == -1)
           break;
         range_left = old;
@@ -737,7 +748,7 @@ __global__ void __launch_bounds__(256)
         }
         break;
       }
-      __threadfence(); // release the finished node before signalling its parent
+      // the node written above is released by the next iteration's CAS (acq_rel)
     }
   }
 }
@@ -930,12 +941,12 @@ template <int K, int W>
 abx_status launchHierarchyLocalW(cudaStream_t s, abx_bvh *t, void const *prims, PendingNode *pending,
                                  unsigned *pending_count)
 {
-  static bool attr_set = false;
-  if (!attr_set)
+  static PerDeviceOnce attr; // function attributes are per device
+  if (attr.needed())
   {
     ABX_CUDA_TRY(cudaFuncSetAttribute(hierarchyLocalKernel<K, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)sizeof(HierSmem<K, W>)));
-    attr_set = true;
+    attr.done();
   }
   int const n = (int)t->n;
   ABX_LAUNCH_TAGGED("hierarchyLocalKernel", (hierarchyLocalKernel<K, W>), divUp(n, W * kHierWarpLeaves), W * 32,
@@ -948,17 +959,17 @@ template <int K>
 abx_status launchHierarchyLocal(cudaStream_t s, abx_bvh *t, void const *prims, PendingNode *pending,
                                 unsigned *pending_count)
 {
-  static int const warps = [] {
-    char const *e = getenv("ABX_HIER_WARPS");
-    return e ? atoi(e) : kHierWarpsDefault;
-  }();
-  switch (warps)
+#ifdef ABX_TUNING
+  switch (ABX_TUNE_INT("ABX_HIER_WARPS", kHierWarpsDefault))
   {
   case 2: return launchHierarchyLocalW<K, 2>(s, t, prims, pending, pending_count);
   case 4: return launchHierarchyLocalW<K, 4>(s, t, prims, pending, pending_count);
   case 16: return launchHierarchyLocalW<K, 16>(s, t, prims, pending, pending_count);
   default: return launchHierarchyLocalW<K, 8>(s, t, prims, pending, pending_count);
   }
+#else
+  return launchHierarchyLocalW<K, kHierWarpsDefault>(s, t, prims, pending, pending_count);
+#endif
 }
 
 // codes (sorted) and perm must already be in bvh; fills nodes / leaf arrays / bounds
@@ -1215,6 +1226,70 @@ abx_status ensureWide(cudaStream_t s, abx_bvh *t)
   return ABX_OK;
 }
 
+// fills a freshly allocated tree; on failure the caller destroys it (every early return below is safe)
+static abx_status buildTreeInto(cudaStream_t s, abx_bvh *t, void const *prims, uint64_t const *sorted_codes)
+{
+  int const kind = t->kind;
+  int64_t const n = t->n;
+  ABX_TRY(deviceAlloc((void **)&t->bounds_dev, 6 * sizeof(float), s));
+  t->bytes += 6 * sizeof(float);
+  if (n == 0)
+  {
+    // LinearBVH.hpp:203-206: bounds() stays the default (empty) box
+    ABX_LAUNCH(emptyBoundsKernel, 1, 32, 0, s, t->bounds_dev);
+    return ABX_OK;
+  }
+  size_t const leaf_f4 = (kind == ABX_PRIM_POINT3F) ? 1 : 2;
+  ABX_TRY(deviceAlloc((void **)&t->leaf_box, sizeof(float4) * leaf_f4 * n, s));
+  t->bytes += sizeof(float4) * leaf_f4 * n;
+  if (kind == ABX_PRIM_TRI3F)
+  {
+    ABX_TRY(deviceAlloc((void **)&t->leaf_tri, sizeof(float4) * 3 * n, s));
+    t->bytes += sizeof(float4) * 3 * n;
+  }
+  ABX_TRY(deviceAlloc((void **)&t->perm, sizeof(uint32_t) * n, s));
+  ABX_TRY(deviceAlloc((void **)&t->codes, sizeof(uint64_t) * n, s));
+  t->bytes += 12 * n;
+  if (n == 1)
+  {
+    ABX_DISPATCH_PRIM(kind, ABX_LAUNCH((singleLeafKernel<K>), 1, 1, 0, s, (float const *)prims, t->leaf_box,
+                                       t->leaf_tri, t->perm, (unsigned long long *)t->codes, t->bounds_dev));
+    return ABX_OK;
+  }
+  ABX_TRY(deviceAlloc((void **)&t->nodes, sizeof(Node64) * (n - 1), s));
+  t->bytes += sizeof(Node64) * (n - 1);
+
+  if (sorted_codes)
+  {
+    ABX_CUDA_TRY(cudaMemcpyAsync(t->codes, sorted_codes, sizeof(uint64_t) * n, cudaMemcpyDeviceToDevice, s));
+    ABX_LAUNCH(iotaKernel, divUp(n, kThreads), kThreads, 0, s, t->perm, n);
+  }
+  else
+  {
+    TempBuffer<unsigned> enc;
+    ABX_TRY(enc.alloc(6, s));
+    ABX_TRY(sceneBounds(s, kind, prims, n, enc.ptr));
+    ABX_TRY(decodeBounds(s, enc.ptr, t->bounds_dev));
+    ABX_TRY(morton64(s, kind, prims, n, t->bounds_dev, t->codes));
+    // Morton64 codes use 63 bits (3 x 21).  Double-buffered: the tree keeps whichever pair of
+    // buffers the sort finished in
+    TempBuffer<uint64_t> codes_alt;
+    TempBuffer<uint32_t> perm_alt;
+    ABX_TRY(codes_alt.alloc(n, s));
+    ABX_TRY(perm_alt.alloc(n, s));
+    uint64_t *kb[2] = {t->codes, codes_alt.ptr};
+    uint32_t *vb[2] = {t->perm, perm_alt.ptr};
+    int cur = 0;
+    ABX_TRY(sortPairsU64DB(s, kb, vb, &cur, n, /*iota_vals=*/true, 63));
+    if (cur != 0)
+    {
+      std::swap(t->codes, codes_alt.ptr);
+      std::swap(t->perm, perm_alt.ptr);
+    }
+  }
+  return buildHierarchy(s, t, prims);
+}
+
 abx_status buildTree(cudaStream_t s, int kind, void const *prims, int64_t n, uint64_t const *sorted_codes,
                      abx_bvh **out)
 {
@@ -1238,80 +1313,14 @@ abx_status buildTree(cudaStream_t s, int kind, void const *prims, int64_t n, uin
   t->n = n;
   t->stream = s;
   cudaGetDevice(&t->device);
-  auto fail = [&](abx_status st) {
+  abx_status const st = buildTreeInto(s, t, prims, sorted_codes);
+  if (st != ABX_OK)
+  {
     destroyTree(t);
     return st;
-  };
-#define ABX_TRY_T(expr)                                                                                               \
-  do                                                                                                                   \
-  {                                                                                                                    \
-    abx_status _s = (expr);                                                                                            \
-    if (_s != ABX_OK)                                                                                                  \
-      return fail(_s);                                                                                                 \
-  } while (0)
-
-  ABX_TRY_T(deviceAlloc((void **)&t->bounds_dev, 6 * sizeof(float), s));
-  t->bytes += 6 * sizeof(float);
-  if (n == 0)
-  {
-    // LinearBVH.hpp:203-206: bounds() stays the default (empty) box
-    ABX_LAUNCH(emptyBoundsKernel, 1, 32, 0, s, t->bounds_dev);
-    *out = t;
-    return ABX_OK;
   }
-  size_t const leaf_f4 = (kind == ABX_PRIM_POINT3F) ? 1 : 2;
-  ABX_TRY_T(deviceAlloc((void **)&t->leaf_box, sizeof(float4) * leaf_f4 * n, s));
-  t->bytes += sizeof(float4) * leaf_f4 * n;
-  if (kind == ABX_PRIM_TRI3F)
-  {
-    ABX_TRY_T(deviceAlloc((void **)&t->leaf_tri, sizeof(float4) * 3 * n, s));
-    t->bytes += sizeof(float4) * 3 * n;
-  }
-  ABX_TRY_T(deviceAlloc((void **)&t->perm, sizeof(uint32_t) * n, s));
-  ABX_TRY_T(deviceAlloc((void **)&t->codes, sizeof(uint64_t) * n, s));
-  t->bytes += 12 * n;
-  if (n == 1)
-  {
-    ABX_DISPATCH_PRIM(kind, ABX_LAUNCH((singleLeafKernel<K>), 1, 1, 0, s, (float const *)prims, t->leaf_box,
-                                       t->leaf_tri, t->perm, (unsigned long long *)t->codes, t->bounds_dev));
-    *out = t;
-    return ABX_OK;
-  }
-  ABX_TRY_T(deviceAlloc((void **)&t->nodes, sizeof(Node64) * (n - 1), s));
-  t->bytes += sizeof(Node64) * (n - 1);
-
-  if (sorted_codes)
-  {
-    ABX_CUDA_TRY(cudaMemcpyAsync(t->codes, sorted_codes, sizeof(uint64_t) * n, cudaMemcpyDeviceToDevice, s));
-    ABX_LAUNCH(iotaKernel, divUp(n, kThreads), kThreads, 0, s, t->perm, n);
-  }
-  else
-  {
-    TempBuffer<unsigned> enc;
-    ABX_TRY_T(enc.alloc(6, s));
-    ABX_TRY_T(sceneBounds(s, kind, prims, n, enc.ptr));
-    ABX_TRY_T(decodeBounds(s, enc.ptr, t->bounds_dev));
-    ABX_TRY_T(morton64(s, kind, prims, n, t->bounds_dev, t->codes));
-    // Morton64 codes use 63 bits (3 x 21).  Double-buffered: the tree keeps whichever pair of
-    // buffers the sort finished in
-    TempBuffer<uint64_t> codes_alt;
-    TempBuffer<uint32_t> perm_alt;
-    ABX_TRY_T(codes_alt.alloc(n, s));
-    ABX_TRY_T(perm_alt.alloc(n, s));
-    uint64_t *kb[2] = {t->codes, codes_alt.ptr};
-    uint32_t *vb[2] = {t->perm, perm_alt.ptr};
-    int cur = 0;
-    ABX_TRY_T(sortPairsU64DB(s, kb, vb, &cur, n, /*iota_vals=*/true, 63));
-    if (cur != 0)
-    {
-      std::swap(t->codes, codes_alt.ptr);
-      std::swap(t->perm, perm_alt.ptr);
-    }
-  }
-  ABX_TRY_T(buildHierarchy(s, t, prims));
   *out = t;
   return ABX_OK;
-#undef ABX_TRY_T
 }
 
 abx_status exportReference(cudaStream_t s, abx_bvh *t, int32_t *leaf_rope, uint32_t *leaf_index, int32_t *left_child,

@@ -3,7 +3,9 @@
 #include "abx_common.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <unordered_map>
@@ -16,6 +18,14 @@ static thread_local std::string t_last_error;
 std::atomic<int64_t> g_launch_count{0};
 
 void setError(std::string const &msg) { t_last_error = msg; }
+
+#ifdef ABX_TUNING
+int tuneIntEnv(char const *name, int dflt)
+{
+  char const *e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+#endif
 
 // ---- per-kernel timing -------------------------------------------------------------
 bool g_profile = false;
@@ -57,7 +67,7 @@ void profileEnd(int handle, cudaStream_t s)
     cudaEventRecord(g_records[handle].stop, s);
 }
 
-static abx_status ensureDevice()
+abx_status ensureDevice()
 {
   static std::once_flag once;
   static cudaError_t init_err = cudaSuccess;
@@ -102,7 +112,13 @@ struct AllocKey
 };
 std::mutex g_alloc_mutex;
 std::map<AllocKey, std::vector<void *>> g_free_blocks;
-std::unordered_map<void *, std::pair<int, size_t>> g_block_info; // ptr -> (device, class)
+struct BlockInfo
+{
+  int device;
+  size_t cls;
+  cudaStream_t owner; // stream of the request that handed the block out (its users are ordered there)
+};
+std::unordered_map<void *, BlockInfo> g_block_info;
 int64_t g_cached_bytes = 0;
 
 size_t sizeClass(size_t bytes)
@@ -130,6 +146,7 @@ abx_status deviceAlloc(void **p, size_t bytes, cudaStream_t s)
       *p = it->second.back();
       it->second.pop_back();
       g_cached_bytes -= (int64_t)cls;
+      g_block_info[*p].owner = s;
       return ABX_OK;
     }
   }
@@ -146,7 +163,7 @@ abx_status deviceAlloc(void **p, size_t bytes, cudaStream_t s)
     return ABX_ERR_CUDA;
   }
   std::lock_guard<std::mutex> lock(g_alloc_mutex);
-  g_block_info[*p] = {dev, cls};
+  g_block_info[*p] = BlockInfo{dev, cls, s};
   return ABX_OK;
 }
 
@@ -154,12 +171,35 @@ void deviceFree(void *p, cudaStream_t s)
 {
   if (!p)
     return;
+  BlockInfo info;
+  {
+    std::lock_guard<std::mutex> lock(g_alloc_mutex);
+    auto it = g_block_info.find(p);
+    if (it == g_block_info.end())
+      return; // not ours
+    info = it->second;
+  }
+  if (info.owner != s)
+  {
+    // Released under another stream than the one its users were enqueued on (abx_free of a result
+    // from a different execution space): the block is filed under `s`, so `s` must first wait for
+    // everything the owner stream has been given so far.
+    cudaEvent_t ev = nullptr;
+    bool ordered = false;
+    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess)
+    {
+      ordered = cudaEventRecord(ev, info.owner) == cudaSuccess && cudaStreamWaitEvent(s, ev, 0) == cudaSuccess;
+      cudaEventDestroy(ev); // released once the wait has been satisfied
+    }
+    if (!ordered)
+    {
+      cudaGetLastError();      // e.g. the owner stream no longer exists
+      cudaDeviceSynchronize(); // nothing can still be using the block after this
+    }
+  }
   std::lock_guard<std::mutex> lock(g_alloc_mutex);
-  auto it = g_block_info.find(p);
-  if (it == g_block_info.end())
-    return; // not ours
-  g_free_blocks[AllocKey{it->second.first, s, it->second.second}].push_back(p);
-  g_cached_bytes += (int64_t)it->second.second;
+  g_free_blocks[AllocKey{info.device, s, info.cls}].push_back(p);
+  g_cached_bytes += (int64_t)info.cls;
 }
 
 static abx_policy defaultPolicy()
@@ -229,9 +269,11 @@ static abx_status checkPredPointer(int pred_kind, void const *preds, int64_t q)
 // writes the CRS rows and re-traverses only queries with more than kStage results.
 // buffer_size never changes the result, so the policy is honoured for its error
 // contract only (hard preallocation overflow throws, :263-268).
-static abx_status spatialCrs(abx_bvh *bvh, cudaStream_t s, int pred_kind, void const *preds, int64_t q,
-                             abx_policy const &policy, abx_alloc_fn alloc, void *user, int32_t **offsets_out,
-                             uint32_t **indices_out, int64_t *nnz_out)
+// before_sync (optional): enqueues more work / read-backs on `s` that the call's one blocking point
+// should cover as well (the DistributedTree exchange piggy-backs its count matrix on it).
+abx_status spatialCrs(abx_bvh *bvh, cudaStream_t s, int pred_kind, void const *preds, int64_t q,
+                      abx_policy const &policy, abx_alloc_fn alloc, void *user, int32_t **offsets_out,
+                      uint32_t **indices_out, int64_t *nnz_out, std::function<abx_status()> const &before_sync)
 {
   ABX_TRY(checkPredPointer(pred_kind, preds, q));
   if (q < 0 || q >= (int64_t)1 << 30)
@@ -251,6 +293,12 @@ static abx_status spatialCrs(abx_bvh *bvh, cudaStream_t s, int pred_kind, void c
     void *idx = nullptr;
     ABX_TRY(allocOut(alloc, user, 1, 0, s, &idx));
     *indices_out = (uint32_t *)idx;
+    if (before_sync)
+    {
+      // the caller counts on this call's blocking point
+      ABX_TRY(before_sync());
+      ABX_CUDA_TRY(cudaStreamSynchronize(s));
+    }
     return ABX_OK;
   }
   TempBuffer<uint32_t> qperm;
@@ -275,10 +323,21 @@ static abx_status spatialCrs(abx_bvh *bvh, cudaStream_t s, int pred_kind, void c
     ABX_LAUNCH(overflowKernel, divUp(q, 256), 256, 0, s, offsets, q, -policy.buffer_size, overflow.ptr);
     ABX_CUDA_TRY(cudaMemcpyAsync(&h_overflow, overflow.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
   }
-  ABX_TRY(exclusiveScanI32(s, offsets, offsets, q + 1));
-  int32_t total = 0;
-  ABX_CUDA_TRY(cudaMemcpyAsync(&total, offsets + q, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  // the int32 scan wraps silently past 2^31 results: the total is accumulated in 64 bits next to it
+  TempBuffer<unsigned long long> total64;
+  ABX_TRY(total64.alloc(1, s));
+  ABX_TRY(exclusiveScanI32(s, offsets, offsets, q + 1, total64.ptr));
+  unsigned long long total_ull = 0;
+  ABX_CUDA_TRY(cudaMemcpyAsync(&total_ull, total64.ptr, sizeof(total_ull), cudaMemcpyDeviceToHost, s));
+  if (before_sync)
+    ABX_TRY(before_sync());
   ABX_CUDA_TRY(cudaStreamSynchronize(s)); // the reference blocks here too (lastElement, :248)
+  if (total_ull >= (1ull << 31))
+  {
+    setError("spatial query: more than 2^31 results (CRS offsets are 32-bit like the reference's)");
+    return ABX_ERR_ARG;
+  }
+  int64_t const total = (int64_t)total_ull;
   *nnz_out = total;
   void *idx = nullptr;
   if (total == 0)
@@ -302,7 +361,7 @@ static abx_status spatialCrs(abx_bvh *bvh, cudaStream_t s, int pred_kind, void c
   return ABX_OK;
 }
 
-static abx_status nearestCrs(abx_bvh *bvh, cudaStream_t s, void const *pts, int64_t q, int32_t k,
+abx_status nearestCrs(abx_bvh *bvh, cudaStream_t s, void const *pts, int64_t q, int32_t k,
                              int32_t const *k_per_query, abx_policy const &policy, abx_alloc_fn alloc, void *user,
                              int32_t **offsets_out, uint32_t **indices_out, float **distances_out, int64_t *nnz_out)
 {
@@ -343,11 +402,18 @@ static abx_status nearestCrs(abx_bvh *bvh, cudaStream_t s, void const *pts, int6
   else
   {
     ABX_TRY(clipK(s, k_per_query, k, n, q, offsets));
-    ABX_TRY(exclusiveScanI32(s, offsets, offsets, q + 1));
-    int32_t t32 = 0;
-    ABX_CUDA_TRY(cudaMemcpyAsync(&t32, offsets + q, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    TempBuffer<unsigned long long> total64;
+    ABX_TRY(total64.alloc(1, s));
+    ABX_TRY(exclusiveScanI32(s, offsets, offsets, q + 1, total64.ptr));
+    unsigned long long t64 = 0;
+    ABX_CUDA_TRY(cudaMemcpyAsync(&t64, total64.ptr, sizeof(t64), cudaMemcpyDeviceToHost, s));
     ABX_CUDA_TRY(cudaStreamSynchronize(s));
-    total = t32;
+    if (t64 >= (1ull << 31))
+    {
+      setError("nearest query: more than 2^31 results");
+      return ABX_ERR_ARG;
+    }
+    total = (int64_t)t64;
   }
   *nnz_out = total;
   void *idx = nullptr, *dist = nullptr;
@@ -823,7 +889,7 @@ abx_status abx_bvh_device_view(const abx_bvh *bvh, abx_device_view *view)
 
 abx_status abx_dist_merge_sorted(void *stream, int64_t q, const int32_t *local_offsets_dev,
                                  const int32_t *local_indices_dev, int32_t rank, int64_t n_remote,
-                                 const int64_t *remote_query_ids_dev, const int32_t *remote_values2_dev,
+                                 const int32_t *remote_query_ids_dev, const int32_t *remote_values2_dev,
                                  int32_t *out_offsets_dev, int32_t *out_values2_dev)
 {
   ABX_TRY(ensureDevice());
@@ -860,42 +926,7 @@ abx_status abx_dist_pair_with_rank(void *stream, const int32_t *indices_dev, int
   return pairWithRank((cudaStream_t)stream, indices_dev, n, rank, values2_dev);
 }
 
-abx_status abx_dist_nearest_pairs(abx_bvh *bvh, void *stream, const void *points_dev, int64_t q, int32_t k,
-                                  int32_t rank, int32_t *values2_dev, float *distances_dev, int64_t *missing_out)
-{
-  ABX_TRY(ensureDevice());
-  if (!bvh || !missing_out || q < 0 || rank < 0)
-  {
-    setError("null argument");
-    return ABX_ERR_ARG;
-  }
-  *missing_out = 0;
-  cudaStream_t s = (cudaStream_t)stream;
-  int const n = (int)bvh->n;
-  int64_t const row = std::max(0, std::min(k, n));
-  if (q == 0 || row == 0)
-    return ABX_OK;
-  if (!points_dev || !values2_dev)
-  {
-    setError("null argument");
-    return ABX_ERR_ARG;
-  }
-  TempBuffer<uint32_t> qperm;
-  if (n > 1)
-    ABX_TRY(predicatePermutation(s, bvh, ABX_PRED_POINT3F, points_dev, q, qperm));
-  TempBuffer<unsigned long long> missing;
-  ABX_TRY(missing.alloc(1, s));
-  ABX_CUDA_TRY(cudaMemsetAsync(missing.ptr, 0, sizeof(unsigned long long), s));
-  ABX_TRY(nearestQuery(s, bvh, (float const *)points_dev, q, k, nullptr, qperm.ptr, nullptr, row * q, nullptr,
-                       (uint32_t *)values2_dev, distances_dev, missing.ptr, rank));
-  unsigned long long h_missing = 0;
-  ABX_CUDA_TRY(cudaMemcpyAsync(&h_missing, missing.ptr, sizeof(h_missing), cudaMemcpyDeviceToHost, s));
-  ABX_CUDA_TRY(cudaStreamSynchronize(s));
-  *missing_out = (int64_t)h_missing;
-  return ABX_OK;
-}
-
-abx_status abx_dist_knn_merge(void *stream, int64_t n_candidates, const int64_t *query_ids_dev,
+abx_status abx_dist_knn_merge(void *stream, int64_t n_candidates, const int32_t *query_ids_dev,
                               const int32_t *cand_values2_dev, const float *cand_distances_dev, int32_t k,
                               int32_t *values2_dev, float *distances_dev)
 {

@@ -11,6 +11,7 @@
 #include <climits>
 #include <cstdint>
 #include <cstdio>
+#include <functional>
 #include <string>
 
 #include <cuda_runtime.h>
@@ -65,6 +66,34 @@ void profileEnd(int handle, cudaStream_t s);
   ABX_LAUNCH_TAGGED(#kernel, kernel, grid, block, smem, stream, __VA_ARGS__)
 
 constexpr int kNumSMs = 148; // B200
+
+// Tuning switches: the release library has none.  Built with -DABX_TUNING (make TUNING=1, a separate
+// libabx_tuning.so for scripts/), tuneInt reads the named environment variable once per call site;
+// otherwise it is the compile-time default and the alternative kernel instantiations are not compiled.
+#ifdef ABX_TUNING
+int tuneIntEnv(char const *name, int dflt);
+#define ABX_TUNE_INT(name, dflt) ([] { static int const v = ::abx::tuneIntEnv(name, dflt); return v; }())
+#else
+#define ABX_TUNE_INT(name, dflt) (dflt)
+#endif
+
+// "has this (kernel attribute) set-up been done on the current device": one bit per device ordinal
+struct PerDeviceOnce
+{
+  std::atomic<unsigned long long> mask{0};
+  bool needed() const
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return !(mask.load(std::memory_order_acquire) & (1ull << (dev & 63)));
+  }
+  void done()
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    mask.fetch_or(1ull << (dev & 63), std::memory_order_release);
+  }
+};
 
 static inline int divUp(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
@@ -304,14 +333,16 @@ namespace abx
 // fixup = false forces plain LSD over all key_bits (keys with long runs of equal top bits, e.g. grid cells)
 abx_status sortPairsU64(cudaStream_t s, uint64_t *keys, uint32_t *vals, int64_t n, bool iota_vals, int key_bits = 64,
                         bool fixup = true);
-abx_status sortPairsU32(cudaStream_t s, uint32_t *keys, uint32_t *vals, int64_t n, bool iota_vals, int key_bits = 32);
+abx_status sortPairsU32(cudaStream_t s, uint32_t *keys, uint32_t *vals, int64_t n, bool iota_vals, int key_bits = 32,
+                        bool fixup = true);
 // double-buffer forms: input in keys[0]/vals[0], output in keys[*cur]/vals[*cur].  approx_top_bits > 0
 // orders by the top approx_top_bits of the key_bits only (an ordering hint, e.g. predicate sorting).
 abx_status sortPairsU64DB(cudaStream_t s, uint64_t *const keys[2], uint32_t *const vals[2], int *cur, int64_t n,
                           bool iota_vals, int key_bits);
 abx_status sortPairsU32DB(cudaStream_t s, uint32_t *const keys[2], uint32_t *const vals[2], int *cur, int64_t n,
                           bool iota_vals, int key_bits, int approx_top_bits);
-abx_status exclusiveScanI32(cudaStream_t s, int32_t const *in, int32_t *out, int64_t n_plus_1);
+abx_status exclusiveScanI32(cudaStream_t s, int32_t const *in, int32_t *out, int64_t n_plus_1,
+                            unsigned long long *total64 = nullptr);
 // build.cu
 abx_status sceneBounds(cudaStream_t s, int kind, void const *prims, int64_t n, unsigned *bounds_enc6);
 abx_status decodeBounds(cudaStream_t s, unsigned const *bounds_enc6, float *bounds6);
@@ -345,9 +376,11 @@ abx_status routeLaunch(cudaStream_t s, bool fill, int pred_kind, void const *pre
                        unsigned const *base, unsigned *cursors, int32_t *out_qid);
 abx_status ensureWide(cudaStream_t s, abx_bvh *t);
 abx_status mergeSorted(cudaStream_t s, int64_t q, int32_t const *local_off, int32_t const *local_idx, int rank,
-                       int64_t m, int64_t const *remote_ids, int32_t const *remote_vals2, int32_t *out_off,
+                       int64_t m, int32_t const *remote_ids, int32_t const *remote_vals2, int32_t *out_off,
                        int32_t *out_vals2);
-abx_status knnMerge(cudaStream_t s, int64_t m, int64_t const *ids, int32_t const *cand2, float const *cand_d, int k,
+abx_status mergeCounts(cudaStream_t s, int64_t q, int32_t const *local_off, int64_t m, int32_t const *remote_ids,
+                       int32_t *out_off);
+abx_status knnMerge(cudaStream_t s, int64_t m, int32_t const *ids, int32_t const *cand2, float const *cand_d, int k,
                     int32_t *vals2, float *dists);
 abx_status pairWithRank(cudaStream_t s, int32_t const *indices, int64_t n, int rank, int32_t *out2);
 abx_status mergeCrs(cudaStream_t s, int64_t q, int32_t const *local_off, int32_t const *local_idx, int rank,
@@ -355,6 +388,15 @@ abx_status mergeCrs(cudaStream_t s, int64_t q, int32_t const *local_off, int32_t
 abx_status clipK(cudaStream_t s, int32_t const *k_per_query, int k, int n, int64_t q, int32_t *out);
 abx_status halfTraversalPairs(cudaStream_t s, abx_bvh *bvh, float r, uint32_t *pairs, int64_t capacity,
                               unsigned long long *count_dev);
+// capi.cu: the CRS drivers (also used by the DistributedTree host code, abx_dist.cu)
+abx_status spatialCrs(abx_bvh *bvh, cudaStream_t s, int pred_kind, void const *preds, int64_t q,
+                      abx_policy const &policy, abx_alloc_fn alloc, void *user, int32_t **offsets_out,
+                      uint32_t **indices_out, int64_t *nnz_out,
+                      std::function<abx_status()> const &before_sync = nullptr);
+abx_status nearestCrs(abx_bvh *bvh, cudaStream_t s, void const *pts, int64_t q, int32_t k,
+                      int32_t const *k_per_query, abx_policy const &policy, abx_alloc_fn alloc, void *user,
+                      int32_t **offsets_out, uint32_t **indices_out, float **distances_out, int64_t *nnz_out);
+abx_status ensureDevice();
 // dbscan.cu
 abx_status dbscan(cudaStream_t s, float const *xyz, int64_t n, float eps, int32_t minpts, int impl, int algo,
                   int32_t *labels);

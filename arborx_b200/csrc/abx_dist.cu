@@ -1,0 +1,1354 @@
+// abx_dist.cu -- ArborX::DistributedTree: communicators and the host side of the sharded search.
+//
+// Behavioural contract: distributed/ArborX_DistributedTree.hpp:33-252 (ctor: bottom tree, all-gather of
+// rank boxes and sizes, replicated top tree), detail/ArborX_DistributedTreeSpatial.hpp:31-60,
+// detail/ArborX_DistributedTreeNearest.hpp:41-261 (two-phase kNN), detail/ArborX_DistributedTreeUtils.hpp
+// (forwardQueries :52-115, communicateResultsBack :153-224, countResults / sort :229-263, filterResults
+// :267-342), detail/ArborX_Distributor.hpp:40-541 (MPI point-to-point, three messages each way).
+//
+// Shape here.  The reference forwards EVERY query through its exchange, including the vast majority
+// that only concern the rank they live on.  Here the local tree answers all local predicates directly;
+// a routing kernel tests each predicate against the R rank boxes (the top tree for R <= 64, conservative
+// for spheres) and only predicates that also touch OTHER ranks are forwarded, queried there and merged
+// back per query.  For kNN the local k-th distance bounds the true one, so the reference's phase I needs
+// no exchange at all: rows short of k locally carry an infinite bound and are forwarded everywhere.
+// One schedule of collectives for every input (no rank-local fall-back decision):
+//   spatial   all-gather(R x R counts) | send/recv(predicates, ids) | all-gather(R x R counts) | send/recv(results)
+//   nearest   the same, with (index, id, distance) results
+// and two blocking points per call (each covers one count matrix; the first one is the local query's own).
+// Columns of one exchange travel in ONE NCCL group (a single fused kernel on NVLink / NVSwitch).
+#include "abx_common.cuh"
+
+#include <algorithm>
+#include <condition_variable>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <vector>
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+// ---------------------------------------------------------------- communicators ----
+struct ExchangeColumn
+{
+  void const *send;
+  void *recv;
+  size_t elem_bytes;
+};
+
+struct abx_comm
+{
+  int rank = 0, size = 1;
+  virtual ~abx_comm() {}
+  // every rank contributes `bytes` bytes; recv holds size * bytes
+  virtual abx_status allGather(void const *send, void *recv, size_t bytes, cudaStream_t s) = 0;
+  // element ranges [off[r], off[r + 1]) of every column go to / come from rank r (host arrays, R + 1 entries)
+  virtual abx_status allToAllV(ExchangeColumn const *cols, int ncols, int64_t const *send_off, int64_t const *recv_off,
+                               cudaStream_t s) = 0;
+};
+
+namespace abx
+{
+namespace
+{
+
+// ---- NCCL, resolved at run time: the library loads (and the single-GPU path works) without it ----
+struct NcclApi
+{
+  void *handle = nullptr;
+  std::string error;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*CommCount)(const ncclComm_t, int *) = nullptr;
+  ncclResult_t (*CommUserRank)(const ncclComm_t, int *) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+NcclApi *ncclApi()
+{
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    // the copy the process already has (e.g. the one torch loaded) wins: same soname
+    api.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!api.handle)
+      api.handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!api.handle)
+    {
+      api.error = std::string("libnccl.so.2 not found: ") + dlerror();
+      return;
+    }
+#define ABX_NCCL_SYM(field, name)                                                                                     \
+  api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.handle, name));                                          \
+  if (!api.field)                                                                                                      \
+    api.error = std::string("missing NCCL symbol ") + name;
+    ABX_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+    ABX_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+    ABX_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+    ABX_NCCL_SYM(CommCount, "ncclCommCount")
+    ABX_NCCL_SYM(CommUserRank, "ncclCommUserRank")
+    ABX_NCCL_SYM(AllGather, "ncclAllGather")
+    ABX_NCCL_SYM(Send, "ncclSend")
+    ABX_NCCL_SYM(Recv, "ncclRecv")
+    ABX_NCCL_SYM(GroupStart, "ncclGroupStart")
+    ABX_NCCL_SYM(GroupEnd, "ncclGroupEnd")
+    ABX_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef ABX_NCCL_SYM
+  });
+  if (!api.error.empty())
+  {
+    setError("NCCL unavailable: " + api.error);
+    return nullptr;
+  }
+  return &api;
+}
+
+#define ABX_NCCL_TRY(api, expr)                                                                                       \
+  do                                                                                                                   \
+  {                                                                                                                    \
+    ncclResult_t _r = (expr);                                                                                          \
+    if (_r != ncclSuccess)                                                                                             \
+    {                                                                                                                  \
+      ::abx::setError(std::string(#expr) + ": " + (api)->GetErrorString(_r));                                          \
+      return ABX_ERR_CUDA;                                                                                             \
+    }                                                                                                                  \
+  } while (0)
+
+struct NcclComm : abx_comm
+{
+  NcclApi *api = nullptr;
+  ncclComm_t comm = nullptr;
+  bool owned = false;
+  ~NcclComm() override
+  {
+    if (owned && comm && api)
+      api->CommDestroy(comm);
+  }
+  abx_status allGather(void const *send, void *recv, size_t bytes, cudaStream_t s) override
+  {
+    ABX_NCCL_TRY(api, api->AllGather(send, recv, bytes, ncclInt8, comm, s));
+    ++g_launch_count; // the collective's kernel
+    return ABX_OK;
+  }
+  abx_status allToAllV(ExchangeColumn const *cols, int ncols, int64_t const *send_off, int64_t const *recv_off,
+                       cudaStream_t s) override
+  {
+    bool any = false;
+    for (int r = 0; r < size; ++r)
+      any |= r != rank && (send_off[r + 1] > send_off[r] || recv_off[r + 1] > recv_off[r]);
+    for (int c = 0; c < ncols; ++c)
+    {
+      // a rank is never its own destination in the DistributedTree exchanges, but keep the operation complete
+      size_t const eb = cols[c].elem_bytes;
+      int64_t const cnt = send_off[rank + 1] - send_off[rank];
+      if (cnt > 0)
+        ABX_CUDA_TRY(cudaMemcpyAsync((char *)cols[c].recv + recv_off[rank] * eb,
+                                     (char const *)cols[c].send + send_off[rank] * eb, cnt * eb,
+                                     cudaMemcpyDeviceToDevice, s));
+    }
+    if (!any)
+      return ABX_OK;
+    ABX_NCCL_TRY(api, api->GroupStart());
+    for (int r = 0; r < size; ++r)
+    {
+      if (r == rank)
+        continue;
+      int64_t const ns = send_off[r + 1] - send_off[r], nr = recv_off[r + 1] - recv_off[r];
+      for (int c = 0; c < ncols; ++c)
+      {
+        size_t const eb = cols[c].elem_bytes;
+        if (ns > 0)
+          ABX_NCCL_TRY(api, api->Send((char const *)cols[c].send + send_off[r] * eb, (size_t)ns * eb, ncclInt8, r, comm, s));
+        if (nr > 0)
+          ABX_NCCL_TRY(api, api->Recv((char *)cols[c].recv + recv_off[r] * eb, (size_t)nr * eb, ncclInt8, r, comm, s));
+      }
+    }
+    ABX_NCCL_TRY(api, api->GroupEnd());
+    ++g_launch_count;
+    return ABX_OK;
+  }
+};
+
+// ---- in-process group: R host threads, one GPU.  The collectives are device-to-device copies between
+// the threads' buffers around a thread barrier -- the same protocol code runs on a single-GPU box.
+struct LocalGroup
+{
+  int size = 0;
+  std::mutex m;
+  std::condition_variable cv;
+  int arrived = 0;
+  long generation = 0;
+  std::vector<void const *> ptr;
+  std::vector<ExchangeColumn const *> cols;
+  std::vector<int64_t const *> off;
+  void barrier()
+  {
+    std::unique_lock<std::mutex> lock(m);
+    long const g = generation;
+    if (++arrived == size)
+    {
+      arrived = 0;
+      ++generation;
+      cv.notify_all();
+    }
+    else
+      cv.wait(lock, [&] { return generation != g; });
+  }
+};
+
+struct LocalComm : abx_comm
+{
+  std::shared_ptr<LocalGroup> g;
+  abx_status allGather(void const *send, void *recv, size_t bytes, cudaStream_t s) override
+  {
+    ABX_CUDA_TRY(cudaStreamSynchronize(s)); // the contribution is complete
+    g->ptr[rank] = send;
+    g->barrier();
+    for (int r = 0; r < size; ++r)
+      ABX_CUDA_TRY(cudaMemcpyAsync((char *)recv + (size_t)r * bytes, g->ptr[r], bytes, cudaMemcpyDeviceToDevice, s));
+    ABX_CUDA_TRY(cudaStreamSynchronize(s));
+    g->barrier(); // nobody reuses its send buffer before every reader is done
+    return ABX_OK;
+  }
+  abx_status allToAllV(ExchangeColumn const *cols, int ncols, int64_t const *send_off, int64_t const *recv_off,
+                       cudaStream_t s) override
+  {
+    ABX_CUDA_TRY(cudaStreamSynchronize(s));
+    g->cols[rank] = cols;
+    g->off[rank] = send_off;
+    g->barrier();
+    for (int r = 0; r < size; ++r)
+    {
+      int64_t const first = g->off[r][rank], cnt = g->off[r][rank + 1] - first;
+      if (cnt != recv_off[r + 1] - recv_off[r])
+      {
+        setError("local communicator: send / receive counts disagree");
+        g->barrier();
+        return ABX_ERR_ARG;
+      }
+      for (int c = 0; c < ncols && cnt > 0; ++c)
+      {
+        size_t const eb = cols[c].elem_bytes;
+        ABX_CUDA_TRY(cudaMemcpyAsync((char *)cols[c].recv + recv_off[r] * eb, (char const *)g->cols[r][c].send + first * eb,
+                                     cnt * eb, cudaMemcpyDeviceToDevice, s));
+      }
+    }
+    ABX_CUDA_TRY(cudaStreamSynchronize(s));
+    g->barrier();
+    return ABX_OK;
+  }
+};
+
+// ------------------------------------------------------------------ small kernels ----
+// send_preds[j] = preds[qids[j]] (W 32-bit words per predicate)
+__global__ void gatherWordsKernel(uint32_t const *__restrict__ src, int32_t const *__restrict__ ids, int64_t m, int W,
+                                  uint32_t *__restrict__ dst)
+{
+  int64_t const i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m * W)
+    return;
+  int64_t const j = i / W;
+  int const w = (int)(i - j * W);
+  dst[i] = src[(int64_t)ids[j] * W + w];
+}
+
+// out[r] = off[starts[r + 1]] - off[starts[r]] for r < R (results per source rank of the forwarded queries)
+__global__ void segmentTotalsKernel(int32_t const *__restrict__ off, int32_t const *__restrict__ starts, int R,
+                                    uint32_t *__restrict__ out)
+{
+  int const r = threadIdx.x;
+  if (r < R)
+    out[r] = (uint32_t)(off[starts[r + 1]] - off[starts[r]]);
+}
+
+// ids_out[e] = ids[row of result e] for a CRS with offsets off[0 .. g]
+__global__ void expandRowIdsKernel(int32_t const *__restrict__ off, int32_t const *__restrict__ ids, int g, int64_t nnz,
+                                   int32_t *__restrict__ ids_out)
+{
+  int64_t const e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nnz)
+    return;
+  int lo = 0, hi = g; // largest row with off[row] <= e
+  while (hi - lo > 1)
+  {
+    int const mid = (lo + hi) >> 1;
+    if (off[mid] <= e)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  ids_out[e] = ids[lo];
+}
+
+// kNN results of the forwarded queries: rows of `stride` slots with counts[j] valid entries -> contiguous
+// records (index, distance, query id) at off[j]
+__global__ void packKnnResultsKernel(int g, int stride, int32_t const *__restrict__ counts, int32_t const *__restrict__ off,
+                                     uint32_t const *__restrict__ idx, float const *__restrict__ dist,
+                                     int32_t const *__restrict__ ids, int32_t *__restrict__ out_idx,
+                                     float *__restrict__ out_dist, int32_t *__restrict__ out_ids)
+{
+  int const j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= g)
+    return;
+  int const c = counts[j], o = off[j], id = ids[j];
+  for (int e = 0; e < c; ++e)
+  {
+    out_idx[o + e] = (int32_t)idx[(int64_t)j * stride + e];
+    out_dist[o + e] = dist[(int64_t)j * stride + e];
+    out_ids[o + e] = id;
+  }
+}
+
+// received records in query-id order: position j takes record perm[j]; its owner rank is the segment of the
+// receive buffer the record arrived in (seg_off: R + 1 entries)
+__global__ void finishRemoteKernel(int64_t m, uint32_t const *__restrict__ perm, int32_t const *__restrict__ got_idx,
+                                   float const *__restrict__ got_dist, int32_t const *__restrict__ seg_off, int R,
+                                   int2 *__restrict__ vals2, float *__restrict__ dist_out)
+{
+  int64_t const j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m)
+    return;
+  int const src = (int)perm[j];
+  int rank = 0;
+  while (rank + 1 < R && seg_off[rank + 1] <= src)
+    ++rank;
+  vals2[j] = make_int2(got_idx[src], rank);
+  if (dist_out)
+    dist_out[j] = got_dist[src];
+}
+
+__global__ void fillPaddedRowsKernel(int64_t n, int2 *__restrict__ vals2, float *__restrict__ dist)
+{
+  int64_t const i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  vals2[i] = make_int2(-1, -1);
+  if (dist)
+    dist[i] = __int_as_float(0x7f800000);
+}
+
+__global__ void fillStrideOffsetsKernel(int32_t *offsets, int64_t q_plus_1, int stride)
+{
+  int64_t const i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < q_plus_1)
+    offsets[i] = (int32_t)(i * stride);
+}
+
+// valid (index >= 0) entries per padded kNN row
+__global__ void countValidKernel(int64_t q, int k, int2 const *__restrict__ vals2, int32_t *__restrict__ counts)
+{
+  int64_t const i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= q)
+    return;
+  int c = 0;
+  for (int j = 0; j < k; ++j)
+    c += vals2[i * k + j].x >= 0 ? 1 : 0;
+  counts[i] = c;
+}
+__global__ void compactPaddedRowsKernel(int64_t q, int k, int32_t const *__restrict__ off, int2 const *__restrict__ vals2,
+                                        float const *__restrict__ dist, int2 *__restrict__ out_vals2,
+                                        float *__restrict__ out_dist)
+{
+  int64_t const i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= q)
+    return;
+  int const o = off[i], c = off[i + 1] - o;
+  for (int j = 0; j < c; ++j)
+  {
+    out_vals2[o + j] = vals2[i * k + j];
+    if (out_dist)
+      out_dist[o + j] = dist[i * k + j];
+  }
+}
+
+// ---- compact (host) result form: indices + the list of entries owned by other ranks ----
+// spatial: local rows -> indices at their merged offsets (same walk as mergeLocalRowsKernel, 4-byte values)
+__global__ void __launch_bounds__(256)
+    compactLocalRowsKernel(int64_t q, int32_t const *__restrict__ local_off, uint32_t const *__restrict__ local_idx,
+                           int32_t const *__restrict__ out_off, uint32_t *__restrict__ out_idx)
+{
+  int const lane = threadIdx.x & 31;
+  int64_t const r0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
+  if (r0 >= q)
+    return;
+  int64_t const r = min(r0 + lane, q);
+  int const lo = local_off[r];
+  int const shift = (r < q ? out_off[r] : 0) - lo;
+  int const begin = __shfl_sync(0xffffffffu, lo, 0);
+  int const end = local_off[min(r0 + 32, q)];
+  for (int j = begin + lane; j - lane < end; j += 32)
+  {
+    int l = 0;
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1)
+    {
+      int const probe = __shfl_sync(0xffffffffu, lo, min(l + step, 31));
+      if (l + step < 32 && probe <= j)
+        l += step;
+    }
+    int const sh = __shfl_sync(0xffffffffu, shift, l);
+    if (j < end)
+      out_idx[j + sh] = local_idx[j];
+  }
+}
+// remote records (query id ascending) -> indices behind the local part of their rows + (position, rank) list
+__global__ void compactRemoteRowsKernel(int64_t m, int32_t const *__restrict__ ids, int2 const *__restrict__ vals,
+                                        int32_t const *__restrict__ local_off, int32_t const *__restrict__ out_off,
+                                        uint32_t *__restrict__ out_idx, int32_t *__restrict__ remote_pos,
+                                        int32_t *__restrict__ remote_rank)
+{
+  int64_t const c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= m)
+    return;
+  int const qid = ids[c];
+  if (c > 0 && ids[c - 1] == qid)
+    return;
+  int dst = out_off[qid] + (local_off[qid + 1] - local_off[qid]);
+  for (int64_t e = c; e < m && ids[e] == qid; ++e, ++dst)
+  {
+    int2 const v = vals[e];
+    out_idx[dst] = (uint32_t)v.x;
+    remote_pos[e] = dst; // ids ascending => positions ascending
+    remote_rank[e] = v.y;
+  }
+}
+// kNN: (index, rank) rows -> index rows
+__global__ void splitPairsKernel(int64_t n, int2 const *__restrict__ vals2, uint32_t *__restrict__ idx)
+{
+  int64_t const i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    idx[i] = (uint32_t)vals2[i].x;
+}
+// kNN: the rows that received candidates (segment leaders of ids) list their entries owned by other ranks
+__global__ void listRemoteInRowsKernel(int64_t m, int32_t const *__restrict__ ids, int k, int2 const *__restrict__ vals2,
+                                       int32_t const *__restrict__ row_off /* null: i * k */, int self_rank,
+                                       unsigned *__restrict__ counter, uint32_t *__restrict__ pos_out,
+                                       uint32_t *__restrict__ rank_out)
+{
+  int64_t const c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= m)
+    return;
+  int const qid = ids[c];
+  if (c > 0 && ids[c - 1] == qid)
+    return;
+  int64_t const out_base = row_off ? (int64_t)row_off[qid] : (int64_t)qid * k;
+  int slot = 0;
+  for (int j = 0; j < k; ++j)
+  {
+    int2 const v = vals2[(int64_t)qid * k + j];
+    if (v.x < 0)
+      break; // padding
+    if (v.y != self_rank)
+    {
+      unsigned const o = atomicAdd(counter, 1u);
+      pos_out[o] = (uint32_t)(out_base + slot);
+      rank_out[o] = (uint32_t)v.y;
+    }
+    ++slot;
+  }
+}
+
+int predWords(int kind) { return kind == ABX_PRED_SPHERE3F ? 4 : kind == ABX_PRED_BOX3F ? 6 : 3; }
+int primWords(int kind) { return kind == ABX_PRIM_POINT3F ? 3 : kind == ABX_PRIM_BOX3F ? 6 : 9; }
+
+int bitsFor(int64_t n)
+{
+  int b = 1;
+  while (b < 32 && ((int64_t)1 << b) < n)
+    ++b;
+  return b;
+}
+
+abx_status allocOutDev(abx_alloc_fn alloc, void *user, int which, size_t bytes, cudaStream_t s, void **out)
+{
+  if (alloc)
+  {
+    *out = alloc(user, which, bytes);
+    if (!*out && bytes)
+    {
+      setError("output allocator returned NULL");
+      return ABX_ERR_ARG;
+    }
+    return ABX_OK;
+  }
+  return deviceAlloc(out, std::max<size_t>(bytes, 4), s);
+}
+
+} // namespace
+} // namespace abx
+
+using namespace abx;
+
+// ----------------------------------------------------------------------- the tree ----
+struct abx_dist_tree
+{
+  abx_comm *comm = nullptr;
+  abx_bvh *bottom = nullptr;
+  int kind = 0, R = 1, rank = 0;
+  std::vector<float> boxes;   // R x 6 (rank boxes = leaves of the top tree)
+  std::vector<int64_t> sizes; // primitives per rank
+  int64_t total = 0;
+  float *boxes_dev = nullptr;
+  uint32_t *h_pin = nullptr; // pinned scratch: R x R count matrix, then one 64-bit word (8-byte aligned)
+  float bounds[6];
+};
+
+namespace abx
+{
+namespace
+{
+
+// counts_dev[R] of every rank -> pinned host matrix M[src][dst]; the caller's next blocking point covers it
+abx_status gatherCountMatrix(abx_dist_tree *t, cudaStream_t s, uint32_t const *counts_dev, uint32_t *matrix_dev)
+{
+  int const R = t->R;
+  ABX_TRY(t->comm->allGather(counts_dev, matrix_dev, sizeof(uint32_t) * R, s));
+  ABX_CUDA_TRY(cudaMemcpyAsync(t->h_pin, matrix_dev, sizeof(uint32_t) * R * R, cudaMemcpyDeviceToHost, s));
+  return ABX_OK;
+}
+
+struct ExchangePlan
+{
+  std::vector<int64_t> send_off, recv_off; // R + 1
+  int64_t n_send = 0, n_recv = 0, global = 0;
+  void fromMatrix(uint32_t const *M, int R, int rank)
+  {
+    send_off.assign(R + 1, 0);
+    recv_off.assign(R + 1, 0);
+    global = 0;
+    for (int r = 0; r < R; ++r)
+    {
+      send_off[r + 1] = send_off[r] + M[rank * R + r];
+      recv_off[r + 1] = recv_off[r] + M[r * R + rank];
+    }
+    for (int i = 0; i < R * R; ++i)
+      global += M[i];
+    n_send = send_off[R];
+    n_recv = recv_off[R];
+  }
+};
+
+// Forward the predicates listed by the routing pass (counts already on the host in `plan`), returning the
+// received predicates and their query ids on the source rank.
+abx_status forwardPredicates(abx_dist_tree *t, cudaStream_t s, int route_kind, void const *preds, int words, int64_t q,
+                             float const *radius, int64_t radius_stride, ExchangePlan const &plan,
+                             TempBuffer<uint32_t> &fwd_preds, TempBuffer<int32_t> &fwd_ids)
+{
+  int const R = t->R;
+  int64_t const F = plan.n_send, G = plan.n_recv;
+  TempBuffer<int32_t> qids;
+  TempBuffer<uint32_t> send_preds, base, cursors;
+  ABX_TRY(qids.alloc((size_t)std::max<int64_t>(F, 1), s));
+  ABX_TRY(send_preds.alloc((size_t)std::max<int64_t>(F, 1) * words, s));
+  ABX_TRY(fwd_preds.alloc((size_t)std::max<int64_t>(G, 1) * words, s));
+  ABX_TRY(fwd_ids.alloc((size_t)std::max<int64_t>(G, 1), s));
+  if (F > 0)
+  {
+    ABX_TRY(base.alloc(R, s));
+    ABX_TRY(cursors.alloc(R, s));
+    std::vector<uint32_t> h_base(R);
+    for (int r = 0; r < R; ++r)
+      h_base[r] = (uint32_t)plan.send_off[r];
+    // pageable source: staged by the runtime before the call returns
+    ABX_CUDA_TRY(cudaMemcpyAsync(base.ptr, h_base.data(), sizeof(uint32_t) * R, cudaMemcpyHostToDevice, s));
+    ABX_CUDA_TRY(cudaMemsetAsync(cursors.ptr, 0, sizeof(uint32_t) * R, s));
+    ABX_TRY(routeLaunch(s, true, route_kind, preds, q, radius, radius_stride, t->boxes_dev, R, t->rank, nullptr,
+                        base.ptr, cursors.ptr, qids.ptr));
+    ABX_LAUNCH(gatherWordsKernel, divUp(F * words, 256), 256, 0, s, (uint32_t const *)preds, qids.ptr, F, words,
+               send_preds.ptr);
+  }
+  ExchangeColumn cols[2] = {{send_preds.ptr, fwd_preds.ptr, sizeof(uint32_t) * (size_t)words},
+                            {qids.ptr, fwd_ids.ptr, sizeof(int32_t)}};
+  return t->comm->allToAllV(cols, 2, plan.send_off.data(), plan.recv_off.data(), s);
+}
+
+// received (index, id[, distance]) records -> query-id order with owner ranks
+abx_status sortReceived(abx_dist_tree *t, cudaStream_t s, int64_t M, int64_t q, ExchangePlan const &back,
+                        TempBuffer<int32_t> &got_ids /* in: ids, out: sorted */, int32_t const *got_idx,
+                        float const *got_dist, TempBuffer<int32_t> &vals2, TempBuffer<float> &dist_sorted)
+{
+  int const R = t->R;
+  ABX_TRY(vals2.alloc((size_t)std::max<int64_t>(M, 1) * 2, s));
+  if (got_dist)
+    ABX_TRY(dist_sorted.alloc((size_t)std::max<int64_t>(M, 1), s));
+  if (M == 0)
+    return ABX_OK;
+  TempBuffer<uint32_t> perm;
+  TempBuffer<int32_t> seg;
+  ABX_TRY(perm.alloc((size_t)M, s));
+  ABX_TRY(seg.alloc(R + 1, s));
+  std::vector<int32_t> h_seg(R + 1);
+  for (int r = 0; r <= R; ++r)
+    h_seg[r] = (int32_t)back.recv_off[r];
+  ABX_CUDA_TRY(cudaMemcpyAsync(seg.ptr, h_seg.data(), sizeof(int32_t) * (R + 1), cudaMemcpyHostToDevice, s));
+  // stable: records of one query keep their (source rank, traversal) order
+  // (plain LSD passes: no fix-up stage, hence no blocking point)
+  ABX_TRY(sortPairsU32(s, (uint32_t *)got_ids.ptr, perm.ptr, M, true, bitsFor(q), /*fixup=*/false));
+  ABX_LAUNCH(finishRemoteKernel, divUp(M, 256), 256, 0, s, M, perm.ptr, got_idx, got_dist, seg.ptr, R, (int2 *)vals2.ptr,
+             got_dist ? dist_sorted.ptr : nullptr);
+  return ABX_OK;
+}
+
+} // namespace
+
+abx_status localKnnPairs(abx_bvh *bvh, cudaStream_t s, void const *pts, int64_t q, int32_t k, int rank, int32_t *vals2,
+                         float *dist, unsigned long long *missing_dev);
+
+// ---- spatial -------------------------------------------------------------------------------
+// compact = false: (index, rank) pairs in *values_out (8 bytes per result)
+// compact = true : indices in *values_out (4 bytes per result) + remote_pos / remote_rank lists (device, library-owned)
+abx_status distSpatial(abx_dist_tree *t, cudaStream_t s, int pred_kind, void const *preds, int64_t q, bool compact,
+                       abx_alloc_fn alloc, void *user, int32_t **offsets_out, void **values_out, int64_t *nnz_out,
+                       TempBuffer<int32_t> *remote_pos, TempBuffer<int32_t> *remote_rank, int64_t *n_remote)
+{
+  if (pred_kind != ABX_PRED_SPHERE3F && pred_kind != ABX_PRED_BOX3F && pred_kind != ABX_PRED_POINT3F)
+  {
+    setError("DistributedTree: spatial predicates are intersects(Sphere | Box | Point)");
+    return ABX_ERR_ARG;
+  }
+  if (q < 0 || q >= (int64_t)1 << 30 || (q > 0 && !preds))
+  {
+    setError("DistributedTree: bad predicate array");
+    return ABX_ERR_ARG;
+  }
+  int const R = t->R, W = predWords(pred_kind);
+  *nnz_out = 0;
+  if (n_remote)
+    *n_remote = 0;
+  abx_policy policy;
+  policy.buffer_size = 0;
+  policy.sort_predicates = 1;
+  if (t->total == 0)
+  {
+    // DistributedTreeSpatial.hpp:44-50: nothing to search anywhere (every rank takes this branch)
+    void *off = nullptr, *vals = nullptr;
+    ABX_TRY(allocOutDev(alloc, user, 0, sizeof(int32_t) * (size_t)(q + 1), s, &off));
+    ABX_CUDA_TRY(cudaMemsetAsync(off, 0, sizeof(int32_t) * (size_t)(q + 1), s));
+    ABX_TRY(allocOutDev(alloc, user, 1, 0, s, &vals));
+    *offsets_out = (int32_t *)off;
+    *values_out = vals;
+    return ABX_OK;
+  }
+  // 1. routing counts of every rank -> count matrix on its way to the host
+  TempBuffer<uint32_t> counts, matrix;
+  ABX_TRY(counts.alloc(R, s));
+  ABX_TRY(matrix.alloc((size_t)R * R, s));
+  ABX_CUDA_TRY(cudaMemsetAsync(counts.ptr, 0, sizeof(uint32_t) * R, s));
+  ABX_TRY(routeLaunch(s, false, pred_kind, preds, q, nullptr, 0, t->boxes_dev, R, t->rank, counts.ptr, nullptr, nullptr,
+                      nullptr));
+  ABX_TRY(gatherCountMatrix(t, s, counts.ptr, matrix.ptr));
+  // 2. the local tree answers every local predicate; its blocking point (nnz) also covers the matrix
+  int32_t *off_l = nullptr;
+  uint32_t *idx_l = nullptr;
+  int64_t nnz_l = 0;
+  ABX_TRY(spatialCrs(t->bottom, s, pred_kind, preds, q, policy, nullptr, nullptr, &off_l, &idx_l, &nnz_l,
+                     [&]() -> abx_status { return ABX_OK; }));
+  struct Guard
+  {
+    cudaStream_t s;
+    void *a = nullptr, *b = nullptr;
+    ~Guard()
+    {
+      deviceFree(a, s);
+      deviceFree(b, s);
+    }
+  } local_guard{s, off_l, idx_l};
+  ExchangePlan fwd;
+  fwd.fromMatrix(t->h_pin, R, t->rank);
+
+  TempBuffer<int32_t> got_ids, got_idx, rvals2;
+  TempBuffer<float> unused;
+  int64_t M = 0;
+  if (fwd.global > 0)
+  {
+    // 3. forward, query the bottom tree with what arrived; its blocking point covers the back-count matrix
+    TempBuffer<uint32_t> fwd_preds;
+    TempBuffer<int32_t> fwd_ids;
+    ABX_TRY(forwardPredicates(t, s, pred_kind, preds, W, q, nullptr, 0, fwd, fwd_preds, fwd_ids));
+    int64_t const G = fwd.n_recv;
+    TempBuffer<int32_t> starts;
+    ABX_TRY(starts.alloc(R + 1, s));
+    std::vector<int32_t> h_starts(R + 1);
+    for (int r = 0; r <= R; ++r)
+      h_starts[r] = (int32_t)fwd.recv_off[r];
+    ABX_CUDA_TRY(cudaMemcpyAsync(starts.ptr, h_starts.data(), sizeof(int32_t) * (R + 1), cudaMemcpyHostToDevice, s));
+    int32_t *off_r = nullptr;
+    uint32_t *idx_r = nullptr;
+    int64_t nnz_r = 0;
+    ABX_TRY(spatialCrs(t->bottom, s, pred_kind, fwd_preds.ptr, G, policy, nullptr, nullptr, &off_r, &idx_r, &nnz_r,
+                       [&]() -> abx_status {
+                         // runs right after the scan of the remote query's offsets
+                         ABX_LAUNCH(segmentTotalsKernel, 1, 64, 0, s, off_r, starts.ptr, R, counts.ptr);
+                         return gatherCountMatrix(t, s, counts.ptr, matrix.ptr);
+                       }));
+    Guard remote_guard{s, off_r, idx_r};
+    ExchangePlan back;
+    back.fromMatrix(t->h_pin, R, t->rank);
+    M = back.n_recv;
+    // 4. results back: (index, query id) columns; the indices travel straight out of the CRS array
+    TempBuffer<int32_t> res_ids;
+    ABX_TRY(res_ids.alloc((size_t)std::max<int64_t>(nnz_r, 1), s));
+    if (nnz_r > 0)
+      ABX_LAUNCH(expandRowIdsKernel, divUp(nnz_r, 256), 256, 0, s, off_r, fwd_ids.ptr, (int)G, nnz_r, res_ids.ptr);
+    ABX_TRY(got_idx.alloc((size_t)std::max<int64_t>(M, 1), s));
+    ABX_TRY(got_ids.alloc((size_t)std::max<int64_t>(M, 1), s));
+    ExchangeColumn cols[2] = {{idx_r, got_idx.ptr, sizeof(int32_t)}, {res_ids.ptr, got_ids.ptr, sizeof(int32_t)}};
+    ABX_TRY(t->comm->allToAllV(cols, 2, back.send_off.data(), back.recv_off.data(), s));
+    ABX_TRY(sortReceived(t, s, M, q, back, got_ids, got_idx.ptr, nullptr, rvals2, unused));
+  }
+  // 5. merge per query: local results first, then the remote ones
+  int64_t const nnz = nnz_l + M;
+  if (nnz >= (int64_t)1 << 31)
+  {
+    setError("DistributedTree: more than 2^31 results on one rank");
+    return ABX_ERR_ARG;
+  }
+  void *off_v = nullptr, *vals_v = nullptr;
+  ABX_TRY(allocOutDev(alloc, user, 0, sizeof(int32_t) * (size_t)(q + 1), s, &off_v));
+  ABX_TRY(allocOutDev(alloc, user, 1, (compact ? sizeof(uint32_t) : 2 * sizeof(int32_t)) * (size_t)nnz, s, &vals_v));
+  *offsets_out = (int32_t *)off_v;
+  *values_out = vals_v;
+  *nnz_out = nnz;
+  if (n_remote)
+    *n_remote = M;
+  if (!compact)
+  {
+    if (M == 0)
+    {
+      ABX_CUDA_TRY(cudaMemcpyAsync(off_v, off_l, sizeof(int32_t) * (size_t)(q + 1), cudaMemcpyDeviceToDevice, s));
+      return pairWithRank(s, (int32_t const *)idx_l, nnz_l, t->rank, (int32_t *)vals_v);
+    }
+    return mergeSorted(s, q, off_l, (int32_t const *)idx_l, t->rank, M, got_ids.ptr, rvals2.ptr, (int32_t *)off_v,
+                       (int32_t *)vals_v);
+  }
+  if (M == 0)
+  {
+    ABX_CUDA_TRY(cudaMemcpyAsync(off_v, off_l, sizeof(int32_t) * (size_t)(q + 1), cudaMemcpyDeviceToDevice, s));
+    if (nnz_l > 0)
+      ABX_CUDA_TRY(cudaMemcpyAsync(vals_v, idx_l, sizeof(uint32_t) * (size_t)nnz_l, cudaMemcpyDeviceToDevice, s));
+    return ABX_OK;
+  }
+  ABX_TRY(remote_pos->alloc((size_t)M, s));
+  ABX_TRY(remote_rank->alloc((size_t)M, s));
+  ABX_TRY(mergeCounts(s, q, off_l, M, got_ids.ptr, (int32_t *)off_v));
+  if (q > 0)
+    ABX_LAUNCH(compactLocalRowsKernel, divUp(divUp(q, 32) * 32, 256), 256, 0, s, q, off_l, idx_l, (int32_t const *)off_v,
+               (uint32_t *)vals_v);
+  ABX_LAUNCH(compactRemoteRowsKernel, divUp(M, 256), 256, 0, s, M, got_ids.ptr, (int2 const *)rvals2.ptr, off_l,
+             (int32_t const *)off_v, (uint32_t *)vals_v, remote_pos->ptr, remote_rank->ptr);
+  return ABX_OK;
+}
+
+// ---- nearest -------------------------------------------------------------------------------
+// pairs rows (index, rank) x k per query are produced on the device in both forms; compact = true then
+// splits them into index rows + the list of entries owned by other ranks.
+abx_status distNearest(abx_dist_tree *t, cudaStream_t s, void const *pts, int64_t q, int32_t k, bool compact,
+                       bool want_dist, abx_alloc_fn alloc, void *user, int32_t **offsets_out, void **values_out,
+                       float **dist_out, int64_t *nnz_out, TempBuffer<int32_t> *remote_pos,
+                       TempBuffer<int32_t> *remote_rank, int64_t *n_remote)
+{
+  if (q < 0 || q >= (int64_t)1 << 30 || (q > 0 && !pts))
+  {
+    setError("DistributedTree: bad predicate array");
+    return ABX_ERR_ARG;
+  }
+  int const R = t->R;
+  *nnz_out = 0;
+  if (n_remote)
+    *n_remote = 0;
+  if (dist_out)
+    *dist_out = nullptr;
+  size_t const val_bytes = compact ? sizeof(uint32_t) : 2 * sizeof(int32_t);
+  if (t->total == 0 || k < 1)
+  {
+    void *off = nullptr, *vals = nullptr, *d = nullptr;
+    ABX_TRY(allocOutDev(alloc, user, 0, sizeof(int32_t) * (size_t)(q + 1), s, &off));
+    ABX_CUDA_TRY(cudaMemsetAsync(off, 0, sizeof(int32_t) * (size_t)(q + 1), s));
+    ABX_TRY(allocOutDev(alloc, user, 1, 0, s, &vals));
+    if (want_dist)
+      ABX_TRY(allocOutDev(alloc, user, 2, 0, s, &d));
+    *offsets_out = (int32_t *)off;
+    *values_out = vals;
+    if (dist_out)
+      *dist_out = (float *)d;
+    return ABX_OK;
+  }
+  if ((int64_t)k * q >= (int64_t)1 << 31)
+  {
+    setError("DistributedTree: more than 2^31 results on one rank");
+    return ABX_ERR_ARG;
+  }
+  int64_t const slots = (int64_t)k * q;
+  // 1. local k nearest of every point, rows of k slots in (index, rank) form, padded when short
+  TempBuffer<int32_t> rows;
+  TempBuffer<float> rows_d;
+  ABX_TRY(rows.alloc((size_t)std::max<int64_t>(slots, 1) * 2, s));
+  ABX_TRY(rows_d.alloc((size_t)std::max<int64_t>(slots, 1), s));
+  TempBuffer<unsigned long long> missing;
+  ABX_TRY(missing.alloc(1, s));
+  ABX_CUDA_TRY(cudaMemsetAsync(missing.ptr, 0, sizeof(unsigned long long), s));
+  ABX_TRY(localKnnPairs(t->bottom, s, pts, q, k, t->rank, rows.ptr, rows_d.ptr, missing.ptr));
+  // 2. phase II routing: sphere (point, local k-th distance); an infinite bound reaches every rank
+  TempBuffer<uint32_t> counts, matrix;
+  ABX_TRY(counts.alloc(R, s));
+  ABX_TRY(matrix.alloc((size_t)R * R, s));
+  ABX_CUDA_TRY(cudaMemsetAsync(counts.ptr, 0, sizeof(uint32_t) * R, s));
+  float const *radius = rows_d.ptr + (k - 1);
+  ABX_TRY(routeLaunch(s, false, ABX_PRED_SPHERE3F, pts, q, radius, k, t->boxes_dev, R, t->rank, counts.ptr, nullptr,
+                      nullptr, nullptr));
+  ABX_TRY(gatherCountMatrix(t, s, counts.ptr, matrix.ptr));
+  unsigned long long *h_missing = reinterpret_cast<unsigned long long *>(t->h_pin + (((size_t)R * R + 1) & ~(size_t)1));
+  ABX_CUDA_TRY(cudaMemcpyAsync(h_missing, missing.ptr, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  ABX_CUDA_TRY(cudaStreamSynchronize(s)); // blocking point 1
+  bool maybe_short = *h_missing != 0;
+  ExchangePlan fwd;
+  fwd.fromMatrix(t->h_pin, R, t->rank);
+  TempBuffer<int32_t> got_ids, rvals2;
+  TempBuffer<float> rdist;
+  int64_t M = 0;
+  if (fwd.global > 0)
+  {
+    TempBuffer<uint32_t> fwd_pts;
+    TempBuffer<int32_t> fwd_ids;
+    ABX_TRY(forwardPredicates(t, s, ABX_PRED_SPHERE3F, pts, 3, q, radius, k, fwd, fwd_pts, fwd_ids));
+    int64_t const G = fwd.n_recv;
+    int const nloc = (int)t->bottom->n;
+    int const stride = std::max(1, std::min(k, nloc));
+    // 3. k nearest of the forwarded points in the bottom tree
+    TempBuffer<uint32_t> r_idx, qperm;
+    TempBuffer<float> r_dist;
+    TempBuffer<int32_t> r_counts, r_off, starts;
+    ABX_TRY(r_idx.alloc((size_t)std::max<int64_t>(G, 1) * stride, s));
+    ABX_TRY(r_dist.alloc((size_t)std::max<int64_t>(G, 1) * stride, s));
+    ABX_TRY(r_counts.alloc((size_t)G + 1, s));
+    ABX_TRY(r_off.alloc((size_t)G + 1, s));
+    ABX_TRY(starts.alloc(R + 1, s));
+    ABX_CUDA_TRY(cudaMemsetAsync(r_counts.ptr, 0, sizeof(int32_t) * ((size_t)G + 1), s));
+    if (G > 0 && nloc > 0)
+    {
+      if (nloc > 1)
+        ABX_TRY(predicatePermutation(s, t->bottom, ABX_PRED_POINT3F, fwd_pts.ptr, G, qperm));
+      ABX_TRY(nearestQuery(s, t->bottom, (float const *)fwd_pts.ptr, G, k, nullptr, qperm.ptr, nullptr, G * stride,
+                           r_counts.ptr, r_idx.ptr, r_dist.ptr));
+    }
+    ABX_TRY(exclusiveScanI32(s, r_counts.ptr, r_off.ptr, G + 1));
+    std::vector<int32_t> h_starts(R + 1);
+    for (int r = 0; r <= R; ++r)
+      h_starts[r] = (int32_t)fwd.recv_off[r];
+    ABX_CUDA_TRY(cudaMemcpyAsync(starts.ptr, h_starts.data(), sizeof(int32_t) * (R + 1), cudaMemcpyHostToDevice, s));
+    ABX_LAUNCH(segmentTotalsKernel, 1, 64, 0, s, r_off.ptr, starts.ptr, R, counts.ptr);
+    ABX_TRY(gatherCountMatrix(t, s, counts.ptr, matrix.ptr));
+    ABX_CUDA_TRY(cudaStreamSynchronize(s)); // blocking point 2
+    ExchangePlan back;
+    back.fromMatrix(t->h_pin, R, t->rank);
+    M = back.n_recv;
+    int64_t const nnz_r = back.n_send;
+    // 4. candidates back as (index, distance, query id) columns
+    TempBuffer<int32_t> s_idx, s_ids, got_idx;
+    TempBuffer<float> s_dist, got_dist;
+    ABX_TRY(s_idx.alloc((size_t)std::max<int64_t>(nnz_r, 1), s));
+    ABX_TRY(s_ids.alloc((size_t)std::max<int64_t>(nnz_r, 1), s));
+    ABX_TRY(s_dist.alloc((size_t)std::max<int64_t>(nnz_r, 1), s));
+    if (G > 0)
+      ABX_LAUNCH(packKnnResultsKernel, divUp(G, 128), 128, 0, s, (int)G, stride, r_counts.ptr, r_off.ptr, r_idx.ptr,
+                 r_dist.ptr, fwd_ids.ptr, s_idx.ptr, s_dist.ptr, s_ids.ptr);
+    ABX_TRY(got_idx.alloc((size_t)std::max<int64_t>(M, 1), s));
+    ABX_TRY(got_ids.alloc((size_t)std::max<int64_t>(M, 1), s));
+    ABX_TRY(got_dist.alloc((size_t)std::max<int64_t>(M, 1), s));
+    ExchangeColumn cols[3] = {{s_idx.ptr, got_idx.ptr, sizeof(int32_t)},
+                              {s_ids.ptr, got_ids.ptr, sizeof(int32_t)},
+                              {s_dist.ptr, got_dist.ptr, sizeof(float)}};
+    ABX_TRY(t->comm->allToAllV(cols, 3, back.send_off.data(), back.recv_off.data(), s));
+    ABX_TRY(sortReceived(t, s, M, q, back, got_ids, got_idx.ptr, got_dist.ptr, rvals2, rdist));
+    // 5. final ranking (DistributedTreeNearest.hpp:178-233): the k smallest of local row + candidates
+    ABX_TRY(knnMerge(s, M, got_ids.ptr, rvals2.ptr, rdist.ptr, k, rows.ptr, rows_d.ptr));
+  }
+  // 6. outputs.  Rows are full (k entries) unless some local row was short and stayed short.
+  TempBuffer<int32_t> row_counts, row_off;
+  int64_t nnz = slots;
+  bool short_rows = false;
+  if (maybe_short)
+  {
+    ABX_TRY(row_counts.alloc((size_t)q + 1, s));
+    ABX_TRY(row_off.alloc((size_t)q + 1, s));
+    TempBuffer<unsigned long long> total64;
+    ABX_TRY(total64.alloc(1, s));
+    if (q > 0)
+      ABX_LAUNCH(countValidKernel, divUp(q, 256), 256, 0, s, q, k, (int2 const *)rows.ptr, row_counts.ptr);
+    ABX_TRY(exclusiveScanI32(s, row_counts.ptr, row_off.ptr, q + 1, total64.ptr));
+    unsigned long long h_total = 0;
+    ABX_CUDA_TRY(cudaMemcpyAsync(&h_total, total64.ptr, sizeof(h_total), cudaMemcpyDeviceToHost, s));
+    ABX_CUDA_TRY(cudaStreamSynchronize(s));
+    nnz = (int64_t)h_total;
+    short_rows = nnz != slots;
+  }
+  void *off_v = nullptr, *vals_v = nullptr, *d_v = nullptr;
+  ABX_TRY(allocOutDev(alloc, user, 0, sizeof(int32_t) * (size_t)(q + 1), s, &off_v));
+  ABX_TRY(allocOutDev(alloc, user, 1, val_bytes * (size_t)nnz, s, &vals_v));
+  if (want_dist)
+    ABX_TRY(allocOutDev(alloc, user, 2, sizeof(float) * (size_t)nnz, s, &d_v));
+  *offsets_out = (int32_t *)off_v;
+  *values_out = vals_v;
+  if (dist_out)
+    *dist_out = (float *)d_v;
+  *nnz_out = nnz;
+  if (short_rows)
+    ABX_CUDA_TRY(cudaMemcpyAsync(off_v, row_off.ptr, sizeof(int32_t) * (size_t)(q + 1), cudaMemcpyDeviceToDevice, s));
+  else
+    ABX_LAUNCH(fillStrideOffsetsKernel, divUp(q + 1, 256), 256, 0, s, (int32_t *)off_v, q + 1, k);
+  // rows -> output values (pairs or indices), compacted when rows are short
+  TempBuffer<int32_t> packed;
+  TempBuffer<float> packed_d;
+  int2 const *src_rows = (int2 const *)rows.ptr;
+  float const *src_d = rows_d.ptr;
+  if (short_rows)
+  {
+    ABX_TRY(packed.alloc((size_t)std::max<int64_t>(nnz, 1) * 2, s));
+    ABX_TRY(packed_d.alloc((size_t)std::max<int64_t>(nnz, 1), s));
+    if (q > 0)
+      ABX_LAUNCH(compactPaddedRowsKernel, divUp(q, 256), 256, 0, s, q, k, row_off.ptr, (int2 const *)rows.ptr,
+                 rows_d.ptr, (int2 *)packed.ptr, packed_d.ptr);
+    src_rows = (int2 const *)packed.ptr;
+    src_d = packed_d.ptr;
+  }
+  if (nnz > 0)
+  {
+    if (compact)
+      ABX_LAUNCH(splitPairsKernel, divUp(nnz, 256), 256, 0, s, nnz, src_rows, (uint32_t *)vals_v);
+    else
+      ABX_CUDA_TRY(cudaMemcpyAsync(vals_v, src_rows, 2 * sizeof(int32_t) * (size_t)nnz, cudaMemcpyDeviceToDevice, s));
+    if (want_dist)
+      ABX_CUDA_TRY(cudaMemcpyAsync(d_v, src_d, sizeof(float) * (size_t)nnz, cudaMemcpyDeviceToDevice, s));
+  }
+  if (compact && M > 0)
+  {
+    // entries owned by other ranks can only sit in rows that received candidates
+    TempBuffer<unsigned> counter;
+    TempBuffer<uint32_t> pos, rk;
+    ABX_TRY(counter.alloc(1, s));
+    ABX_TRY(pos.alloc((size_t)M, s));
+    ABX_TRY(rk.alloc((size_t)M, s));
+    ABX_CUDA_TRY(cudaMemsetAsync(counter.ptr, 0, sizeof(unsigned), s));
+    ABX_LAUNCH(listRemoteInRowsKernel, divUp(M, 256), 256, 0, s, M, got_ids.ptr, k, (int2 const *)rows.ptr,
+               short_rows ? row_off.ptr : (int32_t const *)nullptr, t->rank, counter.ptr, pos.ptr, rk.ptr);
+    unsigned h_count = 0;
+    ABX_CUDA_TRY(cudaMemcpyAsync(&h_count, counter.ptr, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    ABX_CUDA_TRY(cudaStreamSynchronize(s));
+    if (h_count > 0)
+    {
+      ABX_TRY(sortPairsU32(s, pos.ptr, rk.ptr, h_count, false, bitsFor(std::max<int64_t>(nnz, 2)), /*fixup=*/false));
+      ABX_TRY(remote_pos->alloc(h_count, s));
+      ABX_TRY(remote_rank->alloc(h_count, s));
+      ABX_CUDA_TRY(cudaMemcpyAsync(remote_pos->ptr, pos.ptr, sizeof(int32_t) * h_count, cudaMemcpyDeviceToDevice, s));
+      ABX_CUDA_TRY(cudaMemcpyAsync(remote_rank->ptr, rk.ptr, sizeof(int32_t) * h_count, cudaMemcpyDeviceToDevice, s));
+    }
+    *n_remote = h_count;
+  }
+  return ABX_OK;
+}
+
+// local phase of the distributed kNN: rows of k (index, rank) slots, padded
+abx_status localKnnPairs(abx_bvh *bvh, cudaStream_t s, void const *pts, int64_t q, int32_t k, int rank, int32_t *vals2,
+                         float *dist, unsigned long long *missing_dev)
+{
+  int64_t const slots = (int64_t)std::max(k, 0) * q;
+  if (slots == 0)
+    return ABX_OK;
+  if (bvh->n == 0)
+  {
+    ABX_LAUNCH(fillPaddedRowsKernel, divUp(slots, 256), 256, 0, s, slots, (int2 *)vals2, dist);
+    if (missing_dev)
+    {
+      unsigned long long const m = (unsigned long long)slots;
+      ABX_CUDA_TRY(cudaMemcpyAsync(missing_dev, &m, sizeof(m), cudaMemcpyHostToDevice, s));
+    }
+    return ABX_OK;
+  }
+  TempBuffer<uint32_t> qperm;
+  if (bvh->n > 1)
+    ABX_TRY(predicatePermutation(s, bvh, ABX_PRED_POINT3F, pts, q, qperm));
+  return nearestQuery(s, bvh, (float const *)pts, q, k, nullptr, qperm.ptr, nullptr, slots, nullptr, (uint32_t *)vals2,
+                      dist, missing_dev, rank);
+}
+
+} // namespace abx
+
+// ------------------------------------------------------------------------- C ABI ----
+extern "C"
+{
+
+abx_status abx_comm_from_nccl(void *nccl_comm, abx_comm **out)
+{
+  if (!nccl_comm || !out)
+  {
+    setError("null argument");
+    return ABX_ERR_ARG;
+  }
+  *out = nullptr;
+  NcclApi *api = ncclApi();
+  if (!api)
+    return ABX_ERR_CUDA;
+  auto c = std::make_unique<NcclComm>();
+  c->api = api;
+  c->comm = (ncclComm_t)nccl_comm;
+  ABX_NCCL_TRY(api, api->CommCount(c->comm, &c->size));
+  ABX_NCCL_TRY(api, api->CommUserRank(c->comm, &c->rank));
+  *out = c.release();
+  return ABX_OK;
+}
+
+abx_status abx_comm_unique_id(char id_out[ABX_COMM_UNIQUE_ID_BYTES])
+{
+  static_assert(sizeof(ncclUniqueId) == ABX_COMM_UNIQUE_ID_BYTES, "unique id size");
+  NcclApi *api = ncclApi();
+  if (!api)
+    return ABX_ERR_CUDA;
+  ncclUniqueId id;
+  ABX_NCCL_TRY(api, api->GetUniqueId(&id));
+  memcpy(id_out, &id, sizeof(id));
+  return ABX_OK;
+}
+
+abx_status abx_comm_init_rank(const char id[ABX_COMM_UNIQUE_ID_BYTES], int32_t n_ranks, int32_t rank, abx_comm **out)
+{
+  if (!id || !out || n_ranks < 1 || rank < 0 || rank >= n_ranks)
+  {
+    setError("bad communicator arguments");
+    return ABX_ERR_ARG;
+  }
+  *out = nullptr;
+  ABX_TRY(ensureDevice());
+  NcclApi *api = ncclApi();
+  if (!api)
+    return ABX_ERR_CUDA;
+  ncclUniqueId uid;
+  memcpy(&uid, id, sizeof(uid));
+  auto c = std::make_unique<NcclComm>();
+  c->api = api;
+  c->owned = true;
+  ABX_NCCL_TRY(api, api->CommInitRank(&c->comm, n_ranks, uid, rank));
+  c->size = n_ranks;
+  c->rank = rank;
+  *out = c.release();
+  return ABX_OK;
+}
+
+abx_status abx_comm_create_local(int32_t n_ranks, abx_comm **out_array)
+{
+  if (!out_array || n_ranks < 1 || n_ranks > 64)
+  {
+    setError("bad communicator arguments");
+    return ABX_ERR_ARG;
+  }
+  auto g = std::make_shared<LocalGroup>();
+  g->size = n_ranks;
+  g->ptr.assign(n_ranks, nullptr);
+  g->cols.assign(n_ranks, nullptr);
+  g->off.assign(n_ranks, nullptr);
+  for (int r = 0; r < n_ranks; ++r)
+  {
+    LocalComm *c = new LocalComm;
+    c->g = g;
+    c->rank = r;
+    c->size = n_ranks;
+    out_array[r] = c;
+  }
+  return ABX_OK;
+}
+
+abx_status abx_comm_destroy(abx_comm *comm)
+{
+  delete comm;
+  return ABX_OK;
+}
+int32_t abx_comm_rank(const abx_comm *comm) { return comm ? comm->rank : -1; }
+int32_t abx_comm_size(const abx_comm *comm) { return comm ? comm->size : 0; }
+
+static abx_status distCreate(abx_comm *comm, cudaStream_t s, int prim_kind, void const *prims_dev, int64_t n,
+                             abx_dist_tree **out)
+{
+  if (comm->size > 64)
+  {
+    setError("DistributedTree: at most 64 ranks (the top tree is evaluated as a flat list of rank boxes)");
+    return ABX_ERR_ARG;
+  }
+  std::unique_ptr<abx_dist_tree, abx_status (*)(abx_dist_tree *)> t(new abx_dist_tree, abx_dist_destroy);
+  t->comm = comm;
+  t->R = comm->size;
+  t->rank = comm->rank;
+  t->kind = prim_kind;
+  int const R = t->R;
+  // bottom tree (ArborX_DistributedTree.hpp:183-186)
+  ABX_TRY(buildTree(s, prim_kind, prims_dev, n, nullptr, &t->bottom));
+  // all-gather of (rank box, size) (:208-227, :243-245): 6 floats + a 64-bit count per rank
+  TempBuffer<uint32_t> meta, all;
+  ABX_TRY(meta.alloc(8, s));
+  ABX_TRY(all.alloc((size_t)8 * R, s));
+  ABX_CUDA_TRY(cudaMemcpyAsync(meta.ptr, t->bottom->bounds_dev, 6 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  int64_t const n_local = n;
+  ABX_CUDA_TRY(cudaMemcpyAsync(meta.ptr + 6, &n_local, sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  ABX_TRY(comm->allGather(meta.ptr, all.ptr, 8 * sizeof(uint32_t), s));
+  std::vector<uint32_t> h(8 * (size_t)R);
+  ABX_CUDA_TRY(cudaMemcpyAsync(h.data(), all.ptr, sizeof(uint32_t) * 8 * R, cudaMemcpyDeviceToHost, s));
+  ABX_CUDA_TRY(cudaStreamSynchronize(s));
+  t->boxes.resize(6 * (size_t)R);
+  t->sizes.resize(R);
+  t->total = 0;
+  for (int d = 0; d < 3; ++d)
+  {
+    t->bounds[d] = FLT_MAX;
+    t->bounds[3 + d] = -FLT_MAX;
+  }
+  for (int r = 0; r < R; ++r)
+  {
+    memcpy(&t->boxes[6 * (size_t)r], &h[8 * (size_t)r], 6 * sizeof(float));
+    memcpy(&t->sizes[r], &h[8 * (size_t)r + 6], sizeof(int64_t));
+    t->total += t->sizes[r];
+    if (t->sizes[r] > 0)
+      for (int d = 0; d < 3; ++d)
+      {
+        t->bounds[d] = std::min(t->bounds[d], t->boxes[6 * (size_t)r + d]);
+        t->bounds[3 + d] = std::max(t->bounds[3 + d], t->boxes[6 * (size_t)r + 3 + d]);
+      }
+  }
+  ABX_TRY(deviceAlloc((void **)&t->boxes_dev, sizeof(float) * 6 * R, s));
+  ABX_CUDA_TRY(cudaMemcpyAsync(t->boxes_dev, t->boxes.data(), sizeof(float) * 6 * R, cudaMemcpyHostToDevice, s));
+  ABX_CUDA_TRY(cudaHostAlloc((void **)&t->h_pin, sizeof(uint32_t) * ((size_t)R * R + 8), cudaHostAllocDefault));
+  ABX_CUDA_TRY(cudaStreamSynchronize(s)); // boxes uploaded from this frame's vector
+  *out = t.release();
+  return ABX_OK;
+}
+
+abx_status abx_dist_create(abx_comm *comm, void *stream, int prim_kind, const void *prims_dev, int64_t n,
+                           abx_dist_tree **out)
+{
+  if (!comm || !out)
+  {
+    setError("null argument");
+    return ABX_ERR_ARG;
+  }
+  *out = nullptr;
+  ABX_TRY(ensureDevice());
+  return distCreate(comm, (cudaStream_t)stream, prim_kind, prims_dev, n, out);
+}
+
+abx_status abx_dist_create_host(abx_comm *comm, void *stream, int prim_kind, const void *prims_host, int64_t n,
+                                abx_dist_tree **out)
+{
+  if (!comm || !out || n < 0 || prim_kind < 0 || prim_kind > ABX_PRIM_TRI3F)
+  {
+    setError("bad argument");
+    return ABX_ERR_ARG;
+  }
+  *out = nullptr;
+  ABX_TRY(ensureDevice());
+  cudaStream_t s = (cudaStream_t)stream;
+  TempBuffer<float> dev;
+  ABX_TRY(dev.alloc((size_t)primWords(prim_kind) * (size_t)std::max<int64_t>(n, 1), s));
+  if (n > 0)
+    ABX_CUDA_TRY(cudaMemcpyAsync(dev.ptr, prims_host, sizeof(float) * primWords(prim_kind) * (size_t)n,
+                                 cudaMemcpyHostToDevice, s));
+  return distCreate(comm, s, prim_kind, dev.ptr, n, out);
+}
+
+abx_status abx_dist_destroy(abx_dist_tree *t)
+{
+  if (!t)
+    return ABX_OK;
+  if (t->bottom)
+  {
+    deviceFree(t->boxes_dev, t->bottom->stream);
+    abx_bvh_destroy(t->bottom);
+  }
+  if (t->h_pin)
+    cudaFreeHost(t->h_pin);
+  delete t;
+  return ABX_OK;
+}
+
+int64_t abx_dist_size(const abx_dist_tree *t) { return t ? t->total : 0; }
+int abx_dist_empty(const abx_dist_tree *t) { return !t || t->total == 0; }
+abx_status abx_dist_bounds(const abx_dist_tree *t, float out6[6])
+{
+  if (!t || !out6)
+  {
+    setError("null argument");
+    return ABX_ERR_ARG;
+  }
+  memcpy(out6, t->bounds, sizeof(t->bounds));
+  return ABX_OK;
+}
+
+abx_status abx_dist_query_spatial_crs(abx_dist_tree *t, void *stream, int pred_kind, const void *preds_dev, int64_t q,
+                                      abx_alloc_fn alloc, void *user, int32_t **offsets_dev, int32_t **values2_dev,
+                                      int64_t *nnz)
+{
+  if (!t || !offsets_dev || !values2_dev || !nnz)
+  {
+    setError("null argument");
+    return ABX_ERR_ARG;
+  }
+  void *vals = nullptr;
+  abx_status const st = distSpatial(t, (cudaStream_t)stream, pred_kind, preds_dev, q, false, alloc, user, offsets_dev,
+                                    &vals, nnz, nullptr, nullptr, nullptr);
+  *values2_dev = (int32_t *)vals;
+  return st;
+}
+
+abx_status abx_dist_query_nearest_crs(abx_dist_tree *t, void *stream, const void *points_dev, int64_t q, int32_t k,
+                                      abx_alloc_fn alloc, void *user, int32_t **offsets_dev, int32_t **values2_dev,
+                                      float **distances_dev, int64_t *nnz)
+{
+  if (!t || !offsets_dev || !values2_dev || !nnz)
+  {
+    setError("null argument");
+    return ABX_ERR_ARG;
+  }
+  void *vals = nullptr;
+  abx_status const st = distNearest(t, (cudaStream_t)stream, points_dev, q, k, false, distances_dev != nullptr, alloc,
+                                    user, offsets_dev, &vals, distances_dev, nnz, nullptr, nullptr, nullptr);
+  *values2_dev = (int32_t *)vals;
+  return st;
+}
+
+// host variants: predicates up, compact results down
+static abx_status copyOut(abx_alloc_fn alloc_host, void *user, int which, void const *dev, size_t bytes, cudaStream_t s,
+                          void **host_out)
+{
+  *host_out = alloc_host(user, which, bytes);
+  if (bytes == 0)
+    return ABX_OK;
+  if (!*host_out)
+  {
+    setError("output allocator returned NULL");
+    return ABX_ERR_ARG;
+  }
+  ABX_CUDA_TRY(cudaMemcpyAsync(*host_out, dev, bytes, cudaMemcpyDeviceToHost, s));
+  return ABX_OK;
+}
+
+abx_status abx_dist_query_spatial_crs_host(abx_dist_tree *t, void *stream, int pred_kind, const void *preds_host,
+                                           int64_t q, abx_alloc_fn alloc_host, void *user, int32_t **offsets_host,
+                                           uint32_t **indices_host, int64_t *nnz, int32_t **remote_pos_host,
+                                           int32_t **remote_rank_host, int64_t *n_remote)
+{
+  if (!t || !alloc_host || !offsets_host || !indices_host || !nnz || !remote_pos_host || !remote_rank_host || !n_remote ||
+      q < 0 || (q > 0 && !preds_host))
+  {
+    setError("null argument");
+    return ABX_ERR_ARG;
+  }
+  if (pred_kind != ABX_PRED_SPHERE3F && pred_kind != ABX_PRED_BOX3F && pred_kind != ABX_PRED_POINT3F)
+  {
+    setError("DistributedTree: spatial predicates are intersects(Sphere | Box | Point)");
+    return ABX_ERR_ARG;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  int const W = predWords(pred_kind);
+  TempBuffer<float> preds;
+  ABX_TRY(preds.alloc((size_t)W * (size_t)std::max<int64_t>(q, 1), s));
+  if (q > 0)
+    ABX_CUDA_TRY(cudaMemcpyAsync(preds.ptr, preds_host, sizeof(float) * W * (size_t)q, cudaMemcpyHostToDevice, s));
+  int32_t *off = nullptr;
+  void *vals = nullptr;
+  TempBuffer<int32_t> rpos, rrank;
+  abx_status st = distSpatial(t, s, pred_kind, preds.ptr, q, true, nullptr, nullptr, &off, &vals, nnz, &rpos, &rrank,
+                              n_remote);
+  if (st == ABX_OK)
+    st = copyOut(alloc_host, user, 0, off, sizeof(int32_t) * (size_t)(q + 1), s, (void **)offsets_host);
+  if (st == ABX_OK)
+    st = copyOut(alloc_host, user, 1, vals, sizeof(uint32_t) * (size_t)*nnz, s, (void **)indices_host);
+  if (st == ABX_OK)
+    st = copyOut(alloc_host, user, 3, rpos.ptr, sizeof(int32_t) * (size_t)*n_remote, s, (void **)remote_pos_host);
+  if (st == ABX_OK)
+    st = copyOut(alloc_host, user, 4, rrank.ptr, sizeof(int32_t) * (size_t)*n_remote, s, (void **)remote_rank_host);
+  if (st == ABX_OK && cudaStreamSynchronize(s) != cudaSuccess)
+  {
+    setError("result copy failed");
+    st = ABX_ERR_CUDA;
+  }
+  deviceFree(off, s);
+  deviceFree(vals, s);
+  return st;
+}
+
+abx_status abx_dist_query_nearest_crs_host(abx_dist_tree *t, void *stream, const void *points_host, int64_t q, int32_t k,
+                                           abx_alloc_fn alloc_host, void *user, int32_t **offsets_host,
+                                           uint32_t **indices_host, float **distances_host, int64_t *nnz,
+                                           int32_t **remote_pos_host, int32_t **remote_rank_host, int64_t *n_remote)
+{
+  if (!t || !alloc_host || !offsets_host || !indices_host || !nnz || !remote_pos_host || !remote_rank_host || !n_remote ||
+      q < 0 || (q > 0 && !points_host))
+  {
+    setError("null argument");
+    return ABX_ERR_ARG;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  TempBuffer<float> pts;
+  ABX_TRY(pts.alloc(3 * (size_t)std::max<int64_t>(q, 1), s));
+  if (q > 0)
+    ABX_CUDA_TRY(cudaMemcpyAsync(pts.ptr, points_host, sizeof(float) * 3 * (size_t)q, cudaMemcpyHostToDevice, s));
+  int32_t *off = nullptr;
+  void *vals = nullptr;
+  float *dist = nullptr;
+  TempBuffer<int32_t> rpos, rrank;
+  abx_status st = distNearest(t, s, pts.ptr, q, k, true, distances_host != nullptr, nullptr, nullptr, &off, &vals,
+                              distances_host ? &dist : nullptr, nnz, &rpos, &rrank, n_remote);
+  if (st == ABX_OK)
+    st = copyOut(alloc_host, user, 0, off, sizeof(int32_t) * (size_t)(q + 1), s, (void **)offsets_host);
+  if (st == ABX_OK)
+    st = copyOut(alloc_host, user, 1, vals, sizeof(uint32_t) * (size_t)*nnz, s, (void **)indices_host);
+  if (st == ABX_OK && distances_host)
+    st = copyOut(alloc_host, user, 2, dist, sizeof(float) * (size_t)*nnz, s, (void **)distances_host);
+  if (st == ABX_OK)
+    st = copyOut(alloc_host, user, 3, rpos.ptr, sizeof(int32_t) * (size_t)*n_remote, s, (void **)remote_pos_host);
+  if (st == ABX_OK)
+    st = copyOut(alloc_host, user, 4, rrank.ptr, sizeof(int32_t) * (size_t)*n_remote, s, (void **)remote_rank_host);
+  if (st == ABX_OK && cudaStreamSynchronize(s) != cudaSuccess)
+  {
+    setError("result copy failed");
+    st = ABX_ERR_CUDA;
+  }
+  deviceFree(off, s);
+  deviceFree(vals, s);
+  deviceFree(dist, s);
+  return st;
+}
+
+abx_status abx_dist_nearest_pairs(abx_bvh *bvh, void *stream, const void *points_dev, int64_t q, int32_t k, int32_t rank,
+                                  int32_t *values2_dev, float *distances_dev, int64_t *missing_out)
+{
+  ABX_TRY(ensureDevice());
+  if (!bvh || !missing_out || q < 0 || rank < 0)
+  {
+    setError("null argument");
+    return ABX_ERR_ARG;
+  }
+  *missing_out = 0;
+  if (q == 0 || k < 1)
+    return ABX_OK;
+  if (!points_dev || !values2_dev)
+  {
+    setError("null argument");
+    return ABX_ERR_ARG;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  TempBuffer<unsigned long long> missing;
+  ABX_TRY(missing.alloc(1, s));
+  ABX_CUDA_TRY(cudaMemsetAsync(missing.ptr, 0, sizeof(unsigned long long), s));
+  ABX_TRY(localKnnPairs(bvh, s, points_dev, q, k, rank, values2_dev, distances_dev, missing.ptr));
+  unsigned long long h_missing = 0;
+  ABX_CUDA_TRY(cudaMemcpyAsync(&h_missing, missing.ptr, sizeof(h_missing), cudaMemcpyDeviceToHost, s));
+  ABX_CUDA_TRY(cudaStreamSynchronize(s));
+  *missing_out = (int64_t)h_missing;
+  return ABX_OK;
+}
+
+} // extern "C"

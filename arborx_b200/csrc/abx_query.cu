@@ -19,7 +19,6 @@
 #define ABX_SPATIAL_MINB 1
 #endif
 
-#include <cstdlib>
 
 namespace abx
 {
@@ -35,6 +34,7 @@ enum
   MODE_COMPACT = 3  // staged results -> CRS rows; re-traverses only the queries that overflowed
 };
 constexpr int kPredicateSortBits = 24;
+constexpr int kWideDefault = 0; // 0: Node64 walk; 1: Wide64 walk in the spatial kernels; 2: also in the kNN kernel
 constexpr int kSpatialVariantDefault = 1; // r01: immediate 5.85 ms; deferred (4,12) 4.89, (4,16) 4.99, (4,8) 4.93, (2,16) 5.75
 // Staging buffer of the single-traversal CRS path: one 128-byte row of kStage slots per query,
 // indexed by the ORIGINAL query id.  CRS rows are in original query order while the traversal
@@ -288,7 +288,17 @@ __global__ void __launch_bounds__(kThreads, (K > 0 && K <= 16) ? ABX_NEAREST_MIN
     float const d2 = TRI ? pointTriangleDist2(px, py, pz, __ldg(leaf_tri), __ldg(leaf_tri + 1), __ldg(leaf_tri + 2))
                          : pointBoxDist2v(px, py, pz, lo, hi);
     if (pair_rank >= 0)
+    {
       reinterpret_cast<int2 *>(indices)[base] = make_int2(0, pair_rank);
+      for (int i = 1; i < row_stride; ++i) // DistributedTree rows are padded to k entries
+      {
+        reinterpret_cast<int2 *>(indices)[base + i] = make_int2(-1, -1);
+        if (distances)
+          distances[base + i] = __int_as_float(0x7f800000);
+      }
+      if (missing && row_stride > 1)
+        atomicAdd(missing, (unsigned long long)(row_stride - 1));
+    }
     else
       indices[base] = 0u;
     if (distances)
@@ -596,11 +606,20 @@ __global__ void __launch_bounds__(kThreads, (K > 0 && K <= 16) ? ABX_NEAREST_MIN
   }
   if (counts)
     counts[qi] = found;
-  if (missing)
+  int const expected = offsets ? (offsets[qi + 1] - (int)base) : row_stride;
+  if (found < expected)
   {
-    int const expected = offsets ? (offsets[qi + 1] - (int)base) : row_stride;
-    if (found < expected)
+    if (missing)
       atomicAdd(missing, (unsigned long long)(expected - found));
+    if (pair_rank >= 0)
+      // DistributedTree rows: pad to the full row (index -1, distance +inf) so that candidates from
+      // other ranks can be merged in place
+      for (int i = found; i < expected; ++i)
+      {
+        reinterpret_cast<int2 *>(indices)[base + i] = make_int2(-1, -1);
+        if (distances)
+          distances[base + i] = __int_as_float(0x7f800000);
+      }
   }
 }
 
@@ -726,15 +745,9 @@ abx_status spatialLaunch(cudaStream_t s, abx_bvh *t, int pred_kind, void const *
     return ABX_OK;
   }
   // tuning aid: ABX_SPATIAL_VARIANT picks (leaf-run size, deferred-queue slots); 0 slots = immediate leaf tests
-  static int const variant = [] {
-    char const *e = getenv("ABX_SPATIAL_VARIANT");
-    return e ? atoi(e) : kSpatialVariantDefault;
-  }();
-  // experimental 4-wide nodes: ABX_WIDE=1 (built on the tree's first query; n < 2^29 for the run encoding)
-  static int const use_wide = [] {
-    char const *e = getenv("ABX_WIDE");
-    return e ? atoi(e) : 0;
-  }();
+  int const variant = ABX_TUNE_INT("ABX_SPATIAL_VARIANT", kSpatialVariantDefault);
+  // 4-wide nodes (n < 2^29 for the run encoding)
+  int const use_wide = ABX_TUNE_INT("ABX_WIDE", kWideDefault);
   bool wide = use_wide && n > 64 && n < (1 << 29);
   if (wide)
   {
@@ -750,6 +763,21 @@ abx_status spatialLaunch(cudaStream_t s, abx_bvh *t, int pred_kind, void const *
   ABX_DISPATCH_PRED(pred_kind, ABX_LAUNCH_TAGGED(tag, (spatialKernel<P, MODE, LF4, TRIFLAG, B, QC>), grid, kThreads,  \
                                                  0, s, t->nodes, t->leaf_box, t->leaf_tri, n, (float const *)preds,   \
                                                  q, qperm, limit, counts, offsets, indices, staging))
+#ifdef ABX_TUNING
+#define ABX_SPATIAL_VARIANTS(LF4, TRIFLAG)                                                                            \
+  switch (variant)                                                                                                     \
+  {                                                                                                                    \
+  case 1: ABX_SPATIAL_B(LF4, TRIFLAG, 4, 12); break;                                                                   \
+  case 2: ABX_SPATIAL_B(LF4, TRIFLAG, 4, 16); break;                                                                   \
+  case 3: ABX_SPATIAL_B(LF4, TRIFLAG, 2, 16); break;                                                                   \
+  case 4: ABX_SPATIAL_B(LF4, TRIFLAG, 4, 8); break;                                                                    \
+  default: ABX_SPATIAL_B(LF4, TRIFLAG, 4, 0); break;                                                                   \
+  }
+#else
+#define ABX_SPATIAL_VARIANTS(LF4, TRIFLAG)                                                                            \
+  (void)variant;                                                                                                       \
+  ABX_SPATIAL_B(LF4, TRIFLAG, 4, 12)
+#endif
 #define ABX_SPATIAL(LF4, TRIFLAG)                                                                                     \
   do                                                                                                                   \
   {                                                                                                                    \
@@ -758,14 +786,7 @@ abx_status spatialLaunch(cudaStream_t s, abx_bvh *t, int pred_kind, void const *
       ABX_SPATIAL_W(LF4, TRIFLAG);                                                                                     \
       break;                                                                                                           \
     }                                                                                                                  \
-    switch (variant)                                                                                                   \
-    {                                                                                                                  \
-    case 1: ABX_SPATIAL_B(LF4, TRIFLAG, 4, 12); break;                                                                 \
-    case 2: ABX_SPATIAL_B(LF4, TRIFLAG, 4, 16); break;                                                                 \
-    case 3: ABX_SPATIAL_B(LF4, TRIFLAG, 2, 16); break;                                                                 \
-    case 4: ABX_SPATIAL_B(LF4, TRIFLAG, 4, 8); break;                                                                  \
-    default: ABX_SPATIAL_B(LF4, TRIFLAG, 4, 0); break;                                                                 \
-    }                                                                                                                  \
+    ABX_SPATIAL_VARIANTS(LF4, TRIFLAG);                                                                                \
   } while (0)
   if (t->kind == ABX_PRIM_TRI3F)
   {
@@ -780,6 +801,7 @@ abx_status spatialLaunch(cudaStream_t s, abx_bvh *t, int pred_kind, void const *
     ABX_SPATIAL(1, false);
   }
 #undef ABX_SPATIAL
+#undef ABX_SPATIAL_VARIANTS
 #undef ABX_SPATIAL_B
 #undef ABX_SPATIAL_W
   return ABX_OK;
@@ -795,10 +817,7 @@ abx_status predicatePermutation(cudaStream_t s, abx_bvh *t, int pred_kind, void 
   // results do not depend on it.  Morton32 codes use 30 bits; ordering by the top
   // kPredicateSortBits of them (ABX_QUERY_SORT_BITS overrides) costs one digit pass less than the
   // reference's full sort and leaves cells far smaller than a warp's worth of queries unordered.
-  static int const sort_bits = [] {
-    char const *e = getenv("ABX_QUERY_SORT_BITS");
-    return e ? atoi(e) : kPredicateSortBits;
-  }();
+  int const sort_bits = ABX_TUNE_INT("ABX_QUERY_SORT_BITS", kPredicateSortBits);
   TempBuffer<uint32_t> codes, codes_alt, perm_alt;
   ABX_TRY(codes.alloc(q, s));
   ABX_TRY(codes_alt.alloc(q, s));
@@ -858,12 +877,10 @@ abx_status nearestQuery(cudaStream_t s, abx_bvh *t, float const *pts, int64_t q,
   int const grid = divUp(q, kThreads);
   bool const tri = t->kind == ABX_PRIM_TRI3F;
   int const kmax = k_per_query ? INT_MAX : k; // per-query k: general path
-  int const row_stride = std::max(0, std::min(k, n));
+  // DistributedTree rows (pair_rank >= 0) always have k slots: short rows are padded
+  int const row_stride = pair_rank >= 0 ? std::max(0, k) : std::max(0, std::min(k, n));
   // experimental 4-wide nodes for the kNN walk: ABX_WIDE=2 (parity tests pass, not yet timed)
-  static int const use_wide = [] {
-    char const *e = getenv("ABX_WIDE");
-    return e ? atoi(e) : 0;
-  }();
+  int const use_wide = ABX_TUNE_INT("ABX_WIDE", kWideDefault);
   bool wide = use_wide >= 2 && n > 64 && n < (1 << 29);
   if (wide)
   {
@@ -1105,17 +1122,17 @@ __global__ void pairWithRankKernel(int32_t const *__restrict__ indices, int64_t 
 // candidates of one query are contiguous (ids ascending): the thread at the start of a segment merges
 // the segment into the query's row by insertion (k and the segment are tens of entries; a few percent
 // of the queries have any)
-__global__ void knnMergeKernel(int64_t m, long long const *__restrict__ ids, int2 const *__restrict__ cand,
+__global__ void knnMergeKernel(int64_t m, int const *__restrict__ ids, int2 const *__restrict__ cand,
                                float const *__restrict__ cand_d, int k, int2 *vals, float *dists)
 {
   int64_t const c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= m)
     return;
-  long long const qid = ids[c];
+  int const qid = ids[c];
   if (c > 0 && ids[c - 1] == qid)
     return;
-  int2 *row_v = vals + qid * k;
-  float *row_d = dists + qid * k;
+  int2 *row_v = vals + (int64_t)qid * k;
+  float *row_d = dists + (int64_t)qid * k;
   for (int64_t e = c; e < m && ids[e] == qid; ++e)
   {
     float const d = cand_d[e];
@@ -1134,11 +1151,11 @@ __global__ void knnMergeKernel(int64_t m, long long const *__restrict__ ids, int
   }
 }
 
-abx_status knnMerge(cudaStream_t s, int64_t m, int64_t const *ids, int32_t const *cand2, float const *cand_d, int k,
+abx_status knnMerge(cudaStream_t s, int64_t m, int32_t const *ids, int32_t const *cand2, float const *cand_d, int k,
                     int32_t *vals2, float *dists)
 {
   if (m > 0 && k > 0)
-    ABX_LAUNCH(knnMergeKernel, divUp(m, 128), 128, 0, s, m, (long long const *)ids, (int2 const *)cand2, cand_d, k,
+    ABX_LAUNCH(knnMergeKernel, divUp(m, 128), 128, 0, s, m, ids, (int2 const *)cand2, cand_d, k,
                (int2 *)vals2, dists);
   return ABX_OK;
 }
@@ -1172,12 +1189,12 @@ __global__ void mergeLocalCountsKernel(int64_t q, int32_t const *__restrict__ lo
     counts[i] = local_off[i + 1] - local_off[i];
 }
 // the thread at the start of a query's segment adds the segment length (one writer per query)
-__global__ void mergeRemoteCountsKernel(int64_t m, long long const *__restrict__ ids, int32_t *__restrict__ counts)
+__global__ void mergeRemoteCountsKernel(int64_t m, int const *__restrict__ ids, int32_t *__restrict__ counts)
 {
   int64_t const c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= m)
     return;
-  long long const qid = ids[c];
+  int const qid = ids[c];
   if (c > 0 && ids[c - 1] == qid)
     return;
   int len = 1;
@@ -1218,14 +1235,14 @@ __global__ void __launch_bounds__(256)
       out_vals[j + sh] = make_int2(local_idx[j], rank);
   }
 }
-__global__ void mergeRemoteRowsKernel(int64_t m, long long const *__restrict__ ids, int2 const *__restrict__ vals,
+__global__ void mergeRemoteRowsKernel(int64_t m, int const *__restrict__ ids, int2 const *__restrict__ vals,
                                       int32_t const *__restrict__ local_off, int32_t const *__restrict__ out_off,
                                       int2 *__restrict__ out_vals)
 {
   int64_t const c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= m)
     return;
-  long long const qid = ids[c];
+  int const qid = ids[c];
   if (c > 0 && ids[c - 1] == qid)
     return;
   int dst = out_off[qid] + (local_off[qid + 1] - local_off[qid]);
@@ -1233,23 +1250,32 @@ __global__ void mergeRemoteRowsKernel(int64_t m, long long const *__restrict__ i
     out_vals[dst++] = vals[e];
 }
 
-abx_status mergeSorted(cudaStream_t s, int64_t q, int32_t const *local_off, int32_t const *local_idx, int rank,
-                       int64_t m, int64_t const *remote_ids, int32_t const *remote_vals2, int32_t *out_off,
-                       int32_t *out_vals2)
+// out_off[q + 1] = offsets of the merged rows (local row lengths + records per query id)
+abx_status mergeCounts(cudaStream_t s, int64_t q, int32_t const *local_off, int64_t m, int32_t const *remote_ids,
+                       int32_t *out_off)
 {
   if (q < 0)
     return ABX_OK;
   if (q > 0)
     ABX_LAUNCH(mergeLocalCountsKernel, divUp(q, 256), 256, 0, s, q, local_off, out_off);
   if (m > 0)
-    ABX_LAUNCH(mergeRemoteCountsKernel, divUp(m, 256), 256, 0, s, m, (long long const *)remote_ids, out_off);
-  ABX_TRY(exclusiveScanI32(s, out_off, out_off, q + 1));
+    ABX_LAUNCH(mergeRemoteCountsKernel, divUp(m, 256), 256, 0, s, m, remote_ids, out_off);
+  return exclusiveScanI32(s, out_off, out_off, q + 1);
+}
+
+abx_status mergeSorted(cudaStream_t s, int64_t q, int32_t const *local_off, int32_t const *local_idx, int rank,
+                       int64_t m, int32_t const *remote_ids, int32_t const *remote_vals2, int32_t *out_off,
+                       int32_t *out_vals2)
+{
+  if (q < 0)
+    return ABX_OK;
+  ABX_TRY(mergeCounts(s, q, local_off, m, remote_ids, out_off));
   if (q > 0)
     ABX_LAUNCH(mergeLocalRowsKernel, divUp(divUp(q, 32) * 32, 256), 256, 0, s, q, local_off, local_idx, rank, out_off,
                (int2 *)out_vals2);
   if (m > 0)
-    ABX_LAUNCH(mergeRemoteRowsKernel, divUp(m, 256), 256, 0, s, m, (long long const *)remote_ids,
-               (int2 const *)remote_vals2, local_off, out_off, (int2 *)out_vals2);
+    ABX_LAUNCH(mergeRemoteRowsKernel, divUp(m, 256), 256, 0, s, m, remote_ids, (int2 const *)remote_vals2, local_off,
+               out_off, (int2 *)out_vals2);
   return ABX_OK;
 }
 

@@ -415,12 +415,12 @@ abx_status launchPasses(cudaStream_t s, int passes, SortShifts const &shifts, Ke
   constexpr int BINS = 1 << BITS;
   auto kernel = onesweepPassKernel<KeyT, BITS, THREADS, ITEMS, MINB, BALLOT, DEBUG>;
   size_t const smem = sizeof(PassSmem<KeyT, BITS, THREADS, ITEMS>);
-  static bool attr_set = false;
-  if (!attr_set)
+  static PerDeviceOnce attr; // function attributes are per device
+  if (attr.needed())
   {
     ABX_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ABX_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    attr_set = true;
+    attr.done();
   }
   for (int p = 0; p < passes; ++p)
   {
@@ -435,10 +435,7 @@ abx_status launchPasses(cudaStream_t s, int passes, SortShifts const &shifts, Ke
 
 inline int sortConfig(bool wide)
 {
-  static int const config = [] {
-    char const *e = getenv("ABX_SORT_CONFIG");
-    return e ? atoi(e) : -1;
-  }();
+  int const config = ABX_TUNE_INT("ABX_SORT_CONFIG", -1);
   return config >= 0 ? config : (wide ? kDefaultConfig64 : kDefaultConfig32);
 }
 
@@ -488,6 +485,9 @@ abx_status runPasses(cudaStream_t s, KeyT *const keys[2], unsigned *const vals[2
 #define ABX_PASSES(T, I, M, B, D)                                                                                     \
   return launchPasses<KeyT, BITS, T, I, M, B, D>(s, passes, shifts, keys, vals, cur, n, iota_vals, hist, counters,    \
                                                  states, tiles)
+#ifdef ABX_TUNING
+  // alternative tile shapes and the phase-removal variants (DEBUG != 0: wrong results on purpose,
+  // scripts/tune_sort.py) exist in the tuning build only
   switch (cfg)
   {
   case 1: ABX_PASSES(256, 8, 5, false, 0);
@@ -505,6 +505,10 @@ abx_status runPasses(cudaStream_t s, KeyT *const keys[2], unsigned *const vals[2
   case 13: ABX_PASSES(384, 12, 2, true, 4);
   default: ABX_PASSES(256, 16, 2, false, 0);
   }
+#else
+  static_assert(kDefaultConfig64 == 7 && kDefaultConfig32 == 7, "release build compiles configuration 7 only");
+  ABX_PASSES(384, 12, 2, true, 0);
+#endif
 #undef ABX_PASSES
 }
 
@@ -691,10 +695,7 @@ abx_status sortPairsDB(cudaStream_t s, KeyT *const keys[2], unsigned *const vals
   int top = 1;
   while (top < full && ((int64_t)1 << (8 * top)) < n / 8)
     ++top;
-  static int const fix_mode = [] {
-    char const *e = getenv("ABX_SORT_FIXUP");
-    return e ? atoi(e) : 1;
-  }();
+  int const fix_mode = ABX_TUNE_INT("ABX_SORT_FIXUP", 1);
   TempBuffer<unsigned> flag;
   if (fixup && fix_mode && top + 1 < full && n >= 2 * kSampleKeys)
   {
@@ -773,7 +774,8 @@ constexpr int kScanItems = 8;
 constexpr int kScanTile = kScanThreads * kScanItems;
 
 __global__ void __launch_bounds__(kScanThreads)
-    scanTileSumsKernel(int32_t const *__restrict__ in, int64_t n, int32_t *__restrict__ tile_sums)
+    scanTileSumsKernel(int32_t const *__restrict__ in, int64_t n, int32_t *__restrict__ tile_sums,
+                       unsigned long long *__restrict__ total64 /* may be null; zeroed */)
 {
   __shared__ int warp_sums[kScanThreads / 32];
   int64_t const base = (int64_t)blockIdx.x * kScanTile;
@@ -797,6 +799,9 @@ __global__ void __launch_bounds__(kScanThreads)
     for (int w = 0; w < kScanThreads / 32; ++w)
       t += warp_sums[w];
     tile_sums[blockIdx.x] = t;
+    // 64-bit total of the (non-negative) inputs: a tile of 2048 counts below 2^20 each cannot wrap
+    if (total64 && t)
+      atomicAdd(total64, (unsigned long long)(unsigned)t);
   }
 }
 
@@ -884,9 +889,10 @@ abx_status sortPairsU64(cudaStream_t s, uint64_t *keys, uint32_t *vals, int64_t 
 {
   return sortPairsInPlace<unsigned long long>(s, (unsigned long long *)keys, vals, n, iota_vals, key_bits, fixup);
 }
-abx_status sortPairsU32(cudaStream_t s, uint32_t *keys, uint32_t *vals, int64_t n, bool iota_vals, int key_bits)
+abx_status sortPairsU32(cudaStream_t s, uint32_t *keys, uint32_t *vals, int64_t n, bool iota_vals, int key_bits,
+                        bool fixup)
 {
-  return sortPairsInPlace<unsigned>(s, keys, vals, n, iota_vals, key_bits, true);
+  return sortPairsInPlace<unsigned>(s, keys, vals, n, iota_vals, key_bits, fixup);
 }
 abx_status sortPairsU64DB(cudaStream_t s, uint64_t *const keys[2], uint32_t *const vals[2], int *cur, int64_t n,
                           bool iota_vals, int key_bits)
@@ -901,15 +907,19 @@ abx_status sortPairsU32DB(cudaStream_t s, uint32_t *const keys[2], uint32_t *con
 }
 
 // out has n_plus_1 entries: out[i] = in[0] + ... + in[i-1]; in[n_plus_1-1] is ignored.
-abx_status exclusiveScanI32(cudaStream_t s, int32_t const *in, int32_t *out, int64_t n_plus_1)
+// total64 (optional, device): receives the sum of the inputs accumulated in 64 bits.
+abx_status exclusiveScanI32(cudaStream_t s, int32_t const *in, int32_t *out, int64_t n_plus_1,
+                            unsigned long long *total64)
 {
+  if (total64)
+    ABX_CUDA_TRY(cudaMemsetAsync(total64, 0, sizeof(unsigned long long), s));
   if (n_plus_1 <= 0)
     return ABX_OK;
   int64_t const n_in = n_plus_1 - 1;
   int const tiles = divUp(n_plus_1, kScanTile);
   TempBuffer<int32_t> tile_sums;
   ABX_TRY(tile_sums.alloc(tiles, s));
-  ABX_LAUNCH(scanTileSumsKernel, tiles, kScanThreads, 0, s, in, n_in, tile_sums.ptr);
+  ABX_LAUNCH(scanTileSumsKernel, tiles, kScanThreads, 0, s, in, n_in, tile_sums.ptr, total64);
   ABX_LAUNCH(scanTileOffsetsKernel, 1, kScanOffsetThreads, 0, s, tile_sums.ptr, tiles);
   bool const aligned16 = ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0);
   ABX_LAUNCH(scanApplyKernel, tiles, kScanThreads, 0, s, in, out, n_in, n_plus_1, tile_sums.ptr, aligned16);

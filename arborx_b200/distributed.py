@@ -1,53 +1,192 @@
-"""DistributedTree -- host-side mirror of ArborX::DistributedTree for one process per GPU.
+"""DistributedTree -- Python binding of ArborX::DistributedTree for one process (or host thread) per GPU.
 
-Reference: distributed/ArborX_DistributedTree.hpp:33-252 (ctor: bottom tree, all-gather of rank
-boxes, replicated top tree, all-gather of sizes), detail/ArborX_DistributedTreeSpatial.hpp:31-60,
-detail/ArborX_DistributedTreeNearest.hpp:41-218 (two-phase kNN), detail/ArborX_DistributedTreeUtils.hpp
-(forwardQueries :52-115, communicateResultsBack :153-224, countResults/sort :229-263, filterResults
-:267-342).  The reference exchanges with MPI point-to-point, three messages each way
-(detail/ArborX_Distributor.hpp:276-440); here every exchange is ONE all-to-all-v of packed 32-bit
-records over torch.distributed (NCCL over NVLink on the GPUs; gloo in the CPU protocol tests), preceded
-by an all-to-all of the R counts.
+The product path is C++ (arborx_b200/csrc/abx_dist.cu behind include/abx.h: abx_comm_*, abx_dist_create,
+abx_dist_query_spatial_crs, abx_dist_query_nearest_crs and their *_host forms): bottom tree, all-gather of the
+rank boxes, routing kernel, two grouped NCCL exchanges and the merge kernels, two blocking points per query.
+`DistributedTree(comm, space, values)` binds it; `comm` is a torch.distributed process group (a NCCL
+communicator for the library is bootstrapped over it once and cached) or a `Communicator`.
 
-The tree work (top-tree queries, bottom-tree queries, kNN) runs in the hand-written CUDA kernels behind
-the C ABI; the packing between exchanges is a handful of torch tensor ops (bucket by destination, gather,
-segmented sort by query id) -- plumbing around the hot path.  The local engine is injectable so that the
-exchange protocol can be exercised on CPU with gloo (tests/ plug the oracle in; the product default is the
-CUDA engine and fails without a GPU).
+Reference: distributed/ArborX_DistributedTree.hpp:33-252, detail/ArborX_DistributedTreeSpatial.hpp:31-60,
+detail/ArborX_DistributedTreeNearest.hpp:41-218, detail/ArborX_DistributedTreeUtils.hpp:52-342,
+detail/ArborX_Distributor.hpp:276-440.
+
+`ProtocolModelTree` is the reference-shaped exchange (every query forwarded through the top tree, two-phase
+kNN) written with torch tensor ops over torch.distributed; its local engine is injectable, so the CPU tests run it
+with gloo and the oracle as the engine (world sizes 1-3).  It is a model of the protocol for those tests, not
+the product path; `DistributedTree(..., engine=...)` selects it.
 
 Values returned by queries are (index, rank) pairs (int32 [nnz, 2]): the reference returns user values or
 `{index, rank}` from a callback (examples/distributed_tree/distributed_knn.cpp:62-104).
 """
-import os
-import time
+import ctypes as C
 
 import torch
 import torch.distributed as dist
 
-_DEBUG = bool(os.environ.get("ABX_DIST_DEBUG"))
-_marks = []
-
-
-def _mark(name):
-    """ABX_DIST_DEBUG=1: host-synchronised section timer (diagnostics only)."""
-    if _DEBUG:
-        torch.cuda.synchronize()
-        _marks.append((name, time.perf_counter()))
-
-
-def _report(tag):
-    if _DEBUG and _marks and dist.get_rank() == 0:
-        t0 = _marks[0][1]
-        print(tag + ": " + "  ".join("%s=%.2f" % (n, (t - t0) * 1e3) for n, t in _marks[1:]), flush=True)
-    _marks.clear()
-
-
 POINT, BOX, TRIANGLE = 0, 1, 2
 SPHERE_PRED, BOX_PRED, POINT_PRED = 0, 1, 2
+_PRIM_STRIDE = {POINT: 3, BOX: 6, TRIANGLE: 9}
 
 
+# ------------------------------------------------------------------------- product path ----
+class Communicator:
+    """abx_comm: the communicator the C++ DistributedTree exchanges over (NCCL, or an in-process group of
+    host threads sharing one GPU for single-GPU tests)."""
+    _by_group = {}
+
+    def __init__(self, handle):
+        self._h = handle
+
+    @property
+    def rank(self):
+        from . import _lib
+        return _lib.lib().abx_comm_rank(self._h)
+
+    @property
+    def size(self):
+        from . import _lib
+        return _lib.lib().abx_comm_size(self._h)
+
+    @classmethod
+    def from_process_group(cls, group=None):
+        """NCCL communicator over the ranks of a torch.distributed group (collective on first use, cached):
+        rank 0 creates the unique id, the group broadcasts it, every rank joins."""
+        from . import _lib
+        key = id(group) if group is not None else 0
+        comm = cls._by_group.get(key)
+        if comm is not None:
+            return comm
+        L = _lib.lib()
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        box = [None]
+        if rank == 0:
+            buf = C.create_string_buffer(128)
+            _lib.check(L.abx_comm_unique_id(buf))
+            box[0] = buf.raw
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        h = C.c_void_p()
+        _lib.check(L.abx_comm_init_rank(box[0], world, rank, C.byref(h)))
+        comm = cls(h)
+        cls._by_group[key] = comm
+        return comm
+
+    @classmethod
+    def local_group(cls, n):
+        """n communicators of one in-process group (rank r must be driven by its own host thread)."""
+        from . import _lib
+        arr = (C.c_void_p * n)()
+        _lib.check(_lib.lib().abx_comm_create_local(n, arr))
+        return [cls(C.c_void_p(arr[r])) for r in range(n)]
+
+
+class DistributedTree:
+    """ArborX::DistributedTree(comm, space, values) (distributed/ArborX_DistributedTree.hpp:129-151).
+    Construction and queries are collective over `comm`."""
+
+    def __new__(cls, comm, space, values, kind=None, engine=None):
+        if engine is not None:  # protocol model with an injected local engine (CPU tests)
+            return ProtocolModelTree(comm, space, values, kind, engine)
+        return super().__new__(cls)
+
+    def __init__(self, comm, space, values, kind=None, engine=None):
+        from . import _lib
+        if not isinstance(comm, Communicator):
+            comm = Communicator.from_process_group(comm)
+        self.comm, self.space = comm, space
+        self.rank, self.world = comm.rank, comm.size
+        if not isinstance(values, torch.Tensor):
+            values = torch.as_tensor(values, dtype=torch.float32)
+        if kind is None:
+            kind = {3: POINT, 6: BOX, 9: TRIANGLE}[values.shape[-1]]
+        self.kind = kind
+        v = values.to(torch.float32).reshape(-1, _PRIM_STRIDE[kind]).contiguous()
+        h = C.c_void_p()
+        L = _lib.lib()
+        with torch.cuda.stream(space.stream):
+            fn = L.abx_dist_create if v.is_cuda else L.abx_dist_create_host
+            _lib.check(fn(comm._h, space.handle, kind, C.c_void_p(v.data_ptr()), v.shape[0], C.byref(h)))
+        self._values = v
+        self._h = h
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                from . import _lib
+                _lib.lib().abx_dist_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def size(self):
+        from . import _lib
+        return _lib.lib().abx_dist_size(self._h)
+
+    def empty(self):
+        from . import _lib
+        return bool(_lib.lib().abx_dist_empty(self._h))
+
+    def bounds(self):
+        from . import _lib
+        out = (C.c_float * 6)()
+        _lib.check(_lib.lib().abx_dist_bounds(self._h, out))
+        return torch.tensor(list(out), dtype=torch.float32)
+
+    def query(self, space, predicates, return_distances=False, out=None):
+        """Collective.  Device predicates -> (values int32 [nnz, 2] = (index, rank), offsets int32 [q + 1]
+        [, distances]) on the device.  Host (CPU tensor) predicates run the host-buffer entry points and
+        return the compact form in pinned host memory: (indices int32 [nnz], offsets[, distances], remote_pos,
+        remote_rank) -- every index belongs to this rank except indices[remote_pos[j]], owned by
+        remote_rank[j].  `out`: HostBufferPool to reuse for the host results."""
+        from . import _Allocator, _lib
+        L = _lib.lib()
+        d = predicates.data
+        q = d.shape[0]
+        host = not d.is_cuda
+        alloc = _Allocator(space.device, pinned_host=host, pool=out if host else None)
+        off, vals, dist_p, rpos, rrank = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        nnz, nrem = C.c_int64(), C.c_int64()
+        nearest = predicates.tag == "nearest"
+        want_d = C.byref(dist_p) if (return_distances and nearest) else None
+        with torch.cuda.stream(space.stream):
+            if host and nearest:
+                _lib.check(L.abx_dist_query_nearest_crs_host(self._h, space.handle, C.c_void_p(d.data_ptr()), q,
+                                                             int(predicates.k), alloc.fn, None, C.byref(off),
+                                                             C.byref(vals), want_d, C.byref(nnz), C.byref(rpos),
+                                                             C.byref(rrank), C.byref(nrem)))
+            elif host:
+                _lib.check(L.abx_dist_query_spatial_crs_host(self._h, space.handle, predicates.kind,
+                                                             C.c_void_p(d.data_ptr()), q, alloc.fn, None, C.byref(off),
+                                                             C.byref(vals), C.byref(nnz), C.byref(rpos), C.byref(rrank),
+                                                             C.byref(nrem)))
+            elif nearest:
+                _lib.check(L.abx_dist_query_nearest_crs(self._h, space.handle, C.c_void_p(d.data_ptr()), q,
+                                                        int(predicates.k), alloc.fn, None, C.byref(off), C.byref(vals),
+                                                        want_d, C.byref(nnz)))
+            else:
+                _lib.check(L.abx_dist_query_spatial_crs(self._h, space.handle, predicates.kind,
+                                                        C.c_void_p(d.data_ptr()), q, alloc.fn, None, C.byref(off),
+                                                        C.byref(vals), C.byref(nnz)))
+        res = alloc.out
+        alloc.out, alloc.fn = {}, None
+        dev = "cpu" if host else space.device
+        empty_i = lambda: torch.empty(0, dtype=torch.int32, device=dev)
+        offsets = res[0]
+        values = res.get(1, empty_i())
+        if not host:
+            values = values.view(-1, 2)
+        outp = (values, offsets)
+        if return_distances:
+            outp += (res.get(2, torch.empty(0, dtype=torch.float32, device=dev)),)
+        if host:
+            outp += (res.get(3, empty_i()), res.get(4, empty_i()))
+        return outp
+
+
+# ------------------------------------------------------- local engine + tensor helpers ----
 class CudaEngine:
-    """Local trees on this rank's GPU through libabx.so."""
+    """Local trees on this rank's GPU through libabx.so (used by the distributed DBSCAN driver and, with the
+    protocol model, by scripts that cross-check it against the C++ path)."""
 
     def __init__(self, space):
         import arborx_b200 as abx
@@ -74,16 +213,15 @@ class CudaEngine:
     def route(self, kind, data, rank_boxes, rank, radius=None, radius_stride=1):
         """-> (query ids grouped by destination rank [F] int64, send_counts list[R]); self is never a destination.
         radius (optional, spheres): data holds points and predicate i has radius radius.view(-1)[i * radius_stride]."""
-        import ctypes as C
         from . import _lib
         L = _lib.lib()
         dev = data.device
         R = rank_boxes.shape[0]
         q = data.shape[0]
-        boxes = rank_boxes.to(device=dev, dtype=torch.float32).contiguous()
-        counts = torch.empty(R, dtype=torch.int32, device=dev)
-        d = data.contiguous()
         with torch.cuda.stream(self.space.stream):
+            boxes = rank_boxes.to(device=dev, dtype=torch.float32).contiguous()
+            counts = torch.empty(R, dtype=torch.int32, device=dev)
+            d = data.contiguous()
             rp = C.c_void_p(radius.data_ptr()) if radius is not None else None
             _lib.check(L.abx_dist_route_count(self.space.handle, kind, C.c_void_p(d.data_ptr()), q, rp, radius_stride,
                                               C.c_void_p(boxes.data_ptr()), R, int(rank), C.c_void_p(counts.data_ptr())))
@@ -96,92 +234,7 @@ class CudaEngine:
                 _lib.check(L.abx_dist_route_fill(self.space.handle, kind, C.c_void_p(d.data_ptr()), q, rp, radius_stride,
                                                  C.c_void_p(boxes.data_ptr()), R, int(rank), C.c_void_p(base.data_ptr()),
                                                  C.c_void_p(cursors.data_ptr()), C.c_void_p(qids.data_ptr())))
-        return qids.long(), send_counts
-
-    def pair_with_rank(self, idx, rank):
-        import ctypes as C
-        from . import _lib
-        i32 = idx.to(torch.int32).contiguous()
-        out = torch.empty((i32.shape[0], 2), dtype=torch.int32, device=i32.device)
-        with torch.cuda.stream(self.space.stream):
-            _lib.check(_lib.lib().abx_dist_pair_with_rank(self.space.handle, C.c_void_p(i32.data_ptr()), i32.shape[0],
-                                                          int(rank), C.c_void_p(out.data_ptr())))
-        return out
-
-    def nearest_pairs(self, tree, pts, k, rank):
-        """k nearest of every point as (index, rank) pairs [q * row, 2] + distances [q * row], row = min(k, size);
-        None when some row could not be filled (the caller takes the general path)."""
-        import ctypes as C
-        from . import _lib
-        q = pts.shape[0]
-        row = max(0, min(int(k), tree.size()))
-        dev = pts.device
-        vals = torch.empty((q * row, 2), dtype=torch.int32, device=dev)
-        d = torch.empty(q * row, dtype=torch.float32, device=dev)
-        missing = C.c_int64(0)
-        p = pts.contiguous()
-        with torch.cuda.stream(self.space.stream):
-            _lib.check(_lib.lib().abx_dist_nearest_pairs(tree._h, self.space.handle, C.c_void_p(p.data_ptr()), q, int(k),
-                                                         int(rank), C.c_void_p(vals.data_ptr()),
-                                                         C.c_void_p(d.data_ptr()), C.byref(missing)))
-        if missing.value:
-            return None
-        return vals, d
-
-    def knn_merge(self, ids, cand_vals, cand_d, k, vals, dists):
-        """Merge remote candidates (ids ascending) into the k-entry rows of their queries, in place."""
-        import ctypes as C
-        from . import _lib
-        i64 = ids.to(torch.int64).contiguous()
-        cv = cand_vals.to(torch.int32).contiguous()
-        cd = cand_d.to(torch.float32).contiguous()
-        with torch.cuda.stream(self.space.stream):
-            _lib.check(_lib.lib().abx_dist_knn_merge(self.space.handle, i64.shape[0], C.c_void_p(i64.data_ptr()),
-                                                     C.c_void_p(cv.data_ptr()), C.c_void_p(cd.data_ptr()), int(k),
-                                                     C.c_void_p(vals.data_ptr()), C.c_void_p(dists.data_ptr())))
-
-    def merge_sorted(self, local_off, local_idx, rank, remote_ids, remote_vals):
-        """Local CRS (index only) + remote records (query id ascending, (index, rank)) -> merged
-        (values [nnz, 2], offsets [q + 1]) (abx_dist_merge_sorted)."""
-        import ctypes as C
-        from . import _lib
-        q = local_off.shape[0] - 1
-        dev = local_off.device
-        m = int(remote_ids.shape[0])
-        nnz = int(local_idx.shape[0]) + m
-        out_off = torch.empty(q + 1, dtype=torch.int32, device=dev)
-        out_vals = torch.empty((nnz, 2), dtype=torch.int32, device=dev)
-        lo = local_off.to(torch.int32).contiguous()
-        li = local_idx.to(torch.int32).contiguous()
-        ri = remote_ids.to(torch.int64).contiguous()
-        rv = remote_vals.to(torch.int32).contiguous()
-        with torch.cuda.stream(self.space.stream):
-            _lib.check(_lib.lib().abx_dist_merge_sorted(self.space.handle, q, C.c_void_p(lo.data_ptr()),
-                                                        C.c_void_p(li.data_ptr()), int(rank), m,
-                                                        C.c_void_p(ri.data_ptr()), C.c_void_p(rv.data_ptr()),
-                                                        C.c_void_p(out_off.data_ptr()), C.c_void_p(out_vals.data_ptr())))
-        return out_vals, out_off
-
-    def merge_rows(self, local_off, local_idx, rank, remote_off, remote_vals):
-        """CRS rows of local results (index only) + CRS rows of remote results ((index, rank) pairs)
-        -> merged (values [nnz, 2], offsets [q + 1]); one kernel pass (abx_dist_merge_crs)."""
-        import ctypes as C
-        from . import _lib
-        q = local_off.shape[0] - 1
-        dev = local_off.device
-        nnz = int(local_idx.shape[0] + remote_vals.shape[0])
-        out_off = torch.empty(q + 1, dtype=torch.int32, device=dev)
-        out_vals = torch.empty((nnz, 2), dtype=torch.int32, device=dev)
-        lo = local_off.to(torch.int32).contiguous()
-        li = local_idx.to(torch.int32).contiguous()
-        ro = remote_off.to(torch.int32).contiguous()
-        rv = remote_vals.to(torch.int32).contiguous()
-        with torch.cuda.stream(self.space.stream):
-            _lib.check(_lib.lib().abx_dist_merge_crs(self.space.handle, q, C.c_void_p(lo.data_ptr()),
-                                                     C.c_void_p(li.data_ptr()), int(rank), C.c_void_p(ro.data_ptr()),
-                                                     C.c_void_p(rv.data_ptr()), C.c_void_p(out_off.data_ptr()),
-                                                     C.c_void_p(out_vals.data_ptr())))
-        return out_vals, out_off
+            return qids.long(), send_counts
 
 
 def route_generic(kind, data, rank_boxes, rank):
@@ -228,7 +281,12 @@ def _alltoallv(comm, rows, send_counts):
     return out, recv_counts
 
 
-class DistributedTree:
+# ------------------------------------------------------------------- protocol model ----
+class ProtocolModelTree:
+    """The reference-shaped exchange over torch.distributed with an injectable local engine: top-tree query ->
+    bucket by destination -> all-to-all-v of packed records -> bottom-tree query -> all-to-all-v back ->
+    segmented sort by query id; kNN in the reference's two phases.  Exercised on CPU (gloo + oracle engine)."""
+
     def __init__(self, comm, space, values, kind=None, engine=None):
         self.comm = comm
         self.rank = dist.get_rank(comm)
@@ -241,34 +299,21 @@ class DistributedTree:
             kind = {3: POINT, 6: BOX, 9: TRIANGLE}[values.shape[-1]]
         self.kind = kind
         self.device = values.device
-        self.force_generic = False  # tests flip this to exercise the reference-shaped exchange
-        # ABX_DIST_OVERLAP=1 runs the exchange on a side stream while a helper thread drives the local
-        # query.  Measured on 2xB200 (10M/rank): radius phase 10.9 ms without, 68 ms with (host-side
-        # contention between the two Python threads) -- off by default.
-        self._overlap = os.environ.get("ABX_DIST_OVERLAP", "0") == "1"
-        self._side = None
         # bottom tree (ArborX_DistributedTree.hpp:183-186)
         self._bottom = self.engine.build(values, kind)
         n_local = int(self.engine.size(self._bottom))
-        # all-gather rank boxes (:208-227) and sizes (:243-245)
-        b = self.engine.bounds(self._bottom).to(torch.float32).cpu()
-        meta = torch.cat([b, torch.tensor([float(n_local)])]).to(self.device)
-        gathered = [torch.empty_like(meta) for _ in range(self.world)]
-        dist.all_gather(gathered, meta, group=comm)
-        g = torch.stack(gathered).cpu()
-        self._rank_boxes = g[:, :6].contiguous()
-        self._sizes = g[:, 6].to(torch.int64)
+        # all-gather rank boxes (:208-227) and sizes (:243-245; 64-bit, separate from the float boxes)
+        b = self.engine.bounds(self._bottom).to(torch.float32).to(self.device)
+        gathered = [torch.empty_like(b) for _ in range(self.world)]
+        dist.all_gather(gathered, b, group=comm)
+        self._rank_boxes = torch.stack(gathered).cpu().contiguous()
+        nl = torch.tensor([n_local], dtype=torch.int64, device=self.device)
+        sizes = [torch.empty_like(nl) for _ in range(self.world)]
+        dist.all_gather(sizes, nl, group=comm)
+        self._sizes = torch.cat(sizes).cpu()
         self._size = int(self._sizes.sum())
-        # replicated top tree over the rank boxes (:227); leaf value = rank.  Built on first use: the
-        # fast paths route against the R boxes directly and never need it.
+        # replicated top tree over the rank boxes (:227); leaf value = rank
         self._top_tree = None
-
-    def _side_space(self):
-        if self._side is None:
-            import arborx_b200 as abx
-            self._side = abx.ExecutionSpace(torch.cuda.Stream(device=self.device, priority=-1))
-            self._side_engine = CudaEngine(self._side)
-        return self._side
 
     @property
     def _top(self):
@@ -301,182 +346,12 @@ class DistributedTree:
             # DistributedTreeSpatial.hpp:44-50
             out = (torch.empty((0, 2), dtype=torch.int32, device=dev), torch.zeros(q + 1, dtype=torch.int32, device=dev))
             return out + ((torch.empty(0, dtype=torch.float32, device=dev),) if return_distances else ())
-        fast = self.world <= 62 and not self.force_generic
         if predicates.tag == "spatial":
-            if fast:
-                vals, offsets = self._spatial_fast(predicates.kind, data)
-            else:
-                ranks, off = self.engine.spatial(self._top, predicates.kind, data)
-                vals, offsets, _ = self._forward_and_collect(data, ranks.long(), off.long(),
-                                                             ("spatial", predicates.kind))
+            ranks, off = self.engine.spatial(self._top, predicates.kind, data)
+            vals, offsets, _ = self._forward_and_collect(data, ranks.long(), off.long(), ("spatial", predicates.kind))
             return (vals, offsets) + ((torch.empty(0, dtype=torch.float32, device=dev),) if return_distances else ())
-        k = int(predicates.k)
-        if fast and k >= 1 and int(self._sizes.min()) >= k:
-            vals, offsets, d = self._nearest_fast(data, k)
-        else:
-            vals, offsets, d = self._nearest(data, k)
+        vals, offsets, d = self._nearest(data, int(predicates.k))
         return (vals, offsets, d) if return_distances else (vals, offsets)
-
-    # ---- fast paths --------------------------------------------------------------------
-    # The reference forwards every query through the exchange, including the (vast majority
-    # of) queries that only concern the rank they live on.  Here the local tree is queried
-    # directly for all local queries, only the queries that also touch OTHER ranks' boxes are
-    # packed, exchanged and merged back, so the full-size arrays are touched by the tree
-    # kernels and one merge pass only.  Routing may be conservative (a rank that gets a query
-    # it has nothing for returns nothing), so it is a plain tensor test against the R boxes.
-    def _route(self, kind, data, radius=None, radius_stride=1):
-        if hasattr(self.engine, "route"):
-            return self.engine.route(kind, data, self._rank_boxes, self.rank, radius, radius_stride)
-        if radius is not None:
-            data = torch.cat([data, radius.view(-1)[::radius_stride][:data.shape[0]].unsqueeze(1)], 1)
-        return route_generic(kind, data, self._rank_boxes, self.rank)
-
-    def _exchange_remote(self, data, qid_s, send_counts, what, engine=None):
-        """Forward the predicates qid_s (grouped by destination), query there, bring the results back.
-        -> (query ids [M] (sorted), values [M, 2] (index, rank), distances [M] or None)"""
-        engine = engine or self.engine
-        dev = data.device
-        R = self.world
-        rows = torch.cat([data[qid_s].contiguous().view(torch.int32), qid_s.to(torch.int32).unsqueeze(1)], 1)
-        fwd, recv_counts = _alltoallv(self.comm, rows, send_counts)
-        stride = data.shape[1]
-        fwd_preds = fwd[:, :stride].contiguous().view(torch.float32)
-        fwd_ids = fwd[:, stride]
-        if what[0] == "spatial":
-            idx, loff = engine.spatial(self._bottom, what[1], fwd_preds)
-            cols = [idx.to(torch.int32).unsqueeze(1)]
-        else:
-            idx, loff, d = engine.nearest(self._bottom, fwd_preds, what[1])
-            cols = [idx.to(torch.int32).unsqueeze(1), d.contiguous().view(torch.int32).unsqueeze(1)]
-        loff = loff.long()
-        # output_size: known from the result's shape, spares the host sync of a data-dependent size
-        res_ids = torch.repeat_interleave(fwd_ids, loff[1:] - loff[:-1], output_size=int(idx.shape[0]))
-        back_rows = torch.cat(cols + [res_ids.unsqueeze(1)], 1)
-        seg = torch.cumsum(torch.tensor([0] + recv_counts, device=dev), 0)
-        back_counts = (loff[seg[1:]] - loff[seg[:-1]]).tolist()
-        got, got_counts = _alltoallv(self.comm, back_rows, back_counts)
-        src_rank = torch.repeat_interleave(torch.arange(R, device=dev, dtype=torch.int32),
-                                           torch.tensor(got_counts, device=dev), output_size=int(got.shape[0]))
-        ids = got[:, -1].long()
-        order = torch.argsort(ids, stable=True)
-        vals = torch.stack([got[:, 0][order], src_rank[order]], 1)
-        dists = got[:, 1][order].contiguous().view(torch.float32) if what[0] == "nearest" else None
-        return ids[order], vals, dists
-
-    def _spatial_fast(self, kind, data):
-        dev = data.device
-        q = data.shape[0]
-        _mark("start")
-        qid_s, send_counts = self._route(kind, data)
-        _mark("route")
-        if self._overlap and isinstance(self.engine, CudaEngine):
-            # the exchange (forward, remote queries for other ranks, results back) runs on a
-            # high-priority side stream while a helper thread drives the big local query
-            # (abx_query_spatial_crs blocks its host thread once for nnz)
-            import threading
-            main = self.space.stream
-            side = self._side_space()
-            side.stream.wait_stream(main)
-            box = {}
-
-            def local():
-                try:
-                    torch.cuda.set_device(data.device)
-                    box["l"] = self.engine.spatial(self._bottom, kind, data)
-                except BaseException as e:  # re-raised on the calling thread
-                    box["e"] = e
-
-            th = threading.Thread(target=local)
-            th.start()
-            with torch.cuda.stream(side.stream):
-                ids, rvals, _ = self._exchange_remote(data, qid_s, send_counts, ("spatial", kind), self._side_engine)
-            th.join()
-            if "e" in box:
-                raise box["e"]
-            idx_l, off_l = box["l"]
-            main.wait_stream(side.stream)
-            ids.record_stream(main)
-            rvals.record_stream(main)
-        else:
-            idx_l, off_l = self.engine.spatial(self._bottom, kind, data)
-            _mark("local")
-            ids, rvals, _ = self._exchange_remote(data, qid_s, send_counts, ("spatial", kind))
-        _mark("exchange")
-        if ids.shape[0] == 0:
-            # nothing came back from other ranks: the local CRS is the answer
-            if hasattr(self.engine, "pair_with_rank"):
-                return self.engine.pair_with_rank(idx_l, self.rank), off_l.to(torch.int32)
-            return torch.stack([idx_l.to(torch.int32), torch.full_like(idx_l, self.rank, dtype=torch.int32)], 1), \
-                off_l.to(torch.int32)
-        if hasattr(self.engine, "merge_sorted"):
-            _mark("roff")
-            out = self.engine.merge_sorted(off_l, idx_l, self.rank, ids, rvals)
-        else:
-            roff = torch.zeros(q + 1, dtype=torch.int64, device=dev)
-            roff[1:] = torch.cumsum(torch.bincount(ids, minlength=q), 0)
-            _mark("roff")
-            out = self.engine.merge_rows(off_l, idx_l, self.rank, roff, rvals)
-        _mark("merge")
-        _report("spatial")
-        return out
-
-    def _nearest_fast(self, pts, k):
-        """Every rank holds >= k primitives: the local k-th distance bounds the true one (phase I
-        without an exchange), ranks within that distance are asked for their k nearest (phase II),
-        and only the queries that received remote candidates are re-ranked."""
-        dev = pts.device
-        q = pts.shape[0]
-        _mark("start")
-        vals = None
-        if hasattr(self.engine, "nearest_pairs"):
-            # local rows written directly as (index, rank) pairs
-            got = self.engine.nearest_pairs(self._bottom, pts, k, self.rank)
-            if got is None or got[0].shape[0] != q * k:
-                return self._nearest(pts, k)  # short local rows (fewer than k leaves, unreachable leaves)
-            vals, d_l = got
-            _mark("local")
-        else:
-            idx_l, off_l, d_l = self.engine.nearest(self._bottom, pts, k)
-            _mark("local")
-            if idx_l.shape[0] != q * k:
-                return self._nearest(pts, k)  # short local rows (unreachable leaves): generic path
-        # phase II spheres (point, local k-th distance): routed without materialising them
-        qid_s, send_counts = self._route(SPHERE_PRED, pts, d_l.view(-1)[k - 1:], k)
-        _mark("route")
-        ids, rvals, rd = self._exchange_remote(pts, qid_s, send_counts, ("nearest", k))
-        _mark("exchange")
-        if vals is None:
-            if hasattr(self.engine, "pair_with_rank"):
-                vals = self.engine.pair_with_rank(idx_l, self.rank)
-            else:
-                vals = torch.stack([idx_l.to(torch.int32), torch.full_like(idx_l, self.rank, dtype=torch.int32)], 1)
-        _mark("pair")
-        out_d = d_l
-        if ids.shape[0] and hasattr(self.engine, "knn_merge"):
-            self.engine.knn_merge(ids, rvals, rd, k, vals, out_d)
-        elif ids.shape[0]:
-            # queries with remote candidates: k local + m remote, keep the k smallest
-            uq, inv = torch.unique(ids, return_inverse=True)
-            cnt = torch.bincount(inv, minlength=uq.shape[0])
-            m = int(cnt.max())
-            start = torch.cumsum(cnt, 0) - cnt
-            pos = torch.arange(ids.shape[0], device=dev) - start[inv]
-            u = uq.shape[0]
-            cd = torch.full((u, k + m), float("inf"), dtype=torch.float32, device=dev)
-            cv = torch.zeros((u, k + m, 2), dtype=torch.int32, device=dev)
-            rows = (uq.unsqueeze(1) * k + torch.arange(k, device=dev)).view(-1)  # local rows of the affected queries
-            cd[:, :k] = out_d[rows].view(u, k)
-            cv[:, :k] = vals[rows].view(u, k, 2)
-            cd[inv, k + pos] = rd
-            cv[inv, k + pos] = rvals
-            sd, so = torch.sort(cd, dim=1, stable=True)
-            so = so[:, :k]
-            out_d[rows] = sd[:, :k].reshape(-1)
-            vals[rows] = torch.gather(cv, 1, so.unsqueeze(2).expand(u, k, 2)).reshape(-1, 2)
-        offsets = torch.arange(q + 1, device=dev, dtype=torch.int32) * k
-        _mark("rerank")
-        _report("nearest")
-        return vals, offsets, out_d
 
     # forwardQueries + bottom query + communicateResultsBack + sort by query id
     # (DistributedTreeUtils.hpp:229-263).  ranks/off: CRS of destination ranks per local query.

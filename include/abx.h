@@ -188,11 +188,78 @@ typedef struct abx_device_view
 } abx_device_view;
 ABX_API abx_status abx_bvh_device_view(const abx_bvh *bvh, abx_device_view *view);
 
+/* ---- ArborX::DistributedTree (distributed/ArborX_DistributedTree.hpp:33-252) ----
+ * One process (or host thread) per GPU.  Primitives are sharded by the caller: every rank builds a
+ * bottom tree over its own primitives, the rank boxes and sizes are all-gathered (:208-245) and form the
+ * replicated top tree.  Queries are COLLECTIVE over the communicator (:120-121): every rank calls with
+ * its own predicates and gets, per predicate, the matching values of ALL ranks as (index, rank) pairs
+ * (index = position in the owner rank's primitives; the reference returns user values or {index, rank}
+ * from a callback, examples/distributed_tree/distributed_knn.cpp:62-104).
+ *
+ * Exchange (detail/ArborX_DistributedTreeUtils.hpp:52-263, ArborX_Distributor.hpp): the local tree
+ * answers every predicate directly; only predicates that also touch OTHER ranks' boxes are forwarded
+ * (one grouped NCCL send/recv each way; counts travel as one all-gather of the R x R count matrix),
+ * queried there and merged back per query.  Two blocking points per query call.
+ *
+ * `comm`: an abx_comm made from the caller's ncclComm_t (abx_comm_from_nccl), bootstrapped from a
+ * unique id (abx_comm_unique_id + abx_comm_init_rank; libnccl.so.2 is resolved at run time, so the
+ * library loads without NCCL), or an in-process group of host threads sharing one GPU
+ * (abx_comm_create_local: the multi-rank protocol on a single-GPU test box). */
+typedef struct abx_comm abx_comm;
+typedef struct abx_dist_tree abx_dist_tree;
+#define ABX_COMM_UNIQUE_ID_BYTES 128
+ABX_API abx_status abx_comm_from_nccl(void *nccl_comm /* ncclComm_t, not owned */, abx_comm **out);
+ABX_API abx_status abx_comm_unique_id(char id_out[ABX_COMM_UNIQUE_ID_BYTES]);
+ABX_API abx_status abx_comm_init_rank(const char id[ABX_COMM_UNIQUE_ID_BYTES], int32_t n_ranks, int32_t rank,
+                                      abx_comm **out);
+/* n_ranks communicators of one in-process group; rank r's calls must come from its own host thread */
+ABX_API abx_status abx_comm_create_local(int32_t n_ranks, abx_comm **out_array);
+ABX_API abx_status abx_comm_destroy(abx_comm *comm);
+ABX_API int32_t abx_comm_rank(const abx_comm *comm);
+ABX_API int32_t abx_comm_size(const abx_comm *comm);
+
+/* DistributedTree(comm, space, values) :129-151.  Collective. */
+ABX_API abx_status abx_dist_create(abx_comm *comm, void *stream, int prim_kind, const void *prims_dev, int64_t n,
+                                   abx_dist_tree **out);
+ABX_API abx_status abx_dist_destroy(abx_dist_tree *tree);
+ABX_API int64_t abx_dist_size(const abx_dist_tree *tree);  /* global number of primitives :114-116 */
+ABX_API int abx_dist_empty(const abx_dist_tree *tree);
+ABX_API abx_status abx_dist_bounds(const abx_dist_tree *tree, float out6[6]); /* union of the rank boxes :122-127 */
+/* query(space, intersects(...) predicates, values, offsets) :84-102; detail/ArborX_DistributedTreeSpatial.hpp:31-60.
+ * Collective.  pred_kind: SPHERE3F, BOX3F or POINT3F.  offsets (which = 0): q + 1 ints; values2 (which = 1):
+ * nnz (index, rank) pairs, row i = results of predicate i, local results first. */
+ABX_API abx_status abx_dist_query_spatial_crs(abx_dist_tree *tree, void *stream, int pred_kind, const void *preds_dev,
+                                              int64_t q, abx_alloc_fn alloc, void *user, int32_t **offsets_dev,
+                                              int32_t **values2_dev, int64_t *nnz);
+/* query(space, nearest(point, k) predicates, ...) detail/ArborX_DistributedTreeNearest.hpp:41-261.  Collective.
+ * Rows ascending by distance, min(k, global size) entries (fewer when leaves are at infinite distance);
+ * distances_dev may be NULL. */
+ABX_API abx_status abx_dist_query_nearest_crs(abx_dist_tree *tree, void *stream, const void *points_dev, int64_t q,
+                                              int32_t k, abx_alloc_fn alloc, void *user, int32_t **offsets_dev,
+                                              int32_t **values2_dev, float **distances_dev, int64_t *nnz);
+/* Host-buffer variants (end-to-end path): primitives / predicates in host memory, results in host arrays
+ * from `alloc_host`.  Results come back in the COMPACT form: indices (which = 1, one uint32 per result) all
+ * belong to the calling rank except the n_remote entries listed in remote_pos (which = 3, ascending positions
+ * into indices) whose owner ranks are remote_rank (which = 4) -- a few percent of the results on spatially
+ * compact shards, so the D2H volume is that of a single-tree query. */
+ABX_API abx_status abx_dist_create_host(abx_comm *comm, void *stream, int prim_kind, const void *prims_host, int64_t n,
+                                        abx_dist_tree **out);
+ABX_API abx_status abx_dist_query_spatial_crs_host(abx_dist_tree *tree, void *stream, int pred_kind,
+                                                   const void *preds_host, int64_t q, abx_alloc_fn alloc_host,
+                                                   void *user, int32_t **offsets_host, uint32_t **indices_host,
+                                                   int64_t *nnz, int32_t **remote_pos_host,
+                                                   int32_t **remote_rank_host, int64_t *n_remote);
+ABX_API abx_status abx_dist_query_nearest_crs_host(abx_dist_tree *tree, void *stream, const void *points_host,
+                                                   int64_t q, int32_t k, abx_alloc_fn alloc_host, void *user,
+                                                   int32_t **offsets_host, uint32_t **indices_host,
+                                                   float **distances_host, int64_t *nnz, int32_t **remote_pos_host,
+                                                   int32_t **remote_rank_host, int64_t *n_remote);
+
 /* ---- DistributedTree building block (distributed/detail/ArborX_DistributedTreeUtils.hpp:229-263) ----
  * Merges, per query, the CRS rows of the local tree's results (indices) with the CRS rows of the
  * results that came back from other ranks ((index, rank) pairs, grouped by query) into one CRS
- * of (index, rank) pairs: out_offsets[q+1], out_values2[2 * (nnz_local + nnz_remote)].  The
- * exchange itself (all-to-all-v over NCCL) is driven by the host side, arborx_b200/distributed.py. */
+ * of (index, rank) pairs: out_offsets[q+1], out_values2[2 * (nnz_local + nnz_remote)].  These are the
+ * kernels behind abx_dist_query_*; exported so that tests can check each one against a restatement. */
 ABX_API abx_status abx_dist_merge_crs(void *stream, int64_t q, const int32_t *local_offsets_dev,
                                       const int32_t *local_indices_dev, int32_t rank,
                                       const int32_t *remote_offsets_dev, const int32_t *remote_values2_dev,
@@ -202,7 +269,7 @@ ABX_API abx_status abx_dist_merge_crs(void *stream, int64_t q, const int32_t *lo
  * (remote_query_ids_dev ascending), one (index, rank) pair each; no remote CRS offsets needed. */
 ABX_API abx_status abx_dist_merge_sorted(void *stream, int64_t q, const int32_t *local_offsets_dev,
                                          const int32_t *local_indices_dev, int32_t rank, int64_t n_remote,
-                                         const int64_t *remote_query_ids_dev, const int32_t *remote_values2_dev,
+                                         const int32_t *remote_query_ids_dev, const int32_t *remote_values2_dev,
                                          int32_t *out_offsets_dev, int32_t *out_values2_dev);
 
 /* Routing of forwarded predicates (the top-tree query of DistributedTreeSpatial.hpp:52-55 for R <= 64
@@ -224,17 +291,16 @@ ABX_API abx_status abx_dist_route_fill(void *stream, int pred_kind, const void *
 ABX_API abx_status abx_dist_pair_with_rank(void *stream, const int32_t *indices_dev, int64_t n, int32_t rank,
                                            int32_t *values2_dev);
 /* DistributedTree kNN, local phase (distributed/detail/ArborX_DistributedTreeNearest.hpp:131-176): the k
- * nearest of every point with rows of exactly row = min(k, size) entries, written directly in the
- * (index, rank) form: values2_dev[2 * (i * row + j)] = index, [.. + 1] = rank; distances_dev[i * row + j].
- * *missing_out = entries that could not be filled (leaves at infinite distance); when it is not 0 the
- * rows are not usable and the caller takes the general path (abx_query_nearest_crs). */
+ * nearest of every point in rows of exactly k slots, written directly in the (index, rank) form:
+ * values2_dev[2 * (i * k + j)] = index, [.. + 1] = rank; distances_dev[i * k + j].  Rows with fewer than k
+ * reachable leaves are padded with (-1, -1) / +inf; *missing_out = number of padded slots. */
 ABX_API abx_status abx_dist_nearest_pairs(abx_bvh *bvh, void *stream, const void *points_dev, int64_t q, int32_t k,
                                           int32_t rank, int32_t *values2_dev, float *distances_dev,
                                           int64_t *missing_out);
 /* DistributedTree kNN, final ranking (same file :178-233): candidates received from other ranks
  * (query_ids_dev ascending, one (index, rank) pair and one distance each) are merged into the rows of
  * their queries (k entries each, ascending): the k smallest survive, local entries first among equals. */
-ABX_API abx_status abx_dist_knn_merge(void *stream, int64_t n_candidates, const int64_t *query_ids_dev,
+ABX_API abx_status abx_dist_knn_merge(void *stream, int64_t n_candidates, const int32_t *query_ids_dev,
                                       const int32_t *cand_values2_dev, const float *cand_distances_dev, int32_t k,
                                       int32_t *values2_dev, float *distances_dev);
 

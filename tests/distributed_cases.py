@@ -65,30 +65,55 @@ def rows(vals, off):
 
 
 def run_all(make_engine, device, space=None):
-    """Runs every case twice: through the fast paths (local-first, remote-only exchange) and through the
-    reference-shaped generic exchange (every query forwarded, incl. to its own rank)."""
-    orig = D.DistributedTree.__init__
-    for generic in (False, True):
-        def patched(self, *a, **k):
-            orig(self, *a, **k)
-            self.force_generic = generic
-        D.DistributedTree.__init__ = patched
-        try:
-            _run_all(make_engine, device, space)
-        finally:
-            D.DistributedTree.__init__ = orig
-    return True
-
-
-def _run_all(make_engine, device, space=None):
-    rank, size = dist.get_rank(), dist.get_world_size()
+    """Protocol model (torch.distributed + injected engine) on every rank of the default process group."""
     comm = dist.group.WORLD
+    make_tree = lambda values, kind=None: D.DistributedTree(comm, space, values, kind, engine=make_engine())
+    return run_cases(dist.get_rank(), dist.get_world_size(), make_tree, device, space)
+
+
+def expand_compact(res, rank, with_dist):
+    """Host (compact) result of the native tree -> ((index, rank) pairs, offsets[, distances])."""
+    idx, off = res[0], res[1]
+    rpos, rrank = res[-2], res[-1]
+    vals = torch.stack([idx, torch.full_like(idx, rank)], 1)
+    vals[rpos.long(), 1] = rrank
+    assert bool((rpos[1:] > rpos[:-1]).all())
+    return (vals, off) + ((res[2],) if with_dist else ())
+
+
+def run_cases(rank, size, make_tree, device, space=None, check_host=False):
+    """Rank-count-agnostic cases; make_tree(values, kind=None) builds this rank's DistributedTree.
+    check_host (native tree): every query is repeated through the host-buffer entry points and the compact
+    result must expand to the same rows."""
+    class _Tree:
+        def __init__(self, values, kind=None):
+            self.t = make_tree(values, kind)
+
+        def size(self):
+            return self.t.size()
+
+        def empty(self):
+            return self.t.empty()
+
+        def query(self, space, pred, return_distances=False):
+            out = self.t.query(space, pred, return_distances=return_distances)
+            if check_host:
+                hp = _Pred(pred.tag, pred.kind, pred.data.cpu(), pred.k)
+                hres = expand_compact(self.t.query(space, hp, return_distances=return_distances), rank,
+                                      return_distances)
+                assert rows(hres[0], hres[1]) == rows(out[0], out[1])
+                assert torch.equal(hres[1], out[1].cpu())
+                if return_distances and pred.tag == "nearest":
+                    assert torch.equal(hres[2], out[2].cpu())
+            return out
+
+    n = 4
     T = lambda a: torch.as_tensor(np.asarray(a, F)).to(device)
     n = 4
 
     # ---- hello world, spatial (tstDistributedTreeSpatial.cpp:32-94) ----
     pts = np.array([[i / n + rank, 0, 0] for i in range(n)], F)
-    tree = D.DistributedTree(comm, space, T(pts), engine=make_engine())
+    tree = _Tree(T(pts))
     assert tree.size() == n * size and not tree.empty()
     q = np.array([[0.5 + size - 1 - rank, 0, 0, 0.5]], F)
     vals, off = tree.query(space, _Pred("spatial", D.SPHERE_PRED, T(q)))
@@ -110,7 +135,7 @@ def _run_all(make_engine, device, space=None):
 
     # ---- non-approximate nearest neighbours (:404-452), box primitives ----
     boxes = np.array([[rank, 0, 0, rank, 0, 0], [rank + 1, 1, 1, rank + 1, 1, 1]], F)
-    tb = D.DistributedTree(comm, space, T(boxes), kind=D.BOX, engine=make_engine())
+    tb = _Tree(T(boxes), D.BOX)
     assert tb.size() == 2 * size
     qn = np.array([[(size - 1 - rank) + 0.75, 0, 0]], F)
     vals, off = tb.query(space, _Pred("nearest", D.POINT_PRED, T(qn), 1))
@@ -118,7 +143,7 @@ def _run_all(make_engine, device, space=None):
 
     # ---- distributed_knn example (examples/distributed_tree/distributed_knn.cpp:62-104) ----
     pe = np.array([[rank, rank, rank], [rank + .5, rank + .5, rank + .5]], F)
-    te = D.DistributedTree(comm, space, T(pe), engine=make_engine())
+    te = _Tree(T(pe))
     vals, off = te.query(space, _Pred("nearest", D.POINT_PRED, T(pe), 3))
     if rank == 0 and size >= 2:
         r = rows(vals, off)
@@ -126,14 +151,14 @@ def _run_all(make_engine, device, space=None):
         assert r[0] == sorted([(0, 0), (1, 0), (0, 1)]) and r[1] == sorted([(1, 0), (0, 0), (0, 1)]), r
 
     # ---- empty tree and partially empty ranks (tstDistributedTreeSpatial.cpp:96-190) ----
-    tz = D.DistributedTree(comm, space, T(np.zeros((0, 3), F)), kind=D.POINT, engine=make_engine())
+    tz = _Tree(T(np.zeros((0, 3), F)), D.POINT)
     assert tz.empty() and tz.size() == 0
     vals, off = tz.query(space, _Pred("spatial", D.SPHERE_PRED, T([[0, 0, 0, 1], [1, 1, 1, 2]])))
     assert list(off.cpu().numpy()) == [0, 0, 0] and vals.shape[0] == 0
     vals, off = tz.query(space, _Pred("nearest", D.POINT_PRED, T([[0, 0, 0]]), 3))
     assert list(off.cpu().numpy()) == [0, 0]
     only0 = pts if rank == 0 else np.zeros((0, 3), F)
-    t0 = D.DistributedTree(comm, space, T(only0), kind=D.POINT, engine=make_engine())
+    t0 = _Tree(T(only0), D.POINT)
     assert t0.size() == n
     vals, off = t0.query(space, _Pred("nearest", D.POINT_PRED, T([[0.3, 0, 0]]), 2))
     assert rows(vals, off) == [[(1, 0), (2, 0)]], rows(vals, off)
@@ -144,7 +169,7 @@ def _run_all(make_engine, device, space=None):
     n_loc, q_loc = 3000, 400
     all_pts = [clouds.uniform01(100 + r, n_loc) + F(0.6) * F(r) for r in range(size)]  # overlapping slabs in x
     mine = all_pts[rank]
-    tr = D.DistributedTree(comm, space, T(mine), engine=make_engine())
+    tr = _Tree(T(mine))
     qs = (clouds.uniform01(500 + rank, q_loc) * F(0.6 * (size - 1) + 1.0)).astype(F)
     qs[:, 1:] = clouds.uniform01(600 + rank, q_loc)[:, 1:]
     glob = np.concatenate(all_pts)

@@ -1,5 +1,6 @@
-"""DistributedTree: the N>1 exchange protocol on CPU (world_size-2/3 gloo, oracle as the local engine) and
-on the GPU (-m gpu: single-rank nccl group in-process; multi-rank via torchrun in scripts/dist_check.py)."""
+"""DistributedTree: the reference-shaped exchange protocol on CPU (world sizes 1-3, gloo, oracle as the local
+engine) and, with -m gpu, the C++ DistributedTree of libabx.so: over a one-rank NCCL communicator and as 2-4 ranks
+(host threads) on one GPU over the in-process communicator; across GPUs via torchrun in scripts/dist_check.py."""
 import os
 
 import pytest
@@ -40,9 +41,10 @@ def test_distributed_protocol_gloo(world):
 
 @pytest.mark.gpu
 def test_distributed_single_rank_cuda():
+    """The C++ DistributedTree over a real (one-rank) NCCL communicator bootstrapped from the process group."""
     import arborx_b200 as abx
-    from arborx_b200.distributed import CudaEngine
-    from tests.distributed_cases import run_all
+    from arborx_b200.distributed import DistributedTree
+    from tests.distributed_cases import run_cases
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     os.environ.setdefault("MASTER_PORT", "29555")
     created = False
@@ -51,10 +53,46 @@ def test_distributed_single_rank_cuda():
         created = True
     try:
         space = abx.ExecutionSpace()
-        run_all(lambda: CudaEngine(space), torch.device("cuda", 0), space)
+        make_tree = lambda v, kind=None: DistributedTree(dist.group.WORLD, space, v, kind)
+        run_cases(0, 1, make_tree, torch.device("cuda", 0), space, check_host=True)
     finally:
         if created:
             dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_distributed_native_local_ranks(world):
+    """The C++ DistributedTree with `world` ranks on ONE GPU: every rank is a host thread with its own
+    execution space, the communicator is the in-process group (abx_comm_create_local), so routing, both
+    exchanges, the sort by query id and the merge kernels run exactly as they do across GPUs."""
+    import threading
+
+    import arborx_b200 as abx
+    from arborx_b200.distributed import Communicator, DistributedTree
+    from tests.distributed_cases import run_cases
+    comms = Communicator.local_group(world)
+    errors = [None] * world
+
+    def worker(r):
+        try:
+            torch.cuda.set_device(0)
+            space = abx.ExecutionSpace(torch.cuda.Stream())
+            with torch.cuda.stream(space.stream):
+                make_tree = lambda v, kind=None: DistributedTree(comms[r], space, v, kind)
+                run_cases(r, world, make_tree, torch.device("cuda", 0), space, check_host=True)
+        except BaseException:
+            import traceback
+            errors[r] = traceback.format_exc()
+
+    threads = [threading.Thread(target=worker, args=(r,), daemon=True) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not any(t.is_alive() for t in threads), "a rank is stuck in a collective: %s" % errors
+    for r, e in enumerate(errors):
+        assert e is None, "rank %d:\n%s" % (r, e)
 
 
 def _dbscan_worker(rank, world, port, q):
