@@ -391,12 +391,12 @@ def profile_enable(on=True):
 
 
 def profile_report():
-    """-> list of (kernel name, launches, total_ms), most expensive first."""
+    """-> list of (kernel name, launches, total_ms, max_ms of one launch), most expensive first."""
     need = lib().abx_profile_report(None, 0)
     buf = C.create_string_buffer(int(need) + 16)
     lib().abx_profile_report(buf, len(buf))
     rows = []
     for line in buf.value.decode().splitlines():
-        name, cnt, ms = line.rsplit("\t", 2)
-        rows.append((name, int(cnt), float(ms)))
+        name, cnt, ms, mx = line.rsplit("\t", 3)
+        rows.append((name, int(cnt), float(ms), float(mx)))
     return rows

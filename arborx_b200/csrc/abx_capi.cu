@@ -512,7 +512,7 @@ abx_status abx_profile_enable(int on)
   return ABX_OK;
 }
 
-// "name\tlaunches\ttotal_ms\n" per kernel, most expensive first; returns the number
+// "name\tlaunches\ttotal_ms\tmax_ms\n" per kernel, most expensive first; returns the number
 // of bytes needed (including the terminating NUL)
 int64_t abx_profile_report(char *buf, int64_t capacity)
 {
@@ -522,7 +522,7 @@ int64_t abx_profile_report(char *buf, int64_t capacity)
   {
     std::string name;
     int64_t count = 0;
-    double ms = 0;
+    double ms = 0, max_ms = 0;
   };
   std::vector<Agg> aggs;
   for (auto &r : g_records)
@@ -534,18 +534,19 @@ int64_t abx_profile_report(char *buf, int64_t capacity)
     auto it = std::find_if(aggs.begin(), aggs.end(), [&](Agg const &a) { return a.name == name; });
     if (it == aggs.end())
     {
-      aggs.push_back(Agg{name, 0, 0});
+      aggs.push_back(Agg{name, 0, 0, 0});
       it = aggs.end() - 1;
     }
     it->count++;
     it->ms += ms;
+    it->max_ms = std::max(it->max_ms, (double)ms);
   }
   std::sort(aggs.begin(), aggs.end(), [](Agg const &a, Agg const &b) { return a.ms > b.ms; });
   std::string out;
   for (auto &a : aggs)
   {
     char line[512];
-    snprintf(line, sizeof line, "%s\t%lld\t%.6f\n", a.name.c_str(), (long long)a.count, a.ms);
+    snprintf(line, sizeof line, "%s\t%lld\t%.6f\t%.6f\n", a.name.c_str(), (long long)a.count, a.ms, a.max_ms);
     out += line;
   }
   if (buf && capacity > 0)

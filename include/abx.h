@@ -75,8 +75,8 @@ typedef struct abx_policy
 
 /* Output allocation.  The reference re-allocates the caller's Views
  * (spatial/detail/ArborX_CrsGraphWrapperImpl.hpp:257,286,337,349); across a C ABI
- * the caller supplies the allocator instead.  `which`: 0 offsets, 1 indices,
- * 2 distances.  Must return device memory of at least `bytes` (may return NULL
+ * the caller supplies the allocator instead.  `which`: 0 offsets, 1 indices / values,
+ * 2 distances, 3 remote positions, 4 remote ranks (DistributedTree host results).  Must return device memory of at least `bytes` (may return NULL
  * for bytes == 0).  Passing a NULL allocator makes the library allocate with
  * cudaMallocAsync on `stream`; release those with abx_free(). */
 typedef void *(*abx_alloc_fn)(void *user, int which, size_t bytes);
@@ -95,7 +95,7 @@ ABX_API int64_t abx_trim(void);
 /* Per-kernel device timing (the analogue of the reference's Kokkos-Tools regions,
  * SURVEY.md section 5): CUDA events on the launching stream around every launch.
  * enable(1) clears and starts recording, enable(0) stops.  report() synchronises
- * and writes "name\tlaunches\ttotal_ms\n" lines, most expensive first; it
+ * and writes "name\tlaunches\ttotal_ms\tmax_ms\n" lines (max_ms: the longest single launch), most expensive first; it
  * returns the bytes needed including the NUL. */
 ABX_API abx_status abx_profile_enable(int on);
 ABX_API int64_t abx_profile_report(char *buf, int64_t capacity);

@@ -3,4 +3,4 @@
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -40 | tee gpurun_out/r02_pytest_call2.log
+timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -60 | tee gpurun_out/r02_pytest_call2.log

@@ -34,5 +34,5 @@ for it in range(reps):
     ts.append(e0.elapsed_time(e1))
 ts.sort()
 print("build n=%d %s: median %.4f ms min %.4f ms  (%.2f Gprims/s)" % (n, kind, ts[len(ts) // 2], ts[0], n / ts[len(ts) // 2] / 1e6))
-for name, cnt, ms in abx.profile_report():
+for name, cnt, ms, _mx in abx.profile_report():
     print("   %-40s %4d  %.4f ms/launch  %.4f ms/build" % (name, cnt, ms / cnt, ms / reps))

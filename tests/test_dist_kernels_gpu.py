@@ -180,7 +180,8 @@ def test_knn_merge(ctx, k):
         ref_d[i], ref_v[i] = d_all[order], v_all[order]
     cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
     d_vals, d_dist = cu(vals.reshape(-1, 2)), cu(dist.reshape(-1))
-    _lib.check(L.abx_dist_knn_merge(space.handle, ids.shape[0], _ptr(cu(ids)), _ptr(cu(cv)), _ptr(cu(cd)), k,
+    d_ids, d_cv, d_cd = cu(ids), cu(cv), cu(cd)  # named: the buffers must outlive the launch
+    _lib.check(L.abx_dist_knn_merge(space.handle, ids.shape[0], _ptr(d_ids), _ptr(d_cv), _ptr(d_cd), k,
                                     _ptr(d_vals), _ptr(d_dist)))
     assert np.array_equal(d_dist.cpu().numpy().reshape(q, k), ref_d)
     got_v = d_vals.cpu().numpy().reshape(q, k, 2)
