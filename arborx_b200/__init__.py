@@ -385,6 +385,13 @@ def launch_count():
     return lib().abx_launch_count()
 
 
+def trim():
+    """Return the library's cached device blocks (and torch's) to the driver; -> bytes released by libabx."""
+    released = lib().abx_trim()
+    torch.cuda.empty_cache()
+    return released
+
+
 def profile_enable(on=True):
     """Start/stop per-kernel CUDA-event timing inside the library."""
     _lib.check(lib().abx_profile_enable(int(bool(on))))
