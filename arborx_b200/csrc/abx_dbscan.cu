@@ -342,11 +342,23 @@ __global__ void markDenseCoreKernel(unsigned const *__restrict__ perm, int num_p
     num_neigh[perm[i]] = INT_MAX; // ArborX_DBSCAN.hpp:438-441
 }
 
-__device__ __forceinline__ bool withinEps(float const *__restrict__ xyz, float px, float py, float pz, int j, float t)
+// the points of the dense cells gathered in reordered (cell by cell) order: (x, y, z, bits(original index)).
+// Every loop over "the points of dense cell k" below reads a contiguous run of this array instead of
+// chasing perm -> xyz.
+__global__ void gatherDensePointsKernel(float const *__restrict__ xyz, unsigned const *__restrict__ perm,
+                                        int num_points_dense, float4 *__restrict__ dense_pts)
 {
-  // distance(query_point, point_j) <= eps with the reference's operand order
-  float tx = __fsub_rn(xyz[3 * (size_t)j], px), ty = __fsub_rn(xyz[3 * (size_t)j + 1], py),
-        tz = __fsub_rn(xyz[3 * (size_t)j + 2], pz);
+  int const i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= num_points_dense)
+    return;
+  unsigned const o = perm[i];
+  dense_pts[i] = make_float4(xyz[3 * (size_t)o], xyz[3 * (size_t)o + 1], xyz[3 * (size_t)o + 2], __uint_as_float(o));
+}
+
+// distance(query_point, point_j) <= eps with the reference's operand order (tmp = point_j - query)
+__device__ __forceinline__ bool withinEps4(float4 pj, float px, float py, float pz, float t)
+{
+  float tx = __fsub_rn(pj.x, px), ty = __fsub_rn(pj.y, py), tz = __fsub_rn(pj.z, pz);
   float d2 = __fmul_rn(tx, tx);
   d2 = __fadd_rn(d2, __fmul_rn(ty, ty));
   d2 = __fadd_rn(d2, __fmul_rn(tz, tz));
@@ -356,8 +368,8 @@ __device__ __forceinline__ bool withinEps(float const *__restrict__ xyz, float p
 // CountUpToN_DenseBox (FDBSCANDenseBox.hpp:32-96) for the points of sparse cells
 __global__ void __launch_bounds__(kThreads)
     denseCountKernel(Node64 const *__restrict__ nodes, float4 const *__restrict__ leaf_box, int n_prims,
-                     float const *__restrict__ xyz,
-                     unsigned const *__restrict__ perm, int const *__restrict__ dense_cell_offsets, int num_dense,
+                     float const *__restrict__ xyz, unsigned const *__restrict__ perm,
+                     float4 const *__restrict__ dense_pts, int const *__restrict__ dense_cell_offsets, int num_dense,
                      int num_points_dense, int n, float eps, int minpts, int *__restrict__ num_neigh)
 {
   int const s = blockIdx.x * kThreads + threadIdx.x;
@@ -376,7 +388,7 @@ __global__ void __launch_bounds__(kThreads)
       {
         int const ce = dense_cell_offsets[k + 1];
         for (int jj = dense_cell_offsets[k]; jj < ce; ++jj)
-          if (withinEps(xyz, px, py, pz, (int)perm[jj], pred.t))
+          if (withinEps4(__ldg(dense_pts + jj), px, py, pz, pred.t))
             if (++count >= minpts)
               return true;
         return false;
@@ -388,68 +400,244 @@ __global__ void __launch_bounds__(kThreads)
   num_neigh[i] = count;
 }
 
-// FDBSCANDenseBoxCallback (FDBSCANDenseBox.hpp:98-205): full traversal per point
+// ---- FDBSCANDenseBoxCallback (FDBSCANDenseBox.hpp:98-205), B200 shape ----------------------------------------
+// The reference runs one full traversal per POINT; on clustered data nearly every point sits in a dense cell,
+// and all points of a cell find the same neighbouring cells and repeat the same "is any point of that cell
+// within eps of me" loops (ncu on GanTao 10M: 82 ms, 6 GB/s of DRAM, 68 warps stalled on dependent label loads
+// per issue).  What the callback computes for dense cells is a relation between CELLS: dense cells A and B end up
+// in one cluster iff some a in A, b in B are within eps (all points of a dense cell are core and mutually
+// within eps).  So:
+//   denseCellPairsKernel   one WARP per dense cell A: a warp-uniform traversal with A's box finds the dense cells
+//                          B > A whose box is within eps, skips the ones already in A's set (one label load) and
+//                          tests the rest cooperatively -- points of A within eps of B's box against the points of
+//                          B (and the mirror image), 32 pairs per step, stopping at the first hit.
+//   sparseMainKernel       one thread per point of a SPARSE cell (a small minority): the reference callback, plus
+//                          border points attaching themselves to the first core neighbour they find (the reference
+//                          lets every core neighbour overwrite the border point's label: same set of outcomes).
+// Core points end up with the same partition as the reference (labels = smallest index of the component).
+__device__ __forceinline__ float boxBoxDist2(float const *A, float4 lo, float4 hi)
+{
+  float d2 = 0.f;
+  float const blo[3] = {lo.x, lo.y, lo.z}, bhi[3] = {hi.x, hi.y, hi.z};
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+  {
+    float const gap = fmaxf(fmaxf(__fsub_rn(blo[d], A[3 + d]), __fsub_rn(A[d], bhi[d])), 0.f);
+    d2 = __fadd_rn(d2, __fmul_rn(gap, gap));
+  }
+  return d2;
+}
+
+__global__ void __launch_bounds__(128)
+    denseCellPairsKernel(Node64 const *__restrict__ nodes, float const *__restrict__ boxes6,
+                         float4 const *__restrict__ dense_pts, int const *__restrict__ dense_cell_offsets, int num_dense,
+                         float eps, int *labels)
+{
+  unsigned const full = 0xffffffffu;
+  int const lane = threadIdx.x & 31;
+  int const c = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (c >= num_dense)
+    return; // the whole warp
+  float const t = sqrtThreshold(eps);
+  // culling threshold for box-to-box distances, inflated: a box pair is only dropped when no point pair can pass
+  // the exact tests below
+  float const t_cull = __fadd_rn(__fmul_rn(t, 1.0001f), 1e-30f);
+  float A[6];
+#pragma unroll
+  for (int d = 0; d < 6; ++d)
+    A[d] = __ldg(boxes6 + 6 * (size_t)c + d);
+  int const a0 = dense_cell_offsets[c], a1 = dense_cell_offsets[c + 1];
+  int const first_c = (int)__float_as_uint(__ldg(dense_pts + a0).w);
+  int rep_c = 0;
+  if (lane == 0)
+    rep_c = ufRepresentative(labels, first_c);
+  rep_c = __shfl_sync(full, rep_c, 0);
+
+  // one candidate cell k (the same value in every lane)
+  auto process = [&](int k) {
+    int const b0 = dense_cell_offsets[k], b1 = dense_cell_offsets[k + 1];
+    int const first_k = (int)__float_as_uint(__ldg(dense_pts + b0).w);
+    if (ufLoad(labels, first_k) == rep_c)
+      return;
+    int rc = 0, rk = 0;
+    if (lane == 0)
+    {
+      rc = ufRepresentative(labels, first_c);
+      rk = ufRepresentative(labels, first_k);
+    }
+    rc = __shfl_sync(full, rc, 0);
+    rk = __shfl_sync(full, rk, 0);
+    rep_c = rc;
+    if (rc == rk)
+      return;
+    float B[6];
+#pragma unroll
+    for (int d = 0; d < 6; ++d)
+      B[d] = __ldg(boxes6 + 6 * (size_t)k + d);
+    bool found = false;
+    // side = 0: points of A that see B's box (what a's own traversal would have reported) against every point
+    // of B; side = 1: the mirror image.  A pair within eps is found by at least one side.
+    for (int side = 0; side < 2 && !found; ++side)
+    {
+      int const p0 = side == 0 ? a0 : b0, p1 = side == 0 ? a1 : b1; // the "query" cell
+      int const o0 = side == 0 ? b0 : a0, o1 = side == 0 ? b1 : a1; // the other cell
+      float const *obox = side == 0 ? B : A;
+      for (int base = p0; base < p1 && !found; base += 32)
+      {
+        int const pi = base + lane;
+        float4 const pp = pi < p1 ? __ldg(dense_pts + pi) : make_float4(0.f, 0.f, 0.f, 0.f);
+        bool const sees = pi < p1 && pointBoxDist2(pp.x, pp.y, pp.z, obox[0], obox[1], obox[2], obox[3], obox[4],
+                                                   obox[5]) <= t;
+        unsigned m = __ballot_sync(full, sees);
+        while (m && !found)
+        {
+          int const src = __ffs(m) - 1;
+          m &= m - 1;
+          float const qx = __shfl_sync(full, pp.x, src), qy = __shfl_sync(full, pp.y, src),
+                      qz = __shfl_sync(full, pp.z, src);
+          for (int ob = o0; ob < o1; ob += 32)
+          {
+            int const oi = ob + lane;
+            bool const hit = oi < o1 && withinEps4(__ldg(dense_pts + oi), qx, qy, qz, t);
+            if (__any_sync(full, hit))
+            {
+              found = true;
+              break;
+            }
+          }
+        }
+      }
+    }
+    if (found)
+    {
+      if (lane == 0)
+      {
+        ufMerge(labels, first_c, first_k);
+        rc = ufRepresentative(labels, first_c);
+      }
+      rep_c = __shfl_sync(full, rc, 0);
+    }
+  };
+
+  // warp-uniform traversal of the mixed tree with A's box grown by eps
+  int stack[kStackSize];
+  int sp = 0;
+  int node = 0;
+  while (true)
+  {
+    float4 const *f = reinterpret_cast<float4 const *>(nodes + node);
+    float4 const n0 = __ldg(f), n1 = __ldg(f + 1), n2 = __ldg(f + 2), n3 = __ldg(f + 3);
+    int const lref = __float_as_int(n0.w), rref = __float_as_int(n1.w);
+    bool hit_l = boxBoxDist2(A, n0, n1) <= t_cull;
+    bool hit_r = boxBoxDist2(A, n2, n3) <= t_cull;
+    if (hit_l && refIsLeaf(lref))
+    {
+      int const k = (int)refOrig(lref);
+      if (k < num_dense && k > c)
+        process(k);
+      hit_l = false;
+    }
+    if (hit_r && refIsLeaf(rref))
+    {
+      int const k = (int)refOrig(rref);
+      if (k < num_dense && k > c)
+        process(k);
+      hit_r = false;
+    }
+    if (hit_l)
+    {
+      if (hit_r)
+        stack[sp++] = rref;
+      node = lref;
+    }
+    else if (hit_r)
+      node = rref;
+    else
+    {
+      if (sp == 0)
+        break;
+      node = stack[--sp];
+    }
+  }
+}
+
 template <bool SPECIAL, bool STAR>
 __global__ void __launch_bounds__(kThreads)
-    denseMainKernel(Node64 const *__restrict__ nodes, float4 const *__restrict__ leaf_box, int n_prims,
-                    float const *__restrict__ xyz,
-                    unsigned const *__restrict__ perm, int const *__restrict__ dense_cell_offsets, int num_dense,
-                    int num_points_dense, int n, float eps, int minpts, int const *__restrict__ num_neigh,
-                    int *labels)
+    sparseMainKernel(Node64 const *__restrict__ nodes, float4 const *__restrict__ leaf_box, int n_prims,
+                     float const *__restrict__ xyz, unsigned const *__restrict__ perm,
+                     float4 const *__restrict__ dense_pts, int const *__restrict__ dense_cell_offsets, int num_dense,
+                     int num_points_dense, int n, float eps, int minpts, int const *__restrict__ num_neigh, int *labels)
 {
   __shared__ unsigned squeue[kDbscanQueue * kThreads];
   if (n_prims < 2)
     return;
-  int const t0 = blockIdx.x * kThreads + threadIdx.x;
-  bool active = t0 < n;
-  // walk the points in the reordered (cell-sorted) order for coherence
-  int const i = (int)perm[active ? t0 : 0];
+  int const s0 = blockIdx.x * kThreads + threadIdx.x;
+  bool active = s0 < n - num_points_dense;
+  int const i = (int)perm[num_points_dense + (active ? s0 : 0)];
   bool const i_core = SPECIAL ? true : (num_neigh[i] >= minpts);
-  if (!i_core)
-    active = false; // border points exit at the first callback (:130-132)
+  if (STAR && !i_core)
+    active = false; // DBSCAN*: border points stay unlabelled
   float const px = xyz[3 * (size_t)i], py = xyz[3 * (size_t)i + 1], pz = xyz[3 * (size_t)i + 2];
   Pred<ABX_PRED_SPHERE3F> pred;
   pred.cx = px, pred.cy = py, pred.cz = pz, pred.r = eps;
   pred.t = sqrtThreshold(eps);
   // rep_i: a (possibly stale) root of i's set -- see fdbscanMainKernel
-  int rep_i = ufRepresentative(labels, i);
+  int rep_i = i_core ? ufRepresentative(labels, i) : -1;
   traverseSpatialDeferred<2, 4, kDbscanQueue>(nodes, leaf_box, pred, active, squeue, [&](unsigned prim, int) {
     int const k = (int)prim;
     if (k < num_dense)
     {
       int const cs = dense_cell_offsets[k], ce = dense_cell_offsets[k + 1];
-      int const first = (int)perm[cs];
-      if (ufLoad(labels, first) == rep_i)
+      if (i_core)
+      {
+        int const first = (int)__float_as_uint(__ldg(dense_pts + cs).w);
+        if (ufLoad(labels, first) == rep_i)
+          return false;
+        if (ufRepresentative(labels, i) == ufRepresentative(labels, first))
+          return false;
+        for (int jj = cs; jj < ce; ++jj)
+        {
+          float4 const pj = __ldg(dense_pts + jj);
+          if (withinEps4(pj, px, py, pz, pred.t))
+          {
+            ufMerge(labels, i, (int)__float_as_uint(pj.w));
+            break;
+          }
+        }
+        rep_i = ufRepresentative(labels, i);
         return false;
-      if (ufRepresentative(labels, i) == ufRepresentative(labels, first))
-        return false;
+      }
+      // border point: it joins the cluster of the first core point found within eps (every point of a dense
+      // cell is core) and stops
       for (int jj = cs; jj < ce; ++jj)
       {
-        int const j = (int)perm[jj];
-        if (ufRepresentative(labels, i) == ufRepresentative(labels, j))
-          break;
-        if (withinEps(xyz, px, py, pz, j, pred.t))
+        float4 const pj = __ldg(dense_pts + jj);
+        if (withinEps4(pj, px, py, pz, pred.t))
         {
-          ufMerge(labels, i, j);
-          break;
+          ufMergeInto(labels, i, (int)__float_as_uint(pj.w));
+          return true;
         }
       }
-      rep_i = ufRepresentative(labels, i);
+      return false;
     }
-    else
+    int const j = (int)perm[num_points_dense + (k - num_dense)];
+    if (j == i)
+      return false;
+    bool const j_core = SPECIAL ? true : (num_neigh[j] >= minpts);
+    if (i_core)
     {
-      int const j = (int)perm[num_points_dense + (k - num_dense)];
-      bool const j_core = SPECIAL ? true : (num_neigh[j] >= minpts);
-      if (j_core && i > j)
+      // core-core pairs are merged by the larger index; border neighbours attach themselves
+      if (j_core && i > j && ufLoad(labels, j) != rep_i)
       {
-        if (ufLoad(labels, j) != rep_i)
-        {
-          ufMerge(labels, i, j);
-          rep_i = ufRepresentative(labels, i);
-        }
+        ufMerge(labels, i, j);
+        rep_i = ufRepresentative(labels, i);
       }
-      else if (!STAR && !j_core)
-        ufMergeInto(labels, j, i);
+      return false;
+    }
+    if (j_core)
+    {
+      ufMergeInto(labels, i, j);
+      return true;
     }
     return false;
   });
@@ -635,6 +823,11 @@ abx_status denseBox(cudaStream_t s, float const *xyz, int n, float eps, int minp
   ABX_TRY(buildTree(s, ABX_PRIM_BOX3F, boxes.ptr, n_prims, nullptr, &tree.t));
   abx_bvh *t = tree.t;
 
+  TempBuffer<float4> dense_pts;
+  ABX_TRY(dense_pts.alloc((size_t)std::max(num_points_dense, 1), s));
+  if (num_points_dense > 0)
+    ABX_LAUNCH(gatherDensePointsKernel, divUp(num_points_dense, 256), 256, 0, s, xyz, perm2.ptr, num_points_dense,
+               dense_pts.ptr);
   TempBuffer<int> num_neigh;
   if (!special)
   {
@@ -643,19 +836,31 @@ abx_status denseBox(cudaStream_t s, float const *xyz, int n, float eps, int minp
       ABX_LAUNCH(markDenseCoreKernel, divUp(num_points_dense, 256), 256, 0, s, perm2.ptr, num_points_dense,
                  num_neigh.ptr);
     if (n_sparse > 0)
-      ABX_LAUNCH(denseCountKernel, divUp(n_sparse, kThreads), kThreads, 0, s, t->nodes, t->leaf_box, n_prims, xyz, perm2.ptr,
-                 dense_cell_offsets.ptr, num_dense, num_points_dense, n, eps, minpts, num_neigh.ptr);
+      ABX_LAUNCH(denseCountKernel, divUp(n_sparse, kThreads), kThreads, 0, s, t->nodes, t->leaf_box, n_prims, xyz,
+                 perm2.ptr, dense_pts.ptr, dense_cell_offsets.ptr, num_dense, num_points_dense, n, eps, minpts,
+                 num_neigh.ptr);
   }
-  int const grid = divUp(n, kThreads);
-  if (special)
-    ABX_LAUNCH((denseMainKernel<true, false>), grid, kThreads, 0, s, t->nodes, t->leaf_box, n_prims, xyz, perm2.ptr,
-               dense_cell_offsets.ptr, num_dense, num_points_dense, n, eps, minpts, (int const *)nullptr, labels);
-  else if (star)
-    ABX_LAUNCH((denseMainKernel<false, true>), grid, kThreads, 0, s, t->nodes, t->leaf_box, n_prims, xyz, perm2.ptr,
-               dense_cell_offsets.ptr, num_dense, num_points_dense, n, eps, minpts, (int const *)num_neigh.ptr, labels);
-  else
-    ABX_LAUNCH((denseMainKernel<false, false>), grid, kThreads, 0, s, t->nodes, t->leaf_box, n_prims, xyz, perm2.ptr,
-               dense_cell_offsets.ptr, num_dense, num_points_dense, n, eps, minpts, (int const *)num_neigh.ptr, labels);
+  // dense cells among themselves: one warp per cell
+  if (num_dense > 1 && n_prims >= 2)
+    ABX_LAUNCH(denseCellPairsKernel, divUp(num_dense, 4), 128, 0, s, t->nodes, boxes.ptr, dense_pts.ptr,
+               dense_cell_offsets.ptr, num_dense, eps, labels);
+  // points of sparse cells: one thread per point
+  if (n_sparse > 0)
+  {
+    int const grid = divUp(n_sparse, kThreads);
+    if (special)
+      ABX_LAUNCH((sparseMainKernel<true, false>), grid, kThreads, 0, s, t->nodes, t->leaf_box, n_prims, xyz, perm2.ptr,
+                 dense_pts.ptr, dense_cell_offsets.ptr, num_dense, num_points_dense, n, eps, minpts,
+                 (int const *)nullptr, labels);
+    else if (star)
+      ABX_LAUNCH((sparseMainKernel<false, true>), grid, kThreads, 0, s, t->nodes, t->leaf_box, n_prims, xyz, perm2.ptr,
+                 dense_pts.ptr, dense_cell_offsets.ptr, num_dense, num_points_dense, n, eps, minpts,
+                 (int const *)num_neigh.ptr, labels);
+    else
+      ABX_LAUNCH((sparseMainKernel<false, false>), grid, kThreads, 0, s, t->nodes, t->leaf_box, n_prims, xyz,
+                 perm2.ptr, dense_pts.ptr, dense_cell_offsets.ptr, num_dense, num_points_dense, n, eps, minpts,
+                 (int const *)num_neigh.ptr, labels);
+  }
   return finalize(s, n, minpts, num_neigh.ptr, labels);
 }
 

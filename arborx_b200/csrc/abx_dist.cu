@@ -455,6 +455,31 @@ __global__ void listRemoteInRowsKernel(int64_t m, int32_t const *__restrict__ id
   }
 }
 
+// pinned host scratch of a tree (count matrices): cudaHostAlloc costs a fraction of a millisecond, and
+// applications build trees inside their time step -- recycled through a small free list
+constexpr size_t kPinnedScratchWords = 64 * 64 + 8;
+std::mutex g_pinned_mutex;
+std::vector<uint32_t *> g_pinned_free;
+abx_status takePinnedScratch(uint32_t **out)
+{
+  {
+    std::lock_guard<std::mutex> lock(g_pinned_mutex);
+    if (!g_pinned_free.empty())
+    {
+      *out = g_pinned_free.back();
+      g_pinned_free.pop_back();
+      return ABX_OK;
+    }
+  }
+  ABX_CUDA_TRY(cudaHostAlloc((void **)out, sizeof(uint32_t) * kPinnedScratchWords, cudaHostAllocPortable));
+  return ABX_OK;
+}
+void returnPinnedScratch(uint32_t *p)
+{
+  std::lock_guard<std::mutex> lock(g_pinned_mutex);
+  g_pinned_free.push_back(p);
+}
+
 int predWords(int kind) { return kind == ABX_PRED_SPHERE3F ? 4 : kind == ABX_PRED_BOX3F ? 6 : 3; }
 int primWords(int kind) { return kind == ABX_PRIM_POINT3F ? 3 : kind == ABX_PRIM_BOX3F ? 6 : 9; }
 
@@ -1120,8 +1145,7 @@ static abx_status distCreate(abx_comm *comm, cudaStream_t s, int prim_kind, void
   }
   ABX_TRY(deviceAlloc((void **)&t->boxes_dev, sizeof(float) * 6 * R, s));
   ABX_CUDA_TRY(cudaMemcpyAsync(t->boxes_dev, t->boxes.data(), sizeof(float) * 6 * R, cudaMemcpyHostToDevice, s));
-  ABX_CUDA_TRY(cudaHostAlloc((void **)&t->h_pin, sizeof(uint32_t) * ((size_t)R * R + 8), cudaHostAllocDefault));
-  ABX_CUDA_TRY(cudaStreamSynchronize(s)); // boxes uploaded from this frame's vector
+  ABX_TRY(takePinnedScratch(&t->h_pin));
   *out = t.release();
   return ABX_OK;
 }
@@ -1168,7 +1192,7 @@ abx_status abx_dist_destroy(abx_dist_tree *t)
     abx_bvh_destroy(t->bottom);
   }
   if (t->h_pin)
-    cudaFreeHost(t->h_pin);
+    returnPinnedScratch(t->h_pin);
   delete t;
   return ABX_OK;
 }

@@ -418,15 +418,15 @@ def run_ours(args):
     hp_spatial_parts = [abx.intersects(h_spheres[bounds[c]:bounds[c + 1]]) for c in range(E2E_CHUNKS)]
     hp_nearest_parts = [abx.nearest(h_queries[bounds[c]:bounds[c + 1]], K_NEIGHBORS) for c in range(E2E_CHUNKS)]
     dist_pools = {"spatial": abx.HostBufferPool(), "nearest": abx.HostBufferPool()}
+    part_pools = [abx.HostBufferPool() for _ in range(2 * E2E_CHUNKS)]
 
     def e2e_task(bvh, preds, slot):
         if not hasattr(e2e_local, "space"):
             torch.cuda.set_device(local_rank)
             e2e_local.space = abx.ExecutionSpace(torch.cuda.Stream())
-            e2e_local.pools = {}
-        # results alias a per-(thread, part) pool of pinned buffers: valid until that part is queried again
-        pool = e2e_local.pools.setdefault(slot, abx.HostBufferPool())
-        idx, off = bvh.query(e2e_local.space, preds, out=pool)
+        # results alias the part's own pool of pinned buffers (one task per part at a time): valid until that
+        # part is queried again
+        idx, off = bvh.query(e2e_local.space, preds, out=part_pools[slot])
         return int(off[-1]), idx.numel()
 
     def e2e_step():

@@ -81,6 +81,28 @@ def test_radius_properties_10m(setup):
     assert torch.equal(lim, torch.clamp(counts, max=3))
 
 
+def test_radius_oracle_sample_10m(setup):
+    """The bench's own radius query (10M spheres of the second cloud, r = cbrt(10 * 6 / pi)) against the oracle on a
+    random sample of 20 000 of those queries: identical index sets per query."""
+    import oracle
+    abx, space, pts_h, pts, bvh = setup
+    r = clouds.bvh_driver_radius(10)
+    qs_h = clouds.filled_box(0x5EED0002, N)
+    spheres_h = np.concatenate([qs_h, np.full((N, 1), r, np.float32)], 1).astype(np.float32)
+    idx, off = bvh.query(space, abx.intersects(torch.from_numpy(spheres_h).cuda()))
+    sel = np.sort(np.random.default_rng(1).choice(N, 20_000, replace=False))
+    roff, ridx = oracle.Tree(pts_h).spatial_crs(spheres_h[sel])
+    off_h = off.cpu().numpy().astype(np.int64)
+    assert np.array_equal(np.diff(roff), (off_h[sel + 1] - off_h[sel]))
+    # gather the sampled rows on the device, compare as sorted rows
+    starts = torch.from_numpy(off_h[sel]).cuda()
+    lens = torch.from_numpy(np.diff(roff).astype(np.int64)).cuda()
+    pos = torch.repeat_interleave(starts - torch.cumsum(lens, 0) + lens, lens) + torch.arange(int(lens.sum()), device="cuda")
+    got = idx[pos].cpu().numpy().view(np.uint32)
+    row = np.repeat(np.arange(len(sel)), np.diff(roff))
+    assert np.array_equal(got[np.lexsort((got, row))], ridx[np.lexsort((ridx, row))])
+
+
 def test_knn_properties_10m(setup):
     abx, space, pts_h, pts, bvh = setup
     k = 10
@@ -112,6 +134,28 @@ def test_knn_properties_10m(setup):
     # queries = values: nearest neighbour of a point is itself at distance 0
     idx0, off0, dist0 = bvh.query(space, abx.make_nearest(pts[:m], 1), return_distances=True)
     assert bool((dist0 == 0).all())
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("minpts", [2, 5])
+def test_dbscan_gantao_vs_oracle(impl, minpts):
+    """ArborX::dbscan on the benchmark's clustered cloud (GanTao, eps = 200) against the oracle at 2M points: the
+    same noise set, the same labels on core points (smallest index of the component), border points accepted by
+    the reference's verifier."""
+    import arborx_b200 as abx
+    import oracle
+    space = abx.ExecutionSpace()
+    n, eps = 2_000_000, 200.0
+    x_h = clouds.gan_tao(3, n)
+    lab = abx.dbscan(space, torch.from_numpy(x_h).cuda(), eps, minpts, abx.DBSCANParameters(impl, 0)).cpu().numpy()
+    ref, core = oracle.dbscan(x_h, eps, minpts, impl, 0, return_core=True)
+    assert np.array_equal(lab == -1, ref == -1)
+    assert np.array_equal(lab[core], ref[core])
+    assert int((lab >= 0).sum()) > n // 2 and len(np.unique(lab[lab >= 0])) == len(np.unique(ref[ref >= 0]))
+    # border points may join any adjacent cluster: checked by the verifier on a 200k-point sub-cloud (it is O(n * m))
+    m = 200_000
+    sub = abx.dbscan(space, torch.from_numpy(x_h[:m].copy()).cuda(), eps, minpts, abx.DBSCANParameters(impl, 0))
+    assert oracle.dbscan_verify(x_h[:m], eps, minpts, sub.cpu().numpy(), 0) == 0
 
 
 def test_dbscan_implementations_agree_10m():
