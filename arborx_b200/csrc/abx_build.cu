@@ -933,6 +933,7 @@ static void destroyTree(abx_bvh *t)
   deviceFree(t->perm, s);
   deviceFree(t->codes, s);
   deviceFree(t->wide, s);
+  deviceFree(t->wide_bad, s);
   deviceFree(t->bounds_dev, s);
   delete t;
 }
@@ -994,101 +995,15 @@ abx_status buildHierarchy(cudaStream_t s, abx_bvh *t, void const *prims)
   return ABX_OK;
 }
 
-// ---- experimental 4-wide nodes (Wide64, abx_common.cuh) ------------------------------------------------------
-// one thread per binary internal node: its children, with internal children of more than kWideRun leaves expanded
+// ---- 4-wide nodes (Wide64, abx_common.cuh) -----------------------------------------------------------------
+// One thread per binary internal node: its children, with internal children of more than kWideRun leaves replaced
+// by their own two children.  Slots 0-1 belong to the left child, 2-3 to the right child; an unexpanded side fills
+// its first slot only.  All indices are compile-time constants, so the twelve child boxes stay in registers.
+// Quantisation: q = floor / ceil of (coordinate - origin) * (1 / scale) with directed rounding, one correction step
+// against the DECODER's arithmetic, and a final containment check with that same arithmetic: a record that is not
+// conservative is counted in *violations and the tree keeps the exact Node64 walk (non-finite boxes end up there).
 __global__ void __launch_bounds__(256) wideConvertKernel(int n, Node64 const *__restrict__ nodes, Wide64 *__restrict__ wide,
                                                        unsigned *__restrict__ violations)
-{
-  int const i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n - 1)
-    return;
-  float lo[4][3], hi[4][3];
-  int ref[4];
-  int m = 0;
-  auto add = [&](float4 const &bl, float4 const &bh, int child_ref, int first, int last) {
-    int const leaves = last - first + 1;
-    lo[m][0] = bl.x, lo[m][1] = bl.y, lo[m][2] = bl.z;
-    hi[m][0] = bh.x, hi[m][1] = bh.y, hi[m][2] = bh.z;
-    ref[m] = leaves <= kWideRun ? ~((first << 2) | (leaves - 1)) : child_ref;
-    ++m;
-  };
-  auto side = [&](float4 const &bl, float4 const &bh, int child_ref, int first, int last) {
-    if (last - first + 1 <= kWideRun)
-    {
-      add(bl, bh, child_ref, first, last);
-      return;
-    }
-    // internal child with more than kWideRun leaves: its two children take its place
-    float4 const *g = reinterpret_cast<float4 const *>(nodes + child_ref);
-    float4 const c0 = ldcg4(g), c1 = ldcg4(g + 1), c2 = ldcg4(g + 2), c3 = ldcg4(g + 3);
-    int const clref = __float_as_int(c0.w), crref = __float_as_int(c1.w);
-    int const crl = __float_as_int(c2.w), crr = __float_as_int(c3.w);
-    add(c0, c1, clref, crl, refIsLeaf(clref) ? crl : clref);
-    add(c2, c3, crref, refIsLeaf(crref) ? crr : crref, crr);
-  };
-  float4 const *f = reinterpret_cast<float4 const *>(nodes + i);
-  float4 const a0 = ldcg4(f), a1 = ldcg4(f + 1), a2 = ldcg4(f + 2), a3 = ldcg4(f + 3);
-  int const lref = __float_as_int(a0.w), rref = __float_as_int(a1.w);
-  int const rl = __float_as_int(a2.w), rr = __float_as_int(a3.w);
-  side(a0, a1, lref, rl, refIsLeaf(lref) ? rl : lref);
-  side(a2, a3, rref, refIsLeaf(rref) ? rr : rref, rr);
-
-  float origin[3], scale[3];
-#pragma unroll
-  for (int d = 0; d < 3; ++d)
-  {
-    float mn = lo[0][d], mx = hi[0][d];
-    for (int k = 1; k < m; ++k)
-    {
-      mn = fminf(mn, lo[k][d]);
-      mx = fmaxf(mx, hi[k][d]);
-    }
-    origin[d] = mn;
-    scale[d] = __fdiv_ru(__fsub_ru(mx, mn), 255.0f);
-  }
-  unsigned q[6] = {0, 0, 0, 0, 0, 0};
-  // boxes with infinite or NaN coordinates cannot be quantised: the tree then keeps the Node64 walk
-  bool bad = !(isfinite(scale[0]) && isfinite(scale[1]) && isfinite(scale[2]) && isfinite(origin[0]) &&
-               isfinite(origin[1]) && isfinite(origin[2]));
-  for (int k = 0; k < m; ++k)
-#pragma unroll
-    for (int d = 0; d < 3; ++d)
-    {
-      int ql = 0, qh = 0;
-      if (scale[d] > 0.f)
-      {
-        ql = min(255, max(0, (int)floorf(__fdiv_rd(__fsub_rd(lo[k][d], origin[d]), scale[d]))));
-        qh = min(255, max(0, (int)ceilf(__fdiv_ru(__fsub_ru(hi[k][d], origin[d]), scale[d]))));
-      }
-      // conservative by construction: checked with the decoder's own arithmetic
-      while (ql > 0 && wideLo((float)ql, scale[d], origin[d]) > lo[k][d])
-        --ql;
-      while (qh < 255 && wideHi((float)qh, scale[d], origin[d]) < hi[k][d])
-        ++qh;
-      bad |= wideLo((float)ql, scale[d], origin[d]) > lo[k][d] || wideHi((float)qh, scale[d], origin[d]) < hi[k][d];
-      int const bl = 6 * k + d, bh = 6 * k + 3 + d;
-      q[bl >> 2] |= (unsigned)ql << (8 * (bl & 3));
-      q[bh >> 2] |= (unsigned)qh << (8 * (bh & 3));
-    }
-  if (bad)
-    atomicAdd(violations, 1u);
-  for (int k = m; k < 4; ++k)
-    ref[k] = kWideEmpty;
-  uint4 *o = wide[i].w;
-  o[0] = make_uint4(__float_as_uint(origin[0]), __float_as_uint(origin[1]), __float_as_uint(origin[2]),
-                    __float_as_uint(scale[0]));
-  o[1] = make_uint4(__float_as_uint(scale[1]), __float_as_uint(scale[2]), q[0], q[1]);
-  o[2] = make_uint4(q[2], q[3], q[4], q[5]);
-  o[3] = make_uint4((unsigned)ref[0], (unsigned)ref[1], (unsigned)ref[2], (unsigned)ref[3]);
-}
-
-// Same records, register-only version (ABX_WIDE_CONVERT=2; written after the round's GPU minutes were spent: it
-// compiles and is meant to replace the kernel above once it has been checked against it).  Slots 0-1 belong to the
-// left child, 2-3 to the right child; an unexpanded side fills its first slot only.  All indices are compile-time
-// constants, so the twelve child boxes live in registers (the kernel above indexes them with a running counter and
-// spills them to local memory: 0.79 ms at 10M nodes against ~0.4 ms of DRAM traffic).
-__global__ void __launch_bounds__(256) wideConvertKernel2(int n, Node64 const *__restrict__ nodes, Wide64 *__restrict__ wide,
-                                                        unsigned *__restrict__ violations)
 {
   int const i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n - 1)
@@ -1123,7 +1038,7 @@ __global__ void __launch_bounds__(256) wideConvertKernel2(int n, Node64 const *_
     else                                                                                                               \
     {                                                                                                                  \
       float4 const *g_ = reinterpret_cast<float4 const *>(nodes + (CHILD_REF));                                        \
-      float4 const c0_ = ldcg4(g_), c1_ = ldcg4(g_ + 1), c2_ = ldcg4(g_ + 2), c3_ = ldcg4(g_ + 3);                     \
+      float4 const c0_ = __ldg(g_), c1_ = __ldg(g_ + 1), c2_ = __ldg(g_ + 2), c3_ = __ldg(g_ + 3);                     \
       int const clref_ = __float_as_int(c0_.w), crref_ = __float_as_int(c1_.w);                                        \
       int const crl_ = __float_as_int(c2_.w), crr_ = __float_as_int(c3_.w);                                            \
       int const cl_hi_ = refIsLeaf(clref_) ? crl_ : clref_;                                                            \
@@ -1133,7 +1048,7 @@ __global__ void __launch_bounds__(256) wideConvertKernel2(int n, Node64 const *_
     }                                                                                                                  \
   } while (0)
   float4 const *f = reinterpret_cast<float4 const *>(nodes + i);
-  float4 const a0 = ldcg4(f), a1 = ldcg4(f + 1), a2 = ldcg4(f + 2), a3 = ldcg4(f + 3);
+  float4 const a0 = __ldg(f), a1 = __ldg(f + 1), a2 = __ldg(f + 2), a3 = __ldg(f + 3);
   int const lref = __float_as_int(a0.w), rref = __float_as_int(a1.w);
   int const rl = __float_as_int(a2.w), rr = __float_as_int(a3.w);
   int const l_hi = refIsLeaf(lref) ? rl : lref;
@@ -1143,7 +1058,7 @@ __global__ void __launch_bounds__(256) wideConvertKernel2(int n, Node64 const *_
 #undef ABX_WIDE_SIDE
 #undef ABX_WIDE_SET
 
-  float origin[3], scale[3];
+  float origin[3], scale[3], inv_dn[3], inv_up[3];
 #pragma unroll
   for (int d = 0; d < 3; ++d)
   {
@@ -1151,6 +1066,9 @@ __global__ void __launch_bounds__(256) wideConvertKernel2(int n, Node64 const *_
     float const mx = fmaxf(fmaxf(hi[0][d], hi[1][d]), fmaxf(hi[2][d], hi[3][d]));
     origin[d] = mn;
     scale[d] = __fdiv_ru(__fsub_ru(mx, mn), 255.0f);
+    bool const pos = scale[d] > 0.f;
+    inv_dn[d] = pos ? __fdiv_rd(1.0f, scale[d]) : 0.f;
+    inv_up[d] = pos ? __fdiv_ru(1.0f, scale[d]) : 0.f;
   }
   bool bad = !(isfinite(scale[0]) && isfinite(scale[1]) && isfinite(scale[2]) && isfinite(origin[0]) &&
                isfinite(origin[1]) && isfinite(origin[2]));
@@ -1163,15 +1081,12 @@ __global__ void __launch_bounds__(256) wideConvertKernel2(int n, Node64 const *_
 #pragma unroll
     for (int d = 0; d < 3; ++d)
     {
-      int ql = 0, qh = 0;
-      if (scale[d] > 0.f)
-      {
-        ql = min(255, max(0, (int)floorf(__fdiv_rd(__fsub_rd(lo[k][d], origin[d]), scale[d]))));
-        qh = min(255, max(0, (int)ceilf(__fdiv_ru(__fsub_ru(hi[k][d], origin[d]), scale[d]))));
-      }
-      while (ql > 0 && wideLo((float)ql, scale[d], origin[d]) > lo[k][d])
+      // estimates from below / above, then one step against the decoder's own arithmetic
+      int ql = min(255, max(0, (int)__fmul_rd(__fsub_rd(lo[k][d], origin[d]), inv_dn[d])));
+      int qh = min(255, max(0, (int)ceilf(__fmul_ru(__fsub_ru(hi[k][d], origin[d]), inv_up[d]))));
+      if (ql > 0 && wideLo((float)ql, scale[d], origin[d]) > lo[k][d])
         --ql;
-      while (qh < 255 && wideHi((float)qh, scale[d], origin[d]) < hi[k][d])
+      if (qh < 255 && wideHi((float)qh, scale[d], origin[d]) < hi[k][d])
         ++qh;
       bad |= wideLo((float)ql, scale[d], origin[d]) > lo[k][d] || wideHi((float)qh, scale[d], origin[d]) < hi[k][d];
       constexpr int kB[4] = {0, 6, 12, 18};
@@ -1190,44 +1105,23 @@ __global__ void __launch_bounds__(256) wideConvertKernel2(int n, Node64 const *_
   o[3] = make_uint4((unsigned)ref[0], (unsigned)ref[1], (unsigned)ref[2], (unsigned)ref[3]);
 }
 
-// built once per tree, on the first query that wants it; blocks until the records are in place
-abx_status ensureWide(cudaStream_t s, abx_bvh *t)
+// written right after the hierarchy, on the build stream; nothing is read back
+static abx_status buildWide(cudaStream_t s, abx_bvh *t)
 {
-  static std::mutex mtx;
-  std::lock_guard<std::mutex> lock(mtx);
-  if (t->wide || t->wide_unsupported || t->n < 2)
-    return ABX_OK;
   int const n = (int)t->n;
-  Wide64 *w = nullptr;
-  ABX_TRY(deviceAlloc((void **)&w, sizeof(Wide64) * (size_t)(n - 1), s));
-  TempBuffer<unsigned> violations;
-  ABX_TRY(violations.alloc(1, s));
-  ABX_CUDA_TRY(cudaMemsetAsync(violations.ptr, 0, sizeof(unsigned), s));
-  static int const convert = [] {
-    char const *e = getenv("ABX_WIDE_CONVERT");
-    return e ? atoi(e) : 1;
-  }();
-  if (convert == 2)
-    ABX_LAUNCH(wideConvertKernel2, divUp(n - 1, 256), 256, 0, s, n, t->nodes, w, violations.ptr);
-  else
-    ABX_LAUNCH(wideConvertKernel, divUp(n - 1, 256), 256, 0, s, n, t->nodes, w, violations.ptr);
-  unsigned h = 0;
-  ABX_CUDA_TRY(cudaMemcpyAsync(&h, violations.ptr, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
-  ABX_CUDA_TRY(cudaStreamSynchronize(s));
-  if (h)
-  {
-    // non-finite boxes (or an encoder bug the check caught): this tree keeps the exact Node64 walk
-    deviceFree(w, s);
-    t->wide_unsupported = true;
+  if (n <= 64 || n >= (1 << 29)) // small trees: nothing to gain; the run encoding needs n < 2^29
     return ABX_OK;
-  }
-  t->wide = w;
+  ABX_TRY(deviceAlloc((void **)&t->wide_bad, sizeof(unsigned), s));
+  ABX_CUDA_TRY(cudaMemsetAsync(t->wide_bad, 0, sizeof(unsigned), s));
+  ABX_TRY(deviceAlloc((void **)&t->wide, sizeof(Wide64) * (size_t)(n - 1), s));
   t->bytes += sizeof(Wide64) * (size_t)(n - 1);
+  ABX_LAUNCH(wideConvertKernel, divUp(n - 1, 256), 256, 0, s, n, t->nodes, t->wide, t->wide_bad);
   return ABX_OK;
 }
 
 // fills a freshly allocated tree; on failure the caller destroys it (every early return below is safe)
-static abx_status buildTreeInto(cudaStream_t s, abx_bvh *t, void const *prims, uint64_t const *sorted_codes)
+static abx_status buildTreeInto(cudaStream_t s, abx_bvh *t, void const *prims, uint64_t const *sorted_codes,
+                                bool want_wide)
 {
   int const kind = t->kind;
   int64_t const n = t->n;
@@ -1287,11 +1181,14 @@ static abx_status buildTreeInto(cudaStream_t s, abx_bvh *t, void const *prims, u
       std::swap(t->perm, perm_alt.ptr);
     }
   }
-  return buildHierarchy(s, t, prims);
+  ABX_TRY(buildHierarchy(s, t, prims));
+  if (want_wide && ABX_TUNE_INT("ABX_WIDE", 1) != 0)
+    ABX_TRY(buildWide(s, t));
+  return ABX_OK;
 }
 
 abx_status buildTree(cudaStream_t s, int kind, void const *prims, int64_t n, uint64_t const *sorted_codes,
-                     abx_bvh **out)
+                     abx_bvh **out, bool want_wide)
 {
   if (kind != ABX_PRIM_POINT3F && kind != ABX_PRIM_BOX3F && kind != ABX_PRIM_TRI3F)
   {
@@ -1313,7 +1210,7 @@ abx_status buildTree(cudaStream_t s, int kind, void const *prims, int64_t n, uin
   t->n = n;
   t->stream = s;
   cudaGetDevice(&t->device);
-  abx_status const st = buildTreeInto(s, t, prims, sorted_codes);
+  abx_status const st = buildTreeInto(s, t, prims, sorted_codes, want_wide);
   if (st != ABX_OK)
   {
     destroyTree(t);

@@ -594,7 +594,7 @@ abx_status abx_bvh_build(void *stream, int prim_kind, const void *prims_dev, int
   }
   *out = nullptr;
   ABX_TRY(ensureDevice());
-  return buildTree((cudaStream_t)stream, prim_kind, prims_dev, n, nullptr, out);
+  return buildTree((cudaStream_t)stream, prim_kind, prims_dev, n, nullptr, out, /*want_wide=*/true);
 }
 
 abx_status abx_bvh_build_host(void *stream, int prim_kind, const void *prims_host, int64_t n, abx_bvh **out)
@@ -617,7 +617,7 @@ abx_status abx_bvh_build_host(void *stream, int prim_kind, const void *prims_hos
   if (n > 0)
     ABX_CUDA_TRY(cudaMemcpyAsync(dev.ptr, prims_host, sizeof(float) * primStride(prim_kind) * (size_t)n,
                                  cudaMemcpyHostToDevice, s));
-  return buildTree(s, prim_kind, dev.ptr, n, nullptr, out);
+  return buildTree(s, prim_kind, dev.ptr, n, nullptr, out, /*want_wide=*/true);
 }
 
 abx_status abx_bvh_build_from_sorted_codes(void *stream, int prim_kind, const void *prims_dev,
@@ -630,7 +630,7 @@ abx_status abx_bvh_build_from_sorted_codes(void *stream, int prim_kind, const vo
   }
   *out = nullptr;
   ABX_TRY(ensureDevice());
-  return buildTree((cudaStream_t)stream, prim_kind, prims_dev, n, sorted_codes_dev, out);
+  return buildTree((cudaStream_t)stream, prim_kind, prims_dev, n, sorted_codes_dev, out, /*want_wide=*/true);
 }
 
 int64_t abx_bvh_size(const abx_bvh *bvh) { return bvh ? bvh->n : 0; }

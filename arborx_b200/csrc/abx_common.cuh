@@ -228,7 +228,7 @@ struct Node64
 };
 static_assert(sizeof(Node64) == 64, "Node64 must be 64 bytes");
 
-// Experimental 4-wide node (ABX_WIDE=1; DESIGN.md "where the time is"): one 64-byte record per internal node of
+// 4-wide node of the spatial query kernels: one 64-byte record per internal node of
 // the binary tree holding up to four children -- the node's grandchildren, or a child itself when that child is a
 // leaf or a subtree of <= 4 leaves (then a "leaf run" of sorted positions).  Child boxes are quantised to 8 bits
 // per coordinate against the node's own box and are CONSERVATIVE (decoded box contains the exact one: the encoder
@@ -318,8 +318,9 @@ struct abx_bvh
   float4 *leaf_tri = nullptr;    // triangles only: 3 float4 per sorted leaf (a, b, c)
   uint32_t *perm = nullptr;      // sorted position -> original index
   uint64_t *codes = nullptr;     // sorted Morton64 codes
-  abx::Wide64 *wide = nullptr;   // experimental 4-wide nodes, built on first use (ABX_WIDE=1)
-  bool wide_unsupported = false; // non-finite boxes: keep the Node64 walk
+  abx::Wide64 *wide = nullptr;   // 4-wide quantised nodes for the spatial kernels (trees built with want_wide)
+  unsigned *wide_bad = nullptr;  // device counter: records the converter could not make conservative (non-finite
+                                 // boxes); non-zero => the kernels keep the Node64 walk
   float *bounds_dev = nullptr;   // 6 floats, root box (scene bounds)
   float bounds_host[6];
   bool bounds_host_valid = false;
@@ -349,8 +350,10 @@ abx_status decodeBounds(cudaStream_t s, unsigned const *bounds_enc6, float *boun
 abx_status morton64(cudaStream_t s, int kind, void const *prims, int64_t n, float const *bounds6, uint64_t *codes);
 abx_status morton32(cudaStream_t s, int pred_kind, void const *preds, int64_t q, float const *bounds6, uint32_t *codes);
 abx_status buildHierarchy(cudaStream_t s, abx_bvh *bvh, void const *prims);
+// want_wide: also write the 4-wide records the spatial query kernels walk (user-facing trees; the trees DBSCAN
+// builds for its own kernels do not need them)
 abx_status buildTree(cudaStream_t s, int kind, void const *prims, int64_t n, uint64_t const *sorted_codes_or_null,
-                     abx_bvh **out);
+                     abx_bvh **out, bool want_wide = false);
 abx_status exportReference(cudaStream_t s, abx_bvh *bvh, int32_t *leaf_rope, uint32_t *leaf_index, int32_t *left_child,
                            int32_t *rope, float *boxes6, uint64_t *codes);
 // query.cu
@@ -374,7 +377,6 @@ abx_status compactRows(cudaStream_t s, int64_t q, int32_t const *old_offsets, in
 abx_status routeLaunch(cudaStream_t s, bool fill, int pred_kind, void const *preds, int64_t q, float const *radius,
                        int64_t radius_stride, float const *boxes6, int R, int self_rank, unsigned *counts,
                        unsigned const *base, unsigned *cursors, int32_t *out_qid);
-abx_status ensureWide(cudaStream_t s, abx_bvh *t);
 abx_status mergeSorted(cudaStream_t s, int64_t q, int32_t const *local_off, int32_t const *local_idx, int rank,
                        int64_t m, int32_t const *remote_ids, int32_t const *remote_vals2, int32_t *out_off,
                        int32_t *out_vals2);

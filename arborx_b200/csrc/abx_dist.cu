@@ -1111,7 +1111,7 @@ static abx_status distCreate(abx_comm *comm, cudaStream_t s, int prim_kind, void
   t->kind = prim_kind;
   int const R = t->R;
   // bottom tree (ArborX_DistributedTree.hpp:183-186)
-  ABX_TRY(buildTree(s, prim_kind, prims_dev, n, nullptr, &t->bottom));
+  ABX_TRY(buildTree(s, prim_kind, prims_dev, n, nullptr, &t->bottom, /*want_wide=*/true));
   // all-gather of (rank box, size) (:208-227, :243-245): 6 floats + a 64-bit count per rank
   TempBuffer<uint32_t> meta, all;
   ABX_TRY(meta.alloc(8, s));

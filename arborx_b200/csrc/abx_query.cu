@@ -34,7 +34,7 @@ enum
   MODE_COMPACT = 3  // staged results -> CRS rows; re-traverses only the queries that overflowed
 };
 constexpr int kPredicateSortBits = 24;
-constexpr int kWideDefault = 0; // 0: Node64 walk; 1: Wide64 walk in the spatial kernels; 2: also in the kNN kernel
+constexpr int kWideDefault = 1; // 1: Wide64 walk in the spatial kernels (r02: stage 4.98 -> 3.76 ms at 10M); 0: Node64
 constexpr int kSpatialVariantDefault = 1; // r01: immediate 5.85 ms; deferred (4,12) 4.89, (4,16) 4.99, (4,8) 4.93, (2,16) 5.75
 // Staging buffer of the single-traversal CRS path: one 128-byte row of kStage slots per query,
 // indexed by the ORIGINAL query id.  CRS rows are in original query order while the traversal
@@ -47,13 +47,16 @@ constexpr int kSpatialVariantDefault = 1; // r01: immediate 5.85 ms; deferred (4
 constexpr int kStage = 32;
 
 // QCAP > 0: deferred leaf tests (traverseSpatialDeferred) with QCAP queue slots per thread
-// WIDE: nodes points at the tree's Wide64 records (experimental, ABX_WIDE=1; needs QCAP > 0)
+// WIDE: walk the tree's 4-wide quantised records (Wide64, half the dependent node loads; needs QCAP >= 5) unless
+// the converter flagged the tree (*wide_bad != 0: non-finite boxes), in which case the Node64 walk runs instead --
+// decided on the device, so no host round trip sits between the build and the first query.
 template <int PRED, int MODE, int LEAF_F4, bool TRI, int BUCKET, int QCAP, bool WIDE = false>
 __global__ void __launch_bounds__(kThreads, ABX_SPATIAL_MINB)
     spatialKernel(Node64 const *__restrict__ nodes, float4 const *__restrict__ leaf_box,
                   float4 const *__restrict__ leaf_tri, int n, float const *__restrict__ preds, int64_t q,
                   unsigned const *__restrict__ qperm, int limit, int32_t *__restrict__ counts,
-                  int32_t const *__restrict__ offsets, uint32_t *__restrict__ indices, uint32_t *__restrict__ staging)
+                  int32_t const *__restrict__ offsets, uint32_t *__restrict__ indices, uint32_t *__restrict__ staging,
+                  Wide64 const *__restrict__ wide, unsigned const *__restrict__ wide_bad)
 {
   __shared__ unsigned squeue[(QCAP > 0 ? QCAP : 1) * kThreads];
   int64_t const t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
@@ -93,9 +96,8 @@ __global__ void __launch_bounds__(kThreads, ABX_SPATIAL_MINB)
     return limit > 0 && count >= limit;
   };
   bool const had_query = active;
-  if (WIDE)
-    traverseWideDeferred<LEAF_F4, (QCAP >= 5 ? QCAP : 5)>(reinterpret_cast<Wide64 const *>(nodes), leaf_box, pred, active,
-                                                          squeue, emit);
+  if (WIDE && __ldg(wide_bad) == 0u)
+    traverseWideDeferred<LEAF_F4, (QCAP >= 5 ? QCAP : 5)>(wide, leaf_box, pred, active, squeue, emit);
   else if (QCAP > 0)
     traverseSpatialDeferred<LEAF_F4, (BUCKET <= 4 ? BUCKET : 4), (QCAP > 0 ? QCAP : 3)>(nodes, leaf_box, pred, active,
                                                                                         squeue, emit);
@@ -253,10 +255,10 @@ constexpr int kNearestBucket = 1; // 1 = leaves only
 // issue slots with 3 of 32 lanes active.  The row is sorted once, at the end, with all lanes
 // converged.  Which of several equal largest distances is replaced is arbitrary: like the
 // reference's heap this only permutes candidates of equal distance.
-// WIDE (experimental, ABX_WIDE=2; kNN parity tests pass, not yet timed): nodes points at the tree's Wide64 records;
-// quantised child boxes give lower bounds of the child distances (enough for ordering and pruning), leaves of a
-// reported run are measured exactly from leaf_box.
-template <int K, int LEAF_F4, bool TRI, bool WIDE = false>
+// (The 4-wide quantised nodes of the spatial kernels were measured here too, r02: 13.9 ms against 10.6 ms at 10M /
+// k = 10 -- decoding four boxes and ranking four children costs more issue slots than the halved chain saves in a
+// kernel that runs at 8 of 32 lanes; the kNN walk stays on Node64.)
+template <int K, int LEAF_F4, bool TRI>
 __global__ void __launch_bounds__(kThreads, (K > 0 && K <= 16) ? ABX_NEAREST_MINB : 1)
     nearestKernel(Node64 const *__restrict__ nodes, float4 const *__restrict__ leaf_box,
                   float4 const *__restrict__ leaf_tri, int n, int prim_kind, float const *__restrict__ pts, int64_t q,
@@ -370,115 +372,12 @@ __global__ void __launch_bounds__(kThreads, (K > 0 && K <= 16) ? ABX_NEAREST_MIN
     }
   };
 
-  // stack of (squared box distance, node) for the farther child (wide: up to three per wide level)
-  unsigned long long stack[WIDE ? 3 * (kStackSize / 2) + 8 : kStackSize];
+  // stack of (squared box distance, node) for the farther child
+  unsigned long long stack[kStackSize];
   int sp = 0;
   int node = 0;
   while (true)
   {
-    if (WIDE)
-    {
-      uint4 const *w = (reinterpret_cast<Wide64 const *>(nodes) + node)->w;
-      uint4 const w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3);
-      float const ox = __uint_as_float(w0.x), oy = __uint_as_float(w0.y), oz = __uint_as_float(w0.z);
-      float const sx = __uint_as_float(w0.w), sy = __uint_as_float(w1.x), sz = __uint_as_float(w1.y);
-      unsigned const qb[6] = {w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
-      int ref[4] = {(int)w3.x, (int)w3.y, (int)w3.z, (int)w3.w};
-      float const inf = __int_as_float(0x7f800000);
-      float dk[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-      {
-        constexpr int kB[4] = {0, 6, 12, 18};
-        int const b = kB[c];
-        float const lx = wideLo(wideByte(qb[(b + 0) >> 2], (b + 0) & 3), sx, ox);
-        float const ly = wideLo(wideByte(qb[(b + 1) >> 2], (b + 1) & 3), sy, oy);
-        float const lz = wideLo(wideByte(qb[(b + 2) >> 2], (b + 2) & 3), sz, oz);
-        float const hx = wideHi(wideByte(qb[(b + 3) >> 2], (b + 3) & 3), sx, ox);
-        float const hy = wideHi(wideByte(qb[(b + 4) >> 2], (b + 4) & 3), sy, oy);
-        float const hz = wideHi(wideByte(qb[(b + 5) >> 2], (b + 5) & 3), sz, oz);
-        dk[c] = ref[c] == kWideEmpty ? inf : pointBoxDist2(px, py, pz, lx, ly, lz, hx, hy, hz);
-      }
-      // leaf runs first: exact distances, the radius may shrink before the internal children are ranked
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-      {
-        if (ref[c] >= 0 || ref[c] == kWideEmpty)
-          continue;
-        if (dk[c] < radius2)
-        {
-          unsigned const run = (unsigned)~ref[c];
-          int const first = (int)(run >> 2), last = first + (int)(run & 3u);
-          for (int j = first; j <= last; ++j)
-          {
-            float d2;
-            unsigned orig;
-            if (LEAF_F4 == 1)
-            {
-              float4 const p = __ldg(leaf_box + j);
-              float tx = __fsub_rn(p.x, px), ty = __fsub_rn(p.y, py), tz = __fsub_rn(p.z, pz);
-              d2 = __fmul_rn(tx, tx);
-              d2 = __fadd_rn(d2, __fmul_rn(ty, ty));
-              d2 = __fadd_rn(d2, __fmul_rn(tz, tz));
-              orig = __float_as_uint(p.w);
-            }
-            else
-            {
-              float4 const l = __ldg(leaf_box + 2 * (size_t)j), h = __ldg(leaf_box + 2 * (size_t)j + 1);
-              d2 = pointBoxDist2v(px, py, pz, l, h);
-              orig = __float_as_uint(l.w);
-            }
-            if (d2 < radius2)
-              offer(d2, orig, j);
-          }
-        }
-        dk[c] = inf; // not a descent candidate
-      }
-      // internal children that may still hold a closer leaf, nearest first (ties: lower slot first)
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        if (!(dk[c] < radius2))
-          dk[c] = inf;
-      auto cswap = [&](int a, int b) {
-        if (dk[b] < dk[a])
-        {
-          float const td = dk[a];
-          dk[a] = dk[b];
-          dk[b] = td;
-          int const tr = ref[a];
-          ref[a] = ref[b];
-          ref[b] = tr;
-        }
-      };
-      cswap(0, 1);
-      cswap(2, 3);
-      cswap(0, 2);
-      cswap(1, 3);
-      cswap(1, 2);
-      if (dk[0] < inf)
-      {
-#pragma unroll
-        for (int c = 3; c >= 1; --c)
-          if (dk[c] < inf)
-            stack[sp++] = ((unsigned long long)__float_as_uint(dk[c]) << 32) | (unsigned)ref[c];
-        node = ref[0];
-        continue;
-      }
-      bool popped_w = false;
-      while (sp > 0)
-      {
-        unsigned long long const e = stack[--sp];
-        if (__uint_as_float((unsigned)(e >> 32)) < radius2)
-        {
-          node = (int)(unsigned)e;
-          popped_w = true;
-          break;
-        }
-      }
-      if (!popped_w)
-        break;
-      continue;
-    }
     float4 const *f = reinterpret_cast<float4 const *>(nodes + node);
     float4 const a0 = __ldg(f), a1 = __ldg(f + 1), a2 = __ldg(f + 2), a3 = __ldg(f + 3);
     int const lref = __float_as_int(a0.w), rref = __float_as_int(a1.w);
@@ -746,23 +645,18 @@ abx_status spatialLaunch(cudaStream_t s, abx_bvh *t, int pred_kind, void const *
   }
   // tuning aid: ABX_SPATIAL_VARIANT picks (leaf-run size, deferred-queue slots); 0 slots = immediate leaf tests
   int const variant = ABX_TUNE_INT("ABX_SPATIAL_VARIANT", kSpatialVariantDefault);
-  // 4-wide nodes (n < 2^29 for the run encoding)
-  int const use_wide = ABX_TUNE_INT("ABX_WIDE", kWideDefault);
-  bool wide = use_wide && n > 64 && n < (1 << 29);
-  if (wide)
-  {
-    ABX_TRY(ensureWide(s, t));
-    wide = t->wide != nullptr;
-  }
+  // 4-wide records, written at build time for trees that asked for them
+  bool const wide = ABX_TUNE_INT("ABX_WIDE", kWideDefault) != 0 && t->wide != nullptr;
 #define ABX_SPATIAL_W(LF4, TRIFLAG)                                                                                   \
   ABX_DISPATCH_PRED(pred_kind,                                                                                         \
                     ABX_LAUNCH_TAGGED(tag, (spatialKernel<P, MODE, LF4, TRIFLAG, 4, 16, true>), grid, kThreads, 0, s,  \
-                                      reinterpret_cast<Node64 const *>(t->wide), t->leaf_box, t->leaf_tri, n,          \
-                                      (float const *)preds, q, qperm, limit, counts, offsets, indices, staging))
+                                      t->nodes, t->leaf_box, t->leaf_tri, n, (float const *)preds, q, qperm, limit,    \
+                                      counts, offsets, indices, staging, t->wide, t->wide_bad))
 #define ABX_SPATIAL_B(LF4, TRIFLAG, B, QC)                                                                            \
   ABX_DISPATCH_PRED(pred_kind, ABX_LAUNCH_TAGGED(tag, (spatialKernel<P, MODE, LF4, TRIFLAG, B, QC>), grid, kThreads,  \
                                                  0, s, t->nodes, t->leaf_box, t->leaf_tri, n, (float const *)preds,   \
-                                                 q, qperm, limit, counts, offsets, indices, staging))
+                                                 q, qperm, limit, counts, offsets, indices, staging,                   \
+                                                 (Wide64 const *)nullptr, (unsigned const *)nullptr))
 #ifdef ABX_TUNING
 #define ABX_SPATIAL_VARIANTS(LF4, TRIFLAG)                                                                            \
   switch (variant)                                                                                                     \
@@ -879,34 +773,9 @@ abx_status nearestQuery(cudaStream_t s, abx_bvh *t, float const *pts, int64_t q,
   int const kmax = k_per_query ? INT_MAX : k; // per-query k: general path
   // DistributedTree rows (pair_rank >= 0) always have k slots: short rows are padded
   int const row_stride = pair_rank >= 0 ? std::max(0, k) : std::max(0, std::min(k, n));
-  // experimental 4-wide nodes for the kNN walk: ABX_WIDE=2 (parity tests pass, not yet timed)
-  int const use_wide = ABX_TUNE_INT("ABX_WIDE", kWideDefault);
-  bool wide = use_wide >= 2 && n > 64 && n < (1 << 29);
-  if (wide)
-  {
-    ABX_TRY(ensureWide(s, t));
-    wide = t->wide != nullptr;
-  }
 #define ABX_NEAREST(KCAP, SCRATCH)                                                                                    \
   do                                                                                                                   \
   {                                                                                                                    \
-    if (wide)                                                                                                          \
-    {                                                                                                                  \
-      Node64 const *wn = reinterpret_cast<Node64 const *>(t->wide);                                                    \
-      if (tri)                                                                                                         \
-        ABX_LAUNCH_TAGGED("nearestKernel<" #KCAP ",tri,wide>", (nearestKernel<KCAP, 2, true, true>), grid, kThreads,  \
-                          0, s, wn, t->leaf_box, t->leaf_tri, n, t->kind, pts, q, qperm, k, row_stride, k_per_query,   \
-                          offsets, counts, indices, distances, SCRATCH, missing, pair_rank);                           \
-      else if (t->kind == ABX_PRIM_BOX3F)                                                                              \
-        ABX_LAUNCH_TAGGED("nearestKernel<" #KCAP ",box,wide>", (nearestKernel<KCAP, 2, false, true>), grid, kThreads, \
-                          0, s, wn, t->leaf_box, t->leaf_tri, n, t->kind, pts, q, qperm, k, row_stride, k_per_query,   \
-                          offsets, counts, indices, distances, SCRATCH, missing, pair_rank);                           \
-      else                                                                                                             \
-        ABX_LAUNCH_TAGGED("nearestKernel<" #KCAP ",wide>", (nearestKernel<KCAP, 1, false, true>), grid, kThreads, 0,  \
-                          s, wn, t->leaf_box, t->leaf_tri, n, t->kind, pts, q, qperm, k, row_stride, k_per_query,      \
-                          offsets, counts, indices, distances, SCRATCH, missing, pair_rank);                           \
-      break;                                                                                                           \
-    }                                                                                                                  \
     if (tri)                                                                                                           \
       ABX_LAUNCH_TAGGED("nearestKernel<" #KCAP ",tri>", (nearestKernel<KCAP, 2, true>), grid, kThreads, 0, s,          \
                         t->nodes, t->leaf_box, t->leaf_tri, n, t->kind, pts, q, qperm, k, row_stride, k_per_query,     \
