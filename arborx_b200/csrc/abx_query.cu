@@ -15,6 +15,9 @@
 #ifndef ABX_NEAREST_MINB
 #define ABX_NEAREST_MINB 12 // 40 registers: 10.6 ms at 10M / k = 10 (1: 48 regs 11.2 ms, 16: 32 regs 10.8 ms)
 #endif
+#ifndef ABX_NEAREST_CHUNK_MINB
+#define ABX_NEAREST_CHUNK_MINB 10 // 48 registers: the chunked kernel carries the chunk bookkeeping (40 spills)
+#endif
 #ifndef ABX_SPATIAL_MINB
 #define ABX_SPATIAL_MINB 1
 #endif
@@ -246,6 +249,12 @@ struct GlobalHeap
 // K > 0: register list of exactly K candidates (the first min(k, found) are
 // reported; K >= k).  K == 0: global heap with run-time k.
 constexpr int kNearestBucket = 1; // 1 = leaves only
+template <int K>
+struct ChunkK // the chunked kernel exists for K >= 1 only (K = 0 is the global-heap form)
+{
+  static constexpr int value = K >= 1 ? K : 1;
+};
+constexpr int kKnnChunkDefault = 0; // sorted queries per warp of the chunked exact-K kernel; 0: one query per lane
 
 // Candidate set of the K > 0 path: K (distance, index) slots per thread in shared memory,
 // UNSORTED, plus the position and value of the largest distance in registers.  The traversal
@@ -292,13 +301,7 @@ __global__ void __launch_bounds__(kThreads, (K > 0 && K <= 16) ? ABX_NEAREST_MIN
     if (pair_rank >= 0)
     {
       reinterpret_cast<int2 *>(indices)[base] = make_int2(0, pair_rank);
-      for (int i = 1; i < row_stride; ++i) // DistributedTree rows are padded to k entries
-      {
-        reinterpret_cast<int2 *>(indices)[base + i] = make_int2(-1, -1);
-        if (distances)
-          distances[base + i] = __int_as_float(0x7f800000);
-      }
-      if (missing && row_stride > 1)
+      if (missing && row_stride > 1) // DistributedTree rows have k slots: the rest is padding (padShortRowsKernel)
         atomicAdd(missing, (unsigned long long)(row_stride - 1));
     }
     else
@@ -505,20 +508,230 @@ __global__ void __launch_bounds__(kThreads, (K > 0 && K <= 16) ? ABX_NEAREST_MIN
   }
   if (counts)
     counts[qi] = found;
-  int const expected = offsets ? (offsets[qi + 1] - (int)base) : row_stride;
-  if (found < expected)
+  if (missing)
   {
-    if (missing)
+    int const expected = offsets ? (offsets[qi + 1] - (int)base) : row_stride;
+    if (found < expected)
       atomicAdd(missing, (unsigned long long)(expected - found));
-    if (pair_rank >= 0)
-      // DistributedTree rows: pad to the full row (index -1, distance +inf) so that candidates from
-      // other ranks can be merged in place
-      for (int i = found; i < expected; ++i)
+  }
+}
+
+// DistributedTree rows ((index, rank) pairs, k slots per query): slots behind the counts[i] entries found are
+// padded with (-1, -1) / +inf so that candidates from other ranks can be merged in place.  Kept out of the
+// traversal kernel: short rows are rare (fewer than k reachable leaves) and the walk should not carry the code.
+__global__ void padShortRowsKernel(int64_t q, int k, int32_t const *__restrict__ counts, int2 *__restrict__ vals2,
+                                   float *__restrict__ dist)
+{
+  int64_t const i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= q)
+    return;
+  for (int j = counts[i]; j < k; ++j)
+  {
+    vals2[i * k + j] = make_int2(-1, -1);
+    if (dist)
+      dist[i * k + j] = __int_as_float(0x7f800000);
+  }
+}
+
+// ---- chunked form of the exact-K kernel ------------------------------------------------------------
+// ncu (profiles/r01_ncu_v5_summary.md, per-line): the walk above runs at 10 of 32 lanes -- the queries of a warp
+// need very different numbers of node visits (the slowest takes about three times the mean) and the lanes that are
+// done wait for it.  Here a warp owns CHUNK consecutive (Morton-sorted) queries instead of 32: a lane that finishes
+// a query stores its candidate set UNSORTED in the query's output row and takes the next query of the warp's chunk
+// (neighbours in Morton order, so the lanes keep walking the same subtrees).  Sorting a row as soon as its query
+// ends would run at one or two lanes, so all rows of the chunk are sorted at the end with the warp converged:
+// the unsorted (squared distance, index) entries are read back, ranked in registers and rewritten in place.
+// Uniform k, n >= 2; `dist` is never null (the host passes a scratch array when the caller wants no distances).
+template <int K, int LEAF_F4, bool TRI, int CHUNK>
+__global__ void __launch_bounds__(kThreads, (K <= 16) ? ABX_NEAREST_CHUNK_MINB : 1)
+    nearestChunkKernel(Node64 const *__restrict__ nodes, float4 const *__restrict__ leaf_box,
+                       float4 const *__restrict__ leaf_tri, float const *__restrict__ pts, int64_t q,
+                       unsigned const *__restrict__ qperm, int k, int row_stride, int32_t *__restrict__ counts,
+                       uint32_t *indices, float *dist, bool write_dist, unsigned long long *__restrict__ missing,
+                       int pair_rank)
+{
+  constexpr int kWarps = kThreads / 32;
+  static_assert(CHUNK % 32 == 0 && CHUNK <= 255, "found counts are bytes");
+  __shared__ float set_d[K * kThreads];
+  __shared__ unsigned set_i[K * kThreads];
+  __shared__ int next_slot[kWarps];
+  __shared__ unsigned char found_s[kWarps][CHUNK];
+  int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int64_t const chunk0 = ((int64_t)blockIdx.x * kWarps + warp) * CHUNK;
+  if (chunk0 >= q)
+    return; // the whole warp
+  int const count = (int)min((int64_t)CHUNK, q - chunk0);
+  float *const my_d = set_d + threadIdx.x;
+  unsigned *const my_i = set_i + threadIdx.x;
+  float const inf = __int_as_float(0x7f800000);
+  if (lane == 0)
+    next_slot[warp] = 32;
+  __syncwarp();
+
+  int slot = lane;
+  int64_t qi = 0;
+  float px = 0.f, py = 0.f, pz = 0.f;
+  int found = 0, worst = 0;
+  float radius2 = inf;
+  auto start = [&](int sl) {
+    qi = qperm ? (int64_t)qperm[chunk0 + sl] : chunk0 + sl;
+    px = pts[3 * qi], py = pts[3 * qi + 1], pz = pts[3 * qi + 2];
+    found = 0;
+    worst = 0;
+    radius2 = inf;
+  };
+  auto offer = [&](float d2, unsigned idx, int pos) {
+    if (TRI)
+    {
+      d2 = pointTriangleDist2(px, py, pz, __ldg(leaf_tri + 3 * (size_t)pos), __ldg(leaf_tri + 3 * (size_t)pos + 1),
+                              __ldg(leaf_tri + 3 * (size_t)pos + 2));
+      if (!(d2 < radius2))
+        return;
+    }
+    int const s = found < K ? found : worst;
+    my_d[s * kThreads] = d2;
+    my_i[s * kThreads] = idx;
+    if (found < K)
+      ++found;
+    if (found == K)
+    {
+      float m = my_d[0];
+      int p = 0;
+#pragma unroll
+      for (int j = 1; j < K; ++j)
       {
-        reinterpret_cast<int2 *>(indices)[base + i] = make_int2(-1, -1);
-        if (distances)
-          distances[base + i] = __int_as_float(0x7f800000);
+        float const v = my_d[j * kThreads];
+        if (v > m)
+        {
+          m = v;
+          p = j;
+        }
       }
+      radius2 = m;
+      worst = p;
+    }
+  };
+
+  if (slot < count)
+  {
+    start(slot);
+    unsigned long long stack[kStackSize];
+    int sp = 0;
+    int node = 0;
+    while (true)
+    {
+      float4 const *f = reinterpret_cast<float4 const *>(nodes + node);
+      float4 const a0 = __ldg(f), a1 = __ldg(f + 1), a2 = __ldg(f + 2), a3 = __ldg(f + 3);
+      int const lref = __float_as_int(a0.w), rref = __float_as_int(a1.w);
+      int const rl = __float_as_int(a2.w), rr = __float_as_int(a3.w);
+      float const dl = pointBoxDist2v(px, py, pz, a0, a1);
+      float const dr = pointBoxDist2v(px, py, pz, a2, a3);
+      bool const l_leaf = refIsLeaf(lref), r_leaf = refIsLeaf(rref);
+      // leaf children are consumed on the spot, nearer one first (one shared call site per slot)
+      bool const swap = l_leaf && r_leaf && dr < dl;
+      bool const first_is_left = l_leaf && !swap;
+      if (l_leaf || r_leaf)
+      {
+        float const d = first_is_left ? dl : dr;
+        if (d < radius2)
+          offer(d, refOrig(first_is_left ? lref : rref), first_is_left ? rl : rr);
+      }
+      if (l_leaf && r_leaf)
+      {
+        float const d = swap ? dl : dr;
+        if (d < radius2)
+          offer(d, refOrig(swap ? lref : rref), swap ? rl : rr);
+      }
+      bool const go_l = !l_leaf && dl < radius2;
+      bool const go_r = !r_leaf && dr < radius2;
+      if (go_l || go_r)
+      {
+        // nearer child first; left on ties (TreeTraversal.hpp:310-313)
+        bool const left_first = go_l && (dl <= dr || !go_r);
+        if (go_l && go_r)
+        {
+          float const fd = left_first ? dr : dl;
+          int const fn = left_first ? rref : lref;
+          stack[sp++] = ((unsigned long long)__float_as_uint(fd) << 32) | (unsigned)fn;
+        }
+        node = left_first ? lref : rref;
+        continue;
+      }
+      bool popped = false;
+      while (sp > 0)
+      {
+        unsigned long long const e = stack[--sp];
+        if (__uint_as_float((unsigned)(e >> 32)) < radius2)
+        {
+          node = (int)(unsigned)e;
+          popped = true;
+          break;
+        }
+      }
+      if (popped)
+        continue;
+      // this query is done: park its candidates (unsorted, squared distances) in its output row ...
+      int64_t const base = qi * (int64_t)row_stride;
+      for (int j = 0; j < found; ++j)
+      {
+        if (pair_rank >= 0)
+          reinterpret_cast<int2 *>(indices)[base + j].x = (int)my_i[j * kThreads];
+        else
+          indices[base + j] = my_i[j * kThreads];
+        dist[base + j] = my_d[j * kThreads];
+      }
+      found_s[warp][slot] = (unsigned char)found;
+      // ... and take the next query of the warp's chunk
+      slot = atomicAdd(&next_slot[warp], 1);
+      if (slot >= count)
+        break;
+      start(slot);
+      sp = 0;
+      node = 0;
+    }
+  }
+  __syncwarp();
+
+  // all rows of the chunk: rank the parked candidates, rewrite the row in place
+  for (int sl = lane; sl < count; sl += 32)
+  {
+    int64_t const qj = qperm ? (int64_t)qperm[chunk0 + sl] : chunk0 + sl;
+    int64_t const base = qj * (int64_t)row_stride;
+    int const f = found_s[warp][sl];
+    RegList<K> list;
+    list.init();
+#pragma unroll 1
+    for (int j = 0; j < f; ++j)
+    {
+      unsigned const id = pair_rank >= 0 ? (unsigned)reinterpret_cast<int2 const *>(indices)[base + j].x : indices[base + j];
+      list.insert(dist[base + j], id);
+    }
+    int const m = min(f, k);
+#pragma unroll
+    for (int i = 0; i < K; ++i)
+      if (i < m)
+      {
+        if (pair_rank >= 0)
+          reinterpret_cast<int2 *>(indices)[base + i] = make_int2((int)list.id[i], pair_rank);
+        else
+          indices[base + i] = list.id[i];
+        if (write_dist)
+          dist[base + i] = __fsqrt_rn(list.d[i]);
+      }
+    if (counts)
+      counts[qj] = m;
+    if (m < row_stride)
+    {
+      if (missing)
+        atomicAdd(missing, (unsigned long long)(row_stride - m));
+      if (pair_rank >= 0)
+        for (int i = m; i < row_stride; ++i)
+        {
+          reinterpret_cast<int2 *>(indices)[base + i] = make_int2(-1, -1);
+          if (write_dist)
+            dist[base + i] = inf;
+        }
+    }
   }
 }
 
@@ -773,9 +986,57 @@ abx_status nearestQuery(cudaStream_t s, abx_bvh *t, float const *pts, int64_t q,
   int const kmax = k_per_query ? INT_MAX : k; // per-query k: general path
   // DistributedTree rows (pair_rank >= 0) always have k slots: short rows are padded
   int const row_stride = pair_rank >= 0 ? std::max(0, k) : std::max(0, std::min(k, n));
+  TempBuffer<int32_t> counts_tmp;
+  if (pair_rank >= 0 && !counts)
+  {
+    ABX_TRY(counts_tmp.alloc((size_t)q, s));
+    counts = counts_tmp.ptr;
+  }
+  // chunked exact-K kernel (a warp owns kKnnChunk sorted queries): uniform k <= 32, n >= 2
+  int const chunk = (kmax <= 32 && n >= 2) ? ABX_TUNE_INT("ABX_KNN_CHUNK", kKnnChunkDefault) : 0;
+  TempBuffer<float> dist_scratch;
+  float *dist_stage = distances;
+  if (chunk > 0 && !distances)
+  {
+    ABX_TRY(dist_scratch.alloc((size_t)std::max<int64_t>(total_rows, 1), s));
+    dist_stage = dist_scratch.ptr;
+  }
+  int const cgrid = divUp(q, (int64_t)std::max(chunk, 32) * (kThreads / 32));
+#define ABX_NEAREST_CHUNK_C(KCAP, CH)                                                                                 \
+  do                                                                                                                   \
+  {                                                                                                                    \
+    if (tri)                                                                                                           \
+      ABX_LAUNCH_TAGGED("nearestChunkKernel<tri>", (nearestChunkKernel<KCAP, 2, true, CH>), cgrid, kThreads, \
+                        0, s, t->nodes, t->leaf_box, t->leaf_tri, pts, q, qperm, k, row_stride, counts, indices,       \
+                        dist_stage, distances != nullptr, missing, pair_rank);                                         \
+    else if (t->kind == ABX_PRIM_BOX3F)                                                                                \
+      ABX_LAUNCH_TAGGED("nearestChunkKernel<box>", (nearestChunkKernel<KCAP, 2, false, CH>), cgrid,          \
+                        kThreads, 0, s, t->nodes, t->leaf_box, t->leaf_tri, pts, q, qperm, k, row_stride, counts,      \
+                        indices, dist_stage, distances != nullptr, missing, pair_rank);                                \
+    else                                                                                                               \
+      ABX_LAUNCH_TAGGED("nearestChunkKernel", (nearestChunkKernel<KCAP, 1, false, CH>), cgrid, kThreads, 0, \
+                        s, t->nodes, t->leaf_box, t->leaf_tri, pts, q, qperm, k, row_stride, counts, indices,          \
+                        dist_stage, distances != nullptr, missing, pair_rank);                                         \
+  } while (0)
+#ifdef ABX_TUNING
+#define ABX_NEAREST_CHUNK(KCAP)                                                                                       \
+  if (chunk == 128)                                                                                                    \
+    ABX_NEAREST_CHUNK_C(KCAP, 128);                                                                                    \
+  else if (chunk == 96)                                                                                                \
+    ABX_NEAREST_CHUNK_C(KCAP, 96);                                                                                     \
+  else                                                                                                                 \
+    ABX_NEAREST_CHUNK_C(KCAP, 64)
+#else
+#define ABX_NEAREST_CHUNK(KCAP) ABX_NEAREST_CHUNK_C(KCAP, (kKnnChunkDefault > 0 ? kKnnChunkDefault : 64))
+#endif
 #define ABX_NEAREST(KCAP, SCRATCH)                                                                                    \
   do                                                                                                                   \
   {                                                                                                                    \
+    if (chunk > 0 && KCAP > 0)                                                                                         \
+    {                                                                                                                  \
+      ABX_NEAREST_CHUNK(ChunkK<KCAP>::value);                                                                          \
+      break;                                                                                                           \
+    }                                                                                                                  \
     if (tri)                                                                                                           \
       ABX_LAUNCH_TAGGED("nearestKernel<" #KCAP ",tri>", (nearestKernel<KCAP, 2, true>), grid, kThreads, 0, s,          \
                         t->nodes, t->leaf_box, t->leaf_tri, n, t->kind, pts, q, qperm, k, row_stride, k_per_query,     \
@@ -824,6 +1085,10 @@ abx_status nearestQuery(cudaStream_t s, abx_bvh *t, float const *pts, int64_t q,
     ABX_NEAREST(0, scratch.ptr);
   }
 #undef ABX_NEAREST
+#undef ABX_NEAREST_CHUNK
+#undef ABX_NEAREST_CHUNK_C
+  if (pair_rank >= 0 && chunk == 0 && row_stride > 0)
+    ABX_LAUNCH(padShortRowsKernel, divUp(q, 256), 256, 0, s, q, row_stride, counts, (int2 *)indices, distances);
   return ABX_OK;
 }
 
