@@ -934,6 +934,8 @@ static void destroyTree(abx_bvh *t)
   deviceFree(t->codes, s);
   deviceFree(t->wide, s);
   deviceFree(t->wide_bad, s);
+  if (t->wide_ready)
+    cudaEventDestroy(t->wide_ready);
   deviceFree(t->bounds_dev, s);
   delete t;
 }
@@ -1105,17 +1107,31 @@ __global__ void __launch_bounds__(256) wideConvertKernel(int n, Node64 const *__
   o[3] = make_uint4((unsigned)ref[0], (unsigned)ref[1], (unsigned)ref[2], (unsigned)ref[3]);
 }
 
-// written right after the hierarchy, on the build stream; nothing is read back
-static abx_status buildWide(cudaStream_t s, abx_bvh *t)
+// Written by the first spatial query of a tree that was built with want_wide (kNN-only users never pay for the
+// records), on that query's stream; nothing is read back -- a tree whose boxes cannot be quantised is flagged on the
+// device and the kernels fall back by themselves.  Queries on other streams wait for the conversion through an event.
+abx_status ensureWide(cudaStream_t s, abx_bvh *t)
 {
-  int const n = (int)t->n;
-  if (n <= 64 || n >= (1 << 29)) // small trees: nothing to gain; the run encoding needs n < 2^29
+  if (!t->want_wide)
     return ABX_OK;
-  ABX_TRY(deviceAlloc((void **)&t->wide_bad, sizeof(unsigned), s));
-  ABX_CUDA_TRY(cudaMemsetAsync(t->wide_bad, 0, sizeof(unsigned), s));
-  ABX_TRY(deviceAlloc((void **)&t->wide, sizeof(Wide64) * (size_t)(n - 1), s));
-  t->bytes += sizeof(Wide64) * (size_t)(n - 1);
-  ABX_LAUNCH(wideConvertKernel, divUp(n - 1, 256), 256, 0, s, n, t->nodes, t->wide, t->wide_bad);
+  static std::mutex mtx;
+  std::lock_guard<std::mutex> lock(mtx);
+  if (!t->wide)
+  {
+    int const n = (int)t->n;
+    ABX_TRY(deviceAlloc((void **)&t->wide_bad, sizeof(unsigned), s));
+    ABX_CUDA_TRY(cudaMemsetAsync(t->wide_bad, 0, sizeof(unsigned), s));
+    Wide64 *w = nullptr;
+    ABX_TRY(deviceAlloc((void **)&w, sizeof(Wide64) * (size_t)(n - 1), s));
+    ABX_LAUNCH(wideConvertKernel, divUp(n - 1, 256), 256, 0, s, n, t->nodes, w, t->wide_bad);
+    ABX_CUDA_TRY(cudaEventCreateWithFlags(&t->wide_ready, cudaEventDisableTiming));
+    ABX_CUDA_TRY(cudaEventRecord(t->wide_ready, s));
+    t->wide_stream = s;
+    t->bytes += sizeof(Wide64) * (size_t)(n - 1);
+    t->wide = w; // published last
+  }
+  else if (s != t->wide_stream)
+    ABX_CUDA_TRY(cudaStreamWaitEvent(s, t->wide_ready, 0));
   return ABX_OK;
 }
 
@@ -1182,8 +1198,8 @@ static abx_status buildTreeInto(cudaStream_t s, abx_bvh *t, void const *prims, u
     }
   }
   ABX_TRY(buildHierarchy(s, t, prims));
-  if (want_wide && ABX_TUNE_INT("ABX_WIDE", 1) != 0)
-    ABX_TRY(buildWide(s, t));
+  // trees of more than 64 leaves may get 4-wide records on their first spatial query (n < 2^29: run encoding)
+  t->want_wide = want_wide && n > 64 && n < ((int64_t)1 << 29);
   return ABX_OK;
 }
 

@@ -318,7 +318,10 @@ struct abx_bvh
   float4 *leaf_tri = nullptr;    // triangles only: 3 float4 per sorted leaf (a, b, c)
   uint32_t *perm = nullptr;      // sorted position -> original index
   uint64_t *codes = nullptr;     // sorted Morton64 codes
-  abx::Wide64 *wide = nullptr;   // 4-wide quantised nodes for the spatial kernels (trees built with want_wide)
+  bool want_wide = false;        // user-facing tree: the first spatial query writes the 4-wide records
+  cudaEvent_t wide_ready = nullptr; // recorded behind the conversion kernel
+  cudaStream_t wide_stream = nullptr;
+  abx::Wide64 *wide = nullptr;   // 4-wide quantised nodes for the spatial kernels
   unsigned *wide_bad = nullptr;  // device counter: records the converter could not make conservative (non-finite
                                  // boxes); non-zero => the kernels keep the Node64 walk
   float *bounds_dev = nullptr;   // 6 floats, root box (scene bounds)
@@ -354,6 +357,7 @@ abx_status buildHierarchy(cudaStream_t s, abx_bvh *bvh, void const *prims);
 // builds for its own kernels do not need them)
 abx_status buildTree(cudaStream_t s, int kind, void const *prims, int64_t n, uint64_t const *sorted_codes_or_null,
                      abx_bvh **out, bool want_wide = false);
+abx_status ensureWide(cudaStream_t s, abx_bvh *t);
 abx_status exportReference(cudaStream_t s, abx_bvh *bvh, int32_t *leaf_rope, uint32_t *leaf_index, int32_t *left_child,
                            int32_t *rope, float *boxes6, uint64_t *codes);
 // query.cu

@@ -15,8 +15,8 @@
 #ifndef ABX_NEAREST_MINB
 #define ABX_NEAREST_MINB 12 // 40 registers: 10.6 ms at 10M / k = 10 (1: 48 regs 11.2 ms, 16: 32 regs 10.8 ms)
 #endif
-#ifndef ABX_NEAREST_CHUNK_MINB
-#define ABX_NEAREST_CHUNK_MINB 10 // 48 registers: the chunked kernel carries the chunk bookkeeping (40 spills)
+#ifndef ABX_NEAREST_DREG_MINB
+#define ABX_NEAREST_DREG_MINB 10 // 48 registers for the form with the candidate distances in registers
 #endif
 #ifndef ABX_SPATIAL_MINB
 #define ABX_SPATIAL_MINB 1
@@ -249,12 +249,8 @@ struct GlobalHeap
 // K > 0: register list of exactly K candidates (the first min(k, found) are
 // reported; K >= k).  K == 0: global heap with run-time k.
 constexpr int kNearestBucket = 1; // 1 = leaves only
-template <int K>
-struct ChunkK // the chunked kernel exists for K >= 1 only (K = 0 is the global-heap form)
-{
-  static constexpr int value = K >= 1 ? K : 1;
-};
-constexpr int kKnnChunkDefault = 0; // sorted queries per warp of the chunked exact-K kernel; 0: one query per lane
+constexpr int kSmemStack = 8;      // stack entries per thread kept in shared memory by the VAR = 2 form
+constexpr int kKnnDregDefault = 0; // 1: exact-K kernels (k <= 16) keep the candidate distances in registers
 
 // Candidate set of the K > 0 path: K (distance, index) slots per thread in shared memory,
 // UNSORTED, plus the position and value of the largest distance in registers.  The traversal
@@ -264,11 +260,21 @@ constexpr int kKnnChunkDefault = 0; // sorted queries per warp of the chunked ex
 // issue slots with 3 of 32 lanes active.  The row is sorted once, at the end, with all lanes
 // converged.  Which of several equal largest distances is replaced is arbitrary: like the
 // reference's heap this only permutes candidates of equal distance.
-// (The 4-wide quantised nodes of the spatial kernels were measured here too, r02: 13.9 ms against 10.6 ms at 10M /
-// k = 10 -- decoding four boxes and ranking four children costs more issue slots than the halved chain saves in a
-// kernel that runs at 8 of 32 lanes; the kNN walk stays on Node64.)
-template <int K, int LEAF_F4, bool TRI>
-__global__ void __launch_bounds__(kThreads, (K > 0 && K <= 16) ? ABX_NEAREST_MINB : 1)
+// Measured and rejected in round 2 (profiles/r02_validate_wide.log, r02_knn_chunk_experiment.log; 10M / k = 10,
+// this kernel 10.6 ms): the 4-wide quantised nodes of the spatial kernels 13.9 ms (decoding four boxes and ranking
+// four children costs more than the halved chain saves); a chunked form where a warp owns 64 / 96 / 128 sorted
+// queries and a finished lane takes the next one (rows ranked at the end, converged) 14.2 / 15.3 / 15.8 ms.  ncu
+// says why: the L1 data pipe is at 85 % of its peak (l1tex__data_pipe_lsu_wavefronts), so what counts is the
+// number of distinct cache lines a warp's loads touch -- lanes that walk neighbouring queries in lock step share
+// them, lanes that drift apart do not.
+// DREG: the K candidate distances live in registers (static indices: the slot to overwrite is selected with K
+// predicated moves, the new largest distance falls out of the same pass) and only the indices stay in shared
+// memory.  The shared-memory form re-reads its K slots after every replacement, and those loads are a fifth of the
+// L1 data-pipe wavefronts of a kernel whose L1 data pipe is the busiest unit (85 %).
+// VAR = 2: DREG, and the first kSmemStack entries of the traversal stack in shared memory (the stack in local
+// memory hits L1 19 % of the time and is written back to DRAM: 2.4 GB per 10M queries).
+template <int K, int LEAF_F4, bool TRI, int VAR = 0>
+__global__ void __launch_bounds__(kThreads, (K > 0 && K <= 16) ? (VAR ? ABX_NEAREST_DREG_MINB : ABX_NEAREST_MINB) : 1)
     nearestKernel(Node64 const *__restrict__ nodes, float4 const *__restrict__ leaf_box,
                   float4 const *__restrict__ leaf_tri, int n, int prim_kind, float const *__restrict__ pts, int64_t q,
                   unsigned const *__restrict__ qperm, int k_uniform, int row_stride,
@@ -314,11 +320,20 @@ __global__ void __launch_bounds__(kThreads, (K > 0 && K <= 16) ? ABX_NEAREST_MIN
   }
 
   constexpr bool USE_REGS = K > 0;
+  constexpr bool DREG = VAR >= 1;
+  constexpr int SSTK = VAR == 2 ? kSmemStack : 0;
   constexpr int KS = USE_REGS ? K : 1;
   __shared__ float set_d[KS * kThreads];
   __shared__ unsigned set_i[KS * kThreads];
   float *const my_d = set_d + threadIdx.x; // slot j at my_d[j * kThreads]: conflict-free across the warp
   unsigned *const my_i = set_i + threadIdx.x;
+  float dreg[DREG ? KS : 1];
+  if (DREG)
+  {
+#pragma unroll
+    for (int j = 0; j < KS; ++j)
+      dreg[j] = -1.f;
+  }
   int worst = 0; // slot holding the largest distance once the set is full
   GlobalHeap heap;
   heap.h = nullptr;
@@ -337,7 +352,32 @@ __global__ void __launch_bounds__(kThreads, (K > 0 && K <= 16) ? ABX_NEAREST_MIN
       if (!(d2 < radius2))
         return;
     }
-    if (USE_REGS)
+    if (USE_REGS && DREG)
+    {
+      int const slot = found < KS ? found : worst;
+      my_i[slot * kThreads] = idx;
+      float m = -1.f;
+      int p = 0;
+#pragma unroll
+      for (int j = 0; j < KS; ++j)
+      {
+        float const x = j == slot ? d2 : dreg[j];
+        dreg[j] = x;
+        if (x > m)
+        {
+          m = x;
+          p = j;
+        }
+      }
+      if (found < KS)
+        ++found;
+      if (found == KS) // unfilled slots hold -1: they never win the maximum once the set is full
+      {
+        radius2 = m;
+        worst = p;
+      }
+    }
+    else if (USE_REGS)
     {
       // d2 < radius2 here; radius2 stays +inf until K candidates are known
       int const slot = found < KS ? found : worst;
@@ -376,7 +416,17 @@ __global__ void __launch_bounds__(kThreads, (K > 0 && K <= 16) ? ABX_NEAREST_MIN
   };
 
   // stack of (squared box distance, node) for the farther child
-  unsigned long long stack[kStackSize];
+  unsigned long long stack[kStackSize - SSTK];
+  __shared__ unsigned long long sstack[(SSTK ? SSTK : 1) * kThreads];
+  auto push = [&](int at, unsigned long long e) {
+    if (SSTK && at < SSTK)
+      sstack[at * kThreads + threadIdx.x] = e;
+    else
+      stack[at - SSTK] = e;
+  };
+  auto top = [&](int at) -> unsigned long long {
+    return (SSTK && at < SSTK) ? sstack[at * kThreads + threadIdx.x] : stack[at - SSTK];
+  };
   int sp = 0;
   int node = 0;
   while (true)
@@ -448,7 +498,7 @@ __global__ void __launch_bounds__(kThreads, (K > 0 && K <= 16) ? ABX_NEAREST_MIN
       {
         float const fd = left_first ? dr : dl;
         int const fn = left_first ? rref : lref;
-        stack[sp++] = ((unsigned long long)__float_as_uint(fd) << 32) | (unsigned)fn;
+        push(sp++, ((unsigned long long)__float_as_uint(fd) << 32) | (unsigned)fn);
       }
       node = left_first ? lref : rref;
       continue;
@@ -457,7 +507,7 @@ __global__ void __launch_bounds__(kThreads, (K > 0 && K <= 16) ? ABX_NEAREST_MIN
     bool popped = false;
     while (sp > 0)
     {
-      unsigned long long const e = stack[--sp];
+      unsigned long long const e = top(--sp);
       if (__uint_as_float((unsigned)(e >> 32)) < radius2)
       {
         node = (int)(unsigned)e;
@@ -474,9 +524,19 @@ __global__ void __launch_bounds__(kThreads, (K > 0 && K <= 16) ? ABX_NEAREST_MIN
     // sort the row: insertion into a register list, in slot order (all lanes are here together)
     RegList<KS> list;
     list.init();
+    if (DREG)
+    {
+#pragma unroll
+      for (int j = 0; j < KS; ++j)
+        if (j < found)
+          list.insert(dreg[j], my_i[j * kThreads]);
+    }
+    else
+    {
 #pragma unroll 1
-    for (int j = 0; j < found; ++j)
-      list.insert(my_d[j * kThreads], my_i[j * kThreads]);
+      for (int j = 0; j < found; ++j)
+        list.insert(my_d[j * kThreads], my_i[j * kThreads]);
+    }
     int const m = min(min(found, k), USE_REGS ? K : 1);
 #pragma unroll
     for (int i = 0; i < (USE_REGS ? K : 1); ++i)
@@ -530,208 +590,6 @@ __global__ void padShortRowsKernel(int64_t q, int k, int32_t const *__restrict__
     vals2[i * k + j] = make_int2(-1, -1);
     if (dist)
       dist[i * k + j] = __int_as_float(0x7f800000);
-  }
-}
-
-// ---- chunked form of the exact-K kernel ------------------------------------------------------------
-// ncu (profiles/r01_ncu_v5_summary.md, per-line): the walk above runs at 10 of 32 lanes -- the queries of a warp
-// need very different numbers of node visits (the slowest takes about three times the mean) and the lanes that are
-// done wait for it.  Here a warp owns CHUNK consecutive (Morton-sorted) queries instead of 32: a lane that finishes
-// a query stores its candidate set UNSORTED in the query's output row and takes the next query of the warp's chunk
-// (neighbours in Morton order, so the lanes keep walking the same subtrees).  Sorting a row as soon as its query
-// ends would run at one or two lanes, so all rows of the chunk are sorted at the end with the warp converged:
-// the unsorted (squared distance, index) entries are read back, ranked in registers and rewritten in place.
-// Uniform k, n >= 2; `dist` is never null (the host passes a scratch array when the caller wants no distances).
-template <int K, int LEAF_F4, bool TRI, int CHUNK>
-__global__ void __launch_bounds__(kThreads, (K <= 16) ? ABX_NEAREST_CHUNK_MINB : 1)
-    nearestChunkKernel(Node64 const *__restrict__ nodes, float4 const *__restrict__ leaf_box,
-                       float4 const *__restrict__ leaf_tri, float const *__restrict__ pts, int64_t q,
-                       unsigned const *__restrict__ qperm, int k, int row_stride, int32_t *__restrict__ counts,
-                       uint32_t *indices, float *dist, bool write_dist, unsigned long long *__restrict__ missing,
-                       int pair_rank)
-{
-  constexpr int kWarps = kThreads / 32;
-  static_assert(CHUNK % 32 == 0 && CHUNK <= 255, "found counts are bytes");
-  __shared__ float set_d[K * kThreads];
-  __shared__ unsigned set_i[K * kThreads];
-  __shared__ int next_slot[kWarps];
-  __shared__ unsigned char found_s[kWarps][CHUNK];
-  int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int64_t const chunk0 = ((int64_t)blockIdx.x * kWarps + warp) * CHUNK;
-  if (chunk0 >= q)
-    return; // the whole warp
-  int const count = (int)min((int64_t)CHUNK, q - chunk0);
-  float *const my_d = set_d + threadIdx.x;
-  unsigned *const my_i = set_i + threadIdx.x;
-  float const inf = __int_as_float(0x7f800000);
-  if (lane == 0)
-    next_slot[warp] = 32;
-  __syncwarp();
-
-  int slot = lane;
-  int64_t qi = 0;
-  float px = 0.f, py = 0.f, pz = 0.f;
-  int found = 0, worst = 0;
-  float radius2 = inf;
-  auto start = [&](int sl) {
-    qi = qperm ? (int64_t)qperm[chunk0 + sl] : chunk0 + sl;
-    px = pts[3 * qi], py = pts[3 * qi + 1], pz = pts[3 * qi + 2];
-    found = 0;
-    worst = 0;
-    radius2 = inf;
-  };
-  auto offer = [&](float d2, unsigned idx, int pos) {
-    if (TRI)
-    {
-      d2 = pointTriangleDist2(px, py, pz, __ldg(leaf_tri + 3 * (size_t)pos), __ldg(leaf_tri + 3 * (size_t)pos + 1),
-                              __ldg(leaf_tri + 3 * (size_t)pos + 2));
-      if (!(d2 < radius2))
-        return;
-    }
-    int const s = found < K ? found : worst;
-    my_d[s * kThreads] = d2;
-    my_i[s * kThreads] = idx;
-    if (found < K)
-      ++found;
-    if (found == K)
-    {
-      float m = my_d[0];
-      int p = 0;
-#pragma unroll
-      for (int j = 1; j < K; ++j)
-      {
-        float const v = my_d[j * kThreads];
-        if (v > m)
-        {
-          m = v;
-          p = j;
-        }
-      }
-      radius2 = m;
-      worst = p;
-    }
-  };
-
-  if (slot < count)
-  {
-    start(slot);
-    unsigned long long stack[kStackSize];
-    int sp = 0;
-    int node = 0;
-    while (true)
-    {
-      float4 const *f = reinterpret_cast<float4 const *>(nodes + node);
-      float4 const a0 = __ldg(f), a1 = __ldg(f + 1), a2 = __ldg(f + 2), a3 = __ldg(f + 3);
-      int const lref = __float_as_int(a0.w), rref = __float_as_int(a1.w);
-      int const rl = __float_as_int(a2.w), rr = __float_as_int(a3.w);
-      float const dl = pointBoxDist2v(px, py, pz, a0, a1);
-      float const dr = pointBoxDist2v(px, py, pz, a2, a3);
-      bool const l_leaf = refIsLeaf(lref), r_leaf = refIsLeaf(rref);
-      // leaf children are consumed on the spot, nearer one first (one shared call site per slot)
-      bool const swap = l_leaf && r_leaf && dr < dl;
-      bool const first_is_left = l_leaf && !swap;
-      if (l_leaf || r_leaf)
-      {
-        float const d = first_is_left ? dl : dr;
-        if (d < radius2)
-          offer(d, refOrig(first_is_left ? lref : rref), first_is_left ? rl : rr);
-      }
-      if (l_leaf && r_leaf)
-      {
-        float const d = swap ? dl : dr;
-        if (d < radius2)
-          offer(d, refOrig(swap ? lref : rref), swap ? rl : rr);
-      }
-      bool const go_l = !l_leaf && dl < radius2;
-      bool const go_r = !r_leaf && dr < radius2;
-      if (go_l || go_r)
-      {
-        // nearer child first; left on ties (TreeTraversal.hpp:310-313)
-        bool const left_first = go_l && (dl <= dr || !go_r);
-        if (go_l && go_r)
-        {
-          float const fd = left_first ? dr : dl;
-          int const fn = left_first ? rref : lref;
-          stack[sp++] = ((unsigned long long)__float_as_uint(fd) << 32) | (unsigned)fn;
-        }
-        node = left_first ? lref : rref;
-        continue;
-      }
-      bool popped = false;
-      while (sp > 0)
-      {
-        unsigned long long const e = stack[--sp];
-        if (__uint_as_float((unsigned)(e >> 32)) < radius2)
-        {
-          node = (int)(unsigned)e;
-          popped = true;
-          break;
-        }
-      }
-      if (popped)
-        continue;
-      // this query is done: park its candidates (unsorted, squared distances) in its output row ...
-      int64_t const base = qi * (int64_t)row_stride;
-      for (int j = 0; j < found; ++j)
-      {
-        if (pair_rank >= 0)
-          reinterpret_cast<int2 *>(indices)[base + j].x = (int)my_i[j * kThreads];
-        else
-          indices[base + j] = my_i[j * kThreads];
-        dist[base + j] = my_d[j * kThreads];
-      }
-      found_s[warp][slot] = (unsigned char)found;
-      // ... and take the next query of the warp's chunk
-      slot = atomicAdd(&next_slot[warp], 1);
-      if (slot >= count)
-        break;
-      start(slot);
-      sp = 0;
-      node = 0;
-    }
-  }
-  __syncwarp();
-
-  // all rows of the chunk: rank the parked candidates, rewrite the row in place
-  for (int sl = lane; sl < count; sl += 32)
-  {
-    int64_t const qj = qperm ? (int64_t)qperm[chunk0 + sl] : chunk0 + sl;
-    int64_t const base = qj * (int64_t)row_stride;
-    int const f = found_s[warp][sl];
-    RegList<K> list;
-    list.init();
-#pragma unroll 1
-    for (int j = 0; j < f; ++j)
-    {
-      unsigned const id = pair_rank >= 0 ? (unsigned)reinterpret_cast<int2 const *>(indices)[base + j].x : indices[base + j];
-      list.insert(dist[base + j], id);
-    }
-    int const m = min(f, k);
-#pragma unroll
-    for (int i = 0; i < K; ++i)
-      if (i < m)
-      {
-        if (pair_rank >= 0)
-          reinterpret_cast<int2 *>(indices)[base + i] = make_int2((int)list.id[i], pair_rank);
-        else
-          indices[base + i] = list.id[i];
-        if (write_dist)
-          dist[base + i] = __fsqrt_rn(list.d[i]);
-      }
-    if (counts)
-      counts[qj] = m;
-    if (m < row_stride)
-    {
-      if (missing)
-        atomicAdd(missing, (unsigned long long)(row_stride - m));
-      if (pair_rank >= 0)
-        for (int i = m; i < row_stride; ++i)
-        {
-          reinterpret_cast<int2 *>(indices)[base + i] = make_int2(-1, -1);
-          if (write_dist)
-            dist[base + i] = inf;
-        }
-    }
   }
 }
 
@@ -858,8 +716,13 @@ abx_status spatialLaunch(cudaStream_t s, abx_bvh *t, int pred_kind, void const *
   }
   // tuning aid: ABX_SPATIAL_VARIANT picks (leaf-run size, deferred-queue slots); 0 slots = immediate leaf tests
   int const variant = ABX_TUNE_INT("ABX_SPATIAL_VARIANT", kSpatialVariantDefault);
-  // 4-wide records, written at build time for trees that asked for them
-  bool const wide = ABX_TUNE_INT("ABX_WIDE", kWideDefault) != 0 && t->wide != nullptr;
+  // 4-wide records, written by the first spatial query of a user-facing tree
+  bool wide = ABX_TUNE_INT("ABX_WIDE", kWideDefault) != 0 && t->want_wide;
+  if (wide)
+  {
+    ABX_TRY(ensureWide(s, t));
+    wide = t->wide != nullptr;
+  }
 #define ABX_SPATIAL_W(LF4, TRIFLAG)                                                                                   \
   ABX_DISPATCH_PRED(pred_kind,                                                                                         \
                     ABX_LAUNCH_TAGGED(tag, (spatialKernel<P, MODE, LF4, TRIFLAG, 4, 16, true>), grid, kThreads, 0, s,  \
@@ -992,51 +855,49 @@ abx_status nearestQuery(cudaStream_t s, abx_bvh *t, float const *pts, int64_t q,
     ABX_TRY(counts_tmp.alloc((size_t)q, s));
     counts = counts_tmp.ptr;
   }
-  // chunked exact-K kernel (a warp owns kKnnChunk sorted queries): uniform k <= 32, n >= 2
-  int const chunk = (kmax <= 32 && n >= 2) ? ABX_TUNE_INT("ABX_KNN_CHUNK", kKnnChunkDefault) : 0;
-  TempBuffer<float> dist_scratch;
-  float *dist_stage = distances;
-  if (chunk > 0 && !distances)
-  {
-    ABX_TRY(dist_scratch.alloc((size_t)std::max<int64_t>(total_rows, 1), s));
-    dist_stage = dist_scratch.ptr;
-  }
-  int const cgrid = divUp(q, (int64_t)std::max(chunk, 32) * (kThreads / 32));
-#define ABX_NEAREST_CHUNK_C(KCAP, CH)                                                                                 \
+  int const dreg = ABX_TUNE_INT("ABX_KNN_DREG", kKnnDregDefault);
+#define ABX_NEAREST_D(KCAP, SCRATCH)                                                                                  \
   do                                                                                                                   \
   {                                                                                                                    \
     if (tri)                                                                                                           \
-      ABX_LAUNCH_TAGGED("nearestChunkKernel<tri>", (nearestChunkKernel<KCAP, 2, true, CH>), cgrid, kThreads, \
-                        0, s, t->nodes, t->leaf_box, t->leaf_tri, pts, q, qperm, k, row_stride, counts, indices,       \
-                        dist_stage, distances != nullptr, missing, pair_rank);                                         \
+      ABX_LAUNCH_TAGGED("nearestKernel<" #KCAP ",tri,dreg>", (nearestKernel<KCAP, 2, true, 1>), grid, kThreads, 0, \
+                        s, t->nodes, t->leaf_box, t->leaf_tri, n, t->kind, pts, q, qperm, k, row_stride, k_per_query,  \
+                        offsets, counts, indices, distances, SCRATCH, missing, pair_rank);                             \
     else if (t->kind == ABX_PRIM_BOX3F)                                                                                \
-      ABX_LAUNCH_TAGGED("nearestChunkKernel<box>", (nearestChunkKernel<KCAP, 2, false, CH>), cgrid,          \
-                        kThreads, 0, s, t->nodes, t->leaf_box, t->leaf_tri, pts, q, qperm, k, row_stride, counts,      \
-                        indices, dist_stage, distances != nullptr, missing, pair_rank);                                \
+      ABX_LAUNCH_TAGGED("nearestKernel<" #KCAP ",box,dreg>", (nearestKernel<KCAP, 2, false, 1>), grid, kThreads,   \
+                        0, s, t->nodes, t->leaf_box, t->leaf_tri, n, t->kind, pts, q, qperm, k, row_stride,            \
+                        k_per_query, offsets, counts, indices, distances, SCRATCH, missing, pair_rank);                \
     else                                                                                                               \
-      ABX_LAUNCH_TAGGED("nearestChunkKernel", (nearestChunkKernel<KCAP, 1, false, CH>), cgrid, kThreads, 0, \
-                        s, t->nodes, t->leaf_box, t->leaf_tri, pts, q, qperm, k, row_stride, counts, indices,          \
-                        dist_stage, distances != nullptr, missing, pair_rank);                                         \
+      ABX_LAUNCH_TAGGED("nearestKernel<" #KCAP ",dreg>", (nearestKernel<KCAP, 1, false, 1>), grid, kThreads, 0, s, \
+                        t->nodes, t->leaf_box, t->leaf_tri, n, t->kind, pts, q, qperm, k, row_stride, k_per_query,     \
+                        offsets, counts, indices, distances, SCRATCH, missing, pair_rank);                             \
   } while (0)
-#ifdef ABX_TUNING
-#define ABX_NEAREST_CHUNK(KCAP)                                                                                       \
-  if (chunk == 128)                                                                                                    \
-    ABX_NEAREST_CHUNK_C(KCAP, 128);                                                                                    \
-  else if (chunk == 96)                                                                                                \
-    ABX_NEAREST_CHUNK_C(KCAP, 96);                                                                                     \
-  else                                                                                                                 \
-    ABX_NEAREST_CHUNK_C(KCAP, 64)
+#if defined(ABX_TUNING)
+#define ABX_NEAREST_PICK(KCAP, SCRATCH)                                                                               \
+  if (dreg == 2 && KCAP > 0 && KCAP <= 16 && !tri && t->kind == ABX_PRIM_POINT3F)                                      \
+  {                                                                                                                    \
+    ABX_LAUNCH_TAGGED("nearestKernel<" #KCAP ",dreg,sstack>", (nearestKernel<KCAP, 1, false, 2>), grid, kThreads, 0,  \
+                      s, t->nodes, t->leaf_box, t->leaf_tri, n, t->kind, pts, q, qperm, k, row_stride, k_per_query,    \
+                      offsets, counts, indices, distances, SCRATCH, missing, pair_rank);                               \
+    break;                                                                                                             \
+  }                                                                                                                    \
+  if (dreg && KCAP > 0 && KCAP <= 16)                                                                                  \
+  {                                                                                                                    \
+    ABX_NEAREST_D(KCAP, SCRATCH);                                                                                      \
+    break;                                                                                                             \
+  }
 #else
-#define ABX_NEAREST_CHUNK(KCAP) ABX_NEAREST_CHUNK_C(KCAP, (kKnnChunkDefault > 0 ? kKnnChunkDefault : 64))
+#define ABX_NEAREST_PICK(KCAP, SCRATCH)                                                                               \
+  if (kKnnDregDefault && KCAP > 0 && KCAP <= 16)                                                                       \
+  {                                                                                                                    \
+    ABX_NEAREST_D(KCAP, SCRATCH);                                                                                      \
+    break;                                                                                                             \
+  }
 #endif
 #define ABX_NEAREST(KCAP, SCRATCH)                                                                                    \
   do                                                                                                                   \
   {                                                                                                                    \
-    if (chunk > 0 && KCAP > 0)                                                                                         \
-    {                                                                                                                  \
-      ABX_NEAREST_CHUNK(ChunkK<KCAP>::value);                                                                          \
-      break;                                                                                                           \
-    }                                                                                                                  \
+    ABX_NEAREST_PICK(KCAP, SCRATCH)                                                                                    \
     if (tri)                                                                                                           \
       ABX_LAUNCH_TAGGED("nearestKernel<" #KCAP ",tri>", (nearestKernel<KCAP, 2, true>), grid, kThreads, 0, s,          \
                         t->nodes, t->leaf_box, t->leaf_tri, n, t->kind, pts, q, qperm, k, row_stride, k_per_query,     \
@@ -1085,9 +946,10 @@ abx_status nearestQuery(cudaStream_t s, abx_bvh *t, float const *pts, int64_t q,
     ABX_NEAREST(0, scratch.ptr);
   }
 #undef ABX_NEAREST
-#undef ABX_NEAREST_CHUNK
-#undef ABX_NEAREST_CHUNK_C
-  if (pair_rank >= 0 && chunk == 0 && row_stride > 0)
+#undef ABX_NEAREST_PICK
+#undef ABX_NEAREST_D
+  (void)dreg;
+  if (pair_rank >= 0 && row_stride > 0)
     ABX_LAUNCH(padShortRowsKernel, divUp(q, 256), 256, 0, s, q, row_stride, counts, (int2 *)indices, distances);
   return ABX_OK;
 }
