@@ -480,6 +480,10 @@ void returnPinnedScratch(uint32_t *p)
   g_pinned_free.push_back(p);
 }
 
+// forwarded batches below this size are traversed in arrival order (already grouped by source rank and, inside a
+// source, by the sender's routing order): six launches of Morton ordering cost more than they return
+constexpr int64_t kSortForwardedAbove = 32768;
+
 int predWords(int kind) { return kind == ABX_PRED_SPHERE3F ? 4 : kind == ABX_PRED_BOX3F ? 6 : 3; }
 int primWords(int kind) { return kind == ABX_PRIM_POINT3F ? 3 : kind == ABX_PRIM_BOX3F ? 6 : 9; }
 
@@ -707,7 +711,9 @@ abx_status distSpatial(abx_dist_tree *t, cudaStream_t s, int pred_kind, void con
     int32_t *off_r = nullptr;
     uint32_t *idx_r = nullptr;
     int64_t nnz_r = 0;
-    ABX_TRY(spatialCrs(t->bottom, s, pred_kind, fwd_preds.ptr, G, policy, nullptr, nullptr, &off_r, &idx_r, &nnz_r,
+    abx_policy remote_policy = policy;
+    remote_policy.sort_predicates = G >= kSortForwardedAbove;
+    ABX_TRY(spatialCrs(t->bottom, s, pred_kind, fwd_preds.ptr, G, remote_policy, nullptr, nullptr, &off_r, &idx_r, &nnz_r,
                        [&]() -> abx_status {
                          // runs right after the scan of the remote query's offsets
                          ABX_LAUNCH(segmentTotalsKernel, 1, 64, 0, s, off_r, starts.ptr, R, counts.ptr);
@@ -811,21 +817,42 @@ abx_status distNearest(abx_dist_tree *t, cudaStream_t s, void const *pts, int64_
     return ABX_ERR_ARG;
   }
   int64_t const slots = (int64_t)k * q;
-  // 1. local k nearest of every point, rows of k slots in (index, rank) form, padded when short
+  // 1. local k nearest of every point, rows of k slots in (index, rank) form, padded when short.  In the pairs
+  // form the rows ARE the caller's output arrays (rows are full unless a row stays short: handled at the end).
   TempBuffer<int32_t> rows;
   TempBuffer<float> rows_d;
-  ABX_TRY(rows.alloc((size_t)std::max<int64_t>(slots, 1) * 2, s));
-  ABX_TRY(rows_d.alloc((size_t)std::max<int64_t>(slots, 1), s));
+  void *off_v = nullptr, *vals_v = nullptr, *d_v = nullptr;
+  int32_t *rows_p = nullptr;
+  float *rowsd_p = nullptr;
+  if (!compact)
+  {
+    ABX_TRY(allocOutDev(alloc, user, 0, sizeof(int32_t) * (size_t)(q + 1), s, &off_v));
+    ABX_TRY(allocOutDev(alloc, user, 1, val_bytes * (size_t)slots, s, &vals_v));
+    if (want_dist)
+      ABX_TRY(allocOutDev(alloc, user, 2, sizeof(float) * (size_t)slots, s, &d_v));
+    rows_p = (int32_t *)vals_v;
+    rowsd_p = (float *)d_v;
+  }
+  else
+  {
+    ABX_TRY(rows.alloc((size_t)std::max<int64_t>(slots, 1) * 2, s));
+    rows_p = rows.ptr;
+  }
+  if (!rowsd_p)
+  {
+    ABX_TRY(rows_d.alloc((size_t)std::max<int64_t>(slots, 1), s));
+    rowsd_p = rows_d.ptr;
+  }
   TempBuffer<unsigned long long> missing;
   ABX_TRY(missing.alloc(1, s));
   ABX_CUDA_TRY(cudaMemsetAsync(missing.ptr, 0, sizeof(unsigned long long), s));
-  ABX_TRY(localKnnPairs(t->bottom, s, pts, q, k, t->rank, rows.ptr, rows_d.ptr, missing.ptr));
+  ABX_TRY(localKnnPairs(t->bottom, s, pts, q, k, t->rank, rows_p, rowsd_p, missing.ptr));
   // 2. phase II routing: sphere (point, local k-th distance); an infinite bound reaches every rank
   TempBuffer<uint32_t> counts, matrix;
   ABX_TRY(counts.alloc(R, s));
   ABX_TRY(matrix.alloc((size_t)R * R, s));
   ABX_CUDA_TRY(cudaMemsetAsync(counts.ptr, 0, sizeof(uint32_t) * R, s));
-  float const *radius = rows_d.ptr + (k - 1);
+  float const *radius = rowsd_p + (k - 1);
   ABX_TRY(routeLaunch(s, false, ABX_PRED_SPHERE3F, pts, q, radius, k, t->boxes_dev, R, t->rank, counts.ptr, nullptr,
                       nullptr, nullptr));
   ABX_TRY(gatherCountMatrix(t, s, counts.ptr, matrix.ptr));
@@ -858,7 +885,7 @@ abx_status distNearest(abx_dist_tree *t, cudaStream_t s, void const *pts, int64_
     ABX_CUDA_TRY(cudaMemsetAsync(r_counts.ptr, 0, sizeof(int32_t) * ((size_t)G + 1), s));
     if (G > 0 && nloc > 0)
     {
-      if (nloc > 1)
+      if (nloc > 1 && G >= kSortForwardedAbove)
         ABX_TRY(predicatePermutation(s, t->bottom, ABX_PRED_POINT3F, fwd_pts.ptr, G, qperm));
       ABX_TRY(nearestQuery(s, t->bottom, (float const *)fwd_pts.ptr, G, k, nullptr, qperm.ptr, nullptr, G * stride,
                            r_counts.ptr, r_idx.ptr, r_dist.ptr));
@@ -893,7 +920,7 @@ abx_status distNearest(abx_dist_tree *t, cudaStream_t s, void const *pts, int64_
     ABX_TRY(t->comm->allToAllV(cols, 3, back.send_off.data(), back.recv_off.data(), s));
     ABX_TRY(sortReceived(t, s, M, q, back, got_ids, got_idx.ptr, got_dist.ptr, rvals2, rdist));
     // 5. final ranking (DistributedTreeNearest.hpp:178-233): the k smallest of local row + candidates
-    ABX_TRY(knnMerge(s, M, got_ids.ptr, rvals2.ptr, rdist.ptr, k, rows.ptr, rows_d.ptr));
+    ABX_TRY(knnMerge(s, M, got_ids.ptr, rvals2.ptr, rdist.ptr, k, rows_p, rowsd_p));
   }
   // 6. outputs.  Rows are full (k entries) unless some local row was short and stayed short.
   TempBuffer<int32_t> row_counts, row_off;
@@ -906,7 +933,7 @@ abx_status distNearest(abx_dist_tree *t, cudaStream_t s, void const *pts, int64_
     TempBuffer<unsigned long long> total64;
     ABX_TRY(total64.alloc(1, s));
     if (q > 0)
-      ABX_LAUNCH(countValidKernel, divUp(q, 256), 256, 0, s, q, k, (int2 const *)rows.ptr, row_counts.ptr);
+      ABX_LAUNCH(countValidKernel, divUp(q, 256), 256, 0, s, q, k, (int2 const *)rows_p, row_counts.ptr);
     ABX_TRY(exclusiveScanI32(s, row_counts.ptr, row_off.ptr, q + 1, total64.ptr));
     unsigned long long h_total = 0;
     ABX_CUDA_TRY(cudaMemcpyAsync(&h_total, total64.ptr, sizeof(h_total), cudaMemcpyDeviceToHost, s));
@@ -914,11 +941,33 @@ abx_status distNearest(abx_dist_tree *t, cudaStream_t s, void const *pts, int64_
     nnz = (int64_t)h_total;
     short_rows = nnz != slots;
   }
-  void *off_v = nullptr, *vals_v = nullptr, *d_v = nullptr;
-  ABX_TRY(allocOutDev(alloc, user, 0, sizeof(int32_t) * (size_t)(q + 1), s, &off_v));
-  ABX_TRY(allocOutDev(alloc, user, 1, val_bytes * (size_t)nnz, s, &vals_v));
-  if (want_dist)
-    ABX_TRY(allocOutDev(alloc, user, 2, sizeof(float) * (size_t)nnz, s, &d_v));
+  TempBuffer<int32_t> keep_rows;
+  TempBuffer<float> keep_d;
+  if (!compact && short_rows)
+  {
+    // the padded rows sit in the caller's arrays, which the allocator is about to replace: set them aside
+    ABX_TRY(keep_rows.alloc((size_t)slots * 2, s));
+    ABX_TRY(keep_d.alloc((size_t)slots, s));
+    ABX_CUDA_TRY(cudaMemcpyAsync(keep_rows.ptr, rows_p, 2 * sizeof(int32_t) * (size_t)slots, cudaMemcpyDeviceToDevice, s));
+    ABX_CUDA_TRY(cudaMemcpyAsync(keep_d.ptr, rowsd_p, sizeof(float) * (size_t)slots, cudaMemcpyDeviceToDevice, s));
+    ABX_CUDA_TRY(cudaStreamSynchronize(s)); // the allocator may release the previous views
+    if (!alloc)
+    {
+      deviceFree(off_v, s);
+      deviceFree(vals_v, s);
+      deviceFree(d_v, s);
+    }
+    rows_p = keep_rows.ptr;
+    rowsd_p = keep_d.ptr;
+    off_v = vals_v = d_v = nullptr;
+  }
+  if (!off_v)
+  {
+    ABX_TRY(allocOutDev(alloc, user, 0, sizeof(int32_t) * (size_t)(q + 1), s, &off_v));
+    ABX_TRY(allocOutDev(alloc, user, 1, val_bytes * (size_t)nnz, s, &vals_v));
+    if (want_dist)
+      ABX_TRY(allocOutDev(alloc, user, 2, sizeof(float) * (size_t)nnz, s, &d_v));
+  }
   *offsets_out = (int32_t *)off_v;
   *values_out = vals_v;
   if (dist_out)
@@ -928,27 +977,27 @@ abx_status distNearest(abx_dist_tree *t, cudaStream_t s, void const *pts, int64_
     ABX_CUDA_TRY(cudaMemcpyAsync(off_v, row_off.ptr, sizeof(int32_t) * (size_t)(q + 1), cudaMemcpyDeviceToDevice, s));
   else
     ABX_LAUNCH(fillStrideOffsetsKernel, divUp(q + 1, 256), 256, 0, s, (int32_t *)off_v, q + 1, k);
-  // rows -> output values (pairs or indices), compacted when rows are short
+  // rows -> output values: nothing to do for full rows in the pairs form (they were written in place)
+  int2 const *src_rows = (int2 const *)rows_p;
+  float const *src_d = rowsd_p;
   TempBuffer<int32_t> packed;
   TempBuffer<float> packed_d;
-  int2 const *src_rows = (int2 const *)rows.ptr;
-  float const *src_d = rows_d.ptr;
-  if (short_rows)
+  if (short_rows && compact)
   {
     ABX_TRY(packed.alloc((size_t)std::max<int64_t>(nnz, 1) * 2, s));
     ABX_TRY(packed_d.alloc((size_t)std::max<int64_t>(nnz, 1), s));
     if (q > 0)
-      ABX_LAUNCH(compactPaddedRowsKernel, divUp(q, 256), 256, 0, s, q, k, row_off.ptr, (int2 const *)rows.ptr,
-                 rows_d.ptr, (int2 *)packed.ptr, packed_d.ptr);
+      ABX_LAUNCH(compactPaddedRowsKernel, divUp(q, 256), 256, 0, s, q, k, row_off.ptr, src_rows, src_d,
+                 (int2 *)packed.ptr, packed_d.ptr);
     src_rows = (int2 const *)packed.ptr;
     src_d = packed_d.ptr;
   }
-  if (nnz > 0)
+  else if (short_rows && q > 0)
+    ABX_LAUNCH(compactPaddedRowsKernel, divUp(q, 256), 256, 0, s, q, k, row_off.ptr, src_rows, src_d, (int2 *)vals_v,
+               (float *)d_v);
+  if (compact && nnz > 0)
   {
-    if (compact)
-      ABX_LAUNCH(splitPairsKernel, divUp(nnz, 256), 256, 0, s, nnz, src_rows, (uint32_t *)vals_v);
-    else
-      ABX_CUDA_TRY(cudaMemcpyAsync(vals_v, src_rows, 2 * sizeof(int32_t) * (size_t)nnz, cudaMemcpyDeviceToDevice, s));
+    ABX_LAUNCH(splitPairsKernel, divUp(nnz, 256), 256, 0, s, nnz, src_rows, (uint32_t *)vals_v);
     if (want_dist)
       ABX_CUDA_TRY(cudaMemcpyAsync(d_v, src_d, sizeof(float) * (size_t)nnz, cudaMemcpyDeviceToDevice, s));
   }
@@ -961,7 +1010,7 @@ abx_status distNearest(abx_dist_tree *t, cudaStream_t s, void const *pts, int64_
     ABX_TRY(pos.alloc((size_t)M, s));
     ABX_TRY(rk.alloc((size_t)M, s));
     ABX_CUDA_TRY(cudaMemsetAsync(counter.ptr, 0, sizeof(unsigned), s));
-    ABX_LAUNCH(listRemoteInRowsKernel, divUp(M, 256), 256, 0, s, M, got_ids.ptr, k, (int2 const *)rows.ptr,
+    ABX_LAUNCH(listRemoteInRowsKernel, divUp(M, 256), 256, 0, s, M, got_ids.ptr, k, (int2 const *)rows_p,
                short_rows ? row_off.ptr : (int32_t const *)nullptr, t->rank, counter.ptr, pos.ptr, rk.ptr);
     unsigned h_count = 0;
     ABX_CUDA_TRY(cudaMemcpyAsync(&h_count, counter.ptr, sizeof(unsigned), cudaMemcpyDeviceToHost, s));

@@ -15,9 +15,6 @@
 #ifndef ABX_NEAREST_MINB
 #define ABX_NEAREST_MINB 12 // 40 registers: 10.6 ms at 10M / k = 10 (1: 48 regs 11.2 ms, 16: 32 regs 10.8 ms)
 #endif
-#ifndef ABX_NEAREST_DREG_MINB
-#define ABX_NEAREST_DREG_MINB 10 // 48 registers for the form with the candidate distances in registers
-#endif
 #ifndef ABX_SPATIAL_MINB
 #define ABX_SPATIAL_MINB 1
 #endif
@@ -249,8 +246,6 @@ struct GlobalHeap
 // K > 0: register list of exactly K candidates (the first min(k, found) are
 // reported; K >= k).  K == 0: global heap with run-time k.
 constexpr int kNearestBucket = 1; // 1 = leaves only
-constexpr int kSmemStack = 8;      // stack entries per thread kept in shared memory by the VAR = 2 form
-constexpr int kKnnDregDefault = 0; // 1: exact-K kernels (k <= 16) keep the candidate distances in registers
 
 // Candidate set of the K > 0 path: K (distance, index) slots per thread in shared memory,
 // UNSORTED, plus the position and value of the largest distance in registers.  The traversal
@@ -266,15 +261,12 @@ constexpr int kKnnDregDefault = 0; // 1: exact-K kernels (k <= 16) keep the cand
 // queries and a finished lane takes the next one (rows ranked at the end, converged) 14.2 / 15.3 / 15.8 ms.  ncu
 // says why: the L1 data pipe is at 85 % of its peak (l1tex__data_pipe_lsu_wavefronts), so what counts is the
 // number of distinct cache lines a warp's loads touch -- lanes that walk neighbouring queries in lock step share
-// them, lanes that drift apart do not.
-// DREG: the K candidate distances live in registers (static indices: the slot to overwrite is selected with K
-// predicated moves, the new largest distance falls out of the same pass) and only the indices stay in shared
-// memory.  The shared-memory form re-reads its K slots after every replacement, and those loads are a fifth of the
-// L1 data-pipe wavefronts of a kernel whose L1 data pipe is the busiest unit (85 %).
-// VAR = 2: DREG, and the first kSmemStack entries of the traversal stack in shared memory (the stack in local
-// memory hits L1 19 % of the time and is written back to DRAM: 2.4 GB per 10M queries).
-template <int K, int LEAF_F4, bool TRI, int VAR = 0>
-__global__ void __launch_bounds__(kThreads, (K > 0 && K <= 16) ? (VAR ? ABX_NEAREST_DREG_MINB : ABX_NEAREST_MINB) : 1)
+// them, lanes that drift apart do not.  Relieving that pipe at the price of instructions does not pay either
+// (issue slots are at 73 %): candidate distances in registers instead of shared memory (no re-read of the K slots
+// after a replacement, 48 registers) 12.2 ms, the same plus the first 8 stack entries in shared memory 12.8 ms
+// (profiles/r02_knn_dreg_sstack_experiment.log).
+template <int K, int LEAF_F4, bool TRI>
+__global__ void __launch_bounds__(kThreads, (K > 0 && K <= 16) ? ABX_NEAREST_MINB : 1)
     nearestKernel(Node64 const *__restrict__ nodes, float4 const *__restrict__ leaf_box,
                   float4 const *__restrict__ leaf_tri, int n, int prim_kind, float const *__restrict__ pts, int64_t q,
                   unsigned const *__restrict__ qperm, int k_uniform, int row_stride,
@@ -320,20 +312,11 @@ __global__ void __launch_bounds__(kThreads, (K > 0 && K <= 16) ? (VAR ? ABX_NEAR
   }
 
   constexpr bool USE_REGS = K > 0;
-  constexpr bool DREG = VAR >= 1;
-  constexpr int SSTK = VAR == 2 ? kSmemStack : 0;
   constexpr int KS = USE_REGS ? K : 1;
   __shared__ float set_d[KS * kThreads];
   __shared__ unsigned set_i[KS * kThreads];
   float *const my_d = set_d + threadIdx.x; // slot j at my_d[j * kThreads]: conflict-free across the warp
   unsigned *const my_i = set_i + threadIdx.x;
-  float dreg[DREG ? KS : 1];
-  if (DREG)
-  {
-#pragma unroll
-    for (int j = 0; j < KS; ++j)
-      dreg[j] = -1.f;
-  }
   int worst = 0; // slot holding the largest distance once the set is full
   GlobalHeap heap;
   heap.h = nullptr;
@@ -352,32 +335,7 @@ __global__ void __launch_bounds__(kThreads, (K > 0 && K <= 16) ? (VAR ? ABX_NEAR
       if (!(d2 < radius2))
         return;
     }
-    if (USE_REGS && DREG)
-    {
-      int const slot = found < KS ? found : worst;
-      my_i[slot * kThreads] = idx;
-      float m = -1.f;
-      int p = 0;
-#pragma unroll
-      for (int j = 0; j < KS; ++j)
-      {
-        float const x = j == slot ? d2 : dreg[j];
-        dreg[j] = x;
-        if (x > m)
-        {
-          m = x;
-          p = j;
-        }
-      }
-      if (found < KS)
-        ++found;
-      if (found == KS) // unfilled slots hold -1: they never win the maximum once the set is full
-      {
-        radius2 = m;
-        worst = p;
-      }
-    }
-    else if (USE_REGS)
+    if (USE_REGS)
     {
       // d2 < radius2 here; radius2 stays +inf until K candidates are known
       int const slot = found < KS ? found : worst;
@@ -416,17 +374,7 @@ __global__ void __launch_bounds__(kThreads, (K > 0 && K <= 16) ? (VAR ? ABX_NEAR
   };
 
   // stack of (squared box distance, node) for the farther child
-  unsigned long long stack[kStackSize - SSTK];
-  __shared__ unsigned long long sstack[(SSTK ? SSTK : 1) * kThreads];
-  auto push = [&](int at, unsigned long long e) {
-    if (SSTK && at < SSTK)
-      sstack[at * kThreads + threadIdx.x] = e;
-    else
-      stack[at - SSTK] = e;
-  };
-  auto top = [&](int at) -> unsigned long long {
-    return (SSTK && at < SSTK) ? sstack[at * kThreads + threadIdx.x] : stack[at - SSTK];
-  };
+  unsigned long long stack[kStackSize];
   int sp = 0;
   int node = 0;
   while (true)
@@ -498,7 +446,7 @@ __global__ void __launch_bounds__(kThreads, (K > 0 && K <= 16) ? (VAR ? ABX_NEAR
       {
         float const fd = left_first ? dr : dl;
         int const fn = left_first ? rref : lref;
-        push(sp++, ((unsigned long long)__float_as_uint(fd) << 32) | (unsigned)fn);
+        stack[sp++] = ((unsigned long long)__float_as_uint(fd) << 32) | (unsigned)fn;
       }
       node = left_first ? lref : rref;
       continue;
@@ -507,7 +455,7 @@ __global__ void __launch_bounds__(kThreads, (K > 0 && K <= 16) ? (VAR ? ABX_NEAR
     bool popped = false;
     while (sp > 0)
     {
-      unsigned long long const e = top(--sp);
+      unsigned long long const e = stack[--sp];
       if (__uint_as_float((unsigned)(e >> 32)) < radius2)
       {
         node = (int)(unsigned)e;
@@ -524,19 +472,9 @@ __global__ void __launch_bounds__(kThreads, (K > 0 && K <= 16) ? (VAR ? ABX_NEAR
     // sort the row: insertion into a register list, in slot order (all lanes are here together)
     RegList<KS> list;
     list.init();
-    if (DREG)
-    {
-#pragma unroll
-      for (int j = 0; j < KS; ++j)
-        if (j < found)
-          list.insert(dreg[j], my_i[j * kThreads]);
-    }
-    else
-    {
 #pragma unroll 1
-      for (int j = 0; j < found; ++j)
-        list.insert(my_d[j * kThreads], my_i[j * kThreads]);
-    }
+    for (int j = 0; j < found; ++j)
+      list.insert(my_d[j * kThreads], my_i[j * kThreads]);
     int const m = min(min(found, k), USE_REGS ? K : 1);
 #pragma unroll
     for (int i = 0; i < (USE_REGS ? K : 1); ++i)
@@ -855,49 +793,9 @@ abx_status nearestQuery(cudaStream_t s, abx_bvh *t, float const *pts, int64_t q,
     ABX_TRY(counts_tmp.alloc((size_t)q, s));
     counts = counts_tmp.ptr;
   }
-  int const dreg = ABX_TUNE_INT("ABX_KNN_DREG", kKnnDregDefault);
-#define ABX_NEAREST_D(KCAP, SCRATCH)                                                                                  \
-  do                                                                                                                   \
-  {                                                                                                                    \
-    if (tri)                                                                                                           \
-      ABX_LAUNCH_TAGGED("nearestKernel<" #KCAP ",tri,dreg>", (nearestKernel<KCAP, 2, true, 1>), grid, kThreads, 0, \
-                        s, t->nodes, t->leaf_box, t->leaf_tri, n, t->kind, pts, q, qperm, k, row_stride, k_per_query,  \
-                        offsets, counts, indices, distances, SCRATCH, missing, pair_rank);                             \
-    else if (t->kind == ABX_PRIM_BOX3F)                                                                                \
-      ABX_LAUNCH_TAGGED("nearestKernel<" #KCAP ",box,dreg>", (nearestKernel<KCAP, 2, false, 1>), grid, kThreads,   \
-                        0, s, t->nodes, t->leaf_box, t->leaf_tri, n, t->kind, pts, q, qperm, k, row_stride,            \
-                        k_per_query, offsets, counts, indices, distances, SCRATCH, missing, pair_rank);                \
-    else                                                                                                               \
-      ABX_LAUNCH_TAGGED("nearestKernel<" #KCAP ",dreg>", (nearestKernel<KCAP, 1, false, 1>), grid, kThreads, 0, s, \
-                        t->nodes, t->leaf_box, t->leaf_tri, n, t->kind, pts, q, qperm, k, row_stride, k_per_query,     \
-                        offsets, counts, indices, distances, SCRATCH, missing, pair_rank);                             \
-  } while (0)
-#if defined(ABX_TUNING)
-#define ABX_NEAREST_PICK(KCAP, SCRATCH)                                                                               \
-  if (dreg == 2 && KCAP > 0 && KCAP <= 16 && !tri && t->kind == ABX_PRIM_POINT3F)                                      \
-  {                                                                                                                    \
-    ABX_LAUNCH_TAGGED("nearestKernel<" #KCAP ",dreg,sstack>", (nearestKernel<KCAP, 1, false, 2>), grid, kThreads, 0,  \
-                      s, t->nodes, t->leaf_box, t->leaf_tri, n, t->kind, pts, q, qperm, k, row_stride, k_per_query,    \
-                      offsets, counts, indices, distances, SCRATCH, missing, pair_rank);                               \
-    break;                                                                                                             \
-  }                                                                                                                    \
-  if (dreg && KCAP > 0 && KCAP <= 16)                                                                                  \
-  {                                                                                                                    \
-    ABX_NEAREST_D(KCAP, SCRATCH);                                                                                      \
-    break;                                                                                                             \
-  }
-#else
-#define ABX_NEAREST_PICK(KCAP, SCRATCH)                                                                               \
-  if (kKnnDregDefault && KCAP > 0 && KCAP <= 16)                                                                       \
-  {                                                                                                                    \
-    ABX_NEAREST_D(KCAP, SCRATCH);                                                                                      \
-    break;                                                                                                             \
-  }
-#endif
 #define ABX_NEAREST(KCAP, SCRATCH)                                                                                    \
   do                                                                                                                   \
   {                                                                                                                    \
-    ABX_NEAREST_PICK(KCAP, SCRATCH)                                                                                    \
     if (tri)                                                                                                           \
       ABX_LAUNCH_TAGGED("nearestKernel<" #KCAP ",tri>", (nearestKernel<KCAP, 2, true>), grid, kThreads, 0, s,          \
                         t->nodes, t->leaf_box, t->leaf_tri, n, t->kind, pts, q, qperm, k, row_stride, k_per_query,     \
@@ -946,9 +844,6 @@ abx_status nearestQuery(cudaStream_t s, abx_bvh *t, float const *pts, int64_t q,
     ABX_NEAREST(0, scratch.ptr);
   }
 #undef ABX_NEAREST
-#undef ABX_NEAREST_PICK
-#undef ABX_NEAREST_D
-  (void)dreg;
   if (pair_rank >= 0 && row_stride > 0)
     ABX_LAUNCH(padShortRowsKernel, divUp(q, 256), 256, 0, s, q, row_stride, counts, (int2 *)indices, distances);
   return ABX_OK;
