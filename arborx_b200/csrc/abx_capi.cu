@@ -269,12 +269,15 @@ static abx_status checkPredPointer(int pred_kind, void const *preds, int64_t q)
 // writes the CRS rows and re-traverses only queries with more than kStage results.
 // buffer_size never changes the result, so the policy is honoured for its error
 // contract only (hard preallocation overflow throws, :263-268).
-// before_sync (optional): enqueues more work / read-backs on `s` that the call's one blocking point
-// should cover as well (the DistributedTree exchange piggy-backs its count matrix on it).
-abx_status spatialCrs(abx_bvh *bvh, cudaStream_t s, int pred_kind, void const *preds, int64_t q,
-                      abx_policy const &policy, abx_alloc_fn alloc, void *user, int32_t **offsets_out,
-                      uint32_t **indices_out, int64_t *nnz_out, std::function<abx_status()> const &before_sync)
+// The CRS driver in two halves, so that a caller (DistributedTree) can put its own host work between the enqueue
+// of the traversal and the one blocking point of the query.
+//   spatialCrsBegin  enqueues the predicate ordering, the traversal (count + stage), the scan and the read-back of nnz
+//   spatialCrsEnd    blocks for nnz (the reference blocks there too: lastElement, CrsGraphWrapperImpl.hpp:248),
+//                    allocates the indices and enqueues the compaction
+abx_status spatialCrsBegin(SpatialCrsCall &c, abx_bvh *bvh, cudaStream_t s, int pred_kind, void const *preds, int64_t q,
+                           abx_policy const &policy, abx_alloc_fn alloc, void *user)
 {
+  c.bvh = bvh, c.s = s, c.pred_kind = pred_kind, c.preds = preds, c.q = q, c.policy = policy, c.alloc = alloc, c.user = user;
   ABX_TRY(checkPredPointer(pred_kind, preds, q));
   if (q < 0 || q >= (int64_t)1 << 30)
   {
@@ -283,82 +286,94 @@ abx_status spatialCrs(abx_bvh *bvh, cudaStream_t s, int pred_kind, void const *p
   }
   void *offsets_v = nullptr;
   ABX_TRY(allocOut(alloc, user, 0, sizeof(int32_t) * (size_t)(q + 1), s, &offsets_v));
-  int32_t *offsets = (int32_t *)offsets_v;
-  *offsets_out = offsets;
-  *indices_out = nullptr;
-  *nnz_out = 0;
-  if (q == 0 || bvh->n == 0)
+  c.offsets = (int32_t *)offsets_v;
+  c.trivial = q == 0 || bvh->n == 0;
+  if (c.trivial)
   {
-    ABX_CUDA_TRY(cudaMemsetAsync(offsets, 0, sizeof(int32_t) * (size_t)(q + 1), s));
-    void *idx = nullptr;
-    ABX_TRY(allocOut(alloc, user, 1, 0, s, &idx));
-    *indices_out = (uint32_t *)idx;
-    if (before_sync)
-    {
-      // the caller counts on this call's blocking point
-      ABX_TRY(before_sync());
-      ABX_CUDA_TRY(cudaStreamSynchronize(s));
-    }
+    ABX_CUDA_TRY(cudaMemsetAsync(c.offsets, 0, sizeof(int32_t) * (size_t)(q + 1), s));
     return ABX_OK;
   }
-  TempBuffer<uint32_t> qperm;
   if (policy.sort_predicates && bvh->n > 1)
-    ABX_TRY(predicatePermutation(s, bvh, pred_kind, preds, q, qperm));
+    ABX_TRY(predicatePermutation(s, bvh, pred_kind, preds, q, c.qperm));
   // the traversal: counts land in offsets[0..q) in ORIGINAL query order
-  TempBuffer<uint32_t> staging;
-  bool const staged = bvh->n > 1;
-  if (staged)
+  c.staged = bvh->n > 1;
+  if (c.staged)
   {
-    ABX_TRY(staging.alloc((size_t)spatialStageSlots() * (size_t)q, s));
-    ABX_TRY(spatialStage(s, bvh, pred_kind, preds, q, qperm.ptr, offsets, staging.ptr));
+    ABX_TRY(c.staging.alloc((size_t)spatialStageSlots() * (size_t)q, s));
+    ABX_TRY(spatialStage(s, bvh, pred_kind, preds, q, c.qperm.ptr, c.offsets, c.staging.ptr));
   }
   else
-    ABX_TRY(spatialCount(s, bvh, pred_kind, preds, q, qperm.ptr, 0, offsets));
-  TempBuffer<int> overflow;
-  int h_overflow = 0;
+    ABX_TRY(spatialCount(s, bvh, pred_kind, preds, q, c.qperm.ptr, 0, c.offsets));
   if (policy.buffer_size < 0)
   {
-    ABX_TRY(overflow.alloc(1, s));
-    ABX_CUDA_TRY(cudaMemsetAsync(overflow.ptr, 0, sizeof(int), s));
-    ABX_LAUNCH(overflowKernel, divUp(q, 256), 256, 0, s, offsets, q, -policy.buffer_size, overflow.ptr);
-    ABX_CUDA_TRY(cudaMemcpyAsync(&h_overflow, overflow.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
+    ABX_TRY(c.overflow.alloc(1, s));
+    ABX_CUDA_TRY(cudaMemsetAsync(c.overflow.ptr, 0, sizeof(int), s));
+    ABX_LAUNCH(overflowKernel, divUp(q, 256), 256, 0, s, c.offsets, q, -policy.buffer_size, c.overflow.ptr);
+    ABX_CUDA_TRY(cudaMemcpyAsync(&c.h_overflow, c.overflow.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
   }
   // the int32 scan wraps silently past 2^31 results: the total is accumulated in 64 bits next to it
-  TempBuffer<unsigned long long> total64;
-  ABX_TRY(total64.alloc(1, s));
-  ABX_TRY(exclusiveScanI32(s, offsets, offsets, q + 1, total64.ptr));
-  unsigned long long total_ull = 0;
-  ABX_CUDA_TRY(cudaMemcpyAsync(&total_ull, total64.ptr, sizeof(total_ull), cudaMemcpyDeviceToHost, s));
-  if (before_sync)
-    ABX_TRY(before_sync());
-  ABX_CUDA_TRY(cudaStreamSynchronize(s)); // the reference blocks here too (lastElement, :248)
-  if (total_ull >= (1ull << 31))
+  ABX_TRY(c.total64.alloc(1, s));
+  ABX_TRY(exclusiveScanI32(s, c.offsets, c.offsets, q + 1, c.total64.ptr));
+  ABX_CUDA_TRY(cudaMemcpyAsync(&c.h_total, c.total64.ptr, sizeof(c.h_total), cudaMemcpyDeviceToHost, s));
+  return ABX_OK;
+}
+
+abx_status spatialCrsEnd(SpatialCrsCall &c, int32_t **offsets_out, uint32_t **indices_out, int64_t *nnz_out, bool sync)
+{
+  cudaStream_t const s = c.s;
+  *offsets_out = c.offsets;
+  *indices_out = nullptr;
+  *nnz_out = 0;
+  void *idx = nullptr;
+  if (c.trivial)
+  {
+    ABX_TRY(allocOut(c.alloc, c.user, 1, 0, s, &idx));
+    *indices_out = (uint32_t *)idx;
+    if (sync)
+      ABX_CUDA_TRY(cudaStreamSynchronize(s));
+    return ABX_OK;
+  }
+  ABX_CUDA_TRY(cudaStreamSynchronize(s));
+  if (c.h_total >= (1ull << 31))
   {
     setError("spatial query: more than 2^31 results (CRS offsets are 32-bit like the reference's)");
     return ABX_ERR_ARG;
   }
-  int64_t const total = (int64_t)total_ull;
+  int64_t const total = (int64_t)c.h_total;
   *nnz_out = total;
-  void *idx = nullptr;
   if (total == 0)
   {
-    ABX_TRY(allocOut(alloc, user, 1, 0, s, &idx));
+    ABX_TRY(allocOut(c.alloc, c.user, 1, 0, s, &idx));
     *indices_out = (uint32_t *)idx;
     return ABX_OK; // :252-261
   }
-  if (h_overflow)
+  if (c.h_overflow)
   {
     setError("SearchException: hard preallocation buffer_size is too small for the results");
     return ABX_ERR_SEARCH;
   }
-  ABX_TRY(allocOut(alloc, user, 1, sizeof(uint32_t) * (size_t)total, s, &idx));
+  ABX_TRY(allocOut(c.alloc, c.user, 1, sizeof(uint32_t) * (size_t)total, s, &idx));
   *indices_out = (uint32_t *)idx;
-  if (staged)
+  if (c.staged)
     // original query order: coalesced staging-row reads and CRS writes (see kStage in abx_query.cu)
-    ABX_TRY(spatialCompact(s, bvh, pred_kind, preds, q, nullptr, offsets, *indices_out, staging.ptr));
+    ABX_TRY(spatialCompact(s, c.bvh, c.pred_kind, c.preds, c.q, nullptr, c.offsets, *indices_out, c.staging.ptr));
   else
-    ABX_TRY(spatialFill(s, bvh, pred_kind, preds, q, qperm.ptr, offsets, *indices_out));
+    ABX_TRY(spatialFill(s, c.bvh, c.pred_kind, c.preds, c.q, c.qperm.ptr, c.offsets, *indices_out));
   return ABX_OK;
+}
+
+// before_sync (optional): enqueues more work / read-backs on `s` that the call's one blocking point
+// should cover as well (the DistributedTree exchange piggy-backs its count matrix on it).
+abx_status spatialCrs(abx_bvh *bvh, cudaStream_t s, int pred_kind, void const *preds, int64_t q,
+                      abx_policy const &policy, abx_alloc_fn alloc, void *user, int32_t **offsets_out,
+                      uint32_t **indices_out, int64_t *nnz_out, std::function<abx_status()> const &before_sync)
+{
+  SpatialCrsCall c;
+  ABX_TRY(spatialCrsBegin(c, bvh, s, pred_kind, preds, q, policy, alloc, user));
+  *offsets_out = c.offsets; // the hook may want to read the scanned offsets
+  if (before_sync)
+    ABX_TRY(before_sync());
+  return spatialCrsEnd(c, offsets_out, indices_out, nnz_out, before_sync != nullptr);
 }
 
 abx_status nearestCrs(abx_bvh *bvh, cudaStream_t s, void const *pts, int64_t q, int32_t k,

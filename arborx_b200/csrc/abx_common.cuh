@@ -395,6 +395,30 @@ abx_status clipK(cudaStream_t s, int32_t const *k_per_query, int k, int n, int64
 abx_status halfTraversalPairs(cudaStream_t s, abx_bvh *bvh, float r, uint32_t *pairs, int64_t capacity,
                               unsigned long long *count_dev);
 // capi.cu: the CRS drivers (also used by the DistributedTree host code, abx_dist.cu)
+struct SpatialCrsCall // state of one spatial CRS query between its two halves; must not move in between
+{
+  abx_bvh *bvh = nullptr;
+  cudaStream_t s = nullptr;
+  int pred_kind = 0;
+  void const *preds = nullptr;
+  int64_t q = 0;
+  abx_policy policy;
+  abx_alloc_fn alloc = nullptr;
+  void *user = nullptr;
+  int32_t *offsets = nullptr;
+  bool trivial = false, staged = false;
+  TempBuffer<uint32_t> qperm, staging;
+  TempBuffer<int> overflow;
+  TempBuffer<unsigned long long> total64;
+  unsigned long long h_total = 0;
+  int h_overflow = 0;
+  SpatialCrsCall() = default;
+  SpatialCrsCall(SpatialCrsCall const &) = delete;
+};
+abx_status spatialCrsBegin(SpatialCrsCall &c, abx_bvh *bvh, cudaStream_t s, int pred_kind, void const *preds, int64_t q,
+                           abx_policy const &policy, abx_alloc_fn alloc, void *user);
+abx_status spatialCrsEnd(SpatialCrsCall &c, int32_t **offsets_out, uint32_t **indices_out, int64_t *nnz_out,
+                         bool sync_if_trivial = false);
 abx_status spatialCrs(abx_bvh *bvh, cudaStream_t s, int pred_kind, void const *preds, int64_t q,
                       abx_policy const &policy, abx_alloc_fn alloc, void *user, int32_t **offsets_out,
                       uint32_t **indices_out, int64_t *nnz_out,

@@ -480,6 +480,36 @@ void returnPinnedScratch(uint32_t *p)
   g_pinned_free.push_back(p);
 }
 
+// side streams are recycled too: the device-memory cache files blocks per stream, and a tree built inside a time
+// step must find the blocks its predecessor released
+std::vector<std::pair<int, cudaStream_t>> g_side_free; // (device, stream), under g_pinned_mutex
+abx_status takeSideStream(cudaStream_t *out)
+{
+  int dev = 0;
+  ABX_CUDA_TRY(cudaGetDevice(&dev));
+  {
+    std::lock_guard<std::mutex> lock(g_pinned_mutex);
+    for (size_t i = 0; i < g_side_free.size(); ++i)
+      if (g_side_free[i].first == dev)
+      {
+        *out = g_side_free[i].second;
+        g_side_free.erase(g_side_free.begin() + i);
+        return ABX_OK;
+      }
+  }
+  int prio_lo = 0, prio_hi = 0;
+  ABX_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  ABX_CUDA_TRY(cudaStreamCreateWithPriority(out, cudaStreamNonBlocking, prio_hi));
+  return ABX_OK;
+}
+void returnSideStream(cudaStream_t s)
+{
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(g_pinned_mutex);
+  g_side_free.push_back({dev, s});
+}
+
 // forwarded batches below this size are traversed in arrival order (already grouped by source rank and, inside a
 // source, by the sender's routing order): six launches of Morton ordering cost more than they return
 constexpr int64_t kSortForwardedAbove = 32768;
@@ -526,6 +556,8 @@ struct abx_dist_tree
   int64_t total = 0;
   float *boxes_dev = nullptr;
   uint32_t *h_pin = nullptr; // pinned scratch: R x R count matrix, then one 64-bit word (8-byte aligned)
+  cudaStream_t side = nullptr; // high-priority stream of the exchange (overlaps the local traversal)
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   float bounds[6];
 };
 
@@ -665,20 +697,54 @@ abx_status distSpatial(abx_dist_tree *t, cudaStream_t s, int pred_kind, void con
     *values_out = vals;
     return ABX_OK;
   }
+  if (R == 1)
+  {
+    // one rank: the bottom tree is the whole tree
+    if (compact)
+    {
+      uint32_t *idx = nullptr;
+      abx_status const st = spatialCrs(t->bottom, s, pred_kind, preds, q, policy, alloc, user, offsets_out, &idx, nnz_out);
+      *values_out = idx;
+      return st;
+    }
+    int32_t *off1 = nullptr;
+    uint32_t *idx1 = nullptr;
+    int64_t nnz1 = 0;
+    ABX_TRY(spatialCrs(t->bottom, s, pred_kind, preds, q, policy, nullptr, nullptr, &off1, &idx1, &nnz1));
+    void *off_o = nullptr, *vals_o = nullptr;
+    abx_status st = allocOutDev(alloc, user, 0, sizeof(int32_t) * (size_t)(q + 1), s, &off_o);
+    if (st == ABX_OK)
+      st = allocOutDev(alloc, user, 1, 2 * sizeof(int32_t) * (size_t)nnz1, s, &vals_o);
+    if (st == ABX_OK && cudaMemcpyAsync(off_o, off1, sizeof(int32_t) * (size_t)(q + 1), cudaMemcpyDeviceToDevice, s) !=
+                            cudaSuccess)
+      st = ABX_ERR_CUDA;
+    if (st == ABX_OK)
+      st = pairWithRank(s, (int32_t const *)idx1, nnz1, t->rank, (int32_t *)vals_o);
+    deviceFree(off1, s);
+    deviceFree(idx1, s);
+    *offsets_out = (int32_t *)off_o;
+    *values_out = vals_o;
+    *nnz_out = nnz1;
+    return st;
+  }
+  // The exchange (routing, both count matrices, both NCCL exchanges, the query for other ranks' predicates) runs on
+  // the tree's side stream while the big local traversal runs on `s`: its host round trips and small kernels hide
+  // behind the local traversal instead of stretching the call.
+  cudaStream_t const x = t->side;
+  ABX_CUDA_TRY(cudaEventRecord(t->ev[0], s)); // the predicates may be produced on s
+  ABX_CUDA_TRY(cudaStreamWaitEvent(x, t->ev[0], 0));
   // 1. routing counts of every rank -> count matrix on its way to the host
   TempBuffer<uint32_t> counts, matrix;
-  ABX_TRY(counts.alloc(R, s));
-  ABX_TRY(matrix.alloc((size_t)R * R, s));
-  ABX_CUDA_TRY(cudaMemsetAsync(counts.ptr, 0, sizeof(uint32_t) * R, s));
-  ABX_TRY(routeLaunch(s, false, pred_kind, preds, q, nullptr, 0, t->boxes_dev, R, t->rank, counts.ptr, nullptr, nullptr,
+  ABX_TRY(counts.alloc(R, x));
+  ABX_TRY(matrix.alloc((size_t)R * R, x));
+  ABX_CUDA_TRY(cudaMemsetAsync(counts.ptr, 0, sizeof(uint32_t) * R, x));
+  ABX_TRY(routeLaunch(x, false, pred_kind, preds, q, nullptr, 0, t->boxes_dev, R, t->rank, counts.ptr, nullptr, nullptr,
                       nullptr));
-  ABX_TRY(gatherCountMatrix(t, s, counts.ptr, matrix.ptr));
-  // 2. the local tree answers every local predicate; its blocking point (nnz) also covers the matrix
-  int32_t *off_l = nullptr;
-  uint32_t *idx_l = nullptr;
-  int64_t nnz_l = 0;
-  ABX_TRY(spatialCrs(t->bottom, s, pred_kind, preds, q, policy, nullptr, nullptr, &off_l, &idx_l, &nnz_l,
-                     [&]() -> abx_status { return ABX_OK; }));
+  ABX_TRY(gatherCountMatrix(t, x, counts.ptr, matrix.ptr));
+  ABX_CUDA_TRY(cudaEventRecord(t->ev[1], x));
+  // 2. the local tree answers every local predicate (enqueued now, collected after the exchange)
+  SpatialCrsCall local;
+  ABX_TRY(spatialCrsBegin(local, t->bottom, s, pred_kind, preds, q, policy, nullptr, nullptr));
   struct Guard
   {
     cudaStream_t s;
@@ -688,7 +754,9 @@ abx_status distSpatial(abx_dist_tree *t, cudaStream_t s, int pred_kind, void con
       deviceFree(a, s);
       deviceFree(b, s);
     }
-  } local_guard{s, off_l, idx_l};
+  };
+  Guard local_guard{s, local.offsets, nullptr};
+  ABX_CUDA_TRY(cudaEventSynchronize(t->ev[1])); // the count matrix is on the host
   ExchangePlan fwd;
   fwd.fromMatrix(t->h_pin, R, t->rank);
 
@@ -700,40 +768,60 @@ abx_status distSpatial(abx_dist_tree *t, cudaStream_t s, int pred_kind, void con
     // 3. forward, query the bottom tree with what arrived; its blocking point covers the back-count matrix
     TempBuffer<uint32_t> fwd_preds;
     TempBuffer<int32_t> fwd_ids;
-    ABX_TRY(forwardPredicates(t, s, pred_kind, preds, W, q, nullptr, 0, fwd, fwd_preds, fwd_ids));
+    ABX_TRY(forwardPredicates(t, x, pred_kind, preds, W, q, nullptr, 0, fwd, fwd_preds, fwd_ids));
     int64_t const G = fwd.n_recv;
     TempBuffer<int32_t> starts;
-    ABX_TRY(starts.alloc(R + 1, s));
+    ABX_TRY(starts.alloc(R + 1, x));
     std::vector<int32_t> h_starts(R + 1);
     for (int r = 0; r <= R; ++r)
       h_starts[r] = (int32_t)fwd.recv_off[r];
-    ABX_CUDA_TRY(cudaMemcpyAsync(starts.ptr, h_starts.data(), sizeof(int32_t) * (R + 1), cudaMemcpyHostToDevice, s));
+    ABX_CUDA_TRY(cudaMemcpyAsync(starts.ptr, h_starts.data(), sizeof(int32_t) * (R + 1), cudaMemcpyHostToDevice, x));
     int32_t *off_r = nullptr;
     uint32_t *idx_r = nullptr;
     int64_t nnz_r = 0;
     abx_policy remote_policy = policy;
     remote_policy.sort_predicates = G >= kSortForwardedAbove;
-    ABX_TRY(spatialCrs(t->bottom, s, pred_kind, fwd_preds.ptr, G, remote_policy, nullptr, nullptr, &off_r, &idx_r, &nnz_r,
+    ABX_TRY(spatialCrs(t->bottom, x, pred_kind, fwd_preds.ptr, G, remote_policy, nullptr, nullptr, &off_r, &idx_r, &nnz_r,
                        [&]() -> abx_status {
                          // runs right after the scan of the remote query's offsets
-                         ABX_LAUNCH(segmentTotalsKernel, 1, 64, 0, s, off_r, starts.ptr, R, counts.ptr);
-                         return gatherCountMatrix(t, s, counts.ptr, matrix.ptr);
+                         ABX_LAUNCH(segmentTotalsKernel, 1, 64, 0, x, off_r, starts.ptr, R, counts.ptr);
+                         return gatherCountMatrix(t, x, counts.ptr, matrix.ptr);
                        }));
-    Guard remote_guard{s, off_r, idx_r};
+    Guard remote_guard{x, off_r, idx_r};
     ExchangePlan back;
     back.fromMatrix(t->h_pin, R, t->rank);
     M = back.n_recv;
     // 4. results back: (index, query id) columns; the indices travel straight out of the CRS array
     TempBuffer<int32_t> res_ids;
-    ABX_TRY(res_ids.alloc((size_t)std::max<int64_t>(nnz_r, 1), s));
+    ABX_TRY(res_ids.alloc((size_t)std::max<int64_t>(nnz_r, 1), x));
     if (nnz_r > 0)
-      ABX_LAUNCH(expandRowIdsKernel, divUp(nnz_r, 256), 256, 0, s, off_r, fwd_ids.ptr, (int)G, nnz_r, res_ids.ptr);
-    ABX_TRY(got_idx.alloc((size_t)std::max<int64_t>(M, 1), s));
-    ABX_TRY(got_ids.alloc((size_t)std::max<int64_t>(M, 1), s));
+      ABX_LAUNCH(expandRowIdsKernel, divUp(nnz_r, 256), 256, 0, x, off_r, fwd_ids.ptr, (int)G, nnz_r, res_ids.ptr);
+    ABX_TRY(got_idx.alloc((size_t)std::max<int64_t>(M, 1), x));
+    ABX_TRY(got_ids.alloc((size_t)std::max<int64_t>(M, 1), x));
     ExchangeColumn cols[2] = {{idx_r, got_idx.ptr, sizeof(int32_t)}, {res_ids.ptr, got_ids.ptr, sizeof(int32_t)}};
-    ABX_TRY(t->comm->allToAllV(cols, 2, back.send_off.data(), back.recv_off.data(), s));
-    ABX_TRY(sortReceived(t, s, M, q, back, got_ids, got_idx.ptr, nullptr, rvals2, unused));
+    ABX_TRY(t->comm->allToAllV(cols, 2, back.send_off.data(), back.recv_off.data(), x));
+    ABX_TRY(sortReceived(t, x, M, q, back, got_ids, got_idx.ptr, nullptr, rvals2, unused));
   }
+  ABX_CUDA_TRY(cudaEventRecord(t->ev[2], x));
+  // the local query's own blocking point (nnz), then its compaction
+  int32_t *off_l = nullptr;
+  uint32_t *idx_l = nullptr;
+  int64_t nnz_l = 0;
+  ABX_TRY(spatialCrsEnd(local, &off_l, &idx_l, &nnz_l));
+  local_guard.b = idx_l;
+  ABX_CUDA_TRY(cudaStreamWaitEvent(s, t->ev[2], 0)); // the remote records are in place
+  // buffers taken under the side stream go back to it when this frame unwinds: not before the merge below (on s)
+  // has read them
+  struct Rejoin
+  {
+    abx_dist_tree *t;
+    cudaStream_t s, x;
+    ~Rejoin()
+    {
+      if (cudaEventRecord(t->ev[0], s) == cudaSuccess)
+        cudaStreamWaitEvent(x, t->ev[0], 0);
+    }
+  } rejoin{t, s, x};
   // 5. merge per query: local results first, then the remote ones
   int64_t const nnz = nnz_l + M;
   if (nnz >= (int64_t)1 << 31)
@@ -1195,6 +1283,9 @@ static abx_status distCreate(abx_comm *comm, cudaStream_t s, int prim_kind, void
   ABX_TRY(deviceAlloc((void **)&t->boxes_dev, sizeof(float) * 6 * R, s));
   ABX_CUDA_TRY(cudaMemcpyAsync(t->boxes_dev, t->boxes.data(), sizeof(float) * 6 * R, cudaMemcpyHostToDevice, s));
   ABX_TRY(takePinnedScratch(&t->h_pin));
+  ABX_TRY(takeSideStream(&t->side));
+  for (auto &e : t->ev)
+    ABX_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   *out = t.release();
   return ABX_OK;
 }
@@ -1242,6 +1333,11 @@ abx_status abx_dist_destroy(abx_dist_tree *t)
   }
   if (t->h_pin)
     returnPinnedScratch(t->h_pin);
+  for (auto &e : t->ev)
+    if (e)
+      cudaEventDestroy(e);
+  if (t->side)
+    returnSideStream(t->side);
   delete t;
   return ABX_OK;
 }
