@@ -922,6 +922,80 @@ static inline void sortHeap(PairID *first, PairID *last)
     popHeap(first, last--);
 }
 
+// query geometries of nearest predicates other than a point (spatial/detail/ArborX_Predicates.hpp:58-80 with
+// geometry/algorithms/ArborX_Distance.hpp:83-108,166-209, ArborX_Ray.hpp:433-444)
+struct SphereQ
+{
+  P3 c;
+  float r;
+};
+// distance box-box :166-197 (a = query, b = other)
+static inline float distance(Box3 const &a, Box3 const &b)
+{
+  float d2 = 0;
+  for (int d = 0; d < 3; ++d)
+  {
+    if (a.lo[d] > b.hi[d])
+    {
+      float const delta = a.lo[d] - b.hi[d];
+      d2 += delta * delta;
+    }
+    else if (b.lo[d] > a.hi[d])
+    {
+      float const delta = b.lo[d] - a.hi[d];
+      d2 += delta * delta;
+    }
+  }
+  return std::sqrt(d2);
+}
+// distance sphere-box :199-209, point-sphere :83-94 (through ReverseDispatch)
+static inline float distance(SphereQ const &s, Box3 const &b) { return std::max(distance(s.c, b) - s.r, 0.f); }
+static inline float distance(SphereQ const &s, P3 const &p) { return std::max(distance(p, s.c) - s.r, 0.f); }
+// distance ray-box ArborX_Ray.hpp:433-444
+static inline float distance(Ray3 const &ray, Box3 const &box)
+{
+  float tmin, tmax;
+  bool const hit = rayBoxIntersection(ray, box, tmin, tmax) && (tmax >= 0);
+  return hit ? std::max(tmin, 0.f) : std::numeric_limits<float>::infinity();
+}
+static inline Box3 pointAsBox(P3 const &p)
+{
+  Box3 b;
+  for (int d = 0; d < 3; ++d)
+    b.lo[d] = b.hi[d] = p[d];
+  return b;
+}
+static inline float nearestDistance(Tree const &t, Box3 const &q, int node)
+{
+  if (t.isLeaf(node))
+  {
+    unsigned o = t.perm[node];
+    if (t.kind == PRIM_POINT)
+      return distance(t.point(o), q); // distance(Box, Point) -> distance(Point, Box)
+    return distance(q, t.pbox(o));
+  }
+  return distance(q, t.box[node - t.n]);
+}
+static inline float nearestDistance(Tree const &t, SphereQ const &q, int node)
+{
+  if (t.isLeaf(node))
+  {
+    unsigned o = t.perm[node];
+    if (t.kind == PRIM_POINT)
+      return distance(q, t.point(o));
+    return distance(q, t.pbox(o));
+  }
+  return distance(q, t.box[node - t.n]);
+}
+static inline float nearestDistance(Tree const &t, Ray3 const &q, int node)
+{
+  if (t.isLeaf(node))
+  {
+    unsigned o = t.perm[node];
+    return distance(q, t.kind == PRIM_POINT ? pointAsBox(t.point(o)) : t.pbox(o));
+  }
+  return distance(q, t.box[node - t.n]);
+}
 static inline float nearestDistance(Tree const &t, P3 const &q, int node)
 {
   if (t.isLeaf(node))
@@ -937,7 +1011,8 @@ static inline float nearestDistance(Tree const &t, P3 const &q, int node)
 }
 
 // returns number of results written to buf (sorted ascending by distance)
-static int traverseNearest(Tree const &t, P3 const &q, int k, PairID *buf, std::vector<int> &stack,
+template <class Q>
+static int traverseNearest(Tree const &t, Q const &q, int k, PairID *buf, std::vector<int> &stack,
                            std::vector<float> &stack_d, Counters *c)
 {
   if (k < 1 || t.n == 0)
@@ -1478,6 +1553,158 @@ ORC_API long long orc_query_nearest_crs(void *h, float const *pts, int q, int k,
         distances[total + j] = e.second;
     }
     total += counts[i];
+  }
+  offsets[q] = (int)total;
+  return total;
+}
+
+// nearest(Box | Sphere | Ray, k): the same traversal with the predicate geometry's distance
+// (spatial/detail/ArborX_Predicates.hpp:58-80).  Point and box primitives.
+ORC_API long long orc_query_nearest_geom_crs(void *h, int pred_kind, float const *preds, int q, int k,
+                                             int sort_predicates, int *offsets, unsigned *indices, float *distances)
+{
+  Tree const &t = *(Tree *)h;
+  if (t.kind == PRIM_TRI || (pred_kind != PRED_POINT && pred_kind != PRED_BOX && pred_kind != PRED_SPHERE && pred_kind != PRED_RAY))
+    return -1;
+  std::vector<unsigned> permute = predicatePermutation(t, pred_kind, preds, q, sort_predicates != 0);
+  int const kk = std::max(0, k);
+  std::vector<PairID> buffer((size_t)q * kk);
+  std::vector<int> counts(q, 0);
+#pragma omp parallel
+  {
+    std::vector<int> stack;
+    std::vector<float> stack_d;
+#pragma omp for schedule(dynamic, 256)
+    for (int i = 0; i < q; ++i)
+    {
+      unsigned const o = permute[i];
+      PairID *buf = buffer.data() + (size_t)o * kk;
+      if (pred_kind == PRED_POINT)
+        counts[o] = traverseNearest(t, P3{{preds[3 * (size_t)o], preds[3 * (size_t)o + 1], preds[3 * (size_t)o + 2]}}, k, buf,
+                                    stack, stack_d, nullptr);
+      else if (pred_kind == PRED_BOX)
+      {
+        Box3 b;
+        for (int d = 0; d < 3; ++d)
+        {
+          b.lo[d] = preds[6 * (size_t)o + d];
+          b.hi[d] = preds[6 * (size_t)o + 3 + d];
+        }
+        counts[o] = traverseNearest(t, b, k, buf, stack, stack_d, nullptr);
+      }
+      else if (pred_kind == PRED_SPHERE)
+      {
+        SphereQ sq{P3{{preds[4 * (size_t)o], preds[4 * (size_t)o + 1], preds[4 * (size_t)o + 2]}}, preds[4 * (size_t)o + 3]};
+        counts[o] = traverseNearest(t, sq, k, buf, stack, stack_d, nullptr);
+      }
+      else
+        counts[o] = traverseNearest(t, makeRay(preds + 6 * (size_t)o), k, buf, stack, stack_d, nullptr);
+    }
+  }
+  long long total = 0;
+  for (int i = 0; i < q; ++i)
+  {
+    offsets[i] = (int)total;
+    for (int j = 0; j < counts[i]; ++j)
+    {
+      PairID const &e = buffer[(size_t)i * kk + j];
+      if (indices)
+        indices[total + j] = t.perm[e.first];
+      if (distances)
+        distances[total + j] = e.second;
+    }
+    total += counts[i];
+  }
+  offsets[q] = (int)total;
+  return total;
+}
+
+// Experimental::ordered_intersects(ray): TreeTraversal<..., OrderedSpatialPredicateTag>
+// (spatial/detail/ArborX_TreeTraversal.hpp:338-489): a priority queue of (node, distance(ray, box)) hands out the
+// leaves in order of entry distance; the callback sees every leaf whose box the ray hits (distance < inf), nearest
+// first, and may end the query.  Here every hit is recorded (limit > 0: the callback exits after `limit` hits).
+// Returns the number of (index, distance) records; rows in predicate order.  pass 1: indices == NULL counts.
+static int traverseOrderedRay(Tree const &t, Ray3 const &ray, int limit, std::vector<PairID> &out)
+{
+  float const inf = std::numeric_limits<float>::infinity();
+  out.clear();
+  if (t.n == 0)
+    return 0;
+  if (t.n == 1)
+  {
+    float const d = nearestDistance(t, ray, 0);
+    if (d != inf)
+      out.push_back(PairID{0, d});
+    return (int)out.size();
+  }
+  // PriorityQueue with CompareDistance (lhs.second > rhs.second): min-heap on the distance
+  std::vector<PairID> heap;
+  auto cmp = [](PairID const &a, PairID const &b) { return a.second > b.second; };
+  int node = t.n;
+  while (true)
+  {
+    if (t.isLeaf(node))
+    {
+      out.push_back(PairID{node, nearestDistance(t, ray, node)});
+      if (limit > 0 && (int)out.size() >= limit)
+        return (int)out.size();
+      if (heap.empty())
+        return (int)out.size();
+      std::pop_heap(heap.begin(), heap.end(), cmp);
+      node = heap.back().first;
+      heap.pop_back();
+    }
+    else
+    {
+      int const left_child = t.left_child[node - t.n];
+      int const right_child = t.getRope(left_child);
+      float const dl = nearestDistance(t, ray, left_child), dr = nearestDistance(t, ray, right_child);
+      PairID const lp{left_child, dl}, rp{right_child, dr};
+      PairID const &closer = dl < dr ? lp : rp;
+      PairID const &further = dl < dr ? rp : lp;
+      if (!heap.empty() && heap.front().second < closer.second)
+      {
+        std::pop_heap(heap.begin(), heap.end(), cmp);
+        node = heap.back().first;
+        heap.pop_back();
+        if (closer.second < inf)
+        {
+          heap.push_back(closer);
+          std::push_heap(heap.begin(), heap.end(), cmp);
+        }
+      }
+      else
+        node = closer.first;
+      if (further.second < inf)
+      {
+        heap.push_back(further);
+        std::push_heap(heap.begin(), heap.end(), cmp);
+      }
+    }
+  }
+}
+ORC_API long long orc_query_ordered_ray_crs(void *h, float const *rays, int q, int limit, int *offsets,
+                                            unsigned *indices, float *distances)
+{
+  Tree const &t = *(Tree *)h;
+  if (t.kind == PRIM_TRI)
+    return -1;
+  std::vector<std::vector<PairID>> rows(q);
+#pragma omp parallel for schedule(dynamic, 64)
+  for (int i = 0; i < q; ++i)
+    traverseOrderedRay(t, makeRay(rays + 6 * (size_t)i), limit, rows[i]);
+  long long total = 0;
+  for (int i = 0; i < q; ++i)
+  {
+    offsets[i] = (int)total;
+    for (size_t j = 0; j < rows[i].size(); ++j)
+    {
+      if (indices)
+        indices[total + j] = t.perm[rows[i][j].first];
+      if (distances)
+        distances[total + j] = rows[i][j].second;
+    }
+    total += (long long)rows[i].size();
   }
   offsets[q] = (int)total;
   return total;
