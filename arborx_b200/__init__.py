@@ -91,9 +91,14 @@ def intersects(geometry, kind=None):
     return Predicates("spatial", kind, _as_f32(geometry, _PRED_STRIDE[kind]))
 
 
-def nearest(points, k=1):
-    """nearest(Point, k) for a batch (Predicates.hpp:221-238); k may be a tensor of per-query k."""
-    return Predicates("nearest", POINT_PRED, _as_f32(points, 3), k)
+def nearest(geometry, k=1, kind=None):
+    """nearest(Geometry, k) for a batch (detail/ArborX_Predicates.hpp:58-80,130-135): [q, 3] points (k may be a
+    tensor of per-query k), [q, 6] boxes, [q, 4] spheres; rays ([q, 6] origin, direction) need kind=RAY_PRED."""
+    if not isinstance(geometry, torch.Tensor):
+        geometry = torch.as_tensor(geometry, dtype=torch.float32)
+    if kind is None:
+        kind = {3: POINT_PRED, 6: BOX_PRED, 4: SPHERE_PRED}[geometry.shape[-1]]
+    return Predicates("nearest", kind, _as_f32(geometry, _PRED_STRIDE[kind]), k)
 
 
 def make_intersects(points, r):
@@ -172,6 +177,23 @@ class BoundingVolumeHierarchy:
         self._h = h
 
     @classmethod
+    def from_indexed_triangles(cls, space, vertices, triangles):
+        """Triangles as vertex-index triples ([V, 3] float32 vertices, [T, 3] int32 indices): the access pattern
+        of benchmarks/triangulated_surface_distance (triangulated_surface_distance.cpp:34-58)."""
+        self = cls.__new__(cls)
+        self.kind = TRIANGLE
+        self._space = space
+        v = _as_f32(vertices, 3).to(space.device)
+        t = torch.as_tensor(triangles).to(device=space.device, dtype=torch.int32).reshape(-1, 3).contiguous()
+        h = C.c_void_p()
+        with torch.cuda.stream(space.stream):
+            _lib.check(lib().abx_bvh_build_indexed_triangles(space.handle, C.c_void_p(v.data_ptr()), v.shape[0],
+                                                             C.c_void_p(t.data_ptr()), t.shape[0], C.byref(h)))
+        self._values = (v, t)
+        self._h = h
+        return self
+
+    @classmethod
     def _from_sorted_codes(cls, space, values, codes, kind):
         self = cls.__new__(cls)
         self.kind = kind
@@ -232,7 +254,13 @@ class BoundingVolumeHierarchy:
             else:
                 k = predicates.k
                 want_d = C.byref(dist) if return_distances else None
-                if isinstance(k, torch.Tensor):
+                if predicates.kind != POINT_PRED:
+                    if host or isinstance(k, torch.Tensor):
+                        raise ValueError("nearest(Box | Sphere | Ray, k): device predicates, uniform k")
+                    _lib.check(L.abx_query_nearest_geom_crs(self._h, space.handle, predicates.kind,
+                                                            C.c_void_p(d.data_ptr()), q, int(k), C.byref(pol), alloc.fn,
+                                                            None, C.byref(off), C.byref(idx), want_d, C.byref(nnz)))
+                elif isinstance(k, torch.Tensor):
                     if host:
                         raise ValueError("per-query k needs device predicates")
                     kk = k.to(device=space.device, dtype=torch.int32).contiguous()

@@ -36,6 +36,7 @@ SIGNATURES = {
     "abx_profile_report": (_i64, [C.c_char_p, _i64]),
     "abx_bvh_build": (C.c_int, [_vp, C.c_int, _vp, _i64, _pp]),
     "abx_bvh_build_host": (C.c_int, [_vp, C.c_int, _vp, _i64, _pp]),
+    "abx_bvh_build_indexed_triangles": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _pp]),
     "abx_bvh_build_from_sorted_codes": (C.c_int, [_vp, C.c_int, _vp, _vp, _i64, _pp]),
     "abx_bvh_destroy": (C.c_int, [_vp]),
     "abx_bvh_size": (_i64, [_vp]),
@@ -46,6 +47,8 @@ SIGNATURES = {
     "abx_query_spatial_crs": (C.c_int, [_vp, _vp, C.c_int, _vp, _i64, _pol, ALLOC_FN, _vp, _pp, _pp, _pi64]),
     "abx_query_spatial_count": (C.c_int, [_vp, _vp, C.c_int, _vp, _i64, C.c_int, _i32, _vp]),
     "abx_query_nearest_crs": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _pol, ALLOC_FN, _vp, _pp, _pp, _pp, _pi64]),
+    "abx_query_nearest_geom_crs": (C.c_int, [_vp, _vp, C.c_int, _vp, _i64, _i32, _pol, ALLOC_FN, _vp, _pp, _pp, _pp,
+                                             _pi64]),
     "abx_query_spatial_crs_host": (C.c_int, [_vp, _vp, C.c_int, _vp, _i64, _pol, ALLOC_FN, _vp, _pp, _pp, _pi64]),
     "abx_query_nearest_crs_host": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _pol, ALLOC_FN, _vp, _pp, _pp, _pp, _pi64]),
     "abx_half_traversal_pairs": (C.c_int, [_vp, _vp, _f, _vp, _i64, _pi64]),

@@ -378,13 +378,41 @@ abx_status spatialCrs(abx_bvh *bvh, cudaStream_t s, int pred_kind, void const *p
 
 abx_status nearestCrs(abx_bvh *bvh, cudaStream_t s, void const *pts, int64_t q, int32_t k,
                              int32_t const *k_per_query, abx_policy const &policy, abx_alloc_fn alloc, void *user,
-                             int32_t **offsets_out, uint32_t **indices_out, float **distances_out, int64_t *nnz_out)
+                             int32_t **offsets_out, uint32_t **indices_out, float **distances_out, int64_t *nnz_out,
+                             int pred_kind)
 {
   if (q > 0 && !pts)
   {
     setError("null query points");
     return ABX_ERR_ARG;
   }
+  if (pred_kind != ABX_PRED_POINT3F && pred_kind != ABX_PRED_BOX3F && pred_kind != ABX_PRED_SPHERE3F &&
+      pred_kind != ABX_PRED_RAY3F)
+  {
+    setError("unknown predicate kind");
+    return ABX_ERR_ARG;
+  }
+  if (pred_kind != ABX_PRED_POINT3F && k_per_query)
+  {
+    setError("per-query k is implemented for nearest(Point, k)");
+    return ABX_ERR_ARG;
+  }
+  if (pred_kind != ABX_PRED_POINT3F && bvh->kind == ABX_PRIM_TRI3F)
+  {
+    setError("nearest(Box | Sphere | Ray, k) is defined for point and box primitives");
+    return ABX_ERR_ARG;
+  }
+  ABX_TRY(checkPredPointer(pred_kind, pts, q));
+  // nearest(Sphere, k): distance(Sphere, X) = max(distance(centre, X) - r, 0) ranks like the centre's distance
+  void const *const preds_in = pts;
+  TempBuffer<float> centres;
+  if (pred_kind == ABX_PRED_SPHERE3F)
+  {
+    ABX_TRY(centres.alloc(3 * (size_t)std::max<int64_t>(q, 1), s));
+    ABX_TRY(sphereCentres(s, (float const *)preds_in, q, centres.ptr));
+    pts = centres.ptr;
+  }
+  bool const geom = pred_kind == ABX_PRED_BOX3F || pred_kind == ABX_PRED_RAY3F;
   if (q < 0 || q >= (int64_t)1 << 30)
   {
     setError("number of predicates must be in [0, 2^30)");
@@ -443,7 +471,7 @@ abx_status nearestCrs(abx_bvh *bvh, cudaStream_t s, void const *pts, int64_t q, 
     return ABX_OK;
   TempBuffer<uint32_t> qperm;
   if (policy.sort_predicates && n > 1)
-    ABX_TRY(predicatePermutation(s, bvh, ABX_PRED_POINT3F, pts, q, qperm));
+    ABX_TRY(predicatePermutation(s, bvh, geom ? pred_kind : ABX_PRED_POINT3F, pts, q, qperm));
   // Rows are laid out for min(k, n) results, but a leaf at infinite (or NaN) distance is never
   // accepted (`distance < radius` with radius = +inf, TreeTraversal.hpp:255): such rows come out
   // short and the reference compacts them (CrsGraphWrapperImpl.hpp:296-318).  The kernel counts
@@ -453,8 +481,14 @@ abx_status nearestCrs(abx_bvh *bvh, cudaStream_t s, void const *pts, int64_t q, 
   ABX_TRY(counts.alloc((size_t)q + 1, s));
   ABX_TRY(missing.alloc(1, s));
   ABX_CUDA_TRY(cudaMemsetAsync(missing.ptr, 0, sizeof(unsigned long long), s));
-  ABX_TRY(nearestQuery(s, bvh, (float const *)pts, q, k, k_per_query, qperm.ptr, uniform ? nullptr : offsets, total,
-                       counts.ptr, *indices_out, (float *)dist, missing.ptr));
+  if (geom)
+    ABX_TRY(nearestGeomQuery(s, bvh, pred_kind, (float const *)pts, q, k, qperm.ptr, total, counts.ptr, *indices_out,
+                             (float *)dist, missing.ptr));
+  else
+    ABX_TRY(nearestQuery(s, bvh, (float const *)pts, q, k, k_per_query, qperm.ptr, uniform ? nullptr : offsets, total,
+                         counts.ptr, *indices_out, (float *)dist, missing.ptr));
+  if (pred_kind == ABX_PRED_SPHERE3F && dist) // rows still have their uniform stride here
+    ABX_TRY(sphereDistances(s, total, std::max(1, std::min(k, n)), (float const *)preds_in, (float *)dist));
   unsigned long long h_missing = 0;
   ABX_CUDA_TRY(cudaMemcpyAsync(&h_missing, missing.ptr, sizeof(h_missing), cudaMemcpyDeviceToHost, s));
   ABX_CUDA_TRY(cudaStreamSynchronize(s));
@@ -635,6 +669,60 @@ abx_status abx_bvh_build_host(void *stream, int prim_kind, const void *prims_hos
   return buildTree(s, prim_kind, dev.ptr, n, nullptr, out, /*want_wide=*/true);
 }
 
+// triangles given as vertex-index triples (the Triangles AccessTraits of
+// benchmarks/triangulated_surface_distance/triangulated_surface_distance.cpp:34-58): gathered into the flat form
+__global__ void gatherTrianglesKernel(float const *__restrict__ vertices, int64_t n_vertices,
+                                      int32_t const *__restrict__ tri3, int64_t n, float *__restrict__ flat9,
+                                      int *__restrict__ bad)
+{
+  int64_t const i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+  {
+    int64_t v = tri3[3 * i + c];
+    if (v < 0 || v >= n_vertices)
+    {
+      *bad = 1;
+      v = 0;
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+      flat9[9 * i + 3 * c + d] = vertices[3 * v + d];
+  }
+}
+
+abx_status abx_bvh_build_indexed_triangles(void *stream, const float *vertices_dev, int64_t n_vertices,
+                                           const int32_t *triangles_dev, int64_t n, abx_bvh **out)
+{
+  if (!out || n < 0 || n_vertices < 0 || (n > 0 && (!vertices_dev || !triangles_dev || n_vertices == 0)))
+  {
+    setError("bad argument");
+    return ABX_ERR_ARG;
+  }
+  *out = nullptr;
+  ABX_TRY(ensureDevice());
+  cudaStream_t s = (cudaStream_t)stream;
+  TempBuffer<float> flat;
+  TempBuffer<int> bad;
+  ABX_TRY(flat.alloc(9 * (size_t)std::max<int64_t>(n, 1), s));
+  ABX_TRY(bad.alloc(1, s));
+  ABX_CUDA_TRY(cudaMemsetAsync(bad.ptr, 0, sizeof(int), s));
+  if (n > 0)
+    ABX_LAUNCH(gatherTrianglesKernel, divUp(n, 256), 256, 0, s, vertices_dev, n_vertices, triangles_dev, n, flat.ptr,
+               bad.ptr);
+  int h_bad = 0;
+  ABX_CUDA_TRY(cudaMemcpyAsync(&h_bad, bad.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
+  ABX_CUDA_TRY(cudaStreamSynchronize(s));
+  if (h_bad)
+  {
+    setError("triangle vertex index out of range");
+    return ABX_ERR_ARG;
+  }
+  return buildTree(s, ABX_PRIM_TRI3F, flat.ptr, n, nullptr, out, /*want_wide=*/true);
+}
+
 abx_status abx_bvh_build_from_sorted_codes(void *stream, int prim_kind, const void *prims_dev,
                                            const uint64_t *sorted_codes_dev, int64_t n, abx_bvh **out)
 {
@@ -724,6 +812,20 @@ abx_status abx_query_nearest_crs(abx_bvh *bvh, void *stream, const void *points_
   abx_policy const p = policy ? *policy : defaultPolicy();
   return nearestCrs(bvh, (cudaStream_t)stream, points_dev, q, k, k_per_query_dev, p, alloc, user, offsets_dev,
                     indices_dev, distances_dev, nnz);
+}
+
+abx_status abx_query_nearest_geom_crs(abx_bvh *bvh, void *stream, int pred_kind, const void *preds_dev, int64_t q,
+                                      int32_t k, const abx_policy *policy, abx_alloc_fn alloc, void *user,
+                                      int32_t **offsets_dev, uint32_t **indices_dev, float **distances_dev, int64_t *nnz)
+{
+  if (!bvh || !offsets_dev || !indices_dev || !nnz)
+  {
+    setError("null argument");
+    return ABX_ERR_ARG;
+  }
+  abx_policy const p = policy ? *policy : defaultPolicy();
+  return nearestCrs(bvh, (cudaStream_t)stream, preds_dev, q, k, nullptr, p, alloc, user, offsets_dev, indices_dev,
+                    distances_dev, nnz, pred_kind);
 }
 
 // ---- host-buffer variants: H2D of the predicates and D2H of the CRS arrays are

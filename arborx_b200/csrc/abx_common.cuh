@@ -376,6 +376,11 @@ abx_status nearestQuery(cudaStream_t s, abx_bvh *bvh, float const *pts, int64_t 
                         int32_t const *k_per_query, uint32_t const *qperm, int32_t const *offsets, int64_t total_rows,
                         int32_t *counts, uint32_t *indices, float *distances,
                         unsigned long long *missing = nullptr, int pair_rank = -1);
+abx_status nearestGeomQuery(cudaStream_t s, abx_bvh *t, int pred_kind, float const *preds, int64_t q, int32_t k,
+                            uint32_t const *qperm, int64_t total_rows, int32_t *counts, uint32_t *indices,
+                            float *distances, unsigned long long *missing);
+abx_status sphereCentres(cudaStream_t s, float const *spheres4, int64_t q, float *pts3);
+abx_status sphereDistances(cudaStream_t s, int64_t total, int row, float const *spheres4, float *dist);
 abx_status compactRows(cudaStream_t s, int64_t q, int32_t const *old_offsets, int32_t const *new_offsets,
                        uint32_t const *old_idx, float const *old_dist, uint32_t *new_idx, float *new_dist);
 abx_status routeLaunch(cudaStream_t s, bool fill, int pred_kind, void const *preds, int64_t q, float const *radius,
@@ -423,9 +428,11 @@ abx_status spatialCrs(abx_bvh *bvh, cudaStream_t s, int pred_kind, void const *p
                       abx_policy const &policy, abx_alloc_fn alloc, void *user, int32_t **offsets_out,
                       uint32_t **indices_out, int64_t *nnz_out,
                       std::function<abx_status()> const &before_sync = nullptr);
+// pred_kind: ABX_PRED_POINT3F (pts = 3 floats each), ABX_PRED_BOX3F, ABX_PRED_SPHERE3F or ABX_PRED_RAY3F
 abx_status nearestCrs(abx_bvh *bvh, cudaStream_t s, void const *pts, int64_t q, int32_t k,
                       int32_t const *k_per_query, abx_policy const &policy, abx_alloc_fn alloc, void *user,
-                      int32_t **offsets_out, uint32_t **indices_out, float **distances_out, int64_t *nnz_out);
+                      int32_t **offsets_out, uint32_t **indices_out, float **distances_out, int64_t *nnz_out,
+                      int pred_kind = ABX_PRED_POINT3F);
 abx_status ensureDevice();
 // dbscan.cu
 abx_status dbscan(cudaStream_t s, float const *xyz, int64_t n, float eps, int32_t minpts, int impl, int algo,

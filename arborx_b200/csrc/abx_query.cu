@@ -531,6 +531,177 @@ __global__ void padShortRowsKernel(int64_t q, int k, int32_t const *__restrict__
   }
 }
 
+// ---- nearest(Box, k) / nearest(Ray, k) ---------------------------------------------------------------
+// Nearest<Geometry> with a query geometry other than a point (spatial/detail/ArborX_Predicates.hpp:58-80).  The
+// walk is the general (global-heap) form of nearestKernel with the predicate geometry's distance:
+//   box   distance(Box, Box) (geometry/algorithms/ArborX_Distance.hpp:166-197), kept squared until a row is
+//         written; a point leaf is the degenerate box, which gives the same per-axis deltas as
+//         distance(Point, Box) (:72-80 through ReverseDispatch)
+//   ray   distance(Ray, Box) = max(tmin, 0) if the ray hits the box, else +inf (geometry/ArborX_Ray.hpp:433-444):
+//         a length along the ray, not squared; leaves the ray misses are never accepted, so rows can be short
+// nearest(Sphere, k) needs no kernel: distance(Sphere, X) = max(distance(centre, X) - r, 0) (:83-108, :199-209)
+// orders like the centre's distance, so the host runs the point form and rewrites the distances.
+template <int QK>
+struct GeomQuery;
+template <>
+struct GeomQuery<ABX_PRED_BOX3F>
+{
+  float lo[3], hi[3];
+  __device__ __forceinline__ void load(float const *__restrict__ p, int64_t i)
+  {
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+    {
+      lo[d] = p[6 * i + d];
+      hi[d] = p[6 * i + 3 + d];
+    }
+  }
+  __device__ __forceinline__ float dist(float4 blo, float4 bhi) const
+  {
+    float const b_lo[3] = {blo.x, blo.y, blo.z}, b_hi[3] = {bhi.x, bhi.y, bhi.z};
+    float d2 = 0.f;
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+    {
+      float delta = 0.f;
+      if (lo[d] > b_hi[d])
+        delta = __fsub_rn(lo[d], b_hi[d]);
+      else if (b_lo[d] > hi[d])
+        delta = __fsub_rn(b_lo[d], hi[d]);
+      d2 = __fadd_rn(d2, __fmul_rn(delta, delta));
+    }
+    return d2;
+  }
+  static __device__ __forceinline__ float report(float d) { return __fsqrt_rn(d); }
+};
+template <>
+struct GeomQuery<ABX_PRED_RAY3F>
+{
+  Pred<ABX_PRED_RAY3F> ray;
+  __device__ __forceinline__ void load(float const *__restrict__ p, int64_t i) { ray.load(p, i); }
+  __device__ __forceinline__ float dist(float4 blo, float4 bhi) const { return ray.distance(blo, bhi); }
+  static __device__ __forceinline__ float report(float d) { return d; }
+};
+
+template <int QK, int LEAF_F4>
+__global__ void __launch_bounds__(kThreads)
+    nearestGeomKernel(Node64 const *__restrict__ nodes, float4 const *__restrict__ leaf_box, int n,
+                      float const *__restrict__ preds, int64_t q, unsigned const *__restrict__ qperm, int k,
+                      int row_stride, int32_t *__restrict__ counts, uint32_t *__restrict__ indices,
+                      float *__restrict__ distances, float2 *__restrict__ scratch,
+                      unsigned long long *__restrict__ missing)
+{
+  int64_t const t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (t >= q)
+    return;
+  int64_t const qi = qperm ? (int64_t)qperm[t] : t;
+  int64_t const base = qi * (int64_t)row_stride;
+  GeomQuery<QK> query;
+  query.load(preds, qi);
+  float const inf = __int_as_float(0x7f800000);
+  int found = 0;
+  if (n == 1)
+  {
+    // TreeTraversal.hpp:168-178: the single value is reported unconditionally
+    float4 const lo = __ldg(leaf_box);
+    float4 const hi = LEAF_F4 == 1 ? lo : __ldg(leaf_box + 1);
+    indices[base] = 0u;
+    if (distances)
+      distances[base] = GeomQuery<QK>::report(query.dist(lo, hi));
+    found = 1;
+  }
+  else
+  {
+    GlobalHeap heap;
+    heap.h = scratch + base;
+    heap.size = 0;
+    float radius = inf;
+    auto offer = [&](float d, unsigned idx) {
+      if (heap.size < k)
+        heap.push(d, idx);
+      else
+        heap.replaceTop(d, idx);
+      if (heap.size == k)
+        radius = heap.top();
+    };
+    unsigned long long stack[kStackSize];
+    int sp = 0;
+    int node = 0;
+    while (true)
+    {
+      float4 const *f = reinterpret_cast<float4 const *>(nodes + node);
+      float4 const a0 = __ldg(f), a1 = __ldg(f + 1), a2 = __ldg(f + 2), a3 = __ldg(f + 3);
+      int const lref = __float_as_int(a0.w), rref = __float_as_int(a1.w);
+      float const dl = query.dist(a0, a1), dr = query.dist(a2, a3);
+      bool const l_leaf = refIsLeaf(lref), r_leaf = refIsLeaf(rref);
+      // leaves are consumed on the spot, nearer one first
+      bool const swap = l_leaf && r_leaf && dr < dl;
+      if (l_leaf && !swap && dl < radius)
+        offer(dl, refOrig(lref));
+      if (r_leaf && dr < radius)
+        offer(dr, refOrig(rref));
+      if (swap && dl < radius)
+        offer(dl, refOrig(lref));
+      bool const go_l = !l_leaf && dl < radius;
+      bool const go_r = !r_leaf && dr < radius;
+      if (go_l || go_r)
+      {
+        bool const left_first = go_l && (dl <= dr || !go_r);
+        if (go_l && go_r)
+          stack[sp++] = ((unsigned long long)__float_as_uint(left_first ? dr : dl) << 32) |
+                        (unsigned)(left_first ? rref : lref);
+        node = left_first ? lref : rref;
+        continue;
+      }
+      bool popped = false;
+      while (sp > 0)
+      {
+        unsigned long long const e = stack[--sp];
+        if (__uint_as_float((unsigned)(e >> 32)) < radius)
+        {
+          node = (int)(unsigned)e;
+          popped = true;
+          break;
+        }
+      }
+      if (!popped)
+        break;
+    }
+    heap.sortAscending();
+    found = heap.size;
+    for (int i = 0; i < found; ++i)
+    {
+      float2 const e = heap.h[i];
+      indices[base + i] = __float_as_uint(e.y);
+      if (distances)
+        distances[base + i] = GeomQuery<QK>::report(e.x);
+    }
+  }
+  if (counts)
+    counts[qi] = found;
+  if (missing && found < row_stride)
+    atomicAdd(missing, (unsigned long long)(row_stride - found));
+}
+
+// distances[i] = max(distances[i] - r(query of i), 0): distance(Sphere, X) from distance(centre, X); rows of
+// `row` entries per query
+__global__ void sphereDistanceKernel(int64_t total, int row, float const *__restrict__ spheres4, float *__restrict__ dist)
+{
+  int64_t const i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total)
+    dist[i] = fmaxf(__fsub_rn(dist[i], spheres4[4 * (i / row) + 3]), 0.f);
+}
+__global__ void sphereCentresKernel(int64_t q, float const *__restrict__ spheres4, float *__restrict__ pts3)
+{
+  int64_t const i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < q)
+  {
+    pts3[3 * i] = spheres4[4 * i];
+    pts3[3 * i + 1] = spheres4[4 * i + 1];
+    pts3[3 * i + 2] = spheres4[4 * i + 2];
+  }
+}
+
 // rows [old_offsets[i], +count_i) -> [new_offsets[i], +count_i), count_i = new_offsets[i+1] - new_offsets[i]
 __global__ void compactRowsKernel(int64_t q, int32_t const *__restrict__ old_offsets,
                                   int32_t const *__restrict__ new_offsets, uint32_t const *__restrict__ old_idx,
@@ -846,6 +1017,66 @@ abx_status nearestQuery(cudaStream_t s, abx_bvh *t, float const *pts, int64_t q,
 #undef ABX_NEAREST
   if (pair_rank >= 0 && row_stride > 0)
     ABX_LAUNCH(padShortRowsKernel, divUp(q, 256), 256, 0, s, q, row_stride, counts, (int2 *)indices, distances);
+  return ABX_OK;
+}
+
+// nearest(Box | Ray, k): rows of min(k, n) slots, counts per row (rows can be short: leaves a ray misses)
+abx_status nearestGeomQuery(cudaStream_t s, abx_bvh *t, int pred_kind, float const *preds, int64_t q, int32_t k,
+                            uint32_t const *qperm, int64_t total_rows, int32_t *counts, uint32_t *indices,
+                            float *distances, unsigned long long *missing)
+{
+  if (q <= 0)
+    return ABX_OK;
+  int const n = (int)t->n;
+  if (t->kind == ABX_PRIM_TRI3F)
+  {
+    setError("nearest(Box | Ray, k) is defined for point and box primitives");
+    return ABX_ERR_ARG;
+  }
+  if (n == 0)
+  {
+    if (counts)
+      ABX_CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(int32_t) * q, s));
+    return ABX_OK;
+  }
+  int const grid = divUp(q, kThreads);
+  int const row_stride = std::max(0, std::min(k, n));
+  TempBuffer<float2> scratch;
+  ABX_TRY(scratch.alloc((size_t)std::max<int64_t>(total_rows, 1), s));
+  bool const boxes = t->kind == ABX_PRIM_BOX3F;
+#define ABX_GEOM(QK)                                                                                                  \
+  do                                                                                                                   \
+  {                                                                                                                    \
+    if (boxes)                                                                                                         \
+      ABX_LAUNCH((nearestGeomKernel<QK, 2>), grid, kThreads, 0, s, t->nodes, t->leaf_box, n, preds, q, qperm, k,       \
+                 row_stride, counts, indices, distances, scratch.ptr, missing);                                        \
+    else                                                                                                               \
+      ABX_LAUNCH((nearestGeomKernel<QK, 1>), grid, kThreads, 0, s, t->nodes, t->leaf_box, n, preds, q, qperm, k,       \
+                 row_stride, counts, indices, distances, scratch.ptr, missing);                                        \
+  } while (0)
+  if (pred_kind == ABX_PRED_BOX3F)
+    ABX_GEOM(ABX_PRED_BOX3F);
+  else if (pred_kind == ABX_PRED_RAY3F)
+    ABX_GEOM(ABX_PRED_RAY3F);
+  else
+  {
+    setError("nearestGeomQuery: box or ray predicates");
+    return ABX_ERR_ARG;
+  }
+#undef ABX_GEOM
+  return ABX_OK;
+}
+
+abx_status sphereCentres(cudaStream_t s, float const *spheres4, int64_t q, float *pts3)
+{
+  if (q > 0)
+    ABX_LAUNCH(sphereCentresKernel, divUp(q, 256), 256, 0, s, q, spheres4, pts3);
+  return ABX_OK;
+}
+abx_status sphereDistances(cudaStream_t s, int64_t total, int row, float const *spheres4, float *dist)
+{
+  if (total > 0 && row > 0)
+    ABX_LAUNCH(sphereDistanceKernel, divUp(total, 256), 256, 0, s, total, row, spheres4, dist);
   return ABX_OK;
 }
 

@@ -135,6 +135,16 @@ struct Pred<ABX_PRED_RAY3F>
     slab(oz, dz, lo.z, hi.z, tmin, tmax);
     return tmin <= tmax && tmax >= 0.f;
   }
+  // distance(Ray, Box) (geometry/ArborX_Ray.hpp:433-444): where the ray enters the box, +inf when it misses
+  __device__ __forceinline__ float distance(float4 lo, float4 hi) const
+  {
+    float const inf = __int_as_float(0x7f800000);
+    float tmin = -inf, tmax = inf;
+    slab(ox, dx, lo.x, hi.x, tmin, tmax);
+    slab(oy, dy, lo.y, hi.y, tmin, tmax);
+    slab(oz, dz, lo.z, hi.z, tmin, tmax);
+    return (tmin <= tmax && tmax >= 0.f) ? fmaxf(tmin, 0.f) : inf;
+  }
   __device__ __forceinline__ bool point(float4 p) const { return box(p, p); }
 };
 

@@ -19,6 +19,9 @@
  *   output form (Callbacks.hpp:86-110, CrsGraphWrapperImpl.hpp:86-110): f(int64_t query, unsigned value, Out &out)
  *       with out(x) emitting zero or more results of any trivially copyable type per match; query_crs() returns
  *       them as CRS rows in the original predicate order (count pass, scan, fill pass, like the reference's 2P path)
+ *   attach(predicates, data): the callback gets data[query] instead of the position (Predicates.hpp:221-238)
+ *   query_per_thread(tree, predicate, callback): one query from inside the caller's kernel (LinearBVH.hpp:112-122)
+ *   ordered_intersects_rays: leaves handed out nearest first along a ray, with early exit (TreeTraversal.hpp:338-489)
  * `query` is the position of the predicate in the batch (what the reference passes through attach()/getData()),
  * `value` the index of the primitive the tree was built on.  Predicates are visited one per thread in batch
  * order; pass a Morton-ordered batch (abx_morton32 + abx_sort_u32) for coherent warps. */
@@ -302,6 +305,294 @@ inline abx_status query_crs(abx_bvh const *bvh, cudaStream_t stream, SpatialPred
   if (cudaMallocAsync((void **)values_dev, sizeof(T) * (size_t)total, stream) != cudaSuccess)
     return ABX_ERR_CUDA;
   return detail::dispatchOutput<T>(v, stream, predicates, callback, nullptr, *offsets_dev, *values_dev);
+}
+
+// ---- attach(predicates, data) (detail/ArborX_Predicates.hpp:221-238, getData) -----------------------------------
+// The callback receives the datum attached to its predicate instead of the predicate's position in the batch:
+//   abx::cb::query(bvh, stream, abx::cb::attach(abx::cb::intersects_spheres(s, q), data_dev), Callback{});
+//   struct Callback { __device__ void operator()(MyData const &d, unsigned value) const; };   // or -> Control
+template <class T>
+struct AttachedPredicates
+{
+  SpatialPredicates predicates;
+  T const *data;
+};
+template <class T>
+inline AttachedPredicates<T> attach(SpatialPredicates const &predicates, T const *data_dev)
+{
+  return {predicates, data_dev};
+}
+namespace detail
+{
+template <class T, class Callback>
+struct AttachAdapter
+{
+  T const *data;
+  Callback cb;
+  __device__ auto operator()(int64_t query, unsigned value) const { return cb(data[query], value); }
+};
+} // namespace detail
+template <class T, class Callback>
+inline abx_status query(abx_bvh const *bvh, cudaStream_t stream, AttachedPredicates<T> const &attached,
+                        Callback const &callback)
+{
+  return query(bvh, stream, attached.predicates, detail::AttachAdapter<T, Callback>{attached.data, callback});
+}
+
+// ---- query(Experimental::PerThread{}, predicate, callback) (spatial/ArborX_LinearBVH.hpp:112-122) ----------------
+// A single query issued from inside the caller's own kernel by the calling thread.  DeviceTree is a plain struct
+// the caller passes to its kernel; the predicate is one of abx::Pred<ABX_PRED_*> (make_sphere / make_box /
+// make_point / make_ray), the callback takes the value (index of the primitive) and may return Control.
+struct DeviceTree
+{
+  Node64 const *nodes;
+  float4 const *leaf_box;
+  float4 const *leaf_tri;
+  int64_t n;
+  int prim_kind;
+};
+inline abx_status device_tree(abx_bvh const *bvh, DeviceTree *out)
+{
+  abx_device_view v;
+  abx_status const st = abx_bvh_device_view(bvh, &v);
+  if (st == ABX_OK)
+    *out = DeviceTree{(Node64 const *)v.nodes, (float4 const *)v.leaf_box, (float4 const *)v.leaf_tri, v.n, v.prim_kind};
+  return st;
+}
+__device__ inline Pred<ABX_PRED_SPHERE3F> make_sphere(float x, float y, float z, float r)
+{
+  Pred<ABX_PRED_SPHERE3F> p;
+  p.cx = x, p.cy = y, p.cz = z, p.r = r;
+  p.t = sqrtThreshold(r);
+  return p;
+}
+__device__ inline Pred<ABX_PRED_BOX3F> make_box(float lx, float ly, float lz, float hx, float hy, float hz)
+{
+  Pred<ABX_PRED_BOX3F> p;
+  p.lx = lx, p.ly = ly, p.lz = lz, p.hx = hx, p.hy = hy, p.hz = hz;
+  return p;
+}
+__device__ inline Pred<ABX_PRED_POINT3F> make_point(float x, float y, float z)
+{
+  Pred<ABX_PRED_POINT3F> p;
+  p.x = x, p.y = y, p.z = z;
+  return p;
+}
+__device__ inline Pred<ABX_PRED_RAY3F> make_ray(float ox, float oy, float oz, float dx, float dy, float dz)
+{
+  float const g[6] = {ox, oy, oz, dx, dy, dz};
+  Pred<ABX_PRED_RAY3F> p;
+  p.load(g, 0); // normalises the direction in double like the Ray constructor
+  return p;
+}
+namespace detail
+{
+template <class Callback>
+__device__ __forceinline__ bool invokeValue(Callback const &cb, unsigned value)
+{
+  if constexpr (std::is_same_v<decltype(cb(value)), Control>)
+    return cb(value) == Control::early_exit;
+  else
+  {
+    cb(value);
+    return false;
+  }
+}
+} // namespace detail
+template <int PRED, class Callback>
+__device__ inline void query_per_thread(DeviceTree const &tree, Pred<PRED> const &pred, Callback const &callback)
+{
+  if (tree.n == 0)
+    return;
+  bool const tri = tree.prim_kind == ABX_PRIM_TRI3F;
+  int const leaf_f4 = tree.prim_kind == ABX_PRIM_POINT3F ? 1 : 2;
+  if (tree.n == 1)
+  {
+    float4 const lo = __ldg(tree.leaf_box);
+    float4 const hi = leaf_f4 == 1 ? lo : __ldg(tree.leaf_box + 1);
+    if (pred.box(lo, hi) && (!tri || triangleLeafTest<PRED>(pred, tree.leaf_tri, 0)))
+      detail::invokeValue(callback, 0u);
+    return;
+  }
+  auto emit = [&](unsigned orig, int pos) {
+    if (tri && !triangleLeafTest<PRED>(pred, tree.leaf_tri, pos))
+      return false;
+    return detail::invokeValue(callback, orig);
+  };
+  if (leaf_f4 == 1)
+    traverseSpatial<1>(tree.nodes, tree.leaf_box, pred, emit);
+  else
+    traverseSpatial<2>(tree.nodes, tree.leaf_box, pred, emit);
+}
+
+// ---- Experimental::ordered_intersects(ray) (detail/ArborX_Predicates.hpp:103-127,148-156;
+//      TreeTraversal<..., OrderedSpatialPredicateTag>, detail/ArborX_TreeTraversal.hpp:338-489) --------------------
+// The leaves whose box the ray hits are handed to the callback nearest first (by where the ray enters the box,
+// distance(Ray, Box), geometry/ArborX_Ray.hpp:433-444); the callback may end the query (first-hit ray casting).
+//   callback(int64_t query, unsigned value, float distance)  -> void or Control
+// Point and box primitives.  Like the reference, the traversal keeps a priority queue of 64 (node, distance)
+// entries, and it shares the reference's corner case: when the queue is empty and the ray misses both children of
+// the node at hand, the walk still ends on that node's last leaf and calls the callback for it (with an infinite
+// distance here; the reference's callback sees the leaf without a distance).
+struct OrderedRayPredicates
+{
+  float const *rays;
+  int64_t q;
+};
+inline OrderedRayPredicates ordered_intersects_rays(float const *rays6_dev, int64_t q) { return {rays6_dev, q}; }
+
+namespace detail
+{
+struct OrderedHeap // min-heap on the distance; item >= 0: internal node, item < 0: leaf at sorted position ~item
+{
+  static constexpr int kCapacity = 64;
+  int item[kCapacity];
+  float dist[kCapacity];
+  int size = 0;
+  __device__ void push(int it, float d)
+  {
+    int pos = size++;
+    while (pos > 0)
+    {
+      int const parent = (pos - 1) / 2;
+      if (!(d < dist[parent]))
+        break;
+      item[pos] = item[parent];
+      dist[pos] = dist[parent];
+      pos = parent;
+    }
+    item[pos] = it;
+    dist[pos] = d;
+  }
+  __device__ void pop(int &it, float &d)
+  {
+    it = item[0];
+    d = dist[0];
+    int const last_item = item[size - 1];
+    float const last_d = dist[size - 1];
+    --size;
+    int pos = 0;
+    while (true)
+    {
+      int child = 2 * pos + 1;
+      if (child >= size)
+        break;
+      if (child + 1 < size && dist[child + 1] < dist[child])
+        ++child;
+      if (!(dist[child] < last_d))
+        break;
+      item[pos] = item[child];
+      dist[pos] = dist[child];
+      pos = child;
+    }
+    if (size > 0)
+    {
+      item[pos] = last_item;
+      dist[pos] = last_d;
+    }
+  }
+};
+
+template <class Callback>
+__device__ __forceinline__ bool invokeOrdered(Callback const &cb, int64_t query, unsigned value, float distance)
+{
+  if constexpr (std::is_same_v<decltype(cb(query, value, distance)), Control>)
+    return cb(query, value, distance) == Control::early_exit;
+  else
+  {
+    cb(query, value, distance);
+    return false;
+  }
+}
+
+template <int LEAF_F4, class Callback>
+__global__ void __launch_bounds__(kThreads)
+    orderedRayKernel(Node64 const *__restrict__ nodes, float4 const *__restrict__ leaf_box, int64_t n,
+                     float const *__restrict__ rays, int64_t q, Callback cb)
+{
+  int64_t const qi = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (qi >= q)
+    return;
+  Pred<ABX_PRED_RAY3F> ray;
+  ray.load(rays, qi);
+  float const inf = __int_as_float(0x7f800000);
+  auto leafValue = [&](int pos) { return __float_as_uint(__ldg(leaf_box + (size_t)LEAF_F4 * pos).w); };
+  if (n == 1)
+  {
+    float4 const lo = __ldg(leaf_box);
+    float4 const hi = LEAF_F4 == 1 ? lo : __ldg(leaf_box + 1);
+    float const d = ray.distance(lo, hi);
+    if (d != inf)
+      invokeOrdered(cb, qi, 0u, d);
+    return;
+  }
+  OrderedHeap heap;
+  int cur = 0; // the root
+  float cur_d = 0.f;
+  while (true)
+  {
+    if (cur < 0)
+    {
+      if (invokeOrdered(cb, qi, leafValue(~cur), cur_d))
+        return;
+      if (heap.size == 0)
+        return;
+      heap.pop(cur, cur_d);
+      continue;
+    }
+    float4 const *f = reinterpret_cast<float4 const *>(nodes + cur);
+    float4 const a0 = __ldg(f), a1 = __ldg(f + 1), a2 = __ldg(f + 2), a3 = __ldg(f + 3);
+    int const lref = __float_as_int(a0.w), rref = __float_as_int(a1.w);
+    int const rl = __float_as_int(a2.w), rr = __float_as_int(a3.w);
+    float const dl = ray.distance(a0, a1), dr = ray.distance(a2, a3);
+    int const litem = refIsLeaf(lref) ? ~rl : lref, ritem = refIsLeaf(rref) ? ~rr : rref;
+    bool const left_closer = dl < dr;
+    int const c_item = left_closer ? litem : ritem, f_item = left_closer ? ritem : litem;
+    float const c_d = left_closer ? dl : dr, f_d = left_closer ? dr : dl;
+    if (heap.size > 0 && heap.dist[0] < c_d)
+    {
+      heap.pop(cur, cur_d);
+      if (c_d < inf && heap.size < OrderedHeap::kCapacity)
+        heap.push(c_item, c_d);
+    }
+    else if (c_d < inf)
+    {
+      cur = c_item;
+      cur_d = c_d;
+    }
+    else
+    {
+      // queue empty and the ray misses both children: the reference walks down the right children and calls the
+      // callback for the last leaf of this node (TreeTraversal.hpp:474-482 with both distances infinite)
+      invokeOrdered(cb, qi, leafValue(rr), inf);
+      return;
+    }
+    if (f_d < inf && heap.size < OrderedHeap::kCapacity)
+      heap.push(f_item, f_d);
+  }
+}
+} // namespace detail
+
+template <class Callback>
+inline abx_status query(abx_bvh const *bvh, cudaStream_t stream, OrderedRayPredicates const &predicates,
+                        Callback const &callback)
+{
+  abx_device_view v;
+  abx_status st = abx_bvh_device_view(bvh, &v);
+  if (st != ABX_OK)
+    return st;
+  if (v.n == 0 || predicates.q <= 0)
+    return ABX_OK;
+  if (v.prim_kind == ABX_PRIM_TRI3F)
+    return ABX_ERR_ARG; // distance(Ray, Triangle) is not defined in the reference either
+  int const grid = (int)((predicates.q + kThreads - 1) / kThreads);
+  if (v.prim_kind == ABX_PRIM_POINT3F)
+    detail::orderedRayKernel<1><<<grid, kThreads, 0, stream>>>((Node64 const *)v.nodes, (float4 const *)v.leaf_box, v.n,
+                                                             predicates.rays, predicates.q, callback);
+  else
+    detail::orderedRayKernel<2><<<grid, kThreads, 0, stream>>>((Node64 const *)v.nodes, (float4 const *)v.leaf_box, v.n,
+                                                             predicates.rays, predicates.q, callback);
+  return cudaGetLastError() == cudaSuccess ? ABX_OK : ABX_ERR_CUDA;
 }
 
 } // namespace cb

@@ -105,6 +105,11 @@ ABX_API int64_t abx_profile_report(char *buf, int64_t capacity);
 ABX_API abx_status abx_bvh_build(void *stream, int prim_kind, const void *prims_dev, int64_t n, abx_bvh **out);
 /* same with primitives in host memory: H2D copy is part of the call */
 ABX_API abx_status abx_bvh_build_host(void *stream, int prim_kind, const void *prims_host, int64_t n, abx_bvh **out);
+/* triangles as vertex-index triples over a shared vertex array (the Triangles AccessTraits of
+ * benchmarks/triangulated_surface_distance/triangulated_surface_distance.cpp:34-58): vertices_dev 3 floats each,
+ * triangles_dev 3 int32 each; the tree is the one abx_bvh_build(ABX_PRIM_TRI3F) gives for the expanded corners */
+ABX_API abx_status abx_bvh_build_indexed_triangles(void *stream, const float *vertices_dev, int64_t n_vertices,
+                                                   const int32_t *triangles_dev, int64_t n, abx_bvh **out);
 ABX_API abx_status abx_bvh_destroy(abx_bvh *bvh);
 ABX_API int64_t abx_bvh_size(const abx_bvh *bvh);               /* size()  :75-76 */
 ABX_API int abx_bvh_empty(const abx_bvh *bvh);                  /* empty() :78-79 */
@@ -138,6 +143,16 @@ ABX_API abx_status abx_query_nearest_crs(abx_bvh *bvh, void *stream, const void 
                                  const int32_t *k_per_query_dev, const abx_policy *policy, abx_alloc_fn alloc,
                                  void *user, int32_t **offsets_dev, uint32_t **indices_dev, float **distances_dev,
                                  int64_t *nnz);
+/* nearest(Geometry, k) for the other predicate geometries of detail/ArborX_Predicates.hpp:58-80 over point and box
+ * primitives: ABX_PRED_BOX3F (distance(Box, Box), geometry/algorithms/ArborX_Distance.hpp:166-197),
+ * ABX_PRED_SPHERE3F (max(distance(centre, X) - r, 0), :83-108,199-209), ABX_PRED_RAY3F (distance(Ray, Box) = the
+ * length along the ray to where it enters the box, geometry/ArborX_Ray.hpp:433-444: the reference's way of ray
+ * casting with nearest queries; boxes the ray misses are at infinite distance and never reported, so rows can be
+ * shorter than k), ABX_PRED_POINT3F (same as abx_query_nearest_crs).  Uniform k. */
+ABX_API abx_status abx_query_nearest_geom_crs(abx_bvh *bvh, void *stream, int pred_kind, const void *preds_dev,
+                                              int64_t q, int32_t k, const abx_policy *policy, abx_alloc_fn alloc,
+                                              void *user, int32_t **offsets_dev, uint32_t **indices_dev,
+                                              float **distances_dev, int64_t *nnz);
 /* Host-buffer variants (end-to-end path): predicates in host memory, results
  * copied into host arrays obtained from `alloc_host` (which: as above). */
 ABX_API abx_status abx_query_spatial_crs_host(abx_bvh *bvh, void *stream, int pred_kind, const void *preds_host, int64_t q,

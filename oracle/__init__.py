@@ -67,6 +67,8 @@ def lib():
         "orc_query_spatial_count": (None, [vp, C.c_int, fp, C.c_int, C.c_int, ip, llp]),
         "orc_query_spatial_crs": (C.c_longlong, [vp, C.c_int, fp, C.c_int, C.c_int, C.c_int, ip, up]),
         "orc_query_nearest_crs": (C.c_longlong, [vp, fp, C.c_int, C.c_int, ip, C.c_int, ip, up, fp, llp]),
+        "orc_query_nearest_geom_crs": (C.c_longlong, [vp, C.c_int, fp, C.c_int, C.c_int, C.c_int, ip, up, fp]),
+        "orc_query_ordered_ray_crs": (C.c_longlong, [vp, fp, C.c_int, C.c_int, ip, up, fp]),
         "orc_half_traversal_pairs": (C.c_longlong, [vp, C.c_float, up, C.c_longlong]),
         "orc_union_find_merge": (None, [ip, C.c_int, C.c_int]),
         "orc_union_find_merge_into": (None, [ip, C.c_int, C.c_int]),
@@ -173,6 +175,34 @@ class Tree:
                                           _p(ctr, C.c_longlong))
         res = (offsets, indices[:nnz], dists[:nnz])
         return res + (ctr,) if counters else res
+
+    def nearest_geom_crs(self, preds, kind, k, sort_predicates=True):
+        """nearest(Box | Sphere | Ray | Point, k) -> (offsets, indices, distances)."""
+        preds = _f32(preds).reshape(-1, PRED_STRIDE[kind])
+        q = preds.shape[0]
+        offsets = np.zeros(q + 1, np.int32)
+        indices = np.empty(q * max(int(k), 0), np.uint32)
+        dists = np.empty(q * max(int(k), 0), np.float32)
+        nnz = lib().orc_query_nearest_geom_crs(self._h, kind, _p(preds, C.c_float), q, int(k), int(sort_predicates),
+                                               _p(offsets, C.c_int), _p(indices, C.c_uint), _p(dists, C.c_float))
+        if nnz < 0:
+            raise ValueError("nearest(geometry, k): point and box primitives only")
+        return offsets, indices[:nnz], dists[:nnz]
+
+    def ordered_ray_crs(self, rays, limit=0):
+        """ordered_intersects(ray): per ray the leaves in the order the reference's traversal hands them to the
+        callback (limit > 0: the callback exits after `limit` calls) -> (offsets, indices, distances)."""
+        rays = _f32(rays).reshape(-1, 6)
+        q = rays.shape[0]
+        offsets = np.zeros(q + 1, np.int32)
+        nnz = lib().orc_query_ordered_ray_crs(self._h, _p(rays, C.c_float), q, int(limit), _p(offsets, C.c_int), None, None)
+        if nnz < 0:
+            raise ValueError("ordered_intersects(ray): point and box primitives only")
+        indices = np.empty(nnz, np.uint32)
+        dists = np.empty(nnz, np.float32)
+        lib().orc_query_ordered_ray_crs(self._h, _p(rays, C.c_float), q, int(limit), _p(offsets, C.c_int),
+                                        _p(indices, C.c_uint), _p(dists, C.c_float))
+        return offsets, indices, dists
 
     def half_pairs(self, r):
         cnt = lib().orc_half_traversal_pairs(self._h, C.c_float(r), None, 0)

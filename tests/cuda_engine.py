@@ -52,6 +52,13 @@ class _CudaTree:
         self.space.fence()
         return off.cpu().numpy(), idx.cpu().numpy().view(np.uint32), dist.cpu().numpy()
 
+    def nearest_geom_crs(self, preds, kind, k, sort_predicates=True):
+        stride = {0: 4, 1: 6, 2: 3, 3: 6}[kind]
+        p = abx.nearest(_dev(np.asarray(preds, np.float32).reshape(-1, stride)), int(k), kind)
+        idx, off, dist = self.bvh.query(self.space, p, abx.TraversalPolicy(0, sort_predicates), return_distances=True)
+        self.space.fence()
+        return off.cpu().numpy(), idx.cpu().numpy().view(np.uint32), dist.cpu().numpy()
+
     def half_pairs(self, r):
         pairs = self.bvh.half_traversal_pairs(self.space, r)
         self.space.fence()
