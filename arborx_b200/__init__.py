@@ -20,7 +20,7 @@ SPHERE_PRED, BOX_PRED, POINT_PRED, RAY_PRED = 0, 1, 2, 3  # predicate geometries
 _PRIM_STRIDE = {POINT: 3, BOX: 6, TRIANGLE: 9}
 _PRED_STRIDE = {SPHERE_PRED: 4, BOX_PRED: 6, POINT_PRED: 3, RAY_PRED: 6}
 
-__all__ = ["ExecutionSpace", "BoundingVolumeHierarchy", "BVH", "TraversalPolicy", "HostBufferPool", "intersects", "nearest",
+__all__ = ["ExecutionSpace", "BoundingVolumeHierarchy", "BVH", "TraversalPolicy", "HostBufferPool", "BruteForce", "intersects", "nearest",
            "make_intersects", "make_nearest", "query", "dbscan", "DBSCANParameters", "SearchException",
            "POINT", "BOX", "TRIANGLE", "launch_count"]
 
@@ -326,41 +326,93 @@ class BoundingVolumeHierarchy:
 BVH = BoundingVolumeHierarchy
 
 
-def _rows_from_pairs(keys, vals, n):
-    """CRS (offsets [n + 1] int32, indices) of vals grouped by keys (rows in ascending key order)."""
-    order = torch.argsort(keys, stable=True)
-    offsets = torch.zeros(n + 1, dtype=torch.int32, device=keys.device)
-    offsets[1:] = torch.cumsum(torch.bincount(keys, minlength=n), 0).to(torch.int32)
-    return offsets, vals[order].to(torch.int32)
+def _neighbor_list(space, points, radius, full):
+    pts = _as_f32(points, 3).to(space.device)
+    alloc = _Allocator(space.device)
+    off, idx, nnz = C.c_void_p(), C.c_void_p(), C.c_int64()
+    L = lib()
+    fn = L.abx_find_full_neighbor_list if full else L.abx_find_half_neighbor_list
+    with torch.cuda.stream(space.stream):
+        _lib.check(fn(space.handle, C.c_void_p(pts.data_ptr()), pts.shape[0], float(radius), alloc.fn, None,
+                      C.byref(off), C.byref(idx), C.byref(nnz)))
+    out = alloc.out
+    alloc.out, alloc.fn = {}, None
+    return out[0], out.get(1, torch.empty(0, dtype=torch.int32, device=space.device))
 
 
 def find_half_neighbor_list(space, points, radius):
     """Experimental::findHalfNeighborList (spatial/detail/ArborX_NeighborList.hpp:47-110): every unordered pair of
-    points within `radius` appears once; row i holds the partners j of the pairs the half traversal reports as
-    (j, i), i.e. (value1, value2) with value2 the later leaf in the tree's order.  -> (offsets, indices); the order
-    inside a row is unspecified in the reference (atomics), ascending partner order here."""
-    pts = _as_f32(points, 3)
-    n = pts.shape[0]
-    bvh = BoundingVolumeHierarchy(space, pts.to(space.device), POINT)
-    pairs = bvh.half_traversal_pairs(space, radius).long()
-    with torch.cuda.stream(space.stream):
-        # sort by (row, partner): partner order first, then a stable sort by row
-        o = torch.argsort(pairs[:, 0], stable=True)
-        return _rows_from_pairs(pairs[o, 1], pairs[o, 0], n)
+    points within `radius` appears once, in the row of the point the half traversal reports second.
+    -> (offsets, indices); the order inside a row is unspecified, as in the reference."""
+    return _neighbor_list(space, points, radius, False)
 
 
 def find_full_neighbor_list(space, points, radius):
     """Experimental::findFullNeighborList (ArborX_NeighborList.hpp:112-190): the symmetric list, every pair in both
     rows (the half list expanded, ArborX_ExpandHalfToFull.hpp:24-72)."""
-    pts = _as_f32(points, 3)
-    n = pts.shape[0]
-    bvh = BoundingVolumeHierarchy(space, pts.to(space.device), POINT)
-    pairs = bvh.half_traversal_pairs(space, radius).long()
-    with torch.cuda.stream(space.stream):
-        a = torch.cat([pairs[:, 0], pairs[:, 1]])
-        b = torch.cat([pairs[:, 1], pairs[:, 0]])
-        o = torch.argsort(b, stable=True)
-        return _rows_from_pairs(a[o], b[o], n)
+    return _neighbor_list(space, points, radius, True)
+
+
+class BruteForce:
+    """ArborX::BruteForce (spatial/ArborX_BruteForce.hpp:42-160): the BVH's query interface answered by exhaustive
+    tests; point and box primitives."""
+
+    def __init__(self, space, values, kind=None):
+        if not isinstance(values, torch.Tensor):
+            values = torch.as_tensor(values, dtype=torch.float32)
+        if kind is None:
+            kind = {3: POINT, 6: BOX}[values.shape[-1]]
+        self.kind = kind
+        v = _as_f32(values, _PRIM_STRIDE[kind]).to(space.device)
+        h = C.c_void_p()
+        with torch.cuda.stream(space.stream):
+            _lib.check(lib().abx_brute_create(space.handle, kind, C.c_void_p(v.data_ptr()), v.shape[0], C.byref(h)))
+        self._values = v
+        self._h = h
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                lib().abx_brute_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def size(self):
+        return lib().abx_brute_size(self._h)
+
+    def empty(self):
+        return self.size() == 0
+
+    def bounds(self):
+        out = (C.c_float * 6)()
+        _lib.check(lib().abx_brute_bounds(self._h, out))
+        return torch.tensor(list(out), dtype=torch.float32)
+
+    def query(self, space, predicates, return_distances=False):
+        d = predicates.data.to(space.device)
+        q = d.shape[0]
+        alloc = _Allocator(space.device)
+        off, idx, dist = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        nnz = C.c_int64()
+        L = lib()
+        with torch.cuda.stream(space.stream):
+            if predicates.tag == "spatial":
+                _lib.check(L.abx_brute_query_spatial_crs(self._h, space.handle, predicates.kind, C.c_void_p(d.data_ptr()),
+                                                         q, alloc.fn, None, C.byref(off), C.byref(idx), C.byref(nnz)))
+            else:
+                if predicates.kind != POINT_PRED:
+                    raise ValueError("BruteForce: nearest(Point, k)")
+                _lib.check(L.abx_brute_query_nearest_crs(self._h, space.handle, C.c_void_p(d.data_ptr()), q,
+                                                         int(predicates.k), alloc.fn, None, C.byref(off), C.byref(idx),
+                                                         C.byref(dist) if return_distances else None, C.byref(nnz)))
+        out = alloc.out
+        alloc.out, alloc.fn = {}, None
+        indices = out.get(1, torch.empty(0, dtype=torch.int32, device=space.device))
+        if return_distances:
+            return indices, out[0], out.get(2, torch.empty(0, dtype=torch.float32, device=space.device))
+        return indices, out[0]
 
 
 def query(tree, space, predicates, policy=None, **kw):

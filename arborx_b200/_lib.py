@@ -52,6 +52,14 @@ SIGNATURES = {
     "abx_query_spatial_crs_host": (C.c_int, [_vp, _vp, C.c_int, _vp, _i64, _pol, ALLOC_FN, _vp, _pp, _pp, _pi64]),
     "abx_query_nearest_crs_host": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _pol, ALLOC_FN, _vp, _pp, _pp, _pp, _pi64]),
     "abx_half_traversal_pairs": (C.c_int, [_vp, _vp, _f, _vp, _i64, _pi64]),
+    "abx_find_half_neighbor_list": (C.c_int, [_vp, _vp, _i64, _f, ALLOC_FN, _vp, _pp, _pp, _pi64]),
+    "abx_find_full_neighbor_list": (C.c_int, [_vp, _vp, _i64, _f, ALLOC_FN, _vp, _pp, _pp, _pi64]),
+    "abx_brute_create": (C.c_int, [_vp, C.c_int, _vp, _i64, _pp]),
+    "abx_brute_destroy": (C.c_int, [_vp]),
+    "abx_brute_size": (_i64, [_vp]),
+    "abx_brute_bounds": (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    "abx_brute_query_spatial_crs": (C.c_int, [_vp, _vp, C.c_int, _vp, _i64, ALLOC_FN, _vp, _pp, _pp, _pi64]),
+    "abx_brute_query_nearest_crs": (C.c_int, [_vp, _vp, _vp, _i64, _i32, ALLOC_FN, _vp, _pp, _pp, _pp, _pi64]),
     "abx_dbscan": (C.c_int, [_vp, _vp, _i64, _f, _i32, C.c_int, C.c_int, _vp]),
     "abx_dbscan_host": (C.c_int, [_vp, _vp, _i64, _f, _i32, C.c_int, C.c_int, _vp]),
     "abx_dist_merge_crs": (C.c_int, [_vp, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),

@@ -537,6 +537,90 @@ abx_status nearestCrs(abx_bvh *bvh, cudaStream_t s, void const *pts, int64_t q, 
 
 } // namespace abx
 
+// ---- Experimental::findHalfNeighborList / findFullNeighborList (spatial/detail/ArborX_NeighborList.hpp:47-192,
+//      ArborX_ExpandHalfToFull.hpp:24-72): CRS neighbour lists from the half traversal's pair list ----
+namespace abx
+{
+namespace
+{
+// pass 1: rows[e] = row of entry e, counts[row] += 1; entry e < m: pair e as (second -> first); full lists add the
+// mirrored entries e >= m as (first -> second)
+__global__ void neighborRowsKernel(uint32_t const *__restrict__ pairs, int64_t m, bool full, uint32_t *__restrict__ rows,
+                                   uint32_t *__restrict__ vals, int32_t *__restrict__ counts)
+{
+  int64_t const e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t const total = full ? 2 * m : m;
+  if (e >= total)
+    return;
+  int64_t const p = e < m ? e : e - m;
+  uint32_t const a = pairs[2 * p], b = pairs[2 * p + 1];
+  uint32_t const row = e < m ? b : a, val = e < m ? a : b;
+  rows[e] = row;
+  vals[e] = val;
+  atomicAdd(counts + row, 1);
+}
+__global__ void gatherU32Kernel(uint32_t const *__restrict__ src, uint32_t const *__restrict__ perm, int64_t m,
+                                uint32_t *__restrict__ dst)
+{
+  int64_t const i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m)
+    dst[i] = src[perm[i]];
+}
+} // namespace
+
+abx_status neighborList(cudaStream_t s, float const *xyz, int64_t n, float radius, bool full, abx_alloc_fn alloc,
+                               void *user, int32_t **offsets_out, uint32_t **indices_out, int64_t *nnz_out)
+{
+  *nnz_out = 0;
+  *indices_out = nullptr;
+  void *off_v = nullptr, *idx_v = nullptr;
+  ABX_TRY(allocOut(alloc, user, 0, sizeof(int32_t) * (size_t)(n + 1), s, &off_v));
+  int32_t *offsets = (int32_t *)off_v;
+  *offsets_out = offsets;
+  ABX_CUDA_TRY(cudaMemsetAsync(offsets, 0, sizeof(int32_t) * (size_t)(n + 1), s));
+  abx_bvh *tree = nullptr;
+  ABX_TRY(buildTree(s, ABX_PRIM_POINT3F, xyz, n, nullptr, &tree));
+  struct Guard
+  {
+    abx_bvh *t;
+    ~Guard() { abx_bvh_destroy(t); }
+  } guard{tree};
+  // the pairs: count, then fill
+  TempBuffer<unsigned long long> cnt;
+  ABX_TRY(cnt.alloc(1, s));
+  ABX_TRY(halfTraversalPairs(s, tree, radius, nullptr, 0, cnt.ptr));
+  unsigned long long m = 0;
+  ABX_CUDA_TRY(cudaMemcpyAsync(&m, cnt.ptr, sizeof(m), cudaMemcpyDeviceToHost, s));
+  ABX_CUDA_TRY(cudaStreamSynchronize(s));
+  int64_t const total = (int64_t)(full ? 2 * m : m);
+  if (total >= (int64_t)1 << 30)
+  {
+    setError("neighbour list: more than 2^30 entries");
+    return ABX_ERR_ARG;
+  }
+  *nnz_out = total;
+  ABX_TRY(allocOut(alloc, user, 1, sizeof(uint32_t) * (size_t)total, s, &idx_v));
+  *indices_out = (uint32_t *)idx_v;
+  if (total == 0)
+    return ABX_OK;
+  TempBuffer<uint32_t> pairs, rows, vals, perm;
+  ABX_TRY(pairs.alloc(2 * (size_t)m, s));
+  ABX_TRY(rows.alloc((size_t)total, s));
+  ABX_TRY(vals.alloc((size_t)total, s));
+  ABX_TRY(perm.alloc((size_t)total, s));
+  ABX_TRY(halfTraversalPairs(s, tree, radius, pairs.ptr, (int64_t)m, cnt.ptr));
+  ABX_LAUNCH(neighborRowsKernel, divUp(total, 256), 256, 0, s, pairs.ptr, (int64_t)m, full, rows.ptr, vals.ptr, offsets);
+  ABX_TRY(exclusiveScanI32(s, offsets, offsets, n + 1));
+  // group the entries by row: stable sort of (row, entry), then one gather
+  int bits = 1;
+  while (bits < 32 && ((int64_t)1 << bits) < n)
+    ++bits;
+  ABX_TRY(sortPairsU32(s, rows.ptr, perm.ptr, total, true, bits, /*fixup=*/false));
+  ABX_LAUNCH(gatherU32Kernel, divUp(total, 256), 256, 0, s, vals.ptr, perm.ptr, total, *indices_out);
+  return ABX_OK;
+}
+} // namespace abx
+
 using namespace abx;
 
 extern "C"
@@ -939,6 +1023,29 @@ abx_status abx_half_traversal_pairs(abx_bvh *bvh, void *stream, float r, uint32_
   ABX_CUDA_TRY(cudaStreamSynchronize(s));
   *count = (int64_t)h;
   return ABX_OK;
+}
+
+abx_status abx_find_half_neighbor_list(void *stream, const float *xyz_dev, int64_t n, float radius, abx_alloc_fn alloc,
+                                       void *user, int32_t **offsets_dev, uint32_t **indices_dev, int64_t *nnz)
+{
+  ABX_TRY(ensureDevice());
+  if (!offsets_dev || !indices_dev || !nnz || n < 0 || (n > 0 && !xyz_dev))
+  {
+    setError("bad argument");
+    return ABX_ERR_ARG;
+  }
+  return neighborList((cudaStream_t)stream, xyz_dev, n, radius, false, alloc, user, offsets_dev, indices_dev, nnz);
+}
+abx_status abx_find_full_neighbor_list(void *stream, const float *xyz_dev, int64_t n, float radius, abx_alloc_fn alloc,
+                                       void *user, int32_t **offsets_dev, uint32_t **indices_dev, int64_t *nnz)
+{
+  ABX_TRY(ensureDevice());
+  if (!offsets_dev || !indices_dev || !nnz || n < 0 || (n > 0 && !xyz_dev))
+  {
+    setError("bad argument");
+    return ABX_ERR_ARG;
+  }
+  return neighborList((cudaStream_t)stream, xyz_dev, n, radius, true, alloc, user, offsets_dev, indices_dev, nnz);
 }
 
 abx_status abx_dbscan(void *stream, const float *xyz_dev, int64_t n, float eps, int32_t minpts, int implementation,

@@ -170,6 +170,32 @@ ABX_API abx_status abx_query_nearest_crs_host(abx_bvh *bvh, void *stream, const 
 ABX_API abx_status abx_half_traversal_pairs(abx_bvh *bvh, void *stream, float r, uint32_t *pairs_dev, int64_t capacity,
                                     int64_t *count);
 
+/* Experimental::findHalfNeighborList / findFullNeighborList (spatial/detail/ArborX_NeighborList.hpp:47-192,
+ * ArborX_ExpandHalfToFull.hpp:24-72): CRS neighbour lists of a point cloud within `radius`.  Half: every unordered
+ * pair once, in the row of the point the half traversal reports second; full: every pair in both rows.  The order
+ * inside a row is unspecified (the reference fills rows with atomics). */
+ABX_API abx_status abx_find_half_neighbor_list(void *stream, const float *xyz_dev, int64_t n, float radius,
+                                               abx_alloc_fn alloc, void *user, int32_t **offsets_dev,
+                                               uint32_t **indices_dev, int64_t *nnz);
+ABX_API abx_status abx_find_full_neighbor_list(void *stream, const float *xyz_dev, int64_t n, float radius,
+                                               abx_alloc_fn alloc, void *user, int32_t **offsets_dev,
+                                               uint32_t **indices_dev, int64_t *nnz);
+
+/* ---- ArborX::BruteForce (spatial/ArborX_BruteForce.hpp:42-160, detail/ArborX_BruteForceImpl.hpp:40-233): the
+ * interface of the BVH answered by testing every predicate against every primitive (tiles of primitives staged in
+ * shared memory).  Point and box primitives; rows of a spatial query in ascending primitive order. ---- */
+typedef struct abx_brute abx_brute;
+ABX_API abx_status abx_brute_create(void *stream, int prim_kind, const void *prims_dev, int64_t n, abx_brute **out);
+ABX_API abx_status abx_brute_destroy(abx_brute *brute);
+ABX_API int64_t abx_brute_size(const abx_brute *brute);
+ABX_API abx_status abx_brute_bounds(abx_brute *brute, float out6[6]);
+ABX_API abx_status abx_brute_query_spatial_crs(abx_brute *brute, void *stream, int pred_kind, const void *preds_dev,
+                                               int64_t q, abx_alloc_fn alloc, void *user, int32_t **offsets_dev,
+                                               uint32_t **indices_dev, int64_t *nnz);
+ABX_API abx_status abx_brute_query_nearest_crs(abx_brute *brute, void *stream, const void *points_dev, int64_t q,
+                                               int32_t k, abx_alloc_fn alloc, void *user, int32_t **offsets_dev,
+                                               uint32_t **indices_dev, float **distances_dev, int64_t *nnz);
+
 /* ---- ArborX::dbscan(space, points, eps, minpts, labels, params) (cluster/ArborX_DBSCAN.hpp:180-223) ---- */
 enum
 {

@@ -44,3 +44,19 @@ def test_bvh_driver_cli():
     for b in data:
         if b["aggregate_name"] == "median":
             assert b["rate"] > 0
+
+
+@pytest.mark.gpu
+def test_dbscan_driver_on_the_benchmark_input(tmp_path):
+    """ArborX_Benchmark_DBSCAN --filename=input.txt --eps=1.4 --verify (benchmarks/cluster/CMakeLists.txt:13) on the
+    benchmark's own 8-point file."""
+    import subprocess
+    import sys
+    txt = tmp_path / "input.txt"
+    txt.write_text("8 3\n0 0 0\n1 1 1\n2 2 2\n3 3 3\n9 9 9\n10 10 10\n11 11 11\n20 20 20\n")
+    for impl in ("fdbscan", "fdbscan-densebox"):
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "dbscan_driver.py"), "--filename", str(txt),
+                              "--eps", "1.8", "--impl", impl, "--verify"], capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stdout + out.stderr
+        assert "#clusters       : 2" in out.stdout and "Verification passed" in out.stdout
+        assert "#noise   points : 1 " in out.stdout
