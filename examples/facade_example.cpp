@@ -55,6 +55,19 @@ int main()
   auto ki = indices.to_host();
   std::printf("knn: %d %d | %d %d\n", ki[0], ki[1], ki[2], ki[3]);
   ok = ok && ki[0] == 1 && ki[2] == 7;
+  // the same queries through BruteForce (spatial/ArborX_BruteForce.hpp) and with nearest(Sphere, k)
+  BruteForce brute(space, d_cloud);
+  DeviceView<int> bi, bo;
+  brute.query(space, q, 2, bi, bo, &dist);
+  auto bki = bi.to_host();
+  ok = ok && brute.size() == 10 && bki[0] == 1 && bki[2] == 7;
+  DeviceView<Sphere<>> qs;
+  qs.assign({{{{0.1f, 0.f, 0.f}}, 0.05f}, {{{3.9f, 3.9f, 0.f}}, 0.05f}});
+  tree.query(space, qs, 2, indices, offsets, &dist);
+  auto si = indices.to_host();
+  auto sd = dist.to_host();
+  std::printf("knn(sphere): %d %d | %d %d  d0 = %g\n", si[0], si[1], si[2], si[3], sd[0]);
+  ok = ok && si[0] == 1 && si[2] == 7 && sd[0] > 0.04f && sd[0] < 0.06f;
   bool threw = false;
   try
   {

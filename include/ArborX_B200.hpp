@@ -125,6 +125,13 @@ Nearest<Geometry> nearest(Geometry const &g, int k = 1)
 
 namespace Experimental
 {
+// geometry/ArborX_Ray.hpp:33-68: origin + direction (normalised by the library, in double, like the constructor)
+struct Ray
+{
+  float _origin[3];
+  float _direction[3];
+};
+static_assert(sizeof(Ray) == 24);
 // TraversalPolicy.hpp:19-48
 struct TraversalPolicy
 {
@@ -254,6 +261,11 @@ struct PredKind<Point<>>
 {
   static constexpr int value = ABX_PRED_POINT3F;
 };
+template <>
+struct PredKind<Experimental::Ray>
+{
+  static constexpr int value = ABX_PRED_RAY3F;
+};
 
 // abx_alloc_fn that resizes the caller's views
 template <class Indices, class Offsets>
@@ -338,6 +350,23 @@ public:
                                          &Details::ViewAllocator<DeviceView<int>, DeviceView<int>>::call, &alloc, &off,
                                          &idx, &nnz));
   }
+  // nearest(Box | Sphere, k) / nearest(Experimental::Ray, k) with the same k for every predicate (Predicates.hpp:58-80)
+  template <class Geometry>
+  void query(Cuda const &space, DeviceView<Geometry> const &geometries, int k, DeviceView<int> &indices,
+             DeviceView<int> &offsets, DeviceView<float> *distances = nullptr,
+             Experimental::TraversalPolicy const &policy = {}) const
+  {
+    abx_policy p{policy._buffer_size, policy._sort_predicates ? 1 : 0};
+    Details::ViewAllocator<DeviceView<int>, DeviceView<int>> alloc{&indices, &offsets, distances};
+    std::int32_t *off = nullptr;
+    std::uint32_t *idx = nullptr;
+    float *dist = nullptr;
+    std::int64_t nnz = 0;
+    Details::check(abx_query_nearest_geom_crs(_h, space.cuda_stream(), Details::PredKind<Geometry>::value,
+                                              geometries.data(), (std::int64_t)geometries.size(), k, &p,
+                                              &Details::ViewAllocator<DeviceView<int>, DeviceView<int>>::call, &alloc,
+                                              &off, &idx, distances ? &dist : nullptr, &nnz));
+  }
   // nearest(Point, k) with the same k for every predicate (Experimental::make_nearest)
   void query(Cuda const &space, DeviceView<Point<>> const &points, int k, DeviceView<int> &indices,
              DeviceView<int> &offsets, DeviceView<float> *distances = nullptr,
@@ -362,6 +391,139 @@ void query(BoundingVolumeHierarchy const &tree, Cuda const &space, Args &&...arg
 {
   tree.query(space, std::forward<Args>(args)...);
 }
+
+// ---- BruteForce: spatial/ArborX_BruteForce.hpp:42-160 ------------------------------------------
+class BruteForce
+{
+  abx_brute *_h = nullptr;
+
+public:
+  BruteForce() = default;
+  template <class Geometry>
+  BruteForce(Cuda const &space, DeviceView<Geometry> const &values)
+  {
+    Details::check(abx_brute_create(space.cuda_stream(), Details::PrimKind<Geometry>::value, values.data(),
+                                    (std::int64_t)values.size(), &_h));
+  }
+  BruteForce(BruteForce const &) = delete;
+  BruteForce &operator=(BruteForce const &) = delete;
+  ~BruteForce()
+  {
+    if (_h)
+      abx_brute_destroy(_h);
+  }
+  std::int64_t size() const { return _h ? abx_brute_size(_h) : 0; }
+  bool empty() const { return size() == 0; }
+  Box<> bounds() const
+  {
+    Box<> bx;
+    float b[6];
+    Details::check(abx_brute_bounds(_h, b));
+    for (int d = 0; d < 3; ++d)
+    {
+      bx._min_corner[d] = b[d];
+      bx._max_corner[d] = b[3 + d];
+    }
+    return bx;
+  }
+  template <class Geometry>
+  void query(Cuda const &space, DeviceView<Intersects<Geometry>> const &predicates, DeviceView<int> &indices,
+             DeviceView<int> &offsets) const
+  {
+    Details::ViewAllocator<DeviceView<int>, DeviceView<int>> alloc{&indices, &offsets, nullptr};
+    std::int32_t *off = nullptr;
+    std::uint32_t *idx = nullptr;
+    std::int64_t nnz = 0;
+    Details::check(abx_brute_query_spatial_crs(_h, space.cuda_stream(), Details::PredKind<Geometry>::value,
+                                               predicates.data(), (std::int64_t)predicates.size(),
+                                               &Details::ViewAllocator<DeviceView<int>, DeviceView<int>>::call, &alloc,
+                                               &off, &idx, &nnz));
+  }
+  void query(Cuda const &space, DeviceView<Point<>> const &points, int k, DeviceView<int> &indices,
+             DeviceView<int> &offsets, DeviceView<float> *distances = nullptr) const
+  {
+    Details::ViewAllocator<DeviceView<int>, DeviceView<int>> alloc{&indices, &offsets, distances};
+    std::int32_t *off = nullptr;
+    std::uint32_t *idx = nullptr;
+    float *dist = nullptr;
+    std::int64_t nnz = 0;
+    Details::check(abx_brute_query_nearest_crs(_h, space.cuda_stream(), points.data(), (std::int64_t)points.size(), k,
+                                               &Details::ViewAllocator<DeviceView<int>, DeviceView<int>>::call, &alloc,
+                                               &off, &idx, distances ? &dist : nullptr, &nnz));
+  }
+};
+
+// ---- DistributedTree: distributed/ArborX_DistributedTree.hpp:33-252 ----------------------------------
+// One process (or host thread) per GPU.  The reference takes an MPI_Comm; here the communicator is the caller's
+// ncclComm_t (passed as void *: this header does not need nccl.h).  Values returned by queries are
+// PairIndexRank{index, rank} like the reference's default (examples/distributed_tree/distributed_knn.cpp:62-104).
+struct PairIndexRank
+{
+  int index;
+  int rank;
+};
+class DistributedTree
+{
+  abx_comm *_comm = nullptr;
+  abx_dist_tree *_h = nullptr;
+
+public:
+  template <class Geometry>
+  DistributedTree(void *nccl_comm, Cuda const &space, DeviceView<Geometry> const &values)
+  {
+    Details::check(abx_comm_from_nccl(nccl_comm, &_comm));
+    Details::check(abx_dist_create(_comm, space.cuda_stream(), Details::PrimKind<Geometry>::value, values.data(),
+                                   (std::int64_t)values.size(), &_h));
+  }
+  DistributedTree(DistributedTree const &) = delete;
+  DistributedTree &operator=(DistributedTree const &) = delete;
+  ~DistributedTree()
+  {
+    if (_h)
+      abx_dist_destroy(_h);
+    if (_comm)
+      abx_comm_destroy(_comm);
+  }
+  std::int64_t size() const { return _h ? abx_dist_size(_h) : 0; }
+  bool empty() const { return size() == 0; }
+  Box<> bounds() const
+  {
+    Box<> bx;
+    float b[6];
+    Details::check(abx_dist_bounds(_h, b));
+    for (int d = 0; d < 3; ++d)
+    {
+      bx._min_corner[d] = b[d];
+      bx._max_corner[d] = b[3 + d];
+    }
+    return bx;
+  }
+  // collective: query(space, intersects(...) predicates, values, offsets) :84-102
+  template <class Geometry>
+  void query(Cuda const &space, DeviceView<Intersects<Geometry>> const &predicates, DeviceView<PairIndexRank> &values,
+             DeviceView<int> &offsets) const
+  {
+    Details::ViewAllocator<DeviceView<PairIndexRank>, DeviceView<int>> alloc{&values, &offsets, nullptr};
+    std::int32_t *off = nullptr, *vals = nullptr;
+    std::int64_t nnz = 0;
+    Details::check(abx_dist_query_spatial_crs(_h, space.cuda_stream(), Details::PredKind<Geometry>::value,
+                                              predicates.data(), (std::int64_t)predicates.size(),
+                                              &Details::ViewAllocator<DeviceView<PairIndexRank>, DeviceView<int>>::call,
+                                              &alloc, &off, &vals, &nnz));
+  }
+  // collective: nearest(Point, k)
+  void query(Cuda const &space, DeviceView<Point<>> const &points, int k, DeviceView<PairIndexRank> &values,
+             DeviceView<int> &offsets, DeviceView<float> *distances = nullptr) const
+  {
+    Details::ViewAllocator<DeviceView<PairIndexRank>, DeviceView<int>> alloc{&values, &offsets, distances};
+    std::int32_t *off = nullptr, *vals = nullptr;
+    float *dist = nullptr;
+    std::int64_t nnz = 0;
+    Details::check(abx_dist_query_nearest_crs(_h, space.cuda_stream(), points.data(), (std::int64_t)points.size(), k,
+                                              &Details::ViewAllocator<DeviceView<PairIndexRank>, DeviceView<int>>::call,
+                                              &alloc, &off, &vals, distances ? &dist : nullptr, &nnz));
+  }
+};
 
 // ---- dbscan: cluster/ArborX_DBSCAN.hpp:180-223 --------------------------------------------
 namespace DBSCAN
