@@ -85,6 +85,7 @@ SIGNATURES = {
     "abx_dist_bounds": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "abx_dist_query_spatial_crs": (C.c_int, [_vp, _vp, C.c_int, _vp, _i64, ALLOC_FN, _vp, _pp, _pp, _pi64]),
     "abx_dist_query_nearest_crs": (C.c_int, [_vp, _vp, _vp, _i64, _i32, ALLOC_FN, _vp, _pp, _pp, _pp, _pi64]),
+    "abx_dist_dbscan_points3f": (C.c_int, [_vp, _vp, _vp, _i64, _f, _i32, C.c_int, C.c_int, _vp]),
     "abx_dist_query_spatial_crs_host": (C.c_int, [_vp, _vp, C.c_int, _vp, _i64, ALLOC_FN, _vp, _pp, _pp, _pi64, _pp,
                                                   _pp, _pi64]),
     "abx_dist_query_nearest_crs_host": (C.c_int, [_vp, _vp, _vp, _i64, _i32, ALLOC_FN, _vp, _pp, _pp, _pp, _pi64, _pp,

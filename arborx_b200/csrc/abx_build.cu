@@ -650,215 +650,15 @@ __global__ void __launch_bounds__(W * 32, ABX_HIER_MINB)
   }
 }
 
-// ---- hierarchy, chunk-local part without rounds (round 2) -----------------------------------------------------
-// Apetrei's merge order is a function of the delta sequence alone: the node that splits at boundary s (between the
-// sorted leaves s and s + 1) owns the range [L, R] where L - 1 is the nearest boundary to the left with a LARGER
-// delta and R the nearest boundary to the right with a delta that is not smaller (a range joins the neighbour with
-// the smaller delta, the left one on ties: TreeConstruction.hpp:222-233 -- so among equal deltas the left boundary
-// is formed first and ends up below the right one).  Its children are [L, s] and [s + 1, R]: leaves when they hold
-// one position, else the nodes with Karras indices s (a left child's index is its last leaf) and s + 1.  Nothing
-// depends on another node, so every boundary of a 256-leaf chunk is handled by its own thread with all lanes busy:
-//   * range ends by binary lifting over a sparse table of range maxima of the chunk's 257 deltas,
-//   * the two child boxes as range unions from a sparse table of leaf-box unions (min/max are exact: any grouping
-//     gives the boxes of the bottom-up refit bit for bit),
-// all in shared memory (68 KB).  The rounds of the previous kernel ran at 14 of 32 lanes with a barrier per tree
-// level.  A node whose range leaves the chunk is not local; the maximal local subtrees (and leaves without a local
-// parent) go to hierarchyGlobalKernel exactly as before.
-constexpr int kChunkLeaves = 256;
-constexpr int kDeltaLevels = 9; // 2^8 = 256 < 257 deltas
-constexpr int kBoxLevels = 8;   // child ranges hold at most 255 leaves
-
-struct ChunkSmem
-{
-  long long dmax[kDeltaLevels][kChunkLeaves + 1]; // [0][j] = delta(a - 1 + j); [k][j] = max over 2^k entries from j
-  float bx[kBoxLevels][6][kChunkLeaves];          // [k][c][j]: component c of the union of leaves j .. j + 2^k - 1
-  unsigned perm[kChunkLeaves];
-  unsigned char local[kChunkLeaves]; // boundary a + j (between leaves j and j + 1 of the chunk) roots a local node
-  int pend_count;
-  unsigned pend_base;
-};
-
-template <int KIND>
-__global__ void __launch_bounds__(kChunkLeaves)
-    hierarchyChunkKernel(int n, unsigned long long const *__restrict__ codes, unsigned const *__restrict__ perm,
-                         float const *__restrict__ prims, Node64 *nodes, float4 *leaf_box, float4 *leaf_tri,
-                         PendingNode *pending, unsigned *pending_count, float *bounds6)
-{
-  constexpr int T = kChunkLeaves;
-  extern __shared__ __align__(16) unsigned char chunk_smem_raw[];
-  ChunkSmem &sm = *reinterpret_cast<ChunkSmem *>(chunk_smem_raw);
-  int const j = threadIdx.x;
-  int const a = blockIdx.x * T;
-  int const cn = min(T, n - a); // leaves in this chunk
-  int const n_int = n - 1;
-  int const i = a + j;
-
-  // leaf records out; leaf boxes, permutation and deltas into shared memory
-  Box mybox = emptyBox();
-  unsigned orig = 0;
-  if (j < cn)
-  {
-    orig = perm[i];
-    mybox = primBox<KIND>(prims, orig);
-    if (KIND == ABX_PRIM_POINT3F)
-      leaf_box[i] = make_float4(mybox.lo[0], mybox.lo[1], mybox.lo[2], __uint_as_float(orig));
-    else
-    {
-      leaf_box[2 * (size_t)i] = make_float4(mybox.lo[0], mybox.lo[1], mybox.lo[2], __uint_as_float(orig));
-      leaf_box[2 * (size_t)i + 1] = make_float4(mybox.hi[0], mybox.hi[1], mybox.hi[2], 0.f);
-    }
-    if (KIND == ABX_PRIM_TRI3F)
-    {
-      float const *t = prims + 9 * (size_t)orig;
-      leaf_tri[3 * (size_t)i] = make_float4(t[0], t[1], t[2], 0.f);
-      leaf_tri[3 * (size_t)i + 1] = make_float4(t[3], t[4], t[5], 0.f);
-      leaf_tri[3 * (size_t)i + 2] = make_float4(t[6], t[7], t[8], 0.f);
-    }
-  }
-#pragma unroll
-  for (int d = 0; d < 3; ++d)
-  {
-    sm.bx[0][d][j] = mybox.lo[d];
-    sm.bx[0][3 + d][j] = mybox.hi[d];
-  }
-  sm.perm[j] = orig;
-  sm.local[j] = 0;
-  // delta(a - 1 + jj) for jj = 0 .. T; positions past the chunk's leaves act as walls
-  sm.dmax[0][j + 1] = j < cn ? deltaOf(codes, i, n_int) : LLONG_MAX;
-  if (j == 0)
-  {
-    sm.dmax[0][0] = deltaOf(codes, a - 1, n_int);
-    sm.pend_count = 0;
-  }
-  __syncthreads();
-  // sparse tables
-#pragma unroll
-  for (int k = 1; k < kDeltaLevels; ++k)
-  {
-    int const half = 1 << (k - 1);
-    for (int jj = j; jj + (1 << k) <= T + 1; jj += T)
-      sm.dmax[k][jj] = max(sm.dmax[k - 1][jj], sm.dmax[k - 1][jj + half]);
-    if (k < kBoxLevels && j + (1 << k) <= T)
-    {
-#pragma unroll
-      for (int d = 0; d < 3; ++d)
-      {
-        sm.bx[k][d][j] = fminf(sm.bx[k - 1][d][j], sm.bx[k - 1][d][j + half]);
-        sm.bx[k][3 + d][j] = fmaxf(sm.bx[k - 1][3 + d][j], sm.bx[k - 1][3 + d][j + half]);
-      }
-    }
-    __syncthreads();
-  }
-
-  auto rangeBox = [&](int lo, int hi, Box &b) { // chunk-relative leaves lo .. hi
-    int const len = hi - lo + 1;
-    int const k = 31 - __clz(len);
-    int const j2 = hi - (1 << k) + 1;
-#pragma unroll
-    for (int d = 0; d < 3; ++d)
-    {
-      b.lo[d] = fminf(sm.bx[k][d][lo], sm.bx[k][d][j2]);
-      b.hi[d] = fmaxf(sm.bx[k][3 + d][lo], sm.bx[k][3 + d][j2]);
-    }
-  };
-
-  // the node that splits at boundary s = a + j (needs leaves j and j + 1 of the chunk)
-  bool is_local = false;
-  int L = 0, R = 0, karras = 0; // chunk-relative leaf positions of the range
-  Box whole = emptyBox();
-  if (j + 1 < cn)
-  {
-    int const js = j + 1; // index of delta(s) in dmax[0]
-    long long const ds = sm.dmax[0][js];
-    // left: largest jj < js with delta > ds
-    int pl = js - 1;
-#pragma unroll
-    for (int k = kDeltaLevels - 1; k >= 0; --k)
-    {
-      int const start = pl - (1 << k) + 1;
-      if (start >= 0 && sm.dmax[k][start] <= ds)
-        pl = start - 1;
-    }
-    // right: smallest jj > js with delta >= ds
-    int pr = js + 1;
-#pragma unroll
-    for (int k = kDeltaLevels - 1; k >= 0; --k)
-      if (pr + (1 << k) <= T + 1 && sm.dmax[k][pr] < ds)
-        pr += 1 << k;
-    if (pl >= 0 && pr <= cn) // both walls inside the chunk (index 0 and index cn are the chunk's own edges)
-    {
-      is_local = true;
-      L = pl;     // boundary index pl is boundary a - 1 + pl: the range starts at leaf a + pl
-      R = pr - 1; // boundary index pr is boundary a - 1 + pr = last leaf of the range
-      Box bl, br;
-      rangeBox(L, j, bl);
-      rangeBox(j + 1, R, br);
-      long long const d_left = sm.dmax[0][L], d_right = sm.dmax[0][R + 1];
-      karras = a + (d_right < d_left ? R : L);
-      int const lref = (L == j) ? refLeaf(sm.perm[j]) : a + j;
-      int const rref = (j + 1 == R) ? refLeaf(sm.perm[j + 1]) : a + j + 1;
-      writeNode(nodes, karras, bl, lref, br, rref, a + L, a + R);
-      whole = bl;
-      boxUnion(whole, br);
-      sm.local[j] = 1;
-      if (a + L == 0 && a + R == n - 1)
-      {
-        // the root (the whole tree fits in one chunk): TreeConstruction.hpp:108-113
-#pragma unroll
-        for (int d = 0; d < 3; ++d)
-        {
-          bounds6[d] = whole.lo[d];
-          bounds6[3 + d] = whole.hi[d];
-        }
-      }
-    }
-  }
-  __syncthreads();
-
-  // hand-over: local subtrees (and leaves) whose parent is not local
-  auto parentLocal = [&](int lo, int hi) { // range lo .. hi (chunk-relative); parent = the boundary with the smaller delta
-    long long const d_left = sm.dmax[0][lo], d_right = sm.dmax[0][hi + 1];
-    int const pj = d_right < d_left ? hi : lo - 1; // chunk-relative boundary index (between leaves pj and pj + 1)
-    return pj >= 0 && pj + 1 < cn && sm.local[pj] != 0;
-  };
-  bool const node_pending = is_local && !(a + L == 0 && a + R == n - 1) && !parentLocal(L, R);
-  bool const leaf_pending = j < cn && !parentLocal(j, j);
-  int const mine = (node_pending ? 1 : 0) + (leaf_pending ? 1 : 0);
-  int slot = 0;
-  if (mine)
-    slot = atomicAdd(&sm.pend_count, mine);
-  __syncthreads();
-  if (j == 0 && sm.pend_count)
-    sm.pend_base = atomicAdd(pending_count, (unsigned)sm.pend_count);
-  __syncthreads();
-  if (node_pending)
-  {
-    PendingNode pn;
-    pn.range_left = a + L;
-    pn.range_right = a + R;
-    pn.ref = karras;
-#pragma unroll
-    for (int d = 0; d < 3; ++d)
-    {
-      pn.box[d] = whole.lo[d];
-      pn.box[3 + d] = whole.hi[d];
-    }
-    pending[sm.pend_base + slot++] = pn;
-  }
-  if (leaf_pending)
-  {
-    PendingNode pn;
-    pn.range_left = pn.range_right = i;
-    pn.ref = refLeaf(orig);
-#pragma unroll
-    for (int d = 0; d < 3; ++d)
-    {
-      pn.box[d] = mybox.lo[d];
-      pn.box[3 + d] = mybox.hi[d];
-    }
-    pending[sm.pend_base + slot] = pn;
-  }
-}
+// Measured and rejected in round 2 (profiles/r02_hierarchy_chunk_experiment.log, bit-exact on the parity suite):
+// a round-free form of this kernel.  Apetrei's merge order is a function of the delta sequence alone -- the node
+// that splits at boundary s owns the range between the nearest boundary to the left with a larger delta and the
+// nearest one to the right with a delta that is not smaller -- so every boundary of a chunk can be finished by its
+// own thread: range ends by binary lifting over a sparse table of delta maxima, the child boxes as range unions from
+// a sparse table of leaf boxes, all lanes busy, no flags.  With 256-leaf chunks (69 KB of shared memory, 3 blocks
+// per SM) it took 0.77 ms against the 0.58 ms of the rounds below, 0.65 ms with 128-leaf chunks (and 0.20 instead of
+// 0.13 ms in the global kernel), 0.53 / 0.47 ms with the leaves gathered by a separate streaming kernel (+0.15 ms):
+// eight block-wide barriers for the tables at a third of the occupancy cost more than the idle lanes of the rounds.
 
 // finishes the nodes that straddle chunk boundaries: global acquire-release CAS flags in `ranges`,
 // sibling records read with __ldcg after it (the reference's CAS + load_fence,
@@ -1185,26 +985,6 @@ abx_status launchHierarchyLocal(cudaStream_t s, abx_bvh *t, void const *prims, P
 #endif
 }
 
-constexpr int kHierChunkDefault = 1; // 1: hierarchyChunkKernel (no rounds); 0: the windowed rounds of round 1
-
-template <int K>
-abx_status launchHierarchyChunk(cudaStream_t s, abx_bvh *t, void const *prims, PendingNode *pending,
-                                unsigned *pending_count)
-{
-  static PerDeviceOnce attr; // function attributes are per device
-  if (attr.needed())
-  {
-    ABX_CUDA_TRY(cudaFuncSetAttribute(hierarchyChunkKernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)sizeof(ChunkSmem)));
-    attr.done();
-  }
-  int const n = (int)t->n;
-  ABX_LAUNCH_TAGGED("hierarchyChunkKernel", (hierarchyChunkKernel<K>), divUp(n, kChunkLeaves), kChunkLeaves,
-                    sizeof(ChunkSmem), s, n, (unsigned long long const *)t->codes, t->perm, (float const *)prims,
-                    t->nodes, t->leaf_box, t->leaf_tri, pending, pending_count, t->bounds_dev);
-  return ABX_OK;
-}
-
 // codes (sorted) and perm must already be in bvh; fills nodes / leaf arrays / bounds
 abx_status buildHierarchy(cudaStream_t s, abx_bvh *t, void const *prims)
 {
@@ -1217,14 +997,7 @@ abx_status buildHierarchy(cudaStream_t s, abx_bvh *t, void const *prims)
   ABX_TRY(pending_count.alloc(1, s));
   ABX_CUDA_TRY(cudaMemsetAsync(ranges.ptr, 0xff, sizeof(int) * (size_t)(n - 1), s));
   ABX_CUDA_TRY(cudaMemsetAsync(pending_count.ptr, 0, sizeof(unsigned), s));
-  if (ABX_TUNE_INT("ABX_HIER_CHUNK", kHierChunkDefault))
-  {
-    ABX_DISPATCH_PRIM(t->kind, ABX_TRY(launchHierarchyChunk<K>(s, t, prims, pending.ptr, pending_count.ptr)));
-  }
-  else
-  {
-    ABX_DISPATCH_PRIM(t->kind, ABX_TRY(launchHierarchyLocal<K>(s, t, prims, pending.ptr, pending_count.ptr)));
-  }
+  ABX_DISPATCH_PRIM(t->kind, ABX_TRY(launchHierarchyLocal<K>(s, t, prims, pending.ptr, pending_count.ptr)));
   // the local kernel's records are complete at the kernel boundary; the global kernel
   // only orders its own writes
   int const grid = std::min(divUp(n, 256 * 8), kNumSMs * 8);

@@ -435,6 +435,7 @@ abx_status nearestCrs(abx_bvh *bvh, cudaStream_t s, void const *pts, int64_t q, 
                       int pred_kind = ABX_PRED_POINT3F);
 abx_status ensureDevice();
 // dbscan.cu
+// core_flags (optional): 1 for core points (all points when minpts == 2)
 abx_status dbscan(cudaStream_t s, float const *xyz, int64_t n, float eps, int32_t minpts, int impl, int algo,
-                  int32_t *labels);
+                  int32_t *labels, int32_t *core_flags = nullptr);
 } // namespace abx

@@ -650,8 +650,19 @@ abx_status readInt(cudaStream_t s, int const *dev, int &out)
   return ABX_OK;
 }
 
-abx_status finalize(cudaStream_t s, int n, int minpts, int const *num_neigh, int *labels)
+// core_flags[i] = 1 when point i is a core point (every point counts as core for minpts == 2, where the
+// reference never counts neighbours: ArborX_DBSCAN.hpp:273-283)
+__global__ void coreFlagsKernel(int n, int const *__restrict__ num_neigh, int minpts, int *__restrict__ core_flags)
 {
+  int const i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    core_flags[i] = (!num_neigh || num_neigh[i] >= minpts) ? 1 : 0;
+}
+
+abx_status finalize(cudaStream_t s, int n, int minpts, int const *num_neigh, int *labels, int *core_flags)
+{
+  if (core_flags)
+    ABX_LAUNCH(coreFlagsKernel, divUp(n, 256), 256, 0, s, n, num_neigh, minpts, core_flags);
   TempBuffer<int> cluster_sizes;
   ABX_TRY(cluster_sizes.alloc(n, s));
   ABX_CUDA_TRY(cudaMemsetAsync(cluster_sizes.ptr, 0, sizeof(int) * (size_t)n, s));
@@ -670,7 +681,8 @@ struct TreeGuard
   }
 };
 
-abx_status fdbscan(cudaStream_t s, float const *xyz, int n, float eps, int minpts, int algo, int *labels)
+abx_status fdbscan(cudaStream_t s, float const *xyz, int n, float eps, int minpts, int algo, int *labels,
+                   int *core_flags)
 {
   TreeGuard tree;
   ABX_TRY(buildTree(s, ABX_PRIM_POINT3F, xyz, n, nullptr, &tree.t));
@@ -700,10 +712,11 @@ abx_status fdbscan(cudaStream_t s, float const *xyz, int n, float eps, int minpt
       ABX_LAUNCH((fdbscanMainKernel<false, false>), grid, kThreads, 0, s, t->nodes, t->leaf_box, n, eps, minpts,
                  (int const *)num_neigh.ptr, labels);
   }
-  return finalize(s, n, minpts, num_neigh.ptr, labels);
+  return finalize(s, n, minpts, num_neigh.ptr, labels, core_flags);
 }
 
-abx_status denseBox(cudaStream_t s, float const *xyz, int n, float eps, int minpts, int algo, int *labels)
+abx_status denseBox(cudaStream_t s, float const *xyz, int n, float eps, int minpts, int algo, int *labels,
+                    int *core_flags)
 {
   bool const special = (minpts == 2);
   bool const star = (algo == ABX_DBSCAN_DBSCAN_STAR);
@@ -861,13 +874,13 @@ abx_status denseBox(cudaStream_t s, float const *xyz, int n, float eps, int minp
                  perm2.ptr, dense_pts.ptr, dense_cell_offsets.ptr, num_dense, num_points_dense, n, eps, minpts,
                  (int const *)num_neigh.ptr, labels);
   }
-  return finalize(s, n, minpts, num_neigh.ptr, labels);
+  return finalize(s, n, minpts, num_neigh.ptr, labels, core_flags);
 }
 
 } // namespace
 
 abx_status dbscan(cudaStream_t s, float const *xyz, int64_t n, float eps, int32_t minpts, int impl, int algo,
-                  int32_t *labels)
+                  int32_t *labels, int32_t *core_flags)
 {
   // ArborX_DBSCAN.hpp:240-241
   if (!(eps > 0))
@@ -893,9 +906,9 @@ abx_status dbscan(cudaStream_t s, float const *xyz, int64_t n, float eps, int32_
   if (n == 0)
     return ABX_OK;
   if (impl == ABX_DBSCAN_FDBSCAN)
-    return fdbscan(s, xyz, (int)n, eps, minpts, algo, labels);
+    return fdbscan(s, xyz, (int)n, eps, minpts, algo, labels, core_flags);
   if (impl == ABX_DBSCAN_FDBSCAN_DENSEBOX)
-    return denseBox(s, xyz, (int)n, eps, minpts, algo, labels);
+    return denseBox(s, xyz, (int)n, eps, minpts, algo, labels, core_flags);
   setError("unknown DBSCAN implementation");
   return ABX_ERR_ARG;
 }

@@ -1140,6 +1140,480 @@ abx_status localKnnPairs(abx_bvh *bvh, cudaStream_t s, void const *pts, int64_t 
                       dist, missing_dev, rank);
 }
 
+
+// ---- distributed DBSCAN ----------------------------------------------------------------------------------------
+// ArborX::Experimental::dbscan(comm, space, primitives, eps, core_min_size, labels, params)
+// (cluster/ArborX_DistributedDBSCAN.hpp:29-190, cluster/detail/ArborX_DistributedDBSCANHelpers.hpp):
+//   1. halo out   all-gather of the rank boxes; the points within the ghost distance of another rank's box (eps for
+//                 core_min_size == 2, nextafter(2 eps) otherwise: a ghost's own core status must be decidable from
+//                 what its host sees, DistributedDBSCAN.hpp:77-84) travel to that rank
+//   2. local      abx::dbscan on local + ghost points (the hot kernels, unchanged)
+//   3. labels     local labels -> global ids (rank offset + index, Helpers.hpp:132-175); ghost labels go back to
+//                 their owners, which derive merge pairs (label -> smaller label) for core points that carry several
+//                 labels (computeMergePairs, :420-499); all-gather-v of the pairs, sorted and filtered
+//                 (sortAndFilterMergePairs, :501-561); every rank flattens its labels through the table (relabel,
+//                 :619-660).
+// Collectives: two all-gathers of R words, two grouped send/recvs, two all-gathers for the pairs; four blocking
+// points.  Everything between them is kernels on the caller's stream.
+namespace
+{
+__global__ void globalLabelsKernel(int64_t n_all, int64_t n_local, int32_t const *__restrict__ local_labels,
+                                   int32_t const *__restrict__ ghost_ids, int32_t const *__restrict__ seg_off, int R,
+                                   long long const *__restrict__ rank_off, int rank, long long *__restrict__ out)
+{
+  int64_t const i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_all)
+    return;
+  int const l = local_labels[i];
+  long long g = -1;
+  if (l >= 0)
+  {
+    if (l < n_local)
+      g = rank_off[rank] + l;
+    else
+    {
+      int const gi = l - (int)n_local; // label = a ghost: its owner's numbering
+      int r = 0;
+      while (r + 1 < R && seg_off[r + 1] <= gi)
+        ++r;
+      g = rank_off[r] + ghost_ids[gi];
+    }
+  }
+  out[i] = g;
+}
+__global__ void flagLabelledKernel(int64_t n, long long const *__restrict__ labels, int32_t *__restrict__ flags)
+{
+  int64_t const i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    flags[i] = labels[i] != -1 ? 1 : 0;
+}
+__global__ void scatterLabelledKernel(int64_t n, long long const *__restrict__ labels, int32_t const *__restrict__ ids,
+                                      int32_t const *__restrict__ pos, long long *__restrict__ out_labels,
+                                      int32_t *__restrict__ out_ids)
+{
+  int64_t const i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && labels[i] != -1)
+  {
+    out_labels[pos[i]] = labels[i];
+    out_ids[pos[i]] = ids[i];
+  }
+}
+__global__ void gatherI64Kernel(long long const *__restrict__ src, uint32_t const *__restrict__ perm, int64_t m,
+                                long long *__restrict__ dst)
+{
+  int64_t const i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m)
+    dst[i] = src[perm[i]];
+}
+// computeMergePairs: one thread per point that received labels (ids ascending; the thread at the start of a segment)
+__global__ void mergePairsKernel(int64_t m, int32_t const *__restrict__ ids, long long const *__restrict__ got,
+                                 int32_t const *__restrict__ core, long long *labels, long long *__restrict__ pairs2,
+                                 unsigned *__restrict__ n_pairs)
+{
+  int64_t const c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= m)
+    return;
+  int const id = ids[c];
+  if (c > 0 && ids[c - 1] == id)
+    return;
+  int64_t e = c;
+  long long gmin = got[c];
+  for (; e < m && ids[e] == id; ++e)
+    gmin = min(gmin, got[e]);
+  int64_t const cnt = e - c;
+  long long const local = labels[id];
+  bool const valid = local != -1;
+  if (cnt + (valid ? 1 : 0) < 2)
+    return; // a noise point or a point with a single label (Helpers.hpp:449-454)
+  if (!core[id])
+  {
+    if (!valid)
+      labels[id] = got[c];
+    return;
+  }
+  long long const min_label = valid ? min(local, gmin) : gmin;
+  auto emit = [&](long long from, long long to) {
+    unsigned const o = atomicAdd(n_pairs, 1u);
+    pairs2[2 * (size_t)o] = from;
+    pairs2[2 * (size_t)o + 1] = to;
+  };
+  if (valid && local != min_label)
+    emit(local, min_label);
+  if (valid)
+    labels[id] = min_label;
+  for (int64_t k = c; k < e; ++k)
+    if (got[k] != min_label)
+      emit(got[k], min_label);
+}
+__global__ void splitPairsI64Kernel(int64_t m, long long const *__restrict__ pairs2, unsigned long long *__restrict__ from,
+                                    unsigned long long *__restrict__ to)
+{
+  int64_t const i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m)
+  {
+    from[i] = (unsigned long long)pairs2[2 * i];
+    to[i] = (unsigned long long)pairs2[2 * i + 1];
+  }
+}
+// rows sorted by (from, to): keep[i] = 1 for the first of equal rows
+__global__ void flagUniqueRowsKernel(int64_t m, unsigned long long const *__restrict__ from,
+                                     unsigned long long const *__restrict__ to, int32_t *__restrict__ keep)
+{
+  int64_t const i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m)
+    keep[i] = (i == 0 || from[i] != from[i - 1] || to[i] != to[i - 1]) ? 1 : 0;
+}
+__global__ void compactRowsI64Kernel(int64_t m, unsigned long long const *__restrict__ from,
+                                     unsigned long long const *__restrict__ to, int32_t const *__restrict__ keep,
+                                     int32_t const *__restrict__ pos, unsigned long long *__restrict__ out_from,
+                                     unsigned long long *__restrict__ out_to)
+{
+  int64_t const i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m && keep[i])
+  {
+    out_from[pos[i]] = from[i];
+    out_to[pos[i]] = to[i];
+  }
+}
+// sortAndFilterMergePairs on unique rows sorted by (from, to): the first row of a `from` keeps its (lowest) `to`,
+// every other `to` of that `from` is linked to the lowest one
+__global__ void relinkRowsKernel(int64_t m, unsigned long long *__restrict__ from, unsigned long long *__restrict__ to)
+{
+  int64_t const i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m || i == 0 || from[i] != from[i - 1])
+    return;
+  int64_t first = i - 1;
+  while (first > 0 && from[first - 1] == from[i])
+    --first;
+  // (from, to_i) -> (to_i, lowest): written after every thread has read its neighbours (separate arrays below)
+  from[m + i] = to[i];
+  to[m + i] = to[first];
+}
+__global__ void applyRelinkKernel(int64_t m, unsigned long long *__restrict__ from, unsigned long long *__restrict__ to)
+{
+  int64_t const i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m)
+    return;
+  if (from[m + i] != ~0ull)
+  {
+    from[i] = from[m + i];
+    to[i] = to[m + i];
+  }
+}
+// relabel: follow label -> to while the label is a `from` (table sorted by from: the first row of a from holds its
+// lowest to)
+__global__ void relabelKernel(int64_t n, long long *labels, int64_t m, unsigned long long const *__restrict__ from,
+                              unsigned long long const *__restrict__ to)
+{
+  int64_t const i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  long long l = labels[i];
+  if (l < 0)
+    return;
+  for (int guard = 0; guard < 64; ++guard)
+  {
+    int64_t lo = 0, hi = m; // first row with from >= l
+    while (lo < hi)
+    {
+      int64_t const mid = (lo + hi) >> 1;
+      if (from[mid] < (unsigned long long)l)
+        lo = mid + 1;
+      else
+        hi = mid;
+    }
+    if (lo >= m || from[lo] != (unsigned long long)l)
+      break;
+    l = (long long)to[lo];
+  }
+  labels[i] = l;
+}
+
+// rows (from, to) -> sorted by (from, to), duplicates dropped; arrays have room for `m` rows, *m_out rows survive
+abx_status sortUniqueRows(cudaStream_t s, int64_t m, TempBuffer<unsigned long long> &from,
+                          TempBuffer<unsigned long long> &to, int64_t *m_out)
+{
+  *m_out = 0;
+  if (m == 0)
+    return ABX_OK;
+  // stable LSD over the two columns: by `to`, then by `from`, carrying a permutation
+  TempBuffer<uint32_t> perm;
+  TempBuffer<unsigned long long> key, tmp_from, tmp_to;
+  ABX_TRY(perm.alloc((size_t)m, s));
+  ABX_TRY(key.alloc((size_t)m, s));
+  ABX_TRY(tmp_from.alloc((size_t)m, s));
+  ABX_TRY(tmp_to.alloc((size_t)m, s));
+  ABX_CUDA_TRY(cudaMemcpyAsync(key.ptr, to.ptr, sizeof(unsigned long long) * m, cudaMemcpyDeviceToDevice, s));
+  ABX_TRY(sortPairsU64(s, (uint64_t *)key.ptr, perm.ptr, m, true, 64, /*fixup=*/false));
+  ABX_LAUNCH(gatherI64Kernel, divUp(m, 256), 256, 0, s, (long long const *)from.ptr, perm.ptr, m, (long long *)tmp_from.ptr);
+  ABX_CUDA_TRY(cudaMemcpyAsync(tmp_to.ptr, key.ptr, sizeof(unsigned long long) * m, cudaMemcpyDeviceToDevice, s));
+  ABX_CUDA_TRY(cudaMemcpyAsync(key.ptr, tmp_from.ptr, sizeof(unsigned long long) * m, cudaMemcpyDeviceToDevice, s));
+  ABX_TRY(sortPairsU64(s, (uint64_t *)key.ptr, perm.ptr, m, true, 64, /*fixup=*/false));
+  ABX_LAUNCH(gatherI64Kernel, divUp(m, 256), 256, 0, s, (long long const *)tmp_to.ptr, perm.ptr, m, (long long *)to.ptr);
+  ABX_CUDA_TRY(cudaMemcpyAsync(from.ptr, key.ptr, sizeof(unsigned long long) * m, cudaMemcpyDeviceToDevice, s));
+  // unique
+  TempBuffer<int32_t> keep, pos;
+  TempBuffer<unsigned long long> total64;
+  ABX_TRY(keep.alloc((size_t)m + 1, s));
+  ABX_TRY(pos.alloc((size_t)m + 1, s));
+  ABX_TRY(total64.alloc(1, s));
+  ABX_LAUNCH(flagUniqueRowsKernel, divUp(m, 256), 256, 0, s, m, from.ptr, to.ptr, keep.ptr);
+  ABX_TRY(exclusiveScanI32(s, keep.ptr, pos.ptr, m + 1, total64.ptr));
+  unsigned long long h_total = 0;
+  ABX_CUDA_TRY(cudaMemcpyAsync(&h_total, total64.ptr, sizeof(h_total), cudaMemcpyDeviceToHost, s));
+  ABX_LAUNCH(compactRowsI64Kernel, divUp(m, 256), 256, 0, s, m, from.ptr, to.ptr, keep.ptr, pos.ptr, tmp_from.ptr,
+             tmp_to.ptr);
+  ABX_CUDA_TRY(cudaStreamSynchronize(s));
+  *m_out = (int64_t)h_total;
+  ABX_CUDA_TRY(cudaMemcpyAsync(from.ptr, tmp_from.ptr, sizeof(unsigned long long) * h_total, cudaMemcpyDeviceToDevice, s));
+  ABX_CUDA_TRY(cudaMemcpyAsync(to.ptr, tmp_to.ptr, sizeof(unsigned long long) * h_total, cudaMemcpyDeviceToDevice, s));
+  return ABX_OK;
+}
+
+// sortAndFilterMergePairs (Helpers.hpp:501-561): arrays hold m rows and have room for 2 m
+abx_status sortAndFilterPairs(cudaStream_t s, int64_t m, TempBuffer<unsigned long long> &from,
+                              TempBuffer<unsigned long long> &to, int64_t *m_out)
+{
+  int64_t u = 0;
+  ABX_TRY(sortUniqueRows(s, m, from, to, &u));
+  *m_out = u;
+  if (u == 0)
+    return ABX_OK;
+  // the rows to re-link are staged behind the table (slots u .. 2u), marked "none" first
+  ABX_CUDA_TRY(cudaMemsetAsync(from.ptr + u, 0xff, sizeof(unsigned long long) * u, s));
+  ABX_LAUNCH(relinkRowsKernel, divUp(u, 256), 256, 0, s, u, from.ptr, to.ptr);
+  ABX_LAUNCH(applyRelinkKernel, divUp(u, 256), 256, 0, s, u, from.ptr, to.ptr);
+  return sortUniqueRows(s, u, from, to, m_out);
+}
+} // namespace
+
+abx_status distDbscan(abx_comm *comm, cudaStream_t s, float const *xyz, int64_t n, float eps, int minpts, int impl,
+                      int algo, long long *labels)
+{
+  if (!(eps > 0))
+  {
+    setError("SearchException: dbscan requires eps > 0");
+    return ABX_ERR_SEARCH;
+  }
+  if (minpts < 2)
+  {
+    setError("SearchException: dbscan requires core_min_size >= 2");
+    return ABX_ERR_SEARCH;
+  }
+  if (n < 0 || n >= (int64_t)1 << 30 || (n > 0 && (!xyz || !labels)))
+  {
+    setError("bad argument");
+    return ABX_ERR_ARG;
+  }
+  int const R = comm->size, rank = comm->rank;
+  if (R > 64)
+  {
+    setError("distributed dbscan: at most 64 ranks");
+    return ABX_ERR_ARG;
+  }
+  // a throw-away "tree" object carries the communicator scratch the exchange helpers use
+  abx_dist_tree t;
+  t.comm = comm;
+  t.R = R;
+  t.rank = rank;
+  ABX_TRY(takePinnedScratch(&t.h_pin));
+  struct Scratch
+  {
+    abx_dist_tree &t;
+    ~Scratch()
+    {
+      returnPinnedScratch(t.h_pin);
+      t.h_pin = nullptr;
+    }
+  } scratch{t};
+
+  // 1. rank boxes and sizes
+  TempBuffer<unsigned> enc;
+  TempBuffer<uint32_t> meta, all;
+  TempBuffer<float> boxes_dev;
+  ABX_TRY(enc.alloc(6, s));
+  ABX_TRY(meta.alloc(8, s));
+  ABX_TRY(all.alloc((size_t)8 * R, s));
+  ABX_TRY(boxes_dev.alloc((size_t)6 * R, s));
+  ABX_TRY(sceneBounds(s, ABX_PRIM_POINT3F, xyz, n, enc.ptr));
+  ABX_TRY(decodeBounds(s, enc.ptr, (float *)meta.ptr));
+  ABX_CUDA_TRY(cudaMemcpyAsync(meta.ptr + 6, &n, sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  ABX_TRY(comm->allGather(meta.ptr, all.ptr, 8 * sizeof(uint32_t), s));
+  std::vector<uint32_t> h(8 * (size_t)R);
+  ABX_CUDA_TRY(cudaMemcpyAsync(h.data(), all.ptr, sizeof(uint32_t) * 8 * R, cudaMemcpyDeviceToHost, s));
+  ABX_CUDA_TRY(cudaStreamSynchronize(s)); // blocking point 1
+  std::vector<float> boxes(6 * (size_t)R);
+  std::vector<long long> rank_off(R + 1, 0);
+  for (int r = 0; r < R; ++r)
+  {
+    memcpy(&boxes[6 * (size_t)r], &h[8 * (size_t)r], 6 * sizeof(float));
+    int64_t sz = 0;
+    memcpy(&sz, &h[8 * (size_t)r + 6], sizeof(int64_t));
+    rank_off[r + 1] = rank_off[r] + sz;
+  }
+  ABX_CUDA_TRY(cudaMemcpyAsync(boxes_dev.ptr, boxes.data(), sizeof(float) * 6 * R, cudaMemcpyHostToDevice, s));
+  t.boxes_dev = boxes_dev.ptr;
+
+  // 2. halo: points within the ghost distance of another rank's box
+  float const e32 = eps;
+  float const ghost = minpts == 2 ? e32 : nextafterf(2.f * e32, 10.f * e32);
+  TempBuffer<float> radius;
+  TempBuffer<uint32_t> counts, matrix;
+  ABX_TRY(radius.alloc(1, s));
+  ABX_TRY(counts.alloc(R, s));
+  ABX_TRY(matrix.alloc((size_t)R * R, s));
+  ABX_CUDA_TRY(cudaMemcpyAsync(radius.ptr, &ghost, sizeof(float), cudaMemcpyHostToDevice, s));
+  ABX_CUDA_TRY(cudaMemsetAsync(counts.ptr, 0, sizeof(uint32_t) * R, s));
+  ABX_TRY(routeLaunch(s, false, ABX_PRED_SPHERE3F, xyz, n, radius.ptr, 0, boxes_dev.ptr, R, rank, counts.ptr, nullptr,
+                      nullptr, nullptr));
+  ABX_TRY(gatherCountMatrix(&t, s, counts.ptr, matrix.ptr));
+  ABX_CUDA_TRY(cudaStreamSynchronize(s)); // blocking point 2
+  ExchangePlan fwd;
+  fwd.fromMatrix(t.h_pin, R, rank);
+  TempBuffer<uint32_t> ghost_pts;
+  TempBuffer<int32_t> ghost_ids;
+  ABX_TRY(forwardPredicates(&t, s, ABX_PRED_SPHERE3F, xyz, 3, n, radius.ptr, 0, fwd, ghost_pts, ghost_ids));
+  int64_t const G = fwd.n_recv, n_all = n + G;
+  if (n_all >= (int64_t)1 << 30)
+  {
+    setError("distributed dbscan: local + ghost points exceed 2^30");
+    return ABX_ERR_ARG;
+  }
+
+  // 3. local DBSCAN on local + ghost points
+  TempBuffer<float> unified;
+  TempBuffer<int32_t> local_labels, core;
+  TempBuffer<long long> glob;
+  ABX_TRY(unified.alloc(3 * (size_t)std::max<int64_t>(n_all, 1), s));
+  ABX_TRY(local_labels.alloc((size_t)std::max<int64_t>(n_all, 1), s));
+  ABX_TRY(core.alloc((size_t)std::max<int64_t>(n_all, 1), s));
+  ABX_TRY(glob.alloc((size_t)std::max<int64_t>(n_all, 1), s));
+  if (n > 0)
+    ABX_CUDA_TRY(cudaMemcpyAsync(unified.ptr, xyz, sizeof(float) * 3 * n, cudaMemcpyDeviceToDevice, s));
+  if (G > 0)
+    ABX_CUDA_TRY(cudaMemcpyAsync(unified.ptr + 3 * n, ghost_pts.ptr, sizeof(float) * 3 * G, cudaMemcpyDeviceToDevice, s));
+  if (n_all > 0)
+    ABX_TRY(dbscan(s, unified.ptr, n_all, eps, minpts, impl, algo, local_labels.ptr, core.ptr));
+
+  // 4. local -> global labels
+  TempBuffer<int32_t> seg;
+  TempBuffer<long long> rank_off_dev;
+  ABX_TRY(seg.alloc(R + 1, s));
+  ABX_TRY(rank_off_dev.alloc(R + 1, s));
+  std::vector<int32_t> h_seg(R + 1);
+  for (int r = 0; r <= R; ++r)
+    h_seg[r] = (int32_t)fwd.recv_off[r];
+  ABX_CUDA_TRY(cudaMemcpyAsync(seg.ptr, h_seg.data(), sizeof(int32_t) * (R + 1), cudaMemcpyHostToDevice, s));
+  ABX_CUDA_TRY(cudaMemcpyAsync(rank_off_dev.ptr, rank_off.data(), sizeof(long long) * (R + 1), cudaMemcpyHostToDevice, s));
+  if (n_all > 0)
+    ABX_LAUNCH(globalLabelsKernel, divUp(n_all, 256), 256, 0, s, n_all, n, local_labels.ptr, ghost_ids.ptr, seg.ptr, R,
+               rank_off_dev.ptr, rank, glob.ptr);
+  if (n > 0)
+    ABX_CUDA_TRY(cudaMemcpyAsync(labels, glob.ptr, sizeof(long long) * n, cudaMemcpyDeviceToDevice, s));
+  if (fwd.global == 0)
+    return ABX_OK; // no rank has a ghost: nothing to reconcile (every rank takes this branch)
+
+  // 5. ghost labels back to their owners (noise is not sent); ghosts are grouped by owner already
+  TempBuffer<int32_t> flags, pos, back_ids;
+  TempBuffer<long long> back_labels;
+  ABX_TRY(flags.alloc((size_t)G + 1, s));
+  ABX_TRY(pos.alloc((size_t)G + 1, s));
+  ABX_TRY(back_ids.alloc((size_t)std::max<int64_t>(G, 1), s));
+  ABX_TRY(back_labels.alloc((size_t)std::max<int64_t>(G, 1), s));
+  ABX_CUDA_TRY(cudaMemsetAsync(flags.ptr, 0, sizeof(int32_t) * ((size_t)G + 1), s));
+  if (G > 0)
+    ABX_LAUNCH(flagLabelledKernel, divUp(G, 256), 256, 0, s, G, glob.ptr + n, flags.ptr);
+  ABX_TRY(exclusiveScanI32(s, flags.ptr, pos.ptr, G + 1));
+  if (G > 0)
+    ABX_LAUNCH(scatterLabelledKernel, divUp(G, 256), 256, 0, s, G, glob.ptr + n, ghost_ids.ptr, pos.ptr, back_labels.ptr,
+               back_ids.ptr);
+  ABX_LAUNCH(segmentTotalsKernel, 1, 64, 0, s, pos.ptr, seg.ptr, R, counts.ptr);
+  ABX_TRY(gatherCountMatrix(&t, s, counts.ptr, matrix.ptr));
+  ABX_CUDA_TRY(cudaStreamSynchronize(s)); // blocking point 3
+  ExchangePlan back;
+  back.fromMatrix(t.h_pin, R, rank);
+  int64_t const M = back.n_recv;
+  TempBuffer<int32_t> got_ids;
+  TempBuffer<long long> got_labels, got_sorted;
+  ABX_TRY(got_ids.alloc((size_t)std::max<int64_t>(M, 1), s));
+  ABX_TRY(got_labels.alloc((size_t)std::max<int64_t>(M, 1), s));
+  ABX_TRY(got_sorted.alloc((size_t)std::max<int64_t>(M, 1), s));
+  ExchangeColumn cols[2] = {{back_labels.ptr, got_labels.ptr, sizeof(long long)}, {back_ids.ptr, got_ids.ptr, sizeof(int32_t)}};
+  ABX_TRY(comm->allToAllV(cols, 2, back.send_off.data(), back.recv_off.data(), s));
+
+  // 6. merge pairs of this rank's multi-labelled points
+  TempBuffer<long long> pairs2;
+  TempBuffer<unsigned> n_pairs;
+  ABX_TRY(pairs2.alloc((size_t)std::max<int64_t>(4 * M, 2), s)); // at most one own pair + cnt pairs per point
+  ABX_TRY(n_pairs.alloc(1, s));
+  ABX_CUDA_TRY(cudaMemsetAsync(n_pairs.ptr, 0, sizeof(unsigned), s));
+  if (M > 0)
+  {
+    TempBuffer<uint32_t> perm;
+    ABX_TRY(perm.alloc((size_t)M, s));
+    ABX_TRY(sortPairsU32(s, (uint32_t *)got_ids.ptr, perm.ptr, M, true, bitsFor(std::max<int64_t>(n, 2)), /*fixup=*/false));
+    ABX_LAUNCH(gatherI64Kernel, divUp(M, 256), 256, 0, s, got_labels.ptr, perm.ptr, M, got_sorted.ptr);
+    ABX_LAUNCH(mergePairsKernel, divUp(M, 256), 256, 0, s, M, got_ids.ptr, got_sorted.ptr, core.ptr, labels, pairs2.ptr,
+               n_pairs.ptr);
+  }
+  unsigned h_pairs = 0;
+  ABX_CUDA_TRY(cudaMemcpyAsync(&h_pairs, n_pairs.ptr, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+  ABX_CUDA_TRY(cudaStreamSynchronize(s));
+  int64_t m_local = h_pairs;
+  TempBuffer<unsigned long long> from, to;
+  ABX_TRY(from.alloc((size_t)std::max<int64_t>(2 * m_local, 2), s));
+  ABX_TRY(to.alloc((size_t)std::max<int64_t>(2 * m_local, 2), s));
+  if (m_local > 0)
+    ABX_LAUNCH(splitPairsI64Kernel, divUp(m_local, 256), 256, 0, s, m_local, pairs2.ptr, from.ptr, to.ptr);
+  ABX_TRY(sortAndFilterPairs(s, m_local, from, to, &m_local));
+
+  // 7. all-gather-v of the merge pairs (counts, then rows padded to the longest contribution)
+  uint32_t const my_count = (uint32_t)m_local;
+  ABX_CUDA_TRY(cudaMemcpyAsync(counts.ptr, &my_count, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+  ABX_TRY(comm->allGather(counts.ptr, matrix.ptr, sizeof(uint32_t), s));
+  ABX_CUDA_TRY(cudaMemcpyAsync(t.h_pin, matrix.ptr, sizeof(uint32_t) * R, cudaMemcpyDeviceToHost, s));
+  ABX_CUDA_TRY(cudaStreamSynchronize(s)); // blocking point 4
+  std::vector<int64_t> pair_counts(R);
+  int64_t mx = 0, total_pairs = 0;
+  for (int r = 0; r < R; ++r)
+  {
+    pair_counts[r] = t.h_pin[r];
+    mx = std::max(mx, pair_counts[r]);
+    total_pairs += pair_counts[r];
+  }
+  if (total_pairs == 0)
+    return ABX_OK;
+  TempBuffer<unsigned long long> send_rows, all_rows, gfrom, gto;
+  ABX_TRY(send_rows.alloc((size_t)2 * mx, s));
+  ABX_TRY(all_rows.alloc((size_t)2 * mx * R, s));
+  ABX_CUDA_TRY(cudaMemsetAsync(send_rows.ptr, 0, sizeof(unsigned long long) * 2 * mx, s));
+  if (m_local > 0)
+  {
+    ABX_CUDA_TRY(cudaMemcpyAsync(send_rows.ptr, from.ptr, sizeof(unsigned long long) * m_local, cudaMemcpyDeviceToDevice, s));
+    ABX_CUDA_TRY(cudaMemcpyAsync(send_rows.ptr + mx, to.ptr, sizeof(unsigned long long) * m_local, cudaMemcpyDeviceToDevice, s));
+  }
+  ABX_TRY(comm->allGather(send_rows.ptr, all_rows.ptr, sizeof(unsigned long long) * 2 * mx, s));
+  ABX_TRY(gfrom.alloc((size_t)2 * total_pairs, s));
+  ABX_TRY(gto.alloc((size_t)2 * total_pairs, s));
+  int64_t o = 0;
+  for (int r = 0; r < R; ++r)
+  {
+    if (pair_counts[r] == 0)
+      continue;
+    ABX_CUDA_TRY(cudaMemcpyAsync(gfrom.ptr + o, all_rows.ptr + (size_t)2 * mx * r, sizeof(unsigned long long) * pair_counts[r],
+                                 cudaMemcpyDeviceToDevice, s));
+    ABX_CUDA_TRY(cudaMemcpyAsync(gto.ptr + o, all_rows.ptr + (size_t)2 * mx * r + mx,
+                                 sizeof(unsigned long long) * pair_counts[r], cudaMemcpyDeviceToDevice, s));
+    o += pair_counts[r];
+  }
+  int64_t m_global = 0;
+  ABX_TRY(sortAndFilterPairs(s, total_pairs, gfrom, gto, &m_global));
+  // 8. flatten
+  if (n > 0 && m_global > 0)
+    ABX_LAUNCH(relabelKernel, divUp(n, 256), 256, 0, s, n, labels, m_global, gfrom.ptr, gto.ptr);
+  return ABX_OK;
+}
+
 } // namespace abx
 
 // ------------------------------------------------------------------------- C ABI ----
@@ -1489,6 +1963,20 @@ abx_status abx_dist_query_nearest_crs_host(abx_dist_tree *t, void *stream, const
   deviceFree(vals, s);
   deviceFree(dist, s);
   return st;
+}
+
+abx_status abx_dist_dbscan_points3f(abx_comm *comm, void *stream, const float *xyz_dev, int64_t n, float eps,
+                                    int32_t minpts, int implementation, int algorithm, int64_t *labels_dev)
+{
+  if (!comm)
+  {
+    setError("null communicator");
+    return ABX_ERR_ARG;
+  }
+  ABX_TRY(ensureDevice());
+  static_assert(sizeof(long long) == sizeof(int64_t), "labels are 64-bit");
+  return distDbscan(comm, (cudaStream_t)stream, xyz_dev, n, eps, minpts, implementation, algorithm,
+                    (long long *)labels_dev);
 }
 
 abx_status abx_dist_nearest_pairs(abx_bvh *bvh, void *stream, const void *points_dev, int64_t q, int32_t k, int32_t rank,

@@ -13,8 +13,9 @@ halo small).  The path has three exchange steps and nothing else crosses ranks:
                 that carry several labels, all-gather-v of the merge pairs, every rank flattens its labels
                 through the sorted pair table.
 
-The exchanges are torch.distributed collectives (NCCL over NVLink on the GPU box, gloo in the CPU tests);
-the local engine is injectable exactly as in DistributedTree (tests use the CPU oracle as the checker)."""
+The product path is C++ (abx_dist_dbscan_points3f in libabx.so: kernels + grouped NCCL exchanges, four blocking
+points); `dbscan(comm, space, points, ...)` binds it.  With `engine=` the same protocol runs as torch tensor code over
+torch.distributed with an injectable local engine: the model the CPU tests exercise (gloo + the oracle)."""
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -78,15 +79,37 @@ def _relabel(pairs, labels):
     return labels
 
 
+def _dbscan_native(comm, space, points, eps, core_min_size, parameters):
+    """The C++ path: abx_dist_dbscan_points3f (halo routing kernel, grouped NCCL exchanges, abx::dbscan on local +
+    ghost points, merge-pair kernels; arborx_b200/csrc/abx_dist.cu)."""
+    import ctypes as C
+
+    from . import DBSCANParameters, _lib
+    from .distributed import Communicator
+    if not isinstance(comm, Communicator):
+        comm = Communicator.from_process_group(comm)
+    p = parameters or DBSCANParameters()
+    x = points.to(device=space.device, dtype=torch.float32).reshape(-1, 3).contiguous()
+    labels = torch.empty(x.shape[0], dtype=torch.int64, device=space.device)
+    with torch.cuda.stream(space.stream):
+        _lib.check(_lib.lib().abx_dist_dbscan_points3f(comm._h, space.handle, C.c_void_p(x.data_ptr()), x.shape[0],
+                                                       float(eps), int(core_min_size), p._implementation, p._algorithm,
+                                                       C.c_void_p(labels.data_ptr())))
+    return labels
+
+
 def dbscan(comm, space, points, eps, core_min_size, parameters=None, engine=None):
     """-> labels [n_local] int64: global id (rank offset + local index) of the cluster's representative
-    point, -1 for noise; equal labels across ranks mean the same cluster."""
+    point, -1 for noise; equal labels across ranks mean the same cluster.  Collective.  engine=None: the C++ path of
+    libabx.so (`comm`: a torch.distributed group or a Communicator); with an injected engine: the torch.distributed
+    protocol model below (CPU tests: gloo + the oracle as the local engine)."""
+    if engine is None:
+        return _dbscan_native(comm, space, points, eps, core_min_size, parameters)
     if not (eps > 0):
         raise ValueError("eps must be positive")
     if core_min_size < 2:
         raise ValueError("core_min_size must be at least 2")
     rank, R = dist.get_rank(comm), dist.get_world_size(comm)
-    engine = engine or CudaDBSCANEngine(space)
     pts = points.to(torch.float32).reshape(-1, 3).contiguous()
     dev = pts.device
     n_local = pts.shape[0]

@@ -278,6 +278,12 @@ ABX_API abx_status abx_dist_query_spatial_crs(abx_dist_tree *tree, void *stream,
 ABX_API abx_status abx_dist_query_nearest_crs(abx_dist_tree *tree, void *stream, const void *points_dev, int64_t q,
                                               int32_t k, abx_alloc_fn alloc, void *user, int32_t **offsets_dev,
                                               int32_t **values2_dev, float **distances_dev, int64_t *nnz);
+/* ArborX::Experimental::dbscan(comm, space, primitives, eps, core_min_size, labels, params)
+ * (cluster/ArborX_DistributedDBSCAN.hpp:29-190).  Collective.  The points are sharded as the caller sharded them;
+ * labels_dev[n] (64-bit): global id (offset of the owner rank + index there) of the cluster's representative point,
+ * -1 for noise; equal labels on different ranks mean the same cluster.  eps <= 0 or minpts < 2 -> ABX_ERR_SEARCH. */
+ABX_API abx_status abx_dist_dbscan_points3f(abx_comm *comm, void *stream, const float *xyz_dev, int64_t n, float eps,
+                                            int32_t minpts, int implementation, int algorithm, int64_t *labels_dev);
 /* Host-buffer variants (end-to-end path): primitives / predicates in host memory, results in host arrays
  * from `alloc_host`.  Results come back in the COMPACT form: indices (which = 1, one uint32 per result) all
  * belong to the calling rank except the n_remote entries listed in remote_pos (which = 3, ascending positions

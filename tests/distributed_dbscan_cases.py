@@ -77,8 +77,21 @@ def _canonical(labels, members):
 
 
 def run_all(make_engine, device, space=None, n=4000):
+    """The torch.distributed protocol model with an injected engine, on every rank of the default group."""
     rank, world = dist.get_rank(), dist.get_world_size()
     engine = make_engine() if space is None else make_engine(space)
+
+    def gather(a):
+        out = [None] * world
+        dist.all_gather_object(out, a)
+        return out
+
+    run = lambda pts, eps, minpts, params: dist_dbscan(dist.group.WORLD, space, pts, eps, minpts, params, engine=engine)
+    return run_cases(rank, world, run, gather, device, n)
+
+
+def run_cases(rank, world, run, gather, device, n=4000):
+    """run(points, eps, minpts, params) -> this rank's labels; gather(array) -> the arrays of all ranks."""
     ran = 0
     for seed, eps, minpts, impl, how in [(1, 0.12, 2, 0, "slabs"), (1, 0.12, 5, 0, "slabs"), (2, 0.2, 3, 1, "slabs"),
                                          (3, 0.15, 2, 1, "scattered"), (3, 0.15, 4, 0, "scattered"),
@@ -88,10 +101,9 @@ def run_all(make_engine, device, space=None, n=4000):
         parts = _split(xyz, world, how, seed)
         mine = parts[rank]
         pts = torch.from_numpy(xyz[mine]).to(device)
-        labels = dist_dbscan(dist.group.WORLD, space, pts, eps, minpts, DBSCANParameters(impl, 0), engine=engine)
+        labels = run(pts, eps, minpts, DBSCANParameters(impl, 0))
         assert labels.shape == (len(mine),) and labels.dtype == torch.int64
-        gathered = [None] * world
-        dist.all_gather_object(gathered, labels.cpu().numpy())
+        gathered = gather(labels.cpu().numpy())
         # global id = rank offset + local index = position in the rank-ordered concatenation
         order = np.concatenate(parts)
         xyz_cat = xyz[order]

@@ -128,9 +128,10 @@ def test_distributed_dbscan_gloo(world):
 
 @pytest.mark.gpu
 def test_distributed_dbscan_single_rank_cuda():
+    """abx_dist_dbscan_points3f over a one-rank NCCL communicator."""
     import arborx_b200 as abx
-    from arborx_b200.distributed_dbscan import CudaDBSCANEngine
-    from tests.distributed_dbscan_cases import run_all
+    from arborx_b200.distributed_dbscan import dbscan as dist_dbscan
+    from tests.distributed_dbscan_cases import run_cases
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     os.environ.setdefault("MASTER_PORT", "29556")
     created = False
@@ -139,7 +140,54 @@ def test_distributed_dbscan_single_rank_cuda():
         created = True
     try:
         space = abx.ExecutionSpace()
-        assert run_all(lambda s: CudaDBSCANEngine(s), torch.device("cuda", 0), space, n=20000) == 8
+        run = lambda pts, eps, minpts, params: dist_dbscan(dist.group.WORLD, space, pts, eps, minpts, params)
+        assert run_cases(0, 1, run, lambda a: [a], torch.device("cuda", 0), n=20000) == 8
     finally:
         if created:
             dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_distributed_dbscan_native_local_ranks(world):
+    """The C++ distributed DBSCAN with `world` ranks (host threads) on one GPU over the in-process communicator:
+    halo exchange, ghost labels back, merge pairs, all-gather of the pairs and relabelling as across GPUs."""
+    import threading
+
+    import arborx_b200 as abx
+    from arborx_b200.distributed import Communicator
+    from arborx_b200.distributed_dbscan import dbscan as dist_dbscan
+    from tests.distributed_dbscan_cases import run_cases
+    comms = Communicator.local_group(world)
+    errors = [None] * world
+    barrier = threading.Barrier(world)
+    shared = {}
+
+    def worker(r):
+        try:
+            torch.cuda.set_device(0)
+            space = abx.ExecutionSpace(torch.cuda.Stream())
+
+            def gather(a):
+                shared[r] = a
+                barrier.wait(timeout=120)
+                out = [shared[k] for k in range(world)]
+                barrier.wait(timeout=120)
+                return out
+
+            with torch.cuda.stream(space.stream):
+                run = lambda pts, eps, minpts, params: dist_dbscan(comms[r], space, pts, eps, minpts, params)
+                assert run_cases(r, world, run, gather, torch.device("cuda", 0), n=6000) == 8
+        except BaseException:
+            import traceback
+            errors[r] = traceback.format_exc()
+            barrier.abort()
+
+    threads = [threading.Thread(target=worker, args=(r,), daemon=True) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=600)
+    assert not any(t.is_alive() for t in threads), "a rank is stuck in a collective: %s" % errors
+    for r, e in enumerate(errors):
+        assert e is None, "rank %d:\n%s" % (r, e)
