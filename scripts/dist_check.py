@@ -34,9 +34,19 @@ for pred, kw in ((_Pred("spatial", 0, sp), {}), (_Pred("nearest", 2, qs, 8), {"r
         assert torch.equal(a[2].cpu(), b[2].cpu()), "distances differ"
     else:
         assert rows(a[0], a[1]) == rows(b[0], b[1]), "rows differ"
-from arborx_b200.distributed_dbscan import CudaDBSCANEngine
-from tests.distributed_dbscan_cases import run_all as run_dbscan
-assert run_dbscan(lambda s: CudaDBSCANEngine(s), dev, space, n=40000) == 8
+# distributed DBSCAN: the C++ path (abx_dist_dbscan_points3f) and the torch protocol model with the CUDA engine
+from arborx_b200.distributed_dbscan import CudaDBSCANEngine, dbscan as dist_dbscan
+from tests.distributed_dbscan_cases import run_all as run_dbscan_model, run_cases as run_dbscan_cases
+
+
+def gather(a):
+    out = [None] * world
+    dist.all_gather_object(out, a)
+    return out
+
+
+assert run_dbscan_cases(rank, world, lambda p, eps, m, prm: dist_dbscan(comm, space, p, eps, m, prm), gather, dev, n=40000) == 8
+assert run_dbscan_model(lambda s: CudaDBSCANEngine(s), dev, space, n=40000) == 8
 dist.barrier()
 if rank == 0:
     print("DIST CHECK OK world=%d" % world)
