@@ -21,9 +21,13 @@
 
 #include <algorithm>
 #include <condition_variable>
+#include <cstdio>
 #include <cstring>
+#include <ctime>
 #include <memory>
 #include <mutex>
+#include <string>
+#include <utility>
 #include <vector>
 
 #include <dlfcn.h>
@@ -566,6 +570,60 @@ namespace abx
 namespace
 {
 
+// Phase timeline of a distributed query (tuning build only, ABX_DIST_TRACE=1): every mark drains the streams it is
+// given, so the phases are serialised and the numbers attribute the time instead of reproducing the overlapped call.
+struct PhaseTrace
+{
+#ifdef ABX_TUNING
+  char const *what;
+  int rank;
+  bool on;
+  std::vector<std::pair<char const *, double>> marks;
+  static double now()
+  {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+  }
+  PhaseTrace(char const *w, int r) : what(w), rank(r), on(ABX_TUNE_INT("ABX_DIST_TRACE", 0) != 0)
+  {
+    if (on)
+      marks.emplace_back("start", now());
+  }
+  void mark(char const *name, cudaStream_t a, cudaStream_t b = nullptr)
+  {
+    if (!on)
+      return;
+    cudaStreamSynchronize(a);
+    if (b)
+      cudaStreamSynchronize(b);
+    marks.emplace_back(name, now());
+  }
+  ~PhaseTrace()
+  {
+    if (!on)
+      return;
+    cudaDeviceSynchronize();
+    marks.emplace_back("rest", now());
+    if (rank != 0)
+      return;
+    std::string line = std::string("[abx trace] ") + what + ":";
+    for (size_t i = 1; i < marks.size(); ++i)
+    {
+      char buf[96];
+      snprintf(buf, sizeof buf, " %s %.3f", marks[i].first, marks[i].second - marks[i - 1].second);
+      line += buf;
+    }
+    char buf[64];
+    snprintf(buf, sizeof buf, " | total %.3f", marks.back().second - marks.front().second);
+    fprintf(stderr, "%s%s\n", line.c_str(), buf);
+  }
+#else
+  PhaseTrace(char const *, int) {}
+  void mark(char const *, cudaStream_t, cudaStream_t = nullptr) {}
+#endif
+};
+
 // counts_dev[R] of every rank -> pinned host matrix M[src][dst]; the caller's next blocking point covers it
 abx_status gatherCountMatrix(abx_dist_tree *t, cudaStream_t s, uint32_t const *counts_dev, uint32_t *matrix_dev)
 {
@@ -731,6 +789,7 @@ abx_status distSpatial(abx_dist_tree *t, cudaStream_t s, int pred_kind, void con
   // the tree's side stream while the big local traversal runs on `s`: its host round trips and small kernels hide
   // behind the local traversal instead of stretching the call.
   cudaStream_t const x = t->side;
+  PhaseTrace trace("spatial", t->rank);
   ABX_CUDA_TRY(cudaEventRecord(t->ev[0], s)); // the predicates may be produced on s
   ABX_CUDA_TRY(cudaStreamWaitEvent(x, t->ev[0], 0));
   // 1. routing counts of every rank -> count matrix on its way to the host
@@ -742,9 +801,11 @@ abx_status distSpatial(abx_dist_tree *t, cudaStream_t s, int pred_kind, void con
                       nullptr));
   ABX_TRY(gatherCountMatrix(t, x, counts.ptr, matrix.ptr));
   ABX_CUDA_TRY(cudaEventRecord(t->ev[1], x));
+  trace.mark("route_count+matrix", x);
   // 2. the local tree answers every local predicate (enqueued now, collected after the exchange)
   SpatialCrsCall local;
   ABX_TRY(spatialCrsBegin(local, t->bottom, s, pred_kind, preds, q, policy, nullptr, nullptr));
+  trace.mark("local_begin", s);
   struct Guard
   {
     cudaStream_t s;
@@ -769,6 +830,7 @@ abx_status distSpatial(abx_dist_tree *t, cudaStream_t s, int pred_kind, void con
     TempBuffer<uint32_t> fwd_preds;
     TempBuffer<int32_t> fwd_ids;
     ABX_TRY(forwardPredicates(t, x, pred_kind, preds, W, q, nullptr, 0, fwd, fwd_preds, fwd_ids));
+    trace.mark("forward", x);
     int64_t const G = fwd.n_recv;
     TempBuffer<int32_t> starts;
     ABX_TRY(starts.alloc(R + 1, x));
@@ -788,6 +850,7 @@ abx_status distSpatial(abx_dist_tree *t, cudaStream_t s, int pred_kind, void con
                          return gatherCountMatrix(t, x, counts.ptr, matrix.ptr);
                        }));
     Guard remote_guard{x, off_r, idx_r};
+    trace.mark("remote_query", x);
     ExchangePlan back;
     back.fromMatrix(t->h_pin, R, t->rank);
     M = back.n_recv;
@@ -800,7 +863,9 @@ abx_status distSpatial(abx_dist_tree *t, cudaStream_t s, int pred_kind, void con
     ABX_TRY(got_ids.alloc((size_t)std::max<int64_t>(M, 1), x));
     ExchangeColumn cols[2] = {{idx_r, got_idx.ptr, sizeof(int32_t)}, {res_ids.ptr, got_ids.ptr, sizeof(int32_t)}};
     ABX_TRY(t->comm->allToAllV(cols, 2, back.send_off.data(), back.recv_off.data(), x));
+    trace.mark("back", x);
     ABX_TRY(sortReceived(t, x, M, q, back, got_ids, got_idx.ptr, nullptr, rvals2, unused));
+    trace.mark("sort_received", x);
   }
   ABX_CUDA_TRY(cudaEventRecord(t->ev[2], x));
   // the local query's own blocking point (nnz), then its compaction
@@ -808,6 +873,7 @@ abx_status distSpatial(abx_dist_tree *t, cudaStream_t s, int pred_kind, void con
   uint32_t *idx_l = nullptr;
   int64_t nnz_l = 0;
   ABX_TRY(spatialCrsEnd(local, &off_l, &idx_l, &nnz_l));
+  trace.mark("local_end", s);
   local_guard.b = idx_l;
   ABX_CUDA_TRY(cudaStreamWaitEvent(s, t->ev[2], 0)); // the remote records are in place
   // buffers taken under the side stream go back to it when this frame unwinds: not before the merge below (on s)
@@ -934,7 +1000,10 @@ abx_status distNearest(abx_dist_tree *t, cudaStream_t s, void const *pts, int64_
   TempBuffer<unsigned long long> missing;
   ABX_TRY(missing.alloc(1, s));
   ABX_CUDA_TRY(cudaMemsetAsync(missing.ptr, 0, sizeof(unsigned long long), s));
+  PhaseTrace trace("nearest", t->rank);
+  trace.mark("alloc", s);
   ABX_TRY(localKnnPairs(t->bottom, s, pts, q, k, t->rank, rows_p, rowsd_p, missing.ptr));
+  trace.mark("local_knn", s);
   // 2. phase II routing: sphere (point, local k-th distance); an infinite bound reaches every rank
   TempBuffer<uint32_t> counts, matrix;
   ABX_TRY(counts.alloc(R, s));
@@ -947,6 +1016,7 @@ abx_status distNearest(abx_dist_tree *t, cudaStream_t s, void const *pts, int64_
   unsigned long long *h_missing = reinterpret_cast<unsigned long long *>(t->h_pin + (((size_t)R * R + 1) & ~(size_t)1));
   ABX_CUDA_TRY(cudaMemcpyAsync(h_missing, missing.ptr, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
   ABX_CUDA_TRY(cudaStreamSynchronize(s)); // blocking point 1
+  trace.mark("route_count+matrix", s);
   bool maybe_short = *h_missing != 0;
   ExchangePlan fwd;
   fwd.fromMatrix(t->h_pin, R, t->rank);
@@ -958,6 +1028,7 @@ abx_status distNearest(abx_dist_tree *t, cudaStream_t s, void const *pts, int64_
     TempBuffer<uint32_t> fwd_pts;
     TempBuffer<int32_t> fwd_ids;
     ABX_TRY(forwardPredicates(t, s, ABX_PRED_SPHERE3F, pts, 3, q, radius, k, fwd, fwd_pts, fwd_ids));
+    trace.mark("forward", s);
     int64_t const G = fwd.n_recv;
     int const nloc = (int)t->bottom->n;
     int const stride = std::max(1, std::min(k, nloc));
@@ -978,6 +1049,7 @@ abx_status distNearest(abx_dist_tree *t, cudaStream_t s, void const *pts, int64_
       ABX_TRY(nearestQuery(s, t->bottom, (float const *)fwd_pts.ptr, G, k, nullptr, qperm.ptr, nullptr, G * stride,
                            r_counts.ptr, r_idx.ptr, r_dist.ptr));
     }
+    trace.mark("remote_knn", s);
     ABX_TRY(exclusiveScanI32(s, r_counts.ptr, r_off.ptr, G + 1));
     std::vector<int32_t> h_starts(R + 1);
     for (int r = 0; r <= R; ++r)
@@ -986,6 +1058,7 @@ abx_status distNearest(abx_dist_tree *t, cudaStream_t s, void const *pts, int64_
     ABX_LAUNCH(segmentTotalsKernel, 1, 64, 0, s, r_off.ptr, starts.ptr, R, counts.ptr);
     ABX_TRY(gatherCountMatrix(t, s, counts.ptr, matrix.ptr));
     ABX_CUDA_TRY(cudaStreamSynchronize(s)); // blocking point 2
+    trace.mark("scan+matrix", s);
     ExchangePlan back;
     back.fromMatrix(t->h_pin, R, t->rank);
     M = back.n_recv;
@@ -1006,9 +1079,12 @@ abx_status distNearest(abx_dist_tree *t, cudaStream_t s, void const *pts, int64_
                               {s_ids.ptr, got_ids.ptr, sizeof(int32_t)},
                               {s_dist.ptr, got_dist.ptr, sizeof(float)}};
     ABX_TRY(t->comm->allToAllV(cols, 3, back.send_off.data(), back.recv_off.data(), s));
+    trace.mark("back", s);
     ABX_TRY(sortReceived(t, s, M, q, back, got_ids, got_idx.ptr, got_dist.ptr, rvals2, rdist));
+    trace.mark("sort_received", s);
     // 5. final ranking (DistributedTreeNearest.hpp:178-233): the k smallest of local row + candidates
     ABX_TRY(knnMerge(s, M, got_ids.ptr, rvals2.ptr, rdist.ptr, k, rows_p, rowsd_p));
+    trace.mark("merge", s);
   }
   // 6. outputs.  Rows are full (k entries) unless some local row was short and stayed short.
   TempBuffer<int32_t> row_counts, row_off;

@@ -444,8 +444,10 @@ def run_ours(args):
         # The query batches are independent, and so are their parts: each batch is issued as E2E_CHUNKS host
         # calls from E2E_THREADS host threads, every thread on its own execution space instance (stream), so
         # the result copy of one call overlaps the traversal of the next (PCIe is the long pole of this path:
-        # 0.4 GB in, 0.88 GB out per step).  kNN parts first: they are the longer ones.
-        parts_all = hp_nearest_parts + hp_spatial_parts
+        # 0.4 GB in, 0.88 GB out per step).  Spatial parts first: they have the most result bytes per traversal
+        # millisecond, so their copies run under the kNN traversals (scripts/e2e_timeline.py,
+        # profiles/r02_e2e_timeline.log: 26.6 ms against 30.5 ms with the kNN parts first).
+        parts_all = hp_spatial_parts + hp_nearest_parts
         futures = [e2e_pool.submit(e2e_task, bvh, p, i) for i, p in enumerate(parts_all)]
         total, n_idx, n_kidx = 0, 0, 0
         for f, p in zip(futures, parts_all):
