@@ -363,6 +363,11 @@ abx_status exportReference(cudaStream_t s, abx_bvh *bvh, int32_t *leaf_rope, uin
 // query.cu
 abx_status predicatePermutation(cudaStream_t s, abx_bvh *bvh, int pred_kind, void const *preds, int64_t q,
                                 TempBuffer<uint32_t> &perm);
+// the same order with the points within `near` of another rank's box first (DistributedTree's two-stage kNN);
+// *n_near_dev receives their number
+abx_status pointPermutationNearFirst(cudaStream_t s, abx_bvh *bvh, float const *pts, int64_t q, float const *boxes6,
+                                     int R, int self_rank, float near, TempBuffer<uint32_t> &perm,
+                                     unsigned *n_near_dev);
 abx_status spatialCount(cudaStream_t s, abx_bvh *bvh, int pred_kind, void const *preds, int64_t q,
                         uint32_t const *qperm, int32_t limit, int32_t *counts);
 abx_status spatialFill(cudaStream_t s, abx_bvh *bvh, int pred_kind, void const *preds, int64_t q,
@@ -375,7 +380,10 @@ abx_status spatialCompact(cudaStream_t s, abx_bvh *bvh, int pred_kind, void cons
 abx_status nearestQuery(cudaStream_t s, abx_bvh *bvh, float const *pts, int64_t q, int32_t k,
                         int32_t const *k_per_query, uint32_t const *qperm, int32_t const *offsets, int64_t total_rows,
                         int32_t *counts, uint32_t *indices, float *distances,
-                        unsigned long long *missing = nullptr, int pair_rank = -1);
+                        unsigned long long *missing = nullptr, int pair_rank = -1, bool pad_pairs = true);
+// (index, rank) rows of k slots: the slots behind counts[i] become (-1, -1) / +inf; ids = the rows to visit (or all)
+abx_status padShortRows(cudaStream_t s, int64_t rows, int k, int32_t const *counts, int32_t *vals2, float *dist,
+                        uint32_t const *ids = nullptr);
 abx_status nearestGeomQuery(cudaStream_t s, abx_bvh *t, int pred_kind, float const *preds, int64_t q, int32_t k,
                             uint32_t const *qperm, int64_t total_rows, int32_t *counts, uint32_t *indices,
                             float *distances, unsigned long long *missing);
@@ -385,7 +393,7 @@ abx_status compactRows(cudaStream_t s, int64_t q, int32_t const *old_offsets, in
                        uint32_t const *old_idx, float const *old_dist, uint32_t *new_idx, float *new_dist);
 abx_status routeLaunch(cudaStream_t s, bool fill, int pred_kind, void const *preds, int64_t q, float const *radius,
                        int64_t radius_stride, float const *boxes6, int R, int self_rank, unsigned *counts,
-                       unsigned const *base, unsigned *cursors, int32_t *out_qid);
+                       unsigned const *base, unsigned *cursors, int32_t *out_qid, uint32_t const *ids = nullptr);
 abx_status mergeSorted(cudaStream_t s, int64_t q, int32_t const *local_off, int32_t const *local_idx, int rank,
                        int64_t m, int32_t const *remote_ids, int32_t const *remote_vals2, int32_t *out_off,
                        int32_t *out_vals2);

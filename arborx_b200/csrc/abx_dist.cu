@@ -517,6 +517,9 @@ void returnSideStream(cudaStream_t s)
 // forwarded batches below this size are traversed in arrival order (already grouped by source rank and, inside a
 // source, by the sender's routing order): six launches of Morton ordering cost more than they return
 constexpr int64_t kSortForwardedAbove = 32768;
+// distributed kNN with at least this many points per call goes in two stages (near-boundary points first, their
+// exchange hidden behind the interior points' traversal)
+constexpr int64_t kTwoStageKnnAbove = 262144;
 
 int predWords(int kind) { return kind == ABX_PRED_SPHERE3F ? 4 : kind == ABX_PRED_BOX3F ? 6 : 3; }
 int primWords(int kind) { return kind == ABX_PRIM_POINT3F ? 3 : kind == ABX_PRIM_BOX3F ? 6 : 9; }
@@ -577,7 +580,7 @@ struct PhaseTrace
 #ifdef ABX_TUNING
   char const *what;
   int rank;
-  bool on;
+  int on; // 1: drain the streams at every mark (attribution); 2: host clock only (the overlapped call as it runs)
   std::vector<std::pair<char const *, double>> marks;
   static double now()
   {
@@ -585,7 +588,7 @@ struct PhaseTrace
     clock_gettime(CLOCK_MONOTONIC, &ts);
     return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
   }
-  PhaseTrace(char const *w, int r) : what(w), rank(r), on(ABX_TUNE_INT("ABX_DIST_TRACE", 0) != 0)
+  PhaseTrace(char const *w, int r) : what(w), rank(r), on(ABX_TUNE_INT("ABX_DIST_TRACE", 0))
   {
     if (on)
       marks.emplace_back("start", now());
@@ -594,9 +597,12 @@ struct PhaseTrace
   {
     if (!on)
       return;
-    cudaStreamSynchronize(a);
-    if (b)
-      cudaStreamSynchronize(b);
+    if (on == 1)
+    {
+      cudaStreamSynchronize(a);
+      if (b)
+        cudaStreamSynchronize(b);
+    }
     marks.emplace_back(name, now());
   }
   ~PhaseTrace()
@@ -658,7 +664,8 @@ struct ExchangePlan
 // received predicates and their query ids on the source rank.
 abx_status forwardPredicates(abx_dist_tree *t, cudaStream_t s, int route_kind, void const *preds, int words, int64_t q,
                              float const *radius, int64_t radius_stride, ExchangePlan const &plan,
-                             TempBuffer<uint32_t> &fwd_preds, TempBuffer<int32_t> &fwd_ids)
+                             TempBuffer<uint32_t> &fwd_preds, TempBuffer<int32_t> &fwd_ids,
+                             uint32_t const *subset = nullptr /* q predicate ids to route, or all */)
 {
   int const R = t->R;
   int64_t const F = plan.n_send, G = plan.n_recv;
@@ -679,7 +686,7 @@ abx_status forwardPredicates(abx_dist_tree *t, cudaStream_t s, int route_kind, v
     ABX_CUDA_TRY(cudaMemcpyAsync(base.ptr, h_base.data(), sizeof(uint32_t) * R, cudaMemcpyHostToDevice, s));
     ABX_CUDA_TRY(cudaMemsetAsync(cursors.ptr, 0, sizeof(uint32_t) * R, s));
     ABX_TRY(routeLaunch(s, true, route_kind, preds, q, radius, radius_stride, t->boxes_dev, R, t->rank, nullptr,
-                        base.ptr, cursors.ptr, qids.ptr));
+                        base.ptr, cursors.ptr, qids.ptr, subset));
     ABX_LAUNCH(gatherWordsKernel, divUp(F * words, 256), 256, 0, s, (uint32_t const *)preds, qids.ptr, F, words,
                send_preds.ptr);
   }
@@ -931,6 +938,87 @@ abx_status distSpatial(abx_dist_tree *t, cudaStream_t s, int pred_kind, void con
   return ABX_OK;
 }
 
+// One exchange of the distributed kNN for the points listed in `subset` (or all q points): forward those whose
+// (point, local k-th distance) sphere reaches other ranks (`fwd` = the count matrix of the routing pass), k nearest
+// in the receivers' bottom trees, candidates back, re-ranking of the affected rows in place.  All on stream s,
+// one blocking point (the back-count matrix).
+struct KnnRound
+{
+  TempBuffer<int32_t> got_ids; // query ids of the candidates received, ascending
+  int64_t M = 0;
+};
+abx_status knnExchangeRound(abx_dist_tree *t, cudaStream_t s, void const *pts, int64_t q, int32_t k,
+                            uint32_t const *subset, int64_t subset_n, float const *radius, ExchangePlan const &fwd,
+                            TempBuffer<uint32_t> &counts, TempBuffer<uint32_t> &matrix, int32_t *rows_p, float *rowsd_p,
+                            KnnRound &out, PhaseTrace &trace)
+{
+  int const R = t->R;
+  TempBuffer<int32_t> rvals2;
+  TempBuffer<float> rdist;
+  TempBuffer<uint32_t> fwd_pts;
+  TempBuffer<int32_t> fwd_ids;
+  ABX_TRY(forwardPredicates(t, s, ABX_PRED_SPHERE3F, pts, 3, subset_n, radius, k, fwd, fwd_pts, fwd_ids, subset));
+  trace.mark("forward", s);
+  int64_t const G = fwd.n_recv;
+  int const nloc = (int)t->bottom->n;
+  int const stride = std::max(1, std::min(k, nloc));
+  // 3. k nearest of the forwarded points in the bottom tree
+  TempBuffer<uint32_t> r_idx, qperm;
+  TempBuffer<float> r_dist;
+  TempBuffer<int32_t> r_counts, r_off, starts;
+  ABX_TRY(r_idx.alloc((size_t)std::max<int64_t>(G, 1) * stride, s));
+  ABX_TRY(r_dist.alloc((size_t)std::max<int64_t>(G, 1) * stride, s));
+  ABX_TRY(r_counts.alloc((size_t)G + 1, s));
+  ABX_TRY(r_off.alloc((size_t)G + 1, s));
+  ABX_TRY(starts.alloc(R + 1, s));
+  ABX_CUDA_TRY(cudaMemsetAsync(r_counts.ptr, 0, sizeof(int32_t) * ((size_t)G + 1), s));
+  if (G > 0 && nloc > 0)
+  {
+    if (nloc > 1 && G >= kSortForwardedAbove)
+      ABX_TRY(predicatePermutation(s, t->bottom, ABX_PRED_POINT3F, fwd_pts.ptr, G, qperm));
+    ABX_TRY(nearestQuery(s, t->bottom, (float const *)fwd_pts.ptr, G, k, nullptr, qperm.ptr, nullptr, G * stride,
+                         r_counts.ptr, r_idx.ptr, r_dist.ptr));
+  }
+  trace.mark("remote_knn", s);
+  ABX_TRY(exclusiveScanI32(s, r_counts.ptr, r_off.ptr, G + 1));
+  std::vector<int32_t> h_starts(R + 1);
+  for (int r = 0; r <= R; ++r)
+    h_starts[r] = (int32_t)fwd.recv_off[r];
+  ABX_CUDA_TRY(cudaMemcpyAsync(starts.ptr, h_starts.data(), sizeof(int32_t) * (R + 1), cudaMemcpyHostToDevice, s));
+  ABX_LAUNCH(segmentTotalsKernel, 1, 64, 0, s, r_off.ptr, starts.ptr, R, counts.ptr);
+  ABX_TRY(gatherCountMatrix(t, s, counts.ptr, matrix.ptr));
+  ABX_CUDA_TRY(cudaStreamSynchronize(s)); // blocking point
+  trace.mark("scan+matrix", s);
+  ExchangePlan back;
+  back.fromMatrix(t->h_pin, R, t->rank);
+  int64_t const M = back.n_recv;
+  int64_t const nnz_r = back.n_send;
+  // 4. candidates back as (index, distance, query id) columns
+  TempBuffer<int32_t> s_idx, s_ids, got_idx;
+  TempBuffer<float> s_dist, got_dist;
+  ABX_TRY(s_idx.alloc((size_t)std::max<int64_t>(nnz_r, 1), s));
+  ABX_TRY(s_ids.alloc((size_t)std::max<int64_t>(nnz_r, 1), s));
+  ABX_TRY(s_dist.alloc((size_t)std::max<int64_t>(nnz_r, 1), s));
+  if (G > 0)
+    ABX_LAUNCH(packKnnResultsKernel, divUp(G, 128), 128, 0, s, (int)G, stride, r_counts.ptr, r_off.ptr, r_idx.ptr,
+               r_dist.ptr, fwd_ids.ptr, s_idx.ptr, s_dist.ptr, s_ids.ptr);
+  ABX_TRY(got_idx.alloc((size_t)std::max<int64_t>(M, 1), s));
+  ABX_TRY(out.got_ids.alloc((size_t)std::max<int64_t>(M, 1), s));
+  ABX_TRY(got_dist.alloc((size_t)std::max<int64_t>(M, 1), s));
+  ExchangeColumn cols[3] = {{s_idx.ptr, got_idx.ptr, sizeof(int32_t)},
+                            {s_ids.ptr, out.got_ids.ptr, sizeof(int32_t)},
+                            {s_dist.ptr, got_dist.ptr, sizeof(float)}};
+  ABX_TRY(t->comm->allToAllV(cols, 3, back.send_off.data(), back.recv_off.data(), s));
+  trace.mark("back", s);
+  ABX_TRY(sortReceived(t, s, M, q, back, out.got_ids, got_idx.ptr, got_dist.ptr, rvals2, rdist));
+  trace.mark("sort_received", s);
+  // 5. final ranking (DistributedTreeNearest.hpp:178-233): the k smallest of local row + candidates
+  ABX_TRY(knnMerge(s, M, out.got_ids.ptr, rvals2.ptr, rdist.ptr, k, rows_p, rowsd_p));
+  trace.mark("merge", s);
+  out.M = M;
+  return ABX_OK;
+}
+
 // ---- nearest -------------------------------------------------------------------------------
 // pairs rows (index, rank) x k per query are produced on the device in both forms; compact = true then
 // splits them into index rows + the list of entries owned by other ranks.
@@ -1002,90 +1090,138 @@ abx_status distNearest(abx_dist_tree *t, cudaStream_t s, void const *pts, int64_
   ABX_CUDA_TRY(cudaMemsetAsync(missing.ptr, 0, sizeof(unsigned long long), s));
   PhaseTrace trace("nearest", t->rank);
   trace.mark("alloc", s);
-  ABX_TRY(localKnnPairs(t->bottom, s, pts, q, k, t->rank, rows_p, rowsd_p, missing.ptr));
-  trace.mark("local_knn", s);
-  // 2. phase II routing: sphere (point, local k-th distance); an infinite bound reaches every rank
+  float const *radius = rowsd_p + (k - 1);
+  unsigned long long *h_missing = reinterpret_cast<unsigned long long *>(t->h_pin + (((size_t)R * R + 1) & ~(size_t)1));
+  KnnRound round_a, round_b;
+  cudaStream_t const x = t->side;
+  // Two stages when there are other ranks and enough queries to hide an exchange behind: the points close to another
+  // rank's box go first, and their exchange (routing, both count matrices, both NCCL exchanges, the remote kNN, the
+  // re-ranking of their rows) runs on the side stream while the caller's stream walks the interior points.  `near`
+  // is a guess (2.4 x the k-neighbour radius of a uniform cloud with the bottom tree's density): interior points
+  // are routed as well once their k-th distances are known, and the rare one that does reach another rank takes a
+  // second exchange -- the result does not depend on the guess.
+  // Every rank runs the same two rounds of collectives (the split is a local choice: a rank with few points, or a
+  // degenerate box, puts all its points in the first stage).
+  float near = 0.f;
+  if (R > 1 && q >= kTwoStageKnnAbove && t->bottom->n > (int64_t)k)
+  {
+    float const *b = t->boxes.data() + 6 * (size_t)t->rank;
+    double const vol = (double)(b[3] - b[0]) * (double)(b[4] - b[1]) * (double)(b[5] - b[2]);
+    if (vol > 0 && std::isfinite(vol))
+      near = (float)(1.5 * std::cbrt((double)k * vol / (double)t->bottom->n));
+  }
+  bool const two_stage = R > 1;
+  bool const split = near > 0.f && std::isfinite(near);
+  TempBuffer<uint32_t> qperm;
+  TempBuffer<int32_t> row_found;
   TempBuffer<uint32_t> counts, matrix;
   ABX_TRY(counts.alloc(R, s));
   ABX_TRY(matrix.alloc((size_t)R * R, s));
-  ABX_CUDA_TRY(cudaMemsetAsync(counts.ptr, 0, sizeof(uint32_t) * R, s));
-  float const *radius = rowsd_p + (k - 1);
-  ABX_TRY(routeLaunch(s, false, ABX_PRED_SPHERE3F, pts, q, radius, k, t->boxes_dev, R, t->rank, counts.ptr, nullptr,
-                      nullptr, nullptr));
-  ABX_TRY(gatherCountMatrix(t, s, counts.ptr, matrix.ptr));
-  unsigned long long *h_missing = reinterpret_cast<unsigned long long *>(t->h_pin + (((size_t)R * R + 1) & ~(size_t)1));
-  ABX_CUDA_TRY(cudaMemcpyAsync(h_missing, missing.ptr, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-  ABX_CUDA_TRY(cudaStreamSynchronize(s)); // blocking point 1
-  trace.mark("route_count+matrix", s);
-  bool maybe_short = *h_missing != 0;
-  ExchangePlan fwd;
-  fwd.fromMatrix(t->h_pin, R, t->rank);
-  TempBuffer<int32_t> got_ids, rvals2;
-  TempBuffer<float> rdist;
-  int64_t M = 0;
-  if (fwd.global > 0)
+  bool maybe_short = false;
+  if (!two_stage)
   {
-    TempBuffer<uint32_t> fwd_pts;
-    TempBuffer<int32_t> fwd_ids;
-    ABX_TRY(forwardPredicates(t, s, ABX_PRED_SPHERE3F, pts, 3, q, radius, k, fwd, fwd_pts, fwd_ids));
-    trace.mark("forward", s);
-    int64_t const G = fwd.n_recv;
-    int const nloc = (int)t->bottom->n;
-    int const stride = std::max(1, std::min(k, nloc));
-    // 3. k nearest of the forwarded points in the bottom tree
-    TempBuffer<uint32_t> r_idx, qperm;
-    TempBuffer<float> r_dist;
-    TempBuffer<int32_t> r_counts, r_off, starts;
-    ABX_TRY(r_idx.alloc((size_t)std::max<int64_t>(G, 1) * stride, s));
-    ABX_TRY(r_dist.alloc((size_t)std::max<int64_t>(G, 1) * stride, s));
-    ABX_TRY(r_counts.alloc((size_t)G + 1, s));
-    ABX_TRY(r_off.alloc((size_t)G + 1, s));
-    ABX_TRY(starts.alloc(R + 1, s));
-    ABX_CUDA_TRY(cudaMemsetAsync(r_counts.ptr, 0, sizeof(int32_t) * ((size_t)G + 1), s));
-    if (G > 0 && nloc > 0)
-    {
-      if (nloc > 1 && G >= kSortForwardedAbove)
-        ABX_TRY(predicatePermutation(s, t->bottom, ABX_PRED_POINT3F, fwd_pts.ptr, G, qperm));
-      ABX_TRY(nearestQuery(s, t->bottom, (float const *)fwd_pts.ptr, G, k, nullptr, qperm.ptr, nullptr, G * stride,
-                           r_counts.ptr, r_idx.ptr, r_dist.ptr));
-    }
-    trace.mark("remote_knn", s);
-    ABX_TRY(exclusiveScanI32(s, r_counts.ptr, r_off.ptr, G + 1));
-    std::vector<int32_t> h_starts(R + 1);
-    for (int r = 0; r <= R; ++r)
-      h_starts[r] = (int32_t)fwd.recv_off[r];
-    ABX_CUDA_TRY(cudaMemcpyAsync(starts.ptr, h_starts.data(), sizeof(int32_t) * (R + 1), cudaMemcpyHostToDevice, s));
-    ABX_LAUNCH(segmentTotalsKernel, 1, 64, 0, s, r_off.ptr, starts.ptr, R, counts.ptr);
+    ABX_TRY(localKnnPairs(t->bottom, s, pts, q, k, t->rank, rows_p, rowsd_p, missing.ptr));
+    trace.mark("local_knn", s);
+    // 2. phase II routing: sphere (point, local k-th distance); an infinite bound reaches every rank
+    ABX_CUDA_TRY(cudaMemsetAsync(counts.ptr, 0, sizeof(uint32_t) * R, s));
+    ABX_TRY(routeLaunch(s, false, ABX_PRED_SPHERE3F, pts, q, radius, k, t->boxes_dev, R, t->rank, counts.ptr, nullptr,
+                        nullptr, nullptr));
     ABX_TRY(gatherCountMatrix(t, s, counts.ptr, matrix.ptr));
-    ABX_CUDA_TRY(cudaStreamSynchronize(s)); // blocking point 2
-    trace.mark("scan+matrix", s);
-    ExchangePlan back;
-    back.fromMatrix(t->h_pin, R, t->rank);
-    M = back.n_recv;
-    int64_t const nnz_r = back.n_send;
-    // 4. candidates back as (index, distance, query id) columns
-    TempBuffer<int32_t> s_idx, s_ids, got_idx;
-    TempBuffer<float> s_dist, got_dist;
-    ABX_TRY(s_idx.alloc((size_t)std::max<int64_t>(nnz_r, 1), s));
-    ABX_TRY(s_ids.alloc((size_t)std::max<int64_t>(nnz_r, 1), s));
-    ABX_TRY(s_dist.alloc((size_t)std::max<int64_t>(nnz_r, 1), s));
-    if (G > 0)
-      ABX_LAUNCH(packKnnResultsKernel, divUp(G, 128), 128, 0, s, (int)G, stride, r_counts.ptr, r_off.ptr, r_idx.ptr,
-                 r_dist.ptr, fwd_ids.ptr, s_idx.ptr, s_dist.ptr, s_ids.ptr);
-    ABX_TRY(got_idx.alloc((size_t)std::max<int64_t>(M, 1), s));
-    ABX_TRY(got_ids.alloc((size_t)std::max<int64_t>(M, 1), s));
-    ABX_TRY(got_dist.alloc((size_t)std::max<int64_t>(M, 1), s));
-    ExchangeColumn cols[3] = {{s_idx.ptr, got_idx.ptr, sizeof(int32_t)},
-                              {s_ids.ptr, got_ids.ptr, sizeof(int32_t)},
-                              {s_dist.ptr, got_dist.ptr, sizeof(float)}};
-    ABX_TRY(t->comm->allToAllV(cols, 3, back.send_off.data(), back.recv_off.data(), s));
-    trace.mark("back", s);
-    ABX_TRY(sortReceived(t, s, M, q, back, got_ids, got_idx.ptr, got_dist.ptr, rvals2, rdist));
-    trace.mark("sort_received", s);
-    // 5. final ranking (DistributedTreeNearest.hpp:178-233): the k smallest of local row + candidates
-    ABX_TRY(knnMerge(s, M, got_ids.ptr, rvals2.ptr, rdist.ptr, k, rows_p, rowsd_p));
-    trace.mark("merge", s);
+    ABX_CUDA_TRY(cudaMemcpyAsync(h_missing, missing.ptr, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    ABX_CUDA_TRY(cudaStreamSynchronize(s)); // blocking point 1
+    trace.mark("route_count+matrix", s);
+    maybe_short = *h_missing != 0;
+    ExchangePlan fwd;
+    fwd.fromMatrix(t->h_pin, R, t->rank);
+    if (fwd.global > 0)
+      ABX_TRY(knnExchangeRound(t, s, pts, q, k, nullptr, q, radius, fwd, counts, matrix, rows_p, rowsd_p, round_a, trace));
   }
+  else
+  {
+    // 1a. near-first order, number of near points to the host
+    int64_t nb = q;
+    ABX_TRY(row_found.alloc((size_t)std::max<int64_t>(q, 1), s));
+    if (split)
+    {
+      TempBuffer<unsigned> n_near_dev;
+      ABX_TRY(n_near_dev.alloc(1, s));
+      ABX_TRY(pointPermutationNearFirst(s, t->bottom, (float const *)pts, q, t->boxes_dev, R, t->rank, near, qperm,
+                                        n_near_dev.ptr));
+      uint32_t *h_near = t->h_pin + kPinnedScratchWords - 2;
+      ABX_CUDA_TRY(cudaMemcpyAsync(h_near, n_near_dev.ptr, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+      ABX_CUDA_TRY(cudaStreamSynchronize(s)); // blocking point 0 (a few hundred microseconds into the call)
+      nb = (int64_t)*h_near;
+    }
+    else if (q > 0 && t->bottom->n > 1)
+      ABX_TRY(predicatePermutation(s, t->bottom, ABX_PRED_POINT3F, pts, q, qperm));
+    int64_t const ni = q - nb;
+    trace.mark("near_first_order", s);
+    if (t->bottom->n == 0)
+    {
+      // nothing local: every row is padding until candidates arrive
+      unsigned long long const m = (unsigned long long)slots;
+      ABX_CUDA_TRY(cudaMemcpyAsync(missing.ptr, &m, sizeof(m), cudaMemcpyHostToDevice, s));
+    }
+    // 1b. the near points, then (without waiting) the interior ones
+    ABX_TRY(nearestQuery(s, t->bottom, (float const *)pts, nb, k, nullptr, qperm.ptr, nullptr, slots, row_found.ptr,
+                         (uint32_t *)rows_p, rowsd_p, missing.ptr, t->rank, /*pad_pairs=*/false));
+    ABX_TRY(padShortRows(s, nb, k, row_found.ptr, rows_p, rowsd_p, qperm.ptr));
+    ABX_CUDA_TRY(cudaEventRecord(t->ev[0], s));
+    trace.mark("near_knn", s);
+    ABX_TRY(nearestQuery(s, t->bottom, (float const *)pts, ni, k, nullptr, qperm.ptr + nb, nullptr, slots, row_found.ptr,
+                         (uint32_t *)rows_p, rowsd_p, missing.ptr, t->rank, /*pad_pairs=*/false));
+    ABX_TRY(padShortRows(s, ni, k, row_found.ptr, rows_p, rowsd_p, qperm.ptr + nb));
+    ABX_CUDA_TRY(cudaMemsetAsync(counts.ptr, 0, sizeof(uint32_t) * R, s));
+    ABX_TRY(routeLaunch(s, false, ABX_PRED_SPHERE3F, pts, ni, radius, k, t->boxes_dev, R, t->rank, counts.ptr, nullptr,
+                        nullptr, nullptr, qperm.ptr + nb));
+    trace.mark("interior_knn", s);
+    // 2a. the near points' exchange on the side stream (host waits are on that stream only)
+    {
+      ABX_CUDA_TRY(cudaStreamWaitEvent(x, t->ev[0], 0));
+      TempBuffer<uint32_t> counts_a, matrix_a;
+      ABX_TRY(counts_a.alloc(R, x));
+      ABX_TRY(matrix_a.alloc((size_t)R * R, x));
+      ABX_CUDA_TRY(cudaMemsetAsync(counts_a.ptr, 0, sizeof(uint32_t) * R, x));
+      ABX_TRY(routeLaunch(x, false, ABX_PRED_SPHERE3F, pts, nb, radius, k, t->boxes_dev, R, t->rank, counts_a.ptr,
+                          nullptr, nullptr, nullptr, qperm.ptr));
+      ABX_TRY(gatherCountMatrix(t, x, counts_a.ptr, matrix_a.ptr));
+      ABX_CUDA_TRY(cudaStreamSynchronize(x)); // blocking point 1 (side stream)
+      trace.mark("route_count+matrix", x);
+      ExchangePlan fwd;
+      fwd.fromMatrix(t->h_pin, R, t->rank);
+      if (fwd.global > 0)
+        ABX_TRY(knnExchangeRound(t, x, pts, q, k, qperm.ptr, nb, radius, fwd, counts_a, matrix_a, rows_p, rowsd_p, round_a,
+                                 trace));
+      ABX_CUDA_TRY(cudaEventRecord(t->ev[2], x));
+    }
+    // 2b. the interior points: normally none of them reaches another rank.  The communicator is used from one stream
+    // at a time: the caller's stream joins the side stream before its collective.
+    ABX_CUDA_TRY(cudaStreamWaitEvent(s, t->ev[2], 0));
+    ABX_TRY(gatherCountMatrix(t, s, counts.ptr, matrix.ptr));
+    ABX_CUDA_TRY(cudaMemcpyAsync(h_missing, missing.ptr, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    ABX_CUDA_TRY(cudaStreamSynchronize(s)); // blocking point 2
+    trace.mark("interior_route+matrix", s);
+    maybe_short = *h_missing != 0;
+    ExchangePlan fwd;
+    fwd.fromMatrix(t->h_pin, R, t->rank);
+    if (fwd.global > 0)
+      ABX_TRY(knnExchangeRound(t, s, pts, q, k, qperm.ptr + nb, ni, radius, fwd, counts, matrix, rows_p, rowsd_p, round_b,
+                               trace));
+  }
+  // buffers taken under the side stream go back to it when this frame unwinds: not before the work on s that reads
+  // them (this guard is declared after them, so it runs first)
+  struct Rejoin
+  {
+    abx_dist_tree *t;
+    cudaStream_t s, x;
+    bool on;
+    ~Rejoin()
+    {
+      if (on && cudaEventRecord(t->ev[0], s) == cudaSuccess)
+        cudaStreamWaitEvent(x, t->ev[0], 0);
+    }
+  } rejoin{t, s, x, two_stage};
+  int64_t const M = round_a.M + round_b.M;
   // 6. outputs.  Rows are full (k entries) unless some local row was short and stayed short.
   TempBuffer<int32_t> row_counts, row_off;
   int64_t nnz = slots;
@@ -1174,8 +1310,10 @@ abx_status distNearest(abx_dist_tree *t, cudaStream_t s, void const *pts, int64_
     ABX_TRY(pos.alloc((size_t)M, s));
     ABX_TRY(rk.alloc((size_t)M, s));
     ABX_CUDA_TRY(cudaMemsetAsync(counter.ptr, 0, sizeof(unsigned), s));
-    ABX_LAUNCH(listRemoteInRowsKernel, divUp(M, 256), 256, 0, s, M, got_ids.ptr, k, (int2 const *)rows_p,
-               short_rows ? row_off.ptr : (int32_t const *)nullptr, t->rank, counter.ptr, pos.ptr, rk.ptr);
+    for (KnnRound const *r : {&round_a, &round_b})
+      if (r->M > 0)
+        ABX_LAUNCH(listRemoteInRowsKernel, divUp(r->M, 256), 256, 0, s, r->M, r->got_ids.ptr, k, (int2 const *)rows_p,
+                   short_rows ? row_off.ptr : (int32_t const *)nullptr, t->rank, counter.ptr, pos.ptr, rk.ptr);
     unsigned h_count = 0;
     ABX_CUDA_TRY(cudaMemcpyAsync(&h_count, counter.ptr, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
     ABX_CUDA_TRY(cudaStreamSynchronize(s));

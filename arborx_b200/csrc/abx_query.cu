@@ -518,11 +518,12 @@ __global__ void __launch_bounds__(kThreads, (K > 0 && K <= 16) ? ABX_NEAREST_MIN
 // padded with (-1, -1) / +inf so that candidates from other ranks can be merged in place.  Kept out of the
 // traversal kernel: short rows are rare (fewer than k reachable leaves) and the walk should not carry the code.
 __global__ void padShortRowsKernel(int64_t q, int k, int32_t const *__restrict__ counts, int2 *__restrict__ vals2,
-                                   float *__restrict__ dist)
+                                   float *__restrict__ dist, uint32_t const *__restrict__ ids)
 {
-  int64_t const i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= q)
+  int64_t const t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= q)
     return;
+  int64_t const i = ids ? (int64_t)ids[t] : t;
   for (int j = counts[i]; j < k; ++j)
   {
     vals2[i * k + j] = make_int2(-1, -1);
@@ -912,6 +913,73 @@ abx_status predicatePermutation(cudaStream_t s, abx_bvh *t, int pred_kind, void 
   return ABX_OK;
 }
 
+// DistributedTree's two-stage kNN: bit 30 of the sort key is set for points farther than `near` from every other
+// rank's box, so the permutation lists the points that may need other ranks first (Morton order inside both groups)
+__global__ void __launch_bounds__(256)
+    markFarPointsKernel(float const *__restrict__ pts, int64_t q, float const *__restrict__ boxes6, int R, int self_rank,
+                        float near2, unsigned *__restrict__ codes, unsigned *__restrict__ n_near)
+{
+  __shared__ float sbox[64 * 6];
+  __shared__ unsigned scount;
+  for (int i = threadIdx.x; i < R * 6; i += blockDim.x)
+    sbox[i] = boxes6[i];
+  if (threadIdx.x == 0)
+    scount = 0;
+  __syncthreads();
+  int64_t const i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool is_near = false;
+  if (i < q)
+  {
+    float const c[3] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+    for (int rk = 0; rk < R && !is_near; ++rk)
+    {
+      if (rk == self_rank)
+        continue;
+      float const *b = sbox + 6 * rk;
+      if (b[0] > b[3] || b[1] > b[4] || b[2] > b[5])
+        continue;
+      float d2 = 0.f;
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+      {
+        float const p = fminf(fmaxf(c[d], b[d]), b[3 + d]) - c[d];
+        d2 += p * p;
+      }
+      is_near = !(d2 > near2); // NaN coordinates count as near
+    }
+    if (!is_near)
+      codes[i] |= 1u << 30;
+  }
+  unsigned const m = __ballot_sync(0xffffffffu, is_near);
+  if ((threadIdx.x & 31) == 0 && m)
+    atomicAdd(&scount, (unsigned)__popc(m));
+  __syncthreads();
+  if (threadIdx.x == 0 && scount)
+    atomicAdd(n_near, scount);
+}
+
+abx_status pointPermutationNearFirst(cudaStream_t s, abx_bvh *t, float const *pts, int64_t q, float const *boxes6, int R,
+                                     int self_rank, float near, TempBuffer<uint32_t> &perm, unsigned *n_near_dev)
+{
+  TempBuffer<uint32_t> codes, codes_alt, perm_alt;
+  ABX_TRY(codes.alloc(q, s));
+  ABX_TRY(codes_alt.alloc(q, s));
+  ABX_TRY(perm.alloc(q, s));
+  ABX_TRY(perm_alt.alloc(q, s));
+  ABX_TRY(morton32(s, ABX_PRED_POINT3F, pts, q, t->bounds_dev, codes.ptr));
+  ABX_CUDA_TRY(cudaMemsetAsync(n_near_dev, 0, sizeof(unsigned), s));
+  ABX_LAUNCH(markFarPointsKernel, divUp(q, 256), 256, 0, s, pts, q, boxes6, R, self_rank, near * near, codes.ptr,
+             n_near_dev);
+  uint32_t *kb[2] = {codes.ptr, codes_alt.ptr};
+  uint32_t *vb[2] = {perm.ptr, perm_alt.ptr};
+  int cur = 0;
+  // 31-bit keys, ordered by the top kPredicateSortBits: the group bit and the leading Morton bits
+  ABX_TRY(sortPairsU32DB(s, kb, vb, &cur, q, true, 31, kPredicateSortBits));
+  if (cur != 0)
+    std::swap(perm.ptr, perm_alt.ptr);
+  return ABX_OK;
+}
+
 abx_status spatialCount(cudaStream_t s, abx_bvh *t, int pred_kind, void const *preds, int64_t q, uint32_t const *qperm,
                         int32_t limit, int32_t *counts)
 {
@@ -942,7 +1010,7 @@ abx_status spatialCompact(cudaStream_t s, abx_bvh *t, int pred_kind, void const 
 // offsets = CRS offsets of min(k_i, n).  total_rows = size of indices.
 abx_status nearestQuery(cudaStream_t s, abx_bvh *t, float const *pts, int64_t q, int32_t k, int32_t const *k_per_query,
                         uint32_t const *qperm, int32_t const *offsets, int64_t total_rows, int32_t *counts,
-                        uint32_t *indices, float *distances, unsigned long long *missing, int pair_rank)
+                        uint32_t *indices, float *distances, unsigned long long *missing, int pair_rank, bool pad_pairs)
 {
   if (q <= 0)
     return ABX_OK;
@@ -1015,8 +1083,17 @@ abx_status nearestQuery(cudaStream_t s, abx_bvh *t, float const *pts, int64_t q,
     ABX_NEAREST(0, scratch.ptr);
   }
 #undef ABX_NEAREST
-  if (pair_rank >= 0 && row_stride > 0)
-    ABX_LAUNCH(padShortRowsKernel, divUp(q, 256), 256, 0, s, q, row_stride, counts, (int2 *)indices, distances);
+  if (pair_rank >= 0 && row_stride > 0 && pad_pairs)
+    ABX_LAUNCH(padShortRowsKernel, divUp(q, 256), 256, 0, s, q, row_stride, counts, (int2 *)indices, distances,
+               (uint32_t const *)nullptr);
+  return ABX_OK;
+}
+
+abx_status padShortRows(cudaStream_t s, int64_t rows, int k, int32_t const *counts, int32_t *vals2, float *dist,
+                        uint32_t const *ids)
+{
+  if (rows > 0 && k > 0)
+    ABX_LAUNCH(padShortRowsKernel, divUp(rows, 256), 256, 0, s, rows, k, counts, (int2 *)vals2, dist, ids);
   return ABX_OK;
 }
 
@@ -1131,7 +1208,7 @@ __global__ void __launch_bounds__(256)
     routeKernel(float const *__restrict__ preds, int64_t q, float const *__restrict__ radius, int64_t radius_stride,
                 float const *__restrict__ boxes6, int R, int self_rank, unsigned *__restrict__ counts /*[R]*/,
                 unsigned const *__restrict__ base /*[R]*/, unsigned *__restrict__ cursors /*[R]*/,
-                int32_t *__restrict__ out_qid)
+                int32_t *__restrict__ out_qid, uint32_t const *__restrict__ ids /* q predicates to visit, or null */)
 {
   __shared__ float sbox[64 * 6];
   __shared__ unsigned scount[64];
@@ -1140,9 +1217,10 @@ __global__ void __launch_bounds__(256)
   if (threadIdx.x < 64)
     scount[threadIdx.x] = 0;
   __syncthreads();
-  int64_t const i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < q)
+  int64_t const slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot < q)
   {
+    int64_t const i = ids ? (int64_t)ids[slot] : slot;
     float c[3], r2 = 0.f, hi3[3];
     if (PRED == ABX_PRED_SPHERE3F)
     {
@@ -1203,7 +1281,7 @@ __global__ void __launch_bounds__(256)
 
 abx_status routeLaunch(cudaStream_t s, bool fill, int pred_kind, void const *preds, int64_t q, float const *radius,
                        int64_t radius_stride, float const *boxes6, int R, int self_rank, unsigned *counts,
-                       unsigned const *base, unsigned *cursors, int32_t *out_qid)
+                       unsigned const *base, unsigned *cursors, int32_t *out_qid, uint32_t const *ids)
 {
   if (R > 64)
   {
@@ -1218,10 +1296,10 @@ abx_status routeLaunch(cudaStream_t s, bool fill, int pred_kind, void const *pre
   {                                                                                                                    \
     if (fill)                                                                                                          \
       ABX_LAUNCH_TAGGED("routeKernel<fill>", (routeKernel<P, true>), grid, 256, 0, s, (float const *)preds, q, radius, \
-                        radius_stride, boxes6, R, self_rank, counts, base, cursors, out_qid);                          \
+                        radius_stride, boxes6, R, self_rank, counts, base, cursors, out_qid, ids);                     \
     else                                                                                                               \
       ABX_LAUNCH_TAGGED("routeKernel<count>", (routeKernel<P, false>), grid, 256, 0, s, (float const *)preds, q,       \
-                        radius, radius_stride, boxes6, R, self_rank, counts, base, cursors, out_qid);                  \
+                        radius, radius_stride, boxes6, R, self_rank, counts, base, cursors, out_qid, ids);             \
   } while (0)
   switch (pred_kind)
   {

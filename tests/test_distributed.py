@@ -3,6 +3,7 @@ engine) and, with -m gpu, the C++ DistributedTree of libabx.so: over a one-rank 
 (host threads) on one GPU over the in-process communicator; across GPUs via torchrun in scripts/dist_check.py."""
 import os
 
+import numpy as np
 import pytest
 import torch
 import torch.distributed as dist
@@ -81,6 +82,94 @@ def test_distributed_native_local_ranks(world):
             with torch.cuda.stream(space.stream):
                 make_tree = lambda v, kind=None: DistributedTree(comms[r], space, v, kind)
                 run_cases(r, world, make_tree, torch.device("cuda", 0), space, check_host=True)
+        except BaseException:
+            import traceback
+            errors[r] = traceback.format_exc()
+
+    threads = [threading.Thread(target=worker, args=(r,), daemon=True) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not any(t.is_alive() for t in threads), "a rank is stuck in a collective: %s" % errors
+    for r, e in enumerate(errors):
+        assert e is None, "rank %d:\n%s" % (r, e)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,layout", [(2, "slabs"), (4, "blocks"), (3, "lopsided")])
+def test_distributed_native_two_stage_knn(world, layout):
+    """kNN with enough points per rank for the two-stage form (abx_dist.cu: the points near another rank's box go
+    first, their exchange runs under the interior points' traversal; interior points that do reach another rank --
+    here: queries far outside every block -- take a second exchange).  Every rank's rows must be the rows of ONE
+    tree over all points: same distances bit for bit, and every (index, rank) pair names a point at that distance."""
+    import threading
+
+    import arborx_b200 as abx
+    from arborx_b200.distributed import Communicator, DistributedTree
+    from tests import clouds
+    n_per, q_per, k = 300_000, 280_000, 7
+    rng = np.random.default_rng(1234)
+    pts, qs = [], []
+    for r in range(world):
+        p = clouds.filled_box(0xABC0 + r, n_per).astype(np.float32)
+        a = float(np.cbrt(n_per))
+        p = p / a * 0.5 + 0.5  # unit cube
+        if layout == "slabs":
+            off = np.array([r, 0, 0], np.float32)
+        elif layout == "blocks":
+            off = np.array([r % 2, r // 2, 0], np.float32)
+        else:
+            off = np.array([r, 0, 0], np.float32)
+            if r == 1:
+                p = p[:5]  # fewer than k points on this rank, and no split there
+        p = p + off
+        qq = rng.random((q_per, 3), dtype=np.float32) + off
+        qq[:2000] = rng.random((2000, 3), dtype=np.float32) * 40 - 20  # far outside: interior by the guess, remote by k-th distance
+        m = min(100, len(p))
+        qq[2000:2000 + m] = p[:m]
+        pts.append(np.ascontiguousarray(p))
+        qs.append(np.ascontiguousarray(qq))
+    all_pts = np.concatenate(pts)
+    starts = np.cumsum([0] + [len(p) for p in pts])
+    space0 = abx.ExecutionSpace()
+    whole = abx.BoundingVolumeHierarchy(space0, torch.from_numpy(all_pts).cuda())
+    expected = []
+    for r in range(world):
+        idx, off, d = whole.query(space0, abx.nearest(torch.from_numpy(qs[r]).cuda(), k), return_distances=True)
+        expected.append(d.view(-1, k).cpu().numpy())
+    comms = Communicator.local_group(world)
+    errors = [None] * world
+
+    def worker(r):
+        try:
+            torch.cuda.set_device(0)
+            space = abx.ExecutionSpace(torch.cuda.Stream())
+            with torch.cuda.stream(space.stream):
+                tree = DistributedTree(comms[r], space, torch.from_numpy(pts[r]).cuda())
+                for rep in range(2):
+                    vals, off, d = tree.query(space, abx.nearest(torch.from_numpy(qs[r]).cuda(), k),
+                                              return_distances=True)
+                    space.fence()
+                    off = off.cpu().numpy()
+                    assert np.array_equal(off, np.arange(q_per + 1) * k)
+                    d = d.view(-1, k).cpu().numpy()
+                    assert np.array_equal(d, expected[r]), "rank %d rep %d: distances differ" % (r, rep)
+                    v = vals.cpu().numpy().reshape(-1, k, 2)
+                    g = starts[v[..., 1]] + v[..., 0]
+                    assert (v[..., 1] >= 0).all() and (v[..., 1] < world).all()
+                    diff = all_pts[g] - qs[r][:, None, :]
+                    dd = np.sqrt((diff[..., 0] * diff[..., 0] + diff[..., 1] * diff[..., 1]).astype(np.float32)
+                                 + diff[..., 2] * diff[..., 2]).astype(np.float32)
+                    assert np.array_equal(dd, d), "rank %d: a pair does not name a point at its distance" % r
+                    assert all(len(set(row)) == k for row in g[:5000].tolist())
+                # host form (compact results)
+                hv, hoff, hd, rpos, rrank = tree.query(space, abx.nearest(torch.from_numpy(qs[r]), k),
+                                                       return_distances=True)
+                assert np.array_equal(hd.view(-1, k).numpy(), expected[r])
+                owner = np.full(hv.numel(), r, np.int64)
+                owner[rpos.numpy()] = rrank.numpy()
+                assert np.array_equal(starts[owner] + hv.numpy(), g.reshape(-1))
         except BaseException:
             import traceback
             errors[r] = traceback.format_exc()
