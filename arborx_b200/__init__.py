@@ -22,6 +22,7 @@ _PRED_STRIDE = {SPHERE_PRED: 4, BOX_PRED: 6, POINT_PRED: 3, RAY_PRED: 6}
 
 __all__ = ["ExecutionSpace", "BoundingVolumeHierarchy", "BVH", "TraversalPolicy", "HostBufferPool", "BruteForce", "intersects", "nearest",
            "make_intersects", "make_nearest", "query", "dbscan", "DBSCANParameters", "SearchException",
+           "MinimumSpanningTree", "Dendrogram", "hdbscan",
            "POINT", "BOX", "TRIANGLE", "launch_count"]
 
 
@@ -459,6 +460,69 @@ def dbscan(space, primitives, eps, core_min_size, parameters=None):
             _lib.check(L.abx_dbscan_host(space.handle, C.c_void_p(x.data_ptr()), n, float(eps), int(core_min_size),
                                          p._implementation, p._algorithm, C.c_void_p(labels.data_ptr())))
     return labels
+
+
+class MinimumSpanningTree:
+    """ArborX::Experimental::MinimumSpanningTree(space, points, k = 1) (cluster/ArborX_MinimumSpanningTree.hpp:
+    31-101): `.edges` int32 [n - 1, 2] (source, target) in the caller's indices and `.weights` float32 [n - 1] --
+    Euclidean for k = 1, mutual reachability for k > 1.  Device points give device results, host points pinned
+    host results.  The order of the edges is unspecified (sort before comparing, as the reference's tests do)."""
+
+    def __init__(self, space, points, k=1):
+        x = _as_f32(points, 3)
+        n = x.shape[0]
+        m = max(n - 1, 0)
+        it = C.c_int32(0)
+        L = lib()
+        with torch.cuda.stream(space.stream):
+            if x.is_cuda:
+                self.edges = torch.empty((m, 2), dtype=torch.int32, device=space.device)
+                self.weights = torch.empty(m, dtype=torch.float32, device=space.device)
+                fn = L.abx_mst_points3f
+            else:
+                self.edges = torch.empty((m, 2), dtype=torch.int32, pin_memory=m > 0)
+                self.weights = torch.empty(m, dtype=torch.float32, pin_memory=m > 0)
+                fn = L.abx_mst_points3f_host
+            _lib.check(fn(space.handle, C.c_void_p(x.data_ptr()), n, int(k), C.c_void_p(self.edges.data_ptr()),
+                          C.c_void_p(self.weights.data_ptr()), C.byref(it)))
+        self.iterations = int(it.value)
+
+
+class Dendrogram:
+    """ArborX::Experimental::Dendrogram(space, edges) with DendrogramImplementation::UNION_FIND
+    (cluster/ArborX_Dendrogram.hpp:31-76): `_parents` int32 [2 e + 1] (edges in ascending weight order, then the
+    vertices; root -> -1) and `_parent_heights` float32 [e]."""
+
+    def __init__(self, space, edges, weights):
+        e = edges.to(torch.int32).contiguous().view(-1, 2)
+        w = weights.to(torch.float32).contiguous().view(-1)
+        assert e.is_cuda and w.is_cuda and e.shape[0] == w.shape[0]
+        m = e.shape[0]
+        self._parents = torch.empty(2 * m + 1, dtype=torch.int32, device=space.device)
+        self._parent_heights = torch.empty(m, dtype=torch.float32, device=space.device)
+        with torch.cuda.stream(space.stream):
+            _lib.check(lib().abx_dendrogram_union_find(space.handle, C.c_void_p(e.data_ptr()), C.c_void_p(w.data_ptr()),
+                                                       m, C.c_void_p(self._parents.data_ptr()),
+                                                       C.c_void_p(self._parent_heights.data_ptr())))
+
+
+def hdbscan(space, primitives, core_min_size):
+    """ArborX::Experimental::hdbscan(space, primitives, core_min_size, DendrogramImplementation::UNION_FIND)
+    (cluster/ArborX_HDBSCAN.hpp:29-53) -> Dendrogram-like object with `_parents`, `_parent_heights`."""
+    x = _as_f32(primitives, 3)
+    assert x.is_cuda
+    n = x.shape[0]
+
+    class _D:
+        pass
+    d = _D()
+    d._parents = torch.empty(2 * n - 1, dtype=torch.int32, device=space.device)
+    d._parent_heights = torch.empty(max(n - 1, 0), dtype=torch.float32, device=space.device)
+    with torch.cuda.stream(space.stream):
+        _lib.check(lib().abx_hdbscan_points3f(space.handle, C.c_void_p(x.data_ptr()), n, int(core_min_size),
+                                              C.c_void_p(d._parents.data_ptr()),
+                                              C.c_void_p(d._parent_heights.data_ptr())))
+    return d
 
 
 def launch_count():

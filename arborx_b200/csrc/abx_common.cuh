@@ -367,7 +367,7 @@ abx_status predicatePermutation(cudaStream_t s, abx_bvh *bvh, int pred_kind, voi
 // *n_near_dev receives their number
 abx_status pointPermutationNearFirst(cudaStream_t s, abx_bvh *bvh, float const *pts, int64_t q, float const *boxes6,
                                      int R, int self_rank, float near, TempBuffer<uint32_t> &perm,
-                                     unsigned *n_near_dev);
+                                     unsigned long long *n_near_dev);
 abx_status spatialCount(cudaStream_t s, abx_bvh *bvh, int pred_kind, void const *preds, int64_t q,
                         uint32_t const *qperm, int32_t limit, int32_t *counts);
 abx_status spatialFill(cudaStream_t s, abx_bvh *bvh, int pred_kind, void const *preds, int64_t q,
@@ -446,4 +446,9 @@ abx_status ensureDevice();
 // core_flags (optional): 1 for core points (all points when minpts == 2)
 abx_status dbscan(cudaStream_t s, float const *xyz, int64_t n, float eps, int32_t minpts, int impl, int algo,
                   int32_t *labels, int32_t *core_flags = nullptr);
+// mst.cu
+abx_status minimumSpanningTree(cudaStream_t s, float const *xyz, int64_t n, int32_t k, int32_t *edges2, float *weights,
+                               int *iterations);
+abx_status dendrogramUnionFind(cudaStream_t s, int32_t const *edges2, float const *weights, int64_t m, int32_t *parents,
+                               float *heights);
 } // namespace abx

@@ -1110,7 +1110,12 @@ abx_status distNearest(abx_dist_tree *t, cudaStream_t s, void const *pts, int64_
     if (vol > 0 && std::isfinite(vol))
       near = (float)(1.5 * std::cbrt((double)k * vol / (double)t->bottom->n));
   }
-  bool const two_stage = R > 1;
+  // Measured on 2 and 8 B200s (10M points + 10M queries per rank, profiles/r02_knn_two_stage_experiment.log) and NOT
+  // the default: the near launch and the exchange do disappear behind the interior launch, but that launch runs
+  // 11.3-11.7 ms instead of 10.85 next to them, and the split itself costs 0.2 ms: kNN phase 12.5 ms against 12.1 ms
+  // (N = 2), 12.9 against 12.7 (N = 8).  Kept behind the tuning library's ABX_KNN_TWO_STAGE=1 (every rank must agree:
+  // the two forms issue different collectives); the release library always takes the single exchange below.
+  bool const two_stage = R > 1 && ABX_TUNE_INT("ABX_KNN_TWO_STAGE", 0) != 0;
   bool const split = near > 0.f && std::isfinite(near);
   TempBuffer<uint32_t> qperm;
   TempBuffer<int32_t> row_found;
@@ -1143,12 +1148,12 @@ abx_status distNearest(abx_dist_tree *t, cudaStream_t s, void const *pts, int64_
     ABX_TRY(row_found.alloc((size_t)std::max<int64_t>(q, 1), s));
     if (split)
     {
-      TempBuffer<unsigned> n_near_dev;
+      TempBuffer<unsigned long long> n_near_dev;
       ABX_TRY(n_near_dev.alloc(1, s));
       ABX_TRY(pointPermutationNearFirst(s, t->bottom, (float const *)pts, q, t->boxes_dev, R, t->rank, near, qperm,
                                         n_near_dev.ptr));
-      uint32_t *h_near = t->h_pin + kPinnedScratchWords - 2;
-      ABX_CUDA_TRY(cudaMemcpyAsync(h_near, n_near_dev.ptr, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+      unsigned long long *h_near = reinterpret_cast<unsigned long long *>(t->h_pin + kPinnedScratchWords - 2);
+      ABX_CUDA_TRY(cudaMemcpyAsync(h_near, n_near_dev.ptr, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
       ABX_CUDA_TRY(cudaStreamSynchronize(s)); // blocking point 0 (a few hundred microseconds into the call)
       nb = (int64_t)*h_near;
     }
@@ -1162,12 +1167,14 @@ abx_status distNearest(abx_dist_tree *t, cudaStream_t s, void const *pts, int64_
       unsigned long long const m = (unsigned long long)slots;
       ABX_CUDA_TRY(cudaMemcpyAsync(missing.ptr, &m, sizeof(m), cudaMemcpyHostToDevice, s));
     }
-    // 1b. the near points, then (without waiting) the interior ones
-    ABX_TRY(nearestQuery(s, t->bottom, (float const *)pts, nb, k, nullptr, qperm.ptr, nullptr, slots, row_found.ptr,
-                         (uint32_t *)rows_p, rowsd_p, missing.ptr, t->rank, /*pad_pairs=*/false));
-    ABX_TRY(padShortRows(s, nb, k, row_found.ptr, rows_p, rowsd_p, qperm.ptr));
+    // 1b. the near points on the (high-priority) side stream, the interior ones on the caller's stream, at the
+    // same time: the short near launch does not leave the device idle while its last warps finish
     ABX_CUDA_TRY(cudaEventRecord(t->ev[0], s));
-    trace.mark("near_knn", s);
+    ABX_CUDA_TRY(cudaStreamWaitEvent(x, t->ev[0], 0));
+    ABX_TRY(nearestQuery(x, t->bottom, (float const *)pts, nb, k, nullptr, qperm.ptr, nullptr, slots, row_found.ptr,
+                         (uint32_t *)rows_p, rowsd_p, missing.ptr, t->rank, /*pad_pairs=*/false));
+    ABX_TRY(padShortRows(x, nb, k, row_found.ptr, rows_p, rowsd_p, qperm.ptr));
+    trace.mark("near_knn", x);
     ABX_TRY(nearestQuery(s, t->bottom, (float const *)pts, ni, k, nullptr, qperm.ptr + nb, nullptr, slots, row_found.ptr,
                          (uint32_t *)rows_p, rowsd_p, missing.ptr, t->rank, /*pad_pairs=*/false));
     ABX_TRY(padShortRows(s, ni, k, row_found.ptr, rows_p, rowsd_p, qperm.ptr + nb));
@@ -1177,7 +1184,6 @@ abx_status distNearest(abx_dist_tree *t, cudaStream_t s, void const *pts, int64_
     trace.mark("interior_knn", s);
     // 2a. the near points' exchange on the side stream (host waits are on that stream only)
     {
-      ABX_CUDA_TRY(cudaStreamWaitEvent(x, t->ev[0], 0));
       TempBuffer<uint32_t> counts_a, matrix_a;
       ABX_TRY(counts_a.alloc(R, x));
       ABX_TRY(matrix_a.alloc((size_t)R * R, x));

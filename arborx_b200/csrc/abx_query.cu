@@ -913,70 +913,68 @@ abx_status predicatePermutation(cudaStream_t s, abx_bvh *t, int pred_kind, void 
   return ABX_OK;
 }
 
-// DistributedTree's two-stage kNN: bit 30 of the sort key is set for points farther than `near` from every other
-// rank's box, so the permutation lists the points that may need other ranks first (Morton order inside both groups)
+// DistributedTree's two-stage kNN: the Morton-ordered permutation is split (stably) into the points within `near`
+// of another rank's box and the rest, so both groups keep the order that makes neighbouring threads walk
+// neighbouring subtrees.
 __global__ void __launch_bounds__(256)
-    markFarPointsKernel(float const *__restrict__ pts, int64_t q, float const *__restrict__ boxes6, int R, int self_rank,
-                        float near2, unsigned *__restrict__ codes, unsigned *__restrict__ n_near)
+    nearFlagsKernel(float const *__restrict__ pts, uint32_t const *__restrict__ perm, int64_t q,
+                    float const *__restrict__ boxes6, int R, int self_rank, float near2, int32_t *__restrict__ flags)
 {
   __shared__ float sbox[64 * 6];
-  __shared__ unsigned scount;
   for (int i = threadIdx.x; i < R * 6; i += blockDim.x)
     sbox[i] = boxes6[i];
-  if (threadIdx.x == 0)
-    scount = 0;
   __syncthreads();
-  int64_t const i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t const t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= q)
+    return;
+  int64_t const i = perm ? (int64_t)perm[t] : t;
+  float const c[3] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
   bool is_near = false;
-  if (i < q)
+  for (int rk = 0; rk < R && !is_near; ++rk)
   {
-    float const c[3] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
-    for (int rk = 0; rk < R && !is_near; ++rk)
-    {
-      if (rk == self_rank)
-        continue;
-      float const *b = sbox + 6 * rk;
-      if (b[0] > b[3] || b[1] > b[4] || b[2] > b[5])
-        continue;
-      float d2 = 0.f;
+    if (rk == self_rank)
+      continue;
+    float const *b = sbox + 6 * rk;
+    if (b[0] > b[3] || b[1] > b[4] || b[2] > b[5])
+      continue;
+    float d2 = 0.f;
 #pragma unroll
-      for (int d = 0; d < 3; ++d)
-      {
-        float const p = fminf(fmaxf(c[d], b[d]), b[3 + d]) - c[d];
-        d2 += p * p;
-      }
-      is_near = !(d2 > near2); // NaN coordinates count as near
+    for (int d = 0; d < 3; ++d)
+    {
+      float const p = fminf(fmaxf(c[d], b[d]), b[3 + d]) - c[d];
+      d2 += p * p;
     }
-    if (!is_near)
-      codes[i] |= 1u << 30;
+    is_near = !(d2 > near2); // NaN coordinates count as near
   }
-  unsigned const m = __ballot_sync(0xffffffffu, is_near);
-  if ((threadIdx.x & 31) == 0 && m)
-    atomicAdd(&scount, (unsigned)__popc(m));
-  __syncthreads();
-  if (threadIdx.x == 0 && scount)
-    atomicAdd(n_near, scount);
+  flags[t] = is_near ? 1 : 0;
+}
+__global__ void splitByFlagKernel(uint32_t const *__restrict__ perm, int64_t q, int32_t const *__restrict__ flags,
+                                  int32_t const *__restrict__ pos /* exclusive scan of flags, q + 1 */,
+                                  uint32_t *__restrict__ out)
+{
+  int64_t const t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= q)
+    return;
+  uint32_t const v = perm ? perm[t] : (uint32_t)t;
+  int32_t const before = pos[t];
+  int64_t const dst = flags[t] ? (int64_t)before : (int64_t)pos[q] + (t - before);
+  out[dst] = v;
 }
 
 abx_status pointPermutationNearFirst(cudaStream_t s, abx_bvh *t, float const *pts, int64_t q, float const *boxes6, int R,
-                                     int self_rank, float near, TempBuffer<uint32_t> &perm, unsigned *n_near_dev)
+                                     int self_rank, float near, TempBuffer<uint32_t> &perm,
+                                     unsigned long long *n_near_dev)
 {
-  TempBuffer<uint32_t> codes, codes_alt, perm_alt;
-  ABX_TRY(codes.alloc(q, s));
-  ABX_TRY(codes_alt.alloc(q, s));
-  ABX_TRY(perm.alloc(q, s));
-  ABX_TRY(perm_alt.alloc(q, s));
-  ABX_TRY(morton32(s, ABX_PRED_POINT3F, pts, q, t->bounds_dev, codes.ptr));
-  ABX_CUDA_TRY(cudaMemsetAsync(n_near_dev, 0, sizeof(unsigned), s));
-  ABX_LAUNCH(markFarPointsKernel, divUp(q, 256), 256, 0, s, pts, q, boxes6, R, self_rank, near * near, codes.ptr,
-             n_near_dev);
-  uint32_t *kb[2] = {codes.ptr, codes_alt.ptr};
-  uint32_t *vb[2] = {perm.ptr, perm_alt.ptr};
-  int cur = 0;
-  // 31-bit keys, ordered by the top kPredicateSortBits: the group bit and the leading Morton bits
-  ABX_TRY(sortPairsU32DB(s, kb, vb, &cur, q, true, 31, kPredicateSortBits));
-  if (cur != 0)
-    std::swap(perm.ptr, perm_alt.ptr);
+  TempBuffer<uint32_t> sorted;
+  if (t->n > 1)
+    ABX_TRY(predicatePermutation(s, t, ABX_PRED_POINT3F, pts, q, sorted));
+  TempBuffer<int32_t> flags, pos;
+  ABX_TRY(flags.alloc((size_t)q + 1, s));
+  ABX_TRY(pos.alloc((size_t)q + 1, s));
+  ABX_TRY(perm.alloc((size_t)q, s));
+  ABX_LAUNCH(nearFlagsKernel, divUp(q, 256), 256, 0, s, pts, sorted.ptr, q, boxes6, R, self_rank, near * near, flags.ptr);
+  ABX_TRY(exclusiveScanI32(s, flags.ptr, pos.ptr, q + 1, n_near_dev));
+  ABX_LAUNCH(splitByFlagKernel, divUp(q, 256), 256, 0, s, sorted.ptr, q, flags.ptr, pos.ptr, perm.ptr);
   return ABX_OK;
 }
 

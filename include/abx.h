@@ -214,6 +214,29 @@ ABX_API abx_status abx_dbscan(void *stream, const float *xyz_dev, int64_t n, flo
 ABX_API abx_status abx_dbscan_host(void *stream, const float *xyz_host, int64_t n, float eps, int32_t minpts,
                            int implementation, int algorithm, int32_t *labels_host);
 
+/* ---- ArborX::Experimental::MinimumSpanningTree / Dendrogram / hdbscan ----
+ * cluster/ArborX_MinimumSpanningTree.hpp:46-101: Boruvka over the BVH.  k = 1: Euclidean distances; k > 1: mutual
+ * reachability max(core_i, core_j, d) with core_i = distance to the k-th nearest point, i itself included (:70-88,
+ * detail/ArborX_MutualReachabilityDistance.hpp:27-77).  edges2_dev: (n - 1) x (source, target) in the caller's
+ * indices, weights_dev: n - 1.  Equal weights are ordered by the pair of leaf positions like the reference's
+ * DirectedEdge (detail/ArborX_BoruvkaHelpers.hpp:37-105), which makes the tree unique: the edge SET equals the
+ * reference's, the order of the edges in the array is unspecified (as there).  n < 2: nothing is written.
+ * iterations (optional): number of Boruvka rounds.  Blocks once per round (:196-198). */
+ABX_API abx_status abx_mst_points3f(void *stream, const float *xyz_dev, int64_t n, int32_t k, int32_t *edges2_dev,
+                                    float *weights_dev, int32_t *iterations);
+ABX_API abx_status abx_mst_points3f_host(void *stream, const float *xyz_host, int64_t n, int32_t k,
+                                         int32_t *edges2_host, float *weights_host, int32_t *iterations);
+/* cluster/ArborX_Dendrogram.hpp:47-76 (DendrogramImplementation::UNION_FIND): the edges are sorted by weight on the
+ * device; the union-find pass over them is sequential and runs on the host, as it does in the reference
+ * (detail/ArborX_DendrogramHelpers.hpp:31-80).  parents_dev: 2 * num_edges + 1 entries -- the edges in ascending
+ * weight order first, then the num_edges + 1 vertices; the root's parent is -1.  parent_heights_dev: num_edges
+ * (the sorted weights).  The hybrid Boruvka dendrogram (DendrogramImplementation::BORUVKA) is not provided. */
+ABX_API abx_status abx_dendrogram_union_find(void *stream, const int32_t *edges2_dev, const float *weights_dev,
+                                             int64_t num_edges, int32_t *parents_dev, float *parent_heights_dev);
+/* cluster/ArborX_HDBSCAN.hpp:29-53 with DendrogramImplementation::UNION_FIND: MST(core_min_size) + dendrogram */
+ABX_API abx_status abx_hdbscan_points3f(void *stream, const float *xyz_dev, int64_t n, int32_t core_min_size,
+                                        int32_t *parents_dev, float *parent_heights_dev);
+
 /* ---- device view for user callbacks (include/ArborX_B200_Callbacks.cuh) ----
  * The reference instantiates user callbacks inside its traversal templates
  * (spatial/detail/ArborX_Callbacks.hpp:79-150, ArborX_TreeTraversal.hpp:97-119,180-335).  Here the tree's

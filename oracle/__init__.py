@@ -75,6 +75,8 @@ def lib():
         "orc_union_find_representative": (C.c_int, [ip, C.c_int]),
         "orc_dbscan": (C.c_int, [fp, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, ip, ip, llp]),
         "orc_dbscan_verify": (C.c_int, [fp, C.c_int, C.c_float, C.c_int, ip, C.c_int]),
+        "orc_mst": (C.c_int, [fp, C.c_int, C.c_int, ip, fp]),
+        "orc_dendrogram_union_find": (None, [ip, fp, C.c_int, ip, fp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -267,3 +269,26 @@ def dbscan_verify(xyz, eps, minpts, labels, algo=0):
     xyz = _f32(xyz).reshape(-1, 3)
     labels = np.ascontiguousarray(labels, dtype=np.int32)
     return lib().orc_dbscan_verify(_p(xyz, C.c_float), xyz.shape[0], C.c_float(eps), minpts, _p(labels, C.c_int), algo)
+
+
+def mst(xyz, k=1, return_iterations=False):
+    """Euclidean (k = 1) or mutual-reachability (k > 1) minimum spanning tree
+    (ArborX_MinimumSpanningTree.hpp:46-101) -> (edges int32 [n - 1, 2] in original indices, weights float32)."""
+    xyz = _f32(xyz).reshape(-1, 3)
+    n = xyz.shape[0]
+    edges = np.empty((max(n - 1, 0), 2), np.int32)
+    weights = np.empty(max(n - 1, 0), np.float32)
+    it = lib().orc_mst(_p(xyz, C.c_float), n, int(k), _p(edges, C.c_int), _p(weights, C.c_float))
+    return (edges, weights, it) if return_iterations else (edges, weights)
+
+
+def dendrogram(edges, weights):
+    """Dendrogram(space, edges), UNION_FIND (ArborX_Dendrogram.hpp:47-76) -> (parents [2 e + 1], parent_heights [e])."""
+    edges = np.ascontiguousarray(edges, dtype=np.int32).reshape(-1, 2)
+    weights = _f32(weights).reshape(-1)
+    e = edges.shape[0]
+    parents = np.full(2 * e + 1, -1, np.int32)
+    heights = np.empty(e, np.float32)
+    lib().orc_dendrogram_union_find(_p(edges, C.c_int), _p(weights, C.c_float), e, _p(parents, C.c_int),
+                                    _p(heights, C.c_float))
+    return parents, heights

@@ -2183,3 +2183,276 @@ ORC_API int orc_dbscan_verify(float const *xyz, int n, float eps, int minpts, in
     fail |= 16;
   return fail;
 }
+
+// ---------------------------------------------------------------------------
+// Euclidean / mutual-reachability minimum spanning tree (Boruvka over the BVH) and the dendrogram of its edges:
+// cluster/ArborX_MinimumSpanningTree.hpp:46-258 (MST mode), cluster/detail/ArborX_BoruvkaHelpers.hpp,
+// cluster/detail/ArborX_MutualReachabilityDistance.hpp, spatial/detail/ArborX_TreeNodeLabeling.hpp,
+// cluster/ArborX_Dendrogram.hpp:47-76 + cluster/detail/ArborX_DendrogramHelpers.hpp:31-80 (UNION_FIND).
+// ---------------------------------------------------------------------------
+namespace
+{
+// BoruvkaHelpers.hpp:37-105: (weight, unordered pair of leaf positions, direction flag)
+struct DirectedEdge
+{
+  unsigned long long key = ~0ull;
+  float weight = std::numeric_limits<float>::infinity();
+  DirectedEdge() = default;
+  DirectedEdge(int source, int target, float w) : weight(w)
+  {
+    unsigned long long const lo = (unsigned)std::min(source, target), hi = (unsigned)std::max(source, target);
+    key = (lo << 32) | (hi << 1) | (source < target ? 0ull : 1ull);
+  }
+  bool reverse() const { return key & 1ull; }
+  int lo() const { return (int)((key >> 32) & 0x7fffffffull); }
+  int hi() const { return (int)((key >> 1) & 0x7fffffffull); }
+  int source() const { return reverse() ? hi() : lo(); }
+  int target() const { return reverse() ? lo() : hi(); }
+  bool operator<(DirectedEdge const &o) const { return weight != o.weight ? weight < o.weight : key < o.key; }
+};
+} // namespace
+
+// edges2: (n - 1) x (source, target) in ORIGINAL indices; weights: n - 1.  k > 1: mutual reachability with core
+// distance = distance to the k-th nearest point, the point itself included (MinimumSpanningTree.hpp:70-88).
+// Returns the number of Boruvka iterations.
+ORC_API int orc_mst(float const *xyz, int n, int k, int *edges2, float *weights_out)
+{
+  if (n < 2)
+    return 0;
+  Tree t;
+  t.kind = PRIM_POINT;
+  t.n = n;
+  t.prims.assign(xyz, xyz + 3 * (size_t)n);
+  buildTree(t);
+  float const inf = std::numeric_limits<float>::infinity();
+  // core distances by original index (MaxDistance over nearest(point, k))
+  std::vector<float> core;
+  if (k > 1)
+  {
+    core.assign(n, 0.f);
+#pragma omp parallel
+    {
+      std::vector<int> stack;
+      std::vector<float> stack_d;
+      std::vector<PairID> buf(k);
+#pragma omp for schedule(dynamic, 256)
+      for (int pos = 0; pos < n; ++pos)
+      {
+        unsigned const o = t.perm[pos];
+        int const m = traverseNearest(t, t.point(o), k, buf.data(), stack, stack_d, nullptr);
+        float d = 0.f;
+        for (int j = 0; j < m; ++j)
+          d = std::max(d, buf[j].second);
+        core[o] = d;
+      }
+    }
+  }
+  auto metric = [&](unsigned oi, unsigned oj, float d) {
+    return k > 1 ? std::max(std::max(core[oi], core[oj]), d) : d;
+  };
+  // TreeNodeLabeling.hpp:27-42
+  std::vector<int> parents(2 * (size_t)n - 1, -1);
+  for (int i = n; i < 2 * n - 1; ++i)
+  {
+    int const l = t.left_child[i - n];
+    parents[l] = i;
+    parents[t.getRope(l)] = i;
+  }
+  std::vector<int> labels(2 * (size_t)n - 1);
+  for (int i = 0; i < n; ++i)
+    labels[i] = i;
+  std::vector<DirectedEdge> out_edges(n);
+  std::vector<float> comp_weight(n), radii(n);
+  int num_edges = 0, iterations = 0;
+  std::vector<int> e_src(n - 1), e_dst(n - 1);
+  do
+  {
+    ++iterations;
+    // reduceLabels (TreeNodeLabeling.hpp:44-93): an internal node carries a label iff its whole subtree does
+    for (int i = 2 * n - 2; i >= n; --i)
+      labels[i] = -2;
+    {
+      // children before parents: in this numbering a child's internal index is not ordered with its parent's, so
+      // walk up from the leaves like the reference does (second arriver continues)
+      for (int leaf = 0; leaf < n; ++leaf)
+      {
+        int i = leaf;
+        do
+        {
+          int const label = labels[i];
+          int const parent = parents[i];
+          int const parent_label = labels[parent];
+          if (parent_label == -2)
+          {
+            labels[parent] = label;
+            break;
+          }
+          if (parent_label != label)
+            labels[parent] = -1;
+          i = parent;
+        } while (i != n);
+      }
+    }
+    std::fill(out_edges.begin(), out_edges.end(), DirectedEdge());
+    std::fill(comp_weight.begin(), comp_weight.end(), inf);
+    std::fill(radii.begin(), radii.end(), inf);
+    // resetSharedRadii (BoruvkaHelpers.hpp:735-778): Morton neighbours in different components bound both
+    for (int i = 0; i + 1 < n; ++i)
+      if (labels[i] != labels[i + 1])
+      {
+        float const r = metric(t.perm[i], t.perm[i + 1], distance(t.point(t.perm[i]), t.point(t.perm[i + 1])));
+        radii[labels[i]] = std::min(radii[labels[i]], r);
+        radii[labels[i + 1]] = std::min(radii[labels[i + 1]], r);
+      }
+    // FindComponentNearestNeighbors (BoruvkaHelpers.hpp:160-312), private radius copy
+    std::vector<DirectedEdge> best(n);
+#pragma omp parallel
+    {
+      std::vector<int> stack;
+      std::vector<float> stack_d;
+#pragma omp for schedule(dynamic, 256)
+      for (int i = 0; i < n; ++i)
+      {
+        int const component = labels[i];
+        unsigned const oi = t.perm[i];
+        P3 const p = t.point(oi);
+        DirectedEdge current_best;
+        float radius = radii[component];
+        stack.assign(1, -1);
+        stack_d.assign(1, 0.f);
+        int node = n;
+        float distance_node = 0.f;
+        do
+        {
+          bool traverse_left = false, traverse_right = false;
+          int left_child = 0, right_child = 0;
+          float distance_left = inf, distance_right = inf;
+          if (distance_node <= radius)
+          {
+            left_child = t.left_child[node - n];
+            right_child = t.getRope(left_child);
+            distance_left = nearestDistance(t, p, left_child);
+            distance_right = nearestDistance(t, p, right_child);
+            if (labels[left_child] != component && distance_left <= radius)
+            {
+              if (t.isLeaf(left_child))
+              {
+                DirectedEdge const cand(i, left_child, metric(oi, t.perm[left_child], distance_left));
+                if (cand < current_best)
+                {
+                  current_best = cand;
+                  radius = cand.weight;
+                }
+              }
+              else
+                traverse_left = true;
+            }
+            if (labels[right_child] != component && distance_right <= radius)
+            {
+              if (t.isLeaf(right_child))
+              {
+                DirectedEdge const cand(i, right_child, metric(oi, t.perm[right_child], distance_right));
+                if (cand < current_best)
+                {
+                  current_best = cand;
+                  radius = cand.weight;
+                }
+              }
+              else
+                traverse_right = true;
+            }
+          }
+          if (!traverse_left && !traverse_right)
+          {
+            node = stack.back();
+            stack.pop_back();
+            distance_node = stack_d.back();
+            stack_d.pop_back();
+          }
+          else
+          {
+            node = (traverse_left && (distance_left <= distance_right || !traverse_right)) ? left_child : right_child;
+            distance_node = node == left_child ? distance_left : distance_right;
+            if (traverse_left && traverse_right)
+            {
+              stack.push_back(node == left_child ? right_child : left_child);
+              stack_d.push_back(node == left_child ? distance_right : distance_left);
+            }
+          }
+        } while (node != -1);
+        best[i] = current_best;
+      }
+    }
+    // component minimum (the reference's atomic_min on the weight, then retrieveEdges :336-372 on the pair key)
+    for (int i = 0; i < n; ++i)
+      if (best[i].weight < inf && best[i] < out_edges[labels[i]])
+        out_edges[labels[i]] = best[i];
+    // UpdateComponentsAndEdges (BoruvkaHelpers.hpp:381-470)
+    auto nextComponent = [&](int component) {
+      int const next = labels[out_edges[component].target()];
+      int const next_next = labels[out_edges[next].target()];
+      if (next_next != component)
+        return next;
+      return std::min(component, next);
+    };
+    for (int i = 0; i < n; ++i)
+    {
+      if (labels[i] != i || nextComponent(i) == i)
+        continue;
+      e_src[num_edges] = out_edges[i].source();
+      e_dst[num_edges] = out_edges[i].target();
+      weights_out[num_edges] = out_edges[i].weight;
+      ++num_edges;
+    }
+    std::vector<int> new_labels(n);
+    for (int i = 0; i < n; ++i)
+    {
+      int prev = labels[i], next;
+      while ((next = nextComponent(prev)) != prev)
+        prev = next;
+      new_labels[i] = next;
+    }
+    std::copy(new_labels.begin(), new_labels.end(), labels.begin());
+  } while (n - num_edges > 1);
+  // finalizeEdges (BoruvkaHelpers.hpp:472-488)
+  for (int e = 0; e < n - 1; ++e)
+  {
+    edges2[2 * e] = (int)t.perm[e_src[e]];
+    edges2[2 * e + 1] = (int)t.perm[e_dst[e]];
+  }
+  return iterations;
+}
+
+// Dendrogram of weighted edges (Dendrogram.hpp:47-76): edges sorted by weight, then the sequential union-find of
+// DendrogramHelpers.hpp:31-80.  parents: 2 * num_edges + 1 entries (edges first, then vertices); heights: num_edges.
+ORC_API void orc_dendrogram_union_find(int const *edges2, float const *weights, int num_edges, int *parents,
+                                       float *heights)
+{
+  int const num_vertices = num_edges + 1;
+  std::vector<int> order(num_edges);
+  for (int e = 0; e < num_edges; ++e)
+    order[e] = e;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return weights[a] < weights[b]; });
+  std::vector<int> labels(num_vertices), set_edges(num_vertices, -1);
+  for (int i = 0; i < num_vertices; ++i)
+    labels[i] = i;
+  UnionFind uf{labels.data()};
+  for (int e = 0; e < num_edges; ++e)
+  {
+    heights[e] = weights[order[e]];
+    int const i = uf.representative(edges2[2 * order[e]]);
+    int const j = uf.representative(edges2[2 * order[e] + 1]);
+    for (int k : {i, j})
+    {
+      int const child = set_edges[k];
+      if (child != -1)
+        parents[child] = e;
+      else
+        parents[num_edges + k] = e;
+    }
+    uf.merge(i, j);
+    set_edges[uf.representative(i)] = e;
+  }
+  if (num_edges > 0)
+    parents[num_edges - 1] = -1;
+}

@@ -98,11 +98,13 @@ def test_distributed_native_local_ranks(world):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("world,layout", [(2, "slabs"), (4, "blocks"), (3, "lopsided")])
-def test_distributed_native_two_stage_knn(world, layout):
-    """kNN with enough points per rank for the two-stage form (abx_dist.cu: the points near another rank's box go
-    first, their exchange runs under the interior points' traversal; interior points that do reach another rank --
-    here: queries far outside every block -- take a second exchange).  Every rank's rows must be the rows of ONE
-    tree over all points: same distances bit for bit, and every (index, rank) pair names a point at that distance."""
+def test_distributed_native_knn_large(world, layout):
+    """kNN with a few 10^5 points and queries per rank, a rank with fewer than k points, and queries far outside
+    every block (their k-th local distance reaches every rank).  Every rank's rows must be the rows of ONE tree
+    over all points: same distances bit for bit, and every (index, rank) pair names a point at that distance.
+    With ABX_LIBRARY = the tuning library and ABX_KNN_TWO_STAGE=1 (test_distributed_native_knn_two_stage_form) the
+    same cases run the two-stage form of abx_dist.cu: near-boundary points first, their exchange under the interior
+    points' traversal, a second exchange for the far-away queries."""
     import threading
 
     import arborx_b200 as abx
@@ -182,6 +184,21 @@ def test_distributed_native_two_stage_knn(world, layout):
     assert not any(t.is_alive() for t in threads), "a rank is stuck in a collective: %s" % errors
     for r, e in enumerate(errors):
         assert e is None, "rank %d:\n%s" % (r, e)
+
+
+@pytest.mark.gpu
+def test_distributed_native_knn_two_stage_form():
+    """The measured-and-shelved two-stage kNN of abx_dist.cu stays correct: same cases, tuning library."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tuning = os.path.join(root, "arborx_b200", "lib", "libabx_tuning.so")
+    if not os.path.exists(tuning):
+        pytest.skip("libabx_tuning.so not built (make -C arborx_b200/csrc tuning)")
+    env = dict(os.environ, ABX_LIBRARY=tuning, ABX_KNN_TWO_STAGE="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", os.path.abspath(__file__), "-k",
+                        "knn_large"], cwd=root, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
 def _dbscan_worker(rank, world, port, q):

@@ -1,0 +1,261 @@
+"""Minimum spanning tree / dendrogram / HDBSCAN.
+
+CPU: the oracle (oracle/arborx_oracle.cpp: orc_mst, orc_dendrogram_union_find) against the reference's golden
+vectors -- the equidistant / non-equidistant line cases of test/tstMinimumSpanningTree.cpp:90-140, the 1000-point
+golden tree and the k = 5, 10, 15 total weights of test/tstMinimumSpanningTreeGoldenTest.cpp:86-150
+(tests/golden/mst_golden.npz), the three dendrograms of test/tstDendrogram.cpp:56-113 -- and against an all-pairs
+Kruskal.  GPU (-m gpu): the CUDA path through the C ABI against the oracle: identical edge sets and weights."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "mst_golden.npz")
+
+
+def undirected(edges, weights):
+    e = np.asarray(edges).reshape(-1, 2)
+    lo, hi = np.minimum(e[:, 0], e[:, 1]), np.maximum(e[:, 0], e[:, 1])
+    rows = sorted(zip(np.asarray(weights, np.float32).tolist(), lo.tolist(), hi.tolist()))
+    return rows
+
+
+def core_distances(pts, k):
+    d = np.sqrt(((pts[:, None, :] - pts[None, :, :]) ** 2).sum(-1, dtype=np.float32)).astype(np.float32)
+    return np.sort(d, axis=1)[:, min(k, len(pts)) - 1]
+
+
+def kruskal_total(pts, k):
+    """total weight of an MST of the complete graph under the (mutual reachability) metric, float32 weights."""
+    pts = np.asarray(pts, np.float32)
+    n = len(pts)
+    diff = pts[:, None, :] - pts[None, :, :]
+    d = np.sqrt((diff[..., 0] * diff[..., 0] + diff[..., 1] * diff[..., 1]) + diff[..., 2] * diff[..., 2]).astype(np.float32)
+    if k > 1:
+        c = np.sort(d, axis=1)[:, min(k, n) - 1]
+        d = np.maximum(np.maximum(c[:, None], c[None, :]), d)
+    iu = np.triu_indices(n, 1)
+    w = d[iu]
+    order = np.argsort(w, kind="stable")
+    parent = list(range(n))
+
+    def find(x):
+        while parent[x] != x:
+            parent[x] = parent[parent[x]]
+            x = parent[x]
+        return x
+    total, used, ws = 0.0, 0, []
+    for e in order:
+        a, b = find(int(iu[0][e])), find(int(iu[1][e]))
+        if a != b:
+            parent[a] = b
+            ws.append(w[e])
+            used += 1
+            if used == n - 1:
+                break
+    return np.sort(np.array(ws, np.float32))
+
+
+LINE = np.array([[0, 0, 0], [1, 0, 0], [2, 0, 0], [3, 0, 0], [4, 0, 0]], np.float32)
+# tstMinimumSpanningTree.cpp:98-124
+LINE_REF = {
+    1: [(0, 1, 1), (1, 2, 1), (2, 3, 1), (3, 4, 1)],
+    2: [(0, 1, 1), (1, 2, 1), (2, 3, 1), (3, 4, 1)],
+    3: [(0, 1, 2), (1, 2, 1), (2, 3, 1), (2, 4, 2)],
+    4: [(0, 1, 3), (1, 2, 2), (1, 3, 2), (1, 4, 3)],
+    5: [(0, 1, 4), (1, 2, 3), (1, 3, 3), (0, 4, 4)],
+}
+UNEVEN = np.array([[0, 0, 0], [1, 0, 0], [2, 0, 0], [3, 0, 0], [6, 0, 0], [10, 0, 0]], np.float32)
+# :126-139
+UNEVEN_REF = {k: [(0, 1, 1), (1, 2, 1), (2, 3, 1), (3, 4, 3), (4, 5, 4)] for k in (1, 2)}
+
+# tstDendrogram.cpp:56-113: (edges, parents, heights)
+DENDROGRAMS = [
+    ([(0, 1, 3.0)], [-1, 0, 0], [3.0]),
+    ([(0, 3, 7.0), (1, 2, 3.0), (0, 1, 2.0)], [1, 2, -1, 0, 0, 1, 2], [2.0, 3.0, 7.0]),
+    ([(2, 3, 2.0), (2, 0, 9.0), (0, 1, 3.0)], [2, 2, -1, 1, 1, 0, 0], [2.0, 3.0, 9.0]),
+]
+
+
+def ref_rows(ref):
+    return sorted((float(w), min(a, b), max(a, b)) for a, b, w in ref)
+
+
+def check_spanning(n, edges):
+    parent = list(range(n))
+
+    def find(x):
+        while parent[x] != x:
+            parent[x] = parent[parent[x]]
+            x = parent[x]
+        return x
+    for a, b in np.asarray(edges).tolist():
+        ra, rb = find(a), find(b)
+        assert ra != rb, "cycle"
+        parent[ra] = rb
+    assert len({find(i) for i in range(n)}) == 1
+
+
+# ------------------------------------------------------------------ oracle (CPU) ----
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5])
+def test_oracle_line_cases(k):
+    e, w = oracle.mst(LINE, k)
+    assert undirected(e, w) == ref_rows(LINE_REF[k])
+    if k in UNEVEN_REF:
+        e, w = oracle.mst(UNEVEN, k)
+        assert undirected(e, w) == ref_rows(UNEVEN_REF[k])
+
+
+def test_oracle_golden_tree():
+    g = np.load(GOLDEN)
+    pts = g["points"].astype(np.float32)
+    e, w = oracle.mst(pts, 1)
+    got = {(min(a, b), max(a, b)) for a, b in e.tolist()}
+    ref = {(min(a, b), max(a, b)) for a, b in g["edges"].tolist()}
+    assert got == ref
+    # the reference's test compares the vertex pairs only (UndirectedEdge::operator==, :27-33); the csv weights are
+    # double-precision distances of the csv coordinates, the tree's are float distances of the float coordinates
+    gw = dict(zip(map(lambda r: (min(r), max(r)), g["edges"].tolist()), g["weights"].tolist()))
+    for (a, b), x in zip(e.tolist(), w.tolist()):
+        assert abs(gw[(min(a, b), max(a, b))] - x) <= 2e-5 * x
+    # tstMinimumSpanningTreeGoldenTest.cpp:126-150: total weights for k = 5, 10, 15, relative tolerance 1e-8
+    for k, total in zip(g["total_weight_k"].tolist(), g["total_weight"].tolist()):
+        e, w = oracle.mst(pts, k)
+        assert abs(float(np.sum(w.astype(np.float64))) - total) <= 1e-8 * total
+
+
+@pytest.mark.parametrize("k", [1, 3, 8])
+def test_oracle_vs_kruskal(k):
+    rng = np.random.default_rng(7 + k)
+    for pts in (rng.random((600, 3), dtype=np.float32),
+                # a lattice: many equal weights, the tree is unique only through the pair order
+                np.stack(np.meshgrid(*[np.arange(7, dtype=np.float32)] * 3, indexing="ij"), -1).reshape(-1, 3)):
+        e, w = oracle.mst(pts, k)
+        check_spanning(len(pts), e)
+        assert np.array_equal(np.sort(w), kruskal_total(pts, k))
+        # every edge carries its own metric value
+        c = core_distances(pts, k) if k > 1 else np.zeros(len(pts), np.float32)
+        diff = pts[e[:, 0]] - pts[e[:, 1]]
+        d = np.sqrt((diff[:, 0] * diff[:, 0] + diff[:, 1] * diff[:, 1]) + diff[:, 2] * diff[:, 2]).astype(np.float32)
+        assert np.array_equal(np.maximum(np.maximum(c[e[:, 0]], c[e[:, 1]]), d), w)
+
+
+def test_oracle_dendrogram_golden():
+    for edges, parents, heights in DENDROGRAMS:
+        e = np.array([(a, b) for a, b, _ in edges], np.int32)
+        w = np.array([x for _, _, x in edges], np.float32)
+        p, h = oracle.dendrogram(e, w)
+        assert p.tolist() == parents and h.tolist() == heights
+
+
+def test_oracle_degenerate():
+    e, w = oracle.mst(np.zeros((1, 3), np.float32), 1)
+    assert e.shape == (0, 2) and w.shape == (0,)
+    e, w = oracle.mst(np.array([[0, 0, 0], [3, 4, 0]], np.float32), 1)
+    assert undirected(e, w) == [(5.0, 0, 1)]
+    # duplicates: zero-weight edges, still a spanning tree
+    pts = np.repeat(np.random.default_rng(3).random((40, 3), dtype=np.float32), 3, axis=0)
+    e, w = oracle.mst(pts, 1)
+    check_spanning(len(pts), e)
+    assert (w == 0).sum() == 80
+
+
+# ------------------------------------------------------------------ CUDA path ----
+def _gpu():
+    import torch
+
+    import arborx_b200 as abx
+    return torch, abx, abx.ExecutionSpace()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5])
+def test_cuda_line_cases(k):
+    torch, abx, space = _gpu()
+    mst = abx.MinimumSpanningTree(space, torch.from_numpy(LINE).cuda(), k)
+    space.fence()
+    assert undirected(mst.edges.cpu().numpy(), mst.weights.cpu().numpy()) == ref_rows(LINE_REF[k])
+    if k in UNEVEN_REF:
+        mst = abx.MinimumSpanningTree(space, torch.from_numpy(UNEVEN), k)  # host entry point
+        assert undirected(mst.edges.numpy(), mst.weights.numpy()) == ref_rows(UNEVEN_REF[k])
+
+
+@pytest.mark.gpu
+def test_cuda_golden_tree():
+    torch, abx, space = _gpu()
+    g = np.load(GOLDEN)
+    pts = g["points"].astype(np.float32)
+    mst = abx.MinimumSpanningTree(space, torch.from_numpy(pts).cuda())
+    space.fence()
+    got = {(min(a, b), max(a, b)) for a, b in mst.edges.cpu().numpy().tolist()}
+    assert got == {(min(a, b), max(a, b)) for a, b in g["edges"].tolist()}
+    for k, total in zip(g["total_weight_k"].tolist(), g["total_weight"].tolist()):
+        mst = abx.MinimumSpanningTree(space, torch.from_numpy(pts).cuda(), k)
+        space.fence()
+        assert abs(float(mst.weights.double().sum().item()) - total) <= 1e-8 * total
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,k,kind", [(2, 1, "random"), (3, 2, "random"), (1000, 1, "random"), (5000, 4, "random"),
+                                      (343, 1, "lattice"), (343, 5, "lattice"), (4096, 2, "lattice"),
+                                      (3000, 1, "duplicates"), (3000, 6, "duplicates"), (200_000, 1, "random"),
+                                      (200_000, 5, "clustered"), (50, 80, "random")])
+def test_cuda_vs_oracle(n, k, kind):
+    torch, abx, space = _gpu()
+    rng = np.random.default_rng(n * 31 + k)
+    if kind == "lattice":
+        m = round(n ** (1 / 3))
+        pts = np.stack(np.meshgrid(*[np.arange(m, dtype=np.float32)] * 3, indexing="ij"), -1).reshape(-1, 3)
+    elif kind == "duplicates":
+        pts = np.repeat(rng.random((n // 3, 3), dtype=np.float32), 3, axis=0)
+    elif kind == "clustered":
+        from tests import clouds
+        pts = clouds.gan_tao(3, n)
+    else:
+        pts = rng.random((n, 3), dtype=np.float32) * 100
+    pts = np.ascontiguousarray(pts, np.float32)
+    mst = abx.MinimumSpanningTree(space, torch.from_numpy(pts).cuda(), k)
+    space.fence()
+    e, w = oracle.mst(pts, k)
+    assert undirected(mst.edges.cpu().numpy(), mst.weights.cpu().numpy()) == undirected(e, w)
+    assert mst.iterations >= 1
+
+
+@pytest.mark.gpu
+def test_cuda_dendrogram_and_hdbscan():
+    torch, abx, space = _gpu()
+    for edges, parents, heights in DENDROGRAMS:
+        e = torch.tensor([(a, b) for a, b, _ in edges], dtype=torch.int32).cuda()
+        w = torch.tensor([x for _, _, x in edges], dtype=torch.float32).cuda()
+        d = abx.Dendrogram(space, e, w)
+        space.fence()
+        assert d._parents.cpu().tolist() == parents and d._parent_heights.cpu().tolist() == heights
+    # hdbscan = MST(core_min_size) + dendrogram; distinct weights make the dendrogram unique
+    rng = np.random.default_rng(11)
+    pts = (rng.random((3000, 3), dtype=np.float32) * 100).astype(np.float32)
+    for k in (1, 5):
+        d = abx.hdbscan(space, torch.from_numpy(pts).cuda(), k)
+        space.fence()
+        e, w = oracle.mst(pts, k)
+        if len(np.unique(w)) != len(w):
+            continue
+        p, h = oracle.dendrogram(e, w)
+        assert np.array_equal(d._parents.cpu().numpy(), p)
+        assert np.array_equal(d._parent_heights.cpu().numpy(), h)
+    # single vertex
+    d = abx.hdbscan(space, torch.zeros((1, 3), device="cuda"), 2)
+    space.fence()
+    assert d._parents.cpu().tolist() == [-1]
+
+
+@pytest.mark.gpu
+def test_cuda_errors():
+    torch, abx, space = _gpu()
+    with pytest.raises(Exception):
+        abx.MinimumSpanningTree(space, torch.zeros((4, 3), device="cuda"), 0)
+    mst = abx.MinimumSpanningTree(space, torch.zeros((1, 3), device="cuda"))
+    assert mst.edges.shape == (0, 2)
+    mst = abx.MinimumSpanningTree(space, torch.zeros((0, 3), device="cuda"))
+    assert mst.edges.shape == (0, 2)
