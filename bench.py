@@ -487,7 +487,7 @@ def run_ours(args):
     # ---- the other BASELINE configs (outside the headline timed region) ---------------
     workloads = {}
     if not args.skip_workloads:
-        for name, fn in (("dbscan_10M", wl_dbscan), ("triangles_20M", wl_triangles),
+        for name, fn in (("dbscan_10M", wl_dbscan), ("mst_10M", wl_mst), ("triangles_20M", wl_triangles),
                          ("distributed_100M", wl_distributed), ("distributed_dbscan", wl_distributed_dbscan)):
             try:
                 t0 = time.perf_counter()
@@ -686,6 +686,46 @@ def wl_dbscan(args, abx, torch, dist, space, comm, rank, world, peak, traffic):
     return res
 
 
+def wl_mst(args, abx, torch, dist, space, comm, rank, world, peak, traffic):
+    """Euclidean minimum spanning tree (k = 1) and the mutual-reachability tree HDBSCAN uses
+    (k = 5) over 10M points: the bench's uniform cloud and the GanTao cluster cloud
+    (cluster/ArborX_MinimumSpanningTree.hpp; no published number in BASELINE.md).  Single tree: N = 1."""
+    if world > 1:
+        return None
+    from tests import clouds
+    n = args.mst_n
+    res = {"config": "MinimumSpanningTree over n=%d points, Boruvka rounds on the BVH; k = 1 Euclidean, k = 5 mutual "
+                     "reachability (core distance = 5th nearest, the point itself included)" % n}
+    steps = 3
+    for cname, make in (("uniform", lambda m: clouds.filled_box(0x5EED0001, m)), ("gantao", lambda m: clouds.gan_tao(3, m))):
+        d = torch.from_numpy(np.ascontiguousarray(make(n), np.float32)).cuda()
+        for k in (1, 5):
+            abx.MinimumSpanningTree(space, d, k)  # first call of the shape: the device-memory cache fills
+            torch.cuda.synchronize()
+            abx.profile_enable(True)
+            ms, mst = _time_gpu(torch, lambda: abx.MinimumSpanningTree(space, d, k), 0, steps)
+            prof = abx.profile_report()
+            abx.profile_enable(False)
+            res["%s_k%d" % (cname, k)] = {
+                "ms": ms, "Mpoints_s": n / ms / 1e3, "rounds": mst.iterations,
+                "total_weight": float(mst.weights.double().sum().item()),
+                "kernels_ms_per_call": {name: round(t / steps, 3) for name, c, t, mx in prof[:5]}}
+        del d
+    oracle = oracle_all_threads()
+    ns = min(n, args.cpu_n)
+    for cname, make in (("uniform", lambda m: clouds.filled_box(0x5EED0001, m)), ("gantao", lambda m: clouds.gan_tao(3, m))):
+        sample = np.ascontiguousarray(make(ns), np.float32)
+        t0 = time.perf_counter()
+        oracle.mst(sample, 1)
+        t_cpu = time.perf_counter() - t0
+        res["%s_k1" % cname]["cpu_baseline"] = {"Mpoints_s": ns / t_cpu / 1e6, "cores": oracle.num_threads(),
+                                                "kind": "port",
+                                                "sample": "oracle mst (k = 1) of %d points of the same cloud kind, "
+                                                          "measured" % ns}
+    res["value_Mpoints_s"] = res["gantao_k1"]["Mpoints_s"]
+    return res
+
+
 def wl_triangles(args, abx, torch, dist, space, comm, rank, world, peak, traffic):
     """BASELINE configs[4]: BVH over the 20 971 520 triangles of the icosphere (--refinements 10), nearest(point, 1)
     with distances, intersects(ray) CRS (benchmarks/triangulated_surface_distance/triangulated_surface_distance.cpp
@@ -849,6 +889,7 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=1_000_000, help="points (= queries) of the CPU arm's per-step sample")
     ap.add_argument("--counter-sample", type=int, default=200_000,
                     help="queries the oracle counts node visits on (byte model)")
+    ap.add_argument("--mst-n", type=int, default=10_000_000)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--e2e-threads", type=int, default=3, help="host threads (streams) of the end-to-end path")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="host calls per query batch in the end-to-end path")

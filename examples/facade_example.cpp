@@ -78,6 +78,21 @@ int main()
     threw = true;
   }
   ok = ok && threw;
+  // MinimumSpanningTree / hdbscan on the equidistant points of tstMinimumSpanningTree.cpp:90-124 (k = 3:
+  // weights 2, 1, 1, 2)
+  DeviceView<Point<>> line;
+  line.assign({{{0.f, 0.f, 0.f}}, {{1.f, 0.f, 0.f}}, {{2.f, 0.f, 0.f}}, {{3.f, 0.f, 0.f}}, {{4.f, 0.f, 0.f}}});
+  Experimental::MinimumSpanningTree mst(space, line, 3);
+  auto mw = mst.weights.to_host();
+  float total = 0.f;
+  for (float w : mw)
+    total += w;
+  std::printf("mst(k = 3): %zu edges, total weight %g, %d rounds\n", mw.size(), total, mst.iterations);
+  ok = ok && mw.size() == 4 && total == 6.f;
+  auto dendrogram = Experimental::hdbscan(space, line, 3);
+  auto dp = dendrogram._parents.to_host();
+  auto dh = dendrogram._parent_heights.to_host();
+  ok = ok && dp.size() == 9 && dh.size() == 4 && dp[3] == -1 && dh[0] == 1.f && dh[3] == 2.f;
   std::printf(ok ? "FACADE OK\n" : "FACADE FAILED\n");
   return ok ? 0 : 1;
 }

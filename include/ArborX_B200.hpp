@@ -16,6 +16,8 @@
 //   BoundingVolumeHierarchy              spatial/ArborX_LinearBVH.hpp:50-142
 //   query (free function)                spatial/ArborX_CrsGraphWrapper.hpp:22-35
 //   dbscan, DBSCAN::Parameters           cluster/ArborX_DBSCAN.hpp:180-223
+//   Experimental::MinimumSpanningTree,   cluster/ArborX_MinimumSpanningTree.hpp:31-101,
+//     Dendrogram, hdbscan                cluster/ArborX_Dendrogram.hpp:24-76, cluster/ArborX_HDBSCAN.hpp:29-53
 //   SearchException                      misc/ArborX_Exception.hpp:19-38
 //
 // Not covered by a C ABI: arbitrary device callbacks (functors cannot cross it); see
@@ -573,6 +575,72 @@ inline void dbscan(Cuda const &space, DeviceView<Point<>> const &primitives, dou
                                                                                : ABX_DBSCAN_DBSCAN_STAR,
                             labels.data()));
 }
+
+// ---- MinimumSpanningTree / Dendrogram / hdbscan ------------------------------------------------
+// cluster/ArborX_MinimumSpanningTree.hpp:31-101, cluster/ArborX_Dendrogram.hpp:24-76, cluster/ArborX_HDBSCAN.hpp:29-53
+namespace Experimental
+{
+// cluster/detail/ArborX_WeightedEdge.hpp:20-50; the library keeps (source, target) and the weights in two arrays
+struct UnweightedEdge
+{
+  int source;
+  int target;
+};
+
+struct MinimumSpanningTree
+{
+  DeviceView<UnweightedEdge> edges;
+  DeviceView<float> weights;
+  int iterations = 0;
+  MinimumSpanningTree(Cuda const &space, DeviceView<Point<>> const &points, int k = 1)
+  {
+    std::size_t const n = points.size();
+    edges.realloc(n > 0 ? n - 1 : 0);
+    weights.realloc(n > 0 ? n - 1 : 0);
+    std::int32_t it = 0;
+    Details::check(abx_mst_points3f(space.cuda_stream(), reinterpret_cast<float const *>(points.data()),
+                                    (std::int64_t)n, k, reinterpret_cast<std::int32_t *>(edges.data()),
+                                    weights.data(), &it));
+    iterations = it;
+  }
+};
+
+enum class DendrogramImplementation
+{
+  BORUVKA, // not provided: requests fall back to the exception below
+  UNION_FIND
+};
+
+struct Dendrogram
+{
+  DeviceView<int> _parents;
+  DeviceView<float> _parent_heights;
+  Dendrogram() = default;
+  Dendrogram(Cuda const &space, DeviceView<UnweightedEdge> const &edges, DeviceView<float> const &weights)
+  {
+    std::size_t const m = edges.size();
+    _parents.realloc(2 * m + 1);
+    _parent_heights.realloc(m);
+    Details::check(abx_dendrogram_union_find(space.cuda_stream(), reinterpret_cast<std::int32_t const *>(edges.data()),
+                                             weights.data(), (std::int64_t)m, _parents.data(),
+                                             _parent_heights.data()));
+  }
+};
+
+inline Dendrogram hdbscan(Cuda const &space, DeviceView<Point<>> const &primitives, int core_min_size,
+                          DendrogramImplementation impl = DendrogramImplementation::UNION_FIND)
+{
+  if (impl != DendrogramImplementation::UNION_FIND)
+    throw std::invalid_argument("hdbscan: only DendrogramImplementation::UNION_FIND is provided");
+  Dendrogram d;
+  std::size_t const n = primitives.size();
+  d._parents.realloc(n > 0 ? 2 * n - 1 : 0);
+  d._parent_heights.realloc(n > 0 ? n - 1 : 0);
+  Details::check(abx_hdbscan_points3f(space.cuda_stream(), reinterpret_cast<float const *>(primitives.data()),
+                                      (std::int64_t)n, core_min_size, d._parents.data(), d._parent_heights.data()));
+  return d;
+}
+} // namespace Experimental
 
 } // namespace ArborX
 
