@@ -291,8 +291,11 @@ __device__ __forceinline__ void traverseSpatial(Node64 const *__restrict__ nodes
     float4 const a0 = __ldg(f), a1 = __ldg(f + 1), a2 = __ldg(f + 2), a3 = __ldg(f + 3);
     int const lref = __float_as_int(a0.w), rref = __float_as_int(a1.w);
     int const rl = __float_as_int(a2.w), rr = __float_as_int(a3.w);
-    bool hit_l = pred.box(a0, a1);
-    bool hit_r = pred.box(a2, a3);
+    // BUCKET == 0: the reference's leaf rule (TreeTraversal.hpp:97-119): a leaf has no box of its own, its value is
+    // handed to the predicate whenever its parent is visited.  Needed where the exact leaf test can accept what the
+    // leaf's bounding box rejects: ray - triangle, whose watertight test carries tolerances (ArborX_Ray.hpp:340-355).
+    bool hit_l = (BUCKET == 0 && refIsLeaf(lref)) || pred.box(a0, a1);
+    bool hit_r = (BUCKET == 0 && refIsLeaf(rref)) || pred.box(a2, a3);
     // left child covers [rl, l_hi], right child [r_lo, rr] (an internal left child's
     // Karras index is its last leaf, an internal right child's its first)
     int const l_hi = refIsLeaf(lref) ? rl : lref;

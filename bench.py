@@ -303,6 +303,10 @@ def kernel_table(prof, models, traffic, peak, launches_per_step_hint=1):
 
 def phase_fracs(name, model_bytes, dram_bytes, ms, peak):
     out = {name + "_model_bytes": model_bytes, name + "_model_frac": model_bytes / (ms * 1e-3) / 1e9 / peak}
+    if out[name + "_model_frac"] > 1.0:
+        # the model counts the reference algorithm's node visits (two traversal passes for the radius phase, cache
+        # hits included): above the HBM peak it is a statement about the model, not a roofline
+        out[name + "_model_exceeds_peak"] = True
     if dram_bytes:
         out[name + "_dram_bytes_ncu"] = dram_bytes
         out[name + "_dram_frac"] = dram_bytes / (ms * 1e-3) / 1e9 / peak

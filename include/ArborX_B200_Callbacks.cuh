@@ -96,11 +96,11 @@ __global__ void __launch_bounds__(kThreads)
     // TreeTraversal.hpp:80-90: the predicate against the single leaf
     float4 const lo = __ldg(leaf_box);
     float4 const hi = LEAF_F4 == 1 ? lo : __ldg(leaf_box + 1);
-    if (pred.box(lo, hi) && (!TRI || triangleLeafTest<PRED>(pred, leaf_tri, 0)))
+    if (TRI ? triangleLeafTest<PRED>(pred, leaf_tri, 0) : pred.box(lo, hi))
       invoke(cb, qi, 0u);
     return;
   }
-  traverseSpatial<LEAF_F4>(nodes, leaf_box, pred, [&](unsigned orig, int pos) {
+  traverseSpatial<LEAF_F4, (TRI ? 0 : kBucket)>(nodes, leaf_box, pred, [&](unsigned orig, int pos) {
     if (TRI && !triangleLeafTest<PRED>(pred, leaf_tri, pos))
       return false;
     return invoke(cb, qi, orig);
@@ -222,11 +222,11 @@ __global__ void __launch_bounds__(kThreads)
   {
     float4 const lo = __ldg(leaf_box);
     float4 const hi = LEAF_F4 == 1 ? lo : __ldg(leaf_box + 1);
-    if (pred.box(lo, hi) && (!TRI || triangleLeafTest<PRED>(pred, leaf_tri, 0)))
+    if (TRI ? triangleLeafTest<PRED>(pred, leaf_tri, 0) : pred.box(lo, hi))
       cb(qi, 0u, out);
   }
   else
-    traverseSpatial<LEAF_F4>(nodes, leaf_box, pred, [&](unsigned orig, int pos) {
+    traverseSpatial<LEAF_F4, (TRI ? 0 : kBucket)>(nodes, leaf_box, pred, [&](unsigned orig, int pos) {
       if (TRI && !triangleLeafTest<PRED>(pred, leaf_tri, pos))
         return false;
       cb(qi, orig, out);
@@ -410,7 +410,7 @@ __device__ inline void query_per_thread(DeviceTree const &tree, Pred<PRED> const
   {
     float4 const lo = __ldg(tree.leaf_box);
     float4 const hi = leaf_f4 == 1 ? lo : __ldg(tree.leaf_box + 1);
-    if (pred.box(lo, hi) && (!tri || triangleLeafTest<PRED>(pred, tree.leaf_tri, 0)))
+    if (tri ? triangleLeafTest<PRED>(pred, tree.leaf_tri, 0) : pred.box(lo, hi))
       detail::invokeValue(callback, 0u);
     return;
   }
@@ -421,6 +421,8 @@ __device__ inline void query_per_thread(DeviceTree const &tree, Pred<PRED> const
   };
   if (leaf_f4 == 1)
     traverseSpatial<1>(tree.nodes, tree.leaf_box, pred, emit);
+  else if (tri) // triangles: a leaf is tested whenever its parent is visited (the reference's leaves have no box)
+    traverseSpatial<2, 0>(tree.nodes, tree.leaf_box, pred, emit);
   else
     traverseSpatial<2>(tree.nodes, tree.leaf_box, pred, emit);
 }

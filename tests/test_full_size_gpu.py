@@ -170,3 +170,48 @@ def test_dbscan_implementations_agree_10m():
     lc = abx.dbscan(space, x, 200.0, 5, abx.DBSCANParameters(0, 1))
     ld = abx.dbscan(space, x, 200.0, 5, abx.DBSCANParameters(1, 1))
     assert torch.equal(lc, ld)  # DBSCAN*: only core points are labelled, deterministically
+
+
+def test_mst_vs_oracle_2m():
+    """MinimumSpanningTree at 2M points: edge for edge and weight for weight against the oracle (the tree is unique
+    under the reference's edge order, detail/ArborX_BoruvkaHelpers.hpp:37-105)."""
+    import arborx_b200 as abx
+    import oracle
+    space = abx.ExecutionSpace()
+    pts_h = clouds.gan_tao(3, 2_000_000)
+    for k in (1, 4):
+        mst = abx.MinimumSpanningTree(space, torch.from_numpy(pts_h).cuda(), k)
+        space.fence()
+        e, w = oracle.mst(pts_h, k)
+        got = mst.edges.cpu().numpy().astype(np.int64)
+        key_got = np.sort(np.minimum(got[:, 0], got[:, 1]) * (1 << 32) + np.maximum(got[:, 0], got[:, 1]))
+        ee = e.astype(np.int64)
+        key_ref = np.sort(np.minimum(ee[:, 0], ee[:, 1]) * (1 << 32) + np.maximum(ee[:, 0], ee[:, 1]))
+        assert np.array_equal(key_got, key_ref)
+        assert np.array_equal(np.sort(mst.weights.cpu().numpy()), np.sort(w))
+
+
+def test_mst_properties_10m(setup):
+    """10M points: n - 1 edges that connect everything, every weight is the distance of its end points, and no
+    point has a neighbour closer than its lightest tree edge (the cut property at single vertices)."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    abx, space, pts_h, pts, bvh = setup
+    mst = abx.MinimumSpanningTree(space, pts)
+    space.fence()
+    e = mst.edges.cpu().numpy()
+    w = mst.weights.cpu().numpy()
+    assert e.shape == (N - 1, 2) and e.min() >= 0 and e.max() < N
+    g = coo_matrix((np.ones(N - 1, np.int8), (e[:, 0], e[:, 1])), shape=(N, N))
+    ncomp, _ = connected_components(g, directed=False)
+    assert ncomp == 1
+    diff = pts_h[e[:, 0]] - pts_h[e[:, 1]]
+    d = np.sqrt((diff[:, 0] * diff[:, 0] + diff[:, 1] * diff[:, 1]) + diff[:, 2] * diff[:, 2]).astype(np.float32)
+    assert np.array_equal(d, w)
+    # nearest other point of every vertex = its lightest incident tree edge
+    lightest = np.full(N, np.inf, np.float32)
+    np.minimum.at(lightest, e[:, 0], w)
+    np.minimum.at(lightest, e[:, 1], w)
+    idx, off, dist = bvh.query(space, abx.nearest(pts, 2), return_distances=True)
+    nn = dist.view(-1, 2)[:, 1].cpu().numpy()
+    assert np.array_equal(nn, lightest)

@@ -64,3 +64,43 @@ def test_indexed_triangles_equal_flat_triangles(refinements):
         bad = t.copy()
         bad[0, 0] = len(v)
         abx.BoundingVolumeHierarchy.from_indexed_triangles(space, torch.from_numpy(v).cuda(), torch.from_numpy(bad).cuda())
+
+
+@pytest.mark.gpu
+def test_ray_triangle_tolerance_hits_fine_mesh():
+    """On a fine mesh the reference's ray - triangle test (ArborX_Ray.hpp:266-417) accepts hits within its 1e-7
+    tolerance just outside a triangle, i.e. on triangles whose own bounding box the ray may miss.  The reference hands
+    a leaf's value to the predicate whenever the leaf's parent is visited (TreeTraversal.hpp:97-119), so those hits
+    are part of its answer: the row sets must equal the oracle's, and some rays must indeed report more triangles
+    than a leaf-box pre-test would allow (which is what the 20M-triangle bench workload exposed)."""
+    import arborx_b200 as abx
+    import oracle
+    space = abx.ExecutionSpace()
+    v, t = clouds.icosphere(8)  # 1.3M triangles
+    soup = clouds.triangle_soup(v, t)
+    bvh = abx.BoundingVolumeHierarchy(space, torch.from_numpy(soup).cuda(), abx.TRIANGLE)
+    ref = oracle.Tree(soup, oracle.PRIM_TRI)
+    rays = clouds.ball_rays(0x5EED0053, 150_000)
+    idx, off = bvh.query(space, abx.intersects(torch.from_numpy(rays).cuda(), abx.RAY_PRED))
+    roff, ridx = ref.spatial_crs(rays, oracle.PRED_RAY)
+    assert np.array_equal(off.cpu().numpy(), roff)
+    row = np.repeat(np.arange(len(rays)), np.diff(roff))
+    gi = idx.cpu().numpy().view(np.uint32)
+    assert np.array_equal(gi[np.lexsort((gi, row))], ridx[np.lexsort((ridx, row))])
+    # the tolerance hits exist in this sample: a hit triangle whose box the ray misses
+    lo = soup.reshape(-1, 3, 3).min(1)
+    hi = soup.reshape(-1, 3, 3).max(1)
+    o, d = rays[row, :3].astype(np.float64), rays[row, 3:].astype(np.float64)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t0 = (lo[ridx] - o) / d
+        t1 = (hi[ridx] - o) / d
+    tn = np.nanmax(np.minimum(t0, t1), axis=1)
+    tf = np.nanmin(np.maximum(t0, t1), axis=1)
+    assert int((tn > tf).sum()) > 0
+    # sphere predicates over the same tree
+    c = clouds.shell_points(91, 20_000)
+    spheres = np.concatenate([c, np.full((len(c), 1), 0.01, F)], 1).astype(F)
+    idx, off = bvh.query(space, abx.intersects(torch.from_numpy(spheres).cuda()))
+    roff, ridx = ref.spatial_crs(spheres, oracle.PRED_SPHERE)
+    assert np.array_equal(off.cpu().numpy(), roff)
