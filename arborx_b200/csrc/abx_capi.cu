@@ -309,12 +309,12 @@ abx_status spatialCrsBegin(SpatialCrsCall &c, abx_bvh *bvh, cudaStream_t s, int 
     ABX_TRY(c.overflow.alloc(1, s));
     ABX_CUDA_TRY(cudaMemsetAsync(c.overflow.ptr, 0, sizeof(int), s));
     ABX_LAUNCH(overflowKernel, divUp(q, 256), 256, 0, s, c.offsets, q, -policy.buffer_size, c.overflow.ptr);
-    ABX_CUDA_TRY(cudaMemcpyAsync(&c.h_overflow, c.overflow.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
+    ABX_CUDA_TRY(cudaMemcpyAsync(c.overflow_out, c.overflow.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
   }
   // the int32 scan wraps silently past 2^31 results: the total is accumulated in 64 bits next to it
   ABX_TRY(c.total64.alloc(1, s));
   ABX_TRY(exclusiveScanI32(s, c.offsets, c.offsets, q + 1, c.total64.ptr));
-  ABX_CUDA_TRY(cudaMemcpyAsync(&c.h_total, c.total64.ptr, sizeof(c.h_total), cudaMemcpyDeviceToHost, s));
+  ABX_CUDA_TRY(cudaMemcpyAsync(c.total_out, c.total64.ptr, sizeof(c.h_total), cudaMemcpyDeviceToHost, s));
   return ABX_OK;
 }
 
@@ -334,12 +334,12 @@ abx_status spatialCrsEnd(SpatialCrsCall &c, int32_t **offsets_out, uint32_t **in
     return ABX_OK;
   }
   ABX_CUDA_TRY(cudaStreamSynchronize(s));
-  if (c.h_total >= (1ull << 31))
+  if (*c.total_out >= (1ull << 31))
   {
     setError("spatial query: more than 2^31 results (CRS offsets are 32-bit like the reference's)");
     return ABX_ERR_ARG;
   }
-  int64_t const total = (int64_t)c.h_total;
+  int64_t const total = (int64_t)*c.total_out;
   *nnz_out = total;
   if (total == 0)
   {
@@ -347,7 +347,7 @@ abx_status spatialCrsEnd(SpatialCrsCall &c, int32_t **offsets_out, uint32_t **in
     *indices_out = (uint32_t *)idx;
     return ABX_OK; // :252-261
   }
-  if (c.h_overflow)
+  if (*c.overflow_out)
   {
     setError("SearchException: hard preallocation buffer_size is too small for the results");
     return ABX_ERR_SEARCH;

@@ -425,6 +425,11 @@ struct SpatialCrsCall // state of one spatial CRS query between its two halves; 
   TempBuffer<unsigned long long> total64;
   unsigned long long h_total = 0;
   int h_overflow = 0;
+  // where the two read-backs land.  The defaults are pageable (a device-to-host cudaMemcpyAsync into pageable
+  // memory returns only when the copy is done: Begin then blocks like the one-shot call would anyway); a caller
+  // that wants to keep enqueueing other work while the traversal runs points them at PINNED words it owns.
+  unsigned long long *total_out = &h_total;
+  int *overflow_out = &h_overflow;
   SpatialCrsCall() = default;
   SpatialCrsCall(SpatialCrsCall const &) = delete;
 };

@@ -811,6 +811,11 @@ abx_status distSpatial(abx_dist_tree *t, cudaStream_t s, int pred_kind, void con
   trace.mark("route_count+matrix", x);
   // 2. the local tree answers every local predicate (enqueued now, collected after the exchange)
   SpatialCrsCall local;
+  // pinned words for its read-backs: Begin must return while the traversal runs, the exchange is enqueued next
+  local.total_out = reinterpret_cast<unsigned long long *>(t->h_pin + kPinnedScratchWords - 6);
+  local.overflow_out = reinterpret_cast<int *>(t->h_pin + kPinnedScratchWords - 4);
+  *local.total_out = 0;
+  *local.overflow_out = 0;
   ABX_TRY(spatialCrsBegin(local, t->bottom, s, pred_kind, preds, q, policy, nullptr, nullptr));
   trace.mark("local_begin", s);
   struct Guard

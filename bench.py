@@ -604,12 +604,17 @@ def run_ours(args):
 
 # ------------------------------------------------------------ secondary workloads ----
 def _time_gpu(torch, fn, warmup, steps):
+    # the previous result is dropped before the next call (as a time-stepping caller would): its device blocks go
+    # back to the library's cache and the call under test does not pay a driver allocation for a second copy
+    out = None
     for _ in range(warmup):
+        out = None
         out = fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
+        out = None
         out = fn()
     e1.record()
     torch.cuda.synchronize()
