@@ -362,6 +362,37 @@ abx_status spatialCrsEnd(SpatialCrsCall &c, int32_t **offsets_out, uint32_t **in
   return ABX_OK;
 }
 
+abx_status spatialCrsWait(SpatialCrsCall &c, int64_t *nnz_out)
+{
+  *nnz_out = 0;
+  ABX_CUDA_TRY(cudaStreamSynchronize(c.s));
+  if (c.trivial)
+    return ABX_OK;
+  if (*c.total_out >= (1ull << 31))
+  {
+    setError("spatial query: more than 2^31 results (CRS offsets are 32-bit like the reference's)");
+    return ABX_ERR_ARG;
+  }
+  if (*c.overflow_out && *c.total_out > 0)
+  {
+    setError("SearchException: hard preallocation buffer_size is too small for the results");
+    return ABX_ERR_SEARCH;
+  }
+  *nnz_out = (int64_t)*c.total_out;
+  return ABX_OK;
+}
+
+abx_status spatialCrsFillInto(SpatialCrsCall &c, int64_t nnz, int32_t const *out_offsets, void *values, int pair_rank)
+{
+  if (c.trivial || nnz == 0)
+    return ABX_OK;
+  if (c.staged)
+    return spatialCompact(c.s, c.bvh, c.pred_kind, c.preds, c.q, nullptr, c.offsets, (uint32_t *)values, c.staging.ptr,
+                          out_offsets, pair_rank);
+  return spatialFill(c.s, c.bvh, c.pred_kind, c.preds, c.q, c.qperm.ptr, c.offsets, (uint32_t *)values, out_offsets,
+                     pair_rank);
+}
+
 // before_sync (optional): enqueues more work / read-backs on `s` that the call's one blocking point
 // should cover as well (the DistributedTree exchange piggy-backs its count matrix on it).
 abx_status spatialCrs(abx_bvh *bvh, cudaStream_t s, int pred_kind, void const *preds, int64_t q,

@@ -370,13 +370,17 @@ abx_status pointPermutationNearFirst(cudaStream_t s, abx_bvh *bvh, float const *
                                      unsigned long long *n_near_dev);
 abx_status spatialCount(cudaStream_t s, abx_bvh *bvh, int pred_kind, void const *preds, int64_t q,
                         uint32_t const *qperm, int32_t limit, int32_t *counts);
+// out_offsets / pair_rank (also spatialCompact): rows start at out_offsets[i] (lengths still from `offsets`) and
+// values are (index, pair_rank) pairs when pair_rank >= 0
 abx_status spatialFill(cudaStream_t s, abx_bvh *bvh, int pred_kind, void const *preds, int64_t q,
-                       uint32_t const *qperm, int32_t const *offsets, uint32_t *indices);
+                       uint32_t const *qperm, int32_t const *offsets, uint32_t *indices,
+                       int32_t const *out_offsets = nullptr, int pair_rank = -1);
 int spatialStageSlots();
 abx_status spatialStage(cudaStream_t s, abx_bvh *bvh, int pred_kind, void const *preds, int64_t q,
                         uint32_t const *qperm, int32_t *counts, uint32_t *staging);
 abx_status spatialCompact(cudaStream_t s, abx_bvh *bvh, int pred_kind, void const *preds, int64_t q,
-                          uint32_t const *qperm, int32_t const *offsets, uint32_t *indices, uint32_t const *staging);
+                          uint32_t const *qperm, int32_t const *offsets, uint32_t *indices, uint32_t const *staging,
+                          int32_t const *out_offsets = nullptr, int pair_rank = -1);
 abx_status nearestQuery(cudaStream_t s, abx_bvh *bvh, float const *pts, int64_t q, int32_t k,
                         int32_t const *k_per_query, uint32_t const *qperm, int32_t const *offsets, int64_t total_rows,
                         int32_t *counts, uint32_t *indices, float *distances,
@@ -399,6 +403,8 @@ abx_status mergeSorted(cudaStream_t s, int64_t q, int32_t const *local_off, int3
                        int32_t *out_vals2);
 abx_status mergeCounts(cudaStream_t s, int64_t q, int32_t const *local_off, int64_t m, int32_t const *remote_ids,
                        int32_t *out_off);
+abx_status mergeRemoteRows(cudaStream_t s, int64_t m, int32_t const *remote_ids, int32_t const *remote_vals2,
+                           int32_t const *local_off, int32_t const *out_off, int32_t *out_vals2);
 abx_status knnMerge(cudaStream_t s, int64_t m, int32_t const *ids, int32_t const *cand2, float const *cand_d, int k,
                     int32_t *vals2, float *dists);
 abx_status pairWithRank(cudaStream_t s, int32_t const *indices, int64_t n, int rank, int32_t *out2);
@@ -437,6 +443,10 @@ abx_status spatialCrsBegin(SpatialCrsCall &c, abx_bvh *bvh, cudaStream_t s, int 
                            abx_policy const &policy, abx_alloc_fn alloc, void *user);
 abx_status spatialCrsEnd(SpatialCrsCall &c, int32_t **offsets_out, uint32_t **indices_out, int64_t *nnz_out,
                          bool sync_if_trivial = false);
+// End in two steps for a caller that places the rows itself: Wait blocks for the number of results (offsets are in
+// c.offsets); FillInto writes row i at out_offsets[i] of `values` (4-byte indices, or (index, pair_rank) pairs)
+abx_status spatialCrsWait(SpatialCrsCall &c, int64_t *nnz_out);
+abx_status spatialCrsFillInto(SpatialCrsCall &c, int64_t nnz, int32_t const *out_offsets, void *values, int pair_rank);
 abx_status spatialCrs(abx_bvh *bvh, cudaStream_t s, int pred_kind, void const *preds, int64_t q,
                       abx_policy const &policy, abx_alloc_fn alloc, void *user, int32_t **offsets_out,
                       uint32_t **indices_out, int64_t *nnz_out,

@@ -373,35 +373,6 @@ __global__ void compactPaddedRowsKernel(int64_t q, int k, int32_t const *__restr
 }
 
 // ---- compact (host) result form: indices + the list of entries owned by other ranks ----
-// spatial: local rows -> indices at their merged offsets (same walk as mergeLocalRowsKernel, 4-byte values)
-__global__ void __launch_bounds__(256)
-    compactLocalRowsKernel(int64_t q, int32_t const *__restrict__ local_off, uint32_t const *__restrict__ local_idx,
-                           int32_t const *__restrict__ out_off, uint32_t *__restrict__ out_idx)
-{
-  int const lane = threadIdx.x & 31;
-  int64_t const r0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
-  if (r0 >= q)
-    return;
-  int64_t const r = min(r0 + lane, q);
-  int const lo = local_off[r];
-  int const shift = (r < q ? out_off[r] : 0) - lo;
-  int const begin = __shfl_sync(0xffffffffu, lo, 0);
-  int const end = local_off[min(r0 + 32, q)];
-  for (int j = begin + lane; j - lane < end; j += 32)
-  {
-    int l = 0;
-#pragma unroll
-    for (int step = 16; step > 0; step >>= 1)
-    {
-      int const probe = __shfl_sync(0xffffffffu, lo, min(l + step, 31));
-      if (l + step < 32 && probe <= j)
-        l += step;
-    }
-    int const sh = __shfl_sync(0xffffffffu, shift, l);
-    if (j < end)
-      out_idx[j + sh] = local_idx[j];
-  }
-}
 // remote records (query id ascending) -> indices behind the local part of their rows + (position, rank) list
 __global__ void compactRemoteRowsKernel(int64_t m, int32_t const *__restrict__ ids, int2 const *__restrict__ vals,
                                         int32_t const *__restrict__ local_off, int32_t const *__restrict__ out_off,
@@ -828,7 +799,7 @@ abx_status distSpatial(abx_dist_tree *t, cudaStream_t s, int pred_kind, void con
       deviceFree(b, s);
     }
   };
-  Guard local_guard{s, local.offsets, nullptr};
+  Guard local_guard{s, local.offsets, nullptr}; // the local offsets are a library buffer (no allocator was passed)
   ABX_CUDA_TRY(cudaEventSynchronize(t->ev[1])); // the count matrix is on the host
   ExchangePlan fwd;
   fwd.fromMatrix(t->h_pin, R, t->rank);
@@ -880,13 +851,11 @@ abx_status distSpatial(abx_dist_tree *t, cudaStream_t s, int pred_kind, void con
     trace.mark("sort_received", x);
   }
   ABX_CUDA_TRY(cudaEventRecord(t->ev[2], x));
-  // the local query's own blocking point (nnz), then its compaction
-  int32_t *off_l = nullptr;
-  uint32_t *idx_l = nullptr;
+  // the local query's own blocking point (nnz); its rows are written straight into the merged result below
+  int32_t *const off_l = local.offsets;
   int64_t nnz_l = 0;
-  ABX_TRY(spatialCrsEnd(local, &off_l, &idx_l, &nnz_l));
+  ABX_TRY(spatialCrsWait(local, &nnz_l));
   trace.mark("local_end", s);
-  local_guard.b = idx_l;
   ABX_CUDA_TRY(cudaStreamWaitEvent(s, t->ev[2], 0)); // the remote records are in place
   // buffers taken under the side stream go back to it when this frame unwinds: not before the merge below (on s)
   // has read them
@@ -900,7 +869,9 @@ abx_status distSpatial(abx_dist_tree *t, cudaStream_t s, int pred_kind, void con
         cudaStreamWaitEvent(x, t->ev[0], 0);
     }
   } rejoin{t, s, x};
-  // 5. merge per query: local results first, then the remote ones
+  // 5. merge per query: local results first, then the remote ones.  The merged offsets come from the local counts
+  // and the remote ids; the local traversal's compaction writes its rows at those offsets (as pairs or as indices),
+  // the remote records are scattered behind them: no intermediate local CRS, no copy pass.
   int64_t const nnz = nnz_l + M;
   if (nnz >= (int64_t)1 << 31)
   {
@@ -915,29 +886,18 @@ abx_status distSpatial(abx_dist_tree *t, cudaStream_t s, int pred_kind, void con
   *nnz_out = nnz;
   if (n_remote)
     *n_remote = M;
-  if (!compact)
-  {
-    if (M == 0)
-    {
-      ABX_CUDA_TRY(cudaMemcpyAsync(off_v, off_l, sizeof(int32_t) * (size_t)(q + 1), cudaMemcpyDeviceToDevice, s));
-      return pairWithRank(s, (int32_t const *)idx_l, nnz_l, t->rank, (int32_t *)vals_v);
-    }
-    return mergeSorted(s, q, off_l, (int32_t const *)idx_l, t->rank, M, got_ids.ptr, rvals2.ptr, (int32_t *)off_v,
-                       (int32_t *)vals_v);
-  }
+  int const pair_rank = compact ? -1 : t->rank;
   if (M == 0)
   {
     ABX_CUDA_TRY(cudaMemcpyAsync(off_v, off_l, sizeof(int32_t) * (size_t)(q + 1), cudaMemcpyDeviceToDevice, s));
-    if (nnz_l > 0)
-      ABX_CUDA_TRY(cudaMemcpyAsync(vals_v, idx_l, sizeof(uint32_t) * (size_t)nnz_l, cudaMemcpyDeviceToDevice, s));
-    return ABX_OK;
+    return spatialCrsFillInto(local, nnz_l, nullptr, vals_v, pair_rank);
   }
+  ABX_TRY(mergeCounts(s, q, off_l, M, got_ids.ptr, (int32_t *)off_v));
+  ABX_TRY(spatialCrsFillInto(local, nnz_l, (int32_t const *)off_v, vals_v, pair_rank));
+  if (!compact)
+    return mergeRemoteRows(s, M, got_ids.ptr, rvals2.ptr, off_l, (int32_t const *)off_v, (int32_t *)vals_v);
   ABX_TRY(remote_pos->alloc((size_t)M, s));
   ABX_TRY(remote_rank->alloc((size_t)M, s));
-  ABX_TRY(mergeCounts(s, q, off_l, M, got_ids.ptr, (int32_t *)off_v));
-  if (q > 0)
-    ABX_LAUNCH(compactLocalRowsKernel, divUp(divUp(q, 32) * 32, 256), 256, 0, s, q, off_l, idx_l, (int32_t const *)off_v,
-               (uint32_t *)vals_v);
   ABX_LAUNCH(compactRemoteRowsKernel, divUp(M, 256), 256, 0, s, M, got_ids.ptr, (int2 const *)rvals2.ptr, off_l,
              (int32_t const *)off_v, (uint32_t *)vals_v, remote_pos->ptr, remote_rank->ptr);
   return ABX_OK;

@@ -56,8 +56,12 @@ __global__ void __launch_bounds__(kThreads, ABX_SPATIAL_MINB)
                   float4 const *__restrict__ leaf_tri, int n, float const *__restrict__ preds, int64_t q,
                   unsigned const *__restrict__ qperm, int limit, int32_t *__restrict__ counts,
                   int32_t const *__restrict__ offsets, uint32_t *__restrict__ indices, uint32_t *__restrict__ staging,
-                  Wide64 const *__restrict__ wide, unsigned const *__restrict__ wide_bad)
+                  Wide64 const *__restrict__ wide, unsigned const *__restrict__ wide_bad,
+                  int32_t const *__restrict__ out_offsets, int pair_rank)
 {
+  // out_offsets / pair_rank (fill and compact forms): rows start at out_offsets[qi] instead of offsets[qi] (their
+  // lengths still come from `offsets`), and values are written as (index, pair_rank) pairs -- DistributedTree writes
+  // the local rows straight into the merged result this way
   __shared__ unsigned squeue[(QCAP > 0 ? QCAP : 1) * kThreads];
   int64_t const t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   bool active = t < q; // deferred form: the whole warp stays for the converged leaf phase
@@ -66,14 +70,20 @@ __global__ void __launch_bounds__(kThreads, ABX_SPATIAL_MINB)
   int64_t const qi = active ? (qperm ? (int64_t)qperm[t] : t) : 0;
   int64_t base = 0;
   if (active && (MODE == MODE_FILL || MODE == MODE_COMPACT))
-    base = (int64_t)offsets[qi];
+    base = (int64_t)(out_offsets ? out_offsets[qi] : offsets[qi]);
+  auto put = [&](int64_t pos, unsigned orig) {
+    if (pair_rank >= 0)
+      reinterpret_cast<int2 *>(indices)[pos] = make_int2((int)orig, pair_rank);
+    else
+      indices[pos] = orig;
+  };
   if (active && MODE == MODE_COMPACT)
   {
-    int const c = offsets[qi + 1] - (int)base;
+    int const c = offsets[qi + 1] - offsets[qi];
     if (c <= kStage)
     {
       for (int s = 0; s < c; ++s)
-        indices[base + s] = staging[(size_t)qi * kStage + s];
+        put(base + s, staging[(size_t)qi * kStage + s]);
       active = false;
       if (QCAP == 0)
         return;
@@ -89,7 +99,7 @@ __global__ void __launch_bounds__(kThreads, ABX_SPATIAL_MINB)
     if (TRI && !triangleLeafTest<PRED>(pred, leaf_tri, pos))
       return false;
     if (MODE == MODE_FILL || MODE == MODE_COMPACT)
-      indices[base + count] = orig;
+      put(base + count, orig);
     if (MODE == MODE_STAGE && count < kStage)
       staging[(size_t)qi * kStage + count] = orig;
     ++count;
@@ -112,7 +122,8 @@ template <int PRED, int MODE>
 __global__ void __launch_bounds__(kThreads)
     spatialSingleLeafKernel(float4 const *__restrict__ leaf_box, float4 const *__restrict__ leaf_tri, int prim_kind,
                             float const *__restrict__ preds, int64_t q, int32_t *__restrict__ counts,
-                            int32_t const *__restrict__ offsets, uint32_t *__restrict__ indices)
+                            int32_t const *__restrict__ offsets, uint32_t *__restrict__ indices,
+                            int32_t const *__restrict__ out_offsets, int pair_rank)
 {
   int64_t const qi = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (qi >= q)
@@ -126,7 +137,13 @@ __global__ void __launch_bounds__(kThreads)
   if (MODE == MODE_COUNT)
     counts[qi] = hit ? 1 : 0;
   else if (hit)
-    indices[offsets[qi]] = 0u;
+  {
+    int64_t const pos = out_offsets ? out_offsets[qi] : offsets[qi];
+    if (pair_rank >= 0)
+      reinterpret_cast<int2 *>(indices)[pos] = make_int2(0, pair_rank);
+    else
+      indices[pos] = 0u;
+  }
 }
 
 // ---- nearest ---------------------------------------------------------------------
@@ -789,7 +806,8 @@ __global__ void clipKKernel(int32_t const *__restrict__ k_per_query, int k_unifo
 template <int MODE>
 abx_status spatialLaunch(cudaStream_t s, abx_bvh *t, int pred_kind, void const *preds, int64_t q,
                          uint32_t const *qperm, int32_t limit, int32_t *counts, int32_t const *offsets,
-                         uint32_t *indices, uint32_t *staging = nullptr)
+                         uint32_t *indices, uint32_t *staging = nullptr, int32_t const *out_offsets = nullptr,
+                         int pair_rank = -1)
 {
   if (q <= 0)
     return ABX_OK;
@@ -820,7 +838,8 @@ abx_status spatialLaunch(cudaStream_t s, abx_bvh *t, int pred_kind, void const *
     // one leaf: the count and fill forms are all that is needed (no staging)
     constexpr int M1 = (MODE == MODE_COUNT || MODE == MODE_STAGE) ? MODE_COUNT : MODE_FILL;
     ABX_DISPATCH_PRED(pred_kind, ABX_LAUNCH((spatialSingleLeafKernel<P, M1>), grid, kThreads, 0, s, t->leaf_box,
-                                            t->leaf_tri, t->kind, (float const *)preds, q, counts, offsets, indices));
+                                            t->leaf_tri, t->kind, (float const *)preds, q, counts, offsets, indices,
+                                            out_offsets, pair_rank));
     return ABX_OK;
   }
   // tuning aid: ABX_SPATIAL_VARIANT picks (leaf-run size, deferred-queue slots); 0 slots = immediate leaf tests
@@ -836,12 +855,14 @@ abx_status spatialLaunch(cudaStream_t s, abx_bvh *t, int pred_kind, void const *
   ABX_DISPATCH_PRED(pred_kind,                                                                                         \
                     ABX_LAUNCH_TAGGED(tag, (spatialKernel<P, MODE, LF4, TRIFLAG, 4, 16, true>), grid, kThreads, 0, s,  \
                                       t->nodes, t->leaf_box, t->leaf_tri, n, (float const *)preds, q, qperm, limit,    \
-                                      counts, offsets, indices, staging, t->wide, t->wide_bad))
+                                      counts, offsets, indices, staging, t->wide, t->wide_bad, out_offsets,      \
+                                      pair_rank))
 #define ABX_SPATIAL_B(LF4, TRIFLAG, B, QC)                                                                            \
   ABX_DISPATCH_PRED(pred_kind, ABX_LAUNCH_TAGGED(tag, (spatialKernel<P, MODE, LF4, TRIFLAG, B, QC>), grid, kThreads,  \
                                                  0, s, t->nodes, t->leaf_box, t->leaf_tri, n, (float const *)preds,   \
                                                  q, qperm, limit, counts, offsets, indices, staging,                   \
-                                                 (Wide64 const *)nullptr, (unsigned const *)nullptr))
+                                                 (Wide64 const *)nullptr, (unsigned const *)nullptr, out_offsets,     \
+                                                 pair_rank))
 #ifdef ABX_TUNING
 #define ABX_SPATIAL_VARIANTS(LF4, TRIFLAG)                                                                            \
   switch (variant)                                                                                                     \
@@ -989,9 +1010,10 @@ abx_status spatialCount(cudaStream_t s, abx_bvh *t, int pred_kind, void const *p
 }
 
 abx_status spatialFill(cudaStream_t s, abx_bvh *t, int pred_kind, void const *preds, int64_t q, uint32_t const *qperm,
-                       int32_t const *offsets, uint32_t *indices)
+                       int32_t const *offsets, uint32_t *indices, int32_t const *out_offsets, int pair_rank)
 {
-  return spatialLaunch<MODE_FILL>(s, t, pred_kind, preds, q, qperm, 0, nullptr, offsets, indices);
+  return spatialLaunch<MODE_FILL>(s, t, pred_kind, preds, q, qperm, 0, nullptr, offsets, indices, nullptr, out_offsets,
+                                  pair_rank);
 }
 
 // single-traversal CRS: stage (count + keep first kStage results) ... scan ... compact
@@ -1002,10 +1024,11 @@ abx_status spatialStage(cudaStream_t s, abx_bvh *t, int pred_kind, void const *p
   return spatialLaunch<MODE_STAGE>(s, t, pred_kind, preds, q, qperm, 0, counts, nullptr, nullptr, staging);
 }
 abx_status spatialCompact(cudaStream_t s, abx_bvh *t, int pred_kind, void const *preds, int64_t q,
-                          uint32_t const *qperm, int32_t const *offsets, uint32_t *indices, uint32_t const *staging)
+                          uint32_t const *qperm, int32_t const *offsets, uint32_t *indices, uint32_t const *staging,
+                          int32_t const *out_offsets, int pair_rank)
 {
   return spatialLaunch<MODE_COMPACT>(s, t, pred_kind, preds, q, qperm, 0, nullptr, offsets, indices,
-                                     const_cast<uint32_t *>(staging));
+                                     const_cast<uint32_t *>(staging), out_offsets, pair_rank);
 }
 
 // uniform k: offsets == nullptr and rows start at i * min(k, n); per-query k:
@@ -1463,6 +1486,16 @@ abx_status mergeCounts(cudaStream_t s, int64_t q, int32_t const *local_off, int6
   if (m > 0)
     ABX_LAUNCH(mergeRemoteCountsKernel, divUp(m, 256), 256, 0, s, m, remote_ids, out_off);
   return exclusiveScanI32(s, out_off, out_off, q + 1);
+}
+
+// remote (index, rank) records, query id ascending, into the rows of a merged CRS behind their local parts
+abx_status mergeRemoteRows(cudaStream_t s, int64_t m, int32_t const *remote_ids, int32_t const *remote_vals2,
+                           int32_t const *local_off, int32_t const *out_off, int32_t *out_vals2)
+{
+  if (m > 0)
+    ABX_LAUNCH(mergeRemoteRowsKernel, divUp(m, 256), 256, 0, s, m, remote_ids, (int2 const *)remote_vals2, local_off,
+               out_off, (int2 *)out_vals2);
+  return ABX_OK;
 }
 
 abx_status mergeSorted(cudaStream_t s, int64_t q, int32_t const *local_off, int32_t const *local_idx, int rank,
