@@ -1677,8 +1677,30 @@ abx_status distDbscan(abx_comm *comm, cudaStream_t s, float const *xyz, int64_t 
     ABX_CUDA_TRY(cudaMemcpyAsync(unified.ptr, xyz, sizeof(float) * 3 * n, cudaMemcpyDeviceToDevice, s));
   if (G > 0)
     ABX_CUDA_TRY(cudaMemcpyAsync(unified.ptr + 3 * n, ghost_pts.ptr, sizeof(float) * 3 * G, cudaMemcpyDeviceToDevice, s));
-  if (n_all > 0)
-    ABX_TRY(dbscan(s, unified.ptr, n_all, eps, minpts, impl, algo, local_labels.ptr, core.ptr));
+  // The local clustering can fail on one rank alone (the DenseBox precision guard looks at the rank's own bounds,
+  // an allocation can fail): the ranks agree on the outcome before the next collective, so that nobody is left
+  // waiting in it.
+  abx_status const local_st =
+      n_all > 0 ? dbscan(s, unified.ptr, n_all, eps, minpts, impl, algo, local_labels.ptr, core.ptr) : ABX_OK;
+  {
+    TempBuffer<uint32_t> st_dev, st_all;
+    ABX_TRY(st_dev.alloc(1, s));
+    ABX_TRY(st_all.alloc((size_t)R, s));
+    uint32_t const word = (uint32_t)local_st;
+    ABX_CUDA_TRY(cudaMemcpyAsync(st_dev.ptr, &word, sizeof(word), cudaMemcpyHostToDevice, s));
+    ABX_TRY(comm->allGather(st_dev.ptr, st_all.ptr, sizeof(uint32_t), s));
+    ABX_CUDA_TRY(cudaMemcpyAsync(t.h_pin, st_all.ptr, sizeof(uint32_t) * R, cudaMemcpyDeviceToHost, s));
+    ABX_CUDA_TRY(cudaStreamSynchronize(s));
+    if (local_st != ABX_OK)
+      return local_st; // this rank's own message stands
+    for (int r = 0; r < R; ++r)
+      if (t.h_pin[r] != (uint32_t)ABX_OK)
+      {
+        setError("distributed dbscan: rank " + std::to_string(r) + " failed in its local clustering (status " +
+                 std::to_string(t.h_pin[r]) + ")");
+        return (abx_status)t.h_pin[r];
+      }
+  }
 
   // 4. local -> global labels
   TempBuffer<int32_t> seg;

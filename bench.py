@@ -319,8 +319,16 @@ def pin_to_gpu_numa_node(local_rank):
     end-to-end copies of the N ranks do not all cross one socket's memory controller."""
     try:
         import pynvml
+        import torch
         pynvml.nvmlInit()
-        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        try:
+            # the CUDA ordinal is not the NVML index when CUDA_VISIBLE_DEVICES is set: go through the PCI address
+            p = torch.cuda.get_device_properties(local_rank)
+            handle = pynvml.nvmlDeviceGetHandleByPciBusId(
+                ("%08x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)).encode())
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
         return True
     except Exception:
         return False
@@ -338,7 +346,10 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback")
-    numa_pinned = pin_to_gpu_numa_node(local_rank) if world > 1 else False
+    # host threads next to the GPU for the device and end-to-end legs (pinned buffers are allocated from here on);
+    # the full mask comes back before any CPU-arm work so that the OpenMP restatement sees every core
+    full_affinity = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    numa_pinned = False if os.environ.get("ABX_BENCH_NO_PIN") else pin_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -485,6 +496,8 @@ def run_ours(args):
     del d_values, d_queries, d_spheres, p_spatial, p_nearest
     abx.trim()
 
+    if full_affinity is not None:
+        os.sched_setaffinity(0, full_affinity)
     peak, peak_src, _ = peaks()
     traffic = traffic_table()
 
@@ -587,8 +600,8 @@ def run_ours(args):
                 "api": ("abx_dist_create_host + abx_dist_query_spatial_crs_host + abx_dist_query_nearest_crs_host "
                         "(compact results; numa_pinned=%s)" % numa_pinned) if world > 1 else
                        ("abx_bvh_build_host + abx_query_spatial_crs_host + abx_query_nearest_crs_host (each query "
-                        "batch as %d host calls, issued from %d host threads / streams)"
-                        % (args.e2e_chunks, args.e2e_threads))},
+                        "batch as %d host calls, issued from %d host threads / streams; numa_pinned=%s)"
+                        % (args.e2e_chunks, args.e2e_threads, numa_pinned))},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
