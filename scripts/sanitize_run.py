@@ -78,4 +78,59 @@ lab = ddbscan(dist.group.WORLD, space, torch.from_numpy(cl).cuda(), 6.0, 5)
 torch.cuda.synchronize()
 dist.destroy_process_group()
 print("ok distributed", int(o[-1]), int(ko[-1]))
+# round-2 kernel families: rays over triangles (leaves tested without a box), nearest(geometry), BruteForce, MST /
+# dendrogram, and the multi-rank exchange with in-process ranks
+rays = clouds.ball_rays(7, 4000)
+v_ico, t_ico = clouds.icosphere(4)
+soup = clouds.triangle_soup(v_ico, t_ico)
+tb = abx.BoundingVolumeHierarchy(space, torch.from_numpy(soup).cuda(), abx.TRIANGLE)
+ridx, roff = tb.query(space, abx.intersects(torch.from_numpy(rays).cuda(), abx.RAY_PRED))
+o_off, _ = oracle.Tree(soup, oracle.PRIM_TRI).spatial_crs(rays, oracle.PRED_RAY)
+assert np.array_equal(roff.cpu().numpy(), o_off)
+bb = abx.BoundingVolumeHierarchy(space, torch.from_numpy(prim_boxes).cuda(), 1)
+gq = np.concatenate([qp[:2000] - F(0.5), qp[:2000] + F(0.5)], 1)
+gi, go, gd = bb.query(space, abx.nearest(torch.from_numpy(gq).cuda(), 5, kind=abx.BOX_PRED),
+                      return_distances=True)
+brute = abx.BruteForce(space, torch.from_numpy(pts[:5000]).cuda())
+bi, bo = brute.query(space, abx.intersects(torch.from_numpy(spheres[:3000]).cuda()))
+ki, ko2 = brute.query(space, abx.nearest(torch.from_numpy(qp[:3000]).cuda(), 6))
+print("ok rays / nearest(geometry) / brute force", int(roff[-1]), int(go[-1]), int(bo[-1]))
+for k in (1, 4):
+    mst = abx.MinimumSpanningTree(space, torch.from_numpy(cl).cuda(), k)
+    e, w = oracle.mst(cl, k)
+    assert np.array_equal(np.sort(mst.weights.cpu().numpy()), np.sort(w)), k
+d = abx.hdbscan(space, torch.from_numpy(cl[:5000]).cuda(), 3)
+torch.cuda.synchronize()
+print("ok mst / hdbscan", mst.iterations)
+
+import threading  # noqa: E402
+from arborx_b200.distributed import Communicator  # noqa: E402
+from arborx_b200.distributed_dbscan import dbscan as ddbscan2  # noqa: E402
+world = 3
+comms = Communicator.local_group(world)
+errs = [None] * world
+
+
+def worker(rk):
+    try:
+        torch.cuda.set_device(0)
+        sp = abx.ExecutionSpace(torch.cuda.Stream())
+        with torch.cuda.stream(sp.stream):
+            mine = torch.from_numpy(np.ascontiguousarray(pts[rk::world])).cuda()
+            tr = DistributedTree(comms[rk], sp, mine)
+            tr.query(sp, abx.intersects(torch.from_numpy(np.ascontiguousarray(spheres[rk::world])).cuda()))
+            tr.query(sp, abx.nearest(torch.from_numpy(np.ascontiguousarray(qp[rk::world])).cuda(), 7), return_distances=True)
+            tr.query(sp, abx.nearest(torch.from_numpy(np.ascontiguousarray(qp[rk::world])), 7))  # host form
+            ddbscan2(comms[rk], sp, torch.from_numpy(np.ascontiguousarray(cl[rk::world])).cuda(), 6.0, 5)
+            sp.fence()
+    except BaseException:
+        import traceback
+        errs[rk] = traceback.format_exc()
+
+
+ths = [threading.Thread(target=worker, args=(rk,), daemon=True) for rk in range(world)]
+[t.start() for t in ths]
+[t.join(timeout=600) for t in ths]
+assert not any(t.is_alive() for t in ths) and not any(errs), errs
+print("ok in-process ranks")
 print("SANITIZE RUN OK")
