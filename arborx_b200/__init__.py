@@ -22,7 +22,7 @@ _PRED_STRIDE = {SPHERE_PRED: 4, BOX_PRED: 6, POINT_PRED: 3, RAY_PRED: 6}
 
 __all__ = ["ExecutionSpace", "BoundingVolumeHierarchy", "BVH", "TraversalPolicy", "HostBufferPool", "BruteForce", "intersects", "nearest",
            "make_intersects", "make_nearest", "query", "dbscan", "DBSCANParameters", "SearchException",
-           "MinimumSpanningTree", "Dendrogram", "hdbscan",
+           "MinimumSpanningTree", "Dendrogram", "hdbscan", "DENDROGRAM_BORUVKA", "DENDROGRAM_UNION_FIND",
            "POINT", "BOX", "TRIANGLE", "launch_count"]
 
 
@@ -462,19 +462,38 @@ def dbscan(space, primitives, eps, core_min_size, parameters=None):
     return labels
 
 
+DENDROGRAM_BORUVKA, DENDROGRAM_UNION_FIND = 0, 1  # DendrogramImplementation (cluster/ArborX_Dendrogram.hpp:24-28)
+
+
 class MinimumSpanningTree:
     """ArborX::Experimental::MinimumSpanningTree(space, points, k = 1) (cluster/ArborX_MinimumSpanningTree.hpp:
     31-101): `.edges` int32 [n - 1, 2] (source, target) in the caller's indices and `.weights` float32 [n - 1] --
     Euclidean for k = 1, mutual reachability for k > 1.  Device points give device results, host points pinned
-    host results.  The order of the edges is unspecified (sort before comparing, as the reference's tests do)."""
+    host results.  The order of the edges is unspecified (sort before comparing, as the reference's tests do).
+    mode="hdbscan" is BoruvkaMode::HDBSCAN (device points only): the edges come in the hybrid algorithm's (chain,
+    weight) order and `.dendrogram_parents` [2 n - 1] / `.dendrogram_parent_heights` [n - 1] index that order."""
 
-    def __init__(self, space, points, k=1):
+    def __init__(self, space, points, k=1, mode="mst"):
         x = _as_f32(points, 3)
         n = x.shape[0]
         m = max(n - 1, 0)
         it = C.c_int32(0)
         L = lib()
         with torch.cuda.stream(space.stream):
+            if mode == "hdbscan":
+                assert x.is_cuda and n >= 1
+                self.edges = torch.empty((m, 2), dtype=torch.int32, device=space.device)
+                self.weights = torch.empty(m, dtype=torch.float32, device=space.device)
+                self.dendrogram_parents = torch.empty(2 * n - 1, dtype=torch.int32, device=space.device)
+                self.dendrogram_parent_heights = torch.empty(m, dtype=torch.float32, device=space.device)
+                _lib.check(L.abx_mst_hdbscan_points3f(space.handle, C.c_void_p(x.data_ptr()), n, int(k),
+                                                      C.c_void_p(self.edges.data_ptr()),
+                                                      C.c_void_p(self.weights.data_ptr()),
+                                                      C.c_void_p(self.dendrogram_parents.data_ptr()),
+                                                      C.c_void_p(self.dendrogram_parent_heights.data_ptr()),
+                                                      C.byref(it)))
+                self.iterations = int(it.value)
+                return
             if x.is_cuda:
                 self.edges = torch.empty((m, 2), dtype=torch.int32, device=space.device)
                 self.weights = torch.empty(m, dtype=torch.float32, device=space.device)
@@ -506,9 +525,10 @@ class Dendrogram:
                                                        C.c_void_p(self._parent_heights.data_ptr())))
 
 
-def hdbscan(space, primitives, core_min_size):
-    """ArborX::Experimental::hdbscan(space, primitives, core_min_size, DendrogramImplementation::UNION_FIND)
-    (cluster/ArborX_HDBSCAN.hpp:29-53) -> Dendrogram-like object with `_parents`, `_parent_heights`."""
+def hdbscan(space, primitives, core_min_size, dendrogram_impl=DENDROGRAM_BORUVKA):
+    """ArborX::Experimental::hdbscan(space, primitives, core_min_size, dendrogram_impl = BORUVKA)
+    (cluster/ArborX_HDBSCAN.hpp:29-53) -> Dendrogram-like object with `_parents`, `_parent_heights` (BORUVKA: edges
+    in the hybrid algorithm's order, all on the device; UNION_FIND: edges in ascending weight order)."""
     x = _as_f32(primitives, 3)
     assert x.is_cuda
     n = x.shape[0]
@@ -520,7 +540,7 @@ def hdbscan(space, primitives, core_min_size):
     d._parent_heights = torch.empty(max(n - 1, 0), dtype=torch.float32, device=space.device)
     with torch.cuda.stream(space.stream):
         _lib.check(lib().abx_hdbscan_points3f(space.handle, C.c_void_p(x.data_ptr()), n, int(core_min_size),
-                                              C.c_void_p(d._parents.data_ptr()),
+                                              int(dendrogram_impl), C.c_void_p(d._parents.data_ptr()),
                                               C.c_void_p(d._parent_heights.data_ptr())))
     return d
 

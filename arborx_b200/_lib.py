@@ -65,7 +65,8 @@ SIGNATURES = {
     "abx_mst_points3f": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "abx_mst_points3f_host": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "abx_dendrogram_union_find": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
-    "abx_hdbscan_points3f": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
+    "abx_hdbscan_points3f": (C.c_int, [_vp, _vp, _i64, _i32, C.c_int, _vp, _vp]),
+    "abx_mst_hdbscan_points3f": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
     "abx_dist_merge_crs": (C.c_int, [_vp, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "abx_bvh_device_view": (C.c_int, [_vp, _vp]),
     "abx_dist_merge_sorted": (C.c_int, [_vp, _i64, _vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp]),

@@ -462,8 +462,11 @@ abx_status ensureDevice();
 abx_status dbscan(cudaStream_t s, float const *xyz, int64_t n, float eps, int32_t minpts, int impl, int algo,
                   int32_t *labels, int32_t *core_flags = nullptr);
 // mst.cu
+// dendrogram_parents != nullptr: BoruvkaMode::HDBSCAN -- edges in (chain, weight) order, parents [2 n - 1] and
+// heights [n - 1] of the dendrogram over them
 abx_status minimumSpanningTree(cudaStream_t s, float const *xyz, int64_t n, int32_t k, int32_t *edges2, float *weights,
-                               int *iterations);
+                               int *iterations, int32_t *dendrogram_parents = nullptr,
+                               float *dendrogram_heights = nullptr);
 abx_status dendrogramUnionFind(cudaStream_t s, int32_t const *edges2, float const *weights, int64_t m, int32_t *parents,
                                float *heights);
 } // namespace abx

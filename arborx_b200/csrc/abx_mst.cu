@@ -15,7 +15,10 @@
 //   cluster/ArborX_Dendrogram.hpp:47-76 + detail/ArborX_DendrogramHelpers.hpp:31-80   UNION_FIND dendrogram: edges
 //       sorted by weight on the device, the union-find loop itself on the host (in the reference as well: it is a
 //       sequential algorithm)
-//   cluster/ArborX_HDBSCAN.hpp:29-53                hdbscan(space, points, core_min_size) = MST(k) + dendrogram
+//   cluster/ArborX_HDBSCAN.hpp:29-53                hdbscan(space, points, core_min_size, implementation): BORUVKA =
+//       MinimumSpanningTree in HDBSCAN mode, which grows the dendrogram with the rounds and never leaves the device
+//       (MinimumSpanningTree.hpp:176-230,266-297, BoruvkaHelpers.hpp:439-447,490-733); UNION_FIND = MST(k) + the
+//       dendrogram above
 //
 // Under the strict edge order above the minimum spanning tree is unique, so the edge SET is comparable bit for bit
 // with the reference's (the leaf positions are: the trees are bit-identical); the order of the
@@ -272,8 +275,16 @@ __global__ void componentEdgeKernel(int n, int const *__restrict__ lab_leaf, uns
 __device__ __forceinline__ int nextComponent(int c, int const *__restrict__ lab_leaf,
                                              unsigned long long const *__restrict__ comp_key)
 {
-  int const next = lab_leaf[keyTarget(comp_key[c])];
-  int const next_next = lab_leaf[keyTarget(comp_key[next])];
+  // a component without an outgoing edge (possible only with non-finite coordinates) stays where it is: the
+  // round then merges nothing and the host reports it
+  unsigned long long const kc = comp_key[c];
+  if (kc == ~0ull)
+    return c;
+  int const next = lab_leaf[keyTarget(kc)];
+  unsigned long long const kn = comp_key[next];
+  if (kn == ~0ull)
+    return next;
+  int const next_next = lab_leaf[keyTarget(kn)];
   return next_next != c ? next : min(c, next);
 }
 
@@ -281,7 +292,8 @@ __device__ __forceinline__ int nextComponent(int c, int const *__restrict__ lab_
 __global__ void appendEdgesKernel(int n, int const *__restrict__ lab_leaf,
                                   unsigned long long const *__restrict__ comp_key,
                                   unsigned const *__restrict__ comp_w, int *__restrict__ num_edges,
-                                  int2 *__restrict__ edge_pos, float *__restrict__ weights)
+                                  int2 *__restrict__ edge_pos, float *__restrict__ weights,
+                                  int *__restrict__ edges_mapping /* HDBSCAN mode: component -> its edge, or null */)
 {
   int const i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n || lab_leaf[i] != i)
@@ -292,6 +304,8 @@ __global__ void appendEdgesKernel(int n, int const *__restrict__ lab_leaf,
   unsigned long long const key = comp_key[i];
   edge_pos[e] = make_int2(keySource(key), keyTarget(key));
   weights[e] = __uint_as_float(comp_w[i]);
+  if (edges_mapping)
+    edges_mapping[i] = e;
 }
 
 // LabelsTag (:415-420) into a second array (the reference updates in place; the chains it follows end at the same
@@ -350,11 +364,179 @@ __global__ void weightBitsKernel(int64_t m, float const *__restrict__ w, unsigne
   bits[e] = b == 0x80000000u ? 0u : b;
 }
 
+// ---- BoruvkaMode::HDBSCAN: the dendrogram grows with the rounds (MinimumSpanningTree.hpp:176-230,266-297) -----------
+constexpr int kRootChain = -2;   // BoruvkaHelpers.hpp:34
+constexpr int kFollowChain = -3; // :35
+
+// WeightedEdge order (WeightedEdge.hpp:30-50): weight, smaller vertex, larger vertex -- vertices are leaf positions here
+__device__ __forceinline__ bool edgeLess(float wa, int2 a, float wb, int2 b)
+{
+  if (wa != wb)
+    return wa < wb;
+  int const amin = min(a.x, a.y), bmin = min(b.x, b.y);
+  if (amin != bmin)
+    return amin < bmin;
+  return max(a.x, a.y) < max(b.x, b.y);
+}
+
+// BidirectionalEdgesTag (BoruvkaHelpers.hpp:439-447): of two components that chose each other only the larger label
+// appended the edge; the smaller one takes its index from the partner
+__global__ void sharedEdgeMappingKernel(int n, int const *__restrict__ lab_leaf,
+                                        unsigned long long const *__restrict__ comp_key, int *edges_mapping)
+{
+  int const i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || lab_leaf[i] != i)
+    return;
+  if (comp_key[i] == ~0ull || nextComponent(i, lab_leaf, comp_key) != i)
+    return;
+  edges_mapping[i] = edges_mapping[lab_leaf[keyTarget(comp_key[i])]];
+}
+
+// assignVertexParents (:527-548), first round: every vertex is a component, its parent is the edge it picked
+__global__ void vertexParentsKernel(int n, int const *__restrict__ lab_leaf,
+                                    unsigned long long const *__restrict__ comp_key,
+                                    int const *__restrict__ edges_mapping, uint32_t const *__restrict__ perm,
+                                    int *__restrict__ parents)
+{
+  int const e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n || comp_key[e] == ~0ull)
+    return;
+  int const i = lab_leaf[keySource(comp_key[e])];
+  parents[(int)perm[i] + (n - 1)] = edges_mapping[i];
+}
+
+// updateSidedParents (:490-525): the edges of the previous round hang below the edge their (merged) component picks
+// in this round -- on its source or its target side -- or, when they are heavier than it, follow its chain upwards
+__global__ void sidedParentsKernel(int first, int last, int const *__restrict__ lab_leaf,
+                                   int2 const *__restrict__ edge_pos, float const *__restrict__ weights,
+                                   int const *__restrict__ edges_mapping, int *__restrict__ sided_parents)
+{
+  int const e = first + blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= last)
+    return;
+  int2 const edge = edge_pos[e];
+  int const component = lab_leaf[edge.x];
+  int const alpha = edges_mapping[component];
+  int2 const alpha_edge = edge_pos[alpha];
+  if (edgeLess(weights[e], edge, weights[alpha], alpha_edge))
+    sided_parents[e] = 2 * alpha + (lab_leaf[alpha_edge.x] == component ? 1 : 0);
+  else
+    sided_parents[e] = kFollowChain - alpha;
+}
+
+// computeParentsAndReorderEdges (:550-733), step 1: (sided parent, weight) in one 64-bit key
+__global__ void chainKeysKernel(int m, int const *__restrict__ sided_parents, int2 const *__restrict__ edge_pos,
+                                float const *__restrict__ weights, unsigned long long *__restrict__ keys)
+{
+  int const e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= m)
+    return;
+  long long key = sided_parents[e];
+  if (key <= kFollowChain)
+  {
+    int2 const edge = edge_pos[e];
+    float const w = weights[e];
+    int next = kFollowChain - (int)key;
+    while (true)
+    {
+      key = sided_parents[next];
+      if (key <= kFollowChain)
+        next = kFollowChain - (int)key;
+      else if (key >= 0)
+      {
+        next = (int)(key / 2);
+        if (edgeLess(w, edge, weights[next], edge_pos[next]))
+          break;
+      }
+      else if (key == kRootChain)
+        break;
+    }
+  }
+  if (key == kRootChain)
+    key = 0x7fffffff;
+  keys[e] = ((unsigned long long)key << 32) | (unsigned long long)__float_as_uint(weights[e]);
+}
+
+// step 2 (:625-660): within a chain the smallest edge goes first even among equal weights, so that no edge ends up
+// with three children
+__global__ void fixSameWeightOrderKernel(int m, unsigned long long const *__restrict__ keys, uint32_t *permute,
+                                         int2 const *__restrict__ edge_pos, float const *__restrict__ weights)
+{
+  int const i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m - 1)
+    return;
+  unsigned long long const key = keys[i];
+  if (i != 0 && (keys[i - 1] >> 32) == (key >> 32))
+    return;
+  int best = i;
+  for (int k = i + 1; k < m && keys[k] == key; ++k)
+  {
+    uint32_t const a = permute[k], b = permute[best];
+    if (edgeLess(weights[a], edge_pos[a], weights[b], edge_pos[b]))
+      best = k;
+  }
+  if (best != i)
+  {
+    uint32_t const tmp = permute[i];
+    permute[i] = permute[best];
+    permute[best] = tmp;
+  }
+}
+
+__global__ void inversePermutationKernel(int m, uint32_t const *__restrict__ permute, int *__restrict__ rev)
+{
+  int const i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m)
+    rev[permute[i]] = i;
+}
+
+// steps 3-5 (:662-712): parents of the vertices and of the edges in the new edge order, the edges themselves
+__global__ void dendrogramParentsKernel(int n, unsigned long long const *__restrict__ keys,
+                                        uint32_t const *__restrict__ permute, int const *__restrict__ rev,
+                                        int2 const *__restrict__ edge_pos, float const *__restrict__ weights,
+                                        uint32_t const *__restrict__ perm, int *__restrict__ parents,
+                                        int2 *__restrict__ edges_out, float *__restrict__ weights_out,
+                                        float *__restrict__ heights)
+{
+  int const m = n - 1;
+  int const i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    parents[m + i] = rev[parents[m + i]];
+  if (i >= m)
+    return;
+  if (i == m - 1)
+    parents[i] = -1;
+  else if ((keys[i] >> 32) == (keys[i + 1] >> 32))
+    parents[i] = i + 1;
+  else
+    parents[i] = rev[(int)((keys[i] >> 32) / 2)];
+  uint32_t const old = permute[i];
+  int2 const p = edge_pos[old];
+  float const w = weights[old];
+  edges_out[i] = make_int2((int)perm[p.x], (int)perm[p.y]); // finalizeEdges (:472-488)
+  weights_out[i] = w;
+  heights[i] = w; // MinimumSpanningTree.hpp:288-295
+}
+
 template <bool MUTUAL>
-abx_status boruvka(cudaStream_t s, abx_bvh *t, float const *core_pos, int2 *edges, float *weights, int *iterations)
+abx_status boruvka(cudaStream_t s, abx_bvh *t, float const *core_pos, int2 *edges, float *weights_out, int *iterations,
+                   int *dendrogram_parents, float *dendrogram_heights)
 {
   int const n = (int)t->n;
   int const grid = divUp(n, 256);
+  // HDBSCAN mode: the rounds also record which edge every component picked; the edges leave in (chain, weight) order
+  bool const hd = dendrogram_parents != nullptr;
+  TempBuffer<int> edges_mapping, sided_parents;
+  TempBuffer<float> round_weights;
+  float *weights = weights_out;
+  if (hd)
+  {
+    ABX_TRY(edges_mapping.alloc((size_t)n, s));
+    ABX_TRY(sided_parents.alloc((size_t)n, s));
+    ABX_TRY(round_weights.alloc((size_t)n, s));
+    weights = round_weights.ptr; // append order here, reordered into weights_out at the end
+  }
+  int edges_start = 0, edges_end = 0;
   TempBuffer<int> par_int, par_leaf, lab_a, lab_b, lab_int, num_edges;
   TempBuffer<unsigned> comp_w, radii, best_w;
   TempBuffer<unsigned long long> comp_key, best_key;
@@ -389,7 +571,17 @@ abx_status boruvka(cudaStream_t s, abx_bvh *t, float const *core_pos, int2 *edge
                       best_key.ptr);
     ABX_LAUNCH(componentEdgeKernel, grid, 256, 0, s, n, lab, comp_w.ptr, best_w.ptr, best_key.ptr, comp_key.ptr);
     ABX_LAUNCH(appendEdgesKernel, grid, 256, 0, s, n, lab, comp_key.ptr, comp_w.ptr, num_edges.ptr, edge_pos.ptr,
-               weights);
+               weights, hd ? edges_mapping.ptr : (int *)nullptr);
+    if (hd)
+    {
+      ABX_LAUNCH(sharedEdgeMappingKernel, grid, 256, 0, s, n, lab, comp_key.ptr, edges_mapping.ptr);
+      if (rounds == 1)
+        ABX_LAUNCH(vertexParentsKernel, grid, 256, 0, s, n, lab, comp_key.ptr, edges_mapping.ptr, t->perm,
+                   dendrogram_parents);
+      else if (edges_end > edges_start)
+        ABX_LAUNCH(sidedParentsKernel, divUp(edges_end - edges_start, 256), 256, 0, s, edges_start, edges_end, lab,
+                   edge_pos.ptr, weights, edges_mapping.ptr, sided_parents.ptr);
+    }
     ABX_LAUNCH(updateLabelsKernel, grid, 256, 0, s, n, lab, comp_key.ptr, lab_next);
     int h_edges = 0;
     ABX_CUDA_TRY(cudaMemcpyAsync(&h_edges, num_edges.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -402,10 +594,33 @@ abx_status boruvka(cudaStream_t s, abx_bvh *t, float const *core_pos, int2 *edge
       return ABX_ERR_ARG;
     }
     components = left;
+    edges_start = edges_end;
+    edges_end = h_edges;
   }
-  ABX_LAUNCH(finalizeEdgesKernel, divUp(n - 1, 256), 256, 0, s, (int64_t)n - 1, edge_pos.ptr, t->perm, edges);
   if (iterations)
     *iterations = rounds;
+  if (!hd)
+  {
+    ABX_LAUNCH(finalizeEdgesKernel, divUp(n - 1, 256), 256, 0, s, (int64_t)n - 1, edge_pos.ptr, t->perm, edges);
+    return ABX_OK;
+  }
+  // the edges of the last round form the root chain (MinimumSpanningTree.hpp:271-275)
+  int const m = n - 1;
+  if (edges_end > edges_start)
+    ABX_LAUNCH(fillIntKernel, divUp(edges_end - edges_start, 256), 256, 0, s, sided_parents.ptr + edges_start,
+               (int64_t)(edges_end - edges_start), kRootChain);
+  TempBuffer<unsigned long long> keys;
+  TempBuffer<uint32_t> permute;
+  TempBuffer<int> rev;
+  ABX_TRY(keys.alloc((size_t)m, s));
+  ABX_TRY(permute.alloc((size_t)m, s));
+  ABX_TRY(rev.alloc((size_t)m, s));
+  ABX_LAUNCH(chainKeysKernel, divUp(m, 256), 256, 0, s, m, sided_parents.ptr, edge_pos.ptr, weights, keys.ptr);
+  ABX_TRY(sortPairsU64(s, (uint64_t *)keys.ptr, permute.ptr, m, true, 63));
+  ABX_LAUNCH(fixSameWeightOrderKernel, divUp(m, 256), 256, 0, s, m, keys.ptr, permute.ptr, edge_pos.ptr, weights);
+  ABX_LAUNCH(inversePermutationKernel, divUp(m, 256), 256, 0, s, m, permute.ptr, rev.ptr);
+  ABX_LAUNCH(dendrogramParentsKernel, grid, 256, 0, s, n, keys.ptr, permute.ptr, rev.ptr, edge_pos.ptr, weights, t->perm,
+             dendrogram_parents, edges, weights_out, dendrogram_heights);
   return ABX_OK;
 }
 
@@ -413,10 +628,15 @@ abx_status boruvka(cudaStream_t s, abx_bvh *t, float const *core_pos, int2 *edge
 
 // edges2: (n - 1) x (source, target), weights: n - 1, both on the device
 abx_status minimumSpanningTree(cudaStream_t s, float const *xyz, int64_t n, int32_t k, int32_t *edges2, float *weights,
-                               int *iterations)
+                               int *iterations, int32_t *dendrogram_parents, float *dendrogram_heights)
 {
   if (iterations)
     *iterations = 0;
+  if (n == 1 && dendrogram_parents)
+  {
+    int const root = -1;
+    ABX_CUDA_TRY(cudaMemcpyAsync(dendrogram_parents, &root, sizeof(int), cudaMemcpyHostToDevice, s));
+  }
   if (n < 2)
     return ABX_OK;
   if (n >= (int64_t)1 << 30)
@@ -432,7 +652,7 @@ abx_status minimumSpanningTree(cudaStream_t s, float const *xyz, int64_t n, int3
     ~Guard() { abx_bvh_destroy(t); }
   } guard{tree};
   if (k <= 1)
-    return boruvka<false>(s, tree, nullptr, (int2 *)edges2, weights, iterations);
+    return boruvka<false>(s, tree, nullptr, (int2 *)edges2, weights, iterations, dendrogram_parents, dendrogram_heights);
   // core distances: nearest(point, k) of every point in the tree's own order (MinimumSpanningTree.hpp:70-81)
   int const stride = (int)std::min<int64_t>(k, n);
   TempBuffer<float> core_pos;
@@ -448,7 +668,8 @@ abx_status minimumSpanningTree(cudaStream_t s, float const *xyz, int64_t n, int3
     ABX_LAUNCH(coreDistanceKernel, divUp(n, 256), 256, 0, s, (int)n, tree->perm, dist.ptr, counts.ptr, stride,
                core_pos.ptr);
   }
-  return boruvka<true>(s, tree, core_pos.ptr, (int2 *)edges2, weights, iterations);
+  return boruvka<true>(s, tree, core_pos.ptr, (int2 *)edges2, weights, iterations, dendrogram_parents,
+                       dendrogram_heights);
 }
 
 // parents: 2 m + 1 entries (edges in ascending weight order first, then the m + 1 vertices); heights: m
@@ -600,13 +821,32 @@ abx_status abx_dendrogram_union_find(void *stream, const int32_t *edges2_dev, co
   return dendrogramUnionFind((cudaStream_t)stream, edges2_dev, weights_dev, num_edges, parents_dev, parent_heights_dev);
 }
 
-abx_status abx_hdbscan_points3f(void *stream, const float *xyz_dev, int64_t n, int32_t core_min_size,
-                                int32_t *parents_dev, float *parent_heights_dev)
+abx_status abx_mst_hdbscan_points3f(void *stream, const float *xyz_dev, int64_t n, int32_t k, int32_t *edges2_dev,
+                                    float *weights_dev, int32_t *parents_dev, float *parent_heights_dev,
+                                    int32_t *iterations)
 {
   ABX_TRY(ensureDevice());
-  if (n < 1 || core_min_size < 1 || !xyz_dev || !parents_dev || (n > 1 && !parent_heights_dev))
+  if (n < 1 || k < 1 || !xyz_dev || !parents_dev || (n > 1 && (!edges2_dev || !weights_dev || !parent_heights_dev)))
   {
-    setError("hdbscan: bad argument (n >= 1, core_min_size >= 1, non-null arrays)");
+    setError("MinimumSpanningTree (HDBSCAN mode): bad argument (n >= 1, k >= 1, non-null arrays)");
+    return ABX_ERR_ARG;
+  }
+  int it = 0;
+  abx_status const st = minimumSpanningTree((cudaStream_t)stream, xyz_dev, n, k, edges2_dev, weights_dev, &it,
+                                            parents_dev, parent_heights_dev);
+  if (iterations)
+    *iterations = it;
+  return st;
+}
+
+abx_status abx_hdbscan_points3f(void *stream, const float *xyz_dev, int64_t n, int32_t core_min_size,
+                                int dendrogram_impl, int32_t *parents_dev, float *parent_heights_dev)
+{
+  ABX_TRY(ensureDevice());
+  if (n < 1 || core_min_size < 1 || !xyz_dev || !parents_dev || (n > 1 && !parent_heights_dev) ||
+      (dendrogram_impl != ABX_DENDROGRAM_BORUVKA && dendrogram_impl != ABX_DENDROGRAM_UNION_FIND))
+  {
+    setError("hdbscan: bad argument (n >= 1, core_min_size >= 1, non-null arrays, a known dendrogram implementation)");
     return ABX_ERR_ARG;
   }
   cudaStream_t s = (cudaStream_t)stream;
@@ -614,6 +854,8 @@ abx_status abx_hdbscan_points3f(void *stream, const float *xyz_dev, int64_t n, i
   TempBuffer<int32_t> e;
   ABX_TRY(w.alloc((size_t)std::max<int64_t>(n - 1, 1), s));
   ABX_TRY(e.alloc(2 * (size_t)std::max<int64_t>(n - 1, 1), s));
+  if (dendrogram_impl == ABX_DENDROGRAM_BORUVKA) // HDBSCAN.hpp:41-47: the hybrid, all on the device
+    return minimumSpanningTree(s, xyz_dev, n, core_min_size, e.ptr, w.ptr, nullptr, parents_dev, parent_heights_dev);
   ABX_TRY(minimumSpanningTree(s, xyz_dev, n, core_min_size, e.ptr, w.ptr, nullptr));
   return dendrogramUnionFind(s, e.ptr, w.ptr, n - 1, parents_dev, parent_heights_dev);
 }

@@ -89,10 +89,16 @@ int main()
     total += w;
   std::printf("mst(k = 3): %zu edges, total weight %g, %d rounds\n", mw.size(), total, mst.iterations);
   ok = ok && mw.size() == 4 && total == 6.f;
-  auto dendrogram = Experimental::hdbscan(space, line, 3);
+  auto dendrogram = Experimental::hdbscan(space, line, 3, Experimental::DendrogramImplementation::UNION_FIND);
   auto dp = dendrogram._parents.to_host();
   auto dh = dendrogram._parent_heights.to_host();
   ok = ok && dp.size() == 9 && dh.size() == 4 && dp[3] == -1 && dh[0] == 1.f && dh[3] == 2.f;
+  auto hybrid = Experimental::hdbscan(space, line, 3); // BORUVKA: the dendrogram grows with the rounds, on the device
+  auto hp = hybrid._parents.to_host();
+  int roots = 0;
+  for (int i = 0; i < 4; ++i)
+    roots += hp[i] == -1;
+  ok = ok && hp.size() == 9 && roots == 1;
   std::printf(ok ? "FACADE OK\n" : "FACADE FAILED\n");
   return ok ? 0 : 1;
 }

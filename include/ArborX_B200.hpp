@@ -607,7 +607,7 @@ struct MinimumSpanningTree
 
 enum class DendrogramImplementation
 {
-  BORUVKA, // not provided: requests fall back to the exception below
+  BORUVKA,
   UNION_FIND
 };
 
@@ -628,16 +628,17 @@ struct Dendrogram
 };
 
 inline Dendrogram hdbscan(Cuda const &space, DeviceView<Point<>> const &primitives, int core_min_size,
-                          DendrogramImplementation impl = DendrogramImplementation::UNION_FIND)
+                          DendrogramImplementation impl = DendrogramImplementation::BORUVKA)
 {
-  if (impl != DendrogramImplementation::UNION_FIND)
-    throw std::invalid_argument("hdbscan: only DendrogramImplementation::UNION_FIND is provided");
   Dendrogram d;
   std::size_t const n = primitives.size();
   d._parents.realloc(n > 0 ? 2 * n - 1 : 0);
   d._parent_heights.realloc(n > 0 ? n - 1 : 0);
   Details::check(abx_hdbscan_points3f(space.cuda_stream(), reinterpret_cast<float const *>(primitives.data()),
-                                      (std::int64_t)n, core_min_size, d._parents.data(), d._parent_heights.data()));
+                                      (std::int64_t)n, core_min_size,
+                                      impl == DendrogramImplementation::BORUVKA ? ABX_DENDROGRAM_BORUVKA
+                                                                                : ABX_DENDROGRAM_UNION_FIND,
+                                      d._parents.data(), d._parent_heights.data()));
   return d;
 }
 } // namespace Experimental

@@ -230,12 +230,25 @@ ABX_API abx_status abx_mst_points3f_host(void *stream, const float *xyz_host, in
  * device; the union-find pass over them is sequential and runs on the host, as it does in the reference
  * (detail/ArborX_DendrogramHelpers.hpp:31-80).  parents_dev: 2 * num_edges + 1 entries -- the edges in ascending
  * weight order first, then the num_edges + 1 vertices; the root's parent is -1.  parent_heights_dev: num_edges
- * (the sorted weights).  The hybrid Boruvka dendrogram (DendrogramImplementation::BORUVKA) is not provided. */
+ * (the sorted weights). */
 ABX_API abx_status abx_dendrogram_union_find(void *stream, const int32_t *edges2_dev, const float *weights_dev,
                                              int64_t num_edges, int32_t *parents_dev, float *parent_heights_dev);
-/* cluster/ArborX_HDBSCAN.hpp:29-53 with DendrogramImplementation::UNION_FIND: MST(core_min_size) + dendrogram */
+/* MinimumSpanningTree<MemorySpace, BoruvkaMode::HDBSCAN> (cluster/ArborX_MinimumSpanningTree.hpp:31-297): the same
+ * rounds also record which edge every component picked, so the dendrogram is complete when the tree is
+ * (detail/ArborX_BoruvkaHelpers.hpp:439-447,490-733) -- no host pass.  The edges come out in the hybrid algorithm's
+ * (chain, weight) order; parents_dev [2 n - 1] (edges first, then the n vertices; root -> -1) and
+ * parent_heights_dev [n - 1] index that order, like the reference's dendrogram_parents / dendrogram_parent_heights. */
+ABX_API abx_status abx_mst_hdbscan_points3f(void *stream, const float *xyz_dev, int64_t n, int32_t k,
+                                            int32_t *edges2_dev, float *weights_dev, int32_t *parents_dev,
+                                            float *parent_heights_dev, int32_t *iterations);
+/* cluster/ArborX_HDBSCAN.hpp:29-53: hdbscan(space, primitives, core_min_size, dendrogram_impl) */
+enum
+{
+  ABX_DENDROGRAM_BORUVKA = 0,   /* the reference's default: the hybrid above */
+  ABX_DENDROGRAM_UNION_FIND = 1 /* MST(core_min_size), then abx_dendrogram_union_find */
+};
 ABX_API abx_status abx_hdbscan_points3f(void *stream, const float *xyz_dev, int64_t n, int32_t core_min_size,
-                                        int32_t *parents_dev, float *parent_heights_dev);
+                                        int dendrogram_impl, int32_t *parents_dev, float *parent_heights_dev);
 
 /* ---- device view for user callbacks (include/ArborX_B200_Callbacks.cuh) ----
  * The reference instantiates user callbacks inside its traversal templates

@@ -77,6 +77,7 @@ def lib():
         "orc_dbscan_verify": (C.c_int, [fp, C.c_int, C.c_float, C.c_int, ip, C.c_int]),
         "orc_mst": (C.c_int, [fp, C.c_int, C.c_int, ip, fp]),
         "orc_dendrogram_union_find": (None, [ip, fp, C.c_int, ip, fp]),
+        "orc_mst_hdbscan": (C.c_int, [fp, C.c_int, C.c_int, ip, fp, ip, fp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -292,3 +293,18 @@ def dendrogram(edges, weights):
     lib().orc_dendrogram_union_find(_p(edges, C.c_int), _p(weights, C.c_float), e, _p(parents, C.c_int),
                                     _p(heights, C.c_float))
     return parents, heights
+
+
+def mst_hdbscan(xyz, k=1):
+    """MinimumSpanningTree<..., BoruvkaMode::HDBSCAN> (ArborX_MinimumSpanningTree.hpp:31-297) -> (edges, weights,
+    dendrogram_parents [2 n - 1], dendrogram_parent_heights [n - 1]); the edges are in the hybrid algorithm's own
+    (chain, weight) order and the parents index that order."""
+    xyz = _f32(xyz).reshape(-1, 3)
+    n = xyz.shape[0]
+    edges = np.empty((max(n - 1, 0), 2), np.int32)
+    weights = np.empty(max(n - 1, 0), np.float32)
+    parents = np.full(max(2 * n - 1, 0), -1, np.int32)
+    heights = np.empty(max(n - 1, 0), np.float32)
+    lib().orc_mst_hdbscan(_p(xyz, C.c_float), n, int(k), _p(edges, C.c_int), _p(weights, C.c_float),
+                          _p(parents, C.c_int), _p(heights, C.c_float))
+    return edges, weights, parents, heights

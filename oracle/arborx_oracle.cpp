@@ -2215,10 +2215,23 @@ struct DirectedEdge
 // edges2: (n - 1) x (source, target) in ORIGINAL indices; weights: n - 1.  k > 1: mutual reachability with core
 // distance = distance to the k-th nearest point, the point itself included (MinimumSpanningTree.hpp:70-88).
 // Returns the number of Boruvka iterations.
-ORC_API int orc_mst(float const *xyz, int n, int k, int *edges2, float *weights_out)
+// dendrogram_parents != nullptr: BoruvkaMode::HDBSCAN (MinimumSpanningTree.hpp:176-185,214-230,266-297): the rounds
+// also record which edge every component picked, the edges come out ordered by (chain, weight) and
+// dendrogram_parents [2 n - 1] / dendrogram_heights [n - 1] describe the dendrogram in that edge order.
+static int mstImpl(float const *xyz, int n, int k, int *edges2, float *weights_out, int *dendrogram_parents,
+                   float *dendrogram_heights)
 {
   if (n < 2)
     return 0;
+  bool const hdbscan = dendrogram_parents != nullptr;
+  constexpr int ROOT_CHAIN_VALUE = -2, FOLLOW_CHAIN_VALUE = -3; // BoruvkaHelpers.hpp:34-35
+  std::vector<int> edges_mapping, sided_parents;
+  if (hdbscan)
+  {
+    edges_mapping.assign(n, -1);
+    sided_parents.assign(n - 1, ROOT_CHAIN_VALUE);
+  }
+  int edges_start = 0, edges_end = 0;
   Tree t;
   t.kind = PRIM_POINT;
   t.n = n;
@@ -2402,7 +2415,46 @@ ORC_API int orc_mst(float const *xyz, int n, int k, int *edges2, float *weights_
       e_src[num_edges] = out_edges[i].source();
       e_dst[num_edges] = out_edges[i].target();
       weights_out[num_edges] = out_edges[i].weight;
+      if (hdbscan)
+        edges_mapping[i] = num_edges;
       ++num_edges;
+    }
+    if (hdbscan)
+    {
+      // the (weight, smaller position, larger position) order of WeightedEdge.hpp:30-50
+      auto edgeLess = [&](int a, int b) {
+        if (weights_out[a] != weights_out[b])
+          return weights_out[a] < weights_out[b];
+        int const amin = std::min(e_src[a], e_dst[a]), bmin = std::min(e_src[b], e_dst[b]);
+        if (amin != bmin)
+          return amin < bmin;
+        return std::max(e_src[a], e_dst[a]) < std::max(e_src[b], e_dst[b]);
+      };
+      // BidirectionalEdgesTag (BoruvkaHelpers.hpp:439-447): the smaller label of a mutual pair did not append
+      for (int i = 0; i < n; ++i)
+        if (labels[i] == i && nextComponent(i) == i)
+          edges_mapping[i] = edges_mapping[labels[out_edges[i].target()]];
+      if (iterations > 1)
+      {
+        // updateSidedParents (:490-525): the edges of the previous round hang below the edge their merged
+        // component picks now, on its source or target side, or follow its chain upwards
+        for (int e = edges_start; e < edges_end; ++e)
+        {
+          int const component = labels[e_src[e]];
+          int const alpha = edges_mapping[component];
+          if (edgeLess(e, alpha))
+            sided_parents[e] = 2 * alpha + (labels[e_src[alpha]] == component ? 1 : 0);
+          else
+            sided_parents[e] = FOLLOW_CHAIN_VALUE - alpha;
+        }
+      }
+      else
+      {
+        // assignVertexParents (:527-548): in the first round every vertex is a component
+        for (int e = 0; e < n; ++e)
+          dendrogram_parents[(int)t.perm[labels[out_edges[e].source()]] + (n - 1)] =
+              edges_mapping[labels[out_edges[e].source()]];
+      }
     }
     std::vector<int> new_labels(n);
     for (int i = 0; i < n; ++i)
@@ -2413,7 +2465,102 @@ ORC_API int orc_mst(float const *xyz, int n, int k, int *edges2, float *weights_
       new_labels[i] = next;
     }
     std::copy(new_labels.begin(), new_labels.end(), labels.begin());
+    edges_start = edges_end;
+    edges_end = num_edges;
   } while (n - num_edges > 1);
+  if (hdbscan)
+  {
+    // computeParentsAndReorderEdges (BoruvkaHelpers.hpp:550-733)
+    int const m = n - 1;
+    for (int e = edges_start; e < edges_end; ++e)
+      sided_parents[e] = ROOT_CHAIN_VALUE; // MinimumSpanningTree.hpp:271-275
+    auto edgeLess = [&](int a, int b) {
+      if (weights_out[a] != weights_out[b])
+        return weights_out[a] < weights_out[b];
+      int const amin = std::min(e_src[a], e_dst[a]), bmin = std::min(e_src[b], e_dst[b]);
+      if (amin != bmin)
+        return amin < bmin;
+      return std::max(e_src[a], e_dst[a]) < std::max(e_src[b], e_dst[b]);
+    };
+    std::vector<long long> keys(m);
+    for (int e = 0; e < m; ++e)
+    {
+      long long key = sided_parents[e];
+      if (key <= FOLLOW_CHAIN_VALUE)
+      {
+        int next = FOLLOW_CHAIN_VALUE - (int)key;
+        while (true)
+        {
+          key = sided_parents[next];
+          if (key <= FOLLOW_CHAIN_VALUE)
+            next = FOLLOW_CHAIN_VALUE - (int)key;
+          else if (key >= 0)
+          {
+            next = (int)(key / 2);
+            if (edgeLess(e, next))
+              break;
+          }
+          else if (key == ROOT_CHAIN_VALUE)
+            break;
+        }
+      }
+      if (key == ROOT_CHAIN_VALUE)
+        key = INT_MAX;
+      int wbits;
+      std::memcpy(&wbits, &weights_out[e], sizeof(int));
+      keys[e] = (key << 32) + wbits;
+    }
+    std::vector<unsigned> permute(m);
+    for (int e = 0; e < m; ++e)
+      permute[e] = e;
+    std::stable_sort(permute.begin(), permute.end(), [&](unsigned a, unsigned b) { return keys[a] < keys[b]; });
+    {
+      std::vector<long long> sorted(m);
+      for (int e = 0; e < m; ++e)
+        sorted[e] = keys[permute[e]];
+      keys.swap(sorted);
+    }
+    // the smallest edge of a chain goes first even among equal weights (:625-660)
+    for (int i = 0; i + 1 < m; ++i)
+      if (i == 0 || (keys[i - 1] >> 32) != (keys[i] >> 32))
+      {
+        int mm = i;
+        for (int kk = i + 1; kk < m && keys[kk] == keys[i]; ++kk)
+          if (edgeLess((int)permute[kk], (int)permute[mm]))
+            mm = kk;
+        if (mm != i)
+          std::swap(permute[i], permute[mm]);
+      }
+    std::vector<int> rev(m);
+    for (int i = 0; i < m; ++i)
+      rev[permute[i]] = i;
+    for (int i = m; i < 2 * n - 1; ++i)
+      dendrogram_parents[i] = rev[dendrogram_parents[i]];
+    for (int i = 0; i < m; ++i)
+    {
+      if (i == m - 1)
+        dendrogram_parents[i] = -1;
+      else if ((keys[i] >> 32) == (keys[i + 1] >> 32))
+        dendrogram_parents[i] = i + 1;
+      else
+        dendrogram_parents[i] = rev[(int)((keys[i] >> 32) / 2)];
+    }
+    std::vector<int> s2(m), d2(m);
+    std::vector<float> w2(m);
+    for (int i = 0; i < m; ++i)
+    {
+      s2[i] = e_src[permute[i]];
+      d2[i] = e_dst[permute[i]];
+      w2[i] = weights_out[permute[i]];
+    }
+    e_src.swap(s2);
+    e_dst.swap(d2);
+    for (int i = 0; i < m; ++i)
+    {
+      weights_out[i] = w2[i];
+      dendrogram_heights[i] = w2[i];
+    }
+  }
   // finalizeEdges (BoruvkaHelpers.hpp:472-488)
   for (int e = 0; e < n - 1; ++e)
   {
@@ -2421,6 +2568,20 @@ ORC_API int orc_mst(float const *xyz, int n, int k, int *edges2, float *weights_
     edges2[2 * e + 1] = (int)t.perm[e_dst[e]];
   }
   return iterations;
+}
+
+ORC_API int orc_mst(float const *xyz, int n, int k, int *edges2, float *weights_out)
+{
+  return mstImpl(xyz, n, k, edges2, weights_out, nullptr, nullptr);
+}
+
+// MinimumSpanningTree<MemorySpace, BoruvkaMode::HDBSCAN>: edges in (chain, weight) order + the dendrogram over them
+ORC_API int orc_mst_hdbscan(float const *xyz, int n, int k, int *edges2, float *weights_out, int *parents,
+                            float *heights)
+{
+  if (n == 1 && parents)
+    parents[0] = -1;
+  return mstImpl(xyz, n, k, edges2, weights_out, parents, heights);
 }
 
 // Dendrogram of weighted edges (Dendrogram.hpp:47-76): edges sorted by weight, then the sequential union-find of

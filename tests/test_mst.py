@@ -58,6 +58,57 @@ def kruskal_total(pts, k):
     return np.sort(np.array(ws, np.float32))
 
 
+def reorder_to_weight_order(weights, parents):
+    """tstDendrogram.cpp:141-200: renumber a dendrogram whose edges are in the hybrid algorithm's order into the
+    ascending-weight order the UNION_FIND dendrogram uses (weights must be distinct for the two to be comparable)."""
+    m = len(weights)
+    order = np.argsort(weights, kind="stable")
+    rev = np.empty(m, np.int64)
+    rev[order] = np.arange(m)
+    out = np.empty_like(parents)
+    pe = parents[:m]
+    out[:m][rev] = np.where(pe >= 0, rev[np.maximum(pe, 0)], -1)
+    out[m:] = rev[parents[m:]]
+    return out, weights[order]
+
+
+def check_dendrogram(edges, weights, parents, heights):
+    """A dendrogram of a spanning tree, ties or not: one root, every edge node has exactly two children, heights never
+    decrease towards the root, heights are the edge weights, and the two end points of every tree edge meet at the
+    height of that edge (single linkage).  With distinct weights they meet at the edge itself; among edges of EQUAL
+    weight in one chain the hybrid algorithm leaves the order open (BoruvkaHelpers.hpp:603-622), so only the height
+    is required there."""
+    m = len(weights)
+    n = m + 1
+    assert parents.shape == (2 * m + 1,) and np.array_equal(heights, weights)
+    assert int((parents[:m] == -1).sum()) == 1 and parents[m:].min() >= 0 and parents.max() < m
+    children = np.bincount(parents[parents >= 0], minlength=m)
+    assert np.array_equal(children, np.full(m, 2))
+    pe = parents[:m]
+    has = pe >= 0
+    assert (weights[pe[has]] >= weights[has]).all()
+    # depth of every node, then the LCA of each edge's end points by walking up
+    depth = np.full(2 * m + 1, -1, np.int64)
+    root = int(np.nonzero(pe == -1)[0][0])
+    depth[root] = 0
+    order = np.argsort(-weights, kind="stable")
+    for _ in range(4 * m + 8):
+        todo = np.nonzero(depth < 0)[0]
+        if len(todo) == 0:
+            break
+        ready = todo[depth[parents[todo]] >= 0]
+        depth[ready] = depth[parents[ready]] + 1
+    assert (depth >= 0).all()
+    for e in range(0, m, max(1, m // 2000)):
+        a, b = int(edges[e, 0]) + m, int(edges[e, 1]) + m
+        while a != b:
+            if depth[a] >= depth[b]:
+                a = int(parents[a])
+            else:
+                b = int(parents[b])
+        assert weights[a] == weights[e], (e, a)
+
+
 LINE = np.array([[0, 0, 0], [1, 0, 0], [2, 0, 0], [3, 0, 0], [4, 0, 0]], np.float32)
 # tstMinimumSpanningTree.cpp:98-124
 LINE_REF = {
@@ -162,6 +213,33 @@ def test_oracle_degenerate():
     assert (w == 0).sum() == 80
 
 
+@pytest.mark.parametrize("n,k", [(2, 1), (7, 2), (50, 1), (3000, 1), (3000, 5), (20000, 3)])
+def test_oracle_hybrid_dendrogram(n, k):
+    """BoruvkaMode::HDBSCAN in the oracle: same tree as MST mode, a valid dendrogram, and for distinct weights exactly
+    the UNION_FIND dendrogram after renumbering (the reference's own check, tstDendrogram.cpp:115-200)."""
+    rng = np.random.default_rng(100 + n + k)
+    pts = (rng.random((n, 3), dtype=np.float32) * 100).astype(np.float32)
+    e, w, p, h = oracle.mst_hdbscan(pts, k)
+    e0, w0 = oracle.mst(pts, k)
+    assert undirected(e, w) == undirected(e0, w0)
+    check_dendrogram(e, w, p, h)
+    if len(np.unique(w)) == len(w):
+        p2, h2 = reorder_to_weight_order(w, p)
+        pu, hu = oracle.dendrogram(e, w)
+        assert np.array_equal(p2, pu) and np.array_equal(h2, hu)
+
+
+def test_oracle_hybrid_dendrogram_ties():
+    lattice = np.stack(np.meshgrid(*[np.arange(9, dtype=np.float32)] * 3, indexing="ij"), -1).reshape(-1, 3)
+    for k in (1, 4):
+        e, w, p, h = oracle.mst_hdbscan(lattice, k)
+        check_dendrogram(e, w, p, h)
+    e, w, p, h = oracle.mst_hdbscan(LINE, 3)
+    check_dendrogram(e, w, p, h)
+    e, w, p, h = oracle.mst_hdbscan(np.zeros((1, 3), np.float32), 2)
+    assert p.tolist() == [-1]
+
+
 # ------------------------------------------------------------------ CUDA path ----
 def _gpu():
     import torch
@@ -236,7 +314,7 @@ def test_cuda_dendrogram_and_hdbscan():
     rng = np.random.default_rng(11)
     pts = (rng.random((3000, 3), dtype=np.float32) * 100).astype(np.float32)
     for k in (1, 5):
-        d = abx.hdbscan(space, torch.from_numpy(pts).cuda(), k)
+        d = abx.hdbscan(space, torch.from_numpy(pts).cuda(), k, abx.DENDROGRAM_UNION_FIND)
         space.fence()
         e, w = oracle.mst(pts, k)
         if len(np.unique(w)) != len(w):
@@ -245,9 +323,51 @@ def test_cuda_dendrogram_and_hdbscan():
         assert np.array_equal(d._parents.cpu().numpy(), p)
         assert np.array_equal(d._parent_heights.cpu().numpy(), h)
     # single vertex
-    d = abx.hdbscan(space, torch.zeros((1, 3), device="cuda"), 2)
+    for impl in (abx.DENDROGRAM_BORUVKA, abx.DENDROGRAM_UNION_FIND):
+        d = abx.hdbscan(space, torch.zeros((1, 3), device="cuda"), 2, impl)
+        space.fence()
+        assert d._parents.cpu().tolist() == [-1]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,k,kind", [(2, 1, "random"), (7, 2, "random"), (3000, 1, "random"), (3000, 5, "random"),
+                                      (729, 1, "lattice"), (729, 4, "lattice"), (3000, 1, "duplicates"),
+                                      (200_000, 1, "random"), (200_000, 5, "clustered")])
+def test_cuda_hybrid_dendrogram(n, k, kind):
+    """MinimumSpanningTree in HDBSCAN mode on the device (no host pass): the same tree, a valid dendrogram, and for
+    distinct weights exactly the UNION_FIND dendrogram (and the oracle's hybrid dendrogram) after renumbering."""
+    torch, abx, space = _gpu()
+    rng = np.random.default_rng(n * 17 + k)
+    if kind == "lattice":
+        m = round(n ** (1 / 3))
+        pts = np.stack(np.meshgrid(*[np.arange(m, dtype=np.float32)] * 3, indexing="ij"), -1).reshape(-1, 3)
+    elif kind == "duplicates":
+        pts = np.repeat(rng.random((n // 3, 3), dtype=np.float32), 3, axis=0)
+    elif kind == "clustered":
+        from tests import clouds
+        pts = clouds.gan_tao(3, n)
+    else:
+        pts = rng.random((n, 3), dtype=np.float32) * 100
+    pts = np.ascontiguousarray(pts, np.float32)
+    mst = abx.MinimumSpanningTree(space, torch.from_numpy(pts).cuda(), k, mode="hdbscan")
     space.fence()
-    assert d._parents.cpu().tolist() == [-1]
+    e, w = mst.edges.cpu().numpy(), mst.weights.cpu().numpy()
+    p, h = mst.dendrogram_parents.cpu().numpy(), mst.dendrogram_parent_heights.cpu().numpy()
+    e0, w0 = oracle.mst(pts, k)
+    assert undirected(e, w) == undirected(e0, w0)
+    check_dendrogram(e, w, p, h)
+    if len(np.unique(w)) == len(w):
+        p2, h2 = reorder_to_weight_order(w, p)
+        pu, hu = oracle.dendrogram(e, w)
+        assert np.array_equal(p2, pu) and np.array_equal(h2, hu)
+        # (the chains themselves are numbered by the order in which components appended their edges, which is not
+        # deterministic on the device: only the renumbered form is comparable, also with the oracle's hybrid result)
+        eo, wo, po, ho = oracle.mst_hdbscan(pts, k)
+        p3, h3 = reorder_to_weight_order(wo, po)
+        assert np.array_equal(p2, p3) and np.array_equal(h2, h3)
+    d = abx.hdbscan(space, torch.from_numpy(pts).cuda(), k)  # BORUVKA is the default, as in the reference
+    space.fence()
+    assert np.array_equal(d._parents.cpu().numpy(), p) and np.array_equal(d._parent_heights.cpu().numpy(), h)
 
 
 @pytest.mark.gpu
