@@ -709,8 +709,8 @@ def wl_dbscan(args, abx, torch, dist, space, comm, rank, world, peak, traffic):
 
 
 def wl_mst(args, abx, torch, dist, space, comm, rank, world, peak, traffic):
-    """Euclidean minimum spanning tree (k = 1) and the mutual-reachability tree HDBSCAN uses
-    (k = 5) over 10M points: the bench's uniform cloud and the GanTao cluster cloud
+    """Euclidean minimum spanning tree (k = 1), the mutual-reachability tree HDBSCAN uses
+    (k = 5) and hdbscan itself over 10M points: the bench's uniform cloud and the GanTao cluster cloud
     (cluster/ArborX_MinimumSpanningTree.hpp; no published number in BASELINE.md).  Single tree: N = 1."""
     if world > 1:
         return None
@@ -732,6 +732,12 @@ def wl_mst(args, abx, torch, dist, space, comm, rank, world, peak, traffic):
                 "ms": ms, "Mpoints_s": n / ms / 1e3, "rounds": mst.iterations,
                 "total_weight": float(mst.weights.double().sum().item()),
                 "kernels_ms_per_call": {name: round(t / steps, 3) for name, c, t, mx in prof[:5]}}
+        # hdbscan(space, points, 5): the hybrid (dendrogram grown with the rounds, on the device) against MST + the
+        # union-find pass, whose loop runs on the host in the reference as well
+        abx.hdbscan(space, d, 5)
+        ms_h, _ = _time_gpu(torch, lambda: abx.hdbscan(space, d, 5), 0, steps)
+        ms_u, _ = _time_gpu(torch, lambda: abx.hdbscan(space, d, 5, abx.DENDROGRAM_UNION_FIND), 0, 1)
+        res["%s_hdbscan_minpts5" % cname] = {"boruvka_ms": ms_h, "Mpoints_s": n / ms_h / 1e3, "union_find_ms": ms_u}
         del d
     oracle = oracle_all_threads()
     ns = min(n, args.cpu_n)

@@ -367,7 +367,11 @@ def test_cuda_hybrid_dendrogram(n, k, kind):
         assert np.array_equal(p2, p3) and np.array_equal(h2, h3)
     d = abx.hdbscan(space, torch.from_numpy(pts).cuda(), k)  # BORUVKA is the default, as in the reference
     space.fence()
-    assert np.array_equal(d._parents.cpu().numpy(), p) and np.array_equal(d._parent_heights.cpu().numpy(), h)
+    dp, dh = d._parents.cpu().numpy(), d._parent_heights.cpu().numpy()
+    assert np.array_equal(np.sort(dh), np.sort(w))
+    if len(np.unique(w)) == len(w):  # two runs number their chains differently: compare the renumbered forms
+        p4, h4 = reorder_to_weight_order(dh, dp)
+        assert np.array_equal(p4, p2) and np.array_equal(h4, h2)
 
 
 @pytest.mark.gpu
