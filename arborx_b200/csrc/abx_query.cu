@@ -411,7 +411,10 @@ __global__ void __launch_bounds__(kThreads, (K > 0 && K <= 16) ? ABX_NEAREST_MIN
     bool const l_small = kNearestBucket == 1 ? refIsLeaf(lref) : (l_hi - rl < kNearestBucket);
     bool const r_small = kNearestBucket == 1 ? refIsLeaf(rref) : (rr - r_lo < kNearestBucket);
     auto consume = [&](bool is_leaf, float d, int ref, int lo, int hi) {
-      if (!(d < radius2))
+      // Triangle leaves are offered with their own distance whatever their box says, as the reference does (its
+      // leaves have no box, TreeTraversal.hpp:232-262): the computed closest point can fall an ulp outside the
+      // triangle's box, so the box distance is not a safe pre-test for the last bit of the k-th distance.
+      if (!(TRI && is_leaf) && !(d < radius2))
         return;
       if (is_leaf)
       {
