@@ -417,6 +417,12 @@ __global__ void sidedParentsKernel(int first, int last, int const *__restrict__ 
   int2 const edge = edge_pos[e];
   int const component = lab_leaf[edge.x];
   int const alpha = edges_mapping[component];
+  if (alpha < 0)
+  {
+    // the component picked nothing this round (only with non-finite coordinates; the host reports the round)
+    sided_parents[e] = kRootChain;
+    return;
+  }
   int2 const alpha_edge = edge_pos[alpha];
   if (edgeLess(weights[e], edge, weights[alpha], alpha_edge))
     sided_parents[e] = 2 * alpha + (lab_leaf[alpha_edge.x] == component ? 1 : 0);
@@ -532,6 +538,7 @@ abx_status boruvka(cudaStream_t s, abx_bvh *t, float const *core_pos, int2 *edge
   if (hd)
   {
     ABX_TRY(edges_mapping.alloc((size_t)n, s));
+    ABX_CUDA_TRY(cudaMemsetAsync(edges_mapping.ptr, 0xff, sizeof(int) * (size_t)n, s)); // -1: no edge picked yet
     ABX_TRY(sided_parents.alloc((size_t)n, s));
     ABX_TRY(round_weights.alloc((size_t)n, s));
     weights = round_weights.ptr; // append order here, reordered into weights_out at the end
