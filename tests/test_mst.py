@@ -240,6 +240,26 @@ def test_oracle_hybrid_dendrogram_ties():
     assert p.tolist() == [-1]
 
 
+def test_oracle_fuzz_small_clouds():
+    """Random small clouds -- uniform, a 4^3 integer lattice with repeated points, duplicated points -- and k = 1...7:
+    the oracle's tree weighs what an all-pairs Kruskal weighs, and its hybrid dendrogram is a valid one."""
+    rng = np.random.default_rng(2024)
+    for trial in range(45):
+        n, k = int(rng.integers(2, 300)), int(rng.integers(1, 8))
+        if trial % 3 == 0:
+            pts = rng.random((n, 3), dtype=np.float32)
+        elif trial % 3 == 1:
+            pts = rng.integers(0, 4, (n, 3)).astype(np.float32)
+        else:
+            pts = np.repeat(rng.random((max(n // 2, 1), 3), dtype=np.float32), 2, axis=0)
+        e, w = oracle.mst(pts, k)
+        check_spanning(len(pts), e)
+        assert np.array_equal(np.sort(w), kruskal_total(pts, k)), (trial, n, k)
+        e2, w2, p2, h2 = oracle.mst_hdbscan(pts, k)
+        assert np.array_equal(np.sort(w2), np.sort(w))
+        check_dendrogram(e2, w2, p2, h2)
+
+
 # ------------------------------------------------------------------ CUDA path ----
 def _gpu():
     import torch
