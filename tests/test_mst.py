@@ -240,6 +240,23 @@ def test_oracle_hybrid_dendrogram_ties():
     assert p.tolist() == [-1]
 
 
+# tstDetailsMutualReachabilityDistance.cpp:97-128: core distances (distance to the k-th nearest point, the point itself
+# included) of the two line clouds
+CORE_LINE = {1: [0, 0, 0, 0, 0], 2: [1, 1, 1, 1, 1], 3: [2, 1, 1, 1, 2], 4: [3, 2, 2, 2, 3], 5: [4, 3, 2, 3, 4]}
+CORE_UNEVEN = {2: [1, 1, 1, 1, 3, 4], 3: [2, 1, 1, 2, 4, 7], 4: [3, 2, 2, 3, 4, 8], 5: [6, 5, 4, 3, 5, 9],
+               6: [10, 9, 8, 7, 6, 10]}
+
+
+def test_oracle_core_distances_golden():
+    for pts, table in ((LINE, CORE_LINE), (UNEVEN, CORE_UNEVEN)):
+        tree = oracle.Tree(pts)
+        for k, ref in table.items():
+            off, idx, d = tree.nearest_crs(pts, k)
+            assert np.array_equal(np.diff(off), np.full(len(pts), k))
+            assert d.reshape(len(pts), k)[:, -1].tolist() == [float(x) for x in ref]
+            assert core_distances(pts, k).tolist() == [float(x) for x in ref]
+
+
 def test_oracle_fuzz_small_clouds():
     """Random small clouds -- uniform, a 4^3 integer lattice with repeated points, duplicated points -- and k = 1...7:
     the oracle's tree weighs what an all-pairs Kruskal weighs, and its hybrid dendrogram is a valid one."""
